@@ -1,0 +1,1182 @@
+// ORACLE (test infrastructure only) -- CPU restatement of Btrc's wavefront path tracer ("wfpt").
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load
+// this library; the product (btrc_b200/csrc) never links, includes or calls it.
+//
+// Parity pins: closest-hit is pinned against the reference's own vendored lib/bvh (oracle/_ref,
+// built from /root/reference/lib/bvh by oracle/Makefile) and against lib/bvh's golden image
+// (tests/golden/cornell_box_reference.png).  Everything else on the path (generate / shade /
+// shadow / film) is *parity unpinned by the reference* (Btrc ships no tests or fixtures for it,
+// and its device code cannot be built here: it needs LLVM 11 + OptiX 7); this file restates the
+// reference source line by line, each function citing the file:line it follows (paths relative to
+// /root/reference/src unless they start with lib/).
+//
+// Paths are independent (each carries its own PCG stream), so the oracle walks
+// one path at a time instead of in waves; per-path arithmetic and RNG draw order are those of
+// the wavefront kernels.  All arithmetic is IEEE fp32, compiled with -ffp-contract=off.
+#include "orc_math.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+#include <vector>
+#include <string>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace orc;
+
+// ------------------------------------------------------------------------------------------
+// RNG: cstd::PCG (lib/cuj/cuj/src/cstd/random.cpp:83-161), murmur64A (utils/hash.h:12-99),
+// IndependentSampler (builtin/sampler/independent.cpp:6-25)
+// ------------------------------------------------------------------------------------------
+namespace {
+
+constexpr uint64_t PCG_DEFAULT_STATE = 0x853c49e6748fea9bULL;
+constexpr uint64_t PCG_MULT = 0x5851f42d4c957f2dULL;
+
+struct PCG {
+    uint64_t state = 0, inc = 0;
+    uint32_t next() {  // random.cpp:153-160
+        uint64_t old = state;
+        state = old * PCG_MULT + inc;
+        uint32_t xs = uint32_t(((old >> 18u) ^ old) >> 27u);
+        uint32_t rot = uint32_t(old >> 59u);
+        return (xs >> rot) | (xs << ((~rot + 1u) & 31));
+    }
+    void seed(uint64_t s) {  // random.cpp:113-120
+        state = 0;
+        inc = (s << 1u) | 1u;
+        next();
+        state = state + PCG_DEFAULT_STATE;
+        next();
+    }
+    void advance(int64_t idelta) {  // random.cpp:122-141
+        uint64_t cur_mult = PCG_MULT, cur_plus = inc, acc_mult = 1, acc_plus = 0;
+        uint64_t delta = uint64_t(idelta);
+        while (delta > 0) {
+            if (delta & 1) {
+                acc_mult = acc_mult * cur_mult;
+                acc_plus = acc_plus * cur_mult + cur_plus;
+            }
+            cur_plus = (cur_mult + 1) * cur_plus;
+            cur_mult = cur_mult * cur_mult;
+            delta = delta / 2;
+        }
+        state = acc_mult * state + acc_plus;
+    }
+    float uniform_float() {  // random.cpp:143-146
+        return std::fmin(float(next()) * 0x1p-32f, 0x1.fffffep-1f);
+    }
+};
+
+uint64_t murmur_hash64A(const uint8_t *key, uint64_t len, uint64_t seed) {  // hash.h:12-70
+    const uint64_t m = 0xc6a4a7935bd1e995ull;
+    const int r = 47;
+    uint64_t h = seed ^ (len * m);
+    const uint8_t *end = key + 8 * (len / 8);
+    while (key != end) {
+        uint64_t k;
+        std::memcpy(&k, key, 8);
+        key += 8;
+        k *= m; k ^= k >> r; k *= m;
+        h ^= k; h *= m;
+    }
+    switch (len & 7) {
+    case 7: h ^= uint64_t(key[6]) << 48; [[fallthrough]];
+    case 6: h ^= uint64_t(key[5]) << 40; [[fallthrough]];
+    case 5: h ^= uint64_t(key[4]) << 32; [[fallthrough]];
+    case 4: h ^= uint64_t(key[3]) << 24; [[fallthrough]];
+    case 3: h ^= uint64_t(key[2]) << 16; [[fallthrough]];
+    case 2: h ^= uint64_t(key[1]) << 8; [[fallthrough]];
+    case 1: h ^= uint64_t(key[0]); h *= m;
+    }
+    h ^= h >> r; h *= m; h ^= h >> r;
+    return h;
+}
+
+uint64_t hash_pixel(uint32_t px, uint32_t py) {  // hash.h:88-96 with (u32,u32) => 8 bytes
+    uint8_t buf[8];
+    std::memcpy(buf, &px, 4);
+    std::memcpy(buf + 4, &py, 4);
+    return murmur_hash64A(buf, 8, 0);
+}
+
+struct Sampler {  // independent.cpp:11-25, core/sampler.h:22-28
+    PCG rng;
+    void init(uint32_t px, uint32_t py, int sample_index) {
+        rng.seed(hash_pixel(px, py));
+        rng.advance(int64_t(sample_index) * 65536);
+    }
+    float get1d() { return rng.uniform_float(); }
+    V3 get3d() { float a = get1d(); float b = get1d(); float c = get1d(); return {a, b, c}; }
+};
+
+// ------------------------------------------------------------------------------------------
+// Alias table (utils/math/alias.cpp:13-71, utils/cmath/calias.cpp:10-23)
+// ------------------------------------------------------------------------------------------
+struct AliasUnit { float accept_prob; uint32_t another_idx; };
+
+struct AliasTable {
+    std::vector<AliasUnit> units;
+    void initialize(const std::vector<float> &probs) {
+        float sum = 0.0f;
+        for (float p : probs) sum = sum + p;  // std::reduce(.., 0.0f, plus) -- sequential in libstdc++
+        const float ratio = probs.size() / sum;
+        std::vector<uint32_t> overs, unders;
+        units.resize(probs.size());
+        for (uint32_t i = 0; i < (uint32_t)units.size(); ++i) {
+            const float p = probs[i] * ratio;
+            units[i].accept_prob = p;
+            units[i].another_idx = i;
+            if (p > 1) overs.push_back(i);
+            else if (p < 1) unders.push_back(i);
+        }
+        while (!overs.empty() && !unders.empty()) {
+            const uint32_t over = overs.back(), under = unders.back();
+            overs.pop_back(); unders.pop_back();
+            units[over].accept_prob -= 1 - units[under].accept_prob;
+            units[under].another_idx = over;
+            if (units[over].accept_prob > 1) overs.push_back(over);
+            else if (units[over].accept_prob < 1) unders.push_back(over);
+        }
+        for (auto i : overs) units[i].accept_prob = 1;
+        for (auto i : unders) units[i].accept_prob = 1;
+    }
+    uint32_t sample(float u) const {  // calias.cpp:14-20
+        const uint32_t n = (uint32_t)units.size();
+        float nu = float(n) * u;
+        uint32_t i = std::min(uint32_t(nu), n - 1);
+        float s = nu - float(i);
+        return s <= units[i].accept_prob ? i : units[i].another_idx;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Sampling warps (utils/cmath/cdistribution.cpp:5-85)
+// ------------------------------------------------------------------------------------------
+V3 sample_hemisphere_zweighted(float u1, float u2) {  // cdistribution.cpp:31-54
+    float sx = 0, sy = 0;
+    u1 = 2.0f * u1 - 1.0f;
+    u2 = 2.0f * u2 - 1.0f;
+    if (u1 != 0.0f || u2 != 0.0f) {
+        float theta, r;
+        if (std::fabs(u1) > std::fabs(u2)) {
+            r = u1;
+            theta = 0.25f * PI * (u2 / u1);
+        } else {
+            r = u2;
+            theta = 0.5f * PI - 0.25f * PI * (u1 / u2);
+        }
+        sx = r * std::cos(theta);
+        sy = r * std::sin(theta);
+    }
+    float z = std::sqrt(std::fmax(0.0f, 1.0f - (sx * sx + sy * sy)));
+    return {sx, sy, z};
+}
+float pdf_sample_hemisphere_zweighted(V3 v) { return v.z >= 0 ? v.z / PI : 0.0f; }  // :66-69
+V2 sample_triangle_uniform(float u1, float u2) {  // :71-75
+    float t = std::sqrt(u1);
+    return {1.0f - t, t * u2};
+}
+
+// ------------------------------------------------------------------------------------------
+// intersection_offset (utils/intersection.cpp:5-36)
+// ------------------------------------------------------------------------------------------
+V3 intersection_offset(V3 pos, V3 nor) {
+    constexpr float ORIGIN = 1.0f / 32.0f;
+    constexpr float FLOAT_SCALE = 1.0f / 65536.0f;
+    constexpr float INT_SCALE = 256.0f;
+    int32_t of_i_x = int32_t(2 * INT_SCALE * nor.x);
+    int32_t of_i_y = int32_t(2 * INT_SCALE * nor.y);
+    int32_t of_i_z = int32_t(2 * INT_SCALE * nor.z);
+    float p_i_x = i2f(f2i(pos.x) + (pos.x < 0 ? -of_i_x : of_i_x));
+    float p_i_y = i2f(f2i(pos.y) + (pos.y < 0 ? -of_i_y : of_i_y));
+    float p_i_z = i2f(f2i(pos.z) + (pos.z < 0 ? -of_i_z : of_i_z));
+    float r_x = std::fabs(pos.x) < ORIGIN ? pos.x + FLOAT_SCALE * nor.x : p_i_x;
+    float r_y = std::fabs(pos.y) < ORIGIN ? pos.y + FLOAT_SCALE * nor.y : p_i_y;
+    float r_z = std::fabs(pos.z) < ORIGIN ? pos.z + FLOAT_SCALE * nor.z : p_i_z;
+    return {r_x, r_y, r_z};
+}
+V3 intersection_offset(V3 pos, V3 nor, V3 next_dir) {  // intersection.cpp:30-34
+    return intersection_offset(pos, dot(nor, next_dir) > 0 ? nor : -nor);
+}
+
+// ------------------------------------------------------------------------------------------
+// Scene description
+// ------------------------------------------------------------------------------------------
+enum MaterialType { MAT_DIFFUSE = 0, MAT_BLACK = 1 };
+
+struct Texture2D {
+    int type = 0;  // 0 constant
+    V3 value{0, 0, 0};
+};
+
+struct Material {
+    int type = MAT_DIFFUSE;
+    int color_tex = -1;
+    int normal_tex = -1;
+    bool shadow_terminator = true;
+};
+
+struct Mesh {
+    int ntri = 0;
+    std::vector<V3> pos;  // 3 per tri (local space)
+    // per-triangle shading tables (builtin/geometry/triangle_mesh.cpp:40-67), 6 x float4
+    std::vector<float> gx_ua, gy_uba, gz_uca, sn_va, sn_vba, sn_vca;  // 4 floats per tri each
+    // light sampling tables (triangle_mesh.cpp:108-164)
+    std::vector<V3> a_ba_ca;  // 3 per tri
+    AliasTable area_alias;
+    float total_area = 0;
+    V3 bb_lo{MAX_FLOAT, MAX_FLOAT, MAX_FLOAT}, bb_hi{-MAX_FLOAT, -MAX_FLOAT, -MAX_FLOAT};
+};
+
+struct Instance {
+    int mesh = 0, material = 0, light_id = -1;
+    Xf xf;
+    uint32_t inner_medium = 0, outer_medium = 0;
+    V3 intensity{0, 0, 0};
+    float light_scale = 1;
+    int tri_offset = 0;  // offset into flattened world triangle list
+};
+
+struct Tri {  // lib/bvh/include/bvh/triangle.hpp:27-34 (p0, e1 = p0 - p1, e2 = p2 - p0, n = cross(e1, e2))
+    V3 p0, e1, e2, n;
+    V3 p1, p2;  // world-space vertices as transformed (kept so tests can hand them to oracle/_ref)
+    uint32_t inst, prim;
+};
+
+struct BNode { V3 lo, hi; int left, right, first, count; };
+
+struct Hit { bool hit = false; float t = 0, u = 0, v = 0; uint32_t inst = 0, prim = 0; };
+
+struct Stats {
+    uint64_t n_gen = 0, n_closest = 0, n_hit = 0, n_next = 0, n_shadow = 0, n_shadow_miss = 0, n_splat = 0;
+};
+
+}  // namespace
+
+struct orc_scene {
+    std::vector<Texture2D> textures;
+    std::vector<Material> materials;
+    std::vector<Mesh> meshes;
+    std::vector<Instance> instances;
+    std::vector<int> lights;  // instance index per light id
+    // camera (builtin/camera/pinhole.cpp:55-77)
+    V3 eye, dst, up; float fov_y_deg = 60, w_over_h = 1;
+    V3 cam_eye, cam_lbc, cam_fx, cam_fy;
+    int width = 64, height = 64;
+    // renderer params (builtin/renderer/wavefront.h:13-27)
+    int spp = 1, min_depth = 5, max_depth = 10; float rr_threshold = 0.1f, rr_cont_prob = 0.5f;
+    bool tile = false, want_albedo = false, want_normal = false;
+    int filter_type = 0; float filter_radius = 1.3f, filter_alpha = 1.6f;
+    AliasTable gauss_alias;
+    // accel
+    std::vector<Tri> tris;
+    std::vector<BNode> nodes;
+    std::vector<int> tri_order;
+    V3 bb_lo, bb_hi; float world_diagonal = 0;
+    uint32_t vol_prim_medium_id = 0;
+    bool committed = false;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// Mesh tables: utils/triangle_mesh_loader.cpp:61-123, utils/math/triangle.h:8-22,
+// utils/math/frame.cpp:45-57, builtin/geometry/triangle_mesh.cpp:40-171
+// ------------------------------------------------------------------------------------------
+V3 host_frame_from_z_x(V3 z) {  // Frame::from_z(nor).x  (frame.cpp:45-57; NOT normalised)
+    V3 new_z = host_normalize(z), new_y;
+    if (1 - std::fabs(new_z.x) < 0.1f) new_y = cross(new_z, V3(0, 1, 0));
+    else new_y = cross(new_z, V3(1, 0, 0));
+    return cross(new_z, new_y);
+}
+
+V3 triangle_dpdu(V3 B_A, V3 C_A, V2 b_a, V2 c_a, V3 nor) {  // triangle.h:8-22
+    const float m00 = b_a.x, m01 = b_a.y, m10 = c_a.x, m11 = c_a.y;
+    const float det = m00 * m11 - m01 * m10;
+    if (det == 0.0f) return host_frame_from_z_x(nor);
+    const float inv_det = 1 / det;
+    return host_normalize(m11 * inv_det * B_A - m01 * inv_det * C_A);
+}
+
+void build_mesh(Mesh &m, int ntri, const float *pos, const float *nor, const uint8_t *has_nor, const float *uv) {
+    m.ntri = ntri;
+    m.pos.resize(3 * (size_t)ntri);
+    for (size_t i = 0; i < 3 * (size_t)ntri; ++i) m.pos[i] = V3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+    m.gx_ua.resize(4 * (size_t)ntri); m.gy_uba.resize(4 * (size_t)ntri); m.gz_uca.resize(4 * (size_t)ntri);
+    m.sn_va.resize(4 * (size_t)ntri); m.sn_vba.resize(4 * (size_t)ntri); m.sn_vca.resize(4 * (size_t)ntri);
+    m.a_ba_ca.resize(3 * (size_t)ntri);
+    std::vector<float> areas(ntri);
+    for (int i = 0; i < ntri; ++i) {
+        const V3 a = m.pos[3 * i], b = m.pos[3 * i + 1], c = m.pos[3 * i + 2];
+        const V3 geo_z = host_normalize(cross(b - a, c - a));  // loader.cpp:86
+        V3 sz[3]; V2 tc[3];
+        for (int k = 0; k < 3; ++k) {
+            const size_t j = 3 * (size_t)i + k;
+            if (!has_nor || !has_nor[j]) sz[k] = geo_z;
+            else {
+                sz[k] = V3(nor[3 * j], nor[3 * j + 1], nor[3 * j + 2]);
+                if (sz[k].x == 0.0f && sz[k].y == 0.0f && sz[k].z == 0.0f) sz[k] = geo_z;  // loader.cpp:100-102
+            }
+            tc[k] = uv ? V2{uv[2 * j], uv[2 * j + 1]} : V2{0, 0};
+        }
+        const V3 gx = triangle_dpdu(b - a, c - a, V2{tc[1].x - tc[0].x, tc[1].y - tc[0].y},
+                                    V2{tc[2].x - tc[0].x, tc[2].y - tc[0].y}, geo_z);
+        const V3 gz = geo_z;
+        const V3 gy = host_normalize(cross(gz, gx));  // triangle_mesh.cpp:52
+        auto put = [&](std::vector<float> &dst, V3 v, float w) {
+            dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = w;
+        };
+        put(m.gx_ua, gx, tc[0].x);
+        put(m.gy_uba, gy, tc[1].x - tc[0].x);
+        put(m.gz_uca, gz, tc[2].x - tc[0].x);
+        put(m.sn_va, sz[0], tc[0].y);
+        put(m.sn_vba, sz[1] - sz[0], tc[1].y - tc[0].y);
+        put(m.sn_vca, sz[2] - sz[0], tc[2].y - tc[0].y);
+        const V3 ba = b - a, ca = c - a;
+        areas[i] = 0.5f * length(cross(ba, ca));  // triangle.h:24-27
+        m.a_ba_ca[3 * i] = a; m.a_ba_ca[3 * i + 1] = ba; m.a_ba_ca[3 * i + 2] = ca;
+    }
+    m.area_alias.initialize(areas);
+    float total = 0.0f;
+    for (float a : areas) total += a;  // std::accumulate(.., 0.0f)
+    m.total_area = total;
+    for (auto &p : m.pos) {
+        m.bb_lo = V3(std::fmin(m.bb_lo.x, p.x), std::fmin(m.bb_lo.y, p.y), std::fmin(m.bb_lo.z, p.z));
+        m.bb_hi = V3(std::fmax(m.bb_hi.x, p.x), std::fmax(m.bb_hi.y, p.y), std::fmax(m.bb_hi.z, p.z));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Closest hit. Reference: OptiX (closed source) behind wavefront/trace.cpp:38-78; arithmetic oracle =
+// lib/bvh Moeller-Trumbore (lib/bvh/include/bvh/triangle.hpp:95-116), double-sided, tmin <= t <= tmax.
+// Geometry is flattened to world space: vertex = local_to_world.apply_to_point(v) (transform.cpp:66-72).
+// Tie rule (ours, deterministic): smallest t, then smallest (instance, primitive).
+// ------------------------------------------------------------------------------------------
+inline bool tri_intersect(const Tri &tr, V3 o, V3 d, float tmin, float tmax, float &t, float &u, float &v) {
+    V3 c = tr.p0 - o;
+    V3 r = cross(d, c);
+    float inv_det = 1.0f / dot(tr.n, d);
+    u = dot(r, tr.e2) * inv_det;
+    v = dot(r, tr.e1) * inv_det;
+    float w = 1.0f - u - v;
+    if (u >= 0 && v >= 0 && w >= 0) {
+        t = dot(tr.n, c) * inv_det;
+        if (t >= tmin && t <= tmax) return true;
+    }
+    return false;
+}
+
+inline bool better(float t, uint32_t inst, uint32_t prim, const Hit &h) {
+    if (!h.hit) return true;
+    if (t < h.t) return true;
+    if (t > h.t) return false;
+    if (inst != h.inst) return inst < h.inst;
+    return prim < h.prim;
+}
+
+Hit closest_hit_brute(const orc_scene &s, V3 o, V3 d, float tmax) {
+    Hit best;
+    for (const Tri &tr : s.tris) {
+        float t, u, v;
+        if (tri_intersect(tr, o, d, 0.0f, tmax, t, u, v) && better(t, tr.inst, tr.prim, best)) {
+            best.hit = true; best.t = t; best.u = u; best.v = v; best.inst = tr.inst; best.prim = tr.prim;
+        }
+    }
+    return best;
+}
+
+int build_node(orc_scene &s, std::vector<V3> &cent, std::vector<V3> &lo, std::vector<V3> &hi, int first, int count) {
+    BNode n;
+    n.lo = V3(MAX_FLOAT); n.hi = V3(-MAX_FLOAT);
+    V3 clo(MAX_FLOAT), chi(-MAX_FLOAT);
+    for (int i = first; i < first + count; ++i) {
+        int t = s.tri_order[i];
+        n.lo = V3(std::fmin(n.lo.x, lo[t].x), std::fmin(n.lo.y, lo[t].y), std::fmin(n.lo.z, lo[t].z));
+        n.hi = V3(std::fmax(n.hi.x, hi[t].x), std::fmax(n.hi.y, hi[t].y), std::fmax(n.hi.z, hi[t].z));
+        clo = V3(std::fmin(clo.x, cent[t].x), std::fmin(clo.y, cent[t].y), std::fmin(clo.z, cent[t].z));
+        chi = V3(std::fmax(chi.x, cent[t].x), std::fmax(chi.y, cent[t].y), std::fmax(chi.z, cent[t].z));
+    }
+    n.left = n.right = -1; n.first = first; n.count = count;
+    int idx = (int)s.nodes.size();
+    s.nodes.push_back(n);
+    if (count > 4) {
+        V3 ext = chi - clo;
+        int axis = ext.x > ext.y ? (ext.x > ext.z ? 0 : 2) : (ext.y > ext.z ? 1 : 2);
+        if (ext[axis] > 0) {
+            int mid = first + count / 2;
+            std::nth_element(s.tri_order.begin() + first, s.tri_order.begin() + mid, s.tri_order.begin() + first + count,
+                             [&](int a, int b) { return cent[a][axis] < cent[b][axis]; });
+            int l = build_node(s, cent, lo, hi, first, mid - first);
+            int r = build_node(s, cent, lo, hi, mid, first + count - mid);
+            s.nodes[idx].left = l; s.nodes[idx].right = r; s.nodes[idx].count = 0;
+        }
+    }
+    return idx;
+}
+
+void build_accel(orc_scene &s) {
+    s.tris.clear(); s.nodes.clear();
+    for (size_t ii = 0; ii < s.instances.size(); ++ii) {
+        Instance &inst = s.instances[ii];
+        const Mesh &m = s.meshes[inst.mesh];
+        inst.tri_offset = (int)s.tris.size();
+        for (int i = 0; i < m.ntri; ++i) {
+            V3 p0 = inst.xf.point(m.pos[3 * i]), p1 = inst.xf.point(m.pos[3 * i + 1]), p2 = inst.xf.point(m.pos[3 * i + 2]);
+            Tri t;
+            t.p0 = p0; t.e1 = p0 - p1; t.e2 = p2 - p0; t.n = cross(t.e1, t.e2); t.p1 = p1; t.p2 = p2;
+            t.inst = (uint32_t)ii; t.prim = (uint32_t)i;
+            s.tris.push_back(t);
+        }
+    }
+    const size_t n = s.tris.size();
+    std::vector<V3> cent(n), lo(n), hi(n);
+    for (size_t i = 0; i < n; ++i) {
+        const Tri &t = s.tris[i];
+        V3 p1 = t.p0 - t.e1, p2 = t.p0 + t.e2;
+        lo[i] = V3(std::fmin(t.p0.x, std::fmin(p1.x, p2.x)), std::fmin(t.p0.y, std::fmin(p1.y, p2.y)), std::fmin(t.p0.z, std::fmin(p1.z, p2.z)));
+        hi[i] = V3(std::fmax(t.p0.x, std::fmax(p1.x, p2.x)), std::fmax(t.p0.y, std::fmax(p1.y, p2.y)), std::fmax(t.p0.z, std::fmax(p1.z, p2.z)));
+        // generous conservative padding: the oracle must never cull a triangle the exact test accepts
+        V3 ext = hi[i] - lo[i];
+        float pad = 1e-4f * std::fmax(std::fmax(std::fabs(lo[i].x), std::fabs(hi[i].x)),
+                                      std::fmax(std::fmax(std::fabs(lo[i].y), std::fabs(hi[i].y)),
+                                                std::fmax(std::fabs(lo[i].z), std::fabs(hi[i].z)))) +
+                    1e-4f * std::fmax(ext.x, std::fmax(ext.y, ext.z)) + 1e-30f;
+        lo[i] = lo[i] - V3(pad); hi[i] = hi[i] + V3(pad);
+        cent[i] = (lo[i] + hi[i]) * 0.5f;
+    }
+    s.tri_order.resize(n);
+    std::iota(s.tri_order.begin(), s.tri_order.end(), 0);
+    if (n) build_node(s, cent, lo, hi, 0, (int)n);
+}
+
+inline bool box_hit(const BNode &n, V3 o, V3 inv, float tmax) {
+    float t0 = 0.0f, t1 = tmax;
+    for (int a = 0; a < 3; ++a) {
+        float lo = (n.lo[a] - o[a]) * inv[a], hi = (n.hi[a] - o[a]) * inv[a];
+        if (std::isnan(lo) || std::isnan(hi)) continue;  // 0 * inf: origin on slab plane, be conservative
+        if (lo > hi) std::swap(lo, hi);
+        hi *= 1.0000004f;  // robust (1 + 2*gamma3) widening
+        t0 = std::fmax(t0, lo); t1 = std::fmin(t1, hi);
+    }
+    return t0 <= t1;
+}
+
+template <bool ANY>
+Hit traverse(const orc_scene &s, V3 o, V3 d, float tmax) {
+    Hit best;
+    if (s.nodes.empty()) return best;
+    V3 inv(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int stack[128]; int sp = 0;
+    stack[sp++] = 0;
+    float cur_tmax = tmax;
+    while (sp) {
+        const BNode &n = s.nodes[stack[--sp]];
+        if (!box_hit(n, o, inv, cur_tmax)) continue;
+        if (n.left < 0) {
+            for (int i = n.first; i < n.first + n.count; ++i) {
+                const Tri &tr = s.tris[s.tri_order[i]];
+                float t, u, v;
+                if (tri_intersect(tr, o, d, 0.0f, tmax, t, u, v)) {
+                    if (ANY) { best.hit = true; return best; }
+                    if (better(t, tr.inst, tr.prim, best)) {
+                        best.hit = true; best.t = t; best.u = u; best.v = v; best.inst = tr.inst; best.prim = tr.prim;
+                        cur_tmax = t;
+                    }
+                }
+            }
+        } else {
+            stack[sp++] = n.left; stack[sp++] = n.right;
+        }
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------
+// Filters (builtin/film_filter/box.cpp:5-10, gaussian.cpp:27-66)
+// ------------------------------------------------------------------------------------------
+constexpr int GRID_SIZE = 256;
+void build_gaussian(orc_scene &s) {
+    const float radius = s.filter_radius, alpha = s.filter_alpha;
+    const float expv = std::exp(-alpha * radius * radius);
+    auto gaussian = [&](float d) { return std::max(0.0f, std::exp(-alpha * d * d) - expv); };
+    std::vector<float> table(GRID_SIZE * GRID_SIZE, 0.0f);
+    for (int y = 0; y < GRID_SIZE; ++y) {
+        const float yf = 2 * radius * (y + 0.5f) / GRID_SIZE - radius;
+        for (int x = 0; x < GRID_SIZE; ++x) {
+            const float xf = 2 * radius * (x + 0.5f) / GRID_SIZE - radius;
+            const float d2 = xf * xf + yf * yf;
+            if (d2 < radius * radius) table[y * GRID_SIZE + x] = gaussian(xf) * gaussian(yf);
+        }
+    }
+    s.gauss_alias.initialize(table);
+}
+
+V2 filter_sample(const orc_scene &s, Sampler &sampler) {
+    if (s.filter_type == 0) {
+        float x = sampler.get1d() - 0.5f;
+        float y = sampler.get1d() - 0.5f;
+        return {x, y};
+    }
+    const float radius = s.filter_radius;
+    uint32_t grid_index = s.gauss_alias.sample(sampler.get1d());
+    uint32_t grid_y = grid_index / GRID_SIZE, grid_x = grid_index % GRID_SIZE;
+    const float step = 2 * radius / GRID_SIZE;  // host-folded constant in the reference expression
+    float x_beg = -radius + step * float(grid_x);
+    float x_end = -radius + step * float(grid_x + 1);
+    float y_beg = -radius + step * float(grid_y);
+    float y_end = -radius + step * float(grid_y + 1);
+    float xf = lerp(x_beg, x_end, sampler.get1d());
+    float yf = lerp(y_beg, y_end, sampler.get1d());
+    return {xf, yf};
+}
+
+// ------------------------------------------------------------------------------------------
+// Path state, mirroring wavefront/soa.h:8-37
+// ------------------------------------------------------------------------------------------
+struct PathState {
+    V3 o, d; float t1; uint32_t medium_id;
+    uint32_t px, py;
+    V3 beta; int depth;
+    V3 L;
+    Sampler sampler;
+    V3 beta_le; float bsdf_pdf;
+};
+
+struct ShadowRay {
+    bool valid = false;
+    uint32_t px = 0, py = 0; V3 beta_li; V3 o, d; float t1 = 0; uint32_t medium_id = 0;
+};
+
+struct Splat { bool valid = false; V3 value; };
+
+void camera_commit(orc_scene &s) {  // pinhole.cpp:55-77
+    const V3 forward = host_normalize(s.dst - s.eye);
+    const V3 ex = host_normalize(cross(forward, s.up));
+    const V3 ey = host_normalize(cross(forward, ex));
+    const float y_len = 2 * std::tan(0.5f * s.fov_y_deg * PI / 180);
+    const float x_len = s.w_over_h * y_len;
+    s.cam_lbc = s.eye + forward - 0.5f * (x_len * ex + y_len * ey);
+    s.cam_fx = x_len * ex;
+    s.cam_fy = y_len * ey;
+    s.cam_eye = s.eye;
+}
+
+// wavefront/generate.cpp:39-86
+void generate_path(const orc_scene &s, int64_t accu_state_index, PathState &ps) {
+    const int W = s.width, H = s.height;
+    int pixel_index, sample_index;
+    if (!s.tile) {
+        pixel_index = int(accu_state_index % (W * H));
+        sample_index = int(accu_state_index / (W * H));
+    } else {
+        pixel_index = int(accu_state_index / s.spp);
+        sample_index = int(accu_state_index % s.spp);
+    }
+    int pixel_x = pixel_index % W, pixel_y = pixel_index / W;
+    ps.sampler.init((uint32_t)pixel_x, (uint32_t)pixel_y, sample_index);
+    V2 fs = filter_sample(s, ps.sampler);
+    float pixel_xf = float(pixel_x) + 0.5f + fs.x;
+    float pixel_yf = float(pixel_y) + 0.5f + fs.y;
+    float film_x = pixel_xf / float(W);
+    float film_y = pixel_yf / float(H);
+    float time_sample = ps.sampler.get1d();
+    (void)time_sample;
+    // pinhole.cpp:84-99
+    V3 x = film_x * s.cam_fx;
+    V3 y = film_y * s.cam_fy;
+    V3 dst = s.cam_lbc + x + y;
+    V3 dir = normalize(dst - s.cam_eye);
+    ps.px = (uint32_t)pixel_x; ps.py = (uint32_t)pixel_y;
+    ps.depth = 0; ps.beta = V3(1); ps.L = V3(0);
+    ps.o = s.cam_eye; ps.d = dir; ps.t1 = MAX_FLOAT; ps.medium_id = s.vol_prim_medium_id;
+    ps.beta_le = V3(1); ps.bsdf_pdf = -1;
+}
+
+// core/scene.cpp:9-64
+struct SurfacePoint { V3 position; Frame frame; V3 interp_z; V2 uv, tex_coord; };
+
+SurfacePoint get_hitinfo(const orc_scene &s, V3 o, V3 d, const Instance &inst, float t, uint32_t prim, V2 uv) {
+    const Mesh &m = s.meshes[inst.mesh];
+    SurfacePoint sp;
+    sp.position = o + t * d;
+    const float *gx = &m.gx_ua[4 * prim], *gy = &m.gy_uba[4 * prim], *gz = &m.gz_uca[4 * prim];
+    const float *sa = &m.sn_va[4 * prim], *sba = &m.sn_vba[4 * prim], *sca = &m.sn_vca[4 * prim];
+    Frame gf(V3(gx[0], gx[1], gx[2]), V3(gy[0], gy[1], gy[2]), V3(gz[0], gz[1], gz[2]));
+    gf.x = inst.xf.vector(gf.x);
+    gf.y = inst.xf.vector(gf.y);
+    gf.z = inst.xf.normal(gf.z);
+    gf.x = normalize(gf.x); gf.y = normalize(gf.y); gf.z = normalize(gf.z);
+    V3 interp = V3(sa[0], sa[1], sa[2]) + V3(sba[0], sba[1], sba[2]) * uv.x + V3(sca[0], sca[1], sca[2]) * uv.y;
+    interp = normalize(inst.xf.normal(interp));
+    float tu = gx[3] + gy[3] * uv.x + gz[3] * uv.y;
+    float tv = sa[3] + sba[3] * uv.x + sca[3] * uv.y;
+    sp.frame = gf; sp.interp_z = interp; sp.uv = uv; sp.tex_coord = V2{tu, tv};
+    return sp;
+}
+
+V3 eval_texture(const orc_scene &s, int tex, const SurfacePoint &) {
+    const Texture2D &t = s.textures[tex];
+    return t.value;
+}
+
+// ---- lights: builtin/light/mesh_light.cpp:17-76, geometry/triangle_mesh.cpp:188-228,
+//      core/light_sampler.cpp:41-63, wavefront/helper.cpp:10-65,174-207
+struct LiSample { bool success = false; V3 o, d; float t1 = 0, light_pdf = 0; V3 li; };
+
+LiSample sample_surface_light_li(const orc_scene &s, V3 ref_pos, V3 ref_nor, Sampler &sampler) {
+    LiSample r;
+    V3 sam = sampler.get3d();
+    float sel = sampler.get1d();
+    const int n = (int)s.lights.size();
+    if (n == 0) return r;
+    int idx = std::min(int(sel * n), n - 1);
+    float select_pdf = 1.0f / float(n);
+    const Instance &li = s.instances[s.lights[idx]];
+    const Mesh &m = s.meshes[li.mesh];
+    // TriangleMesh::sample_inline
+    uint32_t prim = m.area_alias.sample(sam.x);
+    V2 uv = sample_triangle_uniform(sam.y, sam.z);
+    V3 a = m.a_ba_ca[3 * prim], ba = m.a_ba_ca[3 * prim + 1], ca = m.a_ba_ca[3 * prim + 2];
+    V3 pos = a + ba * uv.x + ca * uv.y;
+    Frame fr(V3(m.gx_ua[4 * prim], m.gx_ua[4 * prim + 1], m.gx_ua[4 * prim + 2]),
+             V3(m.gy_uba[4 * prim], m.gy_uba[4 * prim + 1], m.gy_uba[4 * prim + 2]),
+             V3(m.gz_uca[4 * prim], m.gz_uca[4 * prim + 1], m.gz_uca[4 * prim + 2]));
+    float pdf_area = 1 / m.total_area;
+    // MeshLight::sample_li_inline
+    V3 spos = li.xf.point(pos);
+    V3 snor = normalize(li.xf.normal(fr.z));
+    V3 pos_to_ref = ref_pos - spos;
+    float dist2 = length_square(pos_to_ref);
+    const float inv_scale2 = 1 / (li.light_scale * li.light_scale);
+    float pdf_sa = inv_scale2 * pdf_area * dist2 / std::fabs(dot(snor, normalize(pos_to_ref)));
+    V3 rad = dot(pos_to_ref, snor) > 0 ? li.intensity : V3(0);
+    // helper.cpp:24-34
+    V3 diff = spos - ref_pos;
+    V3 shadow_dst = intersection_offset(spos, snor, -diff);
+    r.o = intersection_offset(ref_pos, ref_nor, diff);
+    r.d = shadow_dst - r.o;
+    r.t1 = 1;
+    r.li = rad;
+    r.light_pdf = select_pdf * pdf_sa;
+    r.success = true;
+    return r;
+}
+
+V3 handle_intersected_light(const orc_scene &s, V3 o, V3 d, const SurfacePoint &inct, V3 beta_le, float bsdf_pdf, int light_index) {
+    V3 result(0);
+    if (light_index >= 0) {
+        const int n = (int)s.lights.size();
+        float select_pdf = 1.0f / float(n);
+        const Instance &li = s.instances[s.lights[light_index]];
+        const Mesh &m = s.meshes[li.mesh];
+        V3 le = dot(inct.frame.z, -d) >= 0 ? li.intensity : V3(0);
+        if (bsdf_pdf < 0) result = beta_le * le / -bsdf_pdf;
+        else {
+            float light_dir_pdf;
+            V3 nor = inct.frame.z, pos = inct.position;
+            if (dot(nor, o - pos) <= 0) light_dir_pdf = 0;
+            else {
+                float pdf_area = 1 / m.total_area;
+                V3 spt_to_ref = o - pos;
+                float dist2 = length_square(spt_to_ref);
+                float dist3 = std::sqrt(dist2) * dist2;
+                const float inv_scale2 = 1 / (li.light_scale * li.light_scale);
+                light_dir_pdf = inv_scale2 * pdf_area * dist3 / std::fabs(dot(nor, spt_to_ref));
+            }
+            float light_pdf = select_pdf * light_dir_pdf;
+            result = beta_le * le / (bsdf_pdf + light_pdf);
+        }
+    }
+    return result;
+}
+
+// wavefront/helper.cpp:67-95
+bool simple_russian_roulette(const orc_scene &s, V3 &beta, int depth, Sampler &sampler) {
+    bool ret = false;
+    if (depth >= s.min_depth) {
+        if (depth >= s.max_depth) ret = true;
+        else {
+            float sam = sampler.get1d();
+            if (lum(beta) < s.rr_threshold) {
+                if (sam > s.rr_cont_prob) ret = true;
+                else beta = beta / s.rr_cont_prob;
+            }
+        }
+    }
+    return ret;
+}
+
+// ---- shader: material/utils/shader_frame.cpp:5-95, material/utils/aggregate.cpp:32-230,
+//      material/component/diffuse.cpp:5-60, material/diffuse.cpp:21-34
+struct ShaderFrame {
+    Frame geometry, shading;
+    bool is_black_fringes(V3 w) const { return geometry.in_positive_z_hemisphere(w) != shading.in_positive_z_hemisphere(w); }
+    float correct_shading_energy(V3 wi) const {
+        float down = std::fabs(dot(geometry.z, wi));
+        if (down > 1e-4f) return std::fabs(dot(shading.z, wi)) / down;
+        return 1;
+    }
+    ShaderFrame flip_for_black_fringes(V3 wo) const {
+        ShaderFrame f; f.geometry = geometry;
+        f.shading = is_black_fringes(wo) ? geometry : shading;
+        return f;
+    }
+};
+
+struct BsdfSample { V3 bsdf{0, 0, 0}, dir{0, 0, 0}; float pdf = 0; bool is_delta = false; };
+
+struct Shader {
+    int type = MAT_DIFFUSE;
+    ShaderFrame frame;
+    bool shadow_terminator = true;
+    V3 albedo_value;  // diffuse
+
+    float shadow_terminator_term(V3 wi) const {  // aggregate.cpp:219-230
+        if (!shadow_terminator) return 1.0f;
+        float wgwi = dot(frame.geometry.z, wi);
+        float wswi = dot(frame.shading.z, wi);
+        float wgws = dot(frame.geometry.z, frame.shading.z);
+        float g = saturate(wgwi / (wswi * wgws));
+        return -g * g * g + g * g + g;
+    }
+    V3 albedo() const { return type == MAT_BLACK ? V3(0) : albedo_value; }
+    V3 normal() const { return frame.shading.z; }
+
+    BsdfSample sample(V3 wo, V3 sam) const {  // aggregate.cpp:47-119 with the single diffuse closure
+        BsdfSample result;
+        if (type == MAT_BLACK) return result;
+        ShaderFrame fr = frame.flip_for_black_fringes(wo);
+        V3 lwo = normalize(fr.shading.global_to_local(wo));
+        float comp_selector = 1.0f * sam.x;          // sum_weight_(=1) * sam[0]
+        float s0 = comp_selector / 1.0f;             // last component: selector / sample_weight
+        // DiffuseComponentImpl::sample_bidir (component/diffuse.cpp:10-30)
+        if (lwo.z <= 0) return result;
+        V3 lwi = sample_hemisphere_zweighted(s0, sam.y);
+        V3 bsdf = albedo_value / PI;
+        float cpdf = pdf_sample_hemisphere_zweighted(lwi);
+        if (cpdf <= 0) return result;
+        float pdf = 1.0f * cpdf;
+        result.dir = fr.shading.local_to_global(lwi);
+        if (frame.is_black_fringes(result.dir)) return BsdfSample();
+        result.bsdf = bsdf;
+        result.pdf = pdf / 1.0f;
+        float corr = fr.correct_shading_energy(result.dir);
+        float stt = shadow_terminator_term(result.dir);
+        result.bsdf = result.bsdf * corr * stt;
+        result.is_delta = false;
+        return result;
+    }
+    V3 eval(V3 wi, V3 wo) const {  // aggregate.cpp:185-197
+        if (type == MAT_BLACK) return V3(0);
+        ShaderFrame fr = frame.flip_for_black_fringes(wo);
+        V3 lwi = normalize(fr.shading.global_to_local(wi));
+        V3 lwo = normalize(fr.shading.global_to_local(wo));
+        V3 result(0);
+        if (!(lwi.z <= 0 || lwo.z <= 0)) result = result + albedo_value / PI;
+        float corr = fr.correct_shading_energy(wi);
+        float stt = shadow_terminator_term(wi);
+        return result * corr * stt;
+    }
+    float pdf(V3 wi, V3 wo) const {  // aggregate.cpp:199-209
+        if (type == MAT_BLACK) return 0;
+        ShaderFrame fr = frame.flip_for_black_fringes(wo);
+        V3 lwi = normalize(fr.shading.global_to_local(wi));
+        V3 lwo = normalize(fr.shading.global_to_local(wo));
+        float result = 0;
+        float c = (lwi.z <= 0 || lwo.z <= 0) ? 0.0f : pdf_sample_hemisphere_zweighted(lwi);
+        result = result + 1.0f * c;
+        return result / 1.0f;
+    }
+};
+
+Shader create_shader(const orc_scene &s, const Material &mat, const SurfacePoint &inct) {
+    Shader sh;
+    sh.type = mat.type;
+    sh.frame.geometry = inct.frame;
+    sh.frame.shading = inct.frame.rotate_to_new_z(inct.interp_z);
+    if (mat.normal_tex >= 0) {  // material/utils/normal_map.cpp:13-21
+        V3 c = eval_texture(s, mat.normal_tex, inct);
+        V3 local_nor = 2.0f * c - V3(1.0f);
+        V3 world_nor = sh.frame.shading.local_to_global(local_nor);
+        sh.frame.shading = sh.frame.shading.rotate_to_new_z(normalize(world_nor));
+    }
+    sh.shadow_terminator = mat.shadow_terminator;
+    if (mat.type == MAT_DIFFUSE) sh.albedo_value = eval_texture(s, mat.color_tex, inct);
+    return sh;
+}
+
+struct ShadeOut {
+    bool has_next = false; PathState next;
+    ShadowRay shadow;
+    Splat radiance;                      // terminal / Le-only splat
+    bool has_gbuffer = false; V3 albedo, normal;
+};
+
+// wavefront/shade.cpp:38-235 (no medium => is_scattered is always false)
+void shade(const orc_scene &s, const PathState &in, const Hit &hit, ShadeOut &out) {
+    PathState path = in;
+    Sampler &sampler = path.sampler;
+    if (!hit.hit) {
+        // no environment light support yet => eval_miss_le contributes 0 (shade.cpp:56-69)
+        out.radiance.valid = true; out.radiance.value = V3(0) + path.L;
+        return;
+    }
+    const Instance &inst = s.instances[hit.inst];
+    SurfacePoint inct = get_hitinfo(s, in.o, in.d, inst, hit.t, hit.prim, V2{hit.u, hit.v});
+    V3 le_rad = handle_intersected_light(s, in.o, in.d, inct, in.beta_le, in.bsdf_pdf, inst.light_id);
+    path.L = path.L + le_rad;
+    if (simple_russian_roulette(s, path.beta, path.depth, sampler)) {
+        out.radiance.valid = true; out.radiance.value = path.L;
+        return;
+    }
+    V3 shadow_bsdf_val(0); float shadow_bsdf_pdf = 0;
+    LiSample ls = sample_surface_light_li(s, inct.position, inct.frame.z, sampler);
+    Shader shader = create_shader(s, s.materials[inst.material], inct);
+    if (path.depth == 0) { out.has_gbuffer = true; out.albedo = shader.albedo(); out.normal = shader.normal(); }
+    V3 wo = -in.d;
+    BsdfSample bs = shader.sample(wo, sampler.get3d());
+    if (ls.success) {
+        shadow_bsdf_val = shader.eval(ls.d, wo);
+        ls.success = !is_zero(shadow_bsdf_val);
+        if (ls.success) shadow_bsdf_pdf = shader.pdf(ls.d, wo);
+    }
+    if (ls.success) {
+        bool shadow_d_out = dot(inct.frame.z, ls.d) > 0;
+        bool last_ray_out = dot(inct.frame.z, in.d) < 0;
+        uint32_t med;
+        if (shadow_d_out == last_ray_out) med = in.medium_id;
+        else if (shadow_d_out) med = inst.outer_medium;
+        else med = inst.inner_medium;
+        float cosv = std::fabs(dot(normalize(ls.d), inct.frame.z));
+        V3 beta_li = ls.li * path.beta * shadow_bsdf_val * cosv / (shadow_bsdf_pdf + ls.light_pdf);
+        out.shadow.valid = true; out.shadow.px = path.px; out.shadow.py = path.py;
+        out.shadow.beta_li = beta_li; out.shadow.o = ls.o; out.shadow.d = ls.d; out.shadow.t1 = ls.t1; out.shadow.medium_id = med;
+    }
+    if (!is_zero(bs.bsdf)) {
+        bs.dir = normalize(bs.dir);
+        float cosv = std::fabs(dot(bs.dir, inct.frame.z));
+        V3 new_beta_le = path.beta * cosv * bs.bsdf;
+        path.beta = new_beta_le / bs.pdf;
+        V3 next_o = intersection_offset(inct.position, inct.frame.z, bs.dir);
+        bool next_out = dot(inct.frame.z, bs.dir) > 0;
+        uint32_t next_med = next_out ? inst.outer_medium : inst.inner_medium;
+        float stored_pdf = bs.is_delta ? -bs.pdf : bs.pdf;
+        out.has_next = true;
+        out.next = path;
+        out.next.depth = path.depth + 1;
+        out.next.beta_le = new_beta_le; out.next.bsdf_pdf = stored_pdf;
+        out.next.o = next_o; out.next.d = bs.dir; out.next.t1 = MAX_FLOAT; out.next.medium_id = next_med;
+    } else {
+        out.radiance.valid = true; out.radiance.value = path.L;
+    }
+}
+
+// core/film.cpp:131-165 (bounds + isfinite checks)
+inline void film_add(float *rgba, V3 v) { if (isfinite3(v)) { rgba[0] += v.x; rgba[1] += v.y; rgba[2] += v.z; } }
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI (ctypes)
+// ==========================================================================================
+extern "C" {
+
+orc_scene *orc_scene_new() { return new orc_scene(); }
+void orc_scene_free(orc_scene *s) { delete s; }
+
+int orc_add_texture_constant(orc_scene *s, float r, float g, float b) {
+    Texture2D t; t.type = 0; t.value = V3(r, g, b);
+    s->textures.push_back(t);
+    return (int)s->textures.size() - 1;
+}
+
+int orc_add_material(orc_scene *s, int type, int color_tex, int normal_tex, int shadow_terminator) {
+    Material m; m.type = type; m.color_tex = color_tex; m.normal_tex = normal_tex; m.shadow_terminator = shadow_terminator != 0;
+    s->materials.push_back(m);
+    return (int)s->materials.size() - 1;
+}
+
+int orc_add_mesh(orc_scene *s, int ntri, const float *pos, const float *nor, const uint8_t *has_nor, const float *uv) {
+    s->meshes.emplace_back();
+    build_mesh(s->meshes.back(), ntri, pos, nor, has_nor, uv);
+    return (int)s->meshes.size() - 1;
+}
+
+int orc_add_instance(orc_scene *s, int mesh, int material, const float *mat16, const float *inv16,
+                     int has_light, const float *intensity) {
+    Instance in; in.mesh = mesh; in.material = material;
+    std::memcpy(in.xf.mat.m, mat16, 64); std::memcpy(in.xf.inv.m, inv16, 64);
+    if (has_light) {
+        in.light_id = (int)s->lights.size();
+        in.intensity = V3(intensity[0], intensity[1], intensity[2]);
+        // MeshLight::set_geometry (mesh_light.cpp:11-15)
+        in.light_scale = length(in.xf.point(V3(1, 0, 0)) - in.xf.point(V3(0, 0, 0)));
+        s->lights.push_back((int)s->instances.size());
+    }
+    s->instances.push_back(in);
+    return (int)s->instances.size() - 1;
+}
+
+void orc_set_camera(orc_scene *s, const float *eye, const float *dst, const float *up, float fov_y_deg) {
+    s->eye = V3(eye[0], eye[1], eye[2]); s->dst = V3(dst[0], dst[1], dst[2]); s->up = V3(up[0], up[1], up[2]);
+    s->fov_y_deg = fov_y_deg;
+}
+
+void orc_set_film(orc_scene *s, int w, int h) { s->width = w; s->height = h; s->w_over_h = float(w) / h; }
+
+void orc_set_renderer(orc_scene *s, int spp, int min_depth, int max_depth, float rr_threshold, float rr_cont_prob,
+                      int tile, int albedo, int normal, int filter_type, float radius, float alpha) {
+    s->spp = spp; s->min_depth = min_depth; s->max_depth = max_depth; s->rr_threshold = rr_threshold;
+    s->rr_cont_prob = rr_cont_prob; s->tile = tile != 0; s->want_albedo = albedo != 0; s->want_normal = normal != 0;
+    s->filter_type = filter_type; s->filter_radius = radius; s->filter_alpha = alpha;
+}
+
+void orc_commit(orc_scene *s) {
+    camera_commit(*s);
+    if (s->filter_type == 1) build_gaussian(*s);
+    build_accel(*s);
+    // Scene::commit bbox (core/scene.cpp:224-237) + wavefront.cpp:138-139
+    V3 lo(MAX_FLOAT), hi(-MAX_FLOAT);
+    for (auto &inst : s->instances) {
+        const Mesh &m = s->meshes[inst.mesh];
+        for (int c = 0; c < 8; ++c) {
+            V3 p(c & 4 ? m.bb_hi.x : m.bb_lo.x, c & 2 ? m.bb_hi.y : m.bb_lo.y, c & 1 ? m.bb_hi.z : m.bb_lo.z);
+            V3 q = inst.xf.point(p);
+            lo = V3(std::fmin(lo.x, q.x), std::fmin(lo.y, q.y), std::fmin(lo.z, q.z));
+            hi = V3(std::fmax(hi.x, q.x), std::fmax(hi.y, q.y), std::fmax(hi.z, q.z));
+        }
+    }
+    lo = V3(std::fmin(lo.x, s->eye.x), std::fmin(lo.y, s->eye.y), std::fmin(lo.z, s->eye.z));
+    hi = V3(std::fmax(hi.x, s->eye.x), std::fmax(hi.y, s->eye.y), std::fmax(hi.z, s->eye.z));
+    s->bb_lo = lo; s->bb_hi = hi;
+    s->world_diagonal = 1.2f * length(hi - lo);
+    s->vol_prim_medium_id = 0;  // no media: the volume-primitive medium is the only one (scene.cpp:144-160)
+    s->committed = true;
+}
+
+int orc_num_triangles(orc_scene *s) { return (int)s->tris.size(); }
+float orc_world_diagonal(orc_scene *s) { return s->world_diagonal; }
+
+// Flattened world-space triangles as (p0, p1, p2) 9 floats + (inst, prim): lets tests feed the very
+// same triangles to oracle/_ref (lib/bvh).
+void orc_get_triangles(orc_scene *s, float *verts, uint32_t *inst_prim) {
+    for (size_t i = 0; i < s->tris.size(); ++i) {
+        const Tri &t = s->tris[i];
+        float *o = verts + 9 * i;
+        o[0] = t.p0.x; o[1] = t.p0.y; o[2] = t.p0.z; o[3] = t.p1.x; o[4] = t.p1.y; o[5] = t.p1.z; o[6] = t.p2.x; o[7] = t.p2.y; o[8] = t.p2.z;
+        inst_prim[2 * i] = t.inst; inst_prim[2 * i + 1] = t.prim;
+    }
+}
+
+// Per-mesh shading tables (6 x float4 per triangle) for table parity tests.
+void orc_get_mesh_tables(orc_scene *s, int mesh, float *out24) {
+    const Mesh &m = s->meshes[mesh];
+    for (int i = 0; i < m.ntri; ++i) {
+        float *o = out24 + 24 * (size_t)i;
+        std::memcpy(o, &m.gx_ua[4 * i], 16); std::memcpy(o + 4, &m.gy_uba[4 * i], 16); std::memcpy(o + 8, &m.gz_uca[4 * i], 16);
+        std::memcpy(o + 12, &m.sn_va[4 * i], 16); std::memcpy(o + 16, &m.sn_vba[4 * i], 16); std::memcpy(o + 20, &m.sn_vca[4 * i], 16);
+    }
+}
+
+// Closest hit on a ray batch in the reference SoA layout (soa.cpp:5-23,55-91): o_med/d_t1 are float4,
+// flag = inst | bit30 on hit, detail = (t bits, prim, u bits, v bits).  mode 0 = BVH, 1 = brute force.
+void orc_closest_hit(orc_scene *s, int n, const float *o_med, const float *d_t1, uint32_t *flag, uint32_t *detail, int mode) {
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int i = 0; i < n; ++i) {
+        V3 o(o_med[4 * i], o_med[4 * i + 1], o_med[4 * i + 2]), d(d_t1[4 * i], d_t1[4 * i + 1], d_t1[4 * i + 2]);
+        float t1 = d_t1[4 * i + 3];
+        Hit h = mode == 1 ? closest_hit_brute(*s, o, d, t1) : traverse<false>(*s, o, d, t1);
+        if (!h.hit) { flag[i] = 0; detail[4 * i] = detail[4 * i + 1] = detail[4 * i + 2] = detail[4 * i + 3] = 0; }
+        else {
+            flag[i] = h.inst | (1u << 30);
+            detail[4 * i] = f2u(h.t); detail[4 * i + 1] = h.prim; detail[4 * i + 2] = f2u(h.u); detail[4 * i + 3] = f2u(h.v);
+        }
+    }
+}
+
+// Occlusion test: out[i] = 1 if any triangle has t in [0, t1] (shadow.cpp:24-36).
+void orc_any_hit(orc_scene *s, int n, const float *o_med, const float *d_t1, uint8_t *out) {
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int i = 0; i < n; ++i) {
+        V3 o(o_med[4 * i], o_med[4 * i + 1], o_med[4 * i + 2]), d(d_t1[4 * i], d_t1[4 * i + 1], d_t1[4 * i + 2]);
+        out[i] = traverse<true>(*s, o, d, d_t1[4 * i + 3]).hit ? 1 : 0;
+    }
+}
+
+static void store_state(const PathState &ps, int i, float *o_med, float *d_t1, uint32_t *pixel, float *beta_depth,
+                        float *path_rad, uint64_t *rng, float *ble) {
+    o_med[4 * i] = ps.o.x; o_med[4 * i + 1] = ps.o.y; o_med[4 * i + 2] = ps.o.z; o_med[4 * i + 3] = u2f(ps.medium_id);
+    d_t1[4 * i] = ps.d.x; d_t1[4 * i + 1] = ps.d.y; d_t1[4 * i + 2] = ps.d.z; d_t1[4 * i + 3] = ps.t1;
+    pixel[2 * i] = ps.px; pixel[2 * i + 1] = ps.py;
+    beta_depth[4 * i] = ps.beta.x; beta_depth[4 * i + 1] = ps.beta.y; beta_depth[4 * i + 2] = ps.beta.z; beta_depth[4 * i + 3] = i2f(ps.depth);
+    path_rad[4 * i] = ps.L.x; path_rad[4 * i + 1] = ps.L.y; path_rad[4 * i + 2] = ps.L.z; path_rad[4 * i + 3] = 1;
+    rng[2 * i] = ps.sampler.rng.state; rng[2 * i + 1] = ps.sampler.rng.inc;
+    ble[4 * i] = ps.beta_le.x; ble[4 * i + 1] = ps.beta_le.y; ble[4 * i + 2] = ps.beta_le.z; ble[4 * i + 3] = ps.bsdf_pdf;
+}
+
+static void load_state(PathState &ps, int i, const float *o_med, const float *d_t1, const uint32_t *pixel, const float *beta_depth,
+                       const float *path_rad, const uint64_t *rng, const float *ble) {
+    ps.o = V3(o_med[4 * i], o_med[4 * i + 1], o_med[4 * i + 2]); ps.medium_id = f2u(o_med[4 * i + 3]);
+    ps.d = V3(d_t1[4 * i], d_t1[4 * i + 1], d_t1[4 * i + 2]); ps.t1 = d_t1[4 * i + 3];
+    ps.px = pixel[2 * i]; ps.py = pixel[2 * i + 1];
+    ps.beta = V3(beta_depth[4 * i], beta_depth[4 * i + 1], beta_depth[4 * i + 2]); ps.depth = f2i(beta_depth[4 * i + 3]);
+    ps.L = V3(path_rad[4 * i], path_rad[4 * i + 1], path_rad[4 * i + 2]);
+    ps.sampler.rng.state = rng[2 * i]; ps.sampler.rng.inc = rng[2 * i + 1];
+    ps.beta_le = V3(ble[4 * i], ble[4 * i + 1], ble[4 * i + 2]); ps.bsdf_pdf = ble[4 * i + 3];
+}
+
+// generate stage in the reference SoA layout (generate.cpp:84-86)
+void orc_generate(orc_scene *s, int64_t first, int n, float *o_med, float *d_t1, uint32_t *pixel, float *beta_depth,
+                  float *path_rad, uint64_t *rng, float *ble) {
+#pragma omp parallel for
+    for (int i = 0; i < n; ++i) {
+        PathState ps;
+        generate_path(*s, first + i, ps);
+        store_state(ps, i, o_med, d_t1, pixel, beta_depth, path_rad, rng, ble);
+    }
+}
+
+// shade stage on a batch (uncompacted outputs: slot i of every output belongs to input i).
+// status bits: 1 = next state emitted, 2 = shadow ray emitted, 4 = radiance splat, 8 = g-buffer splat
+void orc_shade(orc_scene *s, int n,
+               const float *o_med, const float *d_t1, const uint32_t *pixel, const float *beta_depth, const float *path_rad,
+               const uint64_t *rng, const float *ble, const uint32_t *flag, const uint32_t *detail,
+               uint32_t *status,
+               float *n_o_med, float *n_d_t1, uint32_t *n_pixel, float *n_beta_depth, float *n_path_rad, uint64_t *n_rng, float *n_ble,
+               float *sh_o_med, float *sh_d_t1, float *sh_beta_li,
+               float *splat_rgb, float *gbuf_albedo, float *gbuf_normal) {
+#pragma omp parallel for
+    for (int i = 0; i < n; ++i) {
+        PathState ps;
+        load_state(ps, i, o_med, d_t1, pixel, beta_depth, path_rad, rng, ble);
+        Hit h;
+        h.hit = (flag[i] >> 30) & 1;
+        if (h.hit) { h.inst = flag[i] & 0x3fffffffu; h.t = u2f(detail[4 * i]); h.prim = detail[4 * i + 1]; h.u = u2f(detail[4 * i + 2]); h.v = u2f(detail[4 * i + 3]); }
+        ShadeOut out;
+        shade(*s, ps, h, out);
+        uint32_t st = 0;
+        if (out.has_next) { st |= 1; store_state(out.next, i, n_o_med, n_d_t1, n_pixel, n_beta_depth, n_path_rad, n_rng, n_ble); }
+        if (out.shadow.valid) {
+            st |= 2;
+            sh_o_med[4 * i] = out.shadow.o.x; sh_o_med[4 * i + 1] = out.shadow.o.y; sh_o_med[4 * i + 2] = out.shadow.o.z; sh_o_med[4 * i + 3] = u2f(out.shadow.medium_id);
+            sh_d_t1[4 * i] = out.shadow.d.x; sh_d_t1[4 * i + 1] = out.shadow.d.y; sh_d_t1[4 * i + 2] = out.shadow.d.z; sh_d_t1[4 * i + 3] = out.shadow.t1;
+            sh_beta_li[4 * i] = out.shadow.beta_li.x; sh_beta_li[4 * i + 1] = out.shadow.beta_li.y; sh_beta_li[4 * i + 2] = out.shadow.beta_li.z; sh_beta_li[4 * i + 3] = 1;
+        }
+        if (out.radiance.valid) { st |= 4; splat_rgb[3 * i] = out.radiance.value.x; splat_rgb[3 * i + 1] = out.radiance.value.y; splat_rgb[3 * i + 2] = out.radiance.value.z; }
+        if (out.has_gbuffer) {
+            st |= 8;
+            gbuf_albedo[3 * i] = out.albedo.x; gbuf_albedo[3 * i + 1] = out.albedo.y; gbuf_albedo[3 * i + 2] = out.albedo.z;
+            gbuf_normal[3 * i] = out.normal.x; gbuf_normal[3 * i + 1] = out.normal.y; gbuf_normal[3 * i + 2] = out.normal.z;
+        }
+        status[i] = st;
+    }
+}
+
+// Whole render (wavefront.cpp:205-325 + preview.cpp:28-80).  Renders sample indices [spp_begin, spp_end) of every
+// pixel; out_* are W*H float4 (resolved: value/weight, w = 1).  raw_* (optional) receive unresolved sums
+// radiance(float4 stride) / weight(float).  stats (optional): 7 x uint64 event counters.
+void orc_render(orc_scene *s, int spp_begin, int spp_end, float *out_color, float *out_albedo, float *out_normal,
+                float *raw_radiance, float *raw_weight, uint64_t *stats_out) {
+    const int W = s->width, H = s->height;
+    const size_t npix = (size_t)W * H;
+    std::vector<float> rad(4 * npix, 0.0f), wgt(npix, 0.0f), alb(4 * npix, 0.0f), nor(4 * npix, 0.0f);
+    Stats total;
+#pragma omp parallel
+    {
+        Stats st;
+#pragma omp for schedule(dynamic, 64)
+        for (long long pix = 0; pix < (long long)npix; ++pix) {
+            for (int sidx = spp_begin; sidx < spp_end; ++sidx) {
+                // state index for Uniform mode = sidx * W*H + pix, for Tile mode = pix * spp + sidx
+                int64_t accu = s->tile ? (int64_t)pix * s->spp + sidx : (int64_t)sidx * (int64_t)npix + pix;
+                PathState ps;
+                generate_path(*s, accu, ps);
+                wgt[pix] += 1.0f; st.n_gen++;
+                const size_t p = (size_t)ps.py * W + ps.px;
+                for (;;) {
+                    Hit h = traverse<false>(*s, ps.o, ps.d, ps.t1);
+                    st.n_closest++; if (h.hit) st.n_hit++;
+                    ShadeOut out;
+                    shade(*s, ps, h, out);
+                    if (out.shadow.valid) {
+                        st.n_shadow++;
+                        bool occluded = traverse<true>(*s, out.shadow.o, out.shadow.d, out.shadow.t1).hit;
+                        if (!occluded) { st.n_shadow_miss++; st.n_splat++; film_add(&rad[4 * p], out.shadow.beta_li); }  // shadow.cpp:39-74 (tr = 1 without media)
+                    }
+                    if (out.has_gbuffer) {
+                        if (s->want_albedo) film_add(&alb[4 * p], out.albedo);
+                        if (s->want_normal) film_add(&nor[4 * p], out.normal);
+                    }
+                    if (out.radiance.valid) { st.n_splat++; film_add(&rad[4 * p], out.radiance.value); }
+                    if (!out.has_next) break;
+                    st.n_next++;
+                    ps = out.next;
+                }
+            }
+        }
+#pragma omp critical
+        {
+            total.n_gen += st.n_gen; total.n_closest += st.n_closest; total.n_hit += st.n_hit; total.n_next += st.n_next;
+            total.n_shadow += st.n_shadow; total.n_shadow_miss += st.n_shadow_miss; total.n_splat += st.n_splat;
+        }
+    }
+    auto resolve = [&](const std::vector<float> &src, float *dst, bool normalise) {  // preview.cpp:28-80
+        if (!dst) return;
+        for (size_t i = 0; i < npix; ++i) {
+            V3 o(0);
+            if (wgt[i] > 0) {
+                o = V3(src[4 * i], src[4 * i + 1], src[4 * i + 2]) / wgt[i];
+                if (normalise) o = length(o) > 1e-3f ? normalize(o) : V3(0);
+            }
+            dst[4 * i] = o.x; dst[4 * i + 1] = o.y; dst[4 * i + 2] = o.z; dst[4 * i + 3] = 1;
+        }
+    };
+    resolve(rad, out_color, false);
+    if (s->want_albedo) resolve(alb, out_albedo, false);
+    if (s->want_normal) resolve(nor, out_normal, true);
+    if (raw_radiance) std::memcpy(raw_radiance, rad.data(), sizeof(float) * 4 * npix);
+    if (raw_weight) std::memcpy(raw_weight, wgt.data(), sizeof(float) * npix);
+    if (stats_out) {
+        stats_out[0] = total.n_gen; stats_out[1] = total.n_closest; stats_out[2] = total.n_hit; stats_out[3] = total.n_next;
+        stats_out[4] = total.n_shadow; stats_out[5] = total.n_shadow_miss; stats_out[6] = total.n_splat;
+    }
+}
+
+// --- known-answer helpers for RNG / hash / alias / offset tests -------------------------------
+uint64_t orc_murmur_pixel(uint32_t px, uint32_t py) { return hash_pixel(px, py); }
+void orc_pcg_stream(uint32_t px, uint32_t py, int sample_index, int n, uint32_t *out_u32, float *out_f32, uint64_t *state_inc) {
+    Sampler sm; sm.init(px, py, sample_index);
+    if (state_inc) { state_inc[0] = sm.rng.state; state_inc[1] = sm.rng.inc; }
+    for (int i = 0; i < n; ++i) {
+        PCG copy = sm.rng;
+        uint32_t r = copy.next();
+        out_u32[i] = r;
+        out_f32[i] = sm.get1d();
+    }
+}
+void orc_alias_build(int n, const float *probs, float *accept, uint32_t *alias) {
+    AliasTable t; t.initialize(std::vector<float>(probs, probs + n));
+    for (int i = 0; i < n; ++i) { accept[i] = t.units[i].accept_prob; alias[i] = t.units[i].another_idx; }
+}
+void orc_intersection_offset(int n, const float *pos, const float *nor, const float *dir, float *out) {
+    for (int i = 0; i < n; ++i) {
+        V3 r = intersection_offset(V3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]), V3(nor[3 * i], nor[3 * i + 1], nor[3 * i + 2]),
+                                   V3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]));
+        out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
+    }
+}
+int orc_num_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+}  // extern "C"
