@@ -1,0 +1,234 @@
+"""ctypes binding of libbtrc_b200.so (include/btrc_b200.h) -- the call a user of the render path makes.
+
+Mirrors the three calls of the reference CLI (src/cli/main.cpp:36-80): load (parse + create + commit),
+render, run post-processors; plus the stage-level entry points used by the parity tests.  Arrays are numpy
+(host) or anything exposing a CUDA pointer via `.data_ptr()` (torch tensors).  There is no CPU fallback: if the
+library is missing this module raises, and device calls fail with the library's CUDA error when no GPU exists.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_uint32, c_uint64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbtrc_b200.so")
+
+HOST, DEVICE = 0, 1
+
+
+class BtrcError(RuntimeError):
+    """Chained error text from the library (one context per line, like the reference's nested BtrcException)."""
+
+
+class SceneInfo(ctypes.Structure):
+    _fields_ = [(n, c_int32) for n in ("width", "height", "spp", "min_depth", "max_depth", "state_count", "tile", "albedo", "normal",
+                                       "n_instances", "n_lights", "n_triangles", "n_materials", "bvh_depth")] + \
+               [("world_diagonal", c_float), ("bvh_build_seconds", c_float)]
+
+
+class RenderStats(ctypes.Structure):
+    _fields_ = [(n, c_uint64) for n in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss", "n_splat", "n_iter")] + \
+               [("render_ms", c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BtrcError(f"{LIB_PATH} is missing: run `python -m btrc_b200.build` (the render path has no fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.btrc_last_error.restype = c_char_p
+        L.btrc_version.restype = c_char_p
+        L.btrc_scene_load_json.argtypes = [c_char_p, POINTER(c_void_p)]
+        L.btrc_scene_load_json_string.argtypes = [c_char_p, c_char_p, POINTER(c_void_p)]
+        L.btrc_scene_free.argtypes = [c_void_p]
+        L.btrc_scene_free.restype = None
+        L.btrc_scene_info_get.argtypes = [c_void_p, POINTER(SceneInfo)]
+        L.btrc_set_params.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32]
+        L.btrc_render.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, POINTER(RenderStats)]
+        L.btrc_film_clear.argtypes = [c_void_p]
+        L.btrc_render_range.argtypes = [c_void_p, c_int64, c_int64, POINTER(RenderStats)]
+        L.btrc_film_export.argtypes = [c_void_p, c_int] + [c_void_p] * 4
+        L.btrc_film_import.argtypes = [c_void_p, c_int] + [c_void_p] * 4
+        L.btrc_resolve.argtypes = [c_void_p, c_int] + [c_void_p] * 3
+        L.btrc_run_post_processors.argtypes = [c_void_p, c_int] + [c_void_p] * 3
+        L.btrc_closest_hit.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]
+        L.btrc_any_hit.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int32, c_void_p]
+        L.btrc_generate.argtypes = [c_void_p, c_int, c_int64, c_int32] + [c_void_p] * 7
+        L.btrc_shade.argtypes = [c_void_p, c_int, c_int32] + [c_void_p] * 9 + [POINTER(c_int32)] + [c_void_p] * 7 + [POINTER(c_int32)] + [c_void_p] * 4
+        L.btrc_shadow.argtypes = [c_void_p, c_int, c_int32] + [c_void_p] * 4
+        L.btrc_geometry_tables.argtypes = [c_void_p, c_int32, POINTER(c_int32), c_void_p]
+        L.btrc_instance_transform.argtypes = [c_void_p, c_int32, c_void_p, c_void_p]
+        L.btrc_device_sm_count.restype = c_int
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise BtrcError(lib().btrc_last_error().decode())
+
+
+def _p(a):
+    """Pointer of a numpy array (host) or a torch tensor (device or host); None stays None."""
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return c_void_p(a.data_ptr())
+    assert a.flags["C_CONTIGUOUS"]
+    return c_void_p(a.ctypes.data)
+
+
+def _mem(*arrays):
+    for a in arrays:
+        if a is not None and hasattr(a, "is_cuda") and a.is_cuda:
+            return DEVICE
+    return HOST
+
+
+def new_state(n):
+    """Path-state batch in the reference SoA layout (wavefront/soa.h:8-37)."""
+    f32 = np.float32
+    return dict(o_med=np.zeros((n, 4), f32), d_t1=np.zeros((n, 4), f32), pixel=np.zeros((n, 2), np.uint32),
+                beta_depth=np.zeros((n, 4), f32), path_rad=np.zeros((n, 4), f32), rng=np.zeros((n, 2), np.uint64),
+                ble=np.zeros((n, 4), f32))
+
+
+_STATE_KEYS = ("o_med", "d_t1", "pixel", "beta_depth", "path_rad", "rng", "ble")
+
+
+class Scene:
+    """A loaded + committed scene and its wavefront renderer (reference: Scene + WavefrontPathTracer)."""
+
+    def __init__(self, path=None, json_text=None, scene_dir=None, spp=None, state_count=None, min_depth=None, max_depth=None):
+        self.L = lib()
+        self.h = c_void_p()
+        if path is not None:
+            _check(self.L.btrc_scene_load_json(os.fsencode(path), byref(self.h)))
+        else:
+            _check(self.L.btrc_scene_load_json_string(json_text.encode(), os.fsencode(scene_dir or "."), byref(self.h)))
+        if any(v is not None for v in (spp, state_count, min_depth, max_depth)):
+            self.set_params(spp, state_count, min_depth, max_depth)
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.btrc_scene_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, spp=None, state_count=None, min_depth=None, max_depth=None):
+        v = [(-1 if x is None else int(x)) for x in (spp, state_count, min_depth, max_depth)]
+        _check(self.L.btrc_set_params(self.h, *v))
+
+    @property
+    def info(self) -> SceneInfo:
+        i = SceneInfo()
+        _check(self.L.btrc_scene_info_get(self.h, byref(i)))
+        return i
+
+    # ---- whole render -------------------------------------------------------------------------------------
+    def render(self, color=None, albedo=None, normal=None):
+        """Renderer::render(): returns (color, albedo, normal, stats); arrays are (H, W, 4) float32."""
+        i = self.info
+        if color is None:
+            color = np.zeros((i.height, i.width, 4), np.float32)
+        if albedo is None and i.albedo:
+            albedo = np.zeros((i.height, i.width, 4), np.float32)
+        if normal is None and i.normal:
+            normal = np.zeros((i.height, i.width, 4), np.float32)
+        st = RenderStats()
+        _check(self.L.btrc_render(self.h, _mem(color), _p(color), _p(albedo), _p(normal), byref(st)))
+        return color, albedo, normal, st.as_dict()
+
+    def film_clear(self):
+        _check(self.L.btrc_film_clear(self.h))
+
+    def render_range(self, begin, end):
+        st = RenderStats()
+        _check(self.L.btrc_render_range(self.h, int(begin), int(end), byref(st)))
+        return st.as_dict()
+
+    def film_export(self, radiance, weight, albedo=None, normal=None):
+        _check(self.L.btrc_film_export(self.h, _mem(radiance, weight), _p(radiance), _p(weight), _p(albedo), _p(normal)))
+
+    def film_import(self, radiance, weight, albedo=None, normal=None):
+        _check(self.L.btrc_film_import(self.h, _mem(radiance, weight), _p(radiance), _p(weight), _p(albedo), _p(normal)))
+
+    def resolve(self, color, albedo=None, normal=None):
+        _check(self.L.btrc_resolve(self.h, _mem(color), _p(color), _p(albedo), _p(normal)))
+
+    def run_post_processors(self, color, albedo=None, normal=None):
+        _check(self.L.btrc_run_post_processors(self.h, _mem(color), _p(color), _p(albedo), _p(normal)))
+
+    # ---- stage level ----------------------------------------------------------------------------------------
+    def closest_hit(self, o_med, d_t1):
+        n = o_med.shape[0]
+        flag = np.zeros(n, np.uint32)
+        detail = np.zeros((n, 4), np.uint32)
+        _check(self.L.btrc_closest_hit(self.h, HOST, _p(np.ascontiguousarray(o_med, np.float32)), _p(np.ascontiguousarray(d_t1, np.float32)), n, _p(flag), _p(detail)))
+        return flag, detail
+
+    def any_hit(self, o_med, d_t1):
+        n = o_med.shape[0]
+        occ = np.zeros(n, np.uint8)
+        _check(self.L.btrc_any_hit(self.h, HOST, _p(np.ascontiguousarray(o_med, np.float32)), _p(np.ascontiguousarray(d_t1, np.float32)), n, _p(occ)))
+        return occ
+
+    def generate(self, first, n):
+        st = new_state(n)
+        _check(self.L.btrc_generate(self.h, HOST, int(first), n, *[_p(st[k]) for k in _STATE_KEYS]))
+        return st
+
+    def shade(self, st, flag, detail):
+        n = st["o_med"].shape[0]
+        nxt = new_state(n)
+        sh = dict(pixel=np.zeros((n, 2), np.uint32), beta_li=np.zeros((n, 4), np.float32), o_med=np.zeros((n, 4), np.float32),
+                  d_t1=np.zeros((n, 4), np.float32))
+        n_next, n_shadow = c_int32(0), c_int32(0)
+        flag = np.ascontiguousarray(flag, np.uint32)
+        detail = np.ascontiguousarray(detail, np.uint32)
+        _check(self.L.btrc_shade(self.h, HOST, n, *[_p(st[k]) for k in _STATE_KEYS], _p(flag), _p(detail), byref(n_next),
+                                 *[_p(nxt[k]) for k in _STATE_KEYS], byref(n_shadow), _p(sh["pixel"]), _p(sh["beta_li"]), _p(sh["o_med"]), _p(sh["d_t1"])))
+        nn, ns = n_next.value, n_shadow.value
+        return {k: v[:nn] for k, v in nxt.items()}, {k: v[:ns] for k, v in sh.items()}
+
+    def shadow(self, sh):
+        n = sh["pixel"].shape[0]
+        _check(self.L.btrc_shadow(self.h, HOST, n, _p(np.ascontiguousarray(sh["pixel"])), _p(np.ascontiguousarray(sh["beta_li"])),
+                                  _p(np.ascontiguousarray(sh["o_med"])), _p(np.ascontiguousarray(sh["d_t1"]))))
+
+    def geometry_tables(self, geometry_id):
+        n = c_int32(0)
+        _check(self.L.btrc_geometry_tables(self.h, geometry_id, byref(n), None))
+        out = np.zeros((n.value, 24), np.float32)
+        _check(self.L.btrc_geometry_tables(self.h, geometry_id, byref(n), _p(out)))
+        return out
+
+    def instance_transform(self, instance_id):
+        mat = np.zeros((3, 4), np.float32)
+        inv = np.zeros((3, 4), np.float32)
+        _check(self.L.btrc_instance_transform(self.h, instance_id, _p(mat), _p(inv)))
+        return mat, inv
+
+
+def render_file(path, **kw):
+    """cli/main.cpp:17-81 as one call: load, render, run the scene's post-processors. Returns (color, stats)."""
+    s = Scene(path, **kw)
+    color, albedo, normal, stats = s.render()
+    s.run_post_processors(color, albedo, normal)
+    s.close()
+    return color, stats

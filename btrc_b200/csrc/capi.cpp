@@ -1,0 +1,412 @@
+// C ABI of libbtrc_b200.so (declared in include/btrc_b200.h).  No exception crosses this boundary.
+#include "../../include/btrc_b200.h"
+
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "host/image_io.h"
+#include "host/renderer.h"
+#include "host/scene.h"
+
+using namespace btrc;
+
+struct btrc_scene {
+    std::unique_ptr<Scene> scene;
+    std::unique_ptr<Renderer> renderer;
+    int state_count_override = 0;
+    Renderer &r() {
+        scene->upload_device();
+        if (!renderer) renderer = std::make_unique<Renderer>(*scene, state_count_override);
+        return *renderer;
+    }
+};
+
+namespace {
+
+thread_local std::string g_last_error;
+
+template <typename F>
+int guarded(F &&f) {
+    try {
+        f();
+        g_last_error.clear();
+        return 0;
+    } catch (const std::exception &e) {
+        g_last_error = e.what();
+        return 1;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return 1;
+    }
+}
+
+void fill_stats(const RenderStats &s, btrc_render_stats_t *out) {
+    if (!out) return;
+    out->n_gen = s.n_gen; out->n_closest = s.n_closest; out->n_hit = s.n_hit; out->n_next = s.n_next;
+    out->n_shadow = s.n_shadow; out->n_shadow_miss = s.n_shadow_miss; out->n_splat = s.n_splat; out->n_iter = s.n_iter;
+    out->render_ms = s.render_ms;
+}
+
+// copies between any two address spaces (unified virtual addressing)
+void copy_any(void *dst, const void *src, size_t bytes) {
+    if (bytes) BTRC_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+}
+
+void check_scene(btrc_scene_t *s) {
+    if (!s || !s->scene) throw Error("null scene handle");
+}
+
+// Resolve into device scratch, then hand the result to the caller's buffers.
+void resolve_to(btrc_scene_t *s, float *color, float *albedo, float *normal) {
+    Renderer &r = s->r();
+    const size_t bytes = sizeof(float) * 4 * (size_t)s->scene->width * s->scene->height;
+    DeviceBuffer dc(color ? bytes : 0), da(albedo && r.film().albedo ? bytes : 0), dn(normal && r.film().normal ? bytes : 0);
+    r.resolve(dc.as<float>(), da.as<float>(), dn.as<float>());
+    if (color) copy_any(color, dc.ptr, bytes);
+    if (da.ptr) copy_any(albedo, da.ptr, bytes);
+    if (dn.ptr) copy_any(normal, dn.ptr, bytes);
+}
+
+struct HostPaths {
+    std::vector<float4> ray_o, ray_d, beta, rad, ble;
+    std::vector<ulonglong2> rng;
+    explicit HostPaths(size_t n) : ray_o(n), ray_d(n), beta(n), rad(n), ble(n), rng(n) {}
+};
+
+void upload_paths(Renderer &r, int which, int n, int width, const float *o_med, const float *d_t1, const uint32_t *pixel,
+                  const float *beta_depth, const float *path_rad, const uint64_t *rng, const float *ble) {
+    const size_t N = (size_t)n;
+    std::vector<uint32_t> px(2 * N);
+    std::vector<float4> rad(N);
+    copy_any(px.data(), pixel, 8 * N);
+    copy_any(rad.data(), path_rad, 16 * N);
+    for (size_t i = 0; i < N; ++i) {
+        const uint32_t idx = px[2 * i + 1] * (uint32_t)width + px[2 * i];
+        std::memcpy(&rad[i].w, &idx, 4);
+    }
+    PathQueue &q = r.queue(which);
+    copy_any(q.ray_o, o_med, 16 * N);
+    copy_any(q.ray_d, d_t1, 16 * N);
+    copy_any(q.beta, beta_depth, 16 * N);
+    copy_any(q.rad, rad.data(), 16 * N);
+    copy_any(q.rng, rng, 16 * N);
+    copy_any(q.ble, ble, 16 * N);
+}
+
+void download_paths(Renderer &r, int which, int n, int width, float *o_med, float *d_t1, uint32_t *pixel, float *beta_depth,
+                    float *path_rad, uint64_t *rng, float *ble) {
+    const size_t N = (size_t)n;
+    PathQueue &q = r.queue(which);
+    std::vector<float4> rad(N);
+    std::vector<uint32_t> px(2 * N);
+    copy_any(rad.data(), q.rad, 16 * N);
+    for (size_t i = 0; i < N; ++i) {
+        uint32_t idx;
+        std::memcpy(&idx, &rad[i].w, 4);
+        px[2 * i] = idx % (uint32_t)width;
+        px[2 * i + 1] = idx / (uint32_t)width;
+        rad[i].w = 1.0f;  // reference layout: path_radiance.w = 1 (soa.cpp:49)
+    }
+    copy_any(o_med, q.ray_o, 16 * N);
+    copy_any(d_t1, q.ray_d, 16 * N);
+    copy_any(beta_depth, q.beta, 16 * N);
+    copy_any(path_rad, rad.data(), 16 * N);
+    copy_any(pixel, px.data(), 8 * N);
+    copy_any(rng, q.rng, 16 * N);
+    copy_any(ble, q.ble, 16 * N);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *btrc_last_error(void) { return g_last_error.c_str(); }
+const char *btrc_version(void) { return "btrc_b200 0.1 (sm_100a)"; }
+
+int btrc_device_sm_count(void) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    return n;
+}
+
+int btrc_scene_load_json(const char *path, btrc_scene_t **out) {
+    return guarded([&] {
+        if (!path || !out) throw Error("null argument");
+        auto h = std::make_unique<btrc_scene>();
+        h->scene = Scene::from_file(path);
+        h->scene->commit();
+        *out = h.release();
+    });
+}
+
+int btrc_scene_load_json_string(const char *json, const char *scene_dir, btrc_scene_t **out) {
+    return guarded([&] {
+        if (!json || !out) throw Error("null argument");
+        auto h = std::make_unique<btrc_scene>();
+        h->scene = Scene::from_string(json, scene_dir ? scene_dir : ".");
+        h->scene->commit();
+        *out = h.release();
+    });
+}
+
+void btrc_scene_free(btrc_scene_t *scene) { delete scene; }
+
+int btrc_scene_info_get(btrc_scene_t *s, btrc_scene_info_t *o) {
+    return guarded([&] {
+        check_scene(s);
+        const Scene &sc = *s->scene;
+        o->width = sc.width; o->height = sc.height;
+        o->spp = sc.renderer.spp; o->min_depth = sc.renderer.min_depth; o->max_depth = sc.renderer.max_depth;
+        o->state_count = s->state_count_override > 0 ? s->state_count_override : sc.renderer.state_count;
+        o->tile = sc.renderer.tile; o->albedo = sc.renderer.albedo; o->normal = sc.renderer.normal;
+        o->n_instances = (int)sc.instances.size(); o->n_lights = (int)sc.lights.size();
+        o->n_triangles = (int)sc.world_tris.size(); o->n_materials = (int)sc.materials.size();
+        o->bvh_depth = sc.bvh_depth;
+        o->world_diagonal = sc.world_diagonal;
+        o->bvh_build_seconds = (float)sc.bvh_build_seconds;
+    });
+}
+
+int btrc_set_params(btrc_scene_t *s, int32_t spp, int32_t state_count, int32_t min_depth, int32_t max_depth) {
+    return guarded([&] {
+        check_scene(s);
+        if (s->renderer && state_count > 0) throw Error("state_count must be set before the first render");
+        if (spp > 0) s->scene->renderer.spp = spp;
+        if (state_count > 0) s->state_count_override = state_count;
+        if (min_depth >= 0) s->scene->renderer.min_depth = min_depth;
+        if (max_depth >= 0) s->scene->renderer.max_depth = max_depth;
+    });
+}
+
+int btrc_film_clear(btrc_scene_t *s) {
+    return guarded([&] { check_scene(s); s->r().clear_film(); });
+}
+
+int btrc_render_range(btrc_scene_t *s, int64_t begin, int64_t end, btrc_render_stats_t *stats) {
+    return guarded([&] {
+        check_scene(s);
+        s->r().render_range(begin, end);
+        fill_stats(s->r().stats(), stats);
+    });
+}
+
+int btrc_render(btrc_scene_t *s, int memory, float *color, float *albedo, float *normal, btrc_render_stats_t *stats) {
+    (void)memory;
+    return guarded([&] {
+        check_scene(s);
+        Renderer &r = s->r();
+        r.clear_film();
+        r.render_range(0, r.total_paths());
+        resolve_to(s, color, albedo, normal);
+        fill_stats(r.stats(), stats);
+    });
+}
+
+int btrc_resolve(btrc_scene_t *s, int memory, float *color, float *albedo, float *normal) {
+    (void)memory;
+    return guarded([&] { check_scene(s); resolve_to(s, color, albedo, normal); });
+}
+
+int btrc_film_export(btrc_scene_t *s, int memory, float *radiance, float *weight, float *albedo, float *normal) {
+    (void)memory;
+    return guarded([&] {
+        check_scene(s);
+        Renderer &r = s->r();
+        BTRC_CUDA(cudaStreamSynchronize(r.stream()));
+        const size_t npix = (size_t)s->scene->width * s->scene->height;
+        if (radiance) copy_any(radiance, r.film().radiance, 16 * npix);
+        if (weight) copy_any(weight, r.film().weight, 4 * npix);
+        if (albedo && r.film().albedo) copy_any(albedo, r.film().albedo, 16 * npix);
+        if (normal && r.film().normal) copy_any(normal, r.film().normal, 16 * npix);
+    });
+}
+
+int btrc_film_import(btrc_scene_t *s, int memory, const float *radiance, const float *weight, const float *albedo, const float *normal) {
+    (void)memory;
+    return guarded([&] {
+        check_scene(s);
+        Renderer &r = s->r();
+        BTRC_CUDA(cudaStreamSynchronize(r.stream()));
+        const size_t npix = (size_t)s->scene->width * s->scene->height;
+        if (radiance) copy_any(r.film().radiance, radiance, 16 * npix);
+        if (weight) copy_any(r.film().weight, weight, 4 * npix);
+        if (albedo && r.film().albedo) copy_any(r.film().albedo, albedo, 16 * npix);
+        if (normal && r.film().normal) copy_any(r.film().normal, normal, 16 * npix);
+    });
+}
+
+int btrc_run_post_processors(btrc_scene_t *s, int memory, float *color, float *albedo, float *normal) {
+    (void)memory;
+    return guarded([&] {
+        check_scene(s);
+        const int w = s->scene->width, h = s->scene->height;
+        const size_t n = 4 * (size_t)w * h;
+        std::vector<float> c(color ? n : 0), a(albedo ? n : 0), nn(normal ? n : 0);
+        if (color) copy_any(c.data(), color, n * 4);
+        if (albedo) copy_any(a.data(), albedo, n * 4);
+        if (normal) copy_any(nn.data(), normal, n * 4);
+        for (const PostProcessorDesc &p : s->scene->post_processors) {
+            if (p.type == "tonemap") {  // postprocess/tonemap.cpp:14-22,35-51 (ACES fit on exposure-scaled colour, in place)
+                if (!color) continue;
+                auto aces = [](float x) {
+                    constexpr float tA = 2.51f, tB = 0.03f, tC = 2.43f, tD = 0.59f, tE = 0.14f;
+                    return std::fmin(std::fmax((x * (tA * x + tB)) / (x * (tC * x + tD) + tE), 0.0f), 1.0f);
+                };
+                for (size_t i = 0; i < n; i += 4)
+                    for (int k = 0; k < 3; ++k) c[i + k] = aces(p.exposure * c[i + k]);
+                copy_any(color, c.data(), n * 4);
+            } else if (p.type == "save") {  // postprocess/save_to_image.cpp:30-62
+                if (color && !p.color.empty()) {
+                    std::vector<float> g = c;
+                    const float e = 1 / p.gamma;
+                    for (float &v : g) v = std::pow(v, e);  // Image<Vec4f>::pow_ (all four components)
+                    save_image_rgba32f(p.color, w, h, g.data());
+                }
+                if (albedo && !p.albedo.empty()) save_image_rgba32f(p.albedo, w, h, a.data());
+                if (normal && !p.normal.empty()) save_image_rgba32f(p.normal, w, h, nn.data());
+            }
+        }
+    });
+}
+
+int btrc_closest_hit(btrc_scene_t *s, int memory, const float *o_med, const float *d_t1, int32_t n, uint32_t *flag, uint32_t *detail) {
+    (void)memory;
+    return guarded([&] {
+        check_scene(s);
+        if (n <= 0) return;
+        const size_t N = (size_t)n;
+        s->scene->upload_device();
+        DeviceBuffer o(16 * N), d(16 * N), f(4 * N), det(16 * N);
+        copy_any(o.ptr, o_med, 16 * N);
+        copy_any(d.ptr, d_t1, 16 * N);
+        LaunchCfg cfg;
+        cfg.sm_count = btrc_device_sm_count();
+        launch_trace_batch(cfg, s->scene->dev, o.as<float4>(), d.as<float4>(), n, f.as<uint32_t>(), det.as<uint4>(), nullptr);
+        BTRC_CUDA(cudaDeviceSynchronize());
+        BTRC_CUDA(cudaGetLastError());
+        copy_any(flag, f.ptr, 4 * N);
+        copy_any(detail, det.ptr, 16 * N);
+    });
+}
+
+int btrc_any_hit(btrc_scene_t *s, int memory, const float *o_med, const float *d_t1, int32_t n, uint8_t *occluded) {
+    (void)memory;
+    return guarded([&] {
+        check_scene(s);
+        if (n <= 0) return;
+        const size_t N = (size_t)n;
+        s->scene->upload_device();
+        DeviceBuffer o(16 * N), d(16 * N), occ(N);
+        copy_any(o.ptr, o_med, 16 * N);
+        copy_any(d.ptr, d_t1, 16 * N);
+        LaunchCfg cfg;
+        cfg.sm_count = btrc_device_sm_count();
+        launch_anyhit_batch(cfg, s->scene->dev, o.as<float4>(), d.as<float4>(), n, occ.as<uint8_t>(), nullptr);
+        BTRC_CUDA(cudaDeviceSynchronize());
+        BTRC_CUDA(cudaGetLastError());
+        copy_any(occluded, occ.ptr, N);
+    });
+}
+
+int btrc_generate(btrc_scene_t *s, int memory, int64_t first, int32_t n, float *o_med, float *d_t1, uint32_t *pixel, float *beta_depth,
+                  float *path_rad, uint64_t *rng, float *ble) {
+    (void)memory;
+    return guarded([&] {
+        check_scene(s);
+        if (n <= 0) return;
+        Renderer &r = s->r();
+        r.stage_generate(first, n);
+        download_paths(r, 0, n, s->scene->width, o_med, d_t1, pixel, beta_depth, path_rad, rng, ble);
+    });
+}
+
+int btrc_shade(btrc_scene_t *s, int memory, int32_t n, const float *o_med, const float *d_t1, const uint32_t *pixel, const float *beta_depth,
+               const float *path_rad, const uint64_t *rng, const float *ble, const uint32_t *flag, const uint32_t *detail, int32_t *n_next,
+               float *next_o_med, float *next_d_t1, uint32_t *next_pixel, float *next_beta_depth, float *next_path_rad, uint64_t *next_rng,
+               float *next_ble, int32_t *n_shadow, uint32_t *shadow_pixel, float *shadow_beta_li, float *shadow_o_med, float *shadow_d_t1) {
+    (void)memory;
+    return guarded([&] {
+        check_scene(s);
+        *n_next = 0; *n_shadow = 0;
+        if (n <= 0) return;
+        Renderer &r = s->r();
+        const int W = s->scene->width;
+        upload_paths(r, 0, n, W, o_med, d_t1, pixel, beta_depth, path_rad, rng, ble);
+        copy_any(r.hits().flag, flag, 4 * (size_t)n);
+        copy_any(r.hits().detail, detail, 16 * (size_t)n);
+        int nn = 0, ns = 0;
+        r.stage_shade(n, &nn, &ns);
+        *n_next = nn; *n_shadow = ns;
+        if (nn) download_paths(r, 1, nn, W, next_o_med, next_d_t1, next_pixel, next_beta_depth, next_path_rad, next_rng, next_ble);
+        if (ns) {
+            const size_t N = (size_t)ns;
+            std::vector<float4> b(N);
+            std::vector<uint32_t> px(2 * N);
+            copy_any(b.data(), r.shadows().beta_li, 16 * N);
+            for (size_t i = 0; i < N; ++i) {
+                uint32_t idx;
+                std::memcpy(&idx, &b[i].w, 4);
+                px[2 * i] = idx % (uint32_t)W; px[2 * i + 1] = idx / (uint32_t)W;
+                b[i].w = 1.0f;  // soa.cpp:112
+            }
+            copy_any(shadow_beta_li, b.data(), 16 * N);
+            copy_any(shadow_pixel, px.data(), 8 * N);
+            copy_any(shadow_o_med, r.shadows().ray_o, 16 * N);
+            copy_any(shadow_d_t1, r.shadows().ray_d, 16 * N);
+        }
+    });
+}
+
+int btrc_shadow(btrc_scene_t *s, int memory, int32_t n, const uint32_t *shadow_pixel, const float *shadow_beta_li, const float *shadow_o_med,
+                const float *shadow_d_t1) {
+    (void)memory;
+    return guarded([&] {
+        check_scene(s);
+        if (n <= 0) return;
+        Renderer &r = s->r();
+        const size_t N = (size_t)n;
+        const int W = s->scene->width;
+        std::vector<float4> b(N);
+        std::vector<uint32_t> px(2 * N);
+        copy_any(b.data(), shadow_beta_li, 16 * N);
+        copy_any(px.data(), shadow_pixel, 8 * N);
+        for (size_t i = 0; i < N; ++i) {
+            const uint32_t idx = px[2 * i + 1] * (uint32_t)W + px[2 * i];
+            std::memcpy(&b[i].w, &idx, 4);
+        }
+        copy_any(r.shadows().beta_li, b.data(), 16 * N);
+        copy_any(r.shadows().ray_o, shadow_o_med, 16 * N);
+        copy_any(r.shadows().ray_d, shadow_d_t1, 16 * N);
+        r.stage_shadow(n);
+    });
+}
+
+int btrc_geometry_tables(btrc_scene_t *s, int32_t geometry_id, int32_t *n_triangles, float *out24) {
+    return guarded([&] {
+        check_scene(s);
+        if (geometry_id < 0 || geometry_id >= (int)s->scene->meshes.size()) throw Error("geometry id out of range");
+        const MeshData &m = s->scene->meshes[geometry_id];
+        if (n_triangles) *n_triangles = m.ntri;
+        if (!out24) return;
+        for (int i = 0; i < m.ntri; ++i) {
+            float *o = out24 + 24 * (size_t)i;
+            std::memcpy(o, &m.gx_ua[4 * i], 16); std::memcpy(o + 4, &m.gy_uba[4 * i], 16); std::memcpy(o + 8, &m.gz_uca[4 * i], 16);
+            std::memcpy(o + 12, &m.sn_va[4 * i], 16); std::memcpy(o + 16, &m.sn_vba[4 * i], 16); std::memcpy(o + 20, &m.sn_vca[4 * i], 16);
+        }
+    });
+}
+
+int btrc_instance_transform(btrc_scene_t *s, int32_t instance_id, float *mat12, float *inv12) {
+    return guarded([&] {
+        check_scene(s);
+        if (instance_id < 0 || instance_id >= (int)s->scene->instance_info.size()) throw Error("instance id out of range");
+        std::memcpy(mat12, s->scene->instance_info[instance_id].mat, 48);
+        std::memcpy(inv12, s->scene->instance_info[instance_id].inv, 48);
+    });
+}
+
+}  // extern "C"

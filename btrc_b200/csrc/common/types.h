@@ -1,0 +1,166 @@
+// Plain-old-data structures shared by the host runtime and the sm_100a kernels.
+//
+// Queue layout ("path-state pool"): structure of arrays of 16-byte vectors so that every load and
+// store in the wavefront kernels is one coalesced LDG.128/STG.128 per lane.  The reference's SoA
+// (src/builtin/btrc/builtin/renderer/wavefront/soa.h:8-37) is kept field for field, except that the
+// pixel coordinate (uint2 there) rides in the spare .w lane of the radiance vector.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace btrc {
+
+constexpr float kPi = 3.1415926535f;          // reference: utils/math/scalar.h:8
+constexpr float kMaxFloat = 3.402823466e+38f;  // reference: utils/math/scalar.h:7
+
+// reference: wavefront/common.h:12-14
+constexpr uint32_t kFlagHasIntersection = 0b01u << 30;
+constexpr uint32_t kFlagHasScattering = 0b10u << 30;
+constexpr uint32_t kFlagInstanceMask = ~0u << 2 >> 2;
+
+enum MaterialType : int {
+    MAT_DIFFUSE = 0,
+    MAT_BLACK = 1,
+    MAT_COUNT
+};
+
+enum TextureType : int { TEX_CONSTANT = 0 };
+
+struct TextureDesc {
+    int type;
+    float value[3];
+};
+
+struct MaterialDesc {
+    int type;
+    int color_tex;
+    int normal_tex;
+    int shadow_terminator;
+};
+
+// reference: core/geometry.h:10-19 -- six float4 tables per mesh
+struct GeometryInfo {
+    const float4 *gx_ua;    // geometry ex | tex u of vertex a
+    const float4 *gy_uba;   // geometry ey | u_b - u_a
+    const float4 *gz_uca;   // geometry ez | u_c - u_a
+    const float4 *sn_va;    // shading normal a | tex v of a
+    const float4 *sn_vba;   // n_b - n_a | v_b - v_a
+    const float4 *sn_vca;   // n_c - n_a | v_c - v_a
+    // light sampling tables (geometry/triangle_mesh.cpp:108-164)
+    const float *positions;        // 9 floats per triangle: a, b-a, c-a
+    const float2 *area_alias;      // (accept_prob, bit-cast another_idx)
+    int prim_count;
+    float total_area;
+};
+
+// reference: core/scene.h:21-30.  Matrices are row-major 3x4 (the last row of an affine transform is 0 0 0 1).
+struct InstanceInfo {
+    int geometry_id;
+    int material_id;
+    int light_id;
+    float mat[12];  // local_to_world
+    float inv[12];  // world_to_local
+    uint32_t inner_medium_id;
+    uint32_t outer_medium_id;
+    uint32_t flag;
+};
+
+struct LightInfo {  // MeshLight (builtin/light/mesh_light.cpp)
+    int instance_id;
+    float intensity[3];
+    float inv_scale2;  // 1 / (scale_ * scale_)
+};
+
+struct CameraInfo {  // builtin/camera/pinhole.cpp:55-77
+    float eye[3];
+    float left_bottom_corner[3];
+    float film_x[3];
+    float film_y[3];
+};
+
+struct RenderParams {  // builtin/renderer/wavefront.h:13-27
+    int width, height;
+    int spp;
+    int min_depth, max_depth;
+    float rr_threshold, rr_cont_prob;
+    int tile;
+    int albedo, normal;
+    int filter_type;  // 0 box, 1 gaussian
+    float filter_radius;
+    float filter_step;  // 2 * radius / GRID_SIZE
+};
+
+// Binary BVH over world-space triangles, two children per 64-byte node:
+//   n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   n1 = same for child 1
+//   nz = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)   meta = (ref0, ref1, -, -) as int bits
+// ref >= 0: inner node index; ref < 0: leaf, ~ref = (first_triangle << 3) | (count - 1).
+struct BvhDevice {
+    const float4 *nodes;
+    const float4 *tris;      // 3 float4 per triangle: (p0 | n.x) (e1 | n.y) (e2 | n.z)
+    const uint2 *tri_ids;    // (instance, primitive) per triangle slot
+    int root_ref;            // reference of the root (a leaf ref when the scene has <= leaf-size triangles)
+    int n_tris;
+};
+
+struct SceneDevice {
+    BvhDevice bvh;
+    const InstanceInfo *instances;
+    const GeometryInfo *geometries;
+    const MaterialDesc *materials;
+    const TextureDesc *textures;
+    const LightInfo *lights;
+    int n_instances, n_lights;
+    CameraInfo camera;
+    const float2 *filter_alias;  // gaussian filter alias table (256*256)
+    uint32_t vol_prim_medium_id;
+    float world_diagonal;
+};
+
+// Path-state pool (one set = "current", one set = "next").
+struct PathQueue {
+    float4 *ray_o;   // o.xyz | medium id bits
+    float4 *ray_d;   // d.xyz | t1
+    float4 *beta;    // beta.rgb | depth bits
+    float4 *rad;     // path radiance rgb | pixel index bits (y * W + x)
+    ulonglong2 *rng; // PCG state, inc
+    float4 *ble;     // beta_le.rgb | bsdf pdf (negative: delta)
+};
+
+struct HitQueue {
+    uint32_t *flag;  // instance id | kFlagHasIntersection | kFlagHasScattering
+    uint4 *detail;   // t bits, primitive id, u bits, v bits
+};
+
+struct ShadowQueue {
+    float4 *ray_o;   // o.xyz | medium id bits
+    float4 *ray_d;   // d.xyz | t1
+    float4 *beta_li; // beta_li.rgb | pixel index bits
+};
+
+struct FilmDevice {
+    float *radiance;  // W*H*4 (float4 stride, .w unused -- core/film.cpp:55-72)
+    float *weight;    // W*H
+    float *albedo;    // W*H*4 or null
+    float *normal;    // W*H*4 or null
+};
+
+// Device-resident wave control block: lets the host enqueue whole iterations without reading anything back.
+struct WaveCtl {
+    int n_active;       // states processed by trace/shade this iteration
+    int n_survivors;    // states carried over from the previous iteration (slots [0, n_survivors))
+    int n_new;          // camera paths generated this iteration (slots [n_survivors, n_active))
+    int n_next;         // shade's output counter (reference: StateCounters::active_state_counter)
+    int n_shadow;       // shade's shadow-ray counter (reference: StateCounters::shadow_ray_counter)
+    int n_shadow_cur;   // shadow rays to trace this iteration
+    int trace_cursor;   // dynamic work cursors for the persistent traversal kernels
+    int shadow_cursor;
+    long long gen_base;   // first camera-path index generated this iteration
+    long long cursor;     // next camera-path index
+    long long end;        // one past the last camera-path index of this render
+    int pool;             // state_count
+    int done;
+    // statistics (SURVEY 8d event counts)
+    unsigned long long n_gen, n_closest, n_hit, n_next_total, n_shadow_total, n_shadow_miss, n_splat, n_iter;
+};
+
+}  // namespace btrc

@@ -1,0 +1,37 @@
+// Launch wrappers for the wavefront stages (definitions in the .cu files of this directory).
+// One stage of the reference = one kernel here:
+//   generate_kernel (wavefront/generate.cpp:33-87)            -> launch_generate
+//   __raygen__/__closesthit__/__miss__trace (trace.cpp:38-78)  -> launch_trace
+//   shade_kernel (shade.cpp:29-235)                            -> launch_shade
+//   __raygen__/__miss__shadow (shadow.cpp:24-76)               -> launch_shadow
+//   preview kernels (preview.cpp:28-80)                        -> launch_resolve
+// plus launch_prepare, the device-side replacement of the host bookkeeping in wavefront.cpp:227-306.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../common/types.h"
+
+namespace btrc {
+
+struct LaunchCfg {
+    int sm_count = 148;
+};
+
+void launch_prepare(WaveCtl *ctl, cudaStream_t stream);
+void launch_generate(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, FilmDevice film,
+                     WaveCtl *ctl, cudaStream_t stream);
+void launch_trace(const LaunchCfg &cfg, const SceneDevice &scene, PathQueue cur, HitQueue hit, WaveCtl *ctl, cudaStream_t stream);
+void launch_shade(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, HitQueue hit,
+                  PathQueue next, ShadowQueue shadow, FilmDevice film, WaveCtl *ctl, cudaStream_t stream);
+void launch_shadow(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, ShadowQueue shadow, FilmDevice film,
+                   WaveCtl *ctl, cudaStream_t stream);
+// out = value.xyz / weight (normalise == 1: renormalise as a direction); out.w = 1
+void launch_resolve(int width, int height, const float *value, const float *weight, float *out, int normalise, cudaStream_t stream);
+
+// Stage-level entry points for tests on explicit batches (count given by the host; no WaveCtl).
+void launch_trace_batch(const LaunchCfg &cfg, const SceneDevice &scene, const float4 *ray_o, const float4 *ray_d, int n,
+                        uint32_t *flag, uint4 *detail, cudaStream_t stream);
+void launch_anyhit_batch(const LaunchCfg &cfg, const SceneDevice &scene, const float4 *ray_o, const float4 *ray_d, int n,
+                         uint8_t *occluded, cudaStream_t stream);
+
+}  // namespace btrc

@@ -1,0 +1,210 @@
+#include "mesh.h"
+
+#include <cstdlib>
+#include <fstream>
+#include <sstream>
+
+#include "node.h"
+
+namespace btrc {
+
+std::vector<AliasUnit> build_alias_table(const std::vector<float> &probs) {  // utils/math/alias.cpp:13-57
+    if (probs.empty()) throw Error("alias table: empty input");
+    float sum = 0.0f;
+    for (float p : probs) sum = sum + p;
+    const float ratio = probs.size() / sum;
+    std::vector<uint32_t> overs, unders;
+    std::vector<AliasUnit> units(probs.size());
+    for (uint32_t i = 0; i < (uint32_t)units.size(); ++i) {
+        const float p = probs[i] * ratio;
+        units[i].accept_prob = p;
+        units[i].another_idx = i;
+        if (p > 1) overs.push_back(i);
+        else if (p < 1) unders.push_back(i);
+    }
+    while (!overs.empty() && !unders.empty()) {
+        const uint32_t over = overs.back(), under = unders.back();
+        overs.pop_back();
+        unders.pop_back();
+        units[over].accept_prob -= 1 - units[under].accept_prob;
+        units[under].another_idx = over;
+        if (units[over].accept_prob > 1) overs.push_back(over);
+        else if (units[over].accept_prob < 1) unders.push_back(over);
+    }
+    for (auto i : overs) units[i].accept_prob = 1;
+    for (auto i : unders) units[i].accept_prob = 1;
+    return units;
+}
+
+namespace {
+
+struct Corner { int v, t, n; };
+
+inline void skip_space(const char *&p) { while (*p == ' ' || *p == '\t') ++p; }
+
+bool parse_corner(const char *&p, Corner &c, int nv, int nt, int nn) {
+    skip_space(p);
+    if (*p == '\0' || *p == '\n' || *p == '\r' || *p == '#') return false;
+    char *e;
+    long v = std::strtol(p, &e, 10);
+    if (e == p) return false;
+    p = e;
+    c.v = v > 0 ? int(v - 1) : nv + int(v);
+    c.t = c.n = -1;
+    if (*p == '/') {
+        ++p;
+        if (*p != '/') {
+            long t = std::strtol(p, &e, 10);
+            if (e != p) { c.t = t > 0 ? int(t - 1) : nt + int(t); p = e; }
+        }
+        if (*p == '/') {
+            ++p;
+            long n = std::strtol(p, &e, 10);
+            if (e != p) { c.n = n > 0 ? int(n - 1) : nn + int(n); p = e; }
+        }
+    }
+    return true;
+}
+
+Vec3 frame_from_z_x(Vec3 z) {  // Frame::from_z(nor).x -- utils/math/frame.cpp:45-57 (result is not normalised)
+    Vec3 nz = normalize(z), ny;
+    if (1 - std::fabs(nz.x) < 0.1f) ny = cross(nz, Vec3(0, 1, 0));
+    else ny = cross(nz, Vec3(1, 0, 0));
+    return cross(nz, ny);
+}
+
+Vec3 triangle_dpdu(Vec3 B_A, Vec3 C_A, Vec2 b_a, Vec2 c_a, Vec3 nor) {  // utils/math/triangle.h:8-22
+    const float m00 = b_a.x, m01 = b_a.y, m10 = c_a.x, m11 = c_a.y;
+    const float det = m00 * m11 - m01 * m10;
+    if (det == 0.0f) return frame_from_z_x(nor);
+    const float inv_det = 1 / det;
+    return normalize(m11 * inv_det * B_A - m01 * inv_det * C_A);
+}
+
+}  // namespace
+
+MeshData load_triangle_mesh(const std::string &filename, bool to_unit_cube) {
+    const std::string text = read_text_file(filename);
+    std::vector<Vec3> vs, vns;
+    std::vector<Vec2> vts;
+    std::vector<Corner> corners;  // 3 per triangle, face order
+    std::vector<Corner> face;
+    const char *p = text.c_str();
+    while (*p) {
+        skip_space(p);
+        if (p[0] == 'v' && (p[1] == ' ' || p[1] == '\t')) {
+            p += 2;
+            char *e;
+            float x = (float)std::strtod(p, &e); p = e;
+            float y = (float)std::strtod(p, &e); p = e;
+            float z = (float)std::strtod(p, &e); p = e;
+            vs.emplace_back(x, y, z);
+        } else if (p[0] == 'v' && p[1] == 'n' && (p[2] == ' ' || p[2] == '\t')) {
+            p += 3;
+            char *e;
+            float x = (float)std::strtod(p, &e); p = e;
+            float y = (float)std::strtod(p, &e); p = e;
+            float z = (float)std::strtod(p, &e); p = e;
+            vns.emplace_back(x, y, z);
+        } else if (p[0] == 'v' && p[1] == 't' && (p[2] == ' ' || p[2] == '\t')) {
+            p += 3;
+            char *e;
+            float x = (float)std::strtod(p, &e); p = e;
+            float y = (float)std::strtod(p, &e); p = e;
+            vts.push_back(Vec2{x, y});
+        } else if (p[0] == 'f' && (p[1] == ' ' || p[1] == '\t')) {
+            p += 2;
+            face.clear();
+            Corner c;
+            while (parse_corner(p, c, (int)vs.size(), (int)vts.size(), (int)vns.size())) face.push_back(c);
+            for (auto &fc : face)
+                if (fc.v < 0 || fc.v >= (int)vs.size()) throw Error("invalid obj vertex index: out of range");
+            if (face.size() == 3) {
+                corners.insert(corners.end(), face.begin(), face.end());
+            } else if (face.size() == 4) {
+                // tinyobj quad rule (lib/tinyobjloader/tiny_obj_loader.h:1429-1520): split along the shorter diagonal
+                const Vec3 v0 = vs[face[0].v], v1 = vs[face[1].v], v2 = vs[face[2].v], v3 = vs[face[3].v];
+                const Vec3 e02 = v2 - v0, e13 = v3 - v1;
+                const float sqr02 = e02.x * e02.x + e02.y * e02.y + e02.z * e02.z;
+                const float sqr13 = e13.x * e13.x + e13.y * e13.y + e13.z * e13.z;
+                if (sqr02 < sqr13) {
+                    for (int k : {0, 1, 2, 0, 2, 3}) corners.push_back(face[k]);
+                } else {
+                    for (int k : {0, 1, 3, 1, 2, 3}) corners.push_back(face[k]);
+                }
+            } else if (face.size() > 4) {
+                // The reference ear-clips larger polygons; a fan gives the same surface for convex faces.
+                for (size_t k = 1; k + 1 < face.size(); ++k) {
+                    corners.push_back(face[0]); corners.push_back(face[k]); corners.push_back(face[k + 1]);
+                }
+            }
+        }
+        while (*p && *p != '\n') ++p;
+        if (*p == '\n') ++p;
+    }
+
+    if (to_unit_cube) {  // triangle_mesh_loader.cpp:193-213
+        Vec3 lower(3.402823466e+38f), upper(-3.402823466e+38f);
+        for (auto &v : vs) { lower = vmin(lower, v); upper = vmax(upper, v); }
+        const Vec3 extent = upper - lower;
+        const float extent_max = std::max(extent.x, std::max(extent.y, extent.z));
+        const float scale = extent_max > 0 ? 1 / extent_max : 1.0f;
+        for (auto &v : vs) v = scale * (v - 0.5f * (lower + upper));
+    }
+
+    MeshData m;
+    m.ntri = (int)(corners.size() / 3);
+    if (m.ntri == 0) throw Error("obj file has no faces: " + filename);
+    const size_t nt = (size_t)m.ntri;
+    m.pos.resize(3 * nt);
+    m.gx_ua.resize(4 * nt); m.gy_uba.resize(4 * nt); m.gz_uca.resize(4 * nt);
+    m.sn_va.resize(4 * nt); m.sn_vba.resize(4 * nt); m.sn_vca.resize(4 * nt);
+    m.a_ba_ca.resize(9 * nt);
+    std::vector<float> areas(nt);
+    for (size_t i = 0; i < nt; ++i) {
+        const Corner *c = &corners[3 * i];
+        const Vec3 a = vs[c[0].v], b = vs[c[1].v], cc = vs[c[2].v];
+        m.pos[3 * i] = a; m.pos[3 * i + 1] = b; m.pos[3 * i + 2] = cc;
+        const Vec3 geo_z = normalize(cross(b - a, cc - a));  // loader.cpp:86
+        Vec3 sz[3];
+        Vec2 tc[3];
+        for (int k = 0; k < 3; ++k) {
+            if (c[k].n < 0) sz[k] = geo_z;
+            else {
+                if (c[k].n >= (int)vns.size()) throw Error("invalid obj normal index: out of range");
+                sz[k] = vns[c[k].n];
+                if (sz[k].x == 0.0f && sz[k].y == 0.0f && sz[k].z == 0.0f) sz[k] = geo_z;
+            }
+            if (c[k].t < 0) tc[k] = Vec2{0, 0};
+            else {
+                if (c[k].t >= (int)vts.size()) throw Error("invalid obj tex coord index: out of range");
+                tc[k] = vts[c[k].t];
+            }
+        }
+        const Vec3 gx = triangle_dpdu(b - a, cc - a, Vec2{tc[1].x - tc[0].x, tc[1].y - tc[0].y},
+                                      Vec2{tc[2].x - tc[0].x, tc[2].y - tc[0].y}, geo_z);
+        const Vec3 gz = geo_z;
+        const Vec3 gy = normalize(cross(gz, gx));  // triangle_mesh.cpp:52
+        auto put = [&](std::vector<float> &dst, Vec3 v, float w) {
+            dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = w;
+        };
+        put(m.gx_ua, gx, tc[0].x);
+        put(m.gy_uba, gy, tc[1].x - tc[0].x);
+        put(m.gz_uca, gz, tc[2].x - tc[0].x);
+        put(m.sn_va, sz[0], tc[0].y);
+        put(m.sn_vba, sz[1] - sz[0], tc[1].y - tc[0].y);
+        put(m.sn_vca, sz[2] - sz[0], tc[2].y - tc[0].y);
+        const Vec3 ba = b - a, ca = cc - a;
+        areas[i] = 0.5f * length(cross(ba, ca));  // triangle.h:24-27
+        float *o = &m.a_ba_ca[9 * i];
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = ba.x; o[4] = ba.y; o[5] = ba.z; o[6] = ca.x; o[7] = ca.y; o[8] = ca.z;
+    }
+    m.area_alias = build_alias_table(areas);
+    float total = 0.0f;
+    for (float a : areas) total += a;
+    m.total_area = total;
+    for (auto &v : vs) m.bbox.extend(v);  // bbox over all file positions (triangle_mesh.cpp:168-170)
+    return m;
+}
+
+}  // namespace btrc

@@ -1,0 +1,181 @@
+#include "renderer.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace btrc {
+
+namespace {
+constexpr int kLag = 4;  // iterations kept in flight ahead of the host's view of the counters
+}
+
+template <typename T>
+T *Renderer::alloc(size_t n) {
+    bufs_.emplace_back(n * sizeof(T));
+    return bufs_.back().as<T>();
+}
+
+Renderer::Renderer(Scene &scene, int state_count_override) : scene_(scene) {
+    int dev = 0;
+    BTRC_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    BTRC_CUDA(cudaGetDeviceProperties(&prop, dev));
+    cfg_.sm_count = prop.multiProcessorCount;
+    pool_ = state_count_override > 0 ? state_count_override : scene.renderer.state_count;
+    if (pool_ <= 0) throw Error("state_count must be positive");
+    BTRC_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    BTRC_CUDA(cudaEventCreate(&ev_begin_));
+    BTRC_CUDA(cudaEventCreate(&ev_end_));
+    for (auto &e : snap_ev_) BTRC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+
+    const size_t P = (size_t)pool_;
+    for (int k = 0; k < 2; ++k) {
+        q_[k].ray_o = alloc<float4>(P);
+        q_[k].ray_d = alloc<float4>(P);
+        q_[k].beta = alloc<float4>(P);
+        q_[k].rad = alloc<float4>(P);
+        q_[k].rng = alloc<ulonglong2>(P);
+        q_[k].ble = alloc<float4>(P);
+    }
+    hit_.flag = alloc<uint32_t>(P);
+    hit_.detail = alloc<uint4>(P);
+    shadow_.ray_o = alloc<float4>(P);
+    shadow_.ray_d = alloc<float4>(P);
+    shadow_.beta_li = alloc<float4>(P);
+
+    const size_t npix = (size_t)scene.width * scene.height;
+    film_.radiance = alloc<float>(4 * npix);
+    film_.weight = alloc<float>(npix);
+    film_.albedo = scene.renderer.albedo ? alloc<float>(4 * npix) : nullptr;
+    film_.normal = scene.renderer.normal ? alloc<float>(4 * npix) : nullptr;
+    ctl_ = alloc<WaveCtl>(1);
+    BTRC_CUDA(cudaMallocHost(&ctl_host_, sizeof(WaveCtl) * 8));
+    clear_film();
+}
+
+Renderer::~Renderer() {
+    if (ctl_host_) cudaFreeHost(ctl_host_);
+    for (auto &e : snap_ev_) if (e) cudaEventDestroy(e);
+    if (ev_begin_) cudaEventDestroy(ev_begin_);
+    if (ev_end_) cudaEventDestroy(ev_end_);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+void Renderer::clear_film() {
+    const size_t npix = (size_t)scene_.width * scene_.height;
+    BTRC_CUDA(cudaMemsetAsync(film_.radiance, 0, 4 * npix * sizeof(float), stream_));
+    BTRC_CUDA(cudaMemsetAsync(film_.weight, 0, npix * sizeof(float), stream_));
+    if (film_.albedo) BTRC_CUDA(cudaMemsetAsync(film_.albedo, 0, 4 * npix * sizeof(float), stream_));
+    if (film_.normal) BTRC_CUDA(cudaMemsetAsync(film_.normal, 0, 4 * npix * sizeof(float), stream_));
+    stats_ = RenderStats();
+}
+
+void Renderer::render_range(long long begin, long long end) {
+    if (begin < 0 || end < begin || end > total_paths()) throw Error("render_range: path range out of bounds");
+    const RenderParams params = scene_.render_params();
+    WaveCtl init;
+    std::memset(&init, 0, sizeof(init));
+    init.cursor = begin;
+    init.end = end;
+    init.pool = pool_;
+    BTRC_CUDA(cudaMemcpyAsync(ctl_, &init, sizeof(init), cudaMemcpyHostToDevice, stream_));
+    BTRC_CUDA(cudaEventRecord(ev_begin_, stream_));
+
+    int cur = 0;
+    long long iter = 0;
+    bool done = false;
+    WaveCtl last = init;
+    while (!done) {
+        launch_prepare(ctl_, stream_);
+        launch_generate(cfg_, scene_.dev, params, q_[cur], film_, ctl_, stream_);
+        launch_trace(cfg_, scene_.dev, q_[cur], hit_, ctl_, stream_);
+        launch_shade(cfg_, scene_.dev, params, q_[cur], hit_, q_[cur ^ 1], shadow_, film_, ctl_, stream_);
+        launch_shadow(cfg_, scene_.dev, params, shadow_, film_, ctl_, stream_);
+        const int slot = (int)(iter % 8);
+        BTRC_CUDA(cudaMemcpyAsync(&ctl_host_[slot], ctl_, sizeof(WaveCtl), cudaMemcpyDeviceToHost, stream_));
+        BTRC_CUDA(cudaEventRecord(snap_ev_[slot], stream_));
+        cur ^= 1;
+        ++iter;
+        if (iter >= kLag) {
+            const int old = (int)((iter - kLag) % 8);
+            BTRC_CUDA(cudaEventSynchronize(snap_ev_[old]));
+            last = ctl_host_[old];
+            // the snapshot is taken after shade: the wave is finished when nothing survived and nothing is left to generate
+            if (last.n_next == 0 && last.cursor >= last.end) done = true;
+        }
+    }
+    BTRC_CUDA(cudaEventRecord(ev_end_, stream_));
+    BTRC_CUDA(cudaStreamSynchronize(stream_));
+    BTRC_CUDA(cudaGetLastError());
+    // final counters (the drained iterations after `done` are empty)
+    WaveCtl fin;
+    BTRC_CUDA(cudaMemcpy(&fin, ctl_, sizeof(fin), cudaMemcpyDeviceToHost));
+    float ms = 0;
+    BTRC_CUDA(cudaEventElapsedTime(&ms, ev_begin_, ev_end_));
+    stats_.n_gen += fin.n_gen;
+    stats_.n_closest += fin.n_closest;
+    stats_.n_hit += fin.n_hit;
+    stats_.n_next += fin.n_next_total + (unsigned long long)fin.n_next;
+    stats_.n_shadow += fin.n_shadow_total + (unsigned long long)fin.n_shadow;
+    stats_.n_shadow_miss += fin.n_shadow_miss;
+    stats_.n_splat += fin.n_splat;
+    stats_.n_iter += fin.n_iter;
+    stats_.render_ms = ms;
+}
+
+void Renderer::stage_generate(long long first, int n) {
+    if (n > pool_) throw Error("stage batch larger than state_count");
+    WaveCtl c;
+    std::memset(&c, 0, sizeof(c));
+    c.n_new = n; c.n_survivors = 0; c.gen_base = first; c.n_active = n; c.pool = pool_;
+    BTRC_CUDA(cudaMemcpyAsync(ctl_, &c, sizeof(c), cudaMemcpyHostToDevice, stream_));
+    launch_generate(cfg_, scene_.dev, scene_.render_params(), q_[0], film_, ctl_, stream_);
+    BTRC_CUDA(cudaStreamSynchronize(stream_));
+    BTRC_CUDA(cudaGetLastError());
+}
+
+void Renderer::stage_trace(int n) {
+    if (n > pool_) throw Error("stage batch larger than state_count");
+    WaveCtl c;
+    std::memset(&c, 0, sizeof(c));
+    c.n_active = n; c.pool = pool_;
+    BTRC_CUDA(cudaMemcpyAsync(ctl_, &c, sizeof(c), cudaMemcpyHostToDevice, stream_));
+    launch_trace(cfg_, scene_.dev, q_[0], hit_, ctl_, stream_);
+    BTRC_CUDA(cudaStreamSynchronize(stream_));
+    BTRC_CUDA(cudaGetLastError());
+}
+
+void Renderer::stage_shade(int n, int *n_next, int *n_shadow) {
+    if (n > pool_) throw Error("stage batch larger than state_count");
+    WaveCtl c;
+    std::memset(&c, 0, sizeof(c));
+    c.n_active = n; c.pool = pool_;
+    BTRC_CUDA(cudaMemcpyAsync(ctl_, &c, sizeof(c), cudaMemcpyHostToDevice, stream_));
+    launch_shade(cfg_, scene_.dev, scene_.render_params(), q_[0], hit_, q_[1], shadow_, film_, ctl_, stream_);
+    BTRC_CUDA(cudaMemcpyAsync(&c, ctl_, sizeof(c), cudaMemcpyDeviceToHost, stream_));
+    BTRC_CUDA(cudaStreamSynchronize(stream_));
+    BTRC_CUDA(cudaGetLastError());
+    *n_next = c.n_next;
+    *n_shadow = c.n_shadow;
+}
+
+void Renderer::stage_shadow(int n) {
+    if (n > pool_) throw Error("stage batch larger than state_count");
+    WaveCtl c;
+    std::memset(&c, 0, sizeof(c));
+    c.n_shadow = n; c.pool = pool_;
+    BTRC_CUDA(cudaMemcpyAsync(ctl_, &c, sizeof(c), cudaMemcpyHostToDevice, stream_));
+    launch_shadow(cfg_, scene_.dev, scene_.render_params(), shadow_, film_, ctl_, stream_);
+    BTRC_CUDA(cudaStreamSynchronize(stream_));
+    BTRC_CUDA(cudaGetLastError());
+}
+
+void Renderer::resolve(float *d_color, float *d_albedo, float *d_normal) {
+    if (d_color) launch_resolve(scene_.width, scene_.height, film_.radiance, film_.weight, d_color, 0, stream_);
+    if (d_albedo && film_.albedo) launch_resolve(scene_.width, scene_.height, film_.albedo, film_.weight, d_albedo, 0, stream_);
+    if (d_normal && film_.normal) launch_resolve(scene_.width, scene_.height, film_.normal, film_.weight, d_normal, 1, stream_);
+    BTRC_CUDA(cudaStreamSynchronize(stream_));
+    BTRC_CUDA(cudaGetLastError());
+}
+
+}  // namespace btrc

@@ -1,0 +1,68 @@
+// Wavefront path tracer host loop ("wfpt" renderer).
+//
+// Replaces builtin/renderer/wavefront.cpp:98-194 (commit: film + queue allocation) and :205-325 (render loop).
+// Differences by design (results are unaffected, SURVEY B.1: every path owns its RNG stream):
+//   * the pool is refilled every iteration and all bookkeeping lives in a device-resident WaveCtl block, so the
+//     host enqueues iterations ahead of the GPU and never blocks on a per-iteration counter read-back;
+//   * a render can cover any contiguous range of camera-path indices, which is how sample streams are
+//     partitioned across GPUs (the caller sum-reduces the film buffers and resolves once).
+#pragma once
+#include <cstdint>
+
+#include "../device/kernels.h"
+#include "scene.h"
+
+namespace btrc {
+
+struct RenderStats {
+    uint64_t n_gen = 0, n_closest = 0, n_hit = 0, n_next = 0, n_shadow = 0, n_shadow_miss = 0, n_splat = 0, n_iter = 0;
+    double render_ms = 0;  // device time of the last render_range (CUDA events)
+};
+
+class Renderer {
+public:
+    explicit Renderer(Scene &scene, int state_count_override = 0);
+    ~Renderer();
+
+    void clear_film();
+    // Traces camera paths [begin, end) of the scene's path index space (Uniform mode: index = sample * W*H + pixel;
+    // Tile mode: index = pixel * spp + sample) and accumulates them into the film.
+    void render_range(long long begin, long long end);
+    // value / weight into caller-provided DEVICE buffers of W*H float4 (albedo/normal may be null).
+    void resolve(float *d_color, float *d_albedo, float *d_normal);
+
+    // ---- stage-level runs on the internal queues (tests / C-ABI stage entry points); n <= state_count
+    PathQueue &queue(int k) { return q_[k]; }
+    HitQueue &hits() { return hit_; }
+    ShadowQueue &shadows() { return shadow_; }
+    void stage_generate(long long first, int n);                  // fills queue(0)[0, n)
+    void stage_trace(int n);                                      // queue(0) -> hits()
+    void stage_shade(int n, int *n_next, int *n_shadow);          // queue(0) + hits() -> queue(1), shadows()
+    void stage_shadow(int n);                                     // shadows()[0, n) -> film
+    const LaunchCfg &launch_cfg() const { return cfg_; }
+
+    FilmDevice film() const { return film_; }
+    const RenderStats &stats() const { return stats_; }
+    cudaStream_t stream() const { return stream_; }
+    int state_count() const { return pool_; }
+    long long total_paths() const { return (long long)scene_.renderer.spp * scene_.width * scene_.height; }
+
+private:
+    Scene &scene_;
+    int pool_ = 0;
+    LaunchCfg cfg_;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev_begin_ = nullptr, ev_end_ = nullptr;
+    std::vector<DeviceBuffer> bufs_;
+    PathQueue q_[2]{};
+    HitQueue hit_{};
+    ShadowQueue shadow_{};
+    FilmDevice film_{};
+    WaveCtl *ctl_ = nullptr;        // device
+    WaveCtl *ctl_host_ = nullptr;   // pinned ring of snapshots
+    cudaEvent_t snap_ev_[8]{};
+    RenderStats stats_;
+    template <typename T> T *alloc(size_t n);
+};
+
+}  // namespace btrc

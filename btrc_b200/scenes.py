@@ -46,9 +46,11 @@ def write_obj(path, verts, faces, uvs=None, normals=None):
 
 
 def split_cornell_groups(obj_path=CORNELL_OBJ):
-    """Split the Cornell box OBJ (scenes/assets/cornell_box.obj) by `g` group.
+    """Split the Cornell box OBJ (scenes/assets/cornell_box.obj) into its eight objects.
 
-    Returns an ordered dict name -> (verts, faces) with faces re-indexed into the group's own vertex list.
+    The file names each object with `usemtl` BEFORE its faces but places the `g` line AFTER them for the two boxes,
+    so the split follows `usemtl`.  Returns an ordered dict name -> (verts, faces), faces re-indexed into the
+    object's own vertex list.
     """
     verts = []
     groups = {}
@@ -60,7 +62,7 @@ def split_cornell_groups(obj_path=CORNELL_OBJ):
                 continue
             if tok[0] == "v":
                 verts.append(tuple(np.float32(float(t)) for t in tok[1:4]))
-            elif tok[0] == "g":
+            elif tok[0] == "usemtl":
                 cur = tok[1]
                 groups.setdefault(cur, ([], []))
             elif tok[0] == "f":

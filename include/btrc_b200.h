@@ -1,0 +1,125 @@
+/* btrc_b200 -- C ABI of the B200-native wavefront render path (libbtrc_b200.so).
+ *
+ * The reference (AirGuanZ/Btrc) has no FFI: its CLI creates C++ objects through the factory and calls
+ * Renderer::render() (src/cli/main.cpp:17-81).  This header is the boundary a binding would use instead; every
+ * entry point names the reference interface it stands for.  Conventions: plain pointers and sizes only, no C++
+ * or torch types; every function returns 0 on success and non-zero on error, with the chained message (one
+ * context per line, like the reference's nested BtrcException printout, src/cli/main.cpp:97-104) available from
+ * btrc_last_error() on the calling thread.  One host thread drives one GPU (the current CUDA device).
+ *
+ * Buffers are caller-owned; `memory` says where they live: BTRC_HOST (pageable or pinned host memory) or
+ * BTRC_DEVICE (device memory of the current device, e.g. a torch tensor's data_ptr).
+ */
+#ifndef BTRC_B200_H
+#define BTRC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BTRC_HOST 0
+#define BTRC_DEVICE 1
+
+typedef struct btrc_scene btrc_scene_t;
+
+typedef struct btrc_scene_info {
+    int32_t width, height;        /* root["width"], root["height"]            (cli/main.cpp:50-51)          */
+    int32_t spp;                  /* renderer params                          (renderer/wavefront.h:13-27)  */
+    int32_t min_depth, max_depth;
+    int32_t state_count;
+    int32_t tile, albedo, normal;
+    int32_t n_instances, n_lights, n_triangles, n_materials;
+    int32_t bvh_depth;
+    float world_diagonal;         /* 1.2 * |bbox(scene + eye)|                (wavefront.cpp:138-139)       */
+    float bvh_build_seconds;
+} btrc_scene_info_t;
+
+typedef struct btrc_render_stats {
+    uint64_t n_gen;          /* camera paths generated                                         */
+    uint64_t n_closest;      /* closest-hit rays traced                                        */
+    uint64_t n_hit;          /* ... of which hit something                                     */
+    uint64_t n_next;         /* continuation states emitted by shade                           */
+    uint64_t n_shadow;       /* shadow rays emitted by shade                                   */
+    uint64_t n_shadow_miss;  /* ... of which reached the light                                 */
+    uint64_t n_splat;        /* radiance splats (3 float atomics each)                         */
+    uint64_t n_iter;         /* wavefront iterations                                           */
+    double render_ms;        /* device time of the last btrc_render_range (CUDA events)        */
+} btrc_render_stats_t;
+
+/* Chained error text of the last failing call on this thread ("" if none). */
+const char *btrc_last_error(void);
+
+/* parse + create + commit: cli/main.cpp:28-71 (JSONParser, create_scene, camera, renderer, ObjectDAG::commit).
+ * Loads OBJ files, builds the BVH and uploads all tables to the current device. */
+int btrc_scene_load_json(const char *path, btrc_scene_t **out);
+/* Same from memory; scene_dir is what "$env{scene_directory}" and "$include{}" resolve against. */
+int btrc_scene_load_json_string(const char *json, const char *scene_dir, btrc_scene_t **out);
+void btrc_scene_free(btrc_scene_t *scene);
+int btrc_scene_info_get(btrc_scene_t *scene, btrc_scene_info_t *out);
+
+/* Renderer parameter overrides (WavefrontPathTracer::set_params, wavefront.cpp:67-70): spp, state_count,
+ * min_depth, max_depth.  Call before the first render; pass -1 to keep a value. */
+int btrc_set_params(btrc_scene_t *scene, int32_t spp, int32_t state_count, int32_t min_depth, int32_t max_depth);
+
+/* Renderer::render() (wavefront.cpp:205-325): clears the film, traces all spp*W*H camera paths and resolves
+ * value/weight (preview.cpp:28-80).  color is W*H float4 (row 0 = top, .w = 1); albedo / normal may be NULL and
+ * are written only when the renderer was created with "albedo"/"normal": true. */
+int btrc_render(btrc_scene_t *scene, int memory, float *color, float *albedo, float *normal, btrc_render_stats_t *stats);
+
+/* The same render split into its parts, for multi-GPU sample partitioning: each rank renders a
+ * contiguous range of camera-path indices into its own film, the films are summed (NCCL) and resolved once.
+ * Path index space: Uniform mode index = sample * W*H + pixel, Tile mode index = pixel * spp + sample
+ * (generate.cpp:49-60). */
+int btrc_film_clear(btrc_scene_t *scene);
+int btrc_render_range(btrc_scene_t *scene, int64_t path_begin, int64_t path_end, btrc_render_stats_t *stats);
+/* Film::get_float3_output / get_float_output (core/film.cpp): radiance W*H*4 floats, weight W*H floats,
+ * albedo / normal W*H*4 floats or NULL. */
+int btrc_film_export(btrc_scene_t *scene, int memory, float *radiance, float *weight, float *albedo, float *normal);
+int btrc_film_import(btrc_scene_t *scene, int memory, const float *radiance, const float *weight, const float *albedo, const float *normal);
+int btrc_resolve(btrc_scene_t *scene, int memory, float *color, float *albedo, float *normal);
+
+/* PostProcessor::process for every entry of root["post_processors"] (cli/main.cpp:79-80; "save": gamma on colour,
+ * format by extension -- postprocess/save_to_image.cpp:30-62; "tonemap": ACES * exposure -- tonemap.cpp:14-51). */
+int btrc_run_post_processors(btrc_scene_t *scene, int memory, float *color, float *albedo, float *normal);
+
+/* ---- stage-level entry points on explicit batches, in the reference's SoA layout (wavefront/soa.h:8-37) ----
+ * ray: o_med = float4(o.xyz, bit-cast medium id), d_t1 = float4(d.xyz, t1).
+ * hit: flag = instance id | bit30 on hit (common.h:12-14); detail = uint4(t bits, primitive id, u bits, v bits).
+ * path: pixel uint2, beta_depth float4(beta.rgb, bit-cast depth), path_rad float4(L.rgb, 1), rng 2 x uint64
+ *       (PCG state, inc), ble float4(beta_le.rgb, bsdf pdf; negative = delta). */
+
+/* TracePipeline::trace (trace.cpp:127-142) */
+int btrc_closest_hit(btrc_scene_t *scene, int memory, const float *o_med, const float *d_t1, int32_t n, uint32_t *flag, uint32_t *detail);
+/* occlusion part of ShadowPipeline::test (shadow.cpp:24-36): occluded[i] = 1 when any triangle has t in [0, t1] */
+int btrc_any_hit(btrc_scene_t *scene, int memory, const float *o_med, const float *d_t1, int32_t n, uint8_t *occluded);
+/* GeneratePipeline::generate (generate.cpp:140-177) for camera-path indices [first, first + n); also adds the
+ * film weights. */
+int btrc_generate(btrc_scene_t *scene, int memory, int64_t first, int32_t n, float *o_med, float *d_t1, uint32_t *pixel,
+                  float *beta_depth, float *path_rad, uint64_t *rng, float *ble);
+/* ShadePipeline::shade (shade.cpp:263-283) on n states: appends survivors to the next_* arrays and shadow rays to
+ * the shadow_* arrays (any order; counts returned), splats terminated paths into the film. */
+int btrc_shade(btrc_scene_t *scene, int memory, int32_t n,
+               const float *o_med, const float *d_t1, const uint32_t *pixel, const float *beta_depth, const float *path_rad,
+               const uint64_t *rng, const float *ble, const uint32_t *flag, const uint32_t *detail,
+               int32_t *n_next, float *next_o_med, float *next_d_t1, uint32_t *next_pixel, float *next_beta_depth,
+               float *next_path_rad, uint64_t *next_rng, float *next_ble,
+               int32_t *n_shadow, uint32_t *shadow_pixel, float *shadow_beta_li, float *shadow_o_med, float *shadow_d_t1);
+/* ShadowPipeline::test (shadow.cpp:143-158): traces the shadow rays and splats the unoccluded ones into the film. */
+int btrc_shadow(btrc_scene_t *scene, int memory, int32_t n, const uint32_t *shadow_pixel, const float *shadow_beta_li,
+                const float *shadow_o_med, const float *shadow_d_t1);
+
+/* Table access for parity tests: the six float4 shading tables of geometry `geometry_id` (24 floats per triangle,
+ * geometry/triangle_mesh.cpp:40-106) and the instance transforms (local_to_world, world_to_local; 3x4 row-major). */
+int btrc_geometry_tables(btrc_scene_t *scene, int32_t geometry_id, int32_t *n_triangles, float *out24);
+int btrc_instance_transform(btrc_scene_t *scene, int32_t instance_id, float *mat12, float *inv12);
+
+/* Library / device facts. */
+int btrc_device_sm_count(void);
+const char *btrc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BTRC_B200_H */
