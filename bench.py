@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the wavefront render path (BASELINE.json metric: Msamples/s and Mrays/s per scene; % of HBM roofline).
+
+    python bench.py --gpus N --steps K --warmup W          # our arm (one rank per GPU under torchrun for N > 1)
+    python bench.py --impl reference ...                   # CPU arm: the oracle restatement on all host cores
+
+A "step" is one pass of the hot path over one batch of synthetic input: one full render of the workload scene
+(film clear -> generate / closest-hit / shade / shadow waves until every camera path has ended -> [NCCL sum of the
+films] -> resolve).  Rank r renders sample indices [r*spp, (r+1)*spp) of every pixel (sample-stream partition),
+so per-GPU work is fixed as N grows ("weak").  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[0]: Cornell box, diffuse + one area light, 512x512, 16 spp
+    "c1_cornell_512_16spp": dict(kind="cornell", width=512, height=512, spp=16),
+}
+DEFAULT_WORKLOAD = "c1_cornell_512_16spp"
+
+
+def make_scene(workload, out_dir, spp=None):
+    from btrc_b200 import scenes
+
+    w = WORKLOADS[workload]
+    if w["kind"] == "cornell":
+        return scenes.make_cornell(out_dir, width=w["width"], height=w["height"], spp=spp or w["spp"])
+    raise ValueError(workload)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        hi = sorted(sm)[len(sm) // 2:]  # samples under load are the upper half (the GPU idles between steps)
+        return {"sm_mhz": float(np.median(hi)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ algorithmic bytes
+def bvh_alg_per_ray(scene_path, sample_paths=16384):
+    """lib/bvh binary-BVH statistics: mean traversal steps and primitive tests per closest-hit ray, measured
+    by oracle/_ref (the reference's vendored SingleRayTraverser, sweep-SAH) on the ray batches of a bounded path sample."""
+    import ctypes
+
+    from oracle import front
+    from oracle.front import _ptr
+
+    R = front.ref_lib()
+    if R is None:
+        return None
+    o = front.OracleScene(scene_path)
+    verts, _ = o.triangles()
+    h = R.ref_bvh_build(verts.shape[0], _ptr(np.ascontiguousarray(verts), ctypes.c_float), 0)
+    st = o.generate(0, sample_paths)
+    stats = np.zeros(2, np.uint64)
+    n_rays = 0
+    for _ in range(64):
+        n = st["o_med"].shape[0]
+        if n == 0:
+            break
+        prim = np.zeros(n, np.int32)
+        tuv = np.zeros((n, 3), np.float32)
+        R.ref_bvh_closest(h, n, _ptr(st["o_med"], ctypes.c_float), _ptr(st["d_t1"], ctypes.c_float), _ptr(prim, ctypes.c_int32),
+                          _ptr(tuv, ctypes.c_float), _ptr(stats, ctypes.c_uint64))
+        n_rays += n
+        flag, detail = o.closest_hit(st["o_med"], st["d_t1"])
+        sh = o.shade(st, flag, detail)
+        keep = (sh["status"] & 1) != 0
+        st = {k: np.ascontiguousarray(v[keep]) for k, v in sh["next"].items()}
+    R.ref_bvh_free(h)
+    return {"steps_per_ray": float(stats[0]) / n_rays, "tests_per_ray": float(stats[1]) / n_rays, "rays": n_rays}
+
+
+def stage_bytes(stats, bvh):
+    """Algorithmic bytes of one render from the reference SoA layout."""
+    bvh_per_ray = (bvh["steps_per_ray"] * 64 + bvh["tests_per_ray"] * 48) if bvh else 0.0
+    n_closest, n_hit = stats["n_closest"], stats["n_hit"]
+    trace = n_closest * 32 + n_hit * 20 + (n_closest - n_hit) * 4 + n_closest * bvh_per_ray
+    shade = n_closest * 108 + n_hit * (16 + 96) + stats["n_next"] * 104 + stats["n_shadow"] * 56 + (stats["n_splat"] - stats["n_shadow_miss"]) * 12
+    shadow = stats["n_shadow"] * (32 + bvh_per_ray) + stats["n_shadow_miss"] * (24 + 12)
+    generate = stats["n_gen"] * 108
+    return {"generate": generate, "trace": trace, "shade": shade, "shadow": shadow}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def run_reference(args):
+    """The reference has no CPU path and cannot be built here (LLVM 11 + OptiX): this arm times the ORACLE restatement
+    (kind "port") on all host cores, each step a bounded sample of the workload (2 of its spp)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import front
+
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    w = WORKLOADS[args.workload]
+    sample_spp = 2
+    with tempfile.TemporaryDirectory() as d:
+        path = make_scene(args.workload, d)
+        o = front.OracleScene(path)
+        for _ in range(max(args.warmup, 1)):
+            o.render(0, 1)
+        t0 = time.perf_counter()
+        rays = 0
+        for k in range(args.steps):
+            r = o.render(0, sample_spp)
+            rays += r["stats"]["n_closest"] + r["stats"]["n_shadow"]
+        dt = time.perf_counter() - t0
+    paths = w["width"] * w["height"] * sample_spp * args.steps
+    value = paths / dt / 1e6
+    cores = front.lib().orc_num_threads()
+    line = {
+        "impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "mrays_per_s": rays / dt / 1e6,
+        "config": {"workload": args.workload, "width": w["width"], "height": w["height"], "spp": w["spp"]},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample_spp} of {w['spp']} spp per step ({w['width']}x{w['height']}), oracle/liborc.so, OpenMP"},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from btrc_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the render path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w = WORKLOADS[args.workload]
+    W, H, spp = w["width"], w["height"], w["spp"]
+    npix = W * H
+    tmp = tempfile.TemporaryDirectory()
+    path = make_scene(args.workload, tmp.name, spp=spp * world)  # weak scaling: every rank renders `spp` samples per pixel
+    s = api.Scene(path, state_count=args.state_count)
+    s.set_profiling(True)
+    stream = torch.cuda.ExternalStream(s.stream_handle())
+    begin, end = rank * spp * npix, (rank + 1) * spp * npix
+
+    rad = torch.zeros(H, W, 4, device="cuda")
+    wgt = torch.zeros(H, W, device="cuda")
+    color_dev = torch.zeros(H, W, 4, device="cuda")
+    color_host = torch.zeros(H, W, 4).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        """One device-resident step: returns the render statistics of this rank."""
+        s.film_clear()
+        st = s.render_range(begin, end)
+        if world > 1:  # the one collective of the path: sum of the film buffers (radiance float4 + weight), then resolve on rank 0
+            s.film_export(rad, wgt)
+            dist.reduce(rad, 0)
+            dist.reduce(wgt, 0)
+            if rank == 0:
+                s.film_import(rad, wgt)
+        if rank == 0:
+            s.resolve(color_dev)
+        return st
+
+    def step_e2e():
+        """The same step through the public call with HOST buffers: result image read back to pinned host memory."""
+        if world == 1:
+            _, _, _, st = s.render(color_host.numpy())
+            return st
+        st = step()
+        if rank == 0:
+            color_host.copy_(color_dev, non_blocking=False)
+        return st
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---- timed region: K device-resident steps, CUDA events on the renderer's stream, L2 flushed between steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    agg = None
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xff)
+        torch.cuda.synchronize()
+        ev[k][0].record(stream)
+        st = step()
+        ev[k][1].record(stream)
+        if agg is None:
+            agg = {key: 0 for key in st if key != "stage_ms"}
+            agg["stage_ms"] = {key: 0.0 for key in st["stage_ms"]}
+        for key, v in st.items():
+            if key == "stage_ms":
+                for kk, vv in v.items():
+                    agg["stage_ms"][kk] += vv
+            else:
+                agg[key] += v
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+
+    # ---- end to end through the public API with host buffers
+    barrier()
+    e2e_t0 = time.perf_counter()
+    for k in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - e2e_t0
+    t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # whole-job event counts
+    counts = torch.tensor([agg[k] for k in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss", "n_splat", "n_iter", "n_launches")],
+                          device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(counts)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    n_gen, n_closest, n_hit, n_next, n_shadow, n_shadow_miss, n_splat, n_iter, n_launch = [float(x) for x in counts.tolist()]
+    secs = dev_ms / 1e3
+    value = n_gen / secs / 1e6
+    mrays = (n_closest + n_shadow) / secs / 1e6
+
+    # ---- roofline of the dominant kernel (rank 0's stage times; algorithmic bytes per SURVEY 8d)
+    bvh = bvh_alg_per_ray(path)
+    peak, peak_src = measured_peak()
+    sb = stage_bytes({k: agg[k] for k in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss", "n_splat")}, bvh)
+    iters = max(agg["n_iter"], 1)
+    stages = {}
+    for name in ("generate", "trace", "shade", "shadow"):
+        ms = agg["stage_ms"][name]
+        gbs = sb[name] / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+        stages[name] = {"ms_total": ms, "launches": iters, "ms_per_launch": ms / iters, "alg_bytes_per_launch": sb[name] / iters,
+                        "achieved_gbs": gbs, "frac": gbs / peak, "share_of_step": ms / dev_ms}
+    dom = max(stages, key=lambda k: stages[k]["ms_total"])
+    roofline = {"kernel": {"generate": "generate_kernel", "trace": "trace_kernel", "shade": "shade_kernel", "shadow": "shadow_kernel"}[dom],
+                "bound": "hbm", "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"],
+                "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": stages[dom]["alg_bytes_per_launch"],
+                "ms_per_launch": stages[dom]["ms_per_launch"], "bvh_alg": bvh}
+
+    # ---- CPU baseline: the oracle (port) on the host cores of this box, bounded sample of the same workload
+    from oracle import front
+
+    o = front.OracleScene(make_scene(args.workload, tmp.name))
+    cpu_spp = min(spp, 8)
+    t0 = time.perf_counter()
+    o.render(0, cpu_spp)
+    cpu_s = time.perf_counter() - t0
+    cpu = {"value": npix * cpu_spp / cpu_s / 1e6, "unit": "Msamples/s", "cores": front.lib().orc_num_threads(), "kind": "port",
+           "sample": f"{cpu_spp} of {spp} spp of the workload ({W}x{H}), oracle/liborc.so on all host cores, {cpu_s:.1f} s"}
+
+    e2e_value = n_gen / e2e_s / 1e6
+    line = {
+        "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "mrays_per_s": mrays,
+        "config": {"workload": args.workload, "width": W, "height": H, "spp_per_gpu": spp, "state_count": s.info.state_count,
+                   "partition": "sample index ranges per rank; NCCL sum-reduce of radiance+weight films to rank 0; resolve on rank 0" if world > 1 else "single GPU",
+                   "timing": "CUDA events on the renderer's stream per step, max over ranks; 256 MB L2 flush (untimed) between steps",
+                   "wall_ms_per_step_incl_flush": wall / args.steps * 1e3},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": 160, "d2h_bytes_per_step": int(npix * 16 + 160 * (n_iter / args.steps / world)),
+                "note": "api.Scene.render() into pinned host memory: film clear, waves, resolve, D2H of the W*H float4 image; the scene (BVH, tables) stays resident like model weights; H2D per step is the wave control block"},
+        "gpu_launches": int(n_launch + args.steps * (3 + 1)),
+        "events": {"n_gen": n_gen, "n_closest": n_closest, "n_hit": n_hit, "n_next": n_next, "n_shadow": n_shadow, "n_shadow_miss": n_shadow_miss,
+                   "n_splat": n_splat, "iterations_per_step": n_iter / args.steps / world},
+        "roofline": roofline,
+        "roofline_stages": stages,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--state-count", type=int, default=2097152)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

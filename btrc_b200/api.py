@@ -31,10 +31,12 @@ class SceneInfo(ctypes.Structure):
 
 class RenderStats(ctypes.Structure):
     _fields_ = [(n, c_uint64) for n in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss", "n_splat", "n_iter")] + \
-               [("render_ms", c_double)]
+               [("render_ms", c_double), ("stage_ms", c_double * 4), ("n_launches", c_uint64)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {n: getattr(self, n) for n, _ in self._fields_}
+        d["stage_ms"] = dict(zip(("generate", "trace", "shade", "shadow"), [float(x) for x in self.stage_ms]))
+        return d
 
 
 _lib = None
@@ -56,6 +58,9 @@ def lib():
         L.btrc_set_params.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32]
         L.btrc_render.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, POINTER(RenderStats)]
         L.btrc_film_clear.argtypes = [c_void_p]
+        L.btrc_stream.argtypes = [c_void_p]
+        L.btrc_stream.restype = c_void_p
+        L.btrc_set_profiling.argtypes = [c_void_p, c_int32]
         L.btrc_render_range.argtypes = [c_void_p, c_int64, c_int64, POINTER(RenderStats)]
         L.btrc_film_export.argtypes = [c_void_p, c_int] + [c_void_p] * 4
         L.btrc_film_import.argtypes = [c_void_p, c_int] + [c_void_p] * 4
@@ -153,6 +158,16 @@ class Scene:
         st = RenderStats()
         _check(self.L.btrc_render(self.h, _mem(color), _p(color), _p(albedo), _p(normal), byref(st)))
         return color, albedo, normal, st.as_dict()
+
+    def set_profiling(self, on=True):
+        _check(self.L.btrc_set_profiling(self.h, 1 if on else 0))
+
+    def stream_handle(self) -> int:
+        """cudaStream_t of the renderer (wrap with torch.cuda.ExternalStream to record events on it)."""
+        p = self.L.btrc_stream(self.h)
+        if not p:
+            raise BtrcError(self.L.btrc_last_error().decode())
+        return int(p)
 
     def film_clear(self):
         _check(self.L.btrc_film_clear(self.h))

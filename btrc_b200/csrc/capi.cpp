@@ -48,6 +48,8 @@ void fill_stats(const RenderStats &s, btrc_render_stats_t *out) {
     out->n_gen = s.n_gen; out->n_closest = s.n_closest; out->n_hit = s.n_hit; out->n_next = s.n_next;
     out->n_shadow = s.n_shadow; out->n_shadow_miss = s.n_shadow_miss; out->n_splat = s.n_splat; out->n_iter = s.n_iter;
     out->render_ms = s.render_ms;
+    for (int k = 0; k < 4; ++k) out->stage_ms[k] = s.stage_ms[k];
+    out->n_launches = s.n_launches;
 }
 
 // copies between any two address spaces (unified virtual addressing)
@@ -180,6 +182,16 @@ int btrc_set_params(btrc_scene_t *s, int32_t spp, int32_t state_count, int32_t m
         if (min_depth >= 0) s->scene->renderer.min_depth = min_depth;
         if (max_depth >= 0) s->scene->renderer.max_depth = max_depth;
     });
+}
+
+int btrc_set_profiling(btrc_scene_t *s, int32_t on) {
+    return guarded([&] { check_scene(s); s->r().set_profiling(on != 0); });
+}
+
+void *btrc_stream(btrc_scene_t *s) {
+    void *out = nullptr;
+    guarded([&] { check_scene(s); out = (void *)s->r().stream(); });
+    return out;
 }
 
 int btrc_film_clear(btrc_scene_t *s) {

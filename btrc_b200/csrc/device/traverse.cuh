@@ -53,7 +53,12 @@ __device__ __forceinline__ HitRec traverse_bvh2(const BvhDevice &bvh, f3 o, f3 d
     HitRec best;
     best.t = tmax; best.u = 0.0f; best.v = 0.0f; best.slot = -1;
 
-    const float idx = 1.0f / d.x, idy = 1.0f / d.y, idz = 1.0f / d.z;
+    // A zero direction component would give inf * 0 = NaN in the slab test; clamp it to a tiny finite slope instead
+    // (the slab then evaluates to +-huge with the sign of (plane - origin), which is the exact answer for a parallel ray).
+    constexpr float kTiny = 1e-20f;
+    const float idx = 1.0f / (fabsf(d.x) > kTiny ? d.x : copysignf(kTiny, d.x));
+    const float idy = 1.0f / (fabsf(d.y) > kTiny ? d.y : copysignf(kTiny, d.y));
+    const float idz = 1.0f / (fabsf(d.z) > kTiny ? d.z : copysignf(kTiny, d.z));
     const float oox = o.x * idx, ooy = o.y * idy, ooz = o.z * idz;
 
     int stack[kStackSize];

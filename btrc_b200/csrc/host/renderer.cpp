@@ -56,6 +56,7 @@ Renderer::Renderer(Scene &scene, int state_count_override) : scene_(scene) {
 Renderer::~Renderer() {
     if (ctl_host_) cudaFreeHost(ctl_host_);
     for (auto &e : snap_ev_) if (e) cudaEventDestroy(e);
+    for (auto &e : prof_events_) cudaEventDestroy(e);
     if (ev_begin_) cudaEventDestroy(ev_begin_);
     if (ev_end_) cudaEventDestroy(ev_end_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -85,12 +86,27 @@ void Renderer::render_range(long long begin, long long end) {
     long long iter = 0;
     bool done = false;
     WaveCtl last = init;
+    size_t n_prof = 0;
+    auto mark = [&]() {  // profiling: one event between consecutive kernels
+        if (!profiling_) return;
+        if (n_prof == prof_events_.size()) {
+            cudaEvent_t e;
+            BTRC_CUDA(cudaEventCreate(&e));
+            prof_events_.push_back(e);
+        }
+        BTRC_CUDA(cudaEventRecord(prof_events_[n_prof++], stream_));
+    };
     while (!done) {
         launch_prepare(ctl_, stream_);
+        mark();
         launch_generate(cfg_, scene_.dev, params, q_[cur], film_, ctl_, stream_);
+        mark();
         launch_trace(cfg_, scene_.dev, q_[cur], hit_, ctl_, stream_);
+        mark();
         launch_shade(cfg_, scene_.dev, params, q_[cur], hit_, q_[cur ^ 1], shadow_, film_, ctl_, stream_);
+        mark();
         launch_shadow(cfg_, scene_.dev, params, shadow_, film_, ctl_, stream_);
+        mark();
         const int slot = (int)(iter % 8);
         BTRC_CUDA(cudaMemcpyAsync(&ctl_host_[slot], ctl_, sizeof(WaveCtl), cudaMemcpyDeviceToHost, stream_));
         BTRC_CUDA(cudaEventRecord(snap_ev_[slot], stream_));
@@ -121,6 +137,15 @@ void Renderer::render_range(long long begin, long long end) {
     stats_.n_splat += fin.n_splat;
     stats_.n_iter += fin.n_iter;
     stats_.render_ms = ms;
+    stats_.n_launches = 5ull * (unsigned long long)iter;
+    for (double &v : stats_.stage_ms) v = 0;
+    for (size_t k = 0; k + 4 < n_prof; k += 5) {
+        for (int st = 0; st < 4; ++st) {
+            float t = 0;
+            BTRC_CUDA(cudaEventElapsedTime(&t, prof_events_[k + st], prof_events_[k + st + 1]));
+            stats_.stage_ms[st] += t;
+        }
+    }
 }
 
 void Renderer::stage_generate(long long first, int n) {

@@ -17,6 +17,9 @@ namespace btrc {
 struct RenderStats {
     uint64_t n_gen = 0, n_closest = 0, n_hit = 0, n_next = 0, n_shadow = 0, n_shadow_miss = 0, n_splat = 0, n_iter = 0;
     double render_ms = 0;  // device time of the last render_range (CUDA events)
+    // per-stage device time of the last render_range (only when profiling is on): generate, trace, shade, shadow
+    double stage_ms[4] = {0, 0, 0, 0};
+    uint64_t n_launches = 0;  // kernels launched by the last render_range
 };
 
 class Renderer {
@@ -25,6 +28,7 @@ public:
     ~Renderer();
 
     void clear_film();
+    void set_profiling(bool on) { profiling_ = on; }
     // Traces camera paths [begin, end) of the scene's path index space (Uniform mode: index = sample * W*H + pixel;
     // Tile mode: index = pixel * spp + sample) and accumulates them into the film.
     void render_range(long long begin, long long end);
@@ -62,6 +66,8 @@ private:
     WaveCtl *ctl_host_ = nullptr;   // pinned ring of snapshots
     cudaEvent_t snap_ev_[8]{};
     RenderStats stats_;
+    bool profiling_ = false;
+    std::vector<cudaEvent_t> prof_events_;
     template <typename T> T *alloc(size_t n);
 };
 

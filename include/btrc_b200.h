@@ -46,6 +46,9 @@ typedef struct btrc_render_stats {
     uint64_t n_splat;        /* radiance splats (3 float atomics each)                         */
     uint64_t n_iter;         /* wavefront iterations                                           */
     double render_ms;        /* device time of the last btrc_render_range (CUDA events)        */
+    double stage_ms[4];      /* with btrc_set_profiling(1): device time per stage of the last  */
+                             /* range -- generate, closest-hit trace, shade, shadow trace      */
+    uint64_t n_launches;     /* kernels launched by the last btrc_render_range                 */
 } btrc_render_stats_t;
 
 /* Chained error text of the last failing call on this thread ("" if none). */
@@ -62,6 +65,10 @@ int btrc_scene_info_get(btrc_scene_t *scene, btrc_scene_info_t *out);
 /* Renderer parameter overrides (WavefrontPathTracer::set_params, wavefront.cpp:67-70): spp, state_count,
  * min_depth, max_depth.  Call before the first render; pass -1 to keep a value. */
 int btrc_set_params(btrc_scene_t *scene, int32_t spp, int32_t state_count, int32_t min_depth, int32_t max_depth);
+
+/* Record one CUDA event between consecutive stage kernels so that btrc_render_stats_t::stage_ms is filled
+ * (the reference has no profiling hooks: SURVEY 5). */
+int btrc_set_profiling(btrc_scene_t *scene, int32_t on);
 
 /* Renderer::render() (wavefront.cpp:205-325): clears the film, traces all spp*W*H camera paths and resolves
  * value/weight (preview.cpp:28-80).  color is W*H float4 (row 0 = top, .w = 1); albedo / normal may be NULL and
@@ -114,6 +121,10 @@ int btrc_shadow(btrc_scene_t *scene, int memory, int32_t n, const uint32_t *shad
  * geometry/triangle_mesh.cpp:40-106) and the instance transforms (local_to_world, world_to_local; 3x4 row-major). */
 int btrc_geometry_tables(btrc_scene_t *scene, int32_t geometry_id, int32_t *n_triangles, float *out24);
 int btrc_instance_transform(btrc_scene_t *scene, int32_t instance_id, float *mat12, float *inv12);
+
+/* The CUDA stream (cudaStream_t) all of this scene's kernels are launched on, so that a caller can bracket calls
+ * with its own events on the launching stream. */
+void *btrc_stream(btrc_scene_t *scene);
 
 /* Library / device facts. */
 int btrc_device_sm_count(void);
