@@ -25,17 +25,17 @@ class BtrcError(RuntimeError):
 
 class SceneInfo(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in ("width", "height", "spp", "min_depth", "max_depth", "state_count", "tile", "albedo", "normal",
-                                       "n_instances", "n_lights", "n_triangles", "n_materials", "bvh_depth")] + \
+                                       "n_instances", "n_lights", "n_triangles", "n_materials", "bvh_depth", "n_media", "has_medium", "n_textures")] + \
                [("world_diagonal", c_float), ("bvh_build_seconds", c_float)]
 
 
 class RenderStats(ctypes.Structure):
     _fields_ = [(n, c_uint64) for n in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss", "n_splat", "n_iter")] + \
-               [("render_ms", c_double), ("stage_ms", c_double * 4), ("n_launches", c_uint64)]
+               [("render_ms", c_double), ("stage_ms", c_double * 5), ("n_launches", c_uint64)]
 
     def as_dict(self):
         d = {n: getattr(self, n) for n, _ in self._fields_}
-        d["stage_ms"] = dict(zip(("generate", "trace", "shade", "shadow"), [float(x) for x in self.stage_ms]))
+        d["stage_ms"] = dict(zip(("generate", "trace", "shade", "shadow", "medium"), [float(x) for x in self.stage_ms]))
         return d
 
 
@@ -70,6 +70,7 @@ def lib():
         L.btrc_any_hit.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int32, c_void_p]
         L.btrc_generate.argtypes = [c_void_p, c_int, c_int64, c_int32] + [c_void_p] * 7
         L.btrc_shade.argtypes = [c_void_p, c_int, c_int32] + [c_void_p] * 9 + [POINTER(c_int32)] + [c_void_p] * 7 + [POINTER(c_int32)] + [c_void_p] * 4
+        L.btrc_medium.argtypes = L.btrc_shade.argtypes
         L.btrc_shadow.argtypes = [c_void_p, c_int, c_int32] + [c_void_p] * 4
         L.btrc_geometry_tables.argtypes = [c_void_p, c_int32, POINTER(c_int32), c_void_p]
         L.btrc_instance_transform.argtypes = [c_void_p, c_int32, c_void_p, c_void_p]
@@ -220,6 +221,21 @@ class Scene:
                                  *[_p(nxt[k]) for k in _STATE_KEYS], byref(n_shadow), _p(sh["pixel"]), _p(sh["beta_li"]), _p(sh["o_med"]), _p(sh["d_t1"])))
         nn, ns = n_next.value, n_shadow.value
         return {k: v[:nn] for k, v in nxt.items()}, {k: v[:ns] for k, v in sh.items()}
+
+    def medium(self, st, flag, detail):
+        """Medium stage; returns (state updated in place, flag with the scattered bit, next states, shadow rays)."""
+        n = st["o_med"].shape[0]
+        st = {k: np.ascontiguousarray(v.copy()) for k, v in st.items()}
+        flag = np.ascontiguousarray(flag.copy(), np.uint32)
+        detail = np.ascontiguousarray(detail, np.uint32)
+        nxt = new_state(n)
+        sh = dict(pixel=np.zeros((n, 2), np.uint32), beta_li=np.zeros((n, 4), np.float32), o_med=np.zeros((n, 4), np.float32),
+                  d_t1=np.zeros((n, 4), np.float32))
+        n_next, n_shadow = c_int32(0), c_int32(0)
+        _check(self.L.btrc_medium(self.h, HOST, n, *[_p(st[k]) for k in _STATE_KEYS], _p(flag), _p(detail), byref(n_next),
+                                  *[_p(nxt[k]) for k in _STATE_KEYS], byref(n_shadow), _p(sh["pixel"]), _p(sh["beta_li"]), _p(sh["o_med"]), _p(sh["d_t1"])))
+        nn, ns = n_next.value, n_shadow.value
+        return st, flag, {k: v[:nn] for k, v in nxt.items()}, {k: v[:ns] for k, v in sh.items()}
 
     def shadow(self, sh):
         n = sh["pixel"].shape[0]

@@ -28,8 +28,11 @@ HOST_SRCS = ["host/node.cpp", "host/mesh.cpp", "host/bvh.cpp", "host/scene.cpp",
 DEVICE_SRCS = ["device/kernels.cu"]
 
 HOST_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-Wall", "-Wno-unknown-pragmas", f"-I{CUDA_HOME}/include"]
+# -ftz / -prec-div / -prec-sqrt: the reference's own floating-point contract (fast_math => div.approx, sqrt.approx,
+# flush-to-zero; log/exp/pow/atan2/acos stay full precision, so no --use_fast_math).  The triangle test and
+# intersection_offset use explicit round-to-nearest intrinsics and are not affected.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-ccbin", CXX,
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-ftz=true", "-prec-div=false", "-prec-sqrt=false"]
 
 
 def _newer(target, deps):

@@ -48,7 +48,7 @@ void fill_stats(const RenderStats &s, btrc_render_stats_t *out) {
     out->n_gen = s.n_gen; out->n_closest = s.n_closest; out->n_hit = s.n_hit; out->n_next = s.n_next;
     out->n_shadow = s.n_shadow; out->n_shadow_miss = s.n_shadow_miss; out->n_splat = s.n_splat; out->n_iter = s.n_iter;
     out->render_ms = s.render_ms;
-    for (int k = 0; k < 4; ++k) out->stage_ms[k] = s.stage_ms[k];
+    for (int k = 0; k < 5; ++k) out->stage_ms[k] = s.stage_ms[k];
     out->n_launches = s.n_launches;
 }
 
@@ -165,7 +165,8 @@ int btrc_scene_info_get(btrc_scene_t *s, btrc_scene_info_t *o) {
         o->spp = sc.renderer.spp; o->min_depth = sc.renderer.min_depth; o->max_depth = sc.renderer.max_depth;
         o->state_count = s->state_count_override > 0 ? s->state_count_override : sc.renderer.state_count;
         o->tile = sc.renderer.tile; o->albedo = sc.renderer.albedo; o->normal = sc.renderer.normal;
-        o->n_instances = (int)sc.instances.size(); o->n_lights = (int)sc.lights.size();
+        o->n_instances = (int)sc.instances.size(); o->n_lights = (int)sc.lights.size() + (sc.env.type != 0 ? 1 : 0);
+        o->n_media = (int)sc.medium_table.size(); o->has_medium = sc.has_medium ? 1 : 0; o->n_textures = (int)sc.textures.size();
         o->n_triangles = (int)sc.world_tris.size(); o->n_materials = (int)sc.materials.size();
         o->bvh_depth = sc.bvh_depth;
         o->world_diagonal = sc.world_diagonal;
@@ -336,40 +337,70 @@ int btrc_generate(btrc_scene_t *s, int memory, int64_t first, int32_t n, float *
     });
 }
 
+// shared body of btrc_shade / btrc_medium: upload the batch, run the stage, download compacted outputs
+static void run_state_stage(btrc_scene_t *s, bool medium, int32_t n, float *o_med, const float *d_t1, const uint32_t *pixel, const float *beta_depth,
+                            const float *path_rad, uint64_t *rng, float *ble, uint32_t *flag, const uint32_t *detail, int32_t *n_next,
+                            float *next_o_med, float *next_d_t1, uint32_t *next_pixel, float *next_beta_depth, float *next_path_rad,
+                            uint64_t *next_rng, float *next_ble, int32_t *n_shadow, uint32_t *shadow_pixel, float *shadow_beta_li,
+                            float *shadow_o_med, float *shadow_d_t1) {
+    check_scene(s);
+    *n_next = 0; *n_shadow = 0;
+    if (n <= 0) return;
+    Renderer &r = s->r();
+    const int W = s->scene->width;
+    upload_paths(r, 0, n, W, o_med, d_t1, pixel, beta_depth, path_rad, rng, ble);
+    copy_any(r.hits().flag, flag, 4 * (size_t)n);
+    copy_any(r.hits().detail, detail, 16 * (size_t)n);
+    int nn = 0, ns = 0;
+    if (medium) {
+        r.stage_medium(n, &nn, &ns);
+        // in-place results of the medium stage: resolved medium id, beta_le * Tr, advanced sampler, scattered flag
+        copy_any(o_med, r.queue(0).ray_o, 16 * (size_t)n);
+        copy_any(ble, r.queue(0).ble, 16 * (size_t)n);
+        copy_any(rng, r.queue(0).rng, 16 * (size_t)n);
+        copy_any(flag, r.hits().flag, 4 * (size_t)n);
+    } else
+        r.stage_shade(n, &nn, &ns);
+    *n_next = nn; *n_shadow = ns;
+    if (nn) download_paths(r, 1, nn, W, next_o_med, next_d_t1, next_pixel, next_beta_depth, next_path_rad, next_rng, next_ble);
+    if (ns) {
+        const size_t N = (size_t)ns;
+        std::vector<float4> b(N);
+        std::vector<uint32_t> px(2 * N);
+        copy_any(b.data(), r.shadows().beta_li, 16 * N);
+        for (size_t i = 0; i < N; ++i) {
+            uint32_t idx;
+            std::memcpy(&idx, &b[i].w, 4);
+            px[2 * i] = idx % (uint32_t)W; px[2 * i + 1] = idx / (uint32_t)W;
+            b[i].w = 1.0f;  // soa.cpp:112
+        }
+        copy_any(shadow_beta_li, b.data(), 16 * N);
+        copy_any(shadow_pixel, px.data(), 8 * N);
+        copy_any(shadow_o_med, r.shadows().ray_o, 16 * N);
+        copy_any(shadow_d_t1, r.shadows().ray_d, 16 * N);
+    }
+}
+
 int btrc_shade(btrc_scene_t *s, int memory, int32_t n, const float *o_med, const float *d_t1, const uint32_t *pixel, const float *beta_depth,
                const float *path_rad, const uint64_t *rng, const float *ble, const uint32_t *flag, const uint32_t *detail, int32_t *n_next,
                float *next_o_med, float *next_d_t1, uint32_t *next_pixel, float *next_beta_depth, float *next_path_rad, uint64_t *next_rng,
                float *next_ble, int32_t *n_shadow, uint32_t *shadow_pixel, float *shadow_beta_li, float *shadow_o_med, float *shadow_d_t1) {
     (void)memory;
     return guarded([&] {
-        check_scene(s);
-        *n_next = 0; *n_shadow = 0;
-        if (n <= 0) return;
-        Renderer &r = s->r();
-        const int W = s->scene->width;
-        upload_paths(r, 0, n, W, o_med, d_t1, pixel, beta_depth, path_rad, rng, ble);
-        copy_any(r.hits().flag, flag, 4 * (size_t)n);
-        copy_any(r.hits().detail, detail, 16 * (size_t)n);
-        int nn = 0, ns = 0;
-        r.stage_shade(n, &nn, &ns);
-        *n_next = nn; *n_shadow = ns;
-        if (nn) download_paths(r, 1, nn, W, next_o_med, next_d_t1, next_pixel, next_beta_depth, next_path_rad, next_rng, next_ble);
-        if (ns) {
-            const size_t N = (size_t)ns;
-            std::vector<float4> b(N);
-            std::vector<uint32_t> px(2 * N);
-            copy_any(b.data(), r.shadows().beta_li, 16 * N);
-            for (size_t i = 0; i < N; ++i) {
-                uint32_t idx;
-                std::memcpy(&idx, &b[i].w, 4);
-                px[2 * i] = idx % (uint32_t)W; px[2 * i + 1] = idx / (uint32_t)W;
-                b[i].w = 1.0f;  // soa.cpp:112
-            }
-            copy_any(shadow_beta_li, b.data(), 16 * N);
-            copy_any(shadow_pixel, px.data(), 8 * N);
-            copy_any(shadow_o_med, r.shadows().ray_o, 16 * N);
-            copy_any(shadow_d_t1, r.shadows().ray_d, 16 * N);
-        }
+        run_state_stage(s, false, n, const_cast<float *>(o_med), d_t1, pixel, beta_depth, path_rad, const_cast<uint64_t *>(rng), const_cast<float *>(ble),
+                        const_cast<uint32_t *>(flag), detail, n_next, next_o_med, next_d_t1, next_pixel, next_beta_depth, next_path_rad, next_rng,
+                        next_ble, n_shadow, shadow_pixel, shadow_beta_li, shadow_o_med, shadow_d_t1);
+    });
+}
+
+int btrc_medium(btrc_scene_t *s, int memory, int32_t n, float *o_med, const float *d_t1, const uint32_t *pixel, const float *beta_depth,
+                const float *path_rad, uint64_t *rng, float *ble, uint32_t *flag, const uint32_t *detail, int32_t *n_next,
+                float *next_o_med, float *next_d_t1, uint32_t *next_pixel, float *next_beta_depth, float *next_path_rad, uint64_t *next_rng,
+                float *next_ble, int32_t *n_shadow, uint32_t *shadow_pixel, float *shadow_beta_li, float *shadow_o_med, float *shadow_d_t1) {
+    (void)memory;
+    return guarded([&] {
+        run_state_stage(s, true, n, o_med, d_t1, pixel, beta_depth, path_rad, rng, ble, flag, detail, n_next, next_o_med, next_d_t1, next_pixel,
+                        next_beta_depth, next_path_rad, next_rng, next_ble, n_shadow, shadow_pixel, shadow_beta_li, shadow_o_med, shadow_d_t1);
     });
 }
 

@@ -21,21 +21,75 @@ constexpr uint32_t kFlagInstanceMask = ~0u << 2 >> 2;
 enum MaterialType : int {
     MAT_DIFFUSE = 0,
     MAT_BLACK = 1,
+    MAT_DISNEY = 2,
+    MAT_METAL = 3,
+    MAT_GLASS = 4,
+    MAT_MIRROR = 5,
+    MAT_INVISIBLE = 6,
     MAT_COUNT
 };
 
-enum TextureType : int { TEX_CONSTANT = 0 };
+// 2-D textures are small postfix programs over a value stack (constant / array leaves, add sub mul div), with the
+// chain of "transform" wrappers folded into each array leaf's uv matrix.  Replaces the reference's per-object
+// generated sampling code (builtin/texture2d/{array2d,math,transform}.cpp, core/texture2d.cpp).
+enum TexOpCode : int { TEXOP_CONST = 0, TEXOP_ARRAY = 1, TEXOP_ADD = 2, TEXOP_SUB = 3, TEXOP_MUL = 4, TEXOP_DIV = 5 };
+
+struct TexOp {
+    int op;
+    float value[3];                 // TEXOP_CONST
+    unsigned long long tex;         // TEXOP_ARRAY: cudaTextureObject_t
+    float m[6];                     // TEXOP_ARRAY: uv' = (m0 u + m1 v + m2, m3 u + m4 v + m5)
+};
 
 struct TextureDesc {
-    int type;
-    float value[3];
+    int first_op, n_ops;            // program in SceneDevice::tex_ops (n_ops == 1 for a plain constant / array)
+};
+
+// texture slots of a material (argument order of the reference's creators: diffuse.cpp:36-48, disney.cpp:844-894,
+// metal.cpp:50-77, glass.cpp:141-157, mirror.cpp:91-103)
+enum MatSlot : int {
+    SLOT_COLOR = 0, SLOT_METALLIC, SLOT_ROUGHNESS, SLOT_TRANSMISSION, SLOT_IOR, SLOT_SPECULAR, SLOT_SPECULAR_TINT, SLOT_ANISOTROPIC,
+    SLOT_SHEEN, SLOT_SHEEN_TINT, SLOT_CLEARCOAT, SLOT_CLEARCOAT_GLOSS, SLOT_TRANSMISSION_ROUGHNESS, SLOT_COUNT
 };
 
 struct MaterialDesc {
     int type;
-    int color_tex;
-    int normal_tex;
+    int normal_tex;                 // -1: no normal map
     int shadow_terminator;
+    int tex[SLOT_COUNT];            // texture ids, -1 where the type has no such parameter
+};
+
+// 3-D textures: constant or a CUDA 3-D texture object (texture3d/array3d.cpp, core/texture3d.cpp)
+struct Texture3DDesc {
+    int is_array;
+    float value[3];
+    unsigned long long tex;
+};
+
+enum MediumType : int { MED_HOMOGENEOUS = 0, MED_HETEROGENEOUS = 1, MED_VOLPRIM = 2 };
+
+// builtin/medium/homogeneous.cpp, hetergeneous.cpp; TransformMedium chains (core/medium.cpp:98-129) are composed into
+// one world_to_local (3x4 row-major).  The last medium of the table is the volume-primitive medium (empty: Tr = 1).
+struct MediumDesc {
+    int type;
+    float sigma_t, albedo[3], g;            // homogeneous
+    int sigma_t_tex, albedo_tex, g_tex;     // heterogeneous
+    int has_transform;
+    float world_to_local[12];
+    float inv_max_density;                  // 1 / max(max sigma_t, 0.001)   (hetergeneous.cpp:33-34)
+};
+
+enum EnvType : int { ENV_NONE = 0, ENV_GRADIENT_SKY = 1, ENV_IBL = 2 };
+
+struct EnvLight {  // builtin/light/gradient_sky.cpp, ibl.cpp + env_sampler.cpp
+    int type;
+    int light_index;                // index in the uniform light sampler (= number of area lights), -1 without env light
+    float lower[3], upper[3], up[3];        // gradient sky (up normalised)
+    int ibl_tex;                    // texture id (IBL)
+    float frame[9];                 // IBL frame x, y, z
+    int lut_w, lut_h;
+    const float *tile_probs;        // lut_w * lut_h
+    const float2 *tile_alias;
 };
 
 // reference: core/geometry.h:10-19 -- six float4 tables per mesh
@@ -108,8 +162,14 @@ struct SceneDevice {
     const GeometryInfo *geometries;
     const MaterialDesc *materials;
     const TextureDesc *textures;
-    const LightInfo *lights;
-    int n_instances, n_lights;
+    const TexOp *tex_ops;
+    const Texture3DDesc *textures3d;
+    const MediumDesc *media;
+    const LightInfo *lights;        // area lights
+    int n_instances;
+    int n_lights;                   // area lights + (environment light ? 1 : 0)   (core/light_sampler.cpp:24-33)
+    int has_medium;                 // Scene::has_medium (core/scene.cpp:346-356)
+    EnvLight env;
     CameraInfo camera;
     const float2 *filter_alias;  // gaussian filter alias table (256*256)
     uint32_t vol_prim_medium_id;

@@ -9,6 +9,7 @@
 
 #include "dev_math.cuh"
 #include "rng.cuh"
+#include "shading.cuh"
 #include "traverse.cuh"
 
 namespace btrc {
@@ -192,225 +193,132 @@ __global__ void __launch_bounds__(kBlock) anyhit_batch_kernel(SceneDevice scene,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// shade (shade.cpp:38-235, helper.cpp:10-207, core/scene.cpp:9-64, material/*)
+// Queue appends shared by the medium and shade kernels: one atomic per warp and queue (ballot + popc prefix)
+// instead of the reference's one atomic per thread (shade.cpp:165,225; medium.cpp:131,151).
 // ---------------------------------------------------------------------------------------------------------------
-struct SurfacePoint {
-    f3 position;
-    Frame3 frame;
-    f3 interp_z;
-    float2 uv, tex_coord;
-};
-
-// core/scene.cpp:9-64
-__device__ __forceinline__ SurfacePoint get_hitinfo(f3 o, f3 d, const InstanceInfo &inst, const GeometryInfo &geo, float t, uint32_t prim, float2 uv) {
-    SurfacePoint sp;
-    sp.position = o + t * d;
-    const float4 gx = ldg4(geo.gx_ua + prim), gy = ldg4(geo.gy_uba + prim), gz = ldg4(geo.gz_uca + prim);
-    const float4 sa = ldg4(geo.sn_va + prim), sba = ldg4(geo.sn_vba + prim), sca = ldg4(geo.sn_vca + prim);
-    Frame3 gf(xyz(gx), xyz(gy), xyz(gz));
-    gf.x = normalize(xf_vector(inst.mat, gf.x));
-    gf.y = normalize(xf_vector(inst.mat, gf.y));
-    gf.z = normalize(xf_normal(inst.inv, gf.z));
-    f3 interp = xyz(sa) + xyz(sba) * uv.x + xyz(sca) * uv.y;
-    interp = normalize(xf_normal(inst.inv, interp));
-    sp.frame = gf;
-    sp.interp_z = interp;
-    sp.uv = uv;
-    sp.tex_coord = make_float2(gx.w + gy.w * uv.x + gz.w * uv.y, sa.w + sba.w * uv.x + sca.w * uv.y);
-    return sp;
-}
-
-__device__ __forceinline__ f3 eval_texture(const SceneDevice &scene, int tex, const SurfacePoint &) {
-    const TextureDesc &t = scene.textures[tex];
-    return f3(t.value[0], t.value[1], t.value[2]);
-}
-
-// helper.cpp:174-207 + mesh_light.cpp:17-29,60-76
-__device__ __forceinline__ f3 handle_intersected_light(const SceneDevice &scene, f3 o, f3 d, const SurfacePoint &inct, f3 beta_le, float bsdf_pdf, int light_index) {
-    f3 result(0.0f);
-    if (light_index >= 0) {
-        const float select_pdf = 1.0f / float(scene.n_lights);
-        const LightInfo &li = scene.lights[light_index];
-        const f3 intensity(li.intensity[0], li.intensity[1], li.intensity[2]);
-        const f3 le = dot(inct.frame.z, -d) >= 0.0f ? intensity : f3(0.0f);
-        if (bsdf_pdf < 0.0f) {
-            result = beta_le * le / -bsdf_pdf;
-        } else {
-            float light_dir_pdf;
-            const f3 nor = inct.frame.z, pos = inct.position;
-            if (dot(nor, o - pos) <= 0.0f) light_dir_pdf = 0.0f;
-            else {
-                const GeometryInfo &geo = scene.geometries[scene.instances[li.instance_id].geometry_id];
-                const float pdf_area = 1.0f / geo.total_area;
-                const f3 spt_to_ref = o - pos;
-                const float dist2 = length_square(spt_to_ref);
-                const float dist3 = sqrtf(dist2) * dist2;
-                light_dir_pdf = li.inv_scale2 * pdf_area * dist3 / fabsf(dot(nor, spt_to_ref));
-            }
-            const float light_pdf = select_pdf * light_dir_pdf;
-            result = beta_le * le / (bsdf_pdf + light_pdf);
-        }
-    }
-    return result;
-}
-
-struct LiSample {
-    bool success;
-    f3 o, d, li;
-    float t1, light_pdf;
-};
-
-// helper.cpp:10-65,125-142; light_sampler.cpp:41-63; mesh_light.cpp:31-58; triangle_mesh.cpp:188-228
-__device__ __forceinline__ LiSample sample_surface_light_li(const SceneDevice &scene, f3 ref_pos, f3 ref_nor, Sampler &sampler) {
-    LiSample r;
-    r.success = false;
-    const float s0 = sampler.get1d(), s1 = sampler.get1d(), s2 = sampler.get1d();
-    const float sel = sampler.get1d();
-    const int n = scene.n_lights;
-    if (n == 0) return r;
-    const int idx = min(int(sel * n), n - 1);
-    const float select_pdf = 1.0f / float(n);
-    const LightInfo &li = scene.lights[idx];
-    const InstanceInfo &linst = scene.instances[li.instance_id];
-    const GeometryInfo &geo = scene.geometries[linst.geometry_id];
-    const uint32_t prim = alias_sample(geo.area_alias, (uint32_t)geo.prim_count, s0);
-    const float2 uv = sample_triangle_uniform(s1, s2);
-    const float *pp = geo.positions + 9 * (size_t)prim;
-    const f3 a(__ldg(pp), __ldg(pp + 1), __ldg(pp + 2)), ba(__ldg(pp + 3), __ldg(pp + 4), __ldg(pp + 5)), ca(__ldg(pp + 6), __ldg(pp + 7), __ldg(pp + 8));
-    const f3 pos = a + ba * uv.x + ca * uv.y;
-    const f3 ez = normalize(xyz(ldg4(geo.gz_uca + prim)));  // CFrame(ex, ey, ez).z
-    const float pdf_area = 1.0f / geo.total_area;
-    const f3 spos = xf_point(linst.mat, pos);
-    const f3 snor = normalize(xf_normal(linst.inv, ez));
-    const f3 pos_to_ref = ref_pos - spos;
-    const float dist2 = length_square(pos_to_ref);
-    const float pdf_sa = li.inv_scale2 * pdf_area * dist2 / fabsf(dot(snor, normalize(pos_to_ref)));
-    const f3 rad = dot(pos_to_ref, snor) > 0.0f ? f3(li.intensity[0], li.intensity[1], li.intensity[2]) : f3(0.0f);
-    const f3 diff = spos - ref_pos;
-    const f3 shadow_dst = intersection_offset(spos, snor, -diff);
-    r.o = intersection_offset(ref_pos, ref_nor, diff);
-    r.d = shadow_dst - r.o;
-    r.t1 = 1.0f;
-    r.li = rad;
-    r.light_pdf = select_pdf * pdf_sa;
-    r.success = true;
-    return r;
-}
-
-// helper.cpp:67-95
-__device__ __forceinline__ bool simple_russian_roulette(const RenderParams &P, f3 &beta, int depth, Sampler &sampler) {
-    bool ret = false;
-    if (depth >= P.min_depth) {
-        if (depth >= P.max_depth) ret = true;
-        else {
-            const float sam = sampler.get1d();
-            if (lum(beta) < P.rr_threshold) {
-                if (sam > P.rr_cont_prob) ret = true;
-                else beta = beta / P.rr_cont_prob;
-            }
-        }
-    }
-    return ret;
-}
-
-// material/utils/shader_frame.cpp:5-95
-struct ShaderFrame {
-    Frame3 geometry, shading;
-    __device__ __forceinline__ bool is_black_fringes(f3 w) const {
-        return geometry.in_positive_z_hemisphere(w) != shading.in_positive_z_hemisphere(w);
-    }
-    __device__ __forceinline__ float correct_shading_energy(f3 wi) const {
-        const float down = fabsf(dot(geometry.z, wi));
-        return down > 1e-4f ? fabsf(dot(shading.z, wi)) / down : 1.0f;
-    }
-};
-
-struct BsdfSample {
-    f3 bsdf, dir;
+struct NextState {
+    f3 o, d, beta, L, ble;
     float pdf;
-    bool is_delta;
+    uint32_t med;
+    int depth;
+    ulonglong2 rng;
+};
+struct ShadowOut {
+    f3 o, d, beta;
+    float t1;
+    uint32_t med;
 };
 
-// BSDFAggregate with the closures of one material (material/utils/aggregate.cpp:32-230).  The per-material
-// closure sets are compile-time specialisations selected by MaterialDesc::type -- this replaces the reference's
-// per-object run-time code generation (core/context.h:321-382).
-struct Shader {
-    int type;
-    ShaderFrame frame;
-    bool shadow_terminator;
-    f3 albedo_value;
-
-    __device__ __forceinline__ float shadow_terminator_term(f3 wi) const {  // aggregate.cpp:219-230
-        if (!shadow_terminator) return 1.0f;
-        const float wgwi = dot(frame.geometry.z, wi);
-        const float wswi = dot(frame.shading.z, wi);
-        const float wgws = dot(frame.geometry.z, frame.shading.z);
-        const float g = saturate(wgwi / (wswi * wgws));
-        return -g * g * g + g * g + g;
+__device__ __forceinline__ void emit_outputs(PathQueue &nq, ShadowQueue &sq, FilmDevice &film, WaveCtl *ctl, uint32_t pixel, bool emit_next,
+                                             const NextState &ns, bool emit_shadow, const ShadowOut &so, bool splat, f3 splat_value) {
+    const int next_slot = warp_alloc(&ctl->n_next, emit_next);
+    if (emit_next) {
+        nq.ray_o[next_slot] = make4(ns.o, __uint_as_float(ns.med));
+        nq.ray_d[next_slot] = make4(ns.d, kMaxFloat);
+        nq.beta[next_slot] = make4(ns.beta, __int_as_float(ns.depth));
+        nq.rad[next_slot] = make4(ns.L, __uint_as_float(pixel));
+        nq.rng[next_slot] = ns.rng;
+        nq.ble[next_slot] = make4(ns.ble, ns.pdf);
     }
-    __device__ __forceinline__ f3 albedo() const { return type == MAT_BLACK ? f3(0.0f) : albedo_value; }
-    __device__ __forceinline__ f3 normal() const { return frame.shading.z; }
-
-    __device__ __forceinline__ Frame3 flipped_shading(f3 wo) const {  // flip_for_black_fringes
-        return frame.is_black_fringes(wo) ? frame.geometry : frame.shading;
+    const int shadow_slot = warp_alloc(&ctl->n_shadow, emit_shadow);
+    if (emit_shadow) {
+        sq.ray_o[shadow_slot] = make4(so.o, __uint_as_float(so.med));
+        sq.ray_d[shadow_slot] = make4(so.d, so.t1);
+        sq.beta_li[shadow_slot] = make4(so.beta, __uint_as_float(pixel));
     }
-
-    __device__ __forceinline__ BsdfSample sample(f3 wo, float s0, float s1, float s2) const {
-        BsdfSample r;
-        r.bsdf = f3(0.0f); r.dir = f3(0.0f); r.pdf = 0.0f; r.is_delta = false;
-        if (type == MAT_BLACK) return r;
-        const Frame3 sh = flipped_shading(wo);
-        const f3 lwo = normalize(sh.global_to_local(wo));
-        // diffuse closure (material/component/diffuse.cpp:10-30); single closure: selector = sam[0]
-        if (lwo.z <= 0.0f) return r;
-        const f3 lwi = sample_hemisphere_zweighted(s0, s1);
-        const float cpdf = pdf_sample_hemisphere_zweighted(lwi);
-        if (cpdf <= 0.0f) return r;
-        const f3 dir = sh.local_to_global(lwi);
-        if (frame.is_black_fringes(dir)) return r;
-        ShaderFrame fl; fl.geometry = frame.geometry; fl.shading = sh;
-        const float corr = fl.correct_shading_energy(dir);
-        const float stt = shadow_terminator_term(dir);
-        r.dir = dir;
-        r.bsdf = albedo_value / kPi * corr * stt;
-        r.pdf = cpdf;
-        return r;
-    }
-    __device__ __forceinline__ f3 eval(f3 wi, f3 wo) const {  // aggregate.cpp:185-197
-        if (type == MAT_BLACK) return f3(0.0f);
-        const Frame3 sh = flipped_shading(wo);
-        const f3 lwi = normalize(sh.global_to_local(wi));
-        const f3 lwo = normalize(sh.global_to_local(wo));
-        f3 result(0.0f);
-        if (!(lwi.z <= 0.0f || lwo.z <= 0.0f)) result = result + albedo_value / kPi;
-        ShaderFrame fl; fl.geometry = frame.geometry; fl.shading = sh;
-        return result * fl.correct_shading_energy(wi) * shadow_terminator_term(wi);
-    }
-    __device__ __forceinline__ float pdf(f3 wi, f3 wo) const {  // aggregate.cpp:199-209
-        if (type == MAT_BLACK) return 0.0f;
-        const Frame3 sh = flipped_shading(wo);
-        const f3 lwi = normalize(sh.global_to_local(wi));
-        const f3 lwo = normalize(sh.global_to_local(wo));
-        return (lwi.z <= 0.0f || lwo.z <= 0.0f) ? 0.0f : pdf_sample_hemisphere_zweighted(lwi);
-    }
-};
-
-__device__ __forceinline__ Shader create_shader(const SceneDevice &scene, const MaterialDesc &mat, const SurfacePoint &inct) {
-    Shader sh;
-    sh.type = mat.type;
-    sh.frame.geometry = inct.frame;
-    sh.frame.shading = inct.frame.rotate_to_new_z(inct.interp_z);
-    if (mat.normal_tex >= 0) {  // material/utils/normal_map.cpp:13-21
-        const f3 c = eval_texture(scene, mat.normal_tex, inct);
-        const f3 local_nor = 2.0f * c - f3(1.0f);
-        const f3 world_nor = sh.frame.shading.local_to_global(local_nor);
-        sh.frame.shading = sh.frame.shading.rotate_to_new_z(normalize(world_nor));
-    }
-    sh.shadow_terminator = mat.shadow_terminator != 0;
-    sh.albedo_value = mat.type == MAT_DIFFUSE ? eval_texture(scene, mat.color_tex, inct) : f3(0.0f);
-    return sh;
+    if (splat) film_splat3(film.radiance, pixel, splat_value);
+    warp_count(&ctl->n_splat, splat);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// medium (medium.cpp:36-164, 214-249): only launched when the scene has media (wavefront.cpp:254-268)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) medium_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQueue nq, ShadowQueue sq,
+                                                       FilmDevice film, WaveCtl *ctl) {
+    const int n = ctl->n_active;
+    const int n_round = (n + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool emit_next = false, emit_shadow = false, splat = false;
+        f3 splat_value(0.0f);
+        uint32_t pixel = 0;
+        NextState ns;
+        ShadowOut so;
+        if (i < n) {
+            const uint32_t flag = hq.flag[i];
+            const float4 o4 = q.ray_o[i], d4 = q.ray_d[i], beta4 = q.beta[i], rad4 = q.rad[i];
+            const ulonglong2 rng2 = q.rng[i];
+            const f3 o = xyz(o4), d = xyz(d4);
+            pixel = __float_as_uint(rad4.w);
+            Sampler sampler;
+            sampler.rng.state = rng2.x; sampler.rng.inc = rng2.y;
+            // get_medium_segment
+            uint32_t medium_id;
+            f3 medium_end;
+            if (flag & kFlagHasIntersection) {
+                const uint4 det = hq.detail[i];
+                const InstanceInfo &inst = scene.instances[flag & kFlagInstanceMask];
+                const GeometryInfo &geo = scene.geometries[inst.geometry_id];
+                const f3 inct_nor = xf_normal(inst.inv, xyz(ldg4(geo.gz_uca + det.y)));
+                const uint32_t inct_medium_id = dot(d, inct_nor) < 0.0f ? inst.outer_medium_id : inst.inner_medium_id;
+                medium_id = min(inct_medium_id, __float_as_uint(o4.w));  // resolve_mediums: smaller id = higher priority
+                medium_end = intersection_offset(o + __uint_as_float(det.x) * d, inct_nor, -d);
+            } else {
+                medium_id = scene.vol_prim_medium_id;
+                medium_end = o + normalize(d) * scene.world_diagonal;
+            }
+            q.ray_o[i] = make4(o, __uint_as_float(medium_id));
+            const MediumDesc &medium = scene.media[medium_id];
+            const MediumSample ms = medium_sample(scene, medium, o, medium_end, sampler);
+            const f3 unscatter_tr = medium_tr(scene, medium, o, medium_end, sampler);
+            if (medium.type != MED_VOLPRIM) {
+                const float4 ble4 = q.ble[i];
+                q.ble[i] = make4(xyz(ble4) * unscatter_tr, ble4.w);
+            }
+            if (!ms.scattered) {
+                if (medium.type != MED_VOLPRIM) q.rng[i] = make_ulonglong2(sampler.rng.state, sampler.rng.inc);
+            } else {
+                hq.flag[i] = flag | kFlagHasScattering;
+                f3 beta = xyz(beta4);  // throughput of both media is one
+                const f3 L = xyz(rad4);
+                const int depth = __float_as_int(beta4.w);
+                if (simple_russian_roulette(P, beta, depth, sampler)) {
+                    splat = true; splat_value = L;
+                } else {
+                    LiSample ls = sample_light_li<false>(scene, ms.position, f3(0.0f), sampler);
+                    const f3 wo = -d;
+                    if (ls.success) {
+                        const float ph = ms.shader.pdf(ls.d, wo);  // eval = color * pdf
+                        so.beta = ls.li * beta * (ms.shader.color * ph) / (ph + ls.light_pdf);
+                        so.o = ls.o; so.d = ls.d; so.t1 = ls.t1;
+                        so.med = ls.t1 > 1.0f ? scene.vol_prim_medium_id : medium_id;
+                        emit_shadow = true;
+                    }
+                    f3 phase, pdir;
+                    float ppdf;
+                    const float p0 = sampler.get1d(), p1 = sampler.get1d();
+                    (void)sampler.get1d();
+                    ms.shader.sample(wo, p0, p1, phase, pdir, ppdf);
+                    if (!is_zero(phase)) {
+                        ns.d = normalize(pdir);
+                        ns.ble = beta * phase;
+                        ns.beta = ns.ble / ppdf;
+                        ns.pdf = ppdf;
+                        ns.o = ms.position; ns.med = medium_id; ns.L = L; ns.depth = depth + 1;
+                        ns.rng = make_ulonglong2(sampler.rng.state, sampler.rng.inc);
+                        emit_next = true;
+                    } else {
+                        splat = true; splat_value = L;
+                    }
+                }
+            }
+        }
+        emit_outputs(nq, sq, film, ctl, pixel, emit_next, ns, emit_shadow, so, splat, splat_value);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shade (shade.cpp:38-235)
+// ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQueue nq, ShadowQueue sq,
                                                       FilmDevice film, WaveCtl *ctl) {
     const int n = ctl->n_active;
@@ -419,34 +327,23 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(SceneDevice scene, Render
         bool emit_next = false, emit_shadow = false, splat = false;
         f3 splat_value(0.0f);
         uint32_t pixel = 0;
-        // next state
-        f3 n_o, n_d, n_beta, n_L, n_ble;
-        float n_pdf = 0.0f;
-        uint32_t n_med = 0;
-        int n_depth = 0;
-        ulonglong2 n_rng = make_ulonglong2(0, 0);
-        // shadow ray
-        f3 s_o, s_d, s_beta;
-        float s_t1 = 0.0f;
-        uint32_t s_med = 0;
+        NextState ns;
+        ShadowOut so;
 
         if (i < n) {
             const uint32_t flag = hq.flag[i];
-            const float4 beta4 = q.beta[i], rad4 = q.rad[i], o4 = q.ray_o[i], d4 = q.ray_d[i], ble4 = q.ble[i];
-            const ulonglong2 rng2 = q.rng[i];
+            const bool scattered = (flag & kFlagHasScattering) != 0;
+            const float4 rad4 = q.rad[i], o4 = q.ray_o[i], d4 = q.ray_d[i], ble4 = q.ble[i];
             pixel = __float_as_uint(rad4.w);
-            f3 beta = xyz(beta4), L = xyz(rad4);
-            const int depth = __float_as_int(beta4.w);
+            f3 L = xyz(rad4);
             const f3 o = xyz(o4), d = xyz(d4);
-            const uint32_t ray_medium = __float_as_uint(o4.w);
             const f3 beta_le = xyz(ble4);
             const float bsdf_pdf = ble4.w;
-            Sampler sampler;
-            sampler.rng.state = rng2.x; sampler.rng.inc = rng2.y;
 
-            if (!(flag & kFlagHasIntersection)) {
-                // miss: no environment light yet => Le = 0; (shade.cpp:54-69)
-                splat = true; splat_value = L;
+            if (!(flag & kFlagHasIntersection)) {  // shade.cpp:54-69
+                f3 v = eval_miss_le(scene, d, beta_le, bsdf_pdf);
+                if (!scattered) v = v + L;
+                splat = true; splat_value = v;
             } else {
                 const uint4 det = hq.detail[i];
                 const InstanceInfo &inst = scene.instances[flag & kFlagInstanceMask];
@@ -454,79 +351,70 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(SceneDevice scene, Render
                 const SurfacePoint inct = get_hitinfo(o, d, inst, geo, __uint_as_float(det.x), det.y,
                                                       make_float2(__uint_as_float(det.z), __uint_as_float(det.w)));
                 const f3 le_rad = handle_intersected_light(scene, o, d, inct, beta_le, bsdf_pdf, inst.light_id);
-                L = L + le_rad;
-                if (simple_russian_roulette(P, beta, depth, sampler)) {
-                    splat = true; splat_value = L;
+                if (scattered) {
+                    splat = true; splat_value = le_rad;
                 } else {
-                    LiSample ls = sample_surface_light_li(scene, inct.position, inct.frame.z, sampler);
-                    const Shader shader = create_shader(scene, scene.materials[inst.material_id], inct);
-                    if (depth == 0) {
-                        if (film.albedo) film_splat3(film.albedo, pixel, shader.albedo());
-                        if (film.normal) film_splat3(film.normal, pixel, shader.normal());
-                    }
-                    const f3 wo = -d;
-                    const float b0 = sampler.get1d(), b1 = sampler.get1d(), b2 = sampler.get1d();
-                    BsdfSample bs = shader.sample(wo, b0, b1, b2);
-                    f3 shadow_bsdf_val(0.0f);
-                    float shadow_bsdf_pdf = 0.0f;
-                    if (ls.success) {
-                        shadow_bsdf_val = shader.eval(ls.d, wo);
-                        ls.success = !is_zero(shadow_bsdf_val);
-                        if (ls.success) shadow_bsdf_pdf = shader.pdf(ls.d, wo);
-                    }
-                    if (ls.success) {
-                        const bool shadow_d_out = dot(inct.frame.z, ls.d) > 0.0f;
-                        const bool last_ray_out = dot(inct.frame.z, d) < 0.0f;
-                        if (shadow_d_out == last_ray_out) s_med = ray_medium;
-                        else if (shadow_d_out) s_med = inst.outer_medium_id;
-                        else s_med = inst.inner_medium_id;
-                        const float cosv = fabsf(dot(normalize(ls.d), inct.frame.z));
-                        s_beta = ls.li * beta * shadow_bsdf_val * cosv / (shadow_bsdf_pdf + ls.light_pdf);
-                        s_o = ls.o; s_d = ls.d; s_t1 = ls.t1;
-                        emit_shadow = true;
-                    }
-                    if (!is_zero(bs.bsdf)) {
-                        const f3 dir = normalize(bs.dir);
-                        const float cosv = fabsf(dot(dir, inct.frame.z));
-                        const f3 new_beta_le = beta * cosv * bs.bsdf;
-                        beta = new_beta_le / bs.pdf;
-                        n_o = intersection_offset(inct.position, inct.frame.z, dir);
-                        n_d = dir;
-                        n_med = dot(inct.frame.z, dir) > 0.0f ? inst.outer_medium_id : inst.inner_medium_id;
-                        n_pdf = bs.is_delta ? -bs.pdf : bs.pdf;
-                        n_beta = beta; n_L = L; n_ble = new_beta_le; n_depth = depth + 1;
-                        n_rng = make_ulonglong2(sampler.rng.state, sampler.rng.inc);
-                        emit_next = true;
-                    } else {
+                    const float4 beta4 = q.beta[i];
+                    const ulonglong2 rng2 = q.rng[i];
+                    f3 beta = xyz(beta4);
+                    const int depth = __float_as_int(beta4.w);
+                    const uint32_t ray_medium = __float_as_uint(o4.w);
+                    Sampler sampler;
+                    sampler.rng.state = rng2.x; sampler.rng.inc = rng2.y;
+                    L = L + le_rad;
+                    if (simple_russian_roulette(P, beta, depth, sampler)) {
                         splat = true; splat_value = L;
+                    } else {
+                        LiSample ls = sample_light_li<true>(scene, inct.position, inct.frame.z, sampler);
+                        const Shader shader = create_shader(scene, scene.materials[inst.material_id], inct);
+                        if (depth == 0) {
+                            if (film.albedo) film_splat3(film.albedo, pixel, shader.albedo());
+                            if (film.normal) film_splat3(film.normal, pixel, shader.normal());
+                        }
+                        const f3 wo = -d;
+                        const float b0 = sampler.get1d(), b1 = sampler.get1d(), b2 = sampler.get1d();
+                        const BsdfSample bs = shader.sample(wo, b0, b1, b2);
+                        if (ls.success) {
+                            f3 shadow_bsdf_val;
+                            float shadow_bsdf_pdf;
+                            shader.eval_pdf(ls.d, wo, shadow_bsdf_val, shadow_bsdf_pdf);
+                            if (!is_zero(shadow_bsdf_val)) {
+                                const bool shadow_d_out = dot(inct.frame.z, ls.d) > 0.0f;
+                                const bool last_ray_out = dot(inct.frame.z, d) < 0.0f;
+                                if (shadow_d_out == last_ray_out) so.med = ray_medium;
+                                else if (shadow_d_out) so.med = inst.outer_medium_id;
+                                else so.med = inst.inner_medium_id;
+                                const float cosv = fabsf(dot(normalize(ls.d), inct.frame.z));
+                                so.beta = ls.li * beta * shadow_bsdf_val * cosv / (shadow_bsdf_pdf + ls.light_pdf);
+                                so.o = ls.o; so.d = ls.d; so.t1 = ls.t1;
+                                emit_shadow = true;
+                            }
+                        }
+                        if (!is_zero(bs.bsdf)) {
+                            const f3 dir = normalize(bs.dir);
+                            const float cosv = fabsf(dot(dir, inct.frame.z));
+                            ns.ble = beta * cosv * bs.bsdf;
+                            ns.beta = ns.ble / bs.pdf;
+                            ns.o = intersection_offset(inct.position, inct.frame.z, dir);
+                            ns.d = dir;
+                            ns.med = dot(inct.frame.z, dir) > 0.0f ? inst.outer_medium_id : inst.inner_medium_id;
+                            ns.pdf = bs.is_delta ? -bs.pdf : bs.pdf;
+                            ns.L = L; ns.depth = depth + 1;
+                            ns.rng = make_ulonglong2(sampler.rng.state, sampler.rng.inc);
+                            emit_next = true;
+                        } else {
+                            splat = true; splat_value = L;
+                        }
                     }
                 }
             }
         }
-
-        // ---- converged: warp-aggregated queue appends
-        const int next_slot = warp_alloc(&ctl->n_next, emit_next);
-        if (emit_next) {
-            nq.ray_o[next_slot] = make4(n_o, __uint_as_float(n_med));
-            nq.ray_d[next_slot] = make4(n_d, kMaxFloat);
-            nq.beta[next_slot] = make4(n_beta, __int_as_float(n_depth));
-            nq.rad[next_slot] = make4(n_L, __uint_as_float(pixel));
-            nq.rng[next_slot] = n_rng;
-            nq.ble[next_slot] = make4(n_ble, n_pdf);
-        }
-        const int shadow_slot = warp_alloc(&ctl->n_shadow, emit_shadow);
-        if (emit_shadow) {
-            sq.ray_o[shadow_slot] = make4(s_o, __uint_as_float(s_med));
-            sq.ray_d[shadow_slot] = make4(s_d, s_t1);
-            sq.beta_li[shadow_slot] = make4(s_beta, __uint_as_float(pixel));
-        }
-        if (splat) film_splat3(film.radiance, pixel, splat_value);
-        warp_count(&ctl->n_splat, splat);
+        emit_outputs(nq, sq, film, ctl, pixel, emit_next, ns, emit_shadow, so, splat, splat_value);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// shadow rays (shadow.cpp:24-74): occlusion with early exit; unoccluded => splat beta_li * Tr (Tr = 1 without media)
+// shadow rays (shadow.cpp:24-74): occlusion with early exit; unoccluded => splat beta_li * Tr
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) shadow_kernel(SceneDevice scene, RenderParams P, ShadowQueue sq, FilmDevice film, WaveCtl *ctl) {
     const int n = ctl->n_shadow;
@@ -542,7 +430,9 @@ __global__ void __launch_bounds__(kBlock) shadow_kernel(SceneDevice scene, Rende
             const HitRec h = traverse_bvh2<true>(scene.bvh, xyz(o4), xyz(d4), d4.w);
             if (h.slot < 0) {
                 const float4 b4 = sq.beta_li[i];
-                film_splat3(film.radiance, __float_as_uint(b4.w), xyz(b4));
+                f3 v = xyz(b4);
+                if (scene.has_medium) v = v * shadow_tr(scene, o4, d4);
+                film_splat3(film.radiance, __float_as_uint(b4.w), v);
                 misses += 1;
             }
         }
@@ -588,6 +478,11 @@ void launch_trace(const LaunchCfg &cfg, const SceneDevice &scene, PathQueue cur,
 void launch_shade(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, HitQueue hit, PathQueue next,
                   ShadowQueue shadow, FilmDevice film, WaveCtl *ctl, cudaStream_t stream) {
     shade_kernel<<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
+}
+
+void launch_medium(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, HitQueue hit, PathQueue next,
+                   ShadowQueue shadow, FilmDevice film, WaveCtl *ctl, cudaStream_t stream) {
+    medium_kernel<<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
 }
 
 void launch_shadow(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, ShadowQueue shadow, FilmDevice film, WaveCtl *ctl,

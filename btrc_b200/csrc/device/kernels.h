@@ -23,6 +23,9 @@ void launch_generate(const LaunchCfg &cfg, const SceneDevice &scene, const Rende
 void launch_trace(const LaunchCfg &cfg, const SceneDevice &scene, PathQueue cur, HitQueue hit, WaveCtl *ctl, cudaStream_t stream);
 void launch_shade(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, HitQueue hit,
                   PathQueue next, ShadowQueue shadow, FilmDevice film, WaveCtl *ctl, cudaStream_t stream);
+// sample_medium_scattering_kernel (medium.cpp:28-164): runs between trace and shade when the scene has media
+void launch_medium(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, HitQueue hit,
+                   PathQueue next, ShadowQueue shadow, FilmDevice film, WaveCtl *ctl, cudaStream_t stream);
 void launch_shadow(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, ShadowQueue shadow, FilmDevice film,
                    WaveCtl *ctl, cudaStream_t stream);
 // out = value.xyz / weight (normalise == 1: renormalise as a direction); out.w = 1

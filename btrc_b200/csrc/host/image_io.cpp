@@ -1,6 +1,7 @@
 #include "image_io.h"
 
 #include <zlib.h>
+#include <cstdio>
 
 #include <algorithm>
 #include <cmath>
@@ -163,10 +164,72 @@ void save_image_rgba32f(const std::string &filename, int width, int height, cons
         throw Error("unknown image format: " + filename);
 }
 
+// Radiance .hdr (RGBE; flat or new-style RLE scanlines), "-Y h +X w" orientation -- what stbi_loadf reads
+static LoadedImage load_hdr(const std::string &filename) {
+    std::ifstream f(filename, std::ios::binary);
+    if (!f) throw Error("failed to open file: " + filename);
+    std::vector<uint8_t> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    size_t p = 0;
+    auto getline = [&]() {
+        std::string l;
+        while (p < buf.size() && buf[p] != '\n') l.push_back((char)buf[p++]);
+        ++p;
+        return l;
+    };
+    std::string l = getline();
+    if (l.rfind("#?", 0) != 0) throw Error("failed to load image: " + filename);
+    while (p < buf.size() && !(l = getline()).empty()) {}
+    l = getline();
+    int w = 0, h = 0;
+    if (std::sscanf(l.c_str(), "-Y %d +X %d", &h, &w) != 2 || w <= 0 || h <= 0) throw Error("unsupported hdr orientation: " + filename);
+    LoadedImage img;
+    img.width = w; img.height = h; img.channels = 3; img.is_float = true;
+    img.f32.resize((size_t)w * h * 3);
+    std::vector<uint8_t> row(4 * (size_t)w);
+    for (int y = 0; y < h; ++y) {
+        bool rle = false;
+        if (w >= 8 && w < 32768 && p + 4 <= buf.size() && buf[p] == 2 && buf[p + 1] == 2 && (buf[p + 2] & 0x80) == 0) {
+            rle = ((int(buf[p + 2]) << 8) | buf[p + 3]) == w;
+        }
+        if (rle) {
+            p += 4;
+            for (int c = 0; c < 4; ++c) {
+                int x = 0;
+                while (x < w) {
+                    if (p >= buf.size()) throw Error("failed to load image: " + filename);
+                    int count = buf[p++];
+                    if (count > 128) {
+                        count -= 128;
+                        if (p >= buf.size() || x + count > w) throw Error("failed to load image: " + filename);
+                        const uint8_t v = buf[p++];
+                        for (int k = 0; k < count; ++k) row[4 * (size_t)(x++) + c] = v;
+                    } else {
+                        if (p + count > buf.size() || x + count > w) throw Error("failed to load image: " + filename);
+                        for (int k = 0; k < count; ++k) row[4 * (size_t)(x++) + c] = buf[p++];
+                    }
+                }
+            }
+        } else {
+            if (p + 4 * (size_t)w > buf.size()) throw Error("failed to load image: " + filename);
+            std::memcpy(row.data(), &buf[p], 4 * (size_t)w);
+            p += 4 * (size_t)w;
+        }
+        for (int x = 0; x < w; ++x) {
+            const uint8_t *q = &row[4 * (size_t)x];
+            float *o = &img.f32[3 * ((size_t)y * w + x)];
+            if (q[3] == 0) { o[0] = o[1] = o[2] = 0; continue; }
+            const float s = std::ldexp(1.0f, int(q[3]) - (128 + 8));
+            o[0] = q[0] * s; o[1] = q[1] * s; o[2] = q[2] * s;
+        }
+    }
+    return img;
+}
+
 LoadedImage load_image(const std::string &filename) {
     const std::string ext = lower_ext(filename);
     if (ext == "png") return load_png(filename);
-    throw Error("unsupported image format (use .png): " + filename);
+    if (ext == "hdr") return load_hdr(filename);
+    throw Error("unsupported image format (use .png or .hdr): " + filename);
 }
 
 }  // namespace btrc

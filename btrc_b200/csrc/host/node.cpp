@@ -376,8 +376,29 @@ Transform3D Node::as_transform3d() const {  // node.cpp:166-213
     if (auto s = find("scale")) { const Vec3 v = s->as_vec3(); return Transform3D::scale(v.x, v.y, v.z); }
     throw Error("unknown transform3d type");
 }
+// node.cpp:126-164.  translate / scale go through parse<Vec2f>, which the reference never instantiates
+// (node.cpp:321-324 throws "unimplemented"); kept.  Products are true 3x3 products (the reference's Mat3 operator*
+// reads a fourth column that does not exist: utils/math/mat3.cpp:108-123).
 Mat3 Node::as_transform2d() const {
-    throw Error("transform2d: unimplemented");
+    if (is_array()) {
+        Mat3 ret = Mat3::identity();
+        for (auto &e : elements) ret = e->as_transform2d() * ret;
+        return ret;
+    }
+    if (find("translate") || find("scale")) throw Error("unimplemented");
+    auto rows = [](float a, float b, float c, float d, float e, float f, float g, float h, float i) {
+        Mat3 m = {{{a, b, c}, {d, e, f}, {g, h, i}}};
+        return m;
+    };
+    if (auto r = find("rotate")) {
+        const float rad = r->child("angle")->as_radian();
+        const float S = std::sin(rad), C = std::cos(rad);
+        return rows(C, -S, 0, S, C, 0, 0, 0, 1);
+    }
+    if (auto n = find("inverse_u"); n && n->as_bool()) return rows(-1, 0, 1, 0, 1, 0, 0, 0, 0);
+    if (auto n = find("inverse_v"); n && n->as_bool()) return rows(1, 0, 0, 0, -1, 1, 0, 0, 1);
+    if (auto n = find("swap_uv"); n && n->as_bool()) return rows(0, 1, 0, 1, 0, 0, 0, 0, 1);
+    throw Error("unknown transform2d type");
 }
 int Node::int_or(const std::string &name, int d) const { auto c = find(name); return c ? c->as_int() : d; }
 float Node::float_or(const std::string &name, float d) const { auto c = find(name); return c ? c->as_float() : d; }

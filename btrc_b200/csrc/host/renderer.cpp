@@ -82,6 +82,8 @@ void Renderer::render_range(long long begin, long long end) {
     BTRC_CUDA(cudaMemcpyAsync(ctl_, &init, sizeof(init), cudaMemcpyHostToDevice, stream_));
     BTRC_CUDA(cudaEventRecord(ev_begin_, stream_));
 
+    const bool has_medium = scene_.dev.has_medium != 0;
+    const int kernels_per_iter = has_medium ? 6 : 5;
     int cur = 0;
     long long iter = 0;
     bool done = false;
@@ -102,6 +104,8 @@ void Renderer::render_range(long long begin, long long end) {
         launch_generate(cfg_, scene_.dev, params, q_[cur], film_, ctl_, stream_);
         mark();
         launch_trace(cfg_, scene_.dev, q_[cur], hit_, ctl_, stream_);
+        mark();
+        if (has_medium) launch_medium(cfg_, scene_.dev, params, q_[cur], hit_, q_[cur ^ 1], shadow_, film_, ctl_, stream_);
         mark();
         launch_shade(cfg_, scene_.dev, params, q_[cur], hit_, q_[cur ^ 1], shadow_, film_, ctl_, stream_);
         mark();
@@ -137,13 +141,15 @@ void Renderer::render_range(long long begin, long long end) {
     stats_.n_splat += fin.n_splat;
     stats_.n_iter += fin.n_iter;
     stats_.render_ms = ms;
-    stats_.n_launches = 5ull * (unsigned long long)iter;
+    stats_.n_launches = (unsigned long long)kernels_per_iter * (unsigned long long)iter;
     for (double &v : stats_.stage_ms) v = 0;
-    for (size_t k = 0; k + 4 < n_prof; k += 5) {
-        for (int st = 0; st < 4; ++st) {
+    // events per iteration: after prepare, generate, trace, medium, shade, shadow  => intervals gen, trace, medium, shade, shadow
+    static const int kStageOfInterval[5] = {0, 1, 4, 2, 3};
+    for (size_t k = 0; k + 5 < n_prof; k += 6) {
+        for (int iv = 0; iv < 5; ++iv) {
             float t = 0;
-            BTRC_CUDA(cudaEventElapsedTime(&t, prof_events_[k + st], prof_events_[k + st + 1]));
-            stats_.stage_ms[st] += t;
+            BTRC_CUDA(cudaEventElapsedTime(&t, prof_events_[k + iv], prof_events_[k + iv + 1]));
+            stats_.stage_ms[kStageOfInterval[iv]] += t;
         }
     }
 }
@@ -177,6 +183,20 @@ void Renderer::stage_shade(int n, int *n_next, int *n_shadow) {
     c.n_active = n; c.pool = pool_;
     BTRC_CUDA(cudaMemcpyAsync(ctl_, &c, sizeof(c), cudaMemcpyHostToDevice, stream_));
     launch_shade(cfg_, scene_.dev, scene_.render_params(), q_[0], hit_, q_[1], shadow_, film_, ctl_, stream_);
+    BTRC_CUDA(cudaMemcpyAsync(&c, ctl_, sizeof(c), cudaMemcpyDeviceToHost, stream_));
+    BTRC_CUDA(cudaStreamSynchronize(stream_));
+    BTRC_CUDA(cudaGetLastError());
+    *n_next = c.n_next;
+    *n_shadow = c.n_shadow;
+}
+
+void Renderer::stage_medium(int n, int *n_next, int *n_shadow) {
+    if (n > pool_) throw Error("stage batch larger than state_count");
+    WaveCtl c;
+    std::memset(&c, 0, sizeof(c));
+    c.n_active = n; c.pool = pool_;
+    BTRC_CUDA(cudaMemcpyAsync(ctl_, &c, sizeof(c), cudaMemcpyHostToDevice, stream_));
+    launch_medium(cfg_, scene_.dev, scene_.render_params(), q_[0], hit_, q_[1], shadow_, film_, ctl_, stream_);
     BTRC_CUDA(cudaMemcpyAsync(&c, ctl_, sizeof(c), cudaMemcpyDeviceToHost, stream_));
     BTRC_CUDA(cudaStreamSynchronize(stream_));
     BTRC_CUDA(cudaGetLastError());

@@ -17,8 +17,8 @@ namespace btrc {
 struct RenderStats {
     uint64_t n_gen = 0, n_closest = 0, n_hit = 0, n_next = 0, n_shadow = 0, n_shadow_miss = 0, n_splat = 0, n_iter = 0;
     double render_ms = 0;  // device time of the last render_range (CUDA events)
-    // per-stage device time of the last render_range (only when profiling is on): generate, trace, shade, shadow
-    double stage_ms[4] = {0, 0, 0, 0};
+    // per-stage device time of the last render_range (only when profiling is on): generate, trace, shade, shadow, medium
+    double stage_ms[5] = {0, 0, 0, 0, 0};
     uint64_t n_launches = 0;  // kernels launched by the last render_range
 };
 
@@ -42,6 +42,7 @@ public:
     void stage_generate(long long first, int n);                  // fills queue(0)[0, n)
     void stage_trace(int n);                                      // queue(0) -> hits()
     void stage_shade(int n, int *n_next, int *n_shadow);          // queue(0) + hits() -> queue(1), shadows()
+    void stage_medium(int n, int *n_next, int *n_shadow);         // same, medium stage (updates queue(0) / hits() in place)
     void stage_shadow(int n);                                     // shadows()[0, n) -> film
     const LaunchCfg &launch_cfg() const { return cfg_; }
 

@@ -1,6 +1,11 @@
 #include "scene.h"
 
+#include "image_io.h"
+
+#include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <filesystem>
 #include <functional>
 
@@ -71,28 +76,175 @@ std::unique_ptr<Scene> Scene::from_string(const std::string &json, const std::st
     return s;
 }
 
+Scene::~Scene() { release_textures(); }
+
+void Scene::release_textures() {
+    for (auto &src : sources) {
+        if (src.tex) cudaDestroyTextureObject(src.tex);
+        if (src.array) cudaFreeArray(src.array);
+        src.tex = 0;
+        src.array = nullptr;
+    }
+}
+
+static int parse_address_mode(const std::string &s) {  // description.cpp:7-18
+    if (s == "clamp") return 0;
+    if (s == "wrap") return 1;
+    if (s == "mirror") return 2;
+    if (s == "border") return 3;
+    throw Error("unknown address mode: " + s);
+}
+
+void Scene::parse_texture_desc(const NodeP &node, TextureSource &src) const {  // description.cpp:28-80
+    with_context("in parsing texture description", [&]() {
+        src.address[0] = parse_address_mode(node->string_or("address_mode_u", "clamp"));
+        src.address[1] = parse_address_mode(node->string_or("address_mode_v", "clamp"));
+        src.address[2] = parse_address_mode(node->string_or("address_mode_w", "clamp"));
+        const std::string filter = node->string_or("filter", "linear");
+        if (filter == "point") src.linear = false;
+        else if (filter == "linear") src.linear = true;
+        else throw Error("unknown filter mode: " + filter);
+        src.srgb = node->bool_or("srgb_to_linear", false);
+        if (auto n = node->find("border")) {
+            if (n->is_array()) {
+                if (n->elements.size() == 1) {
+                    const float v = n->elements[0]->as_float();
+                    for (float &b : src.border) b = v;
+                } else if (n->elements.size() == 3) {
+                    for (int k = 0; k < 3; ++k) src.border[k] = n->elements[k]->as_float();
+                } else
+                    throw Error("invalid border array size");
+            } else if (n->is_value()) {
+                const float v = n->as_float();
+                for (float &b : src.border) b = v;
+            } else
+                throw Error("border: expect array or value node");
+        }
+        return 0;
+    });
+}
+
+int Scene::constant_texture2d(float v) {
+    Tex2DNode t;
+    t.type = TEXOP_CONST;
+    t.value = Vec3(v);
+    textures.push_back(t);
+    return (int)textures.size() - 1;
+}
+
 int Scene::create_texture2d(const NodeP &node) {
     return with_context("in creating texture2d", [&]() -> int {
         auto it = tex_pool_.find(node.get());
         if (it != tex_pool_.end()) return it->second;
-        TextureDesc t{};
-        if (node->is_value() || node->is_array()) {  // context.h:211-220: literal => Constant2D (not pooled)
-            const Vec3 v = node->as_vec3();
-            t.type = TEX_CONSTANT;
-            t.value[0] = v.x; t.value[1] = v.y; t.value[2] = v.z;
-            textures.push_back(t);
-            return (int)textures.size() - 1;
+        Tex2DNode t;
+        if (node->is_value() || node->is_array()) {  // context.h:211-220: literal => Constant2D
+            t.type = TEXOP_CONST;
+            t.value = node->as_vec3();
+        } else {
+            const std::string type = node->child("type")->as_string();
+            if (type == "constant") {
+                t.type = TEXOP_CONST;
+                t.value = node->child("value")->as_vec3();
+            } else if (type == "array") {  // array2d.cpp:32-39; utils/image.cpp:299-335; cuda/array.cpp:136-149
+                TextureSource src;
+                const std::string filename = resolve_path(node->child("filename")->as_string());
+                parse_texture_desc(node, src);
+                LoadedImage img = load_image(filename);
+                src.width = img.width; src.height = img.height;
+                const size_t npx = (size_t)img.width * img.height;
+                if (img.is_float) {  // Image<Vec3f> -> F32x4
+                    src.is_float = true; src.channels = 4;
+                    src.f32.resize(4 * npx);
+                    for (size_t i = 0; i < npx; ++i) {
+                        for (int k = 0; k < 3; ++k) src.f32[4 * i + k] = img.f32[3 * i + k];
+                        src.f32[4 * i + 3] = 1.0f;
+                    }
+                } else if (img.channels == 1) {  // UNorm8x1
+                    src.channels = 1;
+                    src.u8 = std::move(img.u8);
+                } else if (img.channels == 3 || img.channels == 4) {  // UNorm8x4 (alpha 255 for rgb)
+                    src.channels = 4;
+                    src.u8.resize(4 * npx);
+                    for (size_t i = 0; i < npx; ++i) {
+                        for (int k = 0; k < 3; ++k) src.u8[4 * i + k] = img.u8[img.channels * i + k];
+                        src.u8[4 * i + 3] = img.channels == 4 ? img.u8[4 * i + 3] : 255;
+                    }
+                } else
+                    throw Error("ImageDynamic::load: unsupported channels: " + std::to_string(img.channels));
+                sources.push_back(std::move(src));
+                t.type = TEXOP_ARRAY;
+                t.source = (int)sources.size() - 1;
+            } else if (type == "add" || type == "sub" || type == "mul" || type == "div") {  // math.cpp
+                t.type = type == "add" ? TEXOP_ADD : type == "sub" ? TEXOP_SUB : type == "mul" ? TEXOP_MUL : TEXOP_DIV;
+                t.lhs = create_texture2d(node->child("lhs"));
+                t.rhs = create_texture2d(node->child("rhs"));
+            } else if (type == "transform") {  // transform.cpp:43-53
+                t.type = 6;
+                t.m = node->child("transform")->as_transform2d();
+                t.lhs = create_texture2d(node->child("tex"));
+            } else
+                throw Error("unknown texture2d type: " + type);
         }
-        const std::string type = node->child("type")->as_string();
-        if (type == "constant") {
-            const Vec3 v = node->child("value")->as_vec3();
-            t.type = TEX_CONSTANT;
-            t.value[0] = v.x; t.value[1] = v.y; t.value[2] = v.z;
-        } else
-            throw Error("unknown texture2d type: " + type);
         textures.push_back(t);
         tex_pool_[node.get()] = (int)textures.size() - 1;
         return (int)textures.size() - 1;
+    });
+}
+
+// Text grid "<byte|float> <channels> <W> <H> <D>" + values, x fastest (utils/cuda/array.cpp:313-385)
+static void load_text_grid(const std::string &filename, TextureSource &src) {
+    const std::string text = read_text_file(filename);
+    const char *p = text.c_str();
+    char comp[16] = {0};
+    int channels = 0, w = 0, h = 0, d = 0, used = 0;
+    if (std::sscanf(p, "%15s %d %d %d %d%n", comp, &channels, &w, &h, &d, &used) != 5) throw Error("Array::load_from_text: failed to parse file head");
+    p += used;
+    if (channels != 1 && channels != 3 && channels != 4) throw Error("unsupported channel count: " + std::to_string(channels));
+    if (std::string(comp) == "byte") throw Error("byte text grids are not supported (the reference reads them as characters into SNorm8: SURVEY B.5)");
+    if (std::string(comp) != "float") throw Error(std::string("unknown component type: ") + comp);
+    const size_t n = (size_t)w * h * d;
+    src.width = w; src.height = h; src.depth = d;
+    src.is_float = true;
+    src.channels = channels == 1 ? 1 : 4;
+    src.f32.resize(n * src.channels);
+    for (int k = 0; k < 3; ++k) src.max_value[k] = -3.402823466e+38f;
+    for (size_t i = 0; i < n; ++i) {
+        for (int c = 0; c < channels; ++c) {
+            char *end = nullptr;
+            const float v = std::strtof(p, &end);
+            if (end == p) throw Error("failed to load " + filename);
+            p = end;
+            src.f32[i * src.channels + c] = v;
+            if (c < 3) src.max_value[c] = std::max(src.max_value[c], v);
+        }
+        if (channels == 3) src.f32[i * 4 + 3] = 1.0f;
+    }
+}
+
+int Scene::create_texture3d(const NodeP &node) {
+    return with_context("in creating texture3d", [&]() -> int {
+        auto it = tex3d_pool_.find(node.get());
+        if (it != tex3d_pool_.end()) return it->second;
+        Tex3DNode t;
+        if (node->is_value() || node->is_array()) {
+            t.value = node->as_vec3();
+        } else {
+            const std::string type = node->child("type")->as_string();
+            if (type == "constant") {
+                t.value = node->child("value")->as_vec3();
+            } else if (type == "array") {  // texture3d/array3d.cpp:53-62
+                TextureSource src;
+                parse_texture_desc(node, src);
+                load_text_grid(resolve_path(node->child("text")->as_string()), src);
+                sources.push_back(std::move(src));
+                t.is_array = true;
+                t.source = (int)sources.size() - 1;
+            } else
+                throw Error("unknown texture3d type: " + type);
+        }
+        textures3d.push_back(t);
+        tex3d_pool_[node.get()] = (int)textures3d.size() - 1;
+        return (int)textures3d.size() - 1;
     });
 }
 
@@ -102,20 +254,123 @@ int Scene::create_material(const NodeP &node) {
         if (it != mat_pool_.end()) return it->second;
         const std::string type = node->child("type")->as_string();
         MaterialDesc m{};
-        m.color_tex = m.normal_tex = -1;
+        for (int &t : m.tex) t = -1;
+        m.normal_tex = -1;
         m.shadow_terminator = 1;
+        auto req = [&](int slot, const char *name) { m.tex[slot] = create_texture2d(node->child(name)); };
+        auto opt = [&](int slot, const char *name, float d) {
+            if (auto n = node->find(name)) m.tex[slot] = create_texture2d(n);
+            else m.tex[slot] = constant_texture2d(d);
+        };
+        bool has_normal = true, has_st = true;
         if (type == "diffuse") {  // material/diffuse.cpp:36-48
             m.type = MAT_DIFFUSE;
-            m.shadow_terminator = node->bool_or("shadow_terminator_term", true) ? 1 : 0;
-            m.color_tex = create_texture2d(node->child("color"));
-            if (auto n = node->find("normal")) m.normal_tex = create_texture2d(n);
+            req(SLOT_COLOR, "color");
+        } else if (type == "disney") {  // material/disney.cpp:844-894
+            m.type = MAT_DISNEY;
+            req(SLOT_COLOR, "color"); req(SLOT_METALLIC, "metallic"); req(SLOT_ROUGHNESS, "roughness");
+            opt(SLOT_TRANSMISSION, "transmission", 0); opt(SLOT_IOR, "ior", 1.5f); opt(SLOT_SPECULAR, "specular", 1);
+            opt(SLOT_SPECULAR_TINT, "specular_tint", 0); opt(SLOT_ANISOTROPIC, "anisotropic", 0); opt(SLOT_SHEEN, "sheen", 0);
+            opt(SLOT_SHEEN_TINT, "sheen_tint", 0); opt(SLOT_CLEARCOAT, "clearcoat", 0); opt(SLOT_CLEARCOAT_GLOSS, "clearcoat_gloss", 1);
+            if (auto n = node->find("transmission_roughness")) m.tex[SLOT_TRANSMISSION_ROUGHNESS] = create_texture2d(n);
+            else m.tex[SLOT_TRANSMISSION_ROUGHNESS] = m.tex[SLOT_ROUGHNESS];
+        } else if (type == "metal") {  // material/metal.cpp:50-77
+            m.type = MAT_METAL;
+            req(SLOT_COLOR, "color"); req(SLOT_ROUGHNESS, "roughness"); opt(SLOT_ANISOTROPIC, "anisotropic", 0);
+        } else if (type == "glass") {  // material/glass.cpp:141-157
+            m.type = MAT_GLASS; has_st = false;
+            req(SLOT_COLOR, "color"); req(SLOT_IOR, "ior");
+        } else if (type == "mirror") {  // material/mirror.cpp:91-103
+            m.type = MAT_MIRROR; has_st = false;
+            req(SLOT_COLOR, "color");
         } else if (type == "black") {
-            m.type = MAT_BLACK;
+            m.type = MAT_BLACK; has_normal = has_st = false;
+        } else if (type == "invisible") {
+            m.type = MAT_INVISIBLE; has_normal = has_st = false;
         } else
             throw Error("unknown material type: " + type);
+        if (has_st) m.shadow_terminator = node->bool_or("shadow_terminator_term", true) ? 1 : 0;
+        if (has_normal) if (auto n = node->find("normal")) m.normal_tex = create_texture2d(n);  // utils/normal_map.cpp:5-11
         materials.push_back(m);
         mat_pool_[node.get()] = (int)materials.size() - 1;
         return (int)materials.size() - 1;
+    });
+}
+
+static void mat4_to_3x4(const Mat4 &m, float *out) {
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) out[4 * r + c] = m.m[r][c];
+}
+
+// Returns a handle into `media`.  "transform" wrappers (factory/context.h:146-165, core/medium.cpp:98-129) are folded
+// into the wrapped medium's world_to_local: inner(outer(p)).
+int Scene::create_medium(const NodeP &node, const Mat4 *outer) {
+    return with_context("in creating medium", [&]() -> int {
+        if (!outer) {
+            auto it = med_pool_.find(node.get());
+            if (it != med_pool_.end()) return it->second;
+        }
+        const std::string type = node->child("type")->as_string();
+        int handle = -1;
+        if (type == "transform") {
+            Mat4 w2l;
+            if (auto t = node->find("world_to_local")) w2l = t->as_transform3d().mat;
+            else w2l = node->child("local_to_world")->as_transform3d().inv;
+            if (outer) w2l = w2l * *outer;
+            handle = create_medium(node->child("medium"), &w2l);
+        } else if (type == "homogeneous") {  // medium/homogeneous.cpp:80-92
+            HostMedium m;
+            m.priority = node->float_or("priority", 0.0f);
+            m.desc.type = MED_HOMOGENEOUS;
+            m.desc.sigma_t = node->child("sigma_t")->as_float();
+            const Vec3 a = node->child("albedo")->as_vec3();
+            m.desc.albedo[0] = a.x; m.desc.albedo[1] = a.y; m.desc.albedo[2] = a.z;
+            m.desc.g = node->float_or("g", 0.0f);
+            m.desc.sigma_t_tex = m.desc.albedo_tex = m.desc.g_tex = -1;
+            media.push_back(m);
+            handle = (int)media.size() - 1;
+        } else if (type == "hetergeneous") {  // medium/hetergeneous.cpp:113-135
+            HostMedium m;
+            m.priority = node->float_or("priority", 0.0f);
+            m.desc.type = MED_HETEROGENEOUS;
+            m.desc.sigma_t_tex = create_texture3d(node->child("sigma_t"));
+            m.desc.albedo_tex = create_texture3d(node->child("albedo"));
+            if (auto g = node->find("g")) m.desc.g_tex = create_texture3d(g);
+            else {
+                textures3d.push_back(Tex3DNode());  // Constant3D(0)
+                m.desc.g_tex = (int)textures3d.size() - 1;
+            }
+            if (outer) { m.desc.has_transform = 1; mat4_to_3x4(*outer, m.desc.world_to_local); }
+            const Tex3DNode &st = textures3d[m.desc.sigma_t_tex];
+            const float mx = st.is_array ? sources[st.source].max_value[0] : st.value.x;
+            m.desc.inv_max_density = 1.0f / std::max(mx, 0.001f);  // hetergeneous.cpp:33-34
+            media.push_back(m);
+            handle = (int)media.size() - 1;
+        } else
+            throw Error("unknown medium type: " + type);
+        if (!outer) med_pool_[node.get()] = handle;
+        return handle;
+    });
+}
+
+void Scene::create_envir_light(const NodeP &node) {
+    with_context("in creating light", [&]() {
+        const std::string type = node->child("type")->as_string();
+        if (type == "gradient_sky") {  // light/gradient_sky.cpp:56-67
+            env.type = ENV_GRADIENT_SKY;
+            env.upper = node->child("upper")->as_vec3();
+            env.lower = node->child("lower")->as_vec3();
+            env.up = normalize(node->child("up")->as_vec3());
+        } else if (type == "ibl") {  // light/ibl.cpp:89-102
+            env.type = ENV_IBL;
+            env.tex = create_texture2d(node->child("tex"));
+            env.up = node->find("up") ? node->child("up")->as_vec3() : Vec3(0, 0, 1);
+            env.lut_w = node->int_or("lut_width", 400);
+            env.lut_h = node->int_or("lut_height", 200);
+        } else if (type == "mesh_light")
+            throw Error("'envir_light' is not an environment light");
+        else
+            throw Error("unknown light type: " + type);
+        return 0;
     });
 }
 
@@ -145,7 +400,8 @@ void Scene::create(const NodeP &root) {
             inst.geometry_id = create_geometry(ent->child("geometry"));
             inst.material_id = create_material(ent->child("material"));
             if (auto t = ent->find("local_to_world")) inst.transform = t->as_transform3d();
-            if (ent->find("inner_medium") || ent->find("outer_medium")) throw Error("unknown medium type: (media are not supported yet)");
+            if (auto mn = ent->find("inner_medium")) inst.inner_medium = create_medium(mn, nullptr);
+            if (auto mn = ent->find("outer_medium")) inst.outer_medium = create_medium(mn, nullptr);
             if (auto ln = ent->find("light")) {
                 with_context("in creating light", [&]() {
                     const std::string type = ln->child("type")->as_string();
@@ -163,8 +419,11 @@ void Scene::create(const NodeP &root) {
             if (ent->bool_or("caustics_receiver", false)) inst.flag |= 2u;
             instances.push_back(inst);
         }
-        if (scene_node->find("volumes")) throw Error("'volumes' are not supported yet");
-        if (scene_node->find("envir_light")) throw Error("unknown light type: (environment lights are not supported yet)");
+        if (auto v = scene_node->find("volumes")) {
+            if (!v->is_array()) throw Error("'volumes' is not an array node");
+            if (!v->elements.empty()) throw Error("volume primitives ('volumes') are not supported yet");
+        }
+        if (auto e = scene_node->find("envir_light")) create_envir_light(e);
         return 0;
     });
     width = root->child("width")->as_int();
@@ -242,9 +501,7 @@ RenderParams Scene::render_params() const {
     return p;
 }
 
-static void to_3x4(const Mat4 &m, float *out) {
-    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) out[4 * r + c] = m.m[r][c];
-}
+static void to_3x4(const Mat4 &m, float *out) { mat4_to_3x4(m, out); }
 
 static int tree_depth(const BinaryBvh &b) {
     int best = 0;
@@ -264,6 +521,25 @@ void Scene::commit() {
     buffers_.clear();
     dev = SceneDevice{};
     device_ready_ = false;
+
+    // ---- medium ids (core/scene.cpp:136-161): real media by descending priority (ties: creation order), then the
+    // volume-primitive medium.  A null medium means the volume-primitive medium.
+    std::vector<int> order(media.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return media[a].priority > media[b].priority; });
+    std::vector<int> medium_id_of(media.size());
+    medium_table.clear();
+    for (size_t i = 0; i < order.size(); ++i) {
+        medium_id_of[order[i]] = (int)i;
+        medium_table.push_back(media[order[i]].desc);
+    }
+    const uint32_t vol_prim_id = (uint32_t)medium_table.size();
+    {
+        MediumDesc vp{};
+        vp.type = MED_VOLPRIM;
+        medium_table.push_back(vp);
+    }
+    has_medium = false;
 
     // ---- lights + instance table (core/scene.cpp:94-100, 163-207)
     lights.clear();
@@ -287,8 +563,9 @@ void Scene::commit() {
         inst.light_id = info.light_id;
         to_3x4(inst.transform.mat, info.mat);
         to_3x4(inst.transform.inv, info.inv);
-        // no media: the only medium is the (empty) volume-primitive medium with id 0 (scene.cpp:136-161)
-        info.inner_medium_id = info.outer_medium_id = 0;
+        info.inner_medium_id = inst.inner_medium >= 0 ? (uint32_t)medium_id_of[inst.inner_medium] : vol_prim_id;
+        info.outer_medium_id = inst.outer_medium >= 0 ? (uint32_t)medium_id_of[inst.outer_medium] : vol_prim_id;
+        if (inst.inner_medium >= 0 || inst.outer_medium >= 0) has_medium = true;
         info.flag = inst.flag;
         instance_info.push_back(info);
     }
@@ -386,9 +663,73 @@ void Scene::commit() {
     }
 }
 
+// Postfix program of a texture graph node; `m` = uv transform accumulated from the "transform" wrappers above it.
+void Scene::emit_tex_ops(int node, const Mat3 &m, std::vector<TexOp> &ops) const {
+    const Tex2DNode &t = textures[node];
+    if (t.type == 6) {  // uv' = t.m.apply_to_point(m.apply_to_point(uv)): affine composition of rows 0 and 1
+        Mat3 c = Mat3::identity();
+        for (int r = 0; r < 2; ++r)
+            for (int k = 0; k < 3; ++k) c.m[r][k] = t.m.m[r][0] * m.m[0][k] + t.m.m[r][1] * m.m[1][k] + (k == 2 ? t.m.m[r][2] : 0.0f);
+        emit_tex_ops(t.lhs, c, ops);
+        return;
+    }
+    if (t.type == TEXOP_ADD || t.type == TEXOP_SUB || t.type == TEXOP_MUL || t.type == TEXOP_DIV) {
+        emit_tex_ops(t.lhs, m, ops);
+        emit_tex_ops(t.rhs, m, ops);
+    }
+    TexOp op{};
+    op.op = t.type;
+    op.value[0] = t.value.x; op.value[1] = t.value.y; op.value[2] = t.value.z;
+    if (t.type == TEXOP_ARRAY) {
+        op.tex = (unsigned long long)sources[t.source].tex;
+        for (int r = 0; r < 2; ++r) for (int c = 0; c < 3; ++c) op.m[3 * r + c] = m.m[r][c];
+    }
+    ops.push_back(op);
+}
+
+static void create_texture_object(TextureSource &src) {  // utils/cuda/array.cpp:104-172, texture.cpp:63-105
+    if (src.tex) return;
+    cudaChannelFormatDesc fmt;
+    size_t texel;
+    if (src.is_float) {
+        fmt = src.channels == 1 ? cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat) : cudaCreateChannelDesc(32, 32, 32, 32, cudaChannelFormatKindFloat);
+        texel = 4 * (size_t)src.channels;
+    } else {
+        fmt = src.channels == 1 ? cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned) : cudaCreateChannelDesc(8, 8, 8, 8, cudaChannelFormatKindUnsigned);
+        texel = (size_t)src.channels;
+    }
+    const void *data = src.is_float ? (const void *)src.f32.data() : (const void *)src.u8.data();
+    if (src.depth > 0) {
+        const cudaExtent ext = make_cudaExtent((size_t)src.width, (size_t)src.height, (size_t)src.depth);
+        BTRC_CUDA(cudaMalloc3DArray(&src.array, &fmt, ext));
+        cudaMemcpy3DParms p{};
+        p.srcPtr = make_cudaPitchedPtr(const_cast<void *>(data), src.width * texel, (size_t)src.width, (size_t)src.height);
+        p.dstArray = src.array;
+        p.extent = ext;
+        p.kind = cudaMemcpyHostToDevice;
+        BTRC_CUDA(cudaMemcpy3D(&p));
+    } else {
+        BTRC_CUDA(cudaMallocArray(&src.array, &fmt, (size_t)src.width, (size_t)src.height));
+        BTRC_CUDA(cudaMemcpy2DToArray(src.array, 0, 0, data, src.width * texel, src.width * texel, (size_t)src.height, cudaMemcpyHostToDevice));
+    }
+    static const cudaTextureAddressMode modes[4] = {cudaAddressModeClamp, cudaAddressModeWrap, cudaAddressModeMirror, cudaAddressModeBorder};
+    cudaTextureDesc td{};
+    for (int k = 0; k < 3; ++k) td.addressMode[k] = modes[src.address[k]];
+    td.filterMode = src.linear ? cudaFilterModeLinear : cudaFilterModePoint;
+    td.normalizedCoords = 1;
+    for (int k = 0; k < 4; ++k) td.borderColor[k] = src.border[k];
+    td.sRGB = src.srgb ? 1 : 0;
+    td.readMode = src.is_float ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = src.array;
+    BTRC_CUDA(cudaCreateTextureObject(&src.tex, &rd, &td, nullptr));
+}
+
 void Scene::upload_device() {
     if (device_ready_) return;
     buffers_.clear();
+    release_textures();
     // ---- geometry tables
     std::vector<GeometryInfo> geos;
     for (auto &m : meshes) {
@@ -414,11 +755,40 @@ void Scene::upload_device() {
     dev.instances = upload(instance_info);
     dev.geometries = upload(geos);
     dev.materials = upload(materials);
-    dev.textures = upload(textures);
+    // ---- textures: CUDA texture objects for the "array" sources, postfix programs for the graph
+    for (auto &src : sources) create_texture_object(src);
+    std::vector<TextureDesc> tex_descs;
+    std::vector<TexOp> tex_ops;
+    for (size_t i = 0; i < textures.size(); ++i) {
+        TextureDesc d{};
+        d.first_op = (int)tex_ops.size();
+        emit_tex_ops((int)i, Mat3::identity(), tex_ops);
+        d.n_ops = (int)tex_ops.size() - d.first_op;
+        tex_descs.push_back(d);
+    }
+    dev.textures = upload(tex_descs);
+    dev.tex_ops = upload(tex_ops);
+    std::vector<Texture3DDesc> t3;
+    for (auto &t : textures3d) {
+        Texture3DDesc d{};
+        d.is_array = t.is_array ? 1 : 0;
+        d.value[0] = t.value.x; d.value[1] = t.value.y; d.value[2] = t.value.z;
+        d.tex = t.is_array ? (unsigned long long)sources[t.source].tex : 0ull;
+        t3.push_back(d);
+    }
+    dev.textures3d = upload(t3);
+    dev.media = upload(medium_table);
+    dev.has_medium = has_medium ? 1 : 0;
     dev.lights = upload(lights);
     dev.n_instances = (int)instance_info.size();
-    dev.n_lights = (int)lights.size();
-    dev.vol_prim_medium_id = 0;
+    // ---- environment light (core/light_sampler.cpp:24-33: appended after the area lights)
+    dev.env = EnvLight{};
+    dev.env.type = env.type;
+    dev.env.light_index = env.type != ENV_NONE ? (int)lights.size() : -1;
+    for (int k = 0; k < 3; ++k) { dev.env.lower[k] = env.lower[k]; dev.env.upper[k] = env.upper[k]; dev.env.up[k] = env.up[k]; }
+    if (env.type == ENV_IBL) throw Error("unknown light type: ibl (image-based lighting is not supported yet)");
+    dev.n_lights = (int)lights.size() + (env.type != ENV_NONE ? 1 : 0);
+    dev.vol_prim_medium_id = (uint32_t)medium_table.size() - 1;
     dev.world_diagonal = world_diagonal;
     device_ready_ = true;
 }

@@ -50,8 +50,51 @@ struct HostInstance {
     Transform3D transform;
     bool has_light = false;
     Vec3 intensity;
-    uint32_t inner_medium_id = 0, outer_medium_id = 0;
+    int inner_medium = -1, outer_medium = -1;  // handles into Scene::media (-1: none), ids are assigned by commit()
     uint32_t flag = 0;
+};
+
+// An "array" texture: decoded texels + the sampling description (builtin/texture2d/description.cpp:28-80,
+// utils/cuda/texture.cpp:63-105, utils/cuda/array.cpp:104-172,313-385).  2-D when depth == 0.
+struct TextureSource {
+    int width = 0, height = 0, depth = 0;
+    int channels = 4;            // 1 or 4
+    bool is_float = false;       // false: UNorm8 texels in u8
+    std::vector<uint8_t> u8;
+    std::vector<float> f32;
+    int address[3] = {0, 0, 0};  // 0 clamp, 1 wrap, 2 mirror, 3 border
+    bool linear = true, srgb = false;
+    float border[4] = {0, 0, 0, 0};
+    float max_value[3] = {0, 0, 0};  // Array::find_minmax_values
+    cudaArray_t array = nullptr;
+    cudaTextureObject_t tex = 0;
+};
+
+// host texture graph node (flattened into TexOp programs at upload)
+struct Tex2DNode {
+    int type = 0;  // TexOpCode, or 6 = transform wrapper
+    Vec3 value;
+    int source = -1;
+    int lhs = -1, rhs = -1;
+    Mat3 m = Mat3::identity();
+};
+
+struct Tex3DNode {
+    bool is_array = false;
+    Vec3 value;
+    int source = -1;
+};
+
+struct HostMedium {
+    MediumDesc desc{};
+    float priority = 0;
+};
+
+struct EnvLightDesc {
+    int type = 0;  // EnvType
+    Vec3 lower, upper, up;
+    int tex = -1;
+    int lut_w = 400, lut_h = 200;
 };
 
 struct RendererDesc {  // builtin/renderer/wavefront.cpp:375-398
@@ -74,8 +117,12 @@ public:
     float cam_fov_y_deg = 60;
     RendererDesc renderer;
     std::vector<PostProcessorDesc> post_processors;
-    std::vector<TextureDesc> textures;
+    std::vector<Tex2DNode> textures;
+    std::vector<Tex3DNode> textures3d;
+    std::vector<TextureSource> sources;
     std::vector<MaterialDesc> materials;
+    std::vector<HostMedium> media;      // creation order
+    EnvLightDesc env;
     std::vector<MeshData> meshes;
     std::vector<HostInstance> instances;
     std::string scene_dir;
@@ -83,6 +130,8 @@ public:
     // --- committed state
     std::vector<InstanceInfo> instance_info;
     std::vector<LightInfo> lights;
+    std::vector<MediumDesc> medium_table;   // id order: descending priority, volume-primitive medium last (core/scene.cpp:136-161)
+    bool has_medium = false;
     std::vector<WorldTri> world_tris;
     AABB bbox;
     float world_diagonal = 0;
@@ -92,6 +141,10 @@ public:
     double bvh_build_seconds = 0;
     int bvh_depth = 0;
 
+    Scene() = default;
+    ~Scene();
+    Scene(const Scene &) = delete;
+    Scene &operator=(const Scene &) = delete;
     static std::unique_ptr<Scene> from_file(const std::string &filename);
     static std::unique_ptr<Scene> from_string(const std::string &json, const std::string &scene_dir);
     void commit();          // host side: tables, world triangles, BVH (no GPU needed)
@@ -102,9 +155,16 @@ public:
 private:
     void create(const NodeP &root);
     int create_texture2d(const NodeP &node);
+    int constant_texture2d(float v);
+    int create_texture3d(const NodeP &node);
     int create_material(const NodeP &node);
+    int create_medium(const NodeP &node, const Mat4 *outer_world_to_local);
+    void create_envir_light(const NodeP &node);
+    void parse_texture_desc(const NodeP &node, TextureSource &src) const;
+    void release_textures();
+    void emit_tex_ops(int node, const Mat3 &m, std::vector<TexOp> &ops) const;
     int create_geometry(const NodeP &node);
-    std::map<const Node *, int> tex_pool_, mat_pool_, geo_pool_;
+    std::map<const Node *, int> tex_pool_, tex3d_pool_, mat_pool_, geo_pool_, med_pool_;
     std::vector<DeviceBuffer> buffers_;
     bool device_ready_ = false;
     template <typename T> const T *upload(const std::vector<T> &v);

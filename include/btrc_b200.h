@@ -32,6 +32,9 @@ typedef struct btrc_scene_info {
     int32_t tile, albedo, normal;
     int32_t n_instances, n_lights, n_triangles, n_materials;
     int32_t bvh_depth;
+    int32_t n_media;              /* media incl. the volume-primitive medium  (core/scene.cpp:136-161)     */
+    int32_t has_medium;           /* Scene::has_medium                        (core/scene.cpp:346-356)     */
+    int32_t n_textures;
     float world_diagonal;         /* 1.2 * |bbox(scene + eye)|                (wavefront.cpp:138-139)       */
     float bvh_build_seconds;
 } btrc_scene_info_t;
@@ -46,8 +49,9 @@ typedef struct btrc_render_stats {
     uint64_t n_splat;        /* radiance splats (3 float atomics each)                         */
     uint64_t n_iter;         /* wavefront iterations                                           */
     double render_ms;        /* device time of the last btrc_render_range (CUDA events)        */
-    double stage_ms[4];      /* with btrc_set_profiling(1): device time per stage of the last  */
-                             /* range -- generate, closest-hit trace, shade, shadow trace      */
+    double stage_ms[5];      /* with btrc_set_profiling(1): device time per stage of the last  */
+                             /* range -- generate, closest-hit trace, shade, shadow trace,     */
+                             /* medium                                                         */
     uint64_t n_launches;     /* kernels launched by the last btrc_render_range                 */
 } btrc_render_stats_t;
 
@@ -113,6 +117,16 @@ int btrc_shade(btrc_scene_t *scene, int memory, int32_t n,
                int32_t *n_next, float *next_o_med, float *next_d_t1, uint32_t *next_pixel, float *next_beta_depth,
                float *next_path_rad, uint64_t *next_rng, float *next_ble,
                int32_t *n_shadow, uint32_t *shadow_pixel, float *shadow_beta_li, float *shadow_o_med, float *shadow_d_t1);
+/* MediumPipeline::sample_scattering (medium.cpp:204-211) on n states, run between closest-hit and shade when the scene
+ * has media.  Updated IN PLACE like the kernel updates its own slot: o_med.w (resolved medium id), ble (beta_le * Tr of
+ * the unscattered segment), rng (advanced sampler; only where no scattering happened), flag (bit 31 = scattered).
+ * Scattered paths append their continuation to the next_* arrays and their NEE ray to the shadow_* arrays. */
+int btrc_medium(btrc_scene_t *scene, int memory, int32_t n,
+                float *o_med, const float *d_t1, const uint32_t *pixel, const float *beta_depth, const float *path_rad,
+                uint64_t *rng, float *ble, uint32_t *flag, const uint32_t *detail,
+                int32_t *n_next, float *next_o_med, float *next_d_t1, uint32_t *next_pixel, float *next_beta_depth,
+                float *next_path_rad, uint64_t *next_rng, float *next_ble,
+                int32_t *n_shadow, uint32_t *shadow_pixel, float *shadow_beta_li, float *shadow_o_med, float *shadow_d_t1);
 /* ShadowPipeline::test (shadow.cpp:143-158): traces the shadow rays and splats the unoccluded ones into the film. */
 int btrc_shadow(btrc_scene_t *scene, int memory, int32_t n, const uint32_t *shadow_pixel, const float *shadow_beta_li,
                 const float *shadow_o_med, const float *shadow_d_t1);

@@ -53,9 +53,26 @@ def lib():
         L.orc_scene_new.restype = c_void_p
         L.orc_scene_free.argtypes = [c_void_p]
         L.orc_add_texture_constant.argtypes = [c_void_p, c_float, c_float, c_float]
-        L.orc_add_material.argtypes = [c_void_p, c_int, c_int, c_int, c_int]
+        L.orc_add_material.argtypes = [c_void_p, c_int, POINTER(c_int32), c_int, c_int]
+        L.orc_add_image.argtypes = [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_float), c_int, c_int, c_int, c_int, c_int, POINTER(c_float)]
+        L.orc_add_texture_array.argtypes = [c_void_p, c_int]
+        L.orc_add_texture_binary.argtypes = [c_void_p, c_int, c_int, c_int]
+        L.orc_add_texture_transform.argtypes = [c_void_p, c_int, POINTER(c_float)]
+        L.orc_eval_texture2d.argtypes = [c_void_p, c_int, c_int, POINTER(c_float), POINTER(c_float)]
+        L.orc_add_texture3d_constant.argtypes = [c_void_p, c_float, c_float, c_float]
+        L.orc_add_texture3d_array.argtypes = [c_void_p, c_int]
+        L.orc_add_medium_homogeneous.argtypes = [c_void_p, c_float, POINTER(c_float), c_float]
+        L.orc_add_medium_heterogeneous.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_float)]
+        L.orc_set_gradient_sky.argtypes = [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float)]
+        L.orc_medium.argtypes = ([c_void_p, c_int] + [POINTER(c_float)] * 2 + [POINTER(c_uint32)] + [POINTER(c_float)] * 2 +
+                                 [POINTER(c_uint64), POINTER(c_float), POINTER(c_uint32), POINTER(c_uint32)] + [POINTER(c_uint32)] +
+                                 [POINTER(c_float)] * 2 + [POINTER(c_uint32)] + [POINTER(c_float)] * 2 + [POINTER(c_uint64), POINTER(c_float)] +
+                                 [POINTER(c_float)] * 4)
+        L.orc_shadow_tr.argtypes = [c_void_p, c_int] + [POINTER(c_float)] * 3
+        L.orc_has_medium.argtypes = [c_void_p]
+        L.orc_bsdf_probe.argtypes = [c_void_p, c_int, POINTER(c_float), POINTER(c_float), c_int] + [POINTER(c_float)] * 8
         L.orc_add_mesh.argtypes = [c_void_p, c_int, POINTER(c_float), POINTER(c_float), POINTER(c_uint8), POINTER(c_float)]
-        L.orc_add_instance.argtypes = [c_void_p, c_int, c_int, POINTER(c_float), POINTER(c_float), c_int, POINTER(c_float)]
+        L.orc_add_instance.argtypes = [c_void_p, c_int, c_int, POINTER(c_float), POINTER(c_float), c_int, POINTER(c_float), c_int, c_int]
         L.orc_set_camera.argtypes = [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float), c_float]
         L.orc_set_film.argtypes = [c_void_p, c_int, c_int]
         L.orc_set_renderer.argtypes = [c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_int, c_float, c_float]
@@ -237,6 +254,34 @@ class Node:
             s = c.as_vec3()
             return Transform3D.scale(s[0], s[1], s[2])
         raise ValueError("unknown transform3d type")
+
+
+def _node_transform2d(node):
+    """node.cpp:126-164 -> 3x3 row-major matrix (f32).  translate / scale need parse<Vec2f>, which the reference never
+    instantiates (node.cpp:321-324: "unimplemented"); the 3x3 product is the intended one (Mat3 operator* in
+    utils/math/mat3.cpp:108-123 reads a fourth column that does not exist)."""
+    if node.is_array():
+        ret = np.eye(3, dtype=f32)
+        for e in node.elements():
+            ret = (_node_transform2d(e).astype(f32) @ ret).astype(f32)
+        return ret
+    if node.find("translate") is not None or node.find("scale") is not None:
+        raise ValueError("unimplemented")
+    c = node.find("rotate")
+    if c is not None:
+        rad = c.child("angle").as_radian()
+        S, C = _sin(rad), _cos(rad)
+        return np.array([[C, -S, 0], [S, C, 0], [0, 0, 1]], f32)
+    c = node.find("inverse_u")
+    if c is not None and c.as_bool():
+        return np.array([[-1, 0, 1], [0, 1, 0], [0, 0, 0]], f32)
+    c = node.find("inverse_v")
+    if c is not None and c.as_bool():
+        return np.array([[1, 0, 0], [0, -1, 1], [0, 0, 1]], f32)
+    c = node.find("swap_uv")
+    if c is not None and c.as_bool():
+        return np.array([[0, 1, 0], [1, 0, 0], [0, 0, 1]], f32)
+    raise ValueError("unknown transform2d type")
 
 
 def _json_to_tree(j):
@@ -479,7 +524,10 @@ def load_obj(filename: str):
 class OracleScene:
     """Builds an oracle scene from a Btrc JSON scene file (the same file the product loads)."""
 
-    MAT_TYPES = {"diffuse": 0, "black": 1}
+    MAT_TYPES = {"diffuse": 0, "black": 1, "disney": 2, "metal": 3, "glass": 4, "mirror": 5, "invisible": 6}
+    SLOTS = ["color", "metallic", "roughness", "transmission", "ior", "specular", "specular_tint", "anisotropic", "sheen", "sheen_tint",
+             "clearcoat", "clearcoat_gloss", "transmission_roughness"]
+    ADDR = {"clamp": 0, "wrap": 1, "mirror": 2, "border": 3}
 
     def __init__(self, filename: str | None = None):
         self.L = lib()
@@ -490,6 +538,9 @@ class OracleScene:
         self.mesh_data = []   # (pos, nor, has_nor, uv) per mesh id
         self.instances = []   # dicts
         self.want_albedo = self.want_normal = False
+        self.scene_dir = "."
+        self._pool = {}       # (kind, id(raw node)) -> object id  (Context::create object pooling, context.h:205-236)
+        self.media = []       # (priority, creation order, builder) resolved at commit
         if filename:
             self._load(filename)
 
@@ -498,6 +549,9 @@ class OracleScene:
             self.L.orc_scene_free(self.h)
         except Exception:
             pass
+
+    def resolve(self, p):  # factory/path_resolver.cpp:6-17
+        return os.path.normpath(os.path.abspath(p.replace("$env{scene_directory}", self.scene_dir)))
 
     # -- construction helpers (usable without a JSON file, e.g. the lib/bvh golden test)
     def add_mesh_arrays(self, pos, nor=None, has_nor=None, uv=None):
@@ -510,7 +564,63 @@ class OracleScene:
         self.mesh_data.append((pos, nor, has_nor, uv))
         return mid
 
+    def _texture_desc(self, node):  # builtin/texture2d/description.cpp:28-80
+        au = self.ADDR[node.find("address_mode_u").as_str()] if node.find("address_mode_u") is not None else 0
+        av = self.ADDR[node.find("address_mode_v").as_str()] if node.find("address_mode_v") is not None else 0
+        aw = self.ADDR[node.find("address_mode_w").as_str()] if node.find("address_mode_w") is not None else 0
+        filt = node.find("filter").as_str() if node.find("filter") is not None else "linear"
+        if filt not in ("linear", "point"):
+            raise ValueError(f"unknown filter mode: {filt}")
+        border = np.zeros(4, f32)
+        bn = node.find("border")
+        if bn is not None:
+            if bn.is_array():
+                e = bn.elements()
+                if len(e) == 1:
+                    border[:] = e[0].as_float()
+                elif len(e) == 3:
+                    border[:3] = [x.as_float() for x in e]
+                else:
+                    raise ValueError("invalid border array size")
+            else:
+                border[:] = bn.as_float()
+        return au, av, aw, 1 if filt == "linear" else 0, node.bool_or("srgb_to_linear", False), border
+
+    def add_image_2d(self, filename, desc):
+        """utils/image.cpp:299-335 + cuda/array.cpp:136-149: 1-channel 8-bit -> UNorm8x1, 3/4-channel -> UNorm8x4 (alpha 255),
+        .hdr -> F32x4 (alpha 1)."""
+        from PIL import Image as PILImage
+
+        au, av, aw, linear, srgb, border = desc
+        if filename.lower().endswith(".hdr"):
+            import cv2
+
+            img = cv2.imread(filename, cv2.IMREAD_UNCHANGED)[..., ::-1].astype(f32)
+            data = np.concatenate([img, np.ones(img.shape[:2] + (1,), f32)], axis=2)
+            ch, srgb = 4, False
+        else:
+            im = PILImage.open(filename)
+            if im.mode in ("L", "1"):
+                data = (np.asarray(im.convert("L"), np.uint8).astype(f32) / f32(255.0))[..., None]
+                ch = 1
+            else:
+                rgba = np.asarray(im.convert("RGBA") if im.mode in ("RGBA", "LA") else im.convert("RGB"), np.uint8)
+                if rgba.shape[2] == 3:
+                    rgba = np.concatenate([rgba, np.full(rgba.shape[:2] + (1,), 255, np.uint8)], axis=2)
+                data = rgba.astype(f32) / f32(255.0)
+                ch = 4
+        data = np.ascontiguousarray(data, f32)
+        h, w = data.shape[:2]
+        return self.L.orc_add_image(self.h, w, h, 0, ch, _ptr(data, c_float), int(bool(srgb)), au, av, aw, linear, _ptr(border, c_float))
+
     def add_texture(self, node: Node):
+        key = ("tex2d", id(node.raw))
+        if key in self._pool:
+            return self._pool[key]
+        self._pool[key] = t = self._add_texture(node)
+        return t
+
+    def _add_texture(self, node: Node):
         # Context::create<Texture2D> (factory/context.h:211-220): literal number / array => constant
         if node.is_value() or node.is_array():
             v = node.as_vec3()
@@ -519,24 +629,132 @@ class OracleScene:
         if ty == "constant":
             v = node.child("value").as_vec3()
             return self.L.orc_add_texture_constant(self.h, v[0], v[1], v[2])
-        raise NotImplementedError(f"oracle: texture2d type {ty}")
+        if ty == "array":
+            img = self.add_image_2d(self.resolve(node.child("filename").as_str()), self._texture_desc(node))
+            return self.L.orc_add_texture_array(self.h, img)
+        if ty in ("add", "sub", "mul", "div"):
+            lhs, rhs = self.add_texture(node.child("lhs")), self.add_texture(node.child("rhs"))
+            return self.L.orc_add_texture_binary(self.h, {"add": 2, "sub": 3, "mul": 4, "div": 5}[ty], lhs, rhs)
+        if ty == "transform":
+            m = _node_transform2d(node.child("transform"))
+            inner = self.add_texture(node.child("tex"))
+            m6 = np.ascontiguousarray(m[:2].reshape(-1), f32)
+            return self.L.orc_add_texture_transform(self.h, inner, _ptr(m6, c_float))
+        raise ValueError(f"unknown texture2d type: {ty}")
+
+    def const_texture(self, v):
+        return self.L.orc_add_texture_constant(self.h, c_float(v), c_float(v), c_float(v))
 
     def add_material(self, node: Node):
         ty = node.child("type").as_str()
         if ty not in self.MAT_TYPES:
-            raise NotImplementedError(f"oracle: material type {ty}")
-        color = self.add_texture(node.child("color")) if node.find("color") is not None else -1
-        normal = self.add_texture(node.child("normal")) if node.find("normal") is not None else -1
-        st = node.bool_or("shadow_terminator_term", True)
-        return self.L.orc_add_material(self.h, self.MAT_TYPES[ty], color, normal, 1 if st else 0)
+            raise ValueError(f"unknown material type: {ty}")
+        tex = np.full(13, -1, np.int32)
 
-    def add_instance(self, mesh, material, xf: Transform3D | None = None, intensity=None):
+        def req(name): tex[self.SLOTS.index(name)] = self.add_texture(node.child(name))
+
+        def opt(name, default):
+            n = node.find(name)
+            tex[self.SLOTS.index(name)] = self.add_texture(n) if n is not None else self.const_texture(default)
+
+        normal, st = -1, True
+        if ty == "diffuse":  # diffuse.cpp:36-48
+            req("color")
+        elif ty == "disney":  # disney.cpp:844-894
+            req("color"); req("metallic"); req("roughness")
+            opt("transmission", 0); opt("ior", 1.5); opt("specular", 1); opt("specular_tint", 0); opt("anisotropic", 0)
+            opt("sheen", 0); opt("sheen_tint", 0); opt("clearcoat", 0); opt("clearcoat_gloss", 1)
+            n = node.find("transmission_roughness")
+            tex[12] = self.add_texture(n) if n is not None else tex[2]
+        elif ty == "metal":  # metal.cpp:50-77
+            req("color"); req("roughness"); opt("anisotropic", 0)
+        elif ty == "glass":  # glass.cpp:141-157
+            req("color"); req("ior")
+        elif ty == "mirror":  # mirror.cpp:91-103
+            req("color")
+        if ty in ("diffuse", "disney", "metal"):
+            st = node.bool_or("shadow_terminator_term", True)
+        if ty in ("diffuse", "disney", "metal", "glass", "mirror") and node.find("normal") is not None:
+            normal = self.add_texture(node.child("normal"))
+        return self.L.orc_add_material(self.h, self.MAT_TYPES[ty], _ptr(tex, c_int32), normal, 1 if st else 0)
+
+    # -- 3-D textures and media
+    def add_texture3d(self, node: Node):
+        key = ("tex3d", id(node.raw))
+        if key in self._pool:
+            return self._pool[key]
+        if node.is_value() or node.is_array():
+            v = node.as_vec3()
+            t = self.L.orc_add_texture3d_constant(self.h, v[0], v[1], v[2])
+        else:
+            ty = node.child("type").as_str()
+            if ty == "constant":
+                v = node.child("value").as_vec3()
+                t = self.L.orc_add_texture3d_constant(self.h, v[0], v[1], v[2])
+            elif ty == "array":  # utils/cuda/array.cpp:313-385 (text grid)
+                au, av, aw, linear, srgb, border = self._texture_desc(node)
+                with open(self.resolve(node.child("text").as_str())) as f:
+                    tok = f.read().split()
+                comp, ch, w, h, d = tok[0], int(tok[1]), int(tok[2]), int(tok[3]), int(tok[4])
+                if comp != "float":
+                    raise NotImplementedError("oracle: only float text grids")
+                if ch not in (1, 3, 4):
+                    raise ValueError(f"unsupported channel count: {ch}")
+                vals = np.array(tok[5:5 + w * h * d * ch], dtype=np.float64).astype(f32).reshape(d * h * w, ch)
+                if ch == 3:
+                    vals = np.concatenate([vals, np.ones((vals.shape[0], 1), f32)], axis=1)
+                vals = np.ascontiguousarray(vals, f32)
+                img = self.L.orc_add_image(self.h, w, h, d, 1 if ch == 1 else 4, _ptr(vals, c_float), 0, au, av, aw, linear, _ptr(border, c_float))
+                t = self.L.orc_add_texture3d_array(self.h, img)
+            else:
+                raise ValueError(f"unknown texture3d type: {ty}")
+        self._pool[key] = t
+        return t
+
+    def add_medium(self, node: Node, world_to_local=None):
+        """Returns a handle (index into self.media); ids are assigned at commit in priority order (core/scene.cpp:136-161)."""
+        key = ("medium", id(node.raw))
+        if key in self._pool and world_to_local is None:
+            return self._pool[key]
+        ty = node.child("type").as_str()
+        if ty == "transform":  # factory/context.h:146-165, core/medium.cpp:98-129
+            if node.find("world_to_local") is not None:
+                w2l = node.child("world_to_local").as_transform3d().mat
+            else:
+                w2l = node.child("local_to_world").as_transform3d().inv
+            if world_to_local is not None:  # nested: inner(outer(p))
+                w2l = _matmul(w2l, world_to_local)
+            h = self.add_medium(node.child("medium"), w2l)
+        elif ty == "homogeneous":  # homogeneous.cpp:80-92
+            prio = float(node.float_or("priority", 0.0))
+            sigma_t, albedo, g = node.child("sigma_t").as_float(), node.child("albedo").as_vec3(), node.float_or("g", 0.0)
+            self.media.append((prio, lambda: self.L.orc_add_medium_homogeneous(self.h, c_float(float(sigma_t)), _ptr(np.ascontiguousarray(albedo, f32), c_float), c_float(float(g)))))
+            h = len(self.media) - 1
+        elif ty == "hetergeneous":  # hetergeneous.cpp:113-135
+            prio = float(node.float_or("priority", 0.0))
+            st = self.add_texture3d(node.child("sigma_t"))
+            al = self.add_texture3d(node.child("albedo"))
+            g = self.add_texture3d(node.child("g")) if node.find("g") is not None else self.L.orc_add_texture3d_constant(self.h, 0, 0, 0)
+            w = None if world_to_local is None else np.ascontiguousarray(world_to_local, f32)
+            self.media.append((prio, lambda: self.L.orc_add_medium_heterogeneous(self.h, st, al, g, _ptr(w, c_float))))
+            h = len(self.media) - 1
+        else:
+            raise ValueError(f"unknown medium type: {ty}")
+        if world_to_local is None:
+            self._pool[key] = h
+        return h
+
+    def add_instance(self, mesh, material, xf: Transform3D | None = None, intensity=None, inner_medium=None, outer_medium=None):
+        """inner_medium / outer_medium: handles from add_medium (resolved to ids at commit) or None."""
         xf = xf or Transform3D()
         mat = np.ascontiguousarray(xf.mat, f32)
         inv = np.ascontiguousarray(xf.inv, f32)
         it = None if intensity is None else np.ascontiguousarray(intensity, f32)
-        self.instances.append(dict(mesh=mesh, material=material, mat=mat, inv=inv, intensity=it))
-        return self.L.orc_add_instance(self.h, mesh, material, _ptr(mat, c_float), _ptr(inv, c_float), 0 if it is None else 1, _ptr(it, c_float))
+        self.instances.append(dict(mesh=mesh, material=material, mat=mat, inv=inv, intensity=it, inner=inner_medium, outer=outer_medium))
+
+    def set_gradient_sky(self, lower, upper, up):
+        lo, hi, u = (np.ascontiguousarray(v, f32) for v in (lower, upper, up))
+        self.L.orc_set_gradient_sky(self.h, _ptr(lo, c_float), _ptr(hi, c_float), _ptr(u, c_float))
 
     def set_camera(self, eye, dst, up, fov_y_deg):
         e, d, u = (np.ascontiguousarray(v, f32) for v in (eye, dst, up))
@@ -554,28 +772,35 @@ class OracleScene:
                                 int(tile), int(albedo), int(normal), filter_type, c_float(float(radius)), c_float(float(alpha)))
 
     def commit(self):
+        # medium ids: descending priority (stable for ties: creation order), Scene::commit (core/scene.cpp:136-161)
+        order = sorted(range(len(self.media)), key=lambda i: -self.media[i][0])
+        ids = {}
+        for h in order:
+            ids[h] = self.media[h][1]()
+        for inst in self.instances:
+            it = inst["intensity"]
+            self.L.orc_add_instance(self.h, inst["mesh"], inst["material"], _ptr(inst["mat"], c_float), _ptr(inst["inv"], c_float),
+                                    0 if it is None else 1, _ptr(it, c_float),
+                                    -1 if inst["inner"] is None else ids[inst["inner"]], -1 if inst["outer"] is None else ids[inst["outer"]])
         self.L.orc_commit(self.h)
 
     def _load(self, filename):
         root = parse_scene_file(filename)
-        scene_dir = os.path.dirname(os.path.abspath(filename))
-        pool = {}  # id(raw node) -> object id  (Context::create object pooling, context.h:205-236)
-
-        def resolve(p):
-            return os.path.normpath(os.path.abspath(p.replace("$env{scene_directory}", scene_dir)))
-
-        for ent in root.child("scene").child("entities").elements():
+        self.scene_dir = os.path.dirname(os.path.abspath(filename))
+        pool = self._pool
+        scene = root.child("scene")
+        for ent in scene.child("entities").elements():
             g = ent.child("geometry")
             if g.child("type").as_str() != "triangle_mesh":
-                raise NotImplementedError("oracle: geometry type")
-            if id(g.raw) not in pool:
-                pos, nor, has_nor, uv = load_obj(resolve(g.child("filename").as_str()))
+                raise ValueError("unknown geometry type: " + g.child("type").as_str())
+            if ("geo", id(g.raw)) not in pool:
+                pos, nor, has_nor, uv = load_obj(self.resolve(g.child("filename").as_str()))
                 if g.bool_or("transform_to_unit_cube", False):
                     pos = _to_unit_cube(pos)
-                pool[id(g.raw)] = self.add_mesh_arrays(pos, nor, has_nor, uv)
+                pool[("geo", id(g.raw))] = self.add_mesh_arrays(pos, nor, has_nor, uv)
             m = ent.child("material")
-            if id(m.raw) not in pool:
-                pool[id(m.raw)] = self.add_material(m)
+            if ("mat", id(m.raw)) not in pool:
+                pool[("mat", id(m.raw))] = self.add_material(m)
             xf = ent.child("local_to_world").as_transform3d() if ent.find("local_to_world") is not None else Transform3D()
             inten = None
             ln = ent.find("light")
@@ -583,9 +808,18 @@ class OracleScene:
                 if ln.child("type").as_str() != "mesh_light":
                     raise ValueError("area light expected")
                 inten = ln.child("intensity").as_vec3()
-            if ent.find("inner_medium") is not None or ent.find("outer_medium") is not None:
-                raise NotImplementedError("oracle: media")
-            self.add_instance(pool[id(g.raw)], pool[id(m.raw)], xf, inten)
+            inner = self.add_medium(ent.child("inner_medium")) if ent.find("inner_medium") is not None else None
+            outer = self.add_medium(ent.child("outer_medium")) if ent.find("outer_medium") is not None else None
+            self.add_instance(pool[("geo", id(g.raw))], pool[("mat", id(m.raw))], xf, inten, inner, outer)
+        if scene.find("volumes") is not None and len(scene.child("volumes").elements()) > 0:
+            raise NotImplementedError("oracle: volume primitives")
+        env = scene.find("envir_light")
+        if env is not None:
+            ty = env.child("type").as_str()
+            if ty == "gradient_sky":  # gradient_sky.cpp:56-67
+                self.set_gradient_sky(env.child("lower").as_vec3(), env.child("upper").as_vec3(), env.child("up").as_vec3())
+            else:
+                raise NotImplementedError(f"oracle: envir_light type {ty}")
         w, h = root.child("width").as_int(), root.child("height").as_int()
         self.set_film(w, h)
         cam = root.child("camera")
@@ -646,6 +880,44 @@ class OracleScene:
         self.L.orc_shade(self.h, n, *state_ptrs(st), _ptr(flag, c_uint32), _ptr(detail, c_uint32), _ptr(out["status"], c_uint32),
                          *state_ptrs(nxt), _ptr(out["sh_o_med"], c_float), _ptr(out["sh_d_t1"], c_float), _ptr(out["sh_beta_li"], c_float),
                          _ptr(out["splat"], c_float), _ptr(out["albedo"], c_float), _ptr(out["normal"], c_float))
+        return out
+
+    def medium(self, st, flag, detail):
+        """Medium stage (wavefront/medium.cpp).  Returns (updated state dict, updated flag, out dict like shade())."""
+        n = st["o_med"].shape[0]
+        st = {k: np.ascontiguousarray(v.copy()) for k, v in st.items()}
+        flag = np.ascontiguousarray(flag.copy(), np.uint32); detail = np.ascontiguousarray(detail, np.uint32)
+        nxt = new_state(n)
+        out = dict(status=np.zeros(n, np.uint32), next=nxt, sh_o_med=np.zeros((n, 4), f32), sh_d_t1=np.zeros((n, 4), f32),
+                   sh_beta_li=np.zeros((n, 4), f32), splat=np.zeros((n, 3), f32))
+        self.L.orc_medium(self.h, n, *state_ptrs(st), _ptr(flag, c_uint32), _ptr(detail, c_uint32), _ptr(out["status"], c_uint32),
+                          *state_ptrs(nxt), _ptr(out["sh_o_med"], c_float), _ptr(out["sh_d_t1"], c_float), _ptr(out["sh_beta_li"], c_float),
+                          _ptr(out["splat"], c_float))
+        return st, flag, out
+
+    def shadow_tr(self, o_med, d_t1):
+        o_med = np.ascontiguousarray(o_med, f32); d_t1 = np.ascontiguousarray(d_t1, f32)
+        n = o_med.shape[0]
+        tr = np.zeros((n, 3), f32)
+        self.L.orc_shadow_tr(self.h, n, _ptr(o_med, c_float), _ptr(d_t1, c_float), _ptr(tr, c_float))
+        return tr
+
+    def has_medium(self): return bool(self.L.orc_has_medium(self.h))
+
+    def eval_texture2d(self, tex, uv):
+        uv = np.ascontiguousarray(uv, f32)
+        out = np.zeros((uv.shape[0], 3), f32)
+        self.L.orc_eval_texture2d(self.h, tex, uv.shape[0], _ptr(uv, c_float), _ptr(out, c_float))
+        return out
+
+    def bsdf_probe(self, material, interp_z, uv, wo, wi, sam):
+        wo, wi, sam = (np.ascontiguousarray(a, f32) for a in (wo, wi, sam))
+        n = wo.shape[0]
+        iz = np.ascontiguousarray(interp_z, f32); uvv = np.ascontiguousarray(uv, f32)
+        out = dict(sample=np.zeros((n, 8), f32), eval=np.zeros((n, 3), f32), pdf=np.zeros(n, f32), albedo=np.zeros(3, f32), normal=np.zeros(3, f32))
+        self.L.orc_bsdf_probe(self.h, material, _ptr(iz, c_float), _ptr(uvv, c_float), n, _ptr(wo, c_float), _ptr(wi, c_float), _ptr(sam, c_float),
+                              _ptr(out["sample"], c_float), _ptr(out["eval"], c_float), _ptr(out["pdf"], c_float), _ptr(out["albedo"], c_float),
+                              _ptr(out["normal"], c_float))
         return out
 
     def render(self, spp_begin=0, spp_end=None, raw=False):

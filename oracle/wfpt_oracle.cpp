@@ -15,6 +15,8 @@
 // one path at a time instead of in waves; per-path arithmetic and RNG draw order are those of
 // the wavefront kernels.  All arithmetic is IEEE fp32, compiled with -ffp-contract=off.
 #include "orc_math.h"
+#include "orc_bsdf.h"
+#include "orc_texture.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -156,34 +158,6 @@ struct AliasTable {
 };
 
 // ------------------------------------------------------------------------------------------
-// Sampling warps (utils/cmath/cdistribution.cpp:5-85)
-// ------------------------------------------------------------------------------------------
-V3 sample_hemisphere_zweighted(float u1, float u2) {  // cdistribution.cpp:31-54
-    float sx = 0, sy = 0;
-    u1 = 2.0f * u1 - 1.0f;
-    u2 = 2.0f * u2 - 1.0f;
-    if (u1 != 0.0f || u2 != 0.0f) {
-        float theta, r;
-        if (std::fabs(u1) > std::fabs(u2)) {
-            r = u1;
-            theta = 0.25f * PI * (u2 / u1);
-        } else {
-            r = u2;
-            theta = 0.5f * PI - 0.25f * PI * (u1 / u2);
-        }
-        sx = r * std::cos(theta);
-        sy = r * std::sin(theta);
-    }
-    float z = std::sqrt(std::fmax(0.0f, 1.0f - (sx * sx + sy * sy)));
-    return {sx, sy, z};
-}
-float pdf_sample_hemisphere_zweighted(V3 v) { return v.z >= 0 ? v.z / PI : 0.0f; }  // :66-69
-V2 sample_triangle_uniform(float u1, float u2) {  // :71-75
-    float t = std::sqrt(u1);
-    return {1.0f - t, t * u2};
-}
-
-// ------------------------------------------------------------------------------------------
 // intersection_offset (utils/intersection.cpp:5-36)
 // ------------------------------------------------------------------------------------------
 V3 intersection_offset(V3 pos, V3 nor) {
@@ -208,19 +182,30 @@ V3 intersection_offset(V3 pos, V3 nor, V3 next_dir) {  // intersection.cpp:30-34
 // ------------------------------------------------------------------------------------------
 // Scene description
 // ------------------------------------------------------------------------------------------
-enum MaterialType { MAT_DIFFUSE = 0, MAT_BLACK = 1 };
-
-struct Texture2D {
-    int type = 0;  // 0 constant
-    V3 value{0, 0, 0};
-};
+// Texture slots of a material (creator argument order: diffuse.cpp:36-48, disney.cpp:844-894, metal.cpp:50-77,
+// glass.cpp:141-157, mirror.cpp:91-103)
+enum MatSlot { SLOT_COLOR = 0, SLOT_METALLIC, SLOT_ROUGHNESS, SLOT_TRANSMISSION, SLOT_IOR, SLOT_SPECULAR, SLOT_SPECULAR_TINT,
+               SLOT_ANISOTROPIC, SLOT_SHEEN, SLOT_SHEEN_TINT, SLOT_CLEARCOAT, SLOT_CLEARCOAT_GLOSS, SLOT_TRANSMISSION_ROUGHNESS, SLOT_COUNT };
 
 struct Material {
     int type = MAT_DIFFUSE;
-    int color_tex = -1;
+    int tex[SLOT_COUNT];
     int normal_tex = -1;
     bool shadow_terminator = true;
+    Material() { for (int &t : tex) t = -1; }
 };
+
+enum MediumType { MED_HOMOGENEOUS = 0, MED_HETEROGENEOUS = 1, MED_VOLPRIM = 2 };
+
+struct Medium {
+    int type = MED_VOLPRIM;
+    float sigma_t = 0; V3 albedo{0, 0, 0}; float g = 0;  // homogeneous
+    int sigma_t_tex = -1, albedo_tex = -1, g_tex = -1;   // heterogeneous (3-D textures)
+    bool has_transform = false; M4 world_to_local{};     // TransformMedium chain, composed
+    float max_density = 0.001f;
+};
+
+enum EnvType { ENV_NONE = 0, ENV_GRADIENT_SKY = 1, ENV_IBL = 2 };
 
 struct Mesh {
     int ntri = 0;
@@ -260,11 +245,20 @@ struct Stats {
 }  // namespace
 
 struct orc_scene {
-    std::vector<Texture2D> textures;
+    TextureSet tex;
+    std::vector<Texture3D> tex3d;
     std::vector<Material> materials;
+    std::vector<Medium> media;           // id order = Scene::commit order (core/scene.cpp:136-161); last = volume-primitive medium
+    bool has_medium = false;             // Scene::has_medium (core/scene.cpp:346-356)
+    // environment light (core/light_sampler.cpp:24-33: appended after the area lights)
+    int env_type = ENV_NONE; int env_light_index = -1;
+    V3 sky_lower{0, 0, 0}, sky_upper{0, 0, 0}, sky_up{0, 0, 1};
+    int ibl_tex = -1; Frame ibl_frame; int lut_w = 0, lut_h = 0;
+    std::vector<float> ibl_tile_probs; AliasTable ibl_alias;
     std::vector<Mesh> meshes;
     std::vector<Instance> instances;
-    std::vector<int> lights;  // instance index per light id
+    std::vector<int> lights;  // instance index per area-light id
+    int n_lights() const { return (int)lights.size() + (env_type != ENV_NONE ? 1 : 0); }
     // camera (builtin/camera/pinhole.cpp:55-77)
     V3 eye, dst, up; float fov_y_deg = 60, w_over_h = 1;
     V3 cam_eye, cam_lbc, cam_fx, cam_fy;
@@ -620,23 +614,106 @@ SurfacePoint get_hitinfo(const orc_scene &s, V3 o, V3 d, const Instance &inst, f
     return sp;
 }
 
-V3 eval_texture(const orc_scene &s, int tex, const SurfacePoint &) {
-    const Texture2D &t = s.textures[tex];
-    return t.value;
+V3 eval_texture(const orc_scene &s, int tex, const SurfacePoint &sp) {  // Texture2D::sample_spectrum(spt): uses spt.tex_coord
+    return s.tex.eval2d(tex, sp.tex_coord);
+}
+float eval_texture_float(const orc_scene &s, int tex, const SurfacePoint &sp) { return eval_texture(s, tex, sp).x; }
+
+V3 eval_texture3d(const orc_scene &s, int tex, V3 uvw) {  // texture3d/array3d.cpp:29-41, core/texture3d.cpp (constant)
+    const Texture3D &t = s.tex3d[tex];
+    if (t.type == TEX_CONSTANT) return t.value;
+    float o[4];
+    sample_image(s.tex.images[t.image], uvw.x, uvw.y, uvw.z, o);
+    return V3(o[0], o[1], o[2]);
+}
+
+// ---- environment lights: builtin/light/gradient_sky.cpp:20-54, ibl.cpp:27-78, env_sampler.cpp:124-187 ----------
+V3 ibl_eval_local(const orc_scene &s, V3 dir) {  // ibl.cpp:80-87
+    float phi = local_angle::phi(dir);
+    float theta = local_angle::theta(dir);
+    float u = saturate(1 / (2 * PI) * phi);
+    float v = saturate(1 / PI * theta);
+    return s.tex.eval2d(s.ibl_tex, V2{u, v});
+}
+V3 env_eval_le(const orc_scene &s, V3 to_light) {
+    if (s.env_type == ENV_GRADIENT_SKY) {
+        float cos_theta = dot(s.sky_up, normalize(to_light));
+        float t = saturate(0.5f * (cos_theta + 1.0f));
+        return s.sky_lower * (1.0f - t) + s.sky_upper * t;
+    }
+    return ibl_eval_local(s, normalize(s.ibl_frame.global_to_local(to_light)));
+}
+float ibl_pdf_local(const orc_scene &s, V3 to_light) {  // env_sampler.cpp:159-187
+    V3 dir = normalize(to_light);
+    float cos_theta = dir.z;
+    float theta = std::acos(cos_theta);
+    float phi = local_angle::phi(dir);
+    float u = phi / (2 * PI), v = theta / PI;
+    int tile_x = std::min(std::max(int(std::floor(u * s.lut_w)), 0), s.lut_w - 1);
+    int tile_y = std::min(std::max(int(std::floor(v * s.lut_h)), 0), s.lut_h - 1);
+    int tile_idx = tile_y * s.lut_w + tile_x;
+    float tile_pdf = s.ibl_tile_probs[tile_idx];
+    float u0 = float(tile_x) / s.lut_w, u1 = float(tile_x + 1) / s.lut_w;
+    float v0 = float(tile_y) / s.lut_h, v1 = float(tile_y + 1) / s.lut_h;
+    float c0 = std::cos(PI * v0), c1 = std::cos(PI * v1);
+    float in_tile_pdf = 1.0f / std::fabs(2 * PI * (u1 - u0) * (c1 - c0));
+    return tile_pdf * in_tile_pdf;
+}
+float env_pdf_li(const orc_scene &s, V3 to_light) {
+    if (s.env_type == ENV_GRADIENT_SKY) return pdf_sample_sphere_uniform();
+    return ibl_pdf_local(s, s.ibl_frame.global_to_local(to_light));  // ibl.cpp:48-52 (not normalised before the frame)
+}
+struct EnvSample { V3 dir, radiance; float pdf; };
+EnvSample env_sample_li(const orc_scene &s, V3 sam) {
+    EnvSample r;
+    if (s.env_type == ENV_GRADIENT_SKY) {
+        r.dir = sample_sphere_uniform(sam.x, sam.y);
+        r.radiance = env_eval_le(s, r.dir);
+        r.pdf = pdf_sample_sphere_uniform();
+        return r;
+    }
+    // EnvirLightSampler::sample (env_sampler.cpp:124-157)
+    uint32_t tile_idx = s.ibl_alias.sample(sam.x);
+    int tile_y = int(tile_idx) / s.lut_w, tile_x = int(tile_idx) % s.lut_w;
+    float tile_pdf = s.ibl_tile_probs[tile_idx];
+    float u0 = float(tile_x) / s.lut_w, u1 = float(tile_x + 1) / s.lut_w;
+    float v0 = float(tile_y) / s.lut_h, v1 = float(tile_y + 1) / s.lut_h;
+    float cv0 = std::cos(PI * v0), cv1 = std::cos(PI * v1);
+    if (cv0 > cv1) std::swap(cv0, cv1);
+    float cos_theta = cv0 + sam.z * (cv1 - cv0);
+    float sin_theta = local_angle::cos2sin(cos_theta);
+    float phi = 2 * PI * lerp(u0, u1, sam.y);
+    V3 dir(sin_theta * std::cos(phi), sin_theta * std::sin(phi), cos_theta);
+    float in_tile_pdf = 1.0f / (2 * PI * (u1 - u0) * (cv1 - cv0));
+    r.dir = s.ibl_frame.local_to_global(dir);
+    r.radiance = ibl_eval_local(s, dir);
+    r.pdf = tile_pdf * in_tile_pdf;
+    return r;
 }
 
 // ---- lights: builtin/light/mesh_light.cpp:17-76, geometry/triangle_mesh.cpp:188-228,
-//      core/light_sampler.cpp:41-63, wavefront/helper.cpp:10-65,174-207
+//      core/light_sampler.cpp:41-63, wavefront/helper.cpp:10-65,125-142,174-207
 struct LiSample { bool success = false; V3 o, d; float t1 = 0, light_pdf = 0; V3 li; };
 
-LiSample sample_surface_light_li(const orc_scene &s, V3 ref_pos, V3 ref_nor, Sampler &sampler) {
+// surface = true: o = intersection_offset(ref_pos, ref_nor, dir) (sample_surface_light_li); false: o = ref_pos (medium)
+LiSample sample_light_li(const orc_scene &s, V3 ref_pos, V3 ref_nor, bool surface, Sampler &sampler) {
     LiSample r;
     V3 sam = sampler.get3d();
     float sel = sampler.get1d();
-    const int n = (int)s.lights.size();
+    const int n = s.n_lights();
     if (n == 0) return r;
     int idx = std::min(int(sel * n), n - 1);
     float select_pdf = 1.0f / float(n);
+    if (idx == s.env_light_index) {  // process_envir_light (helper.cpp:36-44)
+        EnvSample es = env_sample_li(s, sam);
+        r.o = surface ? intersection_offset(ref_pos, ref_nor, es.dir) : ref_pos;
+        r.d = es.dir;
+        r.t1 = MAX_FLOAT;
+        r.li = es.radiance;
+        r.light_pdf = select_pdf * es.pdf;
+        r.success = true;
+        return r;
+    }
     const Instance &li = s.instances[s.lights[idx]];
     const Mesh &m = s.meshes[li.mesh];
     // TriangleMesh::sample_inline
@@ -659,7 +736,7 @@ LiSample sample_surface_light_li(const orc_scene &s, V3 ref_pos, V3 ref_nor, Sam
     // helper.cpp:24-34
     V3 diff = spos - ref_pos;
     V3 shadow_dst = intersection_offset(spos, snor, -diff);
-    r.o = intersection_offset(ref_pos, ref_nor, diff);
+    r.o = surface ? intersection_offset(ref_pos, ref_nor, diff) : ref_pos;
     r.d = shadow_dst - r.o;
     r.t1 = 1;
     r.li = rad;
@@ -668,10 +745,26 @@ LiSample sample_surface_light_li(const orc_scene &s, V3 ref_pos, V3 ref_nor, Sam
     return r;
 }
 
+// helper.cpp:144-172
+V3 eval_miss_le(const orc_scene &s, V3 o, V3 d, V3 beta_le, float bsdf_pdf) {
+    V3 result(0);
+    if (s.env_type != ENV_NONE) {
+        V3 le = env_eval_le(s, d);
+        if (bsdf_pdf < 0) result = beta_le * le / -bsdf_pdf;
+        else {
+            float select_light_pdf = 1.0f / float(s.n_lights());
+            float envir_light_pdf = env_pdf_li(s, d);
+            float light_pdf = select_light_pdf * envir_light_pdf;
+            result = beta_le * le / (bsdf_pdf + light_pdf);
+        }
+    }
+    return result;
+}
+
 V3 handle_intersected_light(const orc_scene &s, V3 o, V3 d, const SurfacePoint &inct, V3 beta_le, float bsdf_pdf, int light_index) {
     V3 result(0);
     if (light_index >= 0) {
-        const int n = (int)s.lights.size();
+        const int n = s.n_lights();
         float select_pdf = 1.0f / float(n);
         const Instance &li = s.instances[s.lights[light_index]];
         const Mesh &m = s.meshes[li.mesh];
@@ -712,102 +805,41 @@ bool simple_russian_roulette(const orc_scene &s, V3 &beta, int depth, Sampler &s
     return ret;
 }
 
-// ---- shader: material/utils/shader_frame.cpp:5-95, material/utils/aggregate.cpp:32-230,
-//      material/component/diffuse.cpp:5-60, material/diffuse.cpp:21-34
-struct ShaderFrame {
-    Frame geometry, shading;
-    bool is_black_fringes(V3 w) const { return geometry.in_positive_z_hemisphere(w) != shading.in_positive_z_hemisphere(w); }
-    float correct_shading_energy(V3 wi) const {
-        float down = std::fabs(dot(geometry.z, wi));
-        if (down > 1e-4f) return std::fabs(dot(shading.z, wi)) / down;
-        return 1;
-    }
-    ShaderFrame flip_for_black_fringes(V3 wo) const {
-        ShaderFrame f; f.geometry = geometry;
-        f.shading = is_black_fringes(wo) ? geometry : shading;
-        return f;
-    }
-};
-
-struct BsdfSample { V3 bsdf{0, 0, 0}, dir{0, 0, 0}; float pdf = 0; bool is_delta = false; };
-
-struct Shader {
-    int type = MAT_DIFFUSE;
-    ShaderFrame frame;
-    bool shadow_terminator = true;
-    V3 albedo_value;  // diffuse
-
-    float shadow_terminator_term(V3 wi) const {  // aggregate.cpp:219-230
-        if (!shadow_terminator) return 1.0f;
-        float wgwi = dot(frame.geometry.z, wi);
-        float wswi = dot(frame.shading.z, wi);
-        float wgws = dot(frame.geometry.z, frame.shading.z);
-        float g = saturate(wgwi / (wswi * wgws));
-        return -g * g * g + g * g + g;
-    }
-    V3 albedo() const { return type == MAT_BLACK ? V3(0) : albedo_value; }
-    V3 normal() const { return frame.shading.z; }
-
-    BsdfSample sample(V3 wo, V3 sam) const {  // aggregate.cpp:47-119 with the single diffuse closure
-        BsdfSample result;
-        if (type == MAT_BLACK) return result;
-        ShaderFrame fr = frame.flip_for_black_fringes(wo);
-        V3 lwo = normalize(fr.shading.global_to_local(wo));
-        float comp_selector = 1.0f * sam.x;          // sum_weight_(=1) * sam[0]
-        float s0 = comp_selector / 1.0f;             // last component: selector / sample_weight
-        // DiffuseComponentImpl::sample_bidir (component/diffuse.cpp:10-30)
-        if (lwo.z <= 0) return result;
-        V3 lwi = sample_hemisphere_zweighted(s0, sam.y);
-        V3 bsdf = albedo_value / PI;
-        float cpdf = pdf_sample_hemisphere_zweighted(lwi);
-        if (cpdf <= 0) return result;
-        float pdf = 1.0f * cpdf;
-        result.dir = fr.shading.local_to_global(lwi);
-        if (frame.is_black_fringes(result.dir)) return BsdfSample();
-        result.bsdf = bsdf;
-        result.pdf = pdf / 1.0f;
-        float corr = fr.correct_shading_energy(result.dir);
-        float stt = shadow_terminator_term(result.dir);
-        result.bsdf = result.bsdf * corr * stt;
-        result.is_delta = false;
-        return result;
-    }
-    V3 eval(V3 wi, V3 wo) const {  // aggregate.cpp:185-197
-        if (type == MAT_BLACK) return V3(0);
-        ShaderFrame fr = frame.flip_for_black_fringes(wo);
-        V3 lwi = normalize(fr.shading.global_to_local(wi));
-        V3 lwo = normalize(fr.shading.global_to_local(wo));
-        V3 result(0);
-        if (!(lwi.z <= 0 || lwo.z <= 0)) result = result + albedo_value / PI;
-        float corr = fr.correct_shading_energy(wi);
-        float stt = shadow_terminator_term(wi);
-        return result * corr * stt;
-    }
-    float pdf(V3 wi, V3 wo) const {  // aggregate.cpp:199-209
-        if (type == MAT_BLACK) return 0;
-        ShaderFrame fr = frame.flip_for_black_fringes(wo);
-        V3 lwi = normalize(fr.shading.global_to_local(wi));
-        V3 lwo = normalize(fr.shading.global_to_local(wo));
-        float result = 0;
-        float c = (lwi.z <= 0 || lwo.z <= 0) ? 0.0f : pdf_sample_hemisphere_zweighted(lwi);
-        result = result + 1.0f * c;
-        return result / 1.0f;
-    }
-};
-
+// Material::create_shader: diffuse.cpp:21-34, disney.cpp:813-842, metal.cpp:31-48, glass.cpp:120-139, mirror.cpp:78-89,
+// black.cpp:50-53, invisible.cpp:46-51; normal map: material/utils/normal_map.cpp:13-21
 Shader create_shader(const orc_scene &s, const Material &mat, const SurfacePoint &inct) {
     Shader sh;
     sh.type = mat.type;
     sh.frame.geometry = inct.frame;
+    if (mat.type == MAT_BLACK || mat.type == MAT_INVISIBLE) { sh.frame.shading = inct.frame; return sh; }
     sh.frame.shading = inct.frame.rotate_to_new_z(inct.interp_z);
-    if (mat.normal_tex >= 0) {  // material/utils/normal_map.cpp:13-21
+    if (mat.normal_tex >= 0) {
         V3 c = eval_texture(s, mat.normal_tex, inct);
         V3 local_nor = 2.0f * c - V3(1.0f);
         V3 world_nor = sh.frame.shading.local_to_global(local_nor);
         sh.frame.shading = sh.frame.shading.rotate_to_new_z(normalize(world_nor));
     }
     sh.shadow_terminator = mat.shadow_terminator;
-    if (mat.type == MAT_DIFFUSE) sh.albedo_value = eval_texture(s, mat.color_tex, inct);
+    auto F = [&](int slot) { return eval_texture_float(s, mat.tex[slot], inct); };
+    switch (mat.type) {
+    case MAT_DIFFUSE: sh.diffuse.albedo_value = eval_texture(s, mat.tex[SLOT_COLOR], inct); break;
+    case MAT_METAL:
+        sh.metal = MicrofacetReflection(eval_texture(s, mat.tex[SLOT_COLOR], inct), F(SLOT_ROUGHNESS), F(SLOT_ANISOTROPIC));
+        break;
+    case MAT_DISNEY: {
+        V3 base_color = eval_texture(s, mat.tex[SLOT_COLOR], inct);
+        float metallic = F(SLOT_METALLIC), roughness = F(SLOT_ROUGHNESS), transmission = F(SLOT_TRANSMISSION);
+        float transmission_roughness = F(SLOT_TRANSMISSION_ROUGHNESS), ior = F(SLOT_IOR), specular = F(SLOT_SPECULAR);
+        float specular_tint = F(SLOT_SPECULAR_TINT), anisotropic = F(SLOT_ANISOTROPIC), sheen = F(SLOT_SHEEN), sheen_tint = F(SLOT_SHEEN_TINT);
+        float clearcoat = F(SLOT_CLEARCOAT), clearcoat_gloss = F(SLOT_CLEARCOAT_GLOSS);
+        sh.disney = DisneyBSDF(base_color, metallic, roughness, specular, specular_tint, anisotropic, sheen, sheen_tint, clearcoat,
+                               clearcoat_gloss, transmission, transmission_roughness, ior);
+        break;
+    }
+    case MAT_GLASS: sh.color = eval_texture(s, mat.tex[SLOT_COLOR], inct); sh.ior = F(SLOT_IOR); break;
+    case MAT_MIRROR: sh.color = eval_texture(s, mat.tex[SLOT_COLOR], inct); break;
+    default: break;
+    }
     return sh;
 }
 
@@ -818,25 +850,27 @@ struct ShadeOut {
     bool has_gbuffer = false; V3 albedo, normal;
 };
 
-// wavefront/shade.cpp:38-235 (no medium => is_scattered is always false)
-void shade(const orc_scene &s, const PathState &in, const Hit &hit, ShadeOut &out) {
+// wavefront/shade.cpp:38-235.  `scattered` = bit 31 of the intersection flag, set by the medium stage.
+void shade(const orc_scene &s, const PathState &in, const Hit &hit, bool scattered, ShadeOut &out) {
     PathState path = in;
     Sampler &sampler = path.sampler;
     if (!hit.hit) {
-        // no environment light support yet => eval_miss_le contributes 0 (shade.cpp:56-69)
-        out.radiance.valid = true; out.radiance.value = V3(0) + path.L;
+        V3 splat = eval_miss_le(s, in.o, in.d, in.beta_le, in.bsdf_pdf);
+        if (!scattered) splat = splat + path.L;
+        out.radiance.valid = true; out.radiance.value = splat;
         return;
     }
     const Instance &inst = s.instances[hit.inst];
     SurfacePoint inct = get_hitinfo(s, in.o, in.d, inst, hit.t, hit.prim, V2{hit.u, hit.v});
     V3 le_rad = handle_intersected_light(s, in.o, in.d, inct, in.beta_le, in.bsdf_pdf, inst.light_id);
+    if (scattered) { out.radiance.valid = true; out.radiance.value = le_rad; return; }
     path.L = path.L + le_rad;
     if (simple_russian_roulette(s, path.beta, path.depth, sampler)) {
         out.radiance.valid = true; out.radiance.value = path.L;
         return;
     }
     V3 shadow_bsdf_val(0); float shadow_bsdf_pdf = 0;
-    LiSample ls = sample_surface_light_li(s, inct.position, inct.frame.z, sampler);
+    LiSample ls = sample_light_li(s, inct.position, inct.frame.z, true, sampler);
     Shader shader = create_shader(s, s.materials[inst.material], inct);
     if (path.depth == 0) { out.has_gbuffer = true; out.albedo = shader.albedo(); out.normal = shader.normal(); }
     V3 wo = -in.d;
@@ -877,6 +911,191 @@ void shade(const orc_scene &s, const PathState &in, const Hit &hit, ShadeOut &ou
     }
 }
 
+// ---- media: builtin/medium/homogeneous.cpp:25-73, hetergeneous.cpp:25-106, core/medium.cpp:32-129 -----------------
+float henyey_greenstein(float g, float u) {  // utils/henyey_greenstein.h:10-18
+    float g2 = g * g;
+    float dem = 1.0f + g2 - 2.0f * (g * u);
+    return (1.0f - g2) / (4.0f * PI * dem * std::sqrt(dem));
+}
+float cos_between(V3 a, V3 b) { return dot(normalize(a), normalize(b)); }  // cvec3.h:182-185
+
+struct PhaseShader {  // HenyeyGreensteinPhaseShader (core/medium.cpp:22-76)
+    float g = 0; V3 color{0, 0, 0};
+    V3 eval(V3 wi, V3 wo) const { float f = henyey_greenstein(g, -cos_between(wi, wo)); return color * V3(f, f, f); }
+    float pdf(V3 wi, V3 wo) const { return henyey_greenstein(g, -cos_between(wi, wo)); }
+    void sample(V3 wo, V3 sam, V3 &phase, V3 &dir, float &pdf_out) const {
+        float sv = sam.x + sam.x - 1;
+        float u;
+        if (std::fabs(g) < 0.001f) u = sv;
+        else { float g2 = g * g; u = (1.0f + g2 - sqr((1.0f - g2) / (1.0f + g * sv))) / (g + g); }
+        float cos_theta = -u;
+        float sin_theta = local_angle::cos2sin(cos_theta);
+        float phi = 2 * PI * sam.y;
+        V3 local_wi(sin_theta * std::sin(phi), sin_theta * std::cos(phi), cos_theta);
+        float phase_val = henyey_greenstein(g, u);
+        phase = color * V3(phase_val, phase_val, phase_val);
+        dir = Frame::from_z(wo).local_to_global(local_wi);
+        pdf_out = phase_val;
+    }
+};
+
+V3 medium_uvw(const Medium &m, V3 p) {  // TransformMedium (core/medium.cpp:98-129): world_to_local.apply_to_point
+    if (!m.has_transform) return p;
+    const M4 &w = m.world_to_local;
+    return {w.m[0][0] * p.x + w.m[0][1] * p.y + w.m[0][2] * p.z + w.m[0][3],
+            w.m[1][0] * p.x + w.m[1][1] * p.y + w.m[1][2] * p.z + w.m[1][3],
+            w.m[2][0] * p.x + w.m[2][1] * p.y + w.m[2][2] * p.z + w.m[2][3]};
+}
+
+struct MediumSample { bool scattered = false; V3 position; V3 throughput{1, 1, 1}; PhaseShader shader; };
+
+MediumSample medium_sample(const orc_scene &s, const Medium &m, V3 a, V3 b, Sampler &sampler) {
+    MediumSample r;
+    if (m.type == MED_VOLPRIM) return r;  // no volume primitives: core/volume.cpp:124-129
+    if (m.type == MED_HOMOGENEOUS) {  // homogeneous.cpp:25-58
+        float t_max = length(b - a);
+        float st = -std::log(1.0f - sampler.get1d()) / m.sigma_t;
+        if (st < t_max) {
+            float t = st / t_max;
+            r.scattered = true;
+            r.position = a * (1.0f - t) + b * t;
+            r.shader.g = m.g; r.shader.color = m.albedo;
+        }
+        return r;
+    }
+    // hetergeneous.cpp:25-73 (delta tracking against the global majorant)
+    const float inv_max_density = 1.0f / m.max_density;
+    float t_max = length(b - a), t = 0.0f;
+    V3 local_a = V3(0.5f) + 0.5f * medium_uvw(m, a);
+    V3 local_b = V3(0.5f) + 0.5f * medium_uvw(m, b);
+    V3 local_ba_div_t_max = (local_b - local_a) / t_max;
+    V3 ba_div_t_max = (b - a) / t_max;
+    for (;;) {
+        float dt = -std::log(1.0f - sampler.get1d()) * inv_max_density;
+        t = t + dt;
+        if (t >= t_max) break;
+        V3 uvw = local_a + t * local_ba_div_t_max;
+        float density = eval_texture3d(s, m.sigma_t_tex, uvw).x;
+        if (sampler.get1d() < density * inv_max_density) {
+            r.scattered = true;
+            r.position = a + t * ba_div_t_max;
+            r.shader.color = eval_texture3d(s, m.albedo_tex, uvw);
+            r.shader.g = eval_texture3d(s, m.g_tex, uvw).x;
+            break;
+        }
+    }
+    return r;
+}
+
+V3 medium_tr(const orc_scene &s, const Medium &m, V3 a, V3 b, Sampler &sampler) {
+    if (m.type == MED_VOLPRIM) return V3(1, 1, 1);
+    if (m.type == MED_HOMOGENEOUS) {  // homogeneous.cpp:60-73: sigma_a = sigma_t * (1 - albedo)
+        V3 sigma_a = m.sigma_t * (V3(1, 1, 1) - m.albedo);
+        V3 e = -length(a - b) * sigma_a;
+        return V3(std::exp(e.x), std::exp(e.y), std::exp(e.z));
+    }
+    // hetergeneous.cpp:75-106 (ratio tracking)
+    float result = 1.0f, t = 0.0f, t_max = length(b - a);
+    const float inv_max_density = 1.0f / m.max_density;
+    V3 local_a = V3(0.5f) + 0.5f * medium_uvw(m, a);
+    V3 local_b = V3(0.5f) + 0.5f * medium_uvw(m, b);
+    V3 local_ba_div_t_max = (local_b - local_a) / t_max;
+    for (;;) {
+        float dt = -std::log(1.0f - sampler.get1d()) * inv_max_density;
+        t = t + dt;
+        if (t >= t_max) break;
+        V3 uvw = local_a + t * local_ba_div_t_max;
+        float density = eval_texture3d(s, m.sigma_t_tex, uvw).x;
+        result = result * (1.0f - density * inv_max_density);
+    }
+    return V3(result, result, result);
+}
+
+struct MediumOut {
+    bool scattered = false;
+    bool has_next = false; PathState next;
+    ShadowRay shadow;
+    Splat radiance;
+};
+
+// wavefront/medium.cpp:36-164 + get_medium_segment (:214-249).  `ps` is updated in place the way the kernel updates its
+// slot: resolved medium id, beta_le *= unscatter_tr, and (only when not scattered) the advanced sampler.
+void medium_stage(const orc_scene &s, PathState &ps, const Hit &hit, MediumOut &out) {
+    PathState path = ps;
+    Sampler &sampler = path.sampler;
+    uint32_t medium_id; V3 medium_end;
+    if (hit.hit) {
+        const Instance &inst = s.instances[hit.inst];
+        const Mesh &m = s.meshes[inst.mesh];
+        V3 local_normal(m.gz_uca[4 * hit.prim], m.gz_uca[4 * hit.prim + 1], m.gz_uca[4 * hit.prim + 2]);
+        V3 inct_nor = inst.xf.normal(local_normal);
+        uint32_t inct_medium_id = dot(ps.d, inct_nor) < 0 ? inst.outer_medium : inst.inner_medium;
+        medium_id = std::min(inct_medium_id, ps.medium_id);  // resolve_mediums (wavefront/medium.cpp:12-15): smaller id = higher priority
+        medium_end = intersection_offset(ps.o + hit.t * ps.d, inct_nor, -ps.d);
+    } else {
+        medium_id = s.vol_prim_medium_id;
+        medium_end = ps.o + normalize(ps.d) * s.world_diagonal;
+    }
+    ps.medium_id = medium_id;
+    const Medium &medium = s.media[medium_id];
+    MediumSample ms = medium_sample(s, medium, ps.o, medium_end, sampler);
+    V3 unscatter_tr = medium_tr(s, medium, ps.o, medium_end, sampler);
+    ps.beta_le = ps.beta_le * unscatter_tr;
+    if (!ms.scattered) { ps.sampler = sampler; return; }
+    out.scattered = true;
+    path.beta = path.beta * ms.throughput;
+    if (simple_russian_roulette(s, path.beta, path.depth, sampler)) {
+        out.radiance.valid = true; out.radiance.value = path.L;
+        return;
+    }
+    LiSample ls = sample_light_li(s, ms.position, V3(0), false, sampler);
+    if (ls.success) {
+        V3 shadow_phase_val = ms.shader.eval(ls.d, -ps.d);
+        float shadow_phase_pdf = ms.shader.pdf(ls.d, -ps.d);
+        ls.li = ls.li * path.beta * shadow_phase_val / (shadow_phase_pdf + ls.light_pdf);
+    }
+    V3 phase, pdir; float ppdf;
+    ms.shader.sample(-ps.d, sampler.get3d(), phase, pdir, ppdf);
+    if (ls.success) {
+        out.shadow.valid = true; out.shadow.px = path.px; out.shadow.py = path.py;
+        out.shadow.beta_li = ls.li; out.shadow.o = ls.o; out.shadow.d = ls.d; out.shadow.t1 = ls.t1;
+        out.shadow.medium_id = ls.t1 > 1 ? s.vol_prim_medium_id : medium_id;
+    }
+    if (!is_zero(phase)) {
+        pdir = normalize(pdir);
+        V3 beta_le = path.beta * phase;
+        path.beta = beta_le / ppdf;
+        out.has_next = true;
+        out.next = path;
+        out.next.depth = path.depth + 1;
+        out.next.beta_le = beta_le; out.next.bsdf_pdf = ppdf;
+        out.next.o = ms.position; out.next.d = pdir; out.next.t1 = MAX_FLOAT; out.next.medium_id = medium_id;
+    } else {
+        out.radiance.valid = true; out.radiance.value = path.L;
+    }
+}
+
+// Shadow-ray transmittance sampler.  The reference keeps one PCG per shadow-queue SLOT (soa_buffer.cpp:86-96), so its
+// media renders are not reproducible run to run.  Both this oracle and the CUDA path key the stream on
+// the ray itself instead: seed = murmur64A over the 32 bytes (o.xyz, medium id, d.xyz, t1).  Same distribution.
+Sampler shadow_sampler(const ShadowRay &r) {
+    uint8_t buf[32];
+    float f[8] = {r.o.x, r.o.y, r.o.z, u2f(r.medium_id), r.d.x, r.d.y, r.d.z, r.t1};
+    std::memcpy(buf, f, 32);
+    Sampler sm;
+    sm.rng.seed(murmur_hash64A(buf, 32, 0));
+    return sm;
+}
+
+// shadow.cpp:39-74: transmittance of an unoccluded shadow ray
+V3 shadow_tr(const orc_scene &s, const ShadowRay &r) {
+    if (!s.has_medium) return V3(1, 1, 1);
+    Sampler sm = shadow_sampler(r);
+    if (r.t1 > 1) return medium_tr(s, s.media[s.vol_prim_medium_id], r.o, r.o + normalize(r.d) * s.world_diagonal, sm);
+    V3 end_pnt = r.o + r.d * r.t1;
+    return medium_tr(s, s.media[r.medium_id], r.o, end_pnt, sm);
+}
+
 // core/film.cpp:131-165 (bounds + isfinite checks)
 inline void film_add(float *rgba, V3 v) { if (isfinite3(v)) { rgba[0] += v.x; rgba[1] += v.y; rgba[2] += v.z; } }
 
@@ -891,15 +1110,103 @@ orc_scene *orc_scene_new() { return new orc_scene(); }
 void orc_scene_free(orc_scene *s) { delete s; }
 
 int orc_add_texture_constant(orc_scene *s, float r, float g, float b) {
-    Texture2D t; t.type = 0; t.value = V3(r, g, b);
-    s->textures.push_back(t);
-    return (int)s->textures.size() - 1;
+    Texture2D t; t.type = TEX_CONSTANT; t.value = V3(r, g, b);
+    s->tex.tex2d.push_back(t);
+    return (int)s->tex.tex2d.size() - 1;
 }
 
-int orc_add_material(orc_scene *s, int type, int color_tex, int normal_tex, int shadow_terminator) {
-    Material m; m.type = type; m.color_tex = color_tex; m.normal_tex = normal_tex; m.shadow_terminator = shadow_terminator != 0;
+// Decoded image (2-D when depth == 0).  data: w*h*max(d,1)*channels floats, already normalised to [0,1] for 8-bit sources;
+// srgb != 0 applies the sRGB->linear decode to the first three channels (cudaTextureDesc::sRGB; 8-bit 4-channel only).
+int orc_add_image(orc_scene *s, int w, int h, int d, int channels, const float *data, int srgb, int addr_u, int addr_v, int addr_w,
+                  int linear, const float *border) {
+    TexImage im; im.w = w; im.h = h; im.d = d; im.channels = channels;
+    const size_t n = (size_t)w * h * (d > 0 ? d : 1);
+    im.data.assign(data, data + n * channels);
+    // Array::find_minmax_values runs on the raw texel data (before any sRGB decode)
+    for (int c = 0; c < 3; ++c) { im.max_value[c] = -MAX_FLOAT; im.min_value[c] = MAX_FLOAT; }
+    for (size_t i = 0; i < n; ++i)
+        for (int c = 0; c < std::min(channels, 3); ++c) {
+            im.max_value[c] = std::fmax(im.max_value[c], im.data[i * channels + c]);
+            im.min_value[c] = std::fmin(im.min_value[c], im.data[i * channels + c]);
+        }
+    if (srgb && channels == 4)
+        for (size_t i = 0; i < n; ++i)
+            for (int c = 0; c < 3; ++c) im.data[4 * i + c] = srgb_to_linear(im.data[4 * i + c]);
+    im.addr[0] = addr_u; im.addr[1] = addr_v; im.addr[2] = addr_w; im.linear = linear != 0;
+    if (border) for (int c = 0; c < 4; ++c) im.border[c] = border[c];
+    s->tex.images.push_back(std::move(im));
+    return (int)s->tex.images.size() - 1;
+}
+
+int orc_add_texture_array(orc_scene *s, int image) {
+    Texture2D t; t.type = TEX_ARRAY; t.image = image;
+    s->tex.tex2d.push_back(t);
+    return (int)s->tex.tex2d.size() - 1;
+}
+
+// op: TEX_ADD / TEX_SUB / TEX_MUL / TEX_DIV
+int orc_add_texture_binary(orc_scene *s, int op, int lhs, int rhs) {
+    Texture2D t; t.type = op; t.lhs = lhs; t.rhs = rhs;
+    s->tex.tex2d.push_back(t);
+    return (int)s->tex.tex2d.size() - 1;
+}
+
+int orc_add_texture_transform(orc_scene *s, int inner, const float *m6) {
+    Texture2D t; t.type = TEX_TRANSFORM; t.lhs = inner;
+    for (int i = 0; i < 6; ++i) t.m[i] = m6[i];
+    s->tex.tex2d.push_back(t);
+    return (int)s->tex.tex2d.size() - 1;
+}
+
+void orc_eval_texture2d(orc_scene *s, int tex, int n, const float *uv, float *out_rgb) {
+    for (int i = 0; i < n; ++i) {
+        V3 v = s->tex.eval2d(tex, V2{uv[2 * i], uv[2 * i + 1]});
+        out_rgb[3 * i] = v.x; out_rgb[3 * i + 1] = v.y; out_rgb[3 * i + 2] = v.z;
+    }
+}
+
+int orc_add_texture3d_constant(orc_scene *s, float r, float g, float b) {
+    Texture3D t; t.type = TEX_CONSTANT; t.value = V3(r, g, b);
+    s->tex3d.push_back(t);
+    return (int)s->tex3d.size() - 1;
+}
+
+int orc_add_texture3d_array(orc_scene *s, int image) {
+    Texture3D t; t.type = TEX_ARRAY; t.image = image;
+    s->tex3d.push_back(t);
+    return (int)s->tex3d.size() - 1;
+}
+
+// tex13: texture id per MatSlot (-1 where the material type has no such parameter)
+int orc_add_material(orc_scene *s, int type, const int *tex13, int normal_tex, int shadow_terminator) {
+    Material m; m.type = type; m.normal_tex = normal_tex; m.shadow_terminator = shadow_terminator != 0;
+    for (int i = 0; i < SLOT_COUNT; ++i) m.tex[i] = tex13[i];
     s->materials.push_back(m);
     return (int)s->materials.size() - 1;
+}
+
+// Media are added in final id order (the front-end sorts by priority like Scene::commit); the volume-primitive medium is
+// appended by orc_commit.  Returns the medium id.
+int orc_add_medium_homogeneous(orc_scene *s, float sigma_t, const float *albedo, float g) {
+    Medium m; m.type = MED_HOMOGENEOUS; m.sigma_t = sigma_t; m.albedo = V3(albedo[0], albedo[1], albedo[2]); m.g = g;
+    s->media.push_back(m);
+    return (int)s->media.size() - 1;
+}
+
+int orc_add_medium_heterogeneous(orc_scene *s, int sigma_t_tex, int albedo_tex, int g_tex, const float *world_to_local16) {
+    Medium m; m.type = MED_HETEROGENEOUS; m.sigma_t_tex = sigma_t_tex; m.albedo_tex = albedo_tex; m.g_tex = g_tex;
+    if (world_to_local16) { m.has_transform = true; std::memcpy(m.world_to_local.m, world_to_local16, 64); }
+    const Texture3D &t = s->tex3d[sigma_t_tex];
+    const float mx = t.type == TEX_CONSTANT ? t.value.x : s->tex.images[t.image].max_value[0];
+    m.max_density = std::fmax(mx, 0.001f);  // hetergeneous.cpp:33
+    s->media.push_back(m);
+    return (int)s->media.size() - 1;
+}
+
+void orc_set_gradient_sky(orc_scene *s, const float *lower, const float *upper, const float *up) {
+    s->env_type = ENV_GRADIENT_SKY;
+    s->sky_lower = V3(lower[0], lower[1], lower[2]); s->sky_upper = V3(upper[0], upper[1], upper[2]);
+    s->sky_up = host_normalize(V3(up[0], up[1], up[2]));  // gradient_sky.cpp:15-18
 }
 
 int orc_add_mesh(orc_scene *s, int ntri, const float *pos, const float *nor, const uint8_t *has_nor, const float *uv) {
@@ -908,9 +1215,12 @@ int orc_add_mesh(orc_scene *s, int ntri, const float *pos, const float *nor, con
     return (int)s->meshes.size() - 1;
 }
 
+// inner_medium / outer_medium: medium id, or -1 for "no medium" (= the volume-primitive medium)
 int orc_add_instance(orc_scene *s, int mesh, int material, const float *mat16, const float *inv16,
-                     int has_light, const float *intensity) {
+                     int has_light, const float *intensity, int inner_medium, int outer_medium) {
     Instance in; in.mesh = mesh; in.material = material;
+    in.inner_medium = (uint32_t)inner_medium; in.outer_medium = (uint32_t)outer_medium;
+    if (inner_medium >= 0 || outer_medium >= 0) s->has_medium = true;
     std::memcpy(in.xf.mat.m, mat16, 64); std::memcpy(in.xf.inv.m, inv16, 64);
     if (has_light) {
         in.light_id = (int)s->lights.size();
@@ -956,7 +1266,14 @@ void orc_commit(orc_scene *s) {
     hi = V3(std::fmax(hi.x, s->eye.x), std::fmax(hi.y, s->eye.y), std::fmax(hi.z, s->eye.z));
     s->bb_lo = lo; s->bb_hi = hi;
     s->world_diagonal = 1.2f * length(hi - lo);
-    s->vol_prim_medium_id = 0;  // no media: the volume-primitive medium is the only one (scene.cpp:144-160)
+    // medium ids (scene.cpp:136-161): real media in priority order, then the volume-primitive medium
+    s->vol_prim_medium_id = (uint32_t)s->media.size();
+    s->media.emplace_back();  // MED_VOLPRIM
+    for (auto &inst : s->instances) {
+        if ((int)inst.inner_medium < 0) inst.inner_medium = s->vol_prim_medium_id;
+        if ((int)inst.outer_medium < 0) inst.outer_medium = s->vol_prim_medium_id;
+    }
+    s->env_light_index = s->env_type != ENV_NONE ? (int)s->lights.size() : -1;
     s->committed = true;
 }
 
@@ -1059,7 +1376,7 @@ void orc_shade(orc_scene *s, int n,
         h.hit = (flag[i] >> 30) & 1;
         if (h.hit) { h.inst = flag[i] & 0x3fffffffu; h.t = u2f(detail[4 * i]); h.prim = detail[4 * i + 1]; h.u = u2f(detail[4 * i + 2]); h.v = u2f(detail[4 * i + 3]); }
         ShadeOut out;
-        shade(*s, ps, h, out);
+        shade(*s, ps, h, ((flag[i] >> 31) & 1) != 0, out);
         uint32_t st = 0;
         if (out.has_next) { st |= 1; store_state(out.next, i, n_o_med, n_d_t1, n_pixel, n_beta_depth, n_path_rad, n_rng, n_ble); }
         if (out.shadow.valid) {
@@ -1075,6 +1392,80 @@ void orc_shade(orc_scene *s, int n,
             gbuf_normal[3 * i] = out.normal.x; gbuf_normal[3 * i + 1] = out.normal.y; gbuf_normal[3 * i + 2] = out.normal.z;
         }
         status[i] = st;
+    }
+}
+
+// medium stage on a batch (wavefront/medium.cpp:36-164).  In-place outputs mirror what the kernel writes back to its own
+// slot: o_med.w (resolved medium id), ble (beta_le * unscatter_tr), flag (bit 31 when scattered), rng (advanced only when
+// not scattered).  Uncompacted per-slot outputs like orc_shade: status bits 1 = next state, 2 = shadow ray, 4 = radiance splat.
+void orc_medium(orc_scene *s, int n,
+                float *o_med, const float *d_t1, const uint32_t *pixel, const float *beta_depth, const float *path_rad,
+                uint64_t *rng, float *ble, uint32_t *flag, const uint32_t *detail,
+                uint32_t *status,
+                float *n_o_med, float *n_d_t1, uint32_t *n_pixel, float *n_beta_depth, float *n_path_rad, uint64_t *n_rng, float *n_ble,
+                float *sh_o_med, float *sh_d_t1, float *sh_beta_li, float *splat_rgb) {
+#pragma omp parallel for
+    for (int i = 0; i < n; ++i) {
+        PathState ps;
+        load_state(ps, i, o_med, d_t1, pixel, beta_depth, path_rad, rng, ble);
+        Hit h;
+        h.hit = (flag[i] >> 30) & 1;
+        if (h.hit) { h.inst = flag[i] & 0x3fffffffu; h.t = u2f(detail[4 * i]); h.prim = detail[4 * i + 1]; h.u = u2f(detail[4 * i + 2]); h.v = u2f(detail[4 * i + 3]); }
+        MediumOut out;
+        medium_stage(*s, ps, h, out);
+        o_med[4 * i + 3] = u2f(ps.medium_id);
+        ble[4 * i] = ps.beta_le.x; ble[4 * i + 1] = ps.beta_le.y; ble[4 * i + 2] = ps.beta_le.z;
+        uint32_t st = 0;
+        if (out.scattered) flag[i] |= 1u << 31;
+        else { rng[2 * i] = ps.sampler.rng.state; rng[2 * i + 1] = ps.sampler.rng.inc; }
+        if (out.has_next) { st |= 1; store_state(out.next, i, n_o_med, n_d_t1, n_pixel, n_beta_depth, n_path_rad, n_rng, n_ble); }
+        if (out.shadow.valid) {
+            st |= 2;
+            sh_o_med[4 * i] = out.shadow.o.x; sh_o_med[4 * i + 1] = out.shadow.o.y; sh_o_med[4 * i + 2] = out.shadow.o.z; sh_o_med[4 * i + 3] = u2f(out.shadow.medium_id);
+            sh_d_t1[4 * i] = out.shadow.d.x; sh_d_t1[4 * i + 1] = out.shadow.d.y; sh_d_t1[4 * i + 2] = out.shadow.d.z; sh_d_t1[4 * i + 3] = out.shadow.t1;
+            sh_beta_li[4 * i] = out.shadow.beta_li.x; sh_beta_li[4 * i + 1] = out.shadow.beta_li.y; sh_beta_li[4 * i + 2] = out.shadow.beta_li.z; sh_beta_li[4 * i + 3] = 1;
+        }
+        if (out.radiance.valid) { st |= 4; splat_rgb[3 * i] = out.radiance.value.x; splat_rgb[3 * i + 1] = out.radiance.value.y; splat_rgb[3 * i + 2] = out.radiance.value.z; }
+        status[i] = st;
+    }
+}
+
+// Transmittance factor applied to unoccluded shadow rays (shadow.cpp:39-74); tr_rgb = 1 in scenes without media.
+void orc_shadow_tr(orc_scene *s, int n, const float *o_med, const float *d_t1, float *tr_rgb) {
+#pragma omp parallel for
+    for (int i = 0; i < n; ++i) {
+        ShadowRay r;
+        r.o = V3(o_med[4 * i], o_med[4 * i + 1], o_med[4 * i + 2]); r.medium_id = f2u(o_med[4 * i + 3]);
+        r.d = V3(d_t1[4 * i], d_t1[4 * i + 1], d_t1[4 * i + 2]); r.t1 = d_t1[4 * i + 3];
+        V3 tr = shadow_tr(*s, r);
+        tr_rgb[3 * i] = tr.x; tr_rgb[3 * i + 1] = tr.y; tr_rgb[3 * i + 2] = tr.z;
+    }
+}
+
+int orc_has_medium(orc_scene *s) { return s->has_medium ? 1 : 0; }
+
+// BSDF known-answer access: evaluates one material at a synthetic hit (geometry frame = identity axes, shading normal
+// `interp_z`, texture coordinate uv) for n (wo, wi, sam) triples.  out_* per triple: sample {bsdf rgb, dir xyz, pdf, is_delta},
+// eval rgb, pdf.
+void orc_bsdf_probe(orc_scene *s, int material, const float *interp_z, const float *uv, int n, const float *wo, const float *wi,
+                    const float *sam, float *out_sample8, float *out_eval3, float *out_pdf, float *out_albedo3, float *out_normal3) {
+    SurfacePoint sp;
+    sp.position = V3(0);
+    sp.frame = Frame(V3(1, 0, 0), V3(0, 1, 0), V3(0, 0, 1));
+    sp.interp_z = normalize(V3(interp_z[0], interp_z[1], interp_z[2]));
+    sp.uv = V2{0, 0}; sp.tex_coord = V2{uv[0], uv[1]};
+    Shader sh = create_shader(*s, s->materials[material], sp);
+    V3 al = sh.albedo(), nr = sh.normal();
+    out_albedo3[0] = al.x; out_albedo3[1] = al.y; out_albedo3[2] = al.z;
+    out_normal3[0] = nr.x; out_normal3[1] = nr.y; out_normal3[2] = nr.z;
+    for (int i = 0; i < n; ++i) {
+        V3 o(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]), w(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), sm(sam[3 * i], sam[3 * i + 1], sam[3 * i + 2]);
+        BsdfSample bs = sh.sample(o, sm);
+        float *p = out_sample8 + 8 * i;
+        p[0] = bs.bsdf.x; p[1] = bs.bsdf.y; p[2] = bs.bsdf.z; p[3] = bs.dir.x; p[4] = bs.dir.y; p[5] = bs.dir.z; p[6] = bs.pdf; p[7] = bs.is_delta ? 1.0f : 0.0f;
+        V3 e = sh.eval(w, o);
+        out_eval3[3 * i] = e.x; out_eval3[3 * i + 1] = e.y; out_eval3[3 * i + 2] = e.z;
+        out_pdf[i] = sh.pdf(w, o);
     }
 }
 
@@ -1099,21 +1490,36 @@ void orc_render(orc_scene *s, int spp_begin, int spp_end, float *out_color, floa
                 generate_path(*s, accu, ps);
                 wgt[pix] += 1.0f; st.n_gen++;
                 const size_t p = (size_t)ps.py * W + ps.px;
+                auto do_shadow = [&](const ShadowRay &sr) {  // shadow.cpp:24-74
+                    st.n_shadow++;
+                    bool occluded = traverse<true>(*s, sr.o, sr.d, sr.t1).hit;
+                    if (!occluded) { st.n_shadow_miss++; st.n_splat++; film_add(&rad[4 * p], sr.beta_li * shadow_tr(*s, sr)); }
+                };
                 for (;;) {
                     Hit h = traverse<false>(*s, ps.o, ps.d, ps.t1);
                     st.n_closest++; if (h.hit) st.n_hit++;
-                    ShadeOut out;
-                    shade(*s, ps, h, out);
-                    if (out.shadow.valid) {
-                        st.n_shadow++;
-                        bool occluded = traverse<true>(*s, out.shadow.o, out.shadow.d, out.shadow.t1).hit;
-                        if (!occluded) { st.n_shadow_miss++; st.n_splat++; film_add(&rad[4 * p], out.shadow.beta_li); }  // shadow.cpp:39-74 (tr = 1 without media)
+                    bool scattered = false;
+                    MediumOut mo;
+                    if (s->has_medium) {  // wavefront.cpp:254-268
+                        medium_stage(*s, ps, h, mo);
+                        scattered = mo.scattered;
+                        if (mo.shadow.valid) do_shadow(mo.shadow);
+                        if (mo.radiance.valid) { st.n_splat++; film_add(&rad[4 * p], mo.radiance.value); }
                     }
+                    ShadeOut out;
+                    shade(*s, ps, h, scattered, out);
+                    if (out.shadow.valid) do_shadow(out.shadow);
                     if (out.has_gbuffer) {
                         if (s->want_albedo) film_add(&alb[4 * p], out.albedo);
                         if (s->want_normal) film_add(&nor[4 * p], out.normal);
                     }
                     if (out.radiance.valid) { st.n_splat++; film_add(&rad[4 * p], out.radiance.value); }
+                    if (scattered) {
+                        if (!mo.has_next) break;
+                        st.n_next++;
+                        ps = mo.next;
+                        continue;
+                    }
                     if (!out.has_next) break;
                     st.n_next++;
                     ps = out.next;

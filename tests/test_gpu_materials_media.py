@@ -1,0 +1,237 @@
+"""GPU parity for the material (BASELINE config 2) and medium (config 3) paths: CUDA stages through the C ABI against the
+oracle on identical batches, then whole renders.
+
+Integer work (RNG states, pixels, depth, medium ids) is bit-exact.  Floating-point shading values carry the tolerances
+written at each check: the kernels use the reference's own fast-math contract (approximate div / sqrt / sin / cos, FMA:
+SURVEY B.7) and the GPU's texture unit (8-bit filter weights), the oracle IEEE arithmetic and the published filtering rule.
+A discrete decision that hinges on such a value (lobe selection, the Disney firefly clamp, black-fringe tests) may flip for
+a few states per thousand; those are counted and bounded, not ignored silently.
+"""
+import numpy as np
+import pytest
+
+from tests import util
+from tests.util import f32
+
+pytestmark = pytest.mark.gpu
+
+W2, H2 = 96, 54
+
+
+@pytest.fixture(scope="module")
+def pair_materials(tmp_path_factory, built):
+    from btrc_b200 import api, scenes
+    from oracle import front
+
+    d = tmp_path_factory.mktemp("c2_small")
+    path = scenes.make_material_test(str(d), width=W2, height=H2, spp=8, rings=12, segments=16, tex_res=64, state_count=60000)
+    s = api.Scene(path)
+    o = front.OracleScene(path)
+    yield s, o, path
+    s.close()
+
+
+@pytest.fixture(scope="module")
+def pair_medium(tmp_path_factory, built):
+    from btrc_b200 import api, scenes
+    from oracle import front
+
+    d = tmp_path_factory.mktemp("c3_small")
+    path = scenes.make_medium_scene(str(d), width=64, height=64, spp=8, grid_res=24, state_count=50000)
+    s = api.Scene(path)
+    o = front.OracleScene(path)
+    yield s, o, path
+    s.close()
+
+
+def _bounce_states(o, n, bounces, with_medium=False):
+    """Advance n camera paths with the oracle; yields (state, flag, detail, medium_out | None, state_after_medium, flag_after_medium, shade_out)."""
+    st = o.generate(0, n)
+    out = []
+    for _ in range(bounces):
+        flag, detail = o.closest_hit(st["o_med"], st["d_t1"])
+        if with_medium:
+            st2, flag2, mo = o.medium(st, flag, detail)
+        else:
+            st2, flag2, mo = st, flag, None
+        sh = o.shade(st2, flag2, detail)
+        out.append((st, flag, detail, mo, st2, flag2, sh))
+        parts = [{k: v[(sh["status"] & 1) != 0] for k, v in sh["next"].items()}]
+        if mo is not None:
+            parts.append({k: v[(mo["status"] & 1) != 0] for k, v in mo["next"].items()})
+        st = {k: np.ascontiguousarray(np.concatenate([p[k] for p in parts])) for k in parts[0]}
+        if st["o_med"].shape[0] == 0:
+            break
+    return out
+
+
+def _frac_close(a, b, rtol, atol):
+    ok = np.isclose(a, b, rtol=rtol, atol=atol)
+    while ok.ndim > 1:
+        ok = ok.all(axis=-1)
+    return float(ok.mean()) if ok.size else 1.0
+
+
+def _compare_next(nxt, ref, rtol, max_flip, max_outlier):
+    """Continuation states matched by their RNG state (bit-exact key: every branch of the stage draws the same count)."""
+    ka = {int(k): i for i, k in enumerate(nxt["rng"][:, 0])}
+    kb = {int(k): i for i, k in enumerate(ref["rng"][:, 0])}
+    common = [k for k in ka if k in kb]
+    flips = (len(ka) - len(common)) + (len(kb) - len(common))
+    assert flips <= max_flip * max(len(kb), 200), (flips, len(ka), len(kb))
+    ia = np.array([ka[k] for k in common], np.int64)
+    ib = np.array([kb[k] for k in common], np.int64)
+    if len(common) == 0:
+        return
+    for k in ("rng", "pixel"):
+        assert np.array_equal(nxt[k][ia], ref[k][ib]), k
+    assert np.array_equal(nxt["beta_depth"][ia, 3].view(np.uint32), ref["beta_depth"][ib, 3].view(np.uint32))  # depth
+    same_med = nxt["o_med"][ia, 3].view(np.uint32) == ref["o_med"][ib, 3].view(np.uint32)                      # medium id
+    assert same_med.mean() >= 1 - max_outlier
+    assert _frac_close(nxt["o_med"][ia, :3], ref["o_med"][ib, :3], 0, 1e-4) >= 1 - max_outlier
+    assert _frac_close(nxt["d_t1"][ia, :3], ref["d_t1"][ib, :3], 0, 2e-3) >= 1 - max_outlier
+    assert _frac_close(nxt["beta_depth"][ia, :3], ref["beta_depth"][ib, :3], rtol, 1e-5) >= 1 - max_outlier
+    assert _frac_close(nxt["path_rad"][ia, :3], ref["path_rad"][ib, :3], rtol, 1e-5) >= 1 - max_outlier
+    # beta_le = beta * cos * f and the stored pdf are individually ill-conditioned for glossy lobes (the GGX D term moves by
+    # percents under a 1e-7 change of the half vector when alpha ~ 1e-3) while their ratio (beta, checked above) is not
+    assert _frac_close(nxt["ble"][ia], ref["ble"][ib], 10 * rtol, 1e-5) >= 1 - 3 * max_outlier
+    assert np.array_equal(nxt["ble"][ia, 3] < 0, ref["ble"][ib, 3] < 0)  # delta marker
+
+
+def _film_want(shape, pixel, value):
+    want = np.zeros(shape + (3,), np.float64)
+    np.add.at(want, (pixel[:, 1], pixel[:, 0]), value.astype(np.float64))
+    return want
+
+
+def test_texture_and_scene_tables_loaded(pair_materials):
+    s, o, _ = pair_materials
+    i = s.info
+    assert i.n_lights == 3 and i.has_medium == 0  # two mesh lights + gradient sky
+    assert i.n_triangles == o.num_triangles()
+
+
+def test_closest_hit_material_scene(pair_materials):
+    """Two-level scene (rotated / translated sphere instances): identical rays -> bit-identical hits."""
+    s, o, _ = pair_materials
+    for st, flag, detail, *_ in _bounce_states(o, W2 * H2 * 2, 3):
+        f1, d1 = s.closest_hit(st["o_med"], st["d_t1"])
+        assert np.array_equal(f1, flag)
+        hit = ((flag >> 30) & 1).astype(bool)
+        assert np.array_equal(d1[hit], detail[hit])
+
+
+def test_shade_parity_all_materials(pair_materials):
+    """disney / metal / glass / mirror / diffuse with image textures, normal map, mesh lights and the gradient sky."""
+    s, o, _ = pair_materials
+    total = 0
+    for depth, (st, flag, detail, _, _, _, sh) in enumerate(_bounce_states(o, W2 * H2 * 4, 5)):
+        s.film_clear()
+        nxt, shd = s.shade(st, flag, detail)
+        keep = (sh["status"] & 1) != 0
+        ref = {k: v[keep] for k, v in sh["next"].items()}
+        # Measured on B200 (scripts/diag_shade.py): untextured materials agree to ~3e-7 (median) with the oracle; textured ones
+        # to 1.3e-3 median / 6e-3 at the 99th percentile, which is the texture unit's 8-bit filter weights on a 64x64 noise
+        # texture; very glossy lobes (alpha = 0.0025, pdf ~ 1e5) are ill-conditioned in fp32 and land among the outliers.
+        _compare_next(nxt, ref, rtol=1e-2, max_flip=0.01, max_outlier=0.015)
+        has_sh = (sh["status"] & 2) != 0
+        util.compare_shadow_rays(shd, st, has_sh, sh["sh_o_med"], sh["sh_d_t1"], sh["sh_beta_li"], rtol=1e-2, atol_dir=2e-3,
+                                 max_flip=0.01, max_outlier=0.015)
+        rad = np.zeros((H2, W2, 4), f32)
+        wgt = np.zeros((H2, W2), f32)
+        s.film_export(rad, wgt)
+        term = (sh["status"] & 4) != 0
+        want = _film_want((H2, W2), st["pixel"][term], sh["splat"][term])
+        # terminated-path splats: per pixel within 2 % (or 1e-3 absolute), at most 1 % of the pixels outside
+        ok = np.isclose(rad[..., :3], want, rtol=2e-2, atol=1e-3).all(axis=-1)
+        assert ok.mean() > 0.99, (depth, ok.mean())
+        total += st["o_med"].shape[0]
+    assert total > 30000
+
+
+def test_render_matches_oracle_materials(pair_materials):
+    s, o, _ = pair_materials
+    color, _, _, stats = s.render()
+    ref = o.render()
+    for k in ("n_gen",):
+        assert stats[k] == ref["stats"][k]
+    for k in ("n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss"):
+        assert abs(stats[k] - ref["stats"][k]) <= 5e-3 * ref["stats"][k], (k, stats[k], ref["stats"][k])
+    a, b = color[..., :3], ref["color"][..., :3]
+    assert np.isfinite(a).all()
+    # same sampler seed and spp: the two images differ only where a path took a different discrete branch
+    assert util.rel_mse(a, b) < 2e-2
+    assert abs(a.mean() - b.mean()) / b.mean() < 1e-2
+
+
+def test_medium_stage_parity(pair_medium):
+    s, o, _ = pair_medium
+    assert s.info.has_medium == 1 and o.has_medium()
+    n_scatter = 0
+    for depth, (st, flag, detail, mo, st2, flag2, sh) in enumerate(_bounce_states(o, 64 * 64 * 4, 5, with_medium=True)):
+        s.film_clear()
+        g_st, g_flag, nxt, shd = s.medium(st, flag, detail)
+        # resolved medium ids: integer, exact
+        assert np.array_equal(g_st["o_med"][:, 3].view(np.uint32), st2["o_med"][:, 3].view(np.uint32))
+        # scattered flag: delta tracking compares u < density / majorant with a filtered density -> rare flips allowed
+        same = (g_flag == flag2)
+        assert same.mean() > 0.995, (depth, same.mean())
+        # unscattered paths keep their (advanced) sampler: identical draw counts wherever the walk agreed
+        unsc = same & ((flag2 >> 31) == 0)
+        agree = (g_st["rng"][unsc] == st2["rng"][unsc]).all(axis=1)
+        assert agree.mean() > 0.995
+        assert _frac_close(g_st["ble"][unsc], st2["ble"][unsc], 2e-3, 1e-6) > 0.99
+        keep = (mo["status"] & 1) != 0
+        ref = {k: v[keep] for k, v in mo["next"].items()}
+        _compare_next(nxt, ref, rtol=5e-3, max_flip=0.02, max_outlier=0.02)
+        has_sh = (mo["status"] & 2) != 0
+        util.compare_shadow_rays(shd, st, has_sh, mo["sh_o_med"], mo["sh_d_t1"], mo["sh_beta_li"], rtol=5e-3, atol_dir=2e-3,
+                                 max_flip=0.02, max_outlier=0.02)
+        n_scatter += int(keep.sum())
+    assert n_scatter > 1000
+
+
+def test_shadow_transmittance_parity(pair_medium):
+    """Unoccluded shadow rays through the heterogeneous medium: ratio tracking keyed on the ray (same stream on both sides)."""
+    s, o, _ = pair_medium
+    rows = _bounce_states(o, 64 * 64 * 4, 3, with_medium=True)
+    got_any = False
+    for st, flag, detail, mo, st2, flag2, sh in rows:
+        has_sh = (mo["status"] & 2) != 0
+        if has_sh.sum() < 100:
+            continue
+        shd = dict(pixel=np.ascontiguousarray(st["pixel"][has_sh]), beta_li=np.ascontiguousarray(mo["sh_beta_li"][has_sh]),
+                   o_med=np.ascontiguousarray(mo["sh_o_med"][has_sh]), d_t1=np.ascontiguousarray(mo["sh_d_t1"][has_sh]))
+        s.film_clear()
+        s.shadow(shd)
+        rad = np.zeros((64, 64, 4), f32)
+        wgt = np.zeros((64, 64), f32)
+        s.film_export(rad, wgt)
+        occ = o.any_hit(shd["o_med"], shd["d_t1"]).astype(bool)
+        tr = o.shadow_tr(shd["o_med"], shd["d_t1"])
+        want = _film_want((64, 64), shd["pixel"][~occ], shd["beta_li"][~occ, :3] * tr[~occ])
+        ok = np.isclose(rad[..., :3], want, rtol=2e-2, atol=1e-4).all(axis=-1)
+        assert ok.mean() > 0.98, ok.mean()
+        got_any = True
+    assert got_any
+
+
+@pytest.mark.parametrize("heterogeneous", [True, False])
+def test_render_matches_oracle_medium(tmp_path, built, heterogeneous):
+    from btrc_b200 import api, scenes
+    from oracle import front
+
+    path = scenes.make_medium_scene(str(tmp_path), width=64, height=64, spp=16, grid_res=24, state_count=40000, heterogeneous=heterogeneous)
+    s = api.Scene(path)
+    o = front.OracleScene(path)
+    color, _, _, stats = s.render()
+    ref = o.render()
+    assert stats["n_gen"] == ref["stats"]["n_gen"]
+    for k in ("n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss"):
+        assert abs(stats[k] - ref["stats"][k]) <= 1e-2 * ref["stats"][k], (k, stats[k], ref["stats"][k])
+    a, b = color[..., :3], ref["color"][..., :3]
+    assert np.isfinite(a).all()
+    # tracking decisions diverge for a few paths per thousand, so this is a statistical match at equal spp and seed
+    assert abs(a.mean() - b.mean()) / b.mean() < 2e-2
+    assert util.rel_mse(a, b) < 0.15
+    s.close()

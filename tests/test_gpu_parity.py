@@ -138,36 +138,6 @@ def _match(a, b, key_a, key_b):
     return ia, ib
 
 
-def _shadow_keys(pixel, o_med):
-    """(pixel, quantised origin) -- one shadow ray per path at most; paths of one pixel differ in their origin."""
-    q = np.round(o_med[:, :3].astype(np.float64) * 2000).astype(np.int64)
-    return [(int(px), int(py), int(a), int(b), int(c)) for (px, py), (a, b, c) in zip(pixel, q)]
-
-
-def _compare_shadow_rays(shd, ref_pixel, ref_o, ref_d, ref_beta, depth):
-    """Shadow rays come back compacted in any order: match them by key.  A shadow ray exists iff the BSDF value towards the
-    light sample is non-zero (shade.cpp:151), which for a light sample in the surface's own plane (a path sitting on the
-    emitter) is decided by the sign of a rounding residue -- such rays carry |cos| ~ 1e-7 and may exist on one side only."""
-    ka = _shadow_keys(shd["pixel"], shd["o_med"])
-    kb = _shadow_keys(ref_pixel, ref_o)
-    da = {k: i for i, k in enumerate(ka)}
-    db = {k: i for i, k in enumerate(kb)}
-    common = [k for k in da if k in db]
-    only_a = [da[k] for k in da if k not in db]
-    only_b = [db[k] for k in db if k not in da]
-    scale = max(float(np.abs(ref_beta[:, :3]).max()), 1e-6)
-    assert len(only_a) + len(only_b) <= 0.01 * max(len(kb), 100), (depth, len(only_a), len(only_b), len(kb))
-    for idx, beta, o, d in ((only_a, shd["beta_li"], shd["o_med"], shd["d_t1"]), (only_b, ref_beta, ref_o, ref_d)):
-        for i in idx:
-            assert np.abs(beta[i, :3]).max() <= 1e-4 * scale, ("unmatched shadow ray carries energy", depth, beta[i], o[i], d[i])
-    ia = np.array([da[k] for k in common], np.int64)
-    ib = np.array([db[k] for k in common], np.int64)
-    assert np.allclose(shd["o_med"][ia, :3], ref_o[ib, :3], atol=5e-5)
-    assert np.array_equal(shd["o_med"][ia, 3].view(np.uint32), ref_o[ib, 3].view(np.uint32))
-    assert np.allclose(shd["d_t1"][ia], ref_d[ib], atol=5e-5)
-    assert np.allclose(shd["beta_li"][ia, :3], ref_beta[ib, :3], rtol=5e-4, atol=1e-6 * scale)
-
-
 def test_shade_parity(pair_small):
     """Same states + same hits -> same continuation states, shadow rays and film splats (matched by RNG state)."""
     s, o = pair_small
@@ -188,10 +158,14 @@ def test_shade_parity(pair_small):
         assert np.allclose(nxt["d_t1"][ia, :3], ref["d_t1"][ib, :3], atol=2e-5)
         assert np.allclose(nxt["beta_depth"][ia, :3], ref["beta_depth"][ib, :3], rtol=2e-4, atol=1e-6)
         assert np.allclose(nxt["path_rad"][ia, :3], ref["path_rad"][ib, :3], rtol=2e-4, atol=1e-6)
-        assert np.allclose(nxt["ble"][ia], ref["ble"][ib], rtol=2e-4, atol=1e-6)
+        # beta_le and the pdf carry cos(theta) = sqrt(1 - sx^2 - sy^2) of the sampled direction, whose relative error grows like
+        # 1e-7 / cos^2 towards grazing directions (it cancels in beta = beta_le / pdf above): 2e-4 for 99.5 %, 2 % for all
+        close = np.isclose(nxt["ble"][ia], ref["ble"][ib], rtol=2e-4, atol=1e-6).all(axis=1)
+        assert close.mean() > 0.995, close.mean()
+        assert np.allclose(nxt["ble"][ia], ref["ble"][ib], rtol=2e-2, atol=1e-5)
         # shadow rays: match by (pixel, origin bits) -- one per path at most, paths of one pixel differ in origin
         has_sh = (sh["status"] & 2) != 0
-        _compare_shadow_rays(shd, st["pixel"][has_sh], sh["sh_o_med"][has_sh], sh["sh_d_t1"][has_sh], sh["sh_beta_li"][has_sh], depth)
+        util.compare_shadow_rays(shd, st, has_sh, sh["sh_o_med"], sh["sh_d_t1"], sh["sh_beta_li"], rtol=5e-4)
         # film: radiance splats of terminated paths
         W = H = 96
         rad = np.zeros((H, W, 4), f32)

@@ -110,3 +110,60 @@ def rel_mse(a, b, eps=1e-2):
 def sort_by_key(arrs, key):
     order = np.lexsort(tuple(key[:, k] for k in range(key.shape[1] - 1, -1, -1))) if key.ndim == 2 else np.argsort(key, kind="stable")
     return {k: v[order] for k, v in arrs.items()}
+
+
+def shadow_ray_owners(shadow_pixel, shadow_o, st):
+    """Shadow rays come back compacted in any order.  Each belongs to exactly one input state: the one of its pixel whose ray
+    (o + s * d) passes closest to the shadow origin (a surface NEE ray starts at the offset hit point, a medium NEE ray at
+    the scatter position on the ray).  Returns the owning state index per shadow ray."""
+    from collections import defaultdict
+
+    bypix = defaultdict(list)
+    for i, (px, py) in enumerate(st["pixel"]):
+        bypix[(int(px), int(py))].append(i)
+    o = st["o_med"][:, :3].astype(np.float64)
+    d = st["d_t1"][:, :3].astype(np.float64)
+    d = d / np.linalg.norm(d, axis=1, keepdims=True)
+    owner = np.full(shadow_pixel.shape[0], -1, np.int64)
+    for j, (px, py) in enumerate(shadow_pixel):
+        c = np.array(bypix[(int(px), int(py))], np.int64)
+        w = shadow_o[j, :3].astype(np.float64)[None, :] - o[c]
+        dist = np.linalg.norm(w - (w * d[c]).sum(axis=1, keepdims=True) * d[c], axis=1)
+        owner[j] = c[int(np.argmin(dist))]
+    return owner
+
+
+def compare_shadow_rays(shd, st, has_sh, ref_o, ref_d, ref_beta, rtol, atol_dir=5e-5, max_flip=0.0, max_outlier=0.0, negligible=1e-4):
+    """Compares compacted shadow rays with the oracle's per-state shadow outputs (ref_* indexed by state, has_sh = mask).
+
+    A ray may exist on one side only when the BSDF value towards the light sample is zero on the other side; for a sample in
+    the surface's own plane (a path sitting on the emitter) that is the sign of a rounding residue and the ray carries
+    |cos| ~ 1e-7.  Such rays must be negligible (< `negligible` x the largest beta_li); `max_flip` bounds one-sided rays that
+    do carry energy (decision flips of textured / glossy materials), `max_outlier` the fraction outside the tolerances."""
+    n = st["pixel"].shape[0]
+    owner = shadow_ray_owners(shd["pixel"], shd["o_med"], st)
+    cnt = np.bincount(owner, minlength=n)
+    assert (cnt <= 1).all(), "two shadow rays matched one state"
+    scale = max(float(np.abs(ref_beta[has_sh, :3]).max()), 1e-6) if has_sh.any() else 1.0
+    got = cnt > 0
+    ray_of = np.full(n, -1, np.int64)
+    ray_of[owner] = np.arange(owner.shape[0])
+    only_gpu = np.where(got & ~has_sh)[0]
+    only_ref = np.where(~got & has_sh)[0]
+    energetic = int((np.abs(shd["beta_li"][ray_of[only_gpu], :3]).max(axis=1) > negligible * scale).sum()) if only_gpu.size else 0
+    energetic += int((np.abs(ref_beta[only_ref, :3]).max(axis=1) > negligible * scale).sum()) if only_ref.size else 0
+    assert only_gpu.size + only_ref.size <= max(0.01, max_flip) * max(int(has_sh.sum()), 100), (only_gpu.size, only_ref.size)
+    assert energetic <= max_flip * max(int(has_sh.sum()), 100), ("one-sided shadow rays carry energy", energetic)
+    both = np.where(got & has_sh)[0]
+    if both.size == 0:
+        return
+    j = ray_of[both]
+
+    def frac(a, b, r, t):
+        return float(np.isclose(a, b, rtol=r, atol=t).all(axis=-1).mean())
+
+    assert np.array_equal(shd["pixel"][j], st["pixel"][both])
+    assert (shd["o_med"][j, 3].view(np.uint32) == ref_o[both, 3].view(np.uint32)).mean() >= 1 - max_outlier  # medium id
+    assert frac(shd["o_med"][j, :3], ref_o[both, :3], 0, atol_dir) >= 1 - max_outlier
+    assert frac(shd["d_t1"][j], ref_d[both], 0, atol_dir) >= 1 - max_outlier
+    assert frac(shd["beta_li"][j, :3], ref_beta[both, :3], rtol, 1e-6 * scale) >= 1 - max_outlier
