@@ -28,16 +28,25 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # BASELINE.json configs[0]: Cornell box, diffuse + one area light, 512x512, 16 spp
     "c1_cornell_512_16spp": dict(kind="cornell", width=512, height=512, spp=16),
+    # BASELINE.json configs[1] (the configuration the metric is quoted on): Disney material test with image textures, 1920x1080, 256 spp
+    "c2_disney_1080p_256spp": dict(kind="materials", width=1920, height=1080, spp=256),
+    # BASELINE.json configs[2]: heterogeneous grid-volume medium with NEE, 1920x1080 (spp not stated => reference default 128)
+    "c3_medium_1080p_128spp": dict(kind="medium", width=1920, height=1080, spp=128),
 }
-DEFAULT_WORKLOAD = "c1_cornell_512_16spp"
+DEFAULT_WORKLOAD = "c2_disney_1080p_256spp"
 
 
 def make_scene(workload, out_dir, spp=None):
     from btrc_b200 import scenes
 
     w = WORKLOADS[workload]
+    os.makedirs(out_dir, exist_ok=True)
     if w["kind"] == "cornell":
         return scenes.make_cornell(out_dir, width=w["width"], height=w["height"], spp=spp or w["spp"])
+    if w["kind"] == "materials":
+        return scenes.make_material_test(out_dir, width=w["width"], height=w["height"], spp=spp or w["spp"])
+    if w["kind"] == "medium":
+        return scenes.make_medium_scene(out_dir, width=w["width"], height=w["height"], spp=spp or w["spp"])
     raise ValueError(workload)
 
 
@@ -107,7 +116,10 @@ def bvh_alg_per_ray(scene_path, sample_paths=16384):
     o = front.OracleScene(scene_path)
     verts, _ = o.triangles()
     h = R.ref_bvh_build(verts.shape[0], _ptr(np.ascontiguousarray(verts), ctypes.c_float), 0)
-    st = o.generate(0, sample_paths)
+    # a sample of camera paths spread over the whole image (64 chunks of consecutive path indices), not its first rows
+    npix = o.width * o.height
+    chunks = [o.generate((k * npix) // 64 + (k * 37) % max(o.width - sample_paths // 64, 1), sample_paths // 64) for k in range(64)]
+    st = {k: np.ascontiguousarray(np.concatenate([c[k] for c in chunks])) for k in chunks[0]}
     stats = np.zeros(2, np.uint64)
     n_rays = 0
     for _ in range(64):
@@ -120,14 +132,18 @@ def bvh_alg_per_ray(scene_path, sample_paths=16384):
                           _ptr(tuv, ctypes.c_float), _ptr(stats, ctypes.c_uint64))
         n_rays += n
         flag, detail = o.closest_hit(st["o_med"], st["d_t1"])
+        parts = []
+        if o.has_medium():
+            st, flag, mo = o.medium(st, flag, detail)
+            parts.append({k: v[(mo["status"] & 1) != 0] for k, v in mo["next"].items()})
         sh = o.shade(st, flag, detail)
-        keep = (sh["status"] & 1) != 0
-        st = {k: np.ascontiguousarray(v[keep]) for k, v in sh["next"].items()}
+        parts.append({k: v[(sh["status"] & 1) != 0] for k, v in sh["next"].items()})
+        st = {k: np.ascontiguousarray(np.concatenate([p[k] for p in parts])) for k in parts[0]}
     R.ref_bvh_free(h)
     return {"steps_per_ray": float(stats[0]) / n_rays, "tests_per_ray": float(stats[1]) / n_rays, "rays": n_rays}
 
 
-def stage_bytes(stats, bvh):
+def stage_bytes(stats, bvh, has_medium=False):
     """Algorithmic bytes of one render from the reference SoA layout."""
     bvh_per_ray = (bvh["steps_per_ray"] * 64 + bvh["tests_per_ray"] * 48) if bvh else 0.0
     n_closest, n_hit = stats["n_closest"], stats["n_hit"]
@@ -135,7 +151,10 @@ def stage_bytes(stats, bvh):
     shade = n_closest * 108 + n_hit * (16 + 96) + stats["n_next"] * 104 + stats["n_shadow"] * 56 + (stats["n_splat"] - stats["n_shadow_miss"]) * 12
     shadow = stats["n_shadow"] * (32 + bvh_per_ray) + stats["n_shadow_miss"] * (24 + 12)
     generate = stats["n_gen"] * 108
-    return {"generate": generate, "trace": trace, "shade": shade, "shadow": shadow}
+    # medium kernel (if run): 108 R + (16 + 16 on hit) + 32 + 16 + 4 W per state; its scatter outputs (104 / 56 W) are counted in shade's
+    # n_next / n_shadow terms above, which are whole-iteration totals of both kernels
+    medium = (n_closest * (108 + 52) + n_hit * 32) if has_medium else 0
+    return {"generate": generate, "trace": trace, "shade": shade, "shadow": shadow, "medium": medium}
 
 
 def measured_peak():
@@ -156,12 +175,15 @@ def run_reference(args):
 
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
     w = WORKLOADS[args.workload]
-    sample_spp = 2
     with tempfile.TemporaryDirectory() as d:
         path = make_scene(args.workload, d)
         o = front.OracleScene(path)
+        t0 = time.perf_counter()
         for _ in range(max(args.warmup, 1)):
             o.render(0, 1)
+        t1 = (time.perf_counter() - t0) / max(args.warmup, 1)
+        # each step = a bounded sample of the workload: as many spp as fit in ~60 s / steps of CPU time
+        sample_spp = int(max(1, min(w["spp"], 60.0 / max(args.steps, 1) / max(t1, 1e-3))))
         t0 = time.perf_counter()
         rays = 0
         for k in range(args.steps):
@@ -199,7 +221,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     w = WORKLOADS[args.workload]
-    W, H, spp = w["width"], w["height"], w["spp"]
+    W, H, spp = w["width"], w["height"], (args.spp or w["spp"])
     npix = W * H
     tmp = tempfile.TemporaryDirectory()
     path = make_scene(args.workload, tmp.name, spp=spp * world)  # weak scaling: every rank renders `spp` samples per pixel
@@ -305,18 +327,22 @@ def run_ours(args):
     mrays = (n_closest + n_shadow) / secs / 1e6
 
     # ---- roofline of the dominant kernel (rank 0's stage times; algorithmic bytes per SURVEY 8d)
-    bvh = bvh_alg_per_ray(path)
+    bvh = None if args.no_cpu_baseline else bvh_alg_per_ray(path)
     peak, peak_src = measured_peak()
-    sb = stage_bytes({k: agg[k] for k in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss", "n_splat")}, bvh)
+    sb = stage_bytes({k: agg[k] for k in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss", "n_splat")}, bvh,
+                     has_medium=bool(s.info.has_medium))
     iters = max(agg["n_iter"], 1)
     stages = {}
-    for name in ("generate", "trace", "shade", "shadow"):
+    sb["bookkeeping"] = 0
+    for name in ("generate", "trace", "medium", "shade", "shadow", "bookkeeping"):
         ms = agg["stage_ms"][name]
+        if name == "medium" and not s.info.has_medium:
+            continue
         gbs = sb[name] / (ms / 1e3) / 1e9 if ms > 0 else 0.0
         stages[name] = {"ms_total": ms, "launches": iters, "ms_per_launch": ms / iters, "alg_bytes_per_launch": sb[name] / iters,
                         "achieved_gbs": gbs, "frac": gbs / peak, "share_of_step": ms / dev_ms}
-    dom = max(stages, key=lambda k: stages[k]["ms_total"])
-    roofline = {"kernel": {"generate": "generate_kernel", "trace": "trace_kernel", "shade": "shade_kernel", "shadow": "shadow_kernel"}[dom],
+    dom = max((k for k in stages if k != "bookkeeping"), key=lambda k: stages[k]["ms_total"])
+    roofline = {"kernel": dom + "_kernel",
                 "bound": "hbm", "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"],
                 "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": stages[dom]["alg_bytes_per_launch"],
                 "ms_per_launch": stages[dom]["ms_per_launch"], "bvh_alg": bvh}
@@ -324,13 +350,18 @@ def run_ours(args):
     # ---- CPU baseline: the oracle (port) on the host cores of this box, bounded sample of the same workload
     from oracle import front
 
-    o = front.OracleScene(make_scene(args.workload, tmp.name))
-    cpu_spp = min(spp, 8)
-    t0 = time.perf_counter()
-    o.render(0, cpu_spp)
-    cpu_s = time.perf_counter() - t0
-    cpu = {"value": npix * cpu_spp / cpu_s / 1e6, "unit": "Msamples/s", "cores": front.lib().orc_num_threads(), "kind": "port",
-           "sample": f"{cpu_spp} of {spp} spp of the workload ({W}x{H}), oracle/liborc.so on all host cores, {cpu_s:.1f} s"}
+    cpu = None
+    if not args.no_cpu_baseline:
+        o = front.OracleScene(make_scene(args.workload, os.path.join(tmp.name, "cpu")))
+        t0 = time.perf_counter()
+        o.render(0, 1)  # calibration pass: 1 spp
+        t1 = time.perf_counter() - t0
+        cpu_spp = int(max(1, min(spp, 15.0 / max(t1, 1e-3))))  # ~15 s of CPU work
+        t0 = time.perf_counter()
+        o.render(0, cpu_spp)
+        cpu_s = time.perf_counter() - t0
+        cpu = {"value": npix * cpu_spp / cpu_s / 1e6, "unit": "Msamples/s", "cores": front.lib().orc_num_threads(), "kind": "port",
+               "sample": f"{cpu_spp} of {spp} spp of the workload ({W}x{H}), oracle/liborc.so on all host cores, {cpu_s:.1f} s"}
 
     e2e_value = n_gen / e2e_s / 1e6
     line = {
@@ -364,6 +395,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--state-count", type=int, default=2097152)
+    ap.add_argument("--spp", type=int, default=0, help="override the workload's samples per pixel (profiling runs); reported in config")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (roofline bvh statistics, cpu_baseline): profiler runs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

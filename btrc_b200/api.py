@@ -31,11 +31,11 @@ class SceneInfo(ctypes.Structure):
 
 class RenderStats(ctypes.Structure):
     _fields_ = [(n, c_uint64) for n in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss", "n_splat", "n_iter")] + \
-               [("render_ms", c_double), ("stage_ms", c_double * 5), ("n_launches", c_uint64)]
+               [("render_ms", c_double), ("stage_ms", c_double * 6), ("n_launches", c_uint64)]
 
     def as_dict(self):
         d = {n: getattr(self, n) for n, _ in self._fields_}
-        d["stage_ms"] = dict(zip(("generate", "trace", "shade", "shadow", "medium"), [float(x) for x in self.stage_ms]))
+        d["stage_ms"] = dict(zip(("generate", "trace", "shade", "shadow", "medium", "bookkeeping"), [float(x) for x in self.stage_ms]))
         return d
 
 

@@ -48,7 +48,7 @@ void fill_stats(const RenderStats &s, btrc_render_stats_t *out) {
     out->n_gen = s.n_gen; out->n_closest = s.n_closest; out->n_hit = s.n_hit; out->n_next = s.n_next;
     out->n_shadow = s.n_shadow; out->n_shadow_miss = s.n_shadow_miss; out->n_splat = s.n_splat; out->n_iter = s.n_iter;
     out->render_ms = s.render_ms;
-    for (int k = 0; k < 5; ++k) out->stage_ms[k] = s.stage_ms[k];
+    for (int k = 0; k < 6; ++k) out->stage_ms[k] = s.stage_ms[k];
     out->n_launches = s.n_launches;
 }
 

@@ -166,6 +166,7 @@ struct SceneDevice {
     const Texture3DDesc *textures3d;
     const MediumDesc *media;
     const LightInfo *lights;        // area lights
+    const uint8_t *instance_class;  // shade class of each instance (1 + material type)
     int n_instances;
     int n_lights;                   // area lights + (environment light ? 1 : 0)   (core/light_sampler.cpp:24-33)
     int has_medium;                 // Scene::has_medium (core/scene.cpp:346-356)
@@ -186,9 +187,15 @@ struct PathQueue {
     float4 *ble;     // beta_le.rgb | bsdf pdf (negative: delta)
 };
 
+// Shade classes: 0 = miss, 1 + MaterialType = hit on an instance of that material type.  The closest-hit kernel
+// appends every state index to its class list; shade runs one kernel instantiation per class (material-sorted queues).
+constexpr int kNumShadeClasses = 1 + MAT_COUNT;
+
 struct HitQueue {
     uint32_t *flag;  // instance id | kFlagHasIntersection | kFlagHasScattering
     uint4 *detail;   // t bits, primitive id, u bits, v bits
+    uint32_t *class_list;  // kNumShadeClasses lists of `class_stride` state indices each
+    int class_stride;
 };
 
 struct ShadowQueue {
@@ -214,6 +221,7 @@ struct WaveCtl {
     int n_shadow_cur;   // shadow rays to trace this iteration
     int trace_cursor;   // dynamic work cursors for the persistent traversal kernels
     int shadow_cursor;
+    int class_count[8]; // entries of each shade class list this iteration (kNumShadeClasses <= 8)
     long long gen_base;   // first camera-path index generated this iteration
     long long cursor;     // next camera-path index
     long long end;        // one past the last camera-path index of this render

@@ -1,7 +1,7 @@
-// Material evaluation on the device: one `Shader` value per hit, specialised by MaterialDesc::type at run time with
-// plain branches (a warp usually sees one or two material types; the material-sorted queues keep it that way).
-// This replaces the reference's per-object run-time code generation (core/context.h:321-382) with ordinary device
-// functions whose parameters are data.
+// Material evaluation on the device: one `Shader<MAT>` value per hit.  The material type is a template parameter: the
+// closest-hit kernel bins path states by material type and each bin is shaded by its own kernel instantiation
+// (kernels.cu), so a warp runs one material's code.  This replaces the reference's per-object run-time code
+// generation (core/context.h:321-382) with ordinary device functions whose parameters are data.
 //
 // Reference semantics followed (src/builtin/btrc/builtin/material/...):
 //   utils/aggregate.cpp:32-230        BSDFAggregate (black-fringe flip, shading-energy correction, shadow terminator)
@@ -161,16 +161,15 @@ __device__ __forceinline__ void metal_eval_pdf(const MetalParams &m, f3 lwi, f3 
     eval_out = F * g.D * (g.Gi * g.Go) / fabsf(4.0f * lwi.z * lwo.z);
     pdf_out = g.Go * g.D / (4.0f * lwo.z);
 }
-__device__ __forceinline__ CompSample metal_sample(const MetalParams &m, f3 lwo, float s1, float s2) {
-    CompSample r = comp_none();
+__device__ __forceinline__ f3 metal_sample_dir(const MetalParams &m, f3 lwo, float s1, float s2) {  // microfacet_reflection.h:33-56
     if (lwo.z > 0.0f) {
         const f3 lwh = normalize(sample_anisotropic_gtr2_vnor(lwo, m.ax, m.ay, s1, s2));
         if (lwh.z > 0.0f) {
             const f3 lwi = normalize(2.0f * dot(lwo, lwh) * lwh - lwo);
-            if (lwi.z > 0.0f) { r.dir = lwi; metal_eval_pdf(m, lwi, lwo, r.bsdf, r.pdf); }
+            if (lwi.z > 0.0f) return lwi;
         }
     }
-    return r;
+    return f3(0.0f);
 }
 
 // ---- Disney --------------------------------------------------------------------------------------------------------
@@ -334,33 +333,22 @@ __device__ __forceinline__ void disney_eval_pdf(const DisneyParams &p, f3 lwi, f
     pdf = p.diffuse_weight * pdf_sample_hemisphere_zweighted(lwi) + p.specular_weight * pdf_specular + p.clearcoat_weight * pdf_clearcoat;
 }
 
-__device__ __forceinline__ CompSample disney_sample(const DisneyParams &p, f3 lwo, float s0, float s1, float s2) {  // disney.cpp:560-658
-    CompSample r = comp_none();
-    if (fabsf(lwo.z) < 1e-4f) return r;
-    f3 lwi;
+// Lobe selection and direction sampling of DisneyBSDF::sample (disney.cpp:560-658) without the evaluation: the caller
+// evaluates eval / pdf for the sampled and the light direction through ONE copy of disney_eval_pdf (code size, see shade_kernel).
+__device__ __forceinline__ f3 disney_sample_dir(const DisneyParams &p, f3 lwo, float s0, float s1, float s2) {
+    if (fabsf(lwo.z) < 1e-4f) return f3(0.0f);
     if (lwo.z < 0.0f) {
-        if (p.transmission == 0.0f) return r;
+        if (p.transmission == 0.0f) return f3(0.0f);
         const float macro_F = clampf(dielectric_fresnel(p.ior, 1.0f, lwo.z), 0.1f, 0.9f);
-        lwi = s0 >= macro_F ? disney_sample_transmission(p, lwo, s1, s2) : disney_sample_inner_refl(p, lwo, s1, s2);
-    } else {
-        float sel = s0;
-        if (sel < p.diffuse_weight) lwi = sample_hemisphere_zweighted(s1, s2);
-        else {
-            sel -= p.diffuse_weight;
-            if (sel < p.transmission_weight) lwi = disney_sample_transmission(p, lwo, s1, s2);
-            else {
-                sel -= p.transmission_weight;
-                if (sel < p.specular_weight) lwi = reflect_about(lwo, sample_anisotropic_gtr2_vnor(lwo, p.ax, p.ay, s1, s2));
-                else lwi = reflect_about(lwo, sample_gtr1(p.clearcoat_roughness, s1, s2));
-            }
-        }
+        return s0 >= macro_F ? disney_sample_transmission(p, lwo, s1, s2) : disney_sample_inner_refl(p, lwo, s1, s2);
     }
-    if (is_zero(lwi)) return r;
-    r.dir = lwi;
-    disney_eval_pdf(p, lwi, lwo, r.bsdf, r.pdf);
-    const f3 v = r.bsdf * fabsf(lwi.z) / r.pdf;  // handle_bad_sample
-    if (fmaxf(fmaxf(v.x, v.y), v.z) > 10.0f) return comp_none();
-    return r;
+    float sel = s0;
+    if (sel < p.diffuse_weight) return sample_hemisphere_zweighted(s1, s2);
+    sel -= p.diffuse_weight;
+    if (sel < p.transmission_weight) return disney_sample_transmission(p, lwo, s1, s2);
+    sel -= p.transmission_weight;
+    if (sel < p.specular_weight) return reflect_about(lwo, sample_anisotropic_gtr2_vnor(lwo, p.ax, p.ay, s1, s2));
+    return reflect_about(lwo, sample_gtr1(p.clearcoat_roughness, s1, s2));
 }
 
 // ---- shader ----------------------------------------------------------------------------------------------------------
@@ -382,8 +370,11 @@ struct BsdfSample {
 };
 __device__ __forceinline__ BsdfSample bsdf_none() { BsdfSample r; r.bsdf = f3(0.0f); r.dir = f3(0.0f); r.pdf = 0.0f; r.is_delta = false; return r; }
 
+// MAT is a compile-time constant: every shade kernel instantiation carries the code of one material type only
+// (this is the template specialisation that replaces CUJ's per-object code generation; core/context.h:321-382).
+template <int MAT>
 struct Shader {
-    int type;
+    static constexpr int type = MAT;
     bool shadow_terminator;
     ShaderFrame frame;
     f3 color;          // diffuse albedo / glass & mirror colour
@@ -427,18 +418,28 @@ struct Shader {
         }
     }
 
-    // Shader::eval + Shader::pdf (aggregate.cpp:185-209); zero for the delta / black shaders
-    __device__ __forceinline__ void eval_pdf(f3 wi, f3 wo, f3 &f, float &pdf) const {
-        f = f3(0.0f); pdf = 0.0f;
-        if (!is_aggregate()) return;
-        const Frame3 sh = flipped_shading(wo);
-        const f3 lwi = normalize(sh.global_to_local(wi));
-        const f3 lwo = normalize(sh.global_to_local(wo));
-        comp_eval_pdf(lwi, lwo, f, pdf);
-        f = f * correct_shading_energy(frame.geometry.z, sh.z, wi) * shadow_terminator_term(wi);
+    // ---- aggregate materials (diffuse / metal / disney), BSDFAggregate with one closure of weight 1 (aggregate.cpp:32-230).
+    // The kernel drives them in three steps so that the closure's eval+pdf code exists once:
+    //   lwi = sample_local_dir(lwo, sam)                       direction of BSDFComponent::sample
+    //   comp_eval_pdf(lwi | local light direction, lwo)        BSDFComponent::eval / pdf
+    //   wrap(global dir)                                       black fringes, shading-energy correction, shadow terminator
+    __device__ __forceinline__ f3 sample_local_dir(f3 lwo, float s0, float s1, float s2) const {
+        if (type == MAT_DIFFUSE) return lwo.z > 0.0f ? sample_hemisphere_zweighted(s0, s1) : f3(0.0f);  // component/diffuse.cpp:10-30
+        if (type == MAT_METAL) return metal_sample_dir(metal, lwo, s1, s2);
+        return disney_sample_dir(disney, lwo, s0, s1, s2);
+    }
+    // DisneyBSDF::sample's handle_bad_sample (disney.cpp:566-573)
+    __device__ __forceinline__ bool reject_sample(f3 f, f3 lwi, float pdf) const {
+        if (type != MAT_DISNEY) return false;
+        const f3 v = f * fabsf(lwi.z) / pdf;
+        return fmaxf(fmaxf(v.x, v.y), v.z) > 10.0f;
+    }
+    __device__ __forceinline__ float wrap_factor(f3 shading_z, f3 w) const {
+        return correct_shading_energy(frame.geometry.z, shading_z, w) * shadow_terminator_term(w);
     }
 
-    __device__ __forceinline__ BsdfSample sample(f3 wo, float s0, float s1, float s2) const {
+    // ---- delta / empty shaders: the whole Shader::sample (eval and pdf are zero)
+    __device__ __forceinline__ BsdfSample sample_delta(f3 wo, float s0) const {
         BsdfSample r = bsdf_none();
         if (type == MAT_BLACK) return r;
         if (type == MAT_INVISIBLE) {  // invisible.cpp:19-28
@@ -459,52 +460,29 @@ struct Shader {
             }
             return r;
         }
-        if (type == MAT_GLASS) {  // glass.cpp:41-98
-            const f3 nwo = normalize(sh.global_to_local(wo));
-            const float fr = dielectric_fresnel(ior, 1.0f, nwo.z);
-            if (s0 < fr) {
-                const f3 lwi(-nwo.x, -nwo.y, nwo.z);
-                const f3 wi = sh.local_to_global(lwi);
-                if (frame.is_black_fringes(wi)) return r;
-                r.bsdf = color * fr / fabsf(lwi.z) * correct_shading_energy(frame.geometry.z, sh.z, wi);
-                r.dir = wi; r.pdf = fr; r.is_delta = true;
-                return r;
-            }
-            const f3 nor(0.0f, 0.0f, nwo.z > 0.0f ? 1.0f : -1.0f);
-            const float eta = nwo.z > 0.0f ? 1.0f / ior : ior;
-            const float cos_theta_i = fabsf(nwo.z);
-            const float sin_theta_t_2 = eta * eta * fmaxf(0.0f, 1.0f - cos_theta_i * cos_theta_i);
-            if (sin_theta_t_2 >= 1.0f) return r;
-            const f3 nwi = normalize((eta * cos_theta_i - sqrtf(1.0f - sin_theta_t_2)) * nor - eta * nwo);
-            const f3 wi = sh.local_to_global(nwi);
+        // glass.cpp:41-98
+        const f3 nwo = normalize(sh.global_to_local(wo));
+        const float fr = dielectric_fresnel(ior, 1.0f, nwo.z);
+        if (s0 < fr) {
+            const f3 lwi(-nwo.x, -nwo.y, nwo.z);
+            const f3 wi = sh.local_to_global(lwi);
             if (frame.is_black_fringes(wi)) return r;
-            r.bsdf = (eta * eta) * color * (1.0f - fr) / fabsf(nwi.z) * correct_shading_energy(frame.geometry.z, sh.z, wi);
-            r.dir = wi;
-            r.pdf = 1.0f - dielectric_fresnel(ior, 1.0f, nwi.z);  // glass.cpp:91-92: the second assignment wins
-            r.is_delta = true;
+            r.bsdf = color * fr / fabsf(lwi.z) * correct_shading_energy(frame.geometry.z, sh.z, wi);
+            r.dir = wi; r.pdf = fr; r.is_delta = true;
             return r;
         }
-        // BSDFAggregate::sample with its single closure of weight 1 (aggregate.cpp:32-119)
-        const f3 lwo = normalize(sh.global_to_local(wo));
-        CompSample cs;
-        if (type == MAT_DIFFUSE) {  // component/diffuse.cpp:10-30
-            cs = comp_none();
-            if (lwo.z > 0.0f) {
-                cs.dir = sample_hemisphere_zweighted(s0, s1);
-                cs.bsdf = color / kPi;
-                cs.pdf = pdf_sample_hemisphere_zweighted(cs.dir);
-            }
-        } else if (type == MAT_METAL) {
-            cs = metal_sample(metal, lwo, s1, s2);
-        } else {
-            cs = disney_sample(disney, lwo, s0, s1, s2);
-        }
-        if (cs.pdf <= 0.0f) return r;
-        const f3 dir = sh.local_to_global(cs.dir);
-        if (frame.is_black_fringes(dir)) return r;
-        r.dir = dir;
-        r.bsdf = cs.bsdf * correct_shading_energy(frame.geometry.z, sh.z, dir) * shadow_terminator_term(dir);
-        r.pdf = cs.pdf;
+        const f3 nor(0.0f, 0.0f, nwo.z > 0.0f ? 1.0f : -1.0f);
+        const float eta = nwo.z > 0.0f ? 1.0f / ior : ior;
+        const float cos_theta_i = fabsf(nwo.z);
+        const float sin_theta_t_2 = eta * eta * fmaxf(0.0f, 1.0f - cos_theta_i * cos_theta_i);
+        if (sin_theta_t_2 >= 1.0f) return r;
+        const f3 nwi = normalize((eta * cos_theta_i - sqrtf(1.0f - sin_theta_t_2)) * nor - eta * nwo);
+        const f3 wi = sh.local_to_global(nwi);
+        if (frame.is_black_fringes(wi)) return r;
+        r.bsdf = (eta * eta) * color * (1.0f - fr) / fabsf(nwi.z) * correct_shading_energy(frame.geometry.z, sh.z, wi);
+        r.dir = wi;
+        r.pdf = 1.0f - dielectric_fresnel(ior, 1.0f, nwi.z);  // glass.cpp:91-92: the second assignment wins
+        r.is_delta = true;
         return r;
     }
 };

@@ -107,7 +107,7 @@ __device__ __forceinline__ f3 sample_hemisphere_zweighted(float u1, float u2) {
             theta = 0.5f * kPi - 0.25f * kPi * (u1 / u2);
         }
         float s, c;
-        sincosf(theta, &s, &c);
+        __sincosf(theta, &s, &c);  // |theta| <= pi: the SFU form, like the reference's sin/cos.approx
         sx = r * c;
         sy = r * s;
     }

@@ -66,6 +66,7 @@ __global__ void prepare_kernel(WaveCtl *ctl) {
     ctl->n_shadow = 0;
     ctl->trace_cursor = 0;
     ctl->shadow_cursor = 0;
+    for (int c = 0; c < 8; ++c) ctl->class_count[c] = 0;
     ctl->n_gen += (unsigned long long)n_new;
     ctl->n_closest += (unsigned long long)(survivors + n_new);
     ctl->n_iter += (survivors + n_new) > 0 ? 1 : 0;
@@ -144,14 +145,28 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(SceneDevice scene, Ren
 // ---------------------------------------------------------------------------------------------------------------
 // closest hit (trace.cpp:38-78)
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_hit(const BvhDevice &bvh, const HitRec &h, int i, uint32_t *flag, uint4 *detail) {
+// returns the instance id of the hit, or -1 on a miss
+__device__ __forceinline__ int store_hit(const BvhDevice &bvh, const HitRec &h, int i, uint32_t *flag, uint4 *detail) {
     if (h.slot < 0) {
         flag[i] = 0;  // miss: flag only (save_flag(false, false, 0))
-    } else {
-        const uint2 id = __ldg(bvh.tri_ids + h.slot);
-        flag[i] = id.x | kFlagHasIntersection;
-        detail[i] = make_uint4(__float_as_uint(h.t), id.y, __float_as_uint(h.u), __float_as_uint(h.v));
+        return -1;
     }
+    const uint2 id = __ldg(bvh.tri_ids + h.slot);
+    flag[i] = id.x | kFlagHasIntersection;
+    detail[i] = make_uint4(__float_as_uint(h.t), id.y, __float_as_uint(h.u), __float_as_uint(h.v));
+    return (int)id.x;
+}
+
+// Appends state index i to the list of shade class c: one atomic per warp and class (match.any groups the lanes).
+// All lanes of the warp must call this (inactive ones with valid = false).
+__device__ __forceinline__ void class_append(const HitQueue &hq, WaveCtl *ctl, bool valid, int c, int i) {
+    const unsigned peers = __match_any_sync(kFull, valid ? c : -1);
+    if (!valid) return;
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane_id() == leader) base = atomicAdd(&ctl->class_count[c], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    hq.class_list[(size_t)c * hq.class_stride + base + __popc(peers & ((1u << lane_id()) - 1u))] = (uint32_t)i;
 }
 
 __global__ void __launch_bounds__(kBlock) trace_kernel(SceneDevice scene, PathQueue q, HitQueue hq, WaveCtl *ctl) {
@@ -163,16 +178,32 @@ __global__ void __launch_bounds__(kBlock) trace_kernel(SceneDevice scene, PathQu
         base = __shfl_sync(kFull, base, 0);
         if (base >= n) break;
         const int i = base + lane_id();
+        int cls = 0;
         if (i < n) {
             const float4 o4 = q.ray_o[i], d4 = q.ray_d[i];
             const HitRec h = traverse_bvh2<false>(scene.bvh, xyz(o4), xyz(d4), d4.w);
-            store_hit(scene.bvh, h, i, hq.flag, hq.detail);
-            hits += h.slot >= 0 ? 1 : 0;
+            const int inst = store_hit(scene.bvh, h, i, hq.flag, hq.detail);
+            if (inst >= 0) { cls = __ldg(scene.instance_class + inst); hits += 1; }
         }
         __syncwarp();
+        class_append(hq, ctl, i < n, cls, i);
     }
     for (int off = 16; off; off >>= 1) hits += __shfl_down_sync(kFull, hits, off);
     if (lane_id() == 0 && hits) atomicAdd(&ctl->n_hit, hits);
+}
+
+// Builds the class lists from hit flags (stage-level entry points: the hits come from the caller, not from trace_kernel)
+__global__ void __launch_bounds__(kBlock) classify_kernel(SceneDevice scene, HitQueue hq, WaveCtl *ctl) {
+    const int n = ctl->n_active;
+    const int n_round = (n + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        int cls = 0;
+        if (i < n) {
+            const uint32_t flag = hq.flag[i];
+            if (flag & kFlagHasIntersection) cls = __ldg(scene.instance_class + (flag & kFlagInstanceMask));
+        }
+        class_append(hq, ctl, i < n, cls, i);
+    }
 }
 
 __global__ void __launch_bounds__(kBlock) trace_batch_kernel(SceneDevice scene, const float4 *ray_o, const float4 *ray_d, int n,
@@ -317,20 +348,45 @@ __global__ void __launch_bounds__(kBlock) medium_kernel(SceneDevice scene, Rende
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// shade (shade.cpp:38-235)
+// shade (shade.cpp:38-235), one kernel per shade class: shade_miss_kernel for rays that left the scene and
+// shade_kernel<MAT> for hits on each material type.  The reference dispatches with a switch over per-object generated
+// code inside one kernel (core/scene.cpp:358-374); here the closest-hit kernel has already binned the states.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQueue nq, ShadowQueue sq,
-                                                      FilmDevice film, WaveCtl *ctl) {
-    const int n = ctl->n_active;
+__global__ void __launch_bounds__(kBlock) shade_miss_kernel(SceneDevice scene, PathQueue q, HitQueue hq, FilmDevice film, WaveCtl *ctl) {
+    const int n = ctl->class_count[0];
+    const uint32_t *list = hq.class_list;
+    unsigned long long splats = 0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {  // shade.cpp:54-69
+        const int i = (int)list[j];
+        const float4 rad4 = q.rad[i];
+        f3 v(0.0f);
+        if (scene.env.type != ENV_NONE) {
+            const float4 d4 = q.ray_d[i], ble4 = q.ble[i];
+            v = eval_miss_le(scene, xyz(d4), xyz(ble4), ble4.w);
+        }
+        if (!(hq.flag[i] & kFlagHasScattering)) v = v + xyz(rad4);
+        film_splat3(film.radiance, __float_as_uint(rad4.w), v);
+        splats += 1;
+    }
+    for (int off = 16; off; off >>= 1) splats += __shfl_down_sync(kFull, splats, off);
+    if (lane_id() == 0 && splats) atomicAdd(&ctl->n_splat, splats);
+}
+
+template <int MAT>
+__global__ void __launch_bounds__(kBlock, (MAT == MAT_DISNEY || MAT == MAT_METAL) ? 2 : 3)
+shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQueue nq, ShadowQueue sq, FilmDevice film, WaveCtl *ctl) {
+    const int n = ctl->class_count[1 + MAT];
+    const uint32_t *list = hq.class_list + (size_t)(1 + MAT) * hq.class_stride;
     const int n_round = (n + 31) & ~31;  // whole warps take part in the aggregated allocations
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
         bool emit_next = false, emit_shadow = false, splat = false;
         f3 splat_value(0.0f);
         uint32_t pixel = 0;
         NextState ns;
         ShadowOut so;
 
-        if (i < n) {
+        if (j < n) {
+            const int i = (int)list[j];
             const uint32_t flag = hq.flag[i];
             const bool scattered = (flag & kFlagHasScattering) != 0;
             const float4 rad4 = q.rad[i], o4 = q.ray_o[i], d4 = q.ray_d[i], ble4 = q.ble[i];
@@ -339,45 +395,62 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(SceneDevice scene, Render
             const f3 o = xyz(o4), d = xyz(d4);
             const f3 beta_le = xyz(ble4);
             const float bsdf_pdf = ble4.w;
-
-            if (!(flag & kFlagHasIntersection)) {  // shade.cpp:54-69
-                f3 v = eval_miss_le(scene, d, beta_le, bsdf_pdf);
-                if (!scattered) v = v + L;
-                splat = true; splat_value = v;
+            const uint4 det = hq.detail[i];
+            const InstanceInfo &inst = scene.instances[flag & kFlagInstanceMask];
+            const GeometryInfo &geo = scene.geometries[inst.geometry_id];
+            const SurfacePoint inct = get_hitinfo(o, d, inst, geo, __uint_as_float(det.x), det.y,
+                                                  make_float2(__uint_as_float(det.z), __uint_as_float(det.w)));
+            const f3 le_rad = handle_intersected_light(scene, o, d, inct, beta_le, bsdf_pdf, inst.light_id);
+            if (scattered) {
+                splat = true; splat_value = le_rad;
             } else {
-                const uint4 det = hq.detail[i];
-                const InstanceInfo &inst = scene.instances[flag & kFlagInstanceMask];
-                const GeometryInfo &geo = scene.geometries[inst.geometry_id];
-                const SurfacePoint inct = get_hitinfo(o, d, inst, geo, __uint_as_float(det.x), det.y,
-                                                      make_float2(__uint_as_float(det.z), __uint_as_float(det.w)));
-                const f3 le_rad = handle_intersected_light(scene, o, d, inct, beta_le, bsdf_pdf, inst.light_id);
-                if (scattered) {
-                    splat = true; splat_value = le_rad;
+                const float4 beta4 = q.beta[i];
+                const ulonglong2 rng2 = q.rng[i];
+                f3 beta = xyz(beta4);
+                const int depth = __float_as_int(beta4.w);
+                const uint32_t ray_medium = __float_as_uint(o4.w);
+                Sampler sampler;
+                sampler.rng.state = rng2.x; sampler.rng.inc = rng2.y;
+                L = L + le_rad;
+                if (simple_russian_roulette(P, beta, depth, sampler)) {
+                    splat = true; splat_value = L;
                 } else {
-                    const float4 beta4 = q.beta[i];
-                    const ulonglong2 rng2 = q.rng[i];
-                    f3 beta = xyz(beta4);
-                    const int depth = __float_as_int(beta4.w);
-                    const uint32_t ray_medium = __float_as_uint(o4.w);
-                    Sampler sampler;
-                    sampler.rng.state = rng2.x; sampler.rng.inc = rng2.y;
-                    L = L + le_rad;
-                    if (simple_russian_roulette(P, beta, depth, sampler)) {
-                        splat = true; splat_value = L;
+                    LiSample ls = sample_light_li<true>(scene, inct.position, inct.frame.z, sampler);
+                    const Shader<MAT> shader = create_shader<MAT>(scene, scene.materials[inst.material_id], inct);
+                    if (depth == 0) {
+                        if (film.albedo) film_splat3(film.albedo, pixel, shader.albedo());
+                        if (film.normal) film_splat3(film.normal, pixel, shader.normal());
+                    }
+                    const f3 wo = -d;
+                    const float b0 = sampler.get1d(), b1 = sampler.get1d(), b2 = sampler.get1d();
+                    BsdfSample bs = bsdf_none();
+                    if (!shader.is_aggregate()) {
+                        bs = shader.sample_delta(wo, b0);  // eval == 0: no shadow ray (shade.cpp:151)
                     } else {
-                        LiSample ls = sample_light_li<true>(scene, inct.position, inct.frame.z, sampler);
-                        const Shader shader = create_shader(scene, scene.materials[inst.material_id], inct);
-                        if (depth == 0) {
-                            if (film.albedo) film_splat3(film.albedo, pixel, shader.albedo());
-                            if (film.normal) film_splat3(film.normal, pixel, shader.normal());
+                        const Frame3 shf = shader.flipped_shading(wo);
+                        const f3 lwo = normalize(shf.global_to_local(wo));
+                        const f3 l_sample = shader.sample_local_dir(lwo, b0, b1, b2);
+                        const f3 l_light = ls.success ? normalize(shf.global_to_local(ls.d)) : f3(0.0f);
+                        f3 f_sample(0.0f), f_light(0.0f);
+                        float p_sample = 0.0f, p_light = 0.0f;
+#pragma unroll 1
+                        for (int k = 0; k < 2; ++k) {  // one copy of the closure's eval + pdf for both directions
+                            const f3 lw = k == 0 ? l_sample : l_light;
+                            f3 f(0.0f);
+                            float p = 0.0f;
+                            if (!is_zero(lw)) shader.comp_eval_pdf(lw, lwo, f, p);
+                            if (k == 0) { f_sample = f; p_sample = p; } else { f_light = f; p_light = p; }
                         }
-                        const f3 wo = -d;
-                        const float b0 = sampler.get1d(), b1 = sampler.get1d(), b2 = sampler.get1d();
-                        const BsdfSample bs = shader.sample(wo, b0, b1, b2);
+                        if (p_sample > 0.0f && !shader.reject_sample(f_sample, l_sample, p_sample)) {  // aggregate.cpp:84-117
+                            const f3 dir = shf.local_to_global(l_sample);
+                            if (!shader.frame.is_black_fringes(dir)) {
+                                bs.dir = dir;
+                                bs.bsdf = f_sample * shader.wrap_factor(shf.z, dir);
+                                bs.pdf = p_sample;
+                            }
+                        }
                         if (ls.success) {
-                            f3 shadow_bsdf_val;
-                            float shadow_bsdf_pdf;
-                            shader.eval_pdf(ls.d, wo, shadow_bsdf_val, shadow_bsdf_pdf);
+                            const f3 shadow_bsdf_val = f_light * shader.wrap_factor(shf.z, ls.d);  // aggregate.cpp:185-197
                             if (!is_zero(shadow_bsdf_val)) {
                                 const bool shadow_d_out = dot(inct.frame.z, ls.d) > 0.0f;
                                 const bool last_ray_out = dot(inct.frame.z, d) < 0.0f;
@@ -385,26 +458,26 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(SceneDevice scene, Render
                                 else if (shadow_d_out) so.med = inst.outer_medium_id;
                                 else so.med = inst.inner_medium_id;
                                 const float cosv = fabsf(dot(normalize(ls.d), inct.frame.z));
-                                so.beta = ls.li * beta * shadow_bsdf_val * cosv / (shadow_bsdf_pdf + ls.light_pdf);
+                                so.beta = ls.li * beta * shadow_bsdf_val * cosv / (p_light + ls.light_pdf);
                                 so.o = ls.o; so.d = ls.d; so.t1 = ls.t1;
                                 emit_shadow = true;
                             }
                         }
-                        if (!is_zero(bs.bsdf)) {
-                            const f3 dir = normalize(bs.dir);
-                            const float cosv = fabsf(dot(dir, inct.frame.z));
-                            ns.ble = beta * cosv * bs.bsdf;
-                            ns.beta = ns.ble / bs.pdf;
-                            ns.o = intersection_offset(inct.position, inct.frame.z, dir);
-                            ns.d = dir;
-                            ns.med = dot(inct.frame.z, dir) > 0.0f ? inst.outer_medium_id : inst.inner_medium_id;
-                            ns.pdf = bs.is_delta ? -bs.pdf : bs.pdf;
-                            ns.L = L; ns.depth = depth + 1;
-                            ns.rng = make_ulonglong2(sampler.rng.state, sampler.rng.inc);
-                            emit_next = true;
-                        } else {
-                            splat = true; splat_value = L;
-                        }
+                    }
+                    if (!is_zero(bs.bsdf)) {
+                        const f3 dir = normalize(bs.dir);
+                        const float cosv = fabsf(dot(dir, inct.frame.z));
+                        ns.ble = beta * cosv * bs.bsdf;
+                        ns.beta = ns.ble / bs.pdf;
+                        ns.o = intersection_offset(inct.position, inct.frame.z, dir);
+                        ns.d = dir;
+                        ns.med = dot(inct.frame.z, dir) > 0.0f ? inst.outer_medium_id : inst.inner_medium_id;
+                        ns.pdf = bs.is_delta ? -bs.pdf : bs.pdf;
+                        ns.L = L; ns.depth = depth + 1;
+                        ns.rng = make_ulonglong2(sampler.rng.state, sampler.rng.inc);
+                        emit_next = true;
+                    } else {
+                        splat = true; splat_value = L;
                     }
                 }
             }
@@ -475,9 +548,31 @@ void launch_trace(const LaunchCfg &cfg, const SceneDevice &scene, PathQueue cur,
     trace_kernel<<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, cur, hit, ctl);
 }
 
-void launch_shade(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, HitQueue hit, PathQueue next,
-                  ShadowQueue shadow, FilmDevice film, WaveCtl *ctl, cudaStream_t stream) {
-    shade_kernel<<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
+template <int MAT>
+static void launch_shade_class(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, HitQueue hit, PathQueue next,
+                               ShadowQueue shadow, FilmDevice film, WaveCtl *ctl, cudaStream_t stream) {
+    shade_kernel<MAT><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
+}
+
+int launch_shade(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, uint32_t material_mask, PathQueue cur, HitQueue hit,
+                 PathQueue next, ShadowQueue shadow, FilmDevice film, WaveCtl *ctl, cudaStream_t stream) {
+    int launches = 1;
+    shade_miss_kernel<<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, cur, hit, film, ctl);
+#define BTRC_SHADE_CLASS(M) \
+    if (material_mask & (1u << M)) { launch_shade_class<M>(cfg, scene, params, cur, hit, next, shadow, film, ctl, stream); ++launches; }
+    BTRC_SHADE_CLASS(MAT_DISNEY)
+    BTRC_SHADE_CLASS(MAT_DIFFUSE)
+    BTRC_SHADE_CLASS(MAT_METAL)
+    BTRC_SHADE_CLASS(MAT_GLASS)
+    BTRC_SHADE_CLASS(MAT_MIRROR)
+    BTRC_SHADE_CLASS(MAT_INVISIBLE)
+    BTRC_SHADE_CLASS(MAT_BLACK)
+#undef BTRC_SHADE_CLASS
+    return launches;
+}
+
+void launch_classify(const LaunchCfg &cfg, const SceneDevice &scene, HitQueue hit, WaveCtl *ctl, cudaStream_t stream) {
+    classify_kernel<<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, hit, ctl);
 }
 
 void launch_medium(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, HitQueue hit, PathQueue next,

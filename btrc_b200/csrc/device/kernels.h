@@ -21,8 +21,12 @@ void launch_prepare(WaveCtl *ctl, cudaStream_t stream);
 void launch_generate(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, FilmDevice film,
                      WaveCtl *ctl, cudaStream_t stream);
 void launch_trace(const LaunchCfg &cfg, const SceneDevice &scene, PathQueue cur, HitQueue hit, WaveCtl *ctl, cudaStream_t stream);
-void launch_shade(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, HitQueue hit,
-                  PathQueue next, ShadowQueue shadow, FilmDevice film, WaveCtl *ctl, cudaStream_t stream);
+// One kernel per shade class: misses + one instantiation per material type present in the scene (bit m of material_mask
+// = a material of MaterialType m exists).  Returns the number of kernels launched.
+int launch_shade(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, uint32_t material_mask, PathQueue cur,
+                 HitQueue hit, PathQueue next, ShadowQueue shadow, FilmDevice film, WaveCtl *ctl, cudaStream_t stream);
+// Builds the shade class lists from hit flags (stage-level entry points; in a render trace_kernel builds them)
+void launch_classify(const LaunchCfg &cfg, const SceneDevice &scene, HitQueue hit, WaveCtl *ctl, cudaStream_t stream);
 // sample_medium_scattering_kernel (medium.cpp:28-164): runs between trace and shade when the scene has media
 void launch_medium(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, HitQueue hit,
                    PathQueue next, ShadowQueue shadow, FilmDevice film, WaveCtl *ctl, cudaStream_t stream);

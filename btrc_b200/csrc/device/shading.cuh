@@ -15,12 +15,13 @@
 namespace btrc {
 
 // ---- textures ----------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ f3 eval_texture(const SceneDevice &scene, int tex, float2 uv) {
-    const TextureDesc td = scene.textures[tex];
+// General path: postfix program.  Kept out of line: the shade kernel evaluates up to 15 textures per hit and one copy of
+// this loop is enough (the instruction footprint of the kernel is what limits its issue rate, see profiles/).
+__device__ __noinline__ f3 eval_texture_program(const TexOp *__restrict__ ops, int n_ops, float2 uv) {
     f3 stack[4];
     int sp = 0;
-    for (int k = 0; k < td.n_ops; ++k) {
-        const TexOp &op = scene.tex_ops[td.first_op + k];
+    for (int k = 0; k < n_ops; ++k) {
+        const TexOp &op = ops[k];
         const int code = op.op;
         if (code == TEXOP_CONST) {
             stack[sp++] = f3(op.value[0], op.value[1], op.value[2]);
@@ -35,6 +36,13 @@ __device__ __forceinline__ f3 eval_texture(const SceneDevice &scene, int tex, fl
         }
     }
     return stack[0];
+}
+
+__device__ __forceinline__ f3 eval_texture(const SceneDevice &scene, int tex, float2 uv) {
+    const TextureDesc td = scene.textures[tex];
+    const TexOp &op = scene.tex_ops[td.first_op];
+    if (td.n_ops == 1 && op.op == TEXOP_CONST) return f3(op.value[0], op.value[1], op.value[2]);  // literal / "constant"
+    return eval_texture_program(&op, td.n_ops, uv);
 }
 __device__ __forceinline__ float eval_texture_float(const SceneDevice &scene, int tex, float2 uv) { return eval_texture(scene, tex, uv).x; }
 
@@ -244,12 +252,12 @@ __device__ __forceinline__ bool simple_russian_roulette(const RenderParams &P, f
 }
 
 // Material::create_shader of every material type (see bsdf.cuh for the citations); normal map: utils/normal_map.cpp:13-21
-__device__ __forceinline__ Shader create_shader(const SceneDevice &scene, const MaterialDesc &mat, const SurfacePoint &inct) {
-    Shader sh;
-    sh.type = mat.type;
+template <int MAT>
+__device__ __forceinline__ Shader<MAT> create_shader(const SceneDevice &scene, const MaterialDesc &mat, const SurfacePoint &inct) {
+    Shader<MAT> sh;
     sh.shadow_terminator = mat.shadow_terminator != 0;
     sh.frame.geometry = inct.frame;
-    if (mat.type == MAT_BLACK || mat.type == MAT_INVISIBLE) {
+    if (MAT == MAT_BLACK || MAT == MAT_INVISIBLE) {
         sh.frame.shading = inct.frame;
         return sh;
     }
@@ -261,15 +269,15 @@ __device__ __forceinline__ Shader create_shader(const SceneDevice &scene, const 
         const f3 world_nor = sh.frame.shading.local_to_global(local_nor);
         sh.frame.shading = sh.frame.shading.rotate_to_new_z(normalize(world_nor));
     }
-    if (mat.type == MAT_DISNEY) {
+    if (MAT == MAT_DISNEY) {
         const f3 base = eval_texture(scene, mat.tex[SLOT_COLOR], uv);
-        sh.disney = disney_make(base, eval_texture_float(scene, mat.tex[SLOT_METALLIC], uv), eval_texture_float(scene, mat.tex[SLOT_ROUGHNESS], uv),
-                                eval_texture_float(scene, mat.tex[SLOT_SPECULAR], uv), eval_texture_float(scene, mat.tex[SLOT_SPECULAR_TINT], uv),
-                                eval_texture_float(scene, mat.tex[SLOT_ANISOTROPIC], uv), eval_texture_float(scene, mat.tex[SLOT_SHEEN], uv),
-                                eval_texture_float(scene, mat.tex[SLOT_SHEEN_TINT], uv), eval_texture_float(scene, mat.tex[SLOT_CLEARCOAT], uv),
-                                eval_texture_float(scene, mat.tex[SLOT_CLEARCOAT_GLOSS], uv), eval_texture_float(scene, mat.tex[SLOT_TRANSMISSION], uv),
-                                eval_texture_float(scene, mat.tex[SLOT_TRANSMISSION_ROUGHNESS], uv), eval_texture_float(scene, mat.tex[SLOT_IOR], uv));
-    } else if (mat.type == MAT_METAL) {
+        float v[SLOT_COUNT];
+#pragma unroll 1
+        for (int slot = SLOT_METALLIC; slot < SLOT_COUNT; ++slot) v[slot] = eval_texture_float(scene, mat.tex[slot], uv);
+        sh.disney = disney_make(base, v[SLOT_METALLIC], v[SLOT_ROUGHNESS], v[SLOT_SPECULAR], v[SLOT_SPECULAR_TINT], v[SLOT_ANISOTROPIC], v[SLOT_SHEEN],
+                                v[SLOT_SHEEN_TINT], v[SLOT_CLEARCOAT], v[SLOT_CLEARCOAT_GLOSS], v[SLOT_TRANSMISSION], v[SLOT_TRANSMISSION_ROUGHNESS],
+                                v[SLOT_IOR]);
+    } else if (MAT == MAT_METAL) {
         sh.metal.R0 = eval_texture(scene, mat.tex[SLOT_COLOR], uv);
         const float roughness = eval_texture_float(scene, mat.tex[SLOT_ROUGHNESS], uv);
         const float anisotropic = eval_texture_float(scene, mat.tex[SLOT_ANISOTROPIC], uv);
@@ -279,7 +287,7 @@ __device__ __forceinline__ Shader create_shader(const SceneDevice &scene, const 
         sh.metal.ay = fmaxf(0.001f, roughness * roughness * aspect);
     } else {
         sh.color = eval_texture(scene, mat.tex[SLOT_COLOR], uv);
-        if (mat.type == MAT_GLASS) sh.ior = eval_texture_float(scene, mat.tex[SLOT_IOR], uv);
+        if (MAT == MAT_GLASS) sh.ior = eval_texture_float(scene, mat.tex[SLOT_IOR], uv);
     }
     return sh;
 }

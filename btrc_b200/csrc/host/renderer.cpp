@@ -39,6 +39,9 @@ Renderer::Renderer(Scene &scene, int state_count_override) : scene_(scene) {
     }
     hit_.flag = alloc<uint32_t>(P);
     hit_.detail = alloc<uint4>(P);
+    hit_.class_list = alloc<uint32_t>(P * kNumShadeClasses);
+    hit_.class_stride = pool_;
+    for (const MaterialDesc &m : scene.materials) material_mask_ |= 1u << m.type;
     shadow_.ray_o = alloc<float4>(P);
     shadow_.ray_d = alloc<float4>(P);
     shadow_.beta_li = alloc<float4>(P);
@@ -83,7 +86,8 @@ void Renderer::render_range(long long begin, long long end) {
     BTRC_CUDA(cudaEventRecord(ev_begin_, stream_));
 
     const bool has_medium = scene_.dev.has_medium != 0;
-    const int kernels_per_iter = has_medium ? 6 : 5;
+    const int kernels_per_iter = has_medium ? 5 : 4;  // prepare, generate, trace, [medium], shadow; shade adds its own count
+    unsigned long long n_kernels = 0;
     int cur = 0;
     long long iter = 0;
     bool done = false;
@@ -107,7 +111,7 @@ void Renderer::render_range(long long begin, long long end) {
         mark();
         if (has_medium) launch_medium(cfg_, scene_.dev, params, q_[cur], hit_, q_[cur ^ 1], shadow_, film_, ctl_, stream_);
         mark();
-        launch_shade(cfg_, scene_.dev, params, q_[cur], hit_, q_[cur ^ 1], shadow_, film_, ctl_, stream_);
+        n_kernels += launch_shade(cfg_, scene_.dev, params, material_mask_, q_[cur], hit_, q_[cur ^ 1], shadow_, film_, ctl_, stream_);
         mark();
         launch_shadow(cfg_, scene_.dev, params, shadow_, film_, ctl_, stream_);
         mark();
@@ -141,12 +145,14 @@ void Renderer::render_range(long long begin, long long end) {
     stats_.n_splat += fin.n_splat;
     stats_.n_iter += fin.n_iter;
     stats_.render_ms = ms;
-    stats_.n_launches = (unsigned long long)kernels_per_iter * (unsigned long long)iter;
+    stats_.n_launches = (unsigned long long)kernels_per_iter * (unsigned long long)iter + n_kernels;
     for (double &v : stats_.stage_ms) v = 0;
     // events per iteration: after prepare, generate, trace, medium, shade, shadow  => intervals gen, trace, medium, shade, shadow
-    static const int kStageOfInterval[5] = {0, 1, 4, 2, 3};
+    // the sixth interval (after shadow -> after the next prepare) is the iteration bookkeeping: counter snapshot + prepare kernel
+    static const int kStageOfInterval[6] = {0, 1, 4, 2, 3, 5};
     for (size_t k = 0; k + 5 < n_prof; k += 6) {
-        for (int iv = 0; iv < 5; ++iv) {
+        for (int iv = 0; iv < 6; ++iv) {
+            if (k + iv + 1 >= n_prof) break;
             float t = 0;
             BTRC_CUDA(cudaEventElapsedTime(&t, prof_events_[k + iv], prof_events_[k + iv + 1]));
             stats_.stage_ms[kStageOfInterval[iv]] += t;
@@ -182,7 +188,8 @@ void Renderer::stage_shade(int n, int *n_next, int *n_shadow) {
     std::memset(&c, 0, sizeof(c));
     c.n_active = n; c.pool = pool_;
     BTRC_CUDA(cudaMemcpyAsync(ctl_, &c, sizeof(c), cudaMemcpyHostToDevice, stream_));
-    launch_shade(cfg_, scene_.dev, scene_.render_params(), q_[0], hit_, q_[1], shadow_, film_, ctl_, stream_);
+    launch_classify(cfg_, scene_.dev, hit_, ctl_, stream_);
+    launch_shade(cfg_, scene_.dev, scene_.render_params(), material_mask_, q_[0], hit_, q_[1], shadow_, film_, ctl_, stream_);
     BTRC_CUDA(cudaMemcpyAsync(&c, ctl_, sizeof(c), cudaMemcpyDeviceToHost, stream_));
     BTRC_CUDA(cudaStreamSynchronize(stream_));
     BTRC_CUDA(cudaGetLastError());

@@ -17,8 +17,9 @@ namespace btrc {
 struct RenderStats {
     uint64_t n_gen = 0, n_closest = 0, n_hit = 0, n_next = 0, n_shadow = 0, n_shadow_miss = 0, n_splat = 0, n_iter = 0;
     double render_ms = 0;  // device time of the last render_range (CUDA events)
-    // per-stage device time of the last render_range (only when profiling is on): generate, trace, shade, shadow, medium
-    double stage_ms[5] = {0, 0, 0, 0, 0};
+    // per-stage device time of the last render_range (only when profiling is on): generate, trace, shade, shadow, medium,
+    // iteration bookkeeping (counter snapshot + prepare kernel)
+    double stage_ms[6] = {0, 0, 0, 0, 0, 0};
     uint64_t n_launches = 0;  // kernels launched by the last render_range
 };
 
@@ -63,6 +64,7 @@ private:
     HitQueue hit_{};
     ShadowQueue shadow_{};
     FilmDevice film_{};
+    uint32_t material_mask_ = 0;    // bit m: a material of MaterialType m exists (one shade kernel per set bit)
     WaveCtl *ctl_ = nullptr;        // device
     WaveCtl *ctl_host_ = nullptr;   // pinned ring of snapshots
     cudaEvent_t snap_ev_[8]{};

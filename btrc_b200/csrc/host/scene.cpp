@@ -753,6 +753,11 @@ void Scene::upload_device() {
     dev.bvh.n_tris = (int)world_tris.size();
     if (!filter_alias.empty()) dev.filter_alias = reinterpret_cast<const float2 *>(upload(filter_alias));
     dev.instances = upload(instance_info);
+    {
+        std::vector<uint8_t> cls(instance_info.size());
+        for (size_t i = 0; i < cls.size(); ++i) cls[i] = (uint8_t)(1 + materials[instance_info[i].material_id].type);
+        dev.instance_class = upload(cls);
+    }
     dev.geometries = upload(geos);
     dev.materials = upload(materials);
     // ---- textures: CUDA texture objects for the "array" sources, postfix programs for the graph

@@ -49,9 +49,9 @@ typedef struct btrc_render_stats {
     uint64_t n_splat;        /* radiance splats (3 float atomics each)                         */
     uint64_t n_iter;         /* wavefront iterations                                           */
     double render_ms;        /* device time of the last btrc_render_range (CUDA events)        */
-    double stage_ms[5];      /* with btrc_set_profiling(1): device time per stage of the last  */
+    double stage_ms[6];      /* with btrc_set_profiling(1): device time per stage of the last  */
                              /* range -- generate, closest-hit trace, shade, shadow trace,     */
-                             /* medium                                                         */
+                             /* medium, iteration bookkeeping (counter snapshot + prepare)     */
     uint64_t n_launches;     /* kernels launched by the last btrc_render_range                 */
 } btrc_render_stats_t;
 

@@ -458,7 +458,18 @@ class Transform3D:
 
 
 # --------------------------------------------------------------------------- OBJ
+_OBJ_CACHE = {}
+
+
 def load_obj(filename: str):
+    """Cached by (path, mtime): scenes instance one OBJ many times and every entity creates its own geometry object."""
+    key = (filename, os.path.getmtime(filename))
+    if key not in _OBJ_CACHE:
+        _OBJ_CACHE[key] = _load_obj(filename)
+    return _OBJ_CACHE[key]
+
+
+def _load_obj(filename: str):
     """tinyobj (triangulate=true) + TriangleMeshLoader: returns per-corner arrays in face order.
 
     pos (ntri*3, 3) f32, nor (ntri*3, 3) f32, has_nor (ntri*3) u8, uv (ntri*3, 2) f32.

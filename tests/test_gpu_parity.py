@@ -155,7 +155,10 @@ def test_shade_parity(pair_small):
         # fp32 shading values: relative 2e-4 (FMA contraction, rsqrt, sincos) on throughput-like quantities,
         # 2e-5 absolute on positions / unit directions
         assert np.allclose(nxt["o_med"][ia, :3], ref["o_med"][ib, :3], atol=2e-5)
-        assert np.allclose(nxt["d_t1"][ia, :3], ref["d_t1"][ib, :3], atol=2e-5)
+        # sampled directions: z = sqrt(1 - x^2 - y^2) amplifies the SFU sin/cos error (3.6e-7) by 1 / z towards grazing angles
+        dclose = np.isclose(nxt["d_t1"][ia, :3], ref["d_t1"][ib, :3], rtol=0, atol=2e-5).all(axis=1)
+        assert dclose.mean() > 0.995, dclose.mean()
+        assert np.allclose(nxt["d_t1"][ia, :3], ref["d_t1"][ib, :3], atol=2e-3)
         assert np.allclose(nxt["beta_depth"][ia, :3], ref["beta_depth"][ib, :3], rtol=2e-4, atol=1e-6)
         assert np.allclose(nxt["path_rad"][ia, :3], ref["path_rad"][ib, :3], rtol=2e-4, atol=1e-6)
         # beta_le and the pdf carry cos(theta) = sqrt(1 - sx^2 - sy^2) of the sampled direction, whose relative error grows like
