@@ -228,7 +228,9 @@ def run_ours(args):
     s = api.Scene(path, state_count=args.state_count)
     s.set_profiling(True)
     stream = torch.cuda.ExternalStream(s.stream_handle())
-    begin, end = rank * spp * npix, (rank + 1) * spp * npix
+    from btrc_b200 import partition
+
+    begin, end = partition.path_range(rank, world, spp * world, npix)
 
     rad = torch.zeros(H, W, 4, device="cuda")
     wgt = torch.zeros(H, W, device="cuda")
@@ -247,8 +249,7 @@ def run_ours(args):
         st = s.render_range(begin, end)
         if world > 1:  # the one collective of the path: sum of the film buffers (radiance float4 + weight), then resolve on rank 0
             s.film_export(rad, wgt)
-            dist.reduce(rad, 0)
-            dist.reduce(wgt, 0)
+            partition.reduce_films([rad, wgt], 0)
             if rank == 0:
                 s.film_import(rad, wgt)
         if rank == 0:

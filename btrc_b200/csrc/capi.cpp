@@ -229,12 +229,14 @@ int btrc_film_export(btrc_scene_t *s, int memory, float *radiance, float *weight
     return guarded([&] {
         check_scene(s);
         Renderer &r = s->r();
-        BTRC_CUDA(cudaStreamSynchronize(r.stream()));
+        // the caller's buffers may be in use on other streams (NCCL, torch): fence on both sides (once per render, not per wave)
+        BTRC_CUDA(cudaDeviceSynchronize());
         const size_t npix = (size_t)s->scene->width * s->scene->height;
         if (radiance) copy_any(radiance, r.film().radiance, 16 * npix);
         if (weight) copy_any(weight, r.film().weight, 4 * npix);
         if (albedo && r.film().albedo) copy_any(albedo, r.film().albedo, 16 * npix);
         if (normal && r.film().normal) copy_any(normal, r.film().normal, 16 * npix);
+        BTRC_CUDA(cudaDeviceSynchronize());
     });
 }
 
@@ -243,12 +245,13 @@ int btrc_film_import(btrc_scene_t *s, int memory, const float *radiance, const f
     return guarded([&] {
         check_scene(s);
         Renderer &r = s->r();
-        BTRC_CUDA(cudaStreamSynchronize(r.stream()));
+        BTRC_CUDA(cudaDeviceSynchronize());
         const size_t npix = (size_t)s->scene->width * s->scene->height;
         if (radiance) copy_any(r.film().radiance, radiance, 16 * npix);
         if (weight) copy_any(r.film().weight, weight, 4 * npix);
         if (albedo && r.film().albedo) copy_any(r.film().albedo, albedo, 16 * npix);
         if (normal && r.film().normal) copy_any(r.film().normal, normal, 16 * npix);
+        BTRC_CUDA(cudaDeviceSynchronize());
     });
 }
 

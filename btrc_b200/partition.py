@@ -1,0 +1,33 @@
+"""Multi-GPU partition of one render: sample streams split across ranks, one sum-reduce of the film buffers.
+
+Every camera path is fully determined by (pixel, sample index) through the sampler seed (builtin/sampler/independent.cpp:
+11-15), so a render splits into independent ranges of the path index space (Uniform mode: index = sample * W*H + pixel,
+generate.cpp:49-60).  Rank r of N renders the contiguous block of sample indices [r*spp/N, (r+1)*spp/N) for all pixels into
+its own film; the films (radiance float4 + weight float [+ albedo, normal]) are summed onto rank 0 -- the path's only
+collective -- and resolved there (value / weight, preview.cpp:28-80).  The reference is single-GPU; this is new work.
+"""
+from __future__ import annotations
+
+
+def sample_block(rank: int, world: int, spp: int):
+    """Sample indices [begin, end) of `rank`: blocks differ by at most one sample when world does not divide spp."""
+    base, rem = divmod(spp, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def path_range(rank: int, world: int, spp: int, npix: int):
+    """Camera-path index range [begin, end) of `rank` in Uniform mode (sample-major index space)."""
+    b, e = sample_block(rank, world, spp)
+    return b * npix, e * npix
+
+
+def reduce_films(tensors, dst: int = 0):
+    """Sum-reduce the film buffers onto `dst` (torch.distributed; NCCL on GPUs, gloo in the CPU tests)."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    for t in tensors:
+        if t is not None:
+            dist.reduce(t, dst, op=dist.ReduceOp.SUM)

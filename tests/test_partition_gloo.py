@@ -1,0 +1,68 @@
+"""world_size-2 gloo test of the multi-GPU host logic (no GPU): sample-block partition, film sum-reduce, resolve on rank 0.
+
+The per-rank renders run on the oracle here (the CUDA path needs a GPU; its own linearity in the sample range is covered by
+test_gpu_parity.py::test_render_c1_full_size_properties): what this checks is that partition + reduce + resolve reproduce the
+single-process image, including an spp that the world size does not divide.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_sample_blocks_cover_the_range():
+    from btrc_b200 import partition
+
+    for world in (1, 2, 3, 4, 8):
+        for spp in (1, 7, 16, 1024):
+            blocks = [partition.sample_block(r, world, spp) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == spp
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in blocks]
+            assert max(sizes) - min(sizes) <= 1
+            assert partition.path_range(world - 1, world, spp, 100)[1] == spp * 100
+
+
+def _worker(rank, world, path, port, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from btrc_b200 import partition
+    from oracle import front
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    o = front.OracleScene(path)
+    b, e = partition.sample_block(rank, world, o.spp)
+    r = o.render(b, e, raw=True)
+    rad, wgt = torch.from_numpy(r["raw_radiance"].copy()), torch.from_numpy(r["raw_weight"].copy())
+    partition.reduce_films([rad, wgt], 0)
+    if rank == 0:
+        color = np.zeros_like(rad.numpy())
+        w = wgt.numpy()
+        nz = w > 0
+        color[nz, :3] = rad.numpy()[nz, :3] / w[nz, None]
+        color[..., 3] = 1
+        np.save(out, color)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_render_equals_single_process(tmp_path, built):
+    import torch.multiprocessing as mp
+
+    from btrc_b200 import scenes
+    from oracle import front
+
+    path = scenes.make_cornell(str(tmp_path), width=48, height=48, spp=5, state_count=5000)  # 5 spp over 2 ranks: 3 + 2
+    out = str(tmp_path / "color.npy")
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, path, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    ref = front.OracleScene(path).render()["color"]
+    assert np.allclose(got, ref, rtol=1e-5, atol=1e-6)
