@@ -59,6 +59,7 @@ def _run(cmd):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
+    extra = os.environ.get("BTRC_NVCC_EXTRA", "").split()  # experiment knobs, e.g. -DBTRC_SHADE_BLOCKS_HEAVY=3
     headers = _all_headers()
     jobs = []
     objs = []
@@ -73,7 +74,7 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJ, src.replace("/", "_") + ".o")
         objs.append(o)
         if force or _newer(o, [s] + headers):
-            jobs.append([NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+            jobs.append([NVCC] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
     with cf.ThreadPoolExecutor(max_workers=8) as ex:
         for out in ex.map(_run, jobs):
             if verbose and out.strip():

@@ -178,15 +178,16 @@ __global__ void __launch_bounds__(kBlock) trace_kernel(SceneDevice scene, PathQu
         base = __shfl_sync(kFull, base, 0);
         if (base >= n) break;
         const int i = base + lane_id();
+        const bool valid = i < n;
+        float4 o4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d4 = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
+        if (valid) { o4 = q.ray_o[i]; d4 = q.ray_d[i]; }
+        const HitRec h = traverse_bvh2<false, true>(scene.bvh, xyz(o4), xyz(d4), d4.w, valid);
         int cls = 0;
-        if (i < n) {
-            const float4 o4 = q.ray_o[i], d4 = q.ray_d[i];
-            const HitRec h = traverse_bvh2<false>(scene.bvh, xyz(o4), xyz(d4), d4.w);
+        if (valid) {
             const int inst = store_hit(scene.bvh, h, i, hq.flag, hq.detail);
             if (inst >= 0) { cls = __ldg(scene.instance_class + inst); hits += 1; }
         }
-        __syncwarp();
-        class_append(hq, ctl, i < n, cls, i);
+        class_append(hq, ctl, valid, cls, i);
     }
     for (int off = 16; off; off >>= 1) hits += __shfl_down_sync(kFull, hits, off);
     if (lane_id() == 0 && hits) atomicAdd(&ctl->n_hit, hits);
@@ -372,8 +373,11 @@ __global__ void __launch_bounds__(kBlock) shade_miss_kernel(SceneDevice scene, P
     if (lane_id() == 0 && splats) atomicAdd(&ctl->n_splat, splats);
 }
 
+#ifndef BTRC_SHADE_BLOCKS_HEAVY
+#define BTRC_SHADE_BLOCKS_HEAVY 2
+#endif
 template <int MAT>
-__global__ void __launch_bounds__(kBlock, (MAT == MAT_DISNEY || MAT == MAT_METAL) ? 2 : 3)
+__global__ void __launch_bounds__(kBlock, (MAT == MAT_DISNEY || MAT == MAT_METAL) ? BTRC_SHADE_BLOCKS_HEAVY : 3)
 shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQueue nq, ShadowQueue sq, FilmDevice film, WaveCtl *ctl) {
     const int n = ctl->class_count[1 + MAT];
     const uint32_t *list = hq.class_list + (size_t)(1 + MAT) * hq.class_stride;
@@ -498,18 +502,17 @@ __global__ void __launch_bounds__(kBlock) shadow_kernel(SceneDevice scene, Rende
         base = __shfl_sync(kFull, base, 0);
         if (base >= n) break;
         const int i = base + lane_id();
-        if (i < n) {
-            const float4 o4 = sq.ray_o[i], d4 = sq.ray_d[i];
-            const HitRec h = traverse_bvh2<true>(scene.bvh, xyz(o4), xyz(d4), d4.w);
-            if (h.slot < 0) {
-                const float4 b4 = sq.beta_li[i];
-                f3 v = xyz(b4);
-                if (scene.has_medium) v = v * shadow_tr(scene, o4, d4);
-                film_splat3(film.radiance, __float_as_uint(b4.w), v);
-                misses += 1;
-            }
+        const bool valid = i < n;
+        float4 o4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d4 = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
+        if (valid) { o4 = sq.ray_o[i]; d4 = sq.ray_d[i]; }
+        const HitRec h = traverse_bvh2<true, true>(scene.bvh, xyz(o4), xyz(d4), d4.w, valid);
+        if (valid && h.slot < 0) {  // unoccluded: the reference's miss program (shadow.cpp:39-74)
+            const float4 b4 = sq.beta_li[i];
+            f3 v = xyz(b4);
+            if (scene.has_medium) v = v * shadow_tr(scene, o4, d4);
+            film_splat3(film.radiance, __float_as_uint(b4.w), v);
+            misses += 1;
         }
-        __syncwarp();
     }
     for (int off = 16; off; off >>= 1) misses += __shfl_down_sync(kFull, misses, off);
     if (lane_id() == 0 && misses) {

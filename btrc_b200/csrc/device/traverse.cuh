@@ -48,8 +48,11 @@ __device__ __forceinline__ bool id_less(const uint2 *__restrict__ ids, int a, in
 
 constexpr int kStackSize = 64;
 
-template <bool ANY_HIT>
-__device__ __forceinline__ HitRec traverse_bvh2(const BvhDevice &bvh, f3 o, f3 d, float tmax) {
+// CONVERGE: all 32 lanes of the warp call this together (lanes without a ray pass active = false); the vote at the top of
+// every descend-to-leaf / process-leaf round reconverges the warp (classic while-while), otherwise lanes drift apart and
+// the node loop and the leaf loop are issued separately for a handful of lanes each.
+template <bool ANY_HIT, bool CONVERGE = false>
+__device__ __forceinline__ HitRec traverse_bvh2(const BvhDevice &bvh, f3 o, f3 d, float tmax, bool active = true) {
     HitRec best;
     best.t = tmax; best.u = 0.0f; best.v = 0.0f; best.slot = -1;
 
@@ -63,11 +66,11 @@ __device__ __forceinline__ HitRec traverse_bvh2(const BvhDevice &bvh, f3 o, f3 d
 
     int stack[kStackSize];
     int sp = 0;
-    int cur = bvh.root_ref;
     constexpr int SENTINEL = 0x7fffffff;
+    int cur = active ? bvh.root_ref : SENTINEL;
     stack[sp++] = SENTINEL;
 
-    while (cur != SENTINEL) {
+    while (CONVERGE ? __any_sync(0xffffffffu, cur != SENTINEL) : (cur != SENTINEL)) {
         // descend through inner nodes
         while (cur >= 0 && cur != SENTINEL) {
             const float4 *node = bvh.nodes + 4 * (size_t)cur;
@@ -102,7 +105,12 @@ __device__ __forceinline__ HitRec traverse_bvh2(const BvhDevice &bvh, f3 o, f3 d
             for (int s = first; s < first + count; ++s) {
                 float t, u, v;
                 if (tri_test(bvh.tris + 3 * (size_t)s, o, d, best.t, t, u, v)) {
-                    if (ANY_HIT) { best.slot = s; return best; }
+                    if (ANY_HIT) {
+                        best.slot = s;
+                        if (!CONVERGE) return best;
+                        sp = 1;  // the next pop yields the sentinel
+                        break;
+                    }
                     if (t < best.t || best.slot < 0 || id_less(bvh.tri_ids, s, best.slot)) {
                         best.t = t; best.u = u; best.v = v; best.slot = s;
                     }
@@ -113,5 +121,6 @@ __device__ __forceinline__ HitRec traverse_bvh2(const BvhDevice &bvh, f3 o, f3 d
     }
     return best;
 }
+
 
 }  // namespace btrc
