@@ -74,6 +74,7 @@ def lib():
         L.btrc_shadow.argtypes = [c_void_p, c_int, c_int32] + [c_void_p] * 4
         L.btrc_geometry_tables.argtypes = [c_void_p, c_int32, POINTER(c_int32), c_void_p]
         L.btrc_instance_transform.argtypes = [c_void_p, c_int32, c_void_p, c_void_p]
+        L.btrc_ibl_table.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]
         L.btrc_device_sm_count.restype = c_int
         _lib = L
     return _lib
@@ -248,6 +249,13 @@ class Scene:
         out = np.zeros((n.value, 24), np.float32)
         _check(self.L.btrc_geometry_tables(self.h, geometry_id, byref(n), _p(out)))
         return out
+
+    def ibl_table(self):
+        w, h = c_int32(0), c_int32(0)
+        _check(self.L.btrc_ibl_table(self.h, byref(w), byref(h), None))
+        t = np.zeros((h.value, w.value), np.float32)
+        _check(self.L.btrc_ibl_table(self.h, byref(w), byref(h), _p(t)))
+        return t
 
     def instance_transform(self, instance_id):
         mat = np.zeros((3, 4), np.float32)

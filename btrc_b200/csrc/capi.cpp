@@ -446,6 +446,17 @@ int btrc_geometry_tables(btrc_scene_t *s, int32_t geometry_id, int32_t *n_triang
     });
 }
 
+int btrc_ibl_table(btrc_scene_t *s, int32_t *lut_w, int32_t *lut_h, float *probs) {
+    return guarded([&] {
+        check_scene(s);
+        s->scene->upload_device();
+        if (s->scene->env.type != ENV_IBL) throw Error("the scene has no ibl environment light");
+        if (lut_w) *lut_w = s->scene->env.lut_w;
+        if (lut_h) *lut_h = s->scene->env.lut_h;
+        if (probs) std::memcpy(probs, s->scene->ibl_tile_probs.data(), sizeof(float) * s->scene->ibl_tile_probs.size());
+    });
+}
+
 int btrc_instance_transform(btrc_scene_t *s, int32_t instance_id, float *mat12, float *inv12) {
     return guarded([&] {
         check_scene(s);

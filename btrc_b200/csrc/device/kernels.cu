@@ -537,6 +537,27 @@ __global__ void resolve_kernel(int npix, const float4 *value, const float *weigh
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// IBL set-up: generate_lum_sum_table (light/env_sampler.cpp:22-57) -- per LUT tile, mean luminance of the environment
+// texture over 256 Hammersley taps (stretched by 1.2 around the tile) and the tile's solid angle
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void ibl_lut_kernel(SceneDevice scene, int tex, int lut_w, int lut_h, int n_samples, float *lum_table, float *area_table) {
+    const int xi = blockDim.x * blockIdx.x + threadIdx.x;
+    const int yi = blockDim.y * blockIdx.y + threadIdx.y;
+    if (xi >= lut_w || yi >= lut_h) return;
+    const float x0 = float(xi) / lut_w, x1 = float(xi + 1) / lut_w;
+    const float y0 = float(yi) / lut_h, y1 = float(yi + 1) / lut_h;
+    float lum_sum = 0.0f;
+    for (int i = 0; i < n_samples; ++i) {
+        const float hx = float(i) / n_samples;
+        const float hy = __brev((unsigned)i) * 2.3283064365386963e-10f;  // hammersley_radical_inverse (utils/math/hammersley.h:7-15)
+        const float x = lerpf(x0, x1, 1.2f * hx - 0.1f), y = lerpf(y0, y1, 1.2f * hy - 0.1f);
+        lum_sum += lum(eval_texture(scene, tex, make_float2(x, y)));
+    }
+    lum_table[yi * lut_w + xi] = lum_sum / n_samples;
+    area_table[yi * lut_w + xi] = fabsf(2.0f * kPi * (x1 - x0) * (__cosf(kPi * y1) - __cosf(kPi * y0)));
+}
+
 inline int persistent_blocks(const LaunchCfg &cfg, int per_sm) { return cfg.sm_count * per_sm; }
 
 }  // namespace
@@ -572,6 +593,11 @@ int launch_shade(const LaunchCfg &cfg, const SceneDevice &scene, const RenderPar
     BTRC_SHADE_CLASS(MAT_BLACK)
 #undef BTRC_SHADE_CLASS
     return launches;
+}
+
+void launch_ibl_lut(const SceneDevice &scene, int tex, int lut_w, int lut_h, int n_samples, float *lum_table, float *area_table, cudaStream_t stream) {
+    const dim3 block(8, 8), grid((lut_w + 7) / 8, (lut_h + 7) / 8);
+    ibl_lut_kernel<<<grid, block, 0, stream>>>(scene, tex, lut_w, lut_h, n_samples, lum_table, area_table);
 }
 
 void launch_classify(const LaunchCfg &cfg, const SceneDevice &scene, HitQueue hit, WaveCtl *ctl, cudaStream_t stream) {

@@ -35,6 +35,9 @@ void launch_shadow(const LaunchCfg &cfg, const SceneDevice &scene, const RenderP
 // out = value.xyz / weight (normalise == 1: renormalise as a direction); out.w = 1
 void launch_resolve(int width, int height, const float *value, const float *weight, float *out, int normalise, cudaStream_t stream);
 
+// IBL preprocess (env_sampler.cpp:22-57): per-tile mean luminance and solid angle into two lut_w*lut_h device tables
+void launch_ibl_lut(const SceneDevice &scene, int tex, int lut_w, int lut_h, int n_samples, float *lum_table, float *area_table, cudaStream_t stream);
+
 // Stage-level entry points for tests on explicit batches (count given by the host; no WaveCtl).
 void launch_trace_batch(const LaunchCfg &cfg, const SceneDevice &scene, const float4 *ray_o, const float4 *ray_d, int n,
                         uint32_t *flag, uint4 *detail, cudaStream_t stream);

@@ -1,5 +1,6 @@
 #include "scene.h"
 
+#include "../device/kernels.h"
 #include "image_io.h"
 
 #include <algorithm>
@@ -791,9 +792,38 @@ void Scene::upload_device() {
     dev.env.type = env.type;
     dev.env.light_index = env.type != ENV_NONE ? (int)lights.size() : -1;
     for (int k = 0; k < 3; ++k) { dev.env.lower[k] = env.lower[k]; dev.env.upper[k] = env.upper[k]; dev.env.up[k] = env.up[k]; }
-    if (env.type == ENV_IBL) throw Error("unknown light type: ibl (image-based lighting is not supported yet)");
     dev.n_lights = (int)lights.size() + (env.type != ENV_NONE ? 1 : 0);
     dev.vol_prim_medium_id = (uint32_t)medium_table.size() - 1;
+    if (env.type == ENV_IBL) {  // IBL::commit -> EnvirLightSampler::preprocess (ibl.cpp:27-31, env_sampler.cpp:72-122)
+        dev.env.ibl_tex = env.tex;
+        dev.env.lut_w = env.lut_w; dev.env.lut_h = env.lut_h;
+        {  // Frame::from_z(up) (utils/math/frame.cpp:45-57)
+            const Vec3 nz = normalize(env.up);
+            const Vec3 ny = 1 - std::fabs(nz.x) < 0.1f ? cross(nz, Vec3(0, 1, 0)) : cross(nz, Vec3(1, 0, 0));
+            const Vec3 fx = normalize(cross(nz, ny)), fy = normalize(ny), fz = normalize(nz);
+            for (int k = 0; k < 3; ++k) { dev.env.frame[k] = fx[k]; dev.env.frame[3 + k] = fy[k]; dev.env.frame[6 + k] = fz[k]; }
+        }
+        const size_t nt = (size_t)env.lut_w * env.lut_h;
+        if (nt == 0) throw Error("ibl: empty lookup table");
+        DeviceBuffer d_lum(nt * sizeof(float)), d_area(nt * sizeof(float));
+        launch_ibl_lut(dev, env.tex, env.lut_w, env.lut_h, 256, d_lum.as<float>(), d_area.as<float>(), nullptr);
+        BTRC_CUDA(cudaDeviceSynchronize());
+        BTRC_CUDA(cudaGetLastError());
+        std::vector<float> lum(nt), area(nt);
+        BTRC_CUDA(cudaMemcpy(lum.data(), d_lum.ptr, nt * sizeof(float), cudaMemcpyDeviceToHost));
+        BTRC_CUDA(cudaMemcpy(area.data(), d_area.ptr, nt * sizeof(float), cudaMemcpyDeviceToHost));
+        float lum_area_sum = 0.0f, area_sum = 0.0f;
+        for (size_t i = 0; i < nt; ++i) { lum_area_sum += lum[i] * area[i]; area_sum += area[i]; }
+        const float avg_lum = lum_area_sum / area_sum;
+        for (size_t i = 0; i < nt; ++i) lum[i] = std::max(0.0f, area[i] * (lum[i] - avg_lum));
+        float table_sum = 0.0f;
+        for (float v : lum) table_sum += v;
+        if (table_sum > 1e-3f) { const float ratio = 1 / table_sum; for (float &v : lum) v *= ratio; }
+        ibl_tile_probs = lum;
+        ibl_alias = build_alias_table(lum);
+        dev.env.tile_probs = upload(ibl_tile_probs);
+        dev.env.tile_alias = reinterpret_cast<const float2 *>(upload(ibl_alias));
+    }
     dev.world_diagonal = world_diagonal;
     device_ready_ = true;
 }

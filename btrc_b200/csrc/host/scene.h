@@ -138,6 +138,8 @@ public:
     SceneDevice dev{};
     FlatBvh2 flat_bvh;
     std::vector<AliasUnit> filter_alias;
+    std::vector<float> ibl_tile_probs;      // EnvirLightSampler tile table (light/env_sampler.cpp:72-122)
+    std::vector<AliasUnit> ibl_alias;
     double bvh_build_seconds = 0;
     int bvh_depth = 0;
 

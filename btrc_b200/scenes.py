@@ -318,3 +318,50 @@ def make_medium_scene(out_dir, width=1920, height=1080, spp=128, state_count=100
     if save:
         root["post_processors"] = [{"type": "save", "color": save, "gamma": 2.2}]
     return _dump(out_dir, root)
+
+
+def write_envmap(path, width=512, height=256, seed=5):
+    """Equirectangular environment map as an 8-bit PNG: sky gradient, a bright sun blob and soft clouds (u = phi / 2pi, v = theta / pi)."""
+    from PIL import Image
+
+    rng = np.random.default_rng(seed)
+    v = (np.arange(height) + 0.5) / height
+    u = (np.arange(width) + 0.5) / width
+    sky = np.stack([0.25 + 0.3 * (1 - v), 0.35 + 0.35 * (1 - v), 0.55 + 0.4 * (1 - v)], axis=1)[:, None, :] * np.ones((1, width, 1))
+    ground = np.array([0.18, 0.15, 0.12])
+    img = np.where((v > 0.5)[:, None, None], ground[None, None, :] * np.ones((height, width, 1)), sky)
+    clouds = _smooth_noise(rng, max(width, height), 8)[:height, :width]
+    img[: height // 2] += 0.25 * clouds[: height // 2, :, None]
+    du = np.minimum(np.abs(u - 0.3), 1 - np.abs(u - 0.3))[None, :]
+    dv = (v - 0.22)[:, None]
+    sun = np.exp(-((du * 2) ** 2 + dv ** 2) / (2 * 0.02 ** 2))
+    img += sun[:, :, None] * np.array([4.0, 3.6, 3.0])
+    Image.fromarray((np.clip(img, 0, 1) * 255 + 0.5).astype(np.uint8), "RGB").save(path)
+
+
+def make_ibl_scene(out_dir, width=640, height=360, spp=64, state_count=500000, rings=24, segments=32, env_res=(512, 256), lut=(64, 32),
+                   min_depth=5, max_depth=10, save=None):
+    """Image-based lighting (light/ibl.cpp): ground + three spheres lit by an environment map only; the map is an 8-bit PNG
+    scaled by a `mul` operator texture (texture2d/math.cpp) so that the sun is brighter than 1."""
+    os.makedirs(out_dir, exist_ok=True)
+    write_envmap(os.path.join(out_dir, "env.png"), *env_res)
+    v, f, uv, n = uv_sphere(rings, segments)
+    write_obj(os.path.join(out_dir, "sphere.obj"), v, f, uv, n)
+    gv, gf, guv = quad((-8, 0, 8), (8, 0, 8), (8, 0, -8), (-8, 0, -8))
+    write_obj(os.path.join(out_dir, "ground.obj"), gv, gf, guv)
+    mats = [{"type": "diffuse", "color": [0.7, 0.7, 0.7]},
+            {"type": "metal", "color": [0.95, 0.8, 0.5], "roughness": 0.2},
+            {"type": "disney", "color": [0.2, 0.5, 0.8], "metallic": 0.0, "roughness": 0.4, "clearcoat": 0.5}]
+    entities = [{"geometry": _geo("ground"), "material": {"type": "diffuse", "color": [0.5, 0.5, 0.5]}}]
+    for i, m in enumerate(mats):
+        entities.append({"geometry": _geo("sphere"), "material": m, "local_to_world": {"translate": [(i - 1) * 2.4, 1.0, 0.0]}})
+    env_tex = {"type": "mul", "lhs": {"type": "array", "filename": "$env{scene_directory}/env.png", "address_mode_u": "wrap", "srgb_to_linear": True},
+               "rhs": [6.0, 6.0, 6.0]}
+    root = {"width": width, "height": height,
+            "camera": {"type": "pinhole", "eye": [0, 2.5, 7.5], "dst": [0, 0.8, 0], "up": [0, 1, 0], "fov_y": {"deg": 40}},
+            "renderer": _renderer(spp, state_count, min_depth, max_depth, None),
+            "scene": {"entities": entities,
+                      "envir_light": {"type": "ibl", "tex": env_tex, "up": [0, 1, 0], "lut_width": lut[0], "lut_height": lut[1]}}}
+    if save:
+        root["post_processors"] = [{"type": "tonemap", "exposure": 1.0}, {"type": "save", "color": save, "gamma": 2.2}]
+    return _dump(out_dir, root)

@@ -135,6 +135,9 @@ int btrc_shadow(btrc_scene_t *scene, int memory, int32_t n, const uint32_t *shad
  * geometry/triangle_mesh.cpp:40-106) and the instance transforms (local_to_world, world_to_local; 3x4 row-major). */
 int btrc_geometry_tables(btrc_scene_t *scene, int32_t geometry_id, int32_t *n_triangles, float *out24);
 int btrc_instance_transform(btrc_scene_t *scene, int32_t instance_id, float *mat12, float *inv12);
+/* EnvirLightSampler::preprocess result (light/env_sampler.cpp:72-122): the normalised lut_w * lut_h tile table of the "ibl"
+ * environment light, computed on the device at commit.  probs may be NULL to query the size. */
+int btrc_ibl_table(btrc_scene_t *scene, int32_t *lut_w, int32_t *lut_h, float *probs);
 
 /* The CUDA stream (cudaStream_t) all of this scene's kernels are launched on, so that a caller can bracket calls
  * with its own events on the launching stream. */

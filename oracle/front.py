@@ -64,6 +64,8 @@ def lib():
         L.orc_add_medium_homogeneous.argtypes = [c_void_p, c_float, POINTER(c_float), c_float]
         L.orc_add_medium_heterogeneous.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_float)]
         L.orc_set_gradient_sky.argtypes = [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float)]
+        L.orc_set_ibl.argtypes = [c_void_p, c_int, POINTER(c_float), c_int, c_int]
+        L.orc_get_ibl_table.argtypes = [c_void_p, POINTER(c_float)]
         L.orc_medium.argtypes = ([c_void_p, c_int] + [POINTER(c_float)] * 2 + [POINTER(c_uint32)] + [POINTER(c_float)] * 2 +
                                  [POINTER(c_uint64), POINTER(c_float), POINTER(c_uint32), POINTER(c_uint32)] + [POINTER(c_uint32)] +
                                  [POINTER(c_float)] * 2 + [POINTER(c_uint32)] + [POINTER(c_float)] * 2 + [POINTER(c_uint64), POINTER(c_float)] +
@@ -829,8 +831,13 @@ class OracleScene:
             ty = env.child("type").as_str()
             if ty == "gradient_sky":  # gradient_sky.cpp:56-67
                 self.set_gradient_sky(env.child("lower").as_vec3(), env.child("upper").as_vec3(), env.child("up").as_vec3())
+            elif ty == "ibl":  # ibl.cpp:89-102
+                tex = self.add_texture(env.child("tex"))
+                up = np.ascontiguousarray(env.child("up").as_vec3() if env.find("up") is not None else [0, 0, 1], f32)
+                self.lut = (env.int_or("lut_width", 400), env.int_or("lut_height", 200))
+                self.L.orc_set_ibl(self.h, tex, _ptr(up, c_float), self.lut[0], self.lut[1])
             else:
-                raise NotImplementedError(f"oracle: envir_light type {ty}")
+                raise ValueError(f"unknown light type: {ty}")
         w, h = root.child("width").as_int(), root.child("height").as_int()
         self.set_film(w, h)
         cam = root.child("camera")
@@ -914,6 +921,11 @@ class OracleScene:
         return tr
 
     def has_medium(self): return bool(self.L.orc_has_medium(self.h))
+
+    def ibl_table(self):
+        t = np.zeros((self.lut[1], self.lut[0]), f32)
+        self.L.orc_get_ibl_table(self.h, _ptr(t, c_float))
+        return t
 
     def eval_texture2d(self, tex, uv):
         uv = np.ascontiguousarray(uv, f32)

@@ -1203,6 +1203,56 @@ int orc_add_medium_heterogeneous(orc_scene *s, int sigma_t_tex, int albedo_tex, 
     return (int)s->media.size() - 1;
 }
 
+// IBL + EnvirLightSampler::preprocess (light/ibl.cpp:27-36,89-102; light/env_sampler.cpp:22-122): per-tile mean luminance from
+// 256 Hammersley taps (utils/math/hammersley.h), tile solid angle, table = max(0, area * (lum - avg)), normalised; alias table.
+void orc_set_ibl(orc_scene *s, int tex, const float *up, int lut_w, int lut_h) {
+    s->env_type = ENV_IBL;
+    s->ibl_tex = tex;
+    {  // Frame::from_z (utils/math/frame.cpp:45-57), host normalisation
+        V3 nz = host_normalize(V3(up[0], up[1], up[2])), ny;
+        if (1 - std::fabs(nz.x) < 0.1f) ny = cross(nz, V3(0, 1, 0));
+        else ny = cross(nz, V3(1, 0, 0));
+        V3 nx = cross(nz, ny);
+        s->ibl_frame.x = host_normalize(nx); s->ibl_frame.y = host_normalize(ny); s->ibl_frame.z = host_normalize(nz);
+    }
+    s->lut_w = lut_w; s->lut_h = lut_h;
+    const int n_samples = 256;
+    auto radical_inverse = [](uint32_t bits) {
+        bits = (bits << 16u) | (bits >> 16u);
+        bits = ((bits & 0x55555555u) << 1u) | ((bits & 0xAAAAAAAAu) >> 1u);
+        bits = ((bits & 0x33333333u) << 2u) | ((bits & 0xCCCCCCCCu) >> 2u);
+        bits = ((bits & 0x0F0F0F0Fu) << 4u) | ((bits & 0xF0F0F0F0u) >> 4u);
+        bits = ((bits & 0x00FF00FFu) << 8u) | ((bits & 0xFF00FF00u) >> 8u);
+        return bits * 2.3283064365386963e-10f;
+    };
+    std::vector<float> lum((size_t)lut_w * lut_h), area((size_t)lut_w * lut_h);
+#pragma omp parallel for
+    for (int yi = 0; yi < lut_h; ++yi)
+        for (int xi = 0; xi < lut_w; ++xi) {
+            float x0 = float(xi) / lut_w, x1 = float(xi + 1) / lut_w, y0 = float(yi) / lut_h, y1 = float(yi + 1) / lut_h;
+            float lum_sum = 0.0f;
+            for (int i = 0; i < n_samples; ++i) {
+                V2 h{float(i) / n_samples, radical_inverse((uint32_t)i)};
+                V2 ls{1.2f * h.x - 0.1f, 1.2f * h.y - 0.1f};
+                float x = lerp(x0, x1, ls.x), y = lerp(y0, y1, ls.y);
+                lum_sum = lum_sum + orc::lum(s->tex.eval2d(tex, V2{x, y}));
+            }
+            lum[(size_t)yi * lut_w + xi] = lum_sum / n_samples;
+            area[(size_t)yi * lut_w + xi] = std::fabs(2 * PI * (x1 - x0) * (std::cos(PI * y1) - std::cos(PI * y0)));
+        }
+    float lum_area_sum = 0.0f, area_sum = 0.0f;
+    for (size_t i = 0; i < lum.size(); ++i) { lum_area_sum += lum[i] * area[i]; area_sum += area[i]; }
+    const float avg_lum = lum_area_sum / area_sum;
+    for (size_t i = 0; i < lum.size(); ++i) lum[i] = std::max(0.0f, area[i] * (lum[i] - avg_lum));
+    float table_sum = 0.0f;
+    for (float v : lum) table_sum += v;
+    if (table_sum > 1e-3f) { const float ratio = 1 / table_sum; for (auto &v : lum) v *= ratio; }
+    s->ibl_tile_probs = lum;
+    s->ibl_alias.initialize(lum);
+}
+
+void orc_get_ibl_table(orc_scene *s, float *probs) { std::memcpy(probs, s->ibl_tile_probs.data(), sizeof(float) * s->ibl_tile_probs.size()); }
+
 void orc_set_gradient_sky(orc_scene *s, const float *lower, const float *upper, const float *up) {
     s->env_type = ENV_GRADIENT_SKY;
     s->sky_lower = V3(lower[0], lower[1], lower[2]); s->sky_upper = V3(upper[0], upper[1], upper[2]);
