@@ -32,6 +32,10 @@ WORKLOADS = {
     "c2_disney_1080p_256spp": dict(kind="materials", width=1920, height=1080, spp=256),
     # BASELINE.json configs[2]: heterogeneous grid-volume medium with NEE, 1920x1080 (spp not stated => reference default 128)
     "c3_medium_1080p_128spp": dict(kind="medium", width=1920, height=1080, spp=128),
+    # BASELINE.json configs[3]: synthetic 10M-triangle instanced mesh scene (250 x 40,000) with 64 area lights, max depth 16
+    "c4_instanced_10m_1080p_128spp": dict(kind="instanced", width=1920, height=1080, spp=128),
+    # BASELINE.json configs[4]: the C2 scene at 4K, 1024 spp in total, split over the ranks (strong scaling: --gpus 2/4/8)
+    "c5_disney_4k_1024spp": dict(kind="materials", width=3840, height=2160, spp=1024, strong=True),
 }
 DEFAULT_WORKLOAD = "c2_disney_1080p_256spp"
 
@@ -47,6 +51,8 @@ def make_scene(workload, out_dir, spp=None):
         return scenes.make_material_test(out_dir, width=w["width"], height=w["height"], spp=spp or w["spp"])
     if w["kind"] == "medium":
         return scenes.make_medium_scene(out_dir, width=w["width"], height=w["height"], spp=spp or w["spp"])
+    if w["kind"] == "instanced":
+        return scenes.make_instanced_scene(out_dir, width=w["width"], height=w["height"], spp=spp or w["spp"])
     raise ValueError(workload)
 
 
@@ -222,6 +228,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     w = WORKLOADS[args.workload]
     W, H, spp = w["width"], w["height"], (args.spp or w["spp"])
+    strong = bool(w.get("strong"))
+    if strong:  # total work fixed: every rank renders spp / world samples per pixel
+        if spp % world:
+            raise SystemExit(f"bench.py: {spp} spp do not split evenly over {world} ranks")
+        spp //= world
     npix = W * H
     tmp = tempfile.TemporaryDirectory()
     path = make_scene(args.workload, tmp.name, spp=spp * world)  # weak scaling: every rank renders `spp` samples per pixel
@@ -367,7 +378,7 @@ def run_ours(args):
     e2e_value = n_gen / e2e_s / 1e6
     line = {
         "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "mrays_per_s": mrays,
         "config": {"workload": args.workload, "width": W, "height": H, "spp_per_gpu": spp, "state_count": s.info.state_count,
                    "partition": "sample index ranges per rank; NCCL sum-reduce of radiance+weight films to rank 0; resolve on rank 0" if world > 1 else "single GPU",

@@ -205,7 +205,7 @@ def make_material_test(out_dir, width=1920, height=1080, spp=256, state_count=10
     write_obj(os.path.join(out_dir, "sphere.obj"), v, f, uv, n)
     gv, gf, guv = quad((-12, 0, 8), (12, 0, 8), (12, 0, -12), (-12, 0, -12))
     write_obj(os.path.join(out_dir, "ground.obj"), gv, gf, [(u * 6, w * 6) for u, w in guv])
-    lv, lf, luv = quad((-1, 0, -1), (-1, 0, 1), (1, 0, 1), (1, 0, -1))  # normal pointing down (-y)
+    lv, lf, luv = quad((-1, 0, -1), (1, 0, -1), (1, 0, 1), (-1, 0, 1))  # geometric normal cross(b-a, c-a) = -y: emits downwards (mesh lights are one-sided)
     write_obj(os.path.join(out_dir, "lightquad.obj"), lv, lf, luv)
     entities = [{"geometry": _geo("ground"), "material": {"type": "disney", "color": base_t, "metallic": 0.0, "roughness": rough_t, "normal": tex(nmap)}}]
     nx, ny = grid
@@ -362,6 +362,86 @@ def make_ibl_scene(out_dir, width=640, height=360, spp=64, state_count=500000, r
             "renderer": _renderer(spp, state_count, min_depth, max_depth, None),
             "scene": {"entities": entities,
                       "envir_light": {"type": "ibl", "tex": env_tex, "up": [0, 1, 0], "lut_width": lut[0], "lut_height": lut[1]}}}
+    if save:
+        root["post_processors"] = [{"type": "tonemap", "exposure": 1.0}, {"type": "save", "color": save, "gamma": 2.2}]
+    return _dump(out_dir, root)
+
+
+def blob_mesh(rings, segments, seed=13, amplitude=0.18):
+    """A bumpy sphere: the UV sphere displaced along its normals by low-frequency value noise (2*segments*(rings-1) triangles).
+    Per-vertex normals are those of the underlying sphere (smooth shading across the bumps, as with a normal-less scan)."""
+    rng = np.random.default_rng(seed)
+    verts, faces, uvs, nors = uv_sphere(rings, segments)
+    noise = _smooth_noise(rng, max(rings, segments) + 1, 6)
+    out = []
+    row = segments + 1
+    for i, (v, n) in enumerate(zip(verts, nors)):
+        r, s = divmod(i, row)
+        s = s % segments  # the seam column repeats column 0
+        pole = np.sin(np.pi * r / rings)  # no displacement at the poles (all seam vertices coincide there)
+        out.append(np.asarray(n) * (1.0 + amplitude * pole * (noise[r % noise.shape[0], s % noise.shape[1]] - 0.5) * 2.0))
+    return out, faces, uvs, nors
+
+
+def make_instanced_scene(out_dir, width=1920, height=1080, spp=128, state_count=1000000, rings=101, segments=200, n_instances=250,
+                         n_lights=64, min_depth=5, max_depth=16, seed=13, filter=None, save=None):
+    """BASELINE config 4: one mesh (2*segments*(rings-1) = 40,000 triangles at the defaults) instanced n_instances times with
+    random rigid transforms (+ uniform scale) inside a closed room, mixed diffuse / metal materials, n_lights quad mesh-light
+    entities under the ceiling, deep paths (max_depth 16) (250 x 40,000 = 10 M triangles, 64 lights).
+
+    The mesh is written once; every entity after the first refers to the first one's geometry node with `$reference{...}`, so the
+    factory pools it (factory/context.h:205-236) and the OBJ is loaded once."""
+    os.makedirs(out_dir, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    v, f, uv, n = blob_mesh(rings, segments, seed)
+    write_obj(os.path.join(out_dir, "blob.obj"), v, f, uv, n)
+    X, Y, Z = 20.0, 9.0, 20.0  # room half-extent x, height, half-extent z
+    room = {
+        "floor": quad((-X, 0, Z), (X, 0, Z), (X, 0, -Z), (-X, 0, -Z)),
+        "ceil": quad((-X, Y, -Z), (X, Y, -Z), (X, Y, Z), (-X, Y, Z)),
+        "back": quad((-X, 0, -Z), (X, 0, -Z), (X, Y, -Z), (-X, Y, -Z)),
+        "front": quad((X, 0, Z), (-X, 0, Z), (-X, Y, Z), (X, Y, Z)),
+        "left": quad((-X, 0, Z), (-X, 0, -Z), (-X, Y, -Z), (-X, Y, Z)),
+        "right": quad((X, 0, -Z), (X, 0, Z), (X, Y, Z), (X, Y, -Z)),
+    }
+    wall_col = {"floor": [0.6, 0.6, 0.6], "ceil": [0.75, 0.75, 0.75], "back": [0.7, 0.7, 0.65], "front": [0.7, 0.7, 0.65],
+                "left": [0.65, 0.2, 0.15], "right": [0.2, 0.5, 0.25]}
+    entities = []
+    for name, (qv, qf, quv) in room.items():
+        write_obj(os.path.join(out_dir, f"{name}.obj"), qv, qf, quv)
+        entities.append({"geometry": _geo(name), "material": {"type": "diffuse", "color": wall_col[name]}})
+    first_blob = len(entities)
+    for k in range(n_instances):
+        scale = float(rng.uniform(0.7, 1.6))
+        pos = [float(rng.uniform(-X + 2, X - 2)), float(rng.uniform(1.0, Y - 2.5)), float(rng.uniform(-Z + 2, Z - 6))]
+        axis = rng.normal(size=3)
+        axis = (axis / np.linalg.norm(axis)).tolist()
+        col = [float(c) for c in rng.uniform(0.25, 0.9, 3)]
+        if k % 3 == 2:
+            mat = {"type": "metal", "color": col, "roughness": float(rng.uniform(0.1, 0.5))}
+        else:
+            mat = {"type": "diffuse", "color": col}
+        geo = _geo("blob") if k == 0 else "$reference{$root/scene/entities/%d/geometry}" % first_blob
+        entities.append({"geometry": geo, "material": mat,
+                         "local_to_world": [{"scale": [scale, scale, scale]}, {"rotate": {"axis": axis, "angle": {"deg": float(rng.uniform(0, 360))}}},
+                                            {"translate": pos}]})
+    lv, lf, luv = quad((-1, 0, -1), (1, 0, -1), (1, 0, 1), (-1, 0, 1))  # geometric normal cross(b-a, c-a) = -y: emits downwards (mesh lights are one-sided)
+    write_obj(os.path.join(out_dir, "lightquad.obj"), lv, lf, luv)
+    side = int(np.ceil(np.sqrt(n_lights)))
+    first_light = len(entities)
+    for k in range(n_lights):
+        i, j = k % side, k // side
+        lx = (i + 0.5) / side * 2 * (X - 1.5) - (X - 1.5)
+        lz = (j + 0.5) / side * 2 * (Z - 1.5) - (Z - 1.5)
+        inten = [float(c) for c in (14.0 + 8.0 * rng.random(3))]
+        geo = _geo("lightquad") if k == 0 else "$reference{$root/scene/entities/%d/geometry}" % first_light
+        entities.append({"geometry": geo, "material": {"type": "diffuse", "color": [0.0, 0.0, 0.0]},
+                         "local_to_world": [{"scale": [0.8, 1.0, 0.8]}, {"translate": [lx, Y - 0.05, lz]}],
+                         "light": {"type": "mesh_light", "intensity": inten}})
+    root = {"width": width, "height": height,
+            "camera": {"type": "pinhole", "eye": [0, 5.0, Z - 0.5], "dst": [0, 3.2, 0], "up": [0, 1, 0], "fov_y": {"deg": 55}},
+            "renderer": _renderer(spp, state_count, min_depth, max_depth, filter),
+            "scene": {"entities": entities}}
     if save:
         root["post_processors"] = [{"type": "tonemap", "exposure": 1.0}, {"type": "save", "color": save, "gamma": 2.2}]
     return _dump(out_dir, root)
