@@ -58,53 +58,68 @@ def make_scene(workload, out_dir, spp=None):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """Samples SM clocks / throttle reasons during the timed region (B200_PROFILING.md recipe) through NVML in a
+    background thread (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; an external
+    `nvidia-smi -lms 100` loop was measured to stall kernel launches for 100+ ms at a time -- profiles/r1h_diag_step.log)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    PERIOD_S = 0.25
 
     def __init__(self, gpu_index=0):
-        self.rows = []
-        self.proc = None
         self.gpu_index = gpu_index
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.thread = None
+        self._stop = threading.Event()
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if self.gpu_index < len(ids) and ids[self.gpu_index].isdigit():
+                return int(ids[self.gpu_index])
+        return self.gpu_index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu_index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def _loop(self):
+        nv = self.nv
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", 0x8), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", 0x20), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", 0x4))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mx.append(self.max_sm)
+                if get_reasons is not None:
+                    bits = int(get_reasons(self.h))
+                    for name, attr, default in names:
+                        if bits & int(getattr(nv, attr, default)):
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.PERIOD_S)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self._stop.set()
+        self.thread.join(timeout=2)
+        if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        hi = sorted(sm)[len(sm) // 2:]  # samples under load are the upper half (the GPU idles between steps)
-        return {"sm_mhz": float(np.median(hi)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        hi = sorted(self.sm)[len(self.sm) // 2:]  # samples under load are the upper half (the GPU idles between steps)
+        return {"sm_mhz": float(np.median(hi)), "sm_max_mhz": float(max(self.mx)), "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "NVML, %.2f s period" % self.PERIOD_S}
 
 
 # ------------------------------------------------------------------------------------------------ algorithmic bytes
@@ -237,7 +252,7 @@ def run_ours(args):
     tmp = tempfile.TemporaryDirectory()
     path = make_scene(args.workload, tmp.name, spp=spp * world)  # weak scaling: every rank renders `spp` samples per pixel
     s = api.Scene(path, state_count=args.state_count)
-    s.set_profiling(True)
+    s.set_profiling(False)  # the timed steps carry no per-stage events; the stage breakdown comes from a separate profiled pass
     stream = torch.cuda.ExternalStream(s.stream_handle())
     from btrc_b200 import partition
 
@@ -311,6 +326,27 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
 
+    # ---- stage breakdown: the same steps again with one CUDA event between consecutive kernels (not part of `value`)
+    s.set_profiling(True)
+    prof_steps = min(args.steps, 3)
+    pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(prof_steps)]
+    stage_ms = None
+    prof_iters = 0
+    for k in range(prof_steps):
+        flush.fill_(k & 0xff)
+        torch.cuda.synchronize()
+        pev[k][0].record(stream)
+        st = step()
+        pev[k][1].record(stream)
+        torch.cuda.synchronize()
+        if stage_ms is None:
+            stage_ms = {key: 0.0 for key in st["stage_ms"]}
+        for kk, vv in st["stage_ms"].items():
+            stage_ms[kk] += vv
+        prof_iters += st["n_iter"]
+    prof_ms = sum(a.elapsed_time(b) for a, b in pev)
+    s.set_profiling(False)
+
     # ---- end to end through the public API with host buffers
     barrier()
     e2e_t0 = time.perf_counter()
@@ -343,16 +379,18 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     sb = stage_bytes({k: agg[k] for k in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss", "n_splat")}, bvh,
                      has_medium=bool(s.info.has_medium))
-    iters = max(agg["n_iter"], 1)
+    iters = max(prof_iters, 1)
     stages = {}
     sb["bookkeeping"] = 0
+    scale = prof_steps / args.steps  # the byte totals cover K timed steps, the stage times `prof_steps` identical ones
     for name in ("generate", "trace", "medium", "shade", "shadow", "bookkeeping"):
-        ms = agg["stage_ms"][name]
+        ms = stage_ms[name]
         if name == "medium" and not s.info.has_medium:
             continue
-        gbs = sb[name] / (ms / 1e3) / 1e9 if ms > 0 else 0.0
-        stages[name] = {"ms_total": ms, "launches": iters, "ms_per_launch": ms / iters, "alg_bytes_per_launch": sb[name] / iters,
-                        "achieved_gbs": gbs, "frac": gbs / peak, "share_of_step": ms / dev_ms}
+        nbytes = sb[name] * scale
+        gbs = nbytes / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+        stages[name] = {"ms_total": ms, "launches": iters, "ms_per_launch": ms / iters, "alg_bytes_per_launch": nbytes / iters,
+                        "achieved_gbs": gbs, "frac": gbs / peak, "share_of_step": ms / prof_ms}
     dom = max((k for k in stages if k != "bookkeeping"), key=lambda k: stages[k]["ms_total"])
     roofline = {"kernel": dom + "_kernel",
                 "bound": "hbm", "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"],
@@ -382,7 +420,8 @@ def run_ours(args):
         "data": "synthetic", "mrays_per_s": mrays,
         "config": {"workload": args.workload, "width": W, "height": H, "spp_per_gpu": spp, "state_count": s.info.state_count,
                    "partition": "sample index ranges per rank; NCCL sum-reduce of radiance+weight films to rank 0; resolve on rank 0" if world > 1 else "single GPU",
-                   "timing": "CUDA events on the renderer's stream per step, max over ranks; 256 MB L2 flush (untimed) between steps",
+                   "timing": "CUDA events on the renderer's stream per step, max over ranks; 256 MB L2 flush (untimed) between steps; "
+                             "roofline_stages from a separate pass of %d identical steps with one CUDA event between kernels (%.1f ms/step)" % (prof_steps, prof_ms / prof_steps),
                    "wall_ms_per_step_incl_flush": wall / args.steps * 1e3},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": 160, "d2h_bytes_per_step": int(npix * 16 + 160 * (n_iter / args.steps / world)),
@@ -406,7 +445,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--state-count", type=int, default=2097152)
+    ap.add_argument("--state-count", type=int, default=8388608,
+                    help="path-state pool (the renderer's `state_count` parameter); 8 Mi states = 2.4 GB of queues (profiles/r1h_sweep_pool.log)")
     ap.add_argument("--spp", type=int, default=0, help="override the workload's samples per pixel (profiling runs); reported in config")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (roofline bvh statistics, cpu_baseline): profiler runs")
     args = ap.parse_args()
