@@ -110,6 +110,10 @@ class ClockSampler:
                 pass
             self._stop.wait(self.PERIOD_S)
 
+    def reset(self):
+        """Drops the samples taken so far (warm-up): only the timed region counts."""
+        self.sm, self.mx, self.reasons = [], [], set()
+
     def stop(self):
         if self.thread is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
@@ -292,11 +296,14 @@ def run_ours(args):
             color_host.copy_(color_dev, non_blocking=False)
         return st
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    # NVML is initialised before the warm-up steps (its start-up takes driver locks that stall launches for ~100 ms)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if rank == 0:
+        sampler.reset()
 
     # ---- timed region: K device-resident steps, CUDA events on the renderer's stream, L2 flushed between steps
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]

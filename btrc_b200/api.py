@@ -14,7 +14,7 @@ from ctypes import POINTER, byref, c_char_p, c_double, c_float, c_int, c_int32, 
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbtrc_b200.so")
+LIB_PATH = os.environ.get("BTRC_B200_LIB") or os.path.join(_HERE, "libbtrc_b200.so")  # the override serves A/B builds of the same library
 
 HOST, DEVICE = 0, 1
 

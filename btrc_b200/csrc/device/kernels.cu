@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kBlock) trace_kernel(SceneDevice scene, PathQu
         const bool valid = i < n;
         float4 o4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d4 = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
         if (valid) { o4 = q.ray_o[i]; d4 = q.ray_d[i]; }
-        const HitRec h = traverse_bvh2<false, true>(scene.bvh, xyz(o4), xyz(d4), d4.w, valid);
+        const HitRec h = traverse_bvh2<false, true>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w, valid);
         int cls = 0;
         if (valid) {
             const int inst = store_hit(scene.bvh, h, i, hq.flag, hq.detail);
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kBlock) trace_batch_kernel(SceneDevice scene, 
                                                             uint32_t *flag, uint4 *detail) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 o4 = ray_o[i], d4 = ray_d[i];
-        const HitRec h = traverse_bvh2<false>(scene.bvh, xyz(o4), xyz(d4), d4.w);
+        const HitRec h = traverse_bvh2<false>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w);
         if (h.slot < 0) detail[i] = make_uint4(0, 0, 0, 0);
         store_hit(scene.bvh, h, i, flag, detail);
     }
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kBlock) trace_batch_kernel(SceneDevice scene, 
 __global__ void __launch_bounds__(kBlock) anyhit_batch_kernel(SceneDevice scene, const float4 *ray_o, const float4 *ray_d, int n, uint8_t *occluded) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 o4 = ray_o[i], d4 = ray_d[i];
-        occluded[i] = traverse_bvh2<true>(scene.bvh, xyz(o4), xyz(d4), d4.w).slot >= 0 ? 1 : 0;
+        occluded[i] = traverse_bvh2<true>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w).slot >= 0 ? 1 : 0;
     }
 }
 
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(kBlock) shadow_kernel(SceneDevice scene, Rende
         const bool valid = i < n;
         float4 o4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d4 = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
         if (valid) { o4 = sq.ray_o[i]; d4 = sq.ray_d[i]; }
-        const HitRec h = traverse_bvh2<true, true>(scene.bvh, xyz(o4), xyz(d4), d4.w, valid);
+        const HitRec h = traverse_bvh2<true, true>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w, valid);
         if (valid && h.slot < 0) {  // unoccluded: the reference's miss program (shadow.cpp:39-74)
             const float4 b4 = sq.beta_li[i];
             f3 v = xyz(b4);

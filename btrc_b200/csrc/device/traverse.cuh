@@ -7,8 +7,22 @@
 // Triangle test: Moeller-Trumbore in the exact operation order of lib/bvh/include/bvh/triangle.hpp:95-116, with
 // round-to-nearest intrinsics (no FMA contraction), so t/u/v are bit-identical to the CPU oracle.
 // Tie rule: smallest t, then smallest (instance, primitive) -- independent of traversal order.
+//
+// The file only depends on <cuda_runtime.h> vector types, common/types.h and a handful of intrinsics, so that tests/ can
+// compile the very same function for the host (tests/host/host_traverse.cpp supplies the intrinsics) and check it
+// against the oracle without a GPU.  BTRC_TRAV_QUAL is the only switch; the product build never defines it.
 #pragma once
-#include "dev_math.cuh"
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../common/types.h"
+
+#ifndef BTRC_TRAV_QUAL
+#define BTRC_TRAV_QUAL __device__ __forceinline__
+#endif
+#ifndef BTRC_TRAV_COUNT
+#define BTRC_TRAV_COUNT(which)  // host test harness only: traversal-step / triangle-test statistics
+#endif
 
 namespace btrc {
 
@@ -17,19 +31,20 @@ struct HitRec {
     int slot;  // triangle slot in BvhDevice::tris, -1 = miss
 };
 
-__device__ __forceinline__ float dot_rn(float ax, float ay, float az, float bx, float by, float bz) {
+BTRC_TRAV_QUAL float dot_rn(float ax, float ay, float az, float bx, float by, float bz) {
     return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
 }
 
 // returns true when the triangle is hit with t in [0, tmax]
-__device__ __forceinline__ bool tri_test(const float4 *__restrict__ tri, f3 o, f3 d, float tmax, float &t, float &u, float &v) {
-    const float4 a = ldg4(tri), b = ldg4(tri + 1), c4 = ldg4(tri + 2);  // (p0|n.x) (e1|n.y) (e2|n.z)
-    const float cx = __fsub_rn(a.x, o.x), cy = __fsub_rn(a.y, o.y), cz = __fsub_rn(a.z, o.z);
+BTRC_TRAV_QUAL bool tri_test(const float4 *__restrict__ tri, float ox, float oy, float oz, float dx, float dy, float dz, float tmax,
+                             float &t, float &u, float &v) {
+    const float4 a = __ldg(tri), b = __ldg(tri + 1), c4 = __ldg(tri + 2);  // (p0|n.x) (e1|n.y) (e2|n.z)
+    const float cx = __fsub_rn(a.x, ox), cy = __fsub_rn(a.y, oy), cz = __fsub_rn(a.z, oz);
     // r = cross(d, c)
-    const float rx = __fsub_rn(__fmul_rn(d.y, cz), __fmul_rn(d.z, cy));
-    const float ry = __fsub_rn(__fmul_rn(d.z, cx), __fmul_rn(d.x, cz));
-    const float rz = __fsub_rn(__fmul_rn(d.x, cy), __fmul_rn(d.y, cx));
-    const float det = dot_rn(a.w, b.w, c4.w, d.x, d.y, d.z);
+    const float rx = __fsub_rn(__fmul_rn(dy, cz), __fmul_rn(dz, cy));
+    const float ry = __fsub_rn(__fmul_rn(dz, cx), __fmul_rn(dx, cz));
+    const float rz = __fsub_rn(__fmul_rn(dx, cy), __fmul_rn(dy, cx));
+    const float det = dot_rn(a.w, b.w, c4.w, dx, dy, dz);
     const float inv_det = __fdiv_rn(1.0f, det);
     u = __fmul_rn(dot_rn(rx, ry, rz, c4.x, c4.y, c4.z), inv_det);
     v = __fmul_rn(dot_rn(rx, ry, rz, b.x, b.y, b.z), inv_det);
@@ -41,7 +56,7 @@ __device__ __forceinline__ bool tri_test(const float4 *__restrict__ tri, f3 o, f
     return false;
 }
 
-__device__ __forceinline__ bool id_less(const uint2 *__restrict__ ids, int a, int b) {
+BTRC_TRAV_QUAL bool id_less(const uint2 *__restrict__ ids, int a, int b) {
     const uint2 ia = __ldg(ids + a), ib = __ldg(ids + b);
     return ia.x != ib.x ? ia.x < ib.x : ia.y < ib.y;
 }
@@ -52,17 +67,17 @@ constexpr int kStackSize = 64;
 // every descend-to-leaf / process-leaf round reconverges the warp (classic while-while), otherwise lanes drift apart and
 // the node loop and the leaf loop are issued separately for a handful of lanes each.
 template <bool ANY_HIT, bool CONVERGE = false>
-__device__ __forceinline__ HitRec traverse_bvh2(const BvhDevice &bvh, f3 o, f3 d, float tmax, bool active = true) {
+BTRC_TRAV_QUAL HitRec traverse_bvh2(const BvhDevice &bvh, float ox, float oy, float oz, float dx, float dy, float dz, float tmax, bool active = true) {
     HitRec best;
     best.t = tmax; best.u = 0.0f; best.v = 0.0f; best.slot = -1;
 
     // A zero direction component would give inf * 0 = NaN in the slab test; clamp it to a tiny finite slope instead
     // (the slab then evaluates to +-huge with the sign of (plane - origin), which is the exact answer for a parallel ray).
     constexpr float kTiny = 1e-20f;
-    const float idx = 1.0f / (fabsf(d.x) > kTiny ? d.x : copysignf(kTiny, d.x));
-    const float idy = 1.0f / (fabsf(d.y) > kTiny ? d.y : copysignf(kTiny, d.y));
-    const float idz = 1.0f / (fabsf(d.z) > kTiny ? d.z : copysignf(kTiny, d.z));
-    const float oox = o.x * idx, ooy = o.y * idy, ooz = o.z * idz;
+    const float idx = 1.0f / (fabsf(dx) > kTiny ? dx : copysignf(kTiny, dx));
+    const float idy = 1.0f / (fabsf(dy) > kTiny ? dy : copysignf(kTiny, dy));
+    const float idz = 1.0f / (fabsf(dz) > kTiny ? dz : copysignf(kTiny, dz));
+    const float oox = ox * idx, ooy = oy * idy, ooz = oz * idz;
 
     int stack[kStackSize];
     int sp = 0;
@@ -74,7 +89,8 @@ __device__ __forceinline__ HitRec traverse_bvh2(const BvhDevice &bvh, f3 o, f3 d
         // descend through inner nodes
         while (cur >= 0 && cur != SENTINEL) {
             const float4 *node = bvh.nodes + 4 * (size_t)cur;
-            const float4 n0 = ldg4(node), n1 = ldg4(node + 1), nz = ldg4(node + 2), meta = ldg4(node + 3);
+            const float4 n0 = __ldg(node), n1 = __ldg(node + 1), nz = __ldg(node + 2), meta = __ldg(node + 3);
+            BTRC_TRAV_COUNT(0);
             // slabs; NaN (0 * inf) lanes drop out of fminf/fmaxf, which is the conservative outcome
             const float c0lox = fmaf(n0.x, idx, -oox), c0hix = fmaf(n0.y, idx, -oox);
             const float c0loy = fmaf(n0.z, idy, -ooy), c0hiy = fmaf(n0.w, idy, -ooy);
@@ -104,7 +120,8 @@ __device__ __forceinline__ HitRec traverse_bvh2(const BvhDevice &bvh, f3 o, f3 d
             const int first = ref >> 3, count = (ref & 7) + 1;
             for (int s = first; s < first + count; ++s) {
                 float t, u, v;
-                if (tri_test(bvh.tris + 3 * (size_t)s, o, d, best.t, t, u, v)) {
+                BTRC_TRAV_COUNT(1);
+                if (tri_test(bvh.tris + 3 * (size_t)s, ox, oy, oz, dx, dy, dz, best.t, t, u, v)) {
                     if (ANY_HIT) {
                         best.slot = s;
                         if (!CONVERGE) return best;

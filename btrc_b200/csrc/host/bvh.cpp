@@ -133,6 +133,24 @@ BinaryBvh build_binary_bvh(const std::vector<AABB> &boxes, const std::vector<Vec
     return out;
 }
 
+void padded_triangle_boxes(const std::vector<WorldTri> &tris, float coord_max, std::vector<AABB> &boxes, std::vector<Vec3> &centers) {
+    const size_t n = tris.size();
+    boxes.resize(n);
+    centers.resize(n);
+#pragma omp parallel for
+    for (long long i = 0; i < (long long)n; ++i) {
+        const WorldTri &t = tris[i];
+        AABB b;
+        b.extend(t.p0); b.extend(t.p1); b.extend(t.p2);
+        b.extend(t.p0 - t.e1); b.extend(t.p0 + t.e2);
+        const Vec3 ext = b.hi - b.lo;
+        const float pad = 1e-5f * std::max(ext.x, std::max(ext.y, ext.z)) + 4e-7f * coord_max;
+        b.lo = b.lo - Vec3(pad); b.hi = b.hi + Vec3(pad);
+        boxes[i] = b;
+        centers[i] = 0.5f * (b.lo + b.hi);
+    }
+}
+
 // Conservative widening of a box so that the fp32 slab test in the kernel can never cull a triangle that the
 // exact (lib/bvh-arithmetic) triangle test accepts.
 static inline float next_down(float x) { return std::nextafter(x, -3.402823466e+38f); }

@@ -33,6 +33,11 @@ struct WorldTri {
     uint32_t inst, prim;
 };
 
+// Conservative triangle boxes for the builder: the box of the "effective" triangle the kernels test
+// (p0, p0 - e1, p0 + e2) padded by 1e-5 of its extent + 4e-7 of the largest scene coordinate, so that the fp32 slab
+// test can never cull a triangle the exact test accepts.
+void padded_triangle_boxes(const std::vector<WorldTri> &tris, float coord_max, std::vector<AABB> &boxes, std::vector<Vec3> &centers);
+
 struct FlatBvh2 {
     std::vector<float> nodes;     // 16 floats per inner node
     std::vector<float> tris;      // 12 floats per triangle slot

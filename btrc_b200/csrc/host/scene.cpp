@@ -601,25 +601,11 @@ void Scene::commit() {
     // ---- BVH
     auto t0 = std::chrono::steady_clock::now();
     {
-        const size_t n = world_tris.size();
-        std::vector<AABB> boxes(n);
-        std::vector<Vec3> centers(n);
+        std::vector<AABB> boxes;
+        std::vector<Vec3> centers;
         float coord_max = 0;
         for (int a = 0; a < 3; ++a) coord_max = std::max(coord_max, std::max(std::fabs(wb.lo[a]), std::fabs(wb.hi[a])));
-#pragma omp parallel for
-        for (long long i = 0; i < (long long)n; ++i) {
-            const WorldTri &t = world_tris[i];
-            AABB b;
-            b.extend(t.p0); b.extend(t.p1); b.extend(t.p2);
-            // the kernels test the "effective" triangle (p0, p0 - e1, p0 + e2): include it, then pad so that the
-            // fp32 slab test never culls a triangle the exact test accepts ("conservative boxes")
-            b.extend(t.p0 - t.e1); b.extend(t.p0 + t.e2);
-            const Vec3 ext = b.hi - b.lo;
-            const float pad = 1e-5f * std::max(ext.x, std::max(ext.y, ext.z)) + 4e-7f * coord_max;
-            b.lo = b.lo - Vec3(pad); b.hi = b.hi + Vec3(pad);
-            boxes[i] = b;
-            centers[i] = 0.5f * (b.lo + b.hi);
-        }
+        padded_triangle_boxes(world_tris, coord_max, boxes, centers);  // DESIGN.md, "conservative boxes"
         BinaryBvh bb = build_binary_bvh(boxes, centers, 4);
         bvh_depth = tree_depth(bb);
         if (bvh_depth > 60) throw Error("bvh too deep for the traversal stack: " + std::to_string(bvh_depth));

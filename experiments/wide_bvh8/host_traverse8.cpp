@@ -1,0 +1,116 @@
+// TEST INFRASTRUCTURE (never shipped, never on the product path): compiles the product's wide-BVH builder
+// (btrc_b200/csrc/host/bvh.cpp) and the product's traversal function (btrc_b200/csrc/device/traverse8.cuh) for the HOST,
+// so that the exact code the sm_100a kernels run can be checked against the oracle in the CPU-only test suite.
+// The intrinsics the device header uses are supplied here with their IEEE meaning (g++ -ffp-contract=off).
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include <cuda_runtime.h>  // vector types only
+
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __uint_as_float(unsigned x) { float f; std::memcpy(&f, &x, 4); return f; }
+static inline unsigned __float_as_uint(float f) { unsigned x; std::memcpy(&x, &f, 4); return x; }
+static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline bool __any_sync(unsigned, bool p) { return p; }
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
+    const uint64_t src = (uint64_t)a | ((uint64_t)b << 32);
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) r |= (unsigned)((src >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+}
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+
+static thread_local uint64_t g_count[2];
+#define BTRC_TRAV_COUNT(which) (++g_count[which])
+#define BTRC_TRAV_QUAL static inline
+#include "../../btrc_b200/csrc/device/traverse8.cuh"
+#include "../../btrc_b200/csrc/host/bvh.h"
+
+using namespace btrc;
+
+struct HostBvh8 {
+    WideBvh8 w;
+    int binary_depth = 0;
+};
+
+extern "C" {
+
+// verts: n x 9 floats (p0, p1, p2 world space); ids: n x 2 (instance, primitive)
+void *ht_build(int n, const float *verts, const uint32_t *ids) {
+    std::vector<WorldTri> tris(n);
+    AABB wb;
+    for (int i = 0; i < n; ++i) {
+        WorldTri &t = tris[i];
+        t.p0 = Vec3(verts[9 * i], verts[9 * i + 1], verts[9 * i + 2]);
+        t.p1 = Vec3(verts[9 * i + 3], verts[9 * i + 4], verts[9 * i + 5]);
+        t.p2 = Vec3(verts[9 * i + 6], verts[9 * i + 7], verts[9 * i + 8]);
+        t.e1 = t.p0 - t.p1;
+        t.e2 = t.p2 - t.p0;
+        t.n = cross(t.e1, t.e2);
+        t.inst = ids[2 * i];
+        t.prim = ids[2 * i + 1];
+        wb.extend(t.p0); wb.extend(t.p1); wb.extend(t.p2);
+    }
+    float coord_max = 0;
+    for (int a = 0; a < 3; ++a) coord_max = std::max(coord_max, std::max(std::fabs(wb.lo[a]), std::fabs(wb.hi[a])));
+    std::vector<AABB> boxes;
+    std::vector<Vec3> centers;
+    padded_triangle_boxes(tris, coord_max, boxes, centers);
+    BinaryBvh bb = build_binary_bvh(boxes, centers, 3, true);
+    auto *h = new HostBvh8;
+    h->w = build_wide_bvh8(bb, tris);
+    return h;
+}
+
+void ht_free(void *h) { delete static_cast<HostBvh8 *>(h); }
+int ht_num_nodes(void *h) { return (int)(static_cast<HostBvh8 *>(h)->w.nodes.size() / 20); }
+int ht_depth(void *h) { return static_cast<HostBvh8 *>(h)->w.depth; }
+
+// closest hit: out_ids n x 2 (instance, primitive; 0xffffffff on a miss), out_tuv n x 3; steps: node visits in total
+void ht_closest(void *hh, int n, const float *o_med, const float *d_t1, uint32_t *out_ids, float *out_tuv, uint64_t *steps) {
+    const HostBvh8 *h = static_cast<HostBvh8 *>(hh);
+    Bvh8Device b;
+    b.nodes = reinterpret_cast<const uint4 *>(h->w.nodes.data());
+    b.tris = reinterpret_cast<const float4 *>(h->w.tris.data());
+    b.tri_ids = reinterpret_cast<const uint2 *>(h->w.tri_ids.data());
+    b.n_tris = (int)(h->w.tri_ids.size() / 2);
+    uint64_t n_nodes = 0, n_tests = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : n_nodes, n_tests)
+    for (int i = 0; i < n; ++i) {
+        g_count[0] = g_count[1] = 0;
+        const HitRec r = traverse_bvh8<false, false>(b, o_med[4 * i], o_med[4 * i + 1], o_med[4 * i + 2], d_t1[4 * i], d_t1[4 * i + 1],
+                                                     d_t1[4 * i + 2], d_t1[4 * i + 3]);
+        if (r.slot < 0) {
+            out_ids[2 * i] = out_ids[2 * i + 1] = 0xffffffffu;
+            out_tuv[3 * i] = out_tuv[3 * i + 1] = out_tuv[3 * i + 2] = 0;
+        } else {
+            out_ids[2 * i] = h->w.tri_ids[2 * r.slot];
+            out_ids[2 * i + 1] = h->w.tri_ids[2 * r.slot + 1];
+            out_tuv[3 * i] = r.t; out_tuv[3 * i + 1] = r.u; out_tuv[3 * i + 2] = r.v;
+        }
+        n_nodes += g_count[0];
+        n_tests += g_count[1];
+    }
+    if (steps) { steps[0] = n_nodes; steps[1] = n_tests; }
+}
+
+void ht_any(void *hh, int n, const float *o_med, const float *d_t1, uint8_t *occluded) {
+    const HostBvh8 *h = static_cast<HostBvh8 *>(hh);
+    Bvh8Device b;
+    b.nodes = reinterpret_cast<const uint4 *>(h->w.nodes.data());
+    b.tris = reinterpret_cast<const float4 *>(h->w.tris.data());
+    b.tri_ids = reinterpret_cast<const uint2 *>(h->w.tri_ids.data());
+    b.n_tris = (int)(h->w.tri_ids.size() / 2);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int i = 0; i < n; ++i)
+        occluded[i] = traverse_bvh8<true, false>(b, o_med[4 * i], o_med[4 * i + 1], o_med[4 * i + 2], d_t1[4 * i], d_t1[4 * i + 1], d_t1[4 * i + 2],
+                                                 d_t1[4 * i + 3]).slot >= 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+"""The product's BVH builder and traversal function, compiled for the host by tests/host/host_traverse.cpp, against the
+oracle: bit-identical closest hits (instance, primitive, t, u, v) and occlusion on primary, bounce and shadow ray batches.
+Runs without a GPU; the GPU parity tests check the same function inside the sm_100a kernels."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from . import util
+from .util import ROOT, f32
+
+
+@pytest.fixture(scope="module")
+def ht():
+    src = os.path.join(ROOT, "tests", "host", "host_traverse.cpp")
+    out = os.path.join(ROOT, "tests", "host", "_libhosttrav.so")
+    deps = [src, os.path.join(ROOT, "btrc_b200/csrc/host/bvh.cpp"), os.path.join(ROOT, "btrc_b200/csrc/host/bvh.h"),
+            os.path.join(ROOT, "btrc_b200/csrc/device/traverse.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-I/usr/local/cuda/include", src, deps[1], "-o", out],
+                       check=True)
+    L = ctypes.CDLL(out)
+    L.ht_build.restype = ctypes.c_void_p
+    L.ht_build.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    L.ht_free.argtypes = [ctypes.c_void_p]
+    L.ht_num_nodes.argtypes = [ctypes.c_void_p]
+    L.ht_closest.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 5
+    L.ht_any.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 3
+    return L
+
+
+def _build(L, orc):
+    verts, ids = orc.triangles()
+    verts = np.ascontiguousarray(verts, f32)
+    ids = np.ascontiguousarray(ids, np.uint32)
+    h = L.ht_build(verts.shape[0], verts.ctypes.data, ids.ctypes.data)
+    assert h
+    return h
+
+
+def _closest(L, h, o_med, d_t1):
+    o_med = np.ascontiguousarray(o_med, f32); d_t1 = np.ascontiguousarray(d_t1, f32)
+    n = o_med.shape[0]
+    ids = np.zeros((n, 2), np.uint32)
+    tuv = np.zeros((n, 3), f32)
+    L.ht_closest(h, n, o_med.ctypes.data, d_t1.ctypes.data, ids.ctypes.data, tuv.ctypes.data, None)
+    return ids, tuv
+
+
+def _check_closest(L, h, orc, o_med, d_t1):
+    flag, det = orc.closest_hit(o_med, d_t1)
+    ids, tuv = _closest(L, h, o_med, d_t1)
+    hit = ((flag >> 30) & 1).astype(bool)
+    assert np.array_equal(hit, ids[:, 0] != 0xFFFFFFFF)
+    assert np.array_equal(flag[hit] & 0x3FFFFFFF, ids[hit, 0])
+    assert np.array_equal(det[hit, 1], ids[hit, 1])
+    assert np.array_equal(det[hit][:, [0, 2, 3]], tuv[hit].view(np.uint32))
+    return int(hit.sum())
+
+
+def _walk(orc, st, bounces, visit):
+    """Follows the oracle's own path states for a few bounces, calling visit(o_med, d_t1, shadow) on every ray batch."""
+    for _ in range(bounces):
+        if st["o_med"].shape[0] == 0:
+            break
+        visit(st["o_med"], st["d_t1"], False)
+        flag, detail = orc.closest_hit(st["o_med"], st["d_t1"])
+        parts = []
+        if orc.has_medium():
+            st, flag, mo = orc.medium(st, flag, detail)
+            parts.append({k: v[(mo["status"] & 1) != 0] for k, v in mo["next"].items()})
+        sh = orc.shade(st, flag, detail)
+        m = (sh["status"] & 2) != 0
+        if m.any():
+            visit(sh["sh_o_med"][m], sh["sh_d_t1"][m], True)
+        parts.append({k: v[(sh["status"] & 1) != 0] for k, v in sh["next"].items()})
+        st = {k: np.ascontiguousarray(np.concatenate([p[k] for p in parts])) for k in parts[0]}
+
+
+def test_golden_rays_cornell(ht, built, tmp_path):
+    """777,600 primary rays of lib/bvh's benchmark on the fan-triangulated Cornell box (tests/golden): same hits as the oracle."""
+    from oracle import front
+
+    path, _ = util.write_fan_cornell_scene(str(tmp_path))[:2]
+    orc = front.OracleScene(path)
+    h = _build(ht, orc)
+    o_med, d_t1 = util.bvh_benchmark_rays()
+    assert _check_closest(ht, h, orc, o_med, d_t1) > 700000
+    ht.ht_free(h)
+
+
+@pytest.mark.parametrize("kind", ["cornell", "materials"])
+def test_bounce_and_shadow_rays(ht, built, tmp_path, kind):
+    from btrc_b200 import scenes
+    from oracle import front
+
+    if kind == "cornell":
+        path = scenes.make_cornell(str(tmp_path), width=96, height=96, spp=2, state_count=20000)
+    else:
+        path = scenes.make_material_test(str(tmp_path), width=160, height=90, spp=1)
+    orc = front.OracleScene(path)
+    h = _build(ht, orc)
+    assert ht.ht_num_nodes(h) > 0
+    n_rays = [0, 0]
+
+    def visit(o_med, d_t1, shadow):
+        if shadow:
+            occ = np.zeros(o_med.shape[0], np.uint8)
+            o = np.ascontiguousarray(o_med, f32); d = np.ascontiguousarray(d_t1, f32)
+            ht.ht_any(h, o.shape[0], o.ctypes.data, d.ctypes.data, occ.ctypes.data)
+            assert np.array_equal(occ, orc.any_hit(o, d))
+            n_rays[1] += o.shape[0]
+        else:
+            _check_closest(ht, h, orc, o_med, d_t1)
+            n_rays[0] += o_med.shape[0]
+
+    st = orc.generate(0, orc.width * orc.height)
+    _walk(orc, st, 5, visit)
+    assert n_rays[0] > orc.width * orc.height and n_rays[1] > 0
+    ht.ht_free(h)
+
+
+def test_edge_cases(ht, built, tmp_path):
+    """Axis-parallel rays (zero direction components), zero-length and negative intervals, rays starting on geometry."""
+    from btrc_b200 import scenes
+    from oracle import front
+
+    path = scenes.make_cornell(str(tmp_path), width=32, height=32, spp=1, state_count=4096)
+    orc = front.OracleScene(path)
+    h = _build(ht, orc)
+    rng = np.random.default_rng(5)
+    n = 20000
+    o = np.zeros((n, 4), f32)
+    d = np.zeros((n, 4), f32)
+    o[:, :3] = rng.uniform(-1.2, 2.2, (n, 3)).astype(f32)
+    axis = rng.integers(0, 3, n)
+    d[np.arange(n), axis] = rng.choice(np.array([-1, 1], f32), n)
+    d[: n // 2, 3] = np.finfo(f32).max
+    d[n // 2:, 3] = rng.uniform(0, 2, n - n // 2).astype(f32)
+    d[::97, 3] = 0.0
+    d[1::97, [0, 1, 2]] = f32(-0.0) * d[1::97, [0, 1, 2]] + d[1::97, [0, 1, 2]]
+    _check_closest(ht, h, orc, o, d)
+    ht.ht_free(h)
