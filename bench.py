@@ -227,7 +227,7 @@ def run_reference(args):
                          "sample": f"{sample_spp} of {w['spp']} spp per step ({w['width']}x{w['height']}), oracle/liborc.so, OpenMP"},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -440,9 +440,30 @@ def run_ours(args):
         "roofline_stages": stages,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Library chatter on stdout (e.g. the "NCCL version ..." banner) must not pollute the one JSON line: fd 1 is pointed at
+    stderr for the whole run and the result is written to the original stdout at the end."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -457,6 +478,7 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override the workload's samples per pixel (profiling runs); reported in config")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (roofline bvh statistics, cpu_baseline): profiler runs")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -61,16 +61,7 @@ void check_scene(btrc_scene_t *s) {
     if (!s || !s->scene) throw Error("null scene handle");
 }
 
-// Resolve into device scratch, then hand the result to the caller's buffers.
-void resolve_to(btrc_scene_t *s, float *color, float *albedo, float *normal) {
-    Renderer &r = s->r();
-    const size_t bytes = sizeof(float) * 4 * (size_t)s->scene->width * s->scene->height;
-    DeviceBuffer dc(color ? bytes : 0), da(albedo && r.film().albedo ? bytes : 0), dn(normal && r.film().normal ? bytes : 0);
-    r.resolve(dc.as<float>(), da.as<float>(), dn.as<float>());
-    if (color) copy_any(color, dc.ptr, bytes);
-    if (da.ptr) copy_any(albedo, da.ptr, bytes);
-    if (dn.ptr) copy_any(normal, dn.ptr, bytes);
-}
+void resolve_to(btrc_scene_t *s, float *color, float *albedo, float *normal) { s->r().resolve_any(color, albedo, normal); }
 
 struct HostPaths {
     std::vector<float4> ray_o, ray_d, beta, rad, ble;
@@ -229,14 +220,7 @@ int btrc_film_export(btrc_scene_t *s, int memory, float *radiance, float *weight
     return guarded([&] {
         check_scene(s);
         Renderer &r = s->r();
-        // the caller's buffers may be in use on other streams (NCCL, torch): fence on both sides (once per render, not per wave)
-        BTRC_CUDA(cudaDeviceSynchronize());
-        const size_t npix = (size_t)s->scene->width * s->scene->height;
-        if (radiance) copy_any(radiance, r.film().radiance, 16 * npix);
-        if (weight) copy_any(weight, r.film().weight, 4 * npix);
-        if (albedo && r.film().albedo) copy_any(albedo, r.film().albedo, 16 * npix);
-        if (normal && r.film().normal) copy_any(normal, r.film().normal, 16 * npix);
-        BTRC_CUDA(cudaDeviceSynchronize());
+        r.export_film(radiance, weight, albedo, normal);
     });
 }
 
@@ -245,13 +229,7 @@ int btrc_film_import(btrc_scene_t *s, int memory, const float *radiance, const f
     return guarded([&] {
         check_scene(s);
         Renderer &r = s->r();
-        BTRC_CUDA(cudaDeviceSynchronize());
-        const size_t npix = (size_t)s->scene->width * s->scene->height;
-        if (radiance) copy_any(r.film().radiance, radiance, 16 * npix);
-        if (weight) copy_any(r.film().weight, weight, 4 * npix);
-        if (albedo && r.film().albedo) copy_any(r.film().albedo, albedo, 16 * npix);
-        if (normal && r.film().normal) copy_any(r.film().normal, normal, 16 * npix);
-        BTRC_CUDA(cudaDeviceSynchronize());
+        r.import_film(radiance, weight, albedo, normal);
     });
 }
 

@@ -1,12 +1,31 @@
 #include "renderer.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace btrc {
 
 namespace {
 constexpr int kLag = 4;  // iterations kept in flight ahead of the host's view of the counters
+
+// Diagnostics (BTRC_HOST_TRACE=1): reports host-side spans of the render calls that took longer than 5 ms
+struct HostSpan {
+    const char *name;
+    std::chrono::steady_clock::time_point t0;
+    static bool enabled() {
+        static const bool on = std::getenv("BTRC_HOST_TRACE") != nullptr;
+        return on;
+    }
+    explicit HostSpan(const char *n) : name(n) { if (enabled()) t0 = std::chrono::steady_clock::now(); }
+    ~HostSpan() {
+        if (!enabled()) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 5.0) std::fprintf(stderr, "[btrc host trace] %s: %.1f ms\n", name, ms);
+    }
+};
 }
 
 template <typename T>
@@ -52,7 +71,7 @@ Renderer::Renderer(Scene &scene, int state_count_override) : scene_(scene) {
     film_.albedo = scene.renderer.albedo ? alloc<float>(4 * npix) : nullptr;
     film_.normal = scene.renderer.normal ? alloc<float>(4 * npix) : nullptr;
     ctl_ = alloc<WaveCtl>(1);
-    BTRC_CUDA(cudaMallocHost(&ctl_host_, sizeof(WaveCtl) * 8));
+    BTRC_CUDA(cudaMallocHost(&ctl_host_, sizeof(WaveCtl) * 10));  // 8 snapshot slots + upload staging + final counters
     clear_film();
 }
 
@@ -66,6 +85,7 @@ Renderer::~Renderer() {
 }
 
 void Renderer::clear_film() {
+    HostSpan span("clear_film");
     const size_t npix = (size_t)scene_.width * scene_.height;
     BTRC_CUDA(cudaMemsetAsync(film_.radiance, 0, 4 * npix * sizeof(float), stream_));
     BTRC_CUDA(cudaMemsetAsync(film_.weight, 0, npix * sizeof(float), stream_));
@@ -76,13 +96,15 @@ void Renderer::clear_film() {
 
 void Renderer::render_range(long long begin, long long end) {
     if (begin < 0 || end < begin || end > total_paths()) throw Error("render_range: path range out of bounds");
+    HostSpan span_all("render_range");
     const RenderParams params = scene_.render_params();
     WaveCtl init;
     std::memset(&init, 0, sizeof(init));
     init.cursor = begin;
     init.end = end;
     init.pool = pool_;
-    BTRC_CUDA(cudaMemcpyAsync(ctl_, &init, sizeof(init), cudaMemcpyHostToDevice, stream_));
+    ctl_host_[8] = init;  // pinned staging slot: the upload is a true async copy on the renderer's stream
+    BTRC_CUDA(cudaMemcpyAsync(ctl_, &ctl_host_[8], sizeof(init), cudaMemcpyHostToDevice, stream_));
     BTRC_CUDA(cudaEventRecord(ev_begin_, stream_));
 
     const bool has_medium = scene_.dev.has_medium != 0;
@@ -129,11 +151,12 @@ void Renderer::render_range(long long begin, long long end) {
         }
     }
     BTRC_CUDA(cudaEventRecord(ev_end_, stream_));
+    HostSpan span_tail("render_range tail (final sync + counters)");
+    // final counters (the drained iterations after `done` are empty)
+    BTRC_CUDA(cudaMemcpyAsync(&ctl_host_[9], ctl_, sizeof(WaveCtl), cudaMemcpyDeviceToHost, stream_));
     BTRC_CUDA(cudaStreamSynchronize(stream_));
     BTRC_CUDA(cudaGetLastError());
-    // final counters (the drained iterations after `done` are empty)
-    WaveCtl fin;
-    BTRC_CUDA(cudaMemcpy(&fin, ctl_, sizeof(fin), cudaMemcpyDeviceToHost));
+    const WaveCtl fin = ctl_host_[9];
     float ms = 0;
     BTRC_CUDA(cudaEventElapsedTime(&ms, ev_begin_, ev_end_));
     stats_.n_gen += fin.n_gen;
@@ -228,6 +251,54 @@ void Renderer::resolve(float *d_color, float *d_albedo, float *d_normal) {
     if (d_normal && film_.normal) launch_resolve(scene_.width, scene_.height, film_.normal, film_.weight, d_normal, 1, stream_);
     BTRC_CUDA(cudaStreamSynchronize(stream_));
     BTRC_CUDA(cudaGetLastError());
+}
+
+static bool is_device_pointer(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+void Renderer::resolve_any(float *color, float *albedo, float *normal) {
+    HostSpan span("resolve_any");
+    const size_t bytes = sizeof(float) * 4 * (size_t)scene_.width * scene_.height;
+    float *dst[3] = {color, film_.albedo ? albedo : nullptr, film_.normal ? normal : nullptr};
+    const float *src[3] = {film_.radiance, film_.albedo, film_.normal};
+    for (int k = 0; k < 3; ++k) {
+        if (!dst[k]) continue;
+        float *target = dst[k];
+        const bool direct = is_device_pointer(target);
+        if (!direct) {
+            if (!resolve_scratch_[k]) resolve_scratch_[k] = alloc<float>(bytes / sizeof(float));
+            target = resolve_scratch_[k];
+        }
+        launch_resolve(scene_.width, scene_.height, src[k], film_.weight, target, k == 2 ? 1 : 0, stream_);
+        if (!direct) BTRC_CUDA(cudaMemcpyAsync(dst[k], target, bytes, cudaMemcpyDeviceToHost, stream_));
+    }
+    BTRC_CUDA(cudaStreamSynchronize(stream_));
+    BTRC_CUDA(cudaGetLastError());
+}
+
+void Renderer::export_film(float *radiance, float *weight, float *albedo, float *normal) {
+    HostSpan span("export_film");
+    BTRC_CUDA(cudaDeviceSynchronize());
+    const size_t npix = (size_t)scene_.width * scene_.height;
+    if (radiance) BTRC_CUDA(cudaMemcpyAsync(radiance, film_.radiance, 16 * npix, cudaMemcpyDefault, stream_));
+    if (weight) BTRC_CUDA(cudaMemcpyAsync(weight, film_.weight, 4 * npix, cudaMemcpyDefault, stream_));
+    if (albedo && film_.albedo) BTRC_CUDA(cudaMemcpyAsync(albedo, film_.albedo, 16 * npix, cudaMemcpyDefault, stream_));
+    if (normal && film_.normal) BTRC_CUDA(cudaMemcpyAsync(normal, film_.normal, 16 * npix, cudaMemcpyDefault, stream_));
+    BTRC_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Renderer::import_film(const float *radiance, const float *weight, const float *albedo, const float *normal) {
+    HostSpan span("import_film");
+    BTRC_CUDA(cudaDeviceSynchronize());
+    const size_t npix = (size_t)scene_.width * scene_.height;
+    if (radiance) BTRC_CUDA(cudaMemcpyAsync(film_.radiance, radiance, 16 * npix, cudaMemcpyDefault, stream_));
+    if (weight) BTRC_CUDA(cudaMemcpyAsync(film_.weight, weight, 4 * npix, cudaMemcpyDefault, stream_));
+    if (albedo && film_.albedo) BTRC_CUDA(cudaMemcpyAsync(film_.albedo, albedo, 16 * npix, cudaMemcpyDefault, stream_));
+    if (normal && film_.normal) BTRC_CUDA(cudaMemcpyAsync(film_.normal, normal, 16 * npix, cudaMemcpyDefault, stream_));
+    BTRC_CUDA(cudaStreamSynchronize(stream_));
 }
 
 }  // namespace btrc

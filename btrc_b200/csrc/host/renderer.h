@@ -35,6 +35,14 @@ public:
     void render_range(long long begin, long long end);
     // value / weight into caller-provided DEVICE buffers of W*H float4 (albedo/normal may be null).
     void resolve(float *d_color, float *d_albedo, float *d_normal);
+    // The same into buffers in ANY address space: device destinations are written by the resolve kernel itself, host
+    // destinations through a scratch image owned by the renderer (allocated once) and an async copy on the renderer's
+    // stream -- no per-call cudaMalloc/cudaFree and nothing on the legacy default stream.
+    void resolve_any(float *color, float *albedo, float *normal);
+    // Film buffers to / from caller memory in any address space (multi-GPU accumulation): async copies on the renderer's
+    // stream, one device-wide fence first (the caller's buffers may be in use on torch / NCCL streams).
+    void export_film(float *radiance, float *weight, float *albedo, float *normal);
+    void import_film(const float *radiance, const float *weight, const float *albedo, const float *normal);
 
     // ---- stage-level runs on the internal queues (tests / C-ABI stage entry points); n <= state_count
     PathQueue &queue(int k) { return q_[k]; }
@@ -71,6 +79,7 @@ private:
     RenderStats stats_;
     bool profiling_ = false;
     std::vector<cudaEvent_t> prof_events_;
+    float *resolve_scratch_[3]{};   // lazily allocated W*H float4 images for host destinations
     template <typename T> T *alloc(size_t n);
 };
 
