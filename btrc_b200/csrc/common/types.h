@@ -79,6 +79,17 @@ struct MediumDesc {
     float inv_max_density;                  // 1 / max(max sigma_t, 0.001)   (hetergeneous.cpp:33-34)
 };
 
+// One entry of the scene file's "volumes" array (factory/scene.cpp:57-80): a parallelepiped o + u x + v y + w z, u,v,w in
+// [0,1], with 3-D density and albedo textures addressed by (u,v,w).  core/volume.h:9-45 + core/volume/bvh.h:24-30.
+struct VolumePrim {
+    float o[3];
+    float x[3], y[3], z[3];
+    float x_div_x2[3], y_div_y2[3], z_div_z2[3];   // x / |x|^2 ... (inside test, boundary crossings)
+    float inv_x2, inv_y2, inv_z2;                  // 1 / |x|^2 ... (world_pos_to_uvw, core/volume.cpp:42-49)
+    int sigma_t_tex, albedo_tex;                   // 3-D texture ids
+    float max_sigma_t;                             // Texture3D::get_max_float of sigma_t
+};
+
 enum EnvType : int { ENV_NONE = 0, ENV_GRADIENT_SKY = 1, ENV_IBL = 2 };
 
 struct EnvLight {  // builtin/light/gradient_sky.cpp, ibl.cpp + env_sampler.cpp
@@ -165,6 +176,8 @@ struct SceneDevice {
     const TexOp *tex_ops;
     const Texture3DDesc *textures3d;
     const MediumDesc *media;
+    const VolumePrim *vol_prims;    // members of the volume-primitive medium (the last entry of `media`)
+    int n_vol_prims;
     const LightInfo *lights;        // area lights
     const uint8_t *instance_class;  // shade class of each instance (1 + material type)
     int n_instances;

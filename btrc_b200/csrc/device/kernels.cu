@@ -302,12 +302,13 @@ __global__ void __launch_bounds__(kBlock) medium_kernel(SceneDevice scene, Rende
             const MediumDesc &medium = scene.media[medium_id];
             const MediumSample ms = medium_sample(scene, medium, o, medium_end, sampler);
             const f3 unscatter_tr = medium_tr(scene, medium, o, medium_end, sampler);
-            if (medium.type != MED_VOLPRIM) {
+            const bool tracked = medium.type != MED_VOLPRIM || scene.n_vol_prims > 0;  // an empty volume-primitive medium: Tr = 1, no draws
+            if (tracked) {
                 const float4 ble4 = q.ble[i];
                 q.ble[i] = make4(xyz(ble4) * unscatter_tr, ble4.w);
             }
             if (!ms.scattered) {
-                if (medium.type != MED_VOLPRIM) q.rng[i] = make_ulonglong2(sampler.rng.state, sampler.rng.inc);
+                if (tracked) q.rng[i] = make_ulonglong2(sampler.rng.state, sampler.rng.inc);
             } else {
                 hq.flag[i] = flag | kFlagHasScattering;
                 f3 beta = xyz(beta4);  // throughput of both media is one

@@ -332,16 +332,186 @@ __device__ __forceinline__ f3 medium_uvw(const MediumDesc &m, f3 p) {  // Transf
     return m.has_transform ? xf_point(m.world_to_local, p) : p;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Volume primitives: VolumePrimitiveMedium::sample / tr (core/volume.cpp:112-195), boundary crossings and overlap
+// queries (core/volume/bvh.cpp:146-326), delta / ratio tracking inside an overlap (core/volume/aggregate.cpp:129-253).
+// The reference's per-overlap generated code + trie (volume/indexing.cpp) and its box BVH only select which
+// primitives contain a point; closest boundary (a minimum) and overlap (a set) are order independent, so the kernel
+// loops over the primitive table.  Overlap members are visited in creation order; more than 4 overlapping primitives:
+// the four smallest ids (the reference: first four in its BVH's traversal order).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxVolOverlap = 4;  // volume/bvh.h:11
+
+__device__ __forceinline__ f3 ld3(const float *p) { return f3(p[0], p[1], p[2]); }
+
+__device__ __forceinline__ f3 vol_world_to_uvw(const VolumePrim &v, f3 p) {  // core/volume.cpp:42-49
+    const f3 op = p - ld3(v.o);
+    return f3(dot(op, ld3(v.x)) * v.inv_x2, dot(op, ld3(v.y)) * v.inv_y2, dot(op, ld3(v.z)) * v.inv_z2);
+}
+
+// volume/bvh.cpp:281-326: nearest boundary crossing (entry, else exit) on p + t d with t in (0, t_max); -1 if none
+__device__ __forceinline__ float vol_prim_intersect(f3 p, f3 d, float t_max, const VolumePrim &prim) {
+    const f3 op = p - ld3(prim.o);
+    float t0 = 0.0f, t1 = t_max;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const f3 ax = ld3(a == 0 ? prim.x_div_x2 : (a == 1 ? prim.y_div_y2 : prim.z_div_z2));
+        const float opd = dot(op, ax), dd = dot(d, ax);
+        const float nd = (0.0f - opd) / dd, fd = (1.0f - opd) / dd;
+        t0 = fmaxf(t0, fminf(nd, fd));
+        t1 = fminf(t1, fmaxf(nd, fd));
+    }
+    if (t0 > t1) return -1.0f;
+    if (t0 > 0.0f) return t0;
+    if (t1 < t_max) return t1;
+    return -1.0f;
+}
+
+__device__ __forceinline__ bool vol_find_closest_intersection(const SceneDevice &scene, f3 a, f3 b, f3 &out) {  // volume/bvh.cpp:146-214
+    const f3 dir = b - a;
+    float final_t = kMaxFloat, t_max = 1.0f;
+    for (int i = 0; i < scene.n_vol_prims; ++i) {
+        const float t = vol_prim_intersect(a, dir, t_max, scene.vol_prims[i]);
+        if (t >= 0.0f) { final_t = fminf(final_t, t); t_max = final_t; }
+    }
+    if (final_t > 10.0f) return false;
+    out = a * (1.0f - final_t) + b * final_t;
+    return true;
+}
+
+struct VolOverlap {
+    int data[kMaxVolOverlap];
+    int count;
+};
+
+__device__ __forceinline__ VolOverlap vol_get_overlap(const SceneDevice &scene, f3 pos) {  // volume/bvh.cpp:216-279
+    VolOverlap r;
+    r.count = 0;
+    for (int i = 0; i < scene.n_vol_prims && r.count < kMaxVolOverlap; ++i) {
+        const VolumePrim &prim = scene.vol_prims[i];
+        const f3 op = pos - ld3(prim.o);
+        const float u = dot(op, ld3(prim.x_div_x2)), v = dot(op, ld3(prim.y_div_y2)), w = dot(op, ld3(prim.z_div_z2));
+        if (0.0f <= u && u <= 1.0f && 0.0f <= v && v <= 1.0f && 0.0f <= w && w <= 1.0f) {
+#pragma unroll
+            for (int k = 0; k < kMaxVolOverlap; ++k) if (k == r.count) r.data[k] = i;  // register-resident list
+            r.count++;
+        }
+    }
+    return r;
+}
+
+__device__ __forceinline__ int vol_member(const VolOverlap &ov, int k) {
+    int id = ov.data[0];
+#pragma unroll
+    for (int j = 1; j < kMaxVolOverlap; ++j) if (j == k) id = ov.data[j];
+    return id;
+}
+
+__device__ __forceinline__ float vol_overlap_inv_max_density(const SceneDevice &scene, const VolOverlap &ov) {  // aggregate.cpp:121-127
+    float m = 0.0f;
+    for (int k = 0; k < ov.count; ++k) m += scene.vol_prims[vol_member(ov, k)].max_sigma_t;
+    return 1.0f / fmaxf(m, 0.01f);
+}
+
+// density sum of the overlap's members at parameter tf of segment a -> b (members' uvw are affine in the position)
+__device__ __forceinline__ float vol_density_sum(const SceneDevice &scene, const VolOverlap &ov, f3 a, f3 b, float tf) {
+    float density_sum = 0.0f;
+    for (int k = 0; k < ov.count; ++k) {
+        const VolumePrim &v = scene.vol_prims[vol_member(ov, k)];
+        const f3 uvw = vol_world_to_uvw(v, a) * (1.0f - tf) + vol_world_to_uvw(v, b) * tf;
+        density_sum = density_sum + eval_texture3d(scene, v.sigma_t_tex, uvw).x;
+    }
+    return density_sum;
+}
+
 struct MediumSample {
     bool scattered;
     f3 position;
     PhaseShader shader;
 };
 
+// aggregate.cpp:129-199 (delta tracking over the summed densities; albedo = density-weighted mix, g = 0)
+__device__ __forceinline__ void vol_sample_scattering(const SceneDevice &scene, const VolOverlap &ov, f3 a, f3 b, Sampler &sampler, MediumSample &r) {
+    const float inv_max_density = vol_overlap_inv_max_density(scene, ov);
+    const float t_max = length(b - a);
+    float t = 0.0f;
+    for (;;) {
+        const float dt = -logf(1.0f - sampler.get1d()) * inv_max_density;
+        t = t + dt;
+        if (t >= t_max) { r.scattered = false; return; }
+        const float tf = t / t_max;
+        const float density_sum = vol_density_sum(scene, ov, a, b, tf);
+        if (sampler.get1d() < density_sum * inv_max_density) {
+            r.scattered = true;
+            r.position = a * (1.0f - tf) + b * tf;
+            f3 albedo(0.0f);
+            for (int k = 0; k < ov.count; ++k) {
+                const VolumePrim &v = scene.vol_prims[vol_member(ov, k)];
+                const f3 uvw = vol_world_to_uvw(v, a) * (1.0f - tf) + vol_world_to_uvw(v, b) * tf;
+                const float weight = eval_texture3d(scene, v.sigma_t_tex, uvw).x / density_sum;
+                albedo = albedo + weight * eval_texture3d(scene, v.albedo_tex, uvw);
+            }
+            r.shader.g = 0.0f;
+            r.shader.color = albedo;
+            return;
+        }
+    }
+}
+
+// aggregate.cpp:201-253 (ratio tracking)
+__device__ __forceinline__ float vol_tr_in_overlap(const SceneDevice &scene, const VolOverlap &ov, f3 a, f3 b, Sampler &sampler) {
+    const float inv_max_density = vol_overlap_inv_max_density(scene, ov);
+    const float t_max = length(b - a);
+    float result = 1.0f, t = 0.0f;
+    for (;;) {
+        const float dt = -logf(1.0f - sampler.get1d()) * inv_max_density;
+        t = t + dt;
+        if (t >= t_max) break;
+        result = result * (1.0f - vol_density_sum(scene, ov, a, b, t / t_max) * inv_max_density);
+    }
+    return result;
+}
+
+__device__ __noinline__ MediumSample volprim_sample(const SceneDevice &scene, f3 a, f3 b, Sampler &sampler) {  // core/volume.cpp:112-160
+    MediumSample r;
+    r.scattered = false;
+    if (scene.n_vol_prims == 0) return r;
+    f3 o = a;
+    const f3 d = normalize(b - a);
+    for (;;) {
+        if (dot(b - o, d) <= 0.0f || length_square(b - o) < 0.00001f) { r.scattered = false; break; }
+        f3 inct_pos;
+        if (!vol_find_closest_intersection(scene, o, b, inct_pos)) inct_pos = b;
+        const VolOverlap ov = vol_get_overlap(scene, 0.5f * (o + inct_pos));
+        if (ov.count != 0) {
+            vol_sample_scattering(scene, ov, o, inct_pos, sampler, r);
+            if (r.scattered) break;
+        }
+        o = inct_pos + 0.001f * d;
+    }
+    return r;
+}
+
+__device__ __noinline__ float volprim_tr(const SceneDevice &scene, f3 a, f3 b, Sampler &sampler) {  // core/volume.cpp:162-195
+    float result = 1.0f;
+    if (scene.n_vol_prims == 0) return result;
+    f3 o = a;
+    const f3 d = normalize(b - a);
+    for (;;) {
+        if (dot(b - o, d) <= 0.0f || length_square(b - o) < 0.0001f) break;
+        f3 inct_pos;
+        if (!vol_find_closest_intersection(scene, o, b, inct_pos)) inct_pos = b;
+        const VolOverlap ov = vol_get_overlap(scene, 0.5f * (o + inct_pos));
+        if (ov.count != 0) result = result * vol_tr_in_overlap(scene, ov, o, inct_pos, sampler);
+        o = inct_pos + 0.001f * d;
+    }
+    return result;
+}
+
 __device__ __forceinline__ MediumSample medium_sample(const SceneDevice &scene, const MediumDesc &m, f3 a, f3 b, Sampler &sampler) {
     MediumSample r;
     r.scattered = false;
-    if (m.type == MED_VOLPRIM) return r;  // no volume primitives (core/volume.cpp:124-129)
+    if (m.type == MED_VOLPRIM) return volprim_sample(scene, a, b, sampler);
     if (m.type == MED_HOMOGENEOUS) {  // homogeneous.cpp:25-58
         const float t_max = length(b - a);
         const float st = -logf(1.0f - sampler.get1d()) / m.sigma_t;
@@ -380,7 +550,7 @@ __device__ __forceinline__ MediumSample medium_sample(const SceneDevice &scene, 
 }
 
 __device__ __forceinline__ f3 medium_tr(const SceneDevice &scene, const MediumDesc &m, f3 a, f3 b, Sampler &sampler) {
-    if (m.type == MED_VOLPRIM) return f3(1.0f);
+    if (m.type == MED_VOLPRIM) return f3(volprim_tr(scene, a, b, sampler));
     if (m.type == MED_HOMOGENEOUS) {  // homogeneous.cpp:60-73: sigma_a = sigma_t * (1 - albedo)
         const f3 sigma_a = m.sigma_t * (f3(1.0f) - f3(m.albedo[0], m.albedo[1], m.albedo[2]));
         const f3 e = -length(a - b) * sigma_a;

@@ -422,7 +422,21 @@ void Scene::create(const NodeP &root) {
         }
         if (auto v = scene_node->find("volumes")) {
             if (!v->is_array()) throw Error("'volumes' is not an array node");
-            if (!v->elements.empty()) throw Error("volume primitives ('volumes') are not supported yet");
+            for (const NodeP &vol : v->elements) {  // factory/scene.cpp:64-79
+                VolumePrim vp{};
+                const Vec3 o = vol->child("o")->as_vec3(), x = vol->child("x")->as_vec3(), y = vol->child("y")->as_vec3(), z = vol->child("z")->as_vec3();
+                const float x2 = dot(x, x), y2 = dot(y, y), z2 = dot(z, z);
+                for (int a = 0; a < 3; ++a) {
+                    vp.o[a] = o[a]; vp.x[a] = x[a]; vp.y[a] = y[a]; vp.z[a] = z[a];
+                    vp.x_div_x2[a] = x[a] / x2; vp.y_div_y2[a] = y[a] / y2; vp.z_div_z2[a] = z[a] / z2;  // volume/bvh.cpp:96-102
+                }
+                vp.inv_x2 = 1.0f / x2; vp.inv_y2 = 1.0f / y2; vp.inv_z2 = 1.0f / z2;
+                vp.sigma_t_tex = create_texture3d(vol->child("sigma_t"));
+                vp.albedo_tex = create_texture3d(vol->child("albedo"));
+                const Tex3DNode &st = textures3d[vp.sigma_t_tex];
+                vp.max_sigma_t = st.is_array ? sources[st.source].max_value[0] : st.value.x;
+                volume_prims.push_back(vp);
+            }
         }
         if (auto e = scene_node->find("envir_light")) create_envir_light(e);
         return 0;
@@ -540,7 +554,7 @@ void Scene::commit() {
         vp.type = MED_VOLPRIM;
         medium_table.push_back(vp);
     }
-    has_medium = false;
+    has_medium = !volume_prims.empty();  // core/scene.cpp:346-349
 
     // ---- lights + instance table (core/scene.cpp:94-100, 163-207)
     lights.clear();
@@ -593,6 +607,13 @@ void Scene::commit() {
             Vec3 p(c & 4 ? m.bbox.hi.x : m.bbox.lo.x, c & 2 ? m.bbox.hi.y : m.bbox.lo.y, c & 1 ? m.bbox.hi.z : m.bbox.lo.z);
             bbox.extend(inst.transform.point(p));
         }
+    }
+    for (const VolumePrim &v : volume_prims) {  // core/scene.cpp:233-237; VolumePrimitive::get_bounding_box (core/volume.cpp:51-66)
+        const Vec3 o(v.o[0], v.o[1], v.o[2]);
+        bbox.extend(o);
+        bbox.extend(o + Vec3(v.x[0], v.x[1], v.x[2]));
+        bbox.extend(o + Vec3(v.y[0], v.y[1], v.y[2]));
+        bbox.extend(o + Vec3(v.z[0], v.z[1], v.z[2]));
     }
     AABB wb = bbox;
     wb.extend(cam_eye);  // wavefront.cpp:138-139
@@ -770,6 +791,8 @@ void Scene::upload_device() {
     }
     dev.textures3d = upload(t3);
     dev.media = upload(medium_table);
+    dev.vol_prims = volume_prims.empty() ? nullptr : upload(volume_prims);
+    dev.n_vol_prims = (int)volume_prims.size();
     dev.has_medium = has_medium ? 1 : 0;
     dev.lights = upload(lights);
     dev.n_instances = (int)instance_info.size();

@@ -130,7 +130,8 @@ public:
     // --- committed state
     std::vector<InstanceInfo> instance_info;
     std::vector<LightInfo> lights;
-    std::vector<MediumDesc> medium_table;   // id order: descending priority, volume-primitive medium last (core/scene.cpp:136-161)
+    std::vector<MediumDesc> medium_table;
+    std::vector<VolumePrim> volume_prims;   // "volumes" (core/volume.h), in file order   // id order: descending priority, volume-primitive medium last (core/scene.cpp:136-161)
     bool has_medium = false;
     std::vector<WorldTri> world_tris;
     AABB bbox;

@@ -320,6 +320,44 @@ def make_medium_scene(out_dir, width=1920, height=1080, spp=128, state_count=100
     return _dump(out_dir, root)
 
 
+def make_volume_scene(out_dir, width=640, height=480, spp=32, state_count=500000, grid_res=32, min_depth=5, max_depth=10, filter=None,
+                      save=None, n_extra=0):
+    """Volume primitives (the scene file's "volumes" array; core/volume.cpp): the open Cornell box with two overlapping
+    parallelepipeds -- a rotated grid-density cloud and a constant-density slab that cuts through it -- plus `n_extra`
+    small constant boxes (more than four of them overlap in one corner when n_extra >= 5)."""
+    os.makedirs(out_dir, exist_ok=True)
+    groups = split_cornell_groups()
+    white, red, green = [0.725, 0.71, 0.68], [0.63, 0.065, 0.05], [0.14, 0.45, 0.091]
+    colors = {"floor": white, "ceiling": white, "backWall": white, "rightWall": green, "leftWall": red, "light": [0.78, 0.78, 0.78]}
+    entities = []
+    for name, (gv, gf) in groups.items():
+        if name not in colors:
+            continue
+        write_obj(os.path.join(out_dir, f"{name}.obj"), gv, gf)
+        ent = {"geometry": _geo(name), "material": {"type": "diffuse", "color": colors[name]}}
+        if name == "light":
+            ent["light"] = {"type": "mesh_light", "intensity": [17, 12, 4]}
+        entities.append(ent)
+    write_density_grid(os.path.join(out_dir, "density.txt"), grid_res, max_sigma=6.0)
+    c, s_ = float(np.cos(np.radians(25.0))), float(np.sin(np.radians(25.0)))
+    volumes = [
+        {"o": [-0.55, 0.35, -0.35], "x": [0.9 * c, 0.0, -0.9 * s_], "y": [0.0, 0.9, 0.0], "z": [0.9 * s_, 0.0, 0.9 * c],
+         "sigma_t": {"type": "array", "text": "$env{scene_directory}/density.txt"}, "albedo": [0.9, 0.9, 0.95]},
+        {"o": [-0.9, 0.6, -0.6], "x": [1.8, 0.0, 0.0], "y": [0.0, 0.25, 0.0], "z": [0.0, 0.0, 1.2],
+         "sigma_t": 1.5, "albedo": [0.95, 0.6, 0.3]},
+    ]
+    for k in range(n_extra):
+        volumes.append({"o": [0.35 + 0.02 * k, 1.2 + 0.015 * k, -0.2 + 0.01 * k], "x": [0.4, 0, 0], "y": [0, 0.4, 0], "z": [0, 0, 0.4],
+                        "sigma_t": 0.8 + 0.3 * k, "albedo": [0.5 + 0.05 * k, 0.8, 0.9 - 0.05 * k]})
+    root = {"width": width, "height": height,
+            "camera": {"type": "pinhole", "eye": [0, 1, 3.4], "dst": [0, 1, 0], "up": [0, 1, 0], "fov_y": {"deg": 39}},
+            "renderer": _renderer(spp, state_count, min_depth, max_depth, filter),
+            "scene": {"entities": entities, "volumes": volumes}}
+    if save:
+        root["post_processors"] = [{"type": "save", "color": save, "gamma": 2.2}]
+    return _dump(out_dir, root)
+
+
 def write_envmap(path, width=512, height=256, seed=5):
     """Equirectangular environment map as an 8-bit PNG: sky gradient, a bright sun blob and soft clouds (u = phi / 2pi, v = theta / pi)."""
     from PIL import Image

@@ -63,6 +63,7 @@ def lib():
         L.orc_add_texture3d_array.argtypes = [c_void_p, c_int]
         L.orc_add_medium_homogeneous.argtypes = [c_void_p, c_float, POINTER(c_float), c_float]
         L.orc_add_medium_heterogeneous.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_float)]
+        L.orc_add_volume.argtypes = [c_void_p] + [POINTER(c_float)] * 4 + [c_int, c_int]
         L.orc_set_gradient_sky.argtypes = [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float)]
         L.orc_set_ibl.argtypes = [c_void_p, c_int, POINTER(c_float), c_int, c_int]
         L.orc_get_ibl_table.argtypes = [c_void_p, POINTER(c_float)]
@@ -80,6 +81,8 @@ def lib():
         L.orc_set_renderer.argtypes = [c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_int, c_float, c_float]
         L.orc_commit.argtypes = [c_void_p]
         L.orc_num_triangles.argtypes = [c_void_p]
+        L.orc_vol_prim_medium_id.argtypes = [c_void_p]
+        L.orc_vol_prim_medium_id.restype = c_uint32
         L.orc_world_diagonal.argtypes = [c_void_p]
         L.orc_world_diagonal.restype = c_float
         L.orc_get_triangles.argtypes = [c_void_p, POINTER(c_float), POINTER(c_uint32)]
@@ -824,8 +827,15 @@ class OracleScene:
             inner = self.add_medium(ent.child("inner_medium")) if ent.find("inner_medium") is not None else None
             outer = self.add_medium(ent.child("outer_medium")) if ent.find("outer_medium") is not None else None
             self.add_instance(pool[("geo", id(g.raw))], pool[("mat", id(m.raw))], xf, inten, inner, outer)
-        if scene.find("volumes") is not None and len(scene.child("volumes").elements()) > 0:
-            raise NotImplementedError("oracle: volume primitives")
+        if scene.find("volumes") is not None:  # factory/scene.cpp:57-80
+            vols = scene.child("volumes")
+            if not vols.is_array():
+                raise ValueError("'volumes' is not an array node")
+            for vol in vols.elements():
+                geo = [np.ascontiguousarray(vol.child(k).as_vec3(), f32) for k in ("o", "x", "y", "z")]
+                st = self.add_texture3d(vol.child("sigma_t"))
+                al = self.add_texture3d(vol.child("albedo"))
+                self.L.orc_add_volume(self.h, *[_ptr(g, c_float) for g in geo], st, al)
         env = scene.find("envir_light")
         if env is not None:
             ty = env.child("type").as_str()
@@ -921,6 +931,8 @@ class OracleScene:
         return tr
 
     def has_medium(self): return bool(self.L.orc_has_medium(self.h))
+
+    def vol_prim_medium_id(self): return int(self.L.orc_vol_prim_medium_id(self.h))
 
     def ibl_table(self):
         t = np.zeros((self.lut[1], self.lut[0]), f32)

@@ -244,12 +244,22 @@ struct Stats {
 
 }  // namespace
 
+// core/volume.h:9-45 (VolumePrimitive) + core/volume/bvh.h:24-30 (BVHPrimitive)
+struct VolumePrim {
+    V3 o, x, y, z;
+    V3 x_div_x2, y_div_y2, z_div_z2;     // x / |x|^2 ...            (volume/bvh.cpp:96-102)
+    float inv_x2, inv_y2, inv_z2;        // 1 / |x|^2 ...            (volume.cpp:42-49: world_pos_to_uvw)
+    int sigma_t_tex = -1, albedo_tex = -1;
+    float max_sigma_t = 0;               // Texture3D::get_max_float
+};
+
 struct orc_scene {
     TextureSet tex;
     std::vector<Texture3D> tex3d;
     std::vector<Material> materials;
     std::vector<Medium> media;           // id order = Scene::commit order (core/scene.cpp:136-161); last = volume-primitive medium
     bool has_medium = false;             // Scene::has_medium (core/scene.cpp:346-356)
+    std::vector<struct VolumePrim> volumes;  // "volumes" of the scene file (factory/scene.cpp:57-80), members of the volume-primitive medium
     // environment light (core/light_sampler.cpp:24-33: appended after the area lights)
     int env_type = ENV_NONE; int env_light_index = -1;
     V3 sky_lower{0, 0, 0}, sky_upper{0, 0, 0}, sky_up{0, 0, 1};
@@ -949,9 +959,168 @@ V3 medium_uvw(const Medium &m, V3 p) {  // TransformMedium (core/medium.cpp:98-1
 
 struct MediumSample { bool scattered = false; V3 position; V3 throughput{1, 1, 1}; PhaseShader shader; };
 
+// ------------------------------------------------------------------------------------------
+// Volume primitives: core/volume.cpp:112-195 (VolumePrimitiveMedium::sample / tr), core/volume/bvh.cpp:146-326,
+// core/volume/aggregate.cpp:129-253.
+// The reference walks a small BVH over the primitives' boxes and picks per-overlap generated code through a trie
+// (volume/indexing.cpp, overlap.cpp); both only select WHICH primitives contain a point.  The results they produce are
+// order independent (closest boundary = a minimum, overlap = a set), so this restatement loops over the primitives.
+// Two documented choices where the reference depends on incidental order: the members of an overlap are visited in
+// creation order (the reference iterates a std::set ordered by object address), and when more than
+// MAX_OVERLAP_COUNT = 4 primitives contain a point the four with the smallest ids are kept (the reference keeps the
+// first four in ITS BVH's traversal order).
+// ------------------------------------------------------------------------------------------
+constexpr int MAX_OVERLAP_COUNT = 4;  // volume/bvh.h:11
+
+V3 vol_world_to_uvw(const VolumePrim &v, V3 p) {  // volume.cpp:42-49
+    V3 op = p - v.o;
+    return V3(dot(op, v.x) * v.inv_x2, dot(op, v.y) * v.inv_y2, dot(op, v.z) * v.inv_z2);
+}
+
+// volume/bvh.cpp:281-326: nearest boundary crossing (entry, else exit) of one primitive on p + t d, t in (0, t_max); -1 if none
+float vol_prim_intersect(V3 p, V3 d, float t_max, const VolumePrim &prim) {
+    V3 op = p - prim.o;
+    float t0 = 0.0f, t1 = t_max;
+    const V3 axes[3] = {prim.x_div_x2, prim.y_div_y2, prim.z_div_z2};
+    for (const V3 &a : axes) {
+        float opd = dot(op, a), dd = dot(d, a);
+        float nd = (0.0f - opd) / dd, fd = (1.0f - opd) / dd;
+        t0 = std::fmax(t0, std::fmin(nd, fd));
+        t1 = std::fmin(t1, std::fmax(nd, fd));
+    }
+    if (t0 > t1) return -1;
+    if (t0 > 0) return t0;
+    if (t1 < t_max) return t1;
+    return -1;
+}
+
+// volume/bvh.cpp:146-214
+bool vol_find_closest_intersection(const orc_scene &s, V3 a, V3 b, V3 &out) {
+    V3 dir = b - a;
+    float final_t = MAX_FLOAT, t_max = 1.0f;
+    for (const VolumePrim &prim : s.volumes) {
+        float t = vol_prim_intersect(a, dir, t_max, prim);
+        if (t >= 0.0f) { final_t = std::fmin(final_t, t); t_max = final_t; }
+    }
+    if (final_t > 10) return false;
+    out = a * (1.0f - final_t) + b * final_t;
+    return true;
+}
+
+struct VolOverlap { uint32_t data[MAX_OVERLAP_COUNT]; int count = 0; };
+
+VolOverlap vol_get_overlap(const orc_scene &s, V3 pos) {  // volume/bvh.cpp:216-263, is_in_prim :270-279
+    VolOverlap r;
+    for (size_t i = 0; i < s.volumes.size() && r.count < MAX_OVERLAP_COUNT; ++i) {
+        const VolumePrim &prim = s.volumes[i];
+        V3 op = pos - prim.o;
+        float u = dot(op, prim.x_div_x2), v = dot(op, prim.y_div_y2), w = dot(op, prim.z_div_z2);
+        if (0.0f <= u && u <= 1.0f && 0.0f <= v && v <= 1.0f && 0.0f <= w && w <= 1.0f) r.data[r.count++] = (uint32_t)i;
+    }
+    return r;
+}
+
+float vol_overlap_max_density(const orc_scene &s, const VolOverlap &ov) {  // aggregate.cpp:121-127
+    float m = 0.0f;
+    for (int i = 0; i < ov.count; ++i) m += s.volumes[ov.data[i]].max_sigma_t;
+    return std::fmax(m, 0.01f);
+}
+
+// aggregate.cpp:129-199
+void vol_sample_scattering(const orc_scene &s, const VolOverlap &ov, V3 a, V3 b, Sampler &sampler, MediumSample &r) {
+    const float inv_max_density = 1.0f / vol_overlap_max_density(s, ov);
+    V3 uvw_a[MAX_OVERLAP_COUNT], uvw_b[MAX_OVERLAP_COUNT];
+    for (int i = 0; i < ov.count; ++i) {
+        uvw_a[i] = vol_world_to_uvw(s.volumes[ov.data[i]], a);
+        uvw_b[i] = vol_world_to_uvw(s.volumes[ov.data[i]], b);
+    }
+    float t_max = length(b - a), t = 0.0f;
+    for (;;) {
+        float dt = -std::log(1.0f - sampler.get1d()) * inv_max_density;
+        t = t + dt;
+        if (t >= t_max) { r.scattered = false; return; }
+        float tf = t / t_max;
+        V3 uvws[MAX_OVERLAP_COUNT]; float densities[MAX_OVERLAP_COUNT];
+        float density_sum = 0.0f;
+        for (int i = 0; i < ov.count; ++i) {
+            uvws[i] = uvw_a[i] * (1.0f - tf) + uvw_b[i] * tf;
+            densities[i] = eval_texture3d(s, s.volumes[ov.data[i]].sigma_t_tex, uvws[i]).x;
+            density_sum = density_sum + densities[i];
+        }
+        if (sampler.get1d() < density_sum * inv_max_density) {
+            r.scattered = true;
+            r.position = a * (1.0f - tf) + b * tf;
+            V3 albedo(0, 0, 0);
+            for (int i = 0; i < ov.count; ++i) {
+                float weight = densities[i] / density_sum;
+                albedo = albedo + weight * eval_texture3d(s, s.volumes[ov.data[i]].albedo_tex, uvws[i]);
+            }
+            r.shader.g = 0.0f; r.shader.color = albedo;
+            return;
+        }
+    }
+}
+
+// aggregate.cpp:201-253
+float vol_tr_in_overlap(const orc_scene &s, const VolOverlap &ov, V3 a, V3 b, Sampler &sampler) {
+    const float inv_max_density = 1.0f / vol_overlap_max_density(s, ov);
+    V3 uvw_a[MAX_OVERLAP_COUNT], uvw_b[MAX_OVERLAP_COUNT];
+    for (int i = 0; i < ov.count; ++i) {
+        uvw_a[i] = vol_world_to_uvw(s.volumes[ov.data[i]], a);
+        uvw_b[i] = vol_world_to_uvw(s.volumes[ov.data[i]], b);
+    }
+    float result = 1.0f, t_max = length(b - a), t = 0.0f;
+    for (;;) {
+        float dt = -std::log(1.0f - sampler.get1d()) * inv_max_density;
+        t = t + dt;
+        if (t >= t_max) break;
+        float tf = t / t_max;
+        float density_sum = 0.0f;
+        for (int i = 0; i < ov.count; ++i) {
+            V3 uvw = uvw_a[i] * (1.0f - tf) + uvw_b[i] * tf;
+            density_sum = density_sum + eval_texture3d(s, s.volumes[ov.data[i]].sigma_t_tex, uvw).x;
+        }
+        result = result * (1.0f - density_sum * inv_max_density);
+    }
+    return result;
+}
+
+MediumSample volprim_sample(const orc_scene &s, V3 a, V3 b, Sampler &sampler) {  // volume.cpp:112-160
+    MediumSample r;
+    if (s.volumes.empty()) return r;
+    V3 o = a, d = normalize(b - a);
+    for (;;) {
+        if (dot(b - o, d) <= 0.0f || length_square(b - o) < 0.00001f) { r.scattered = false; break; }
+        V3 inct_pos;
+        if (!vol_find_closest_intersection(s, o, b, inct_pos)) inct_pos = b;
+        VolOverlap ov = vol_get_overlap(s, 0.5f * (o + inct_pos));
+        if (ov.count != 0) {
+            vol_sample_scattering(s, ov, o, inct_pos, sampler, r);
+            if (r.scattered) break;
+        }
+        o = inct_pos + 0.001f * d;
+    }
+    return r;
+}
+
+V3 volprim_tr(const orc_scene &s, V3 a, V3 b, Sampler &sampler) {  // volume.cpp:162-195
+    float result = 1.0f;
+    if (s.volumes.empty()) return V3(1, 1, 1);
+    V3 o = a, d = normalize(b - a);
+    for (;;) {
+        if (dot(b - o, d) <= 0.0f || length_square(b - o) < 0.0001f) break;
+        V3 inct_pos;
+        if (!vol_find_closest_intersection(s, o, b, inct_pos)) inct_pos = b;
+        VolOverlap ov = vol_get_overlap(s, 0.5f * (o + inct_pos));
+        if (ov.count != 0) result = result * vol_tr_in_overlap(s, ov, o, inct_pos, sampler);
+        o = inct_pos + 0.001f * d;
+    }
+    return V3(result, result, result);
+}
+
 MediumSample medium_sample(const orc_scene &s, const Medium &m, V3 a, V3 b, Sampler &sampler) {
     MediumSample r;
-    if (m.type == MED_VOLPRIM) return r;  // no volume primitives: core/volume.cpp:124-129
+    if (m.type == MED_VOLPRIM) return volprim_sample(s, a, b, sampler);
     if (m.type == MED_HOMOGENEOUS) {  // homogeneous.cpp:25-58
         float t_max = length(b - a);
         float st = -std::log(1.0f - sampler.get1d()) / m.sigma_t;
@@ -988,7 +1157,7 @@ MediumSample medium_sample(const orc_scene &s, const Medium &m, V3 a, V3 b, Samp
 }
 
 V3 medium_tr(const orc_scene &s, const Medium &m, V3 a, V3 b, Sampler &sampler) {
-    if (m.type == MED_VOLPRIM) return V3(1, 1, 1);
+    if (m.type == MED_VOLPRIM) return volprim_tr(s, a, b, sampler);
     if (m.type == MED_HOMOGENEOUS) {  // homogeneous.cpp:60-73: sigma_a = sigma_t * (1 - albedo)
         V3 sigma_a = m.sigma_t * (V3(1, 1, 1) - m.albedo);
         V3 e = -length(a - b) * sigma_a;
@@ -1203,6 +1372,21 @@ int orc_add_medium_heterogeneous(orc_scene *s, int sigma_t_tex, int albedo_tex, 
     return (int)s->media.size() - 1;
 }
 
+// factory/scene.cpp:57-80 ("volumes": o, x, y, z, sigma_t, albedo)
+int orc_add_volume(orc_scene *s, const float *o, const float *x, const float *y, const float *z, int sigma_t_tex, int albedo_tex) {
+    VolumePrim v;
+    v.o = V3(o[0], o[1], o[2]); v.x = V3(x[0], x[1], x[2]); v.y = V3(y[0], y[1], y[2]); v.z = V3(z[0], z[1], z[2]);
+    const float x2 = dot(v.x, v.x), y2 = dot(v.y, v.y), z2 = dot(v.z, v.z);
+    v.x_div_x2 = v.x / x2; v.y_div_y2 = v.y / y2; v.z_div_z2 = v.z / z2;
+    v.inv_x2 = 1.0f / x2; v.inv_y2 = 1.0f / y2; v.inv_z2 = 1.0f / z2;
+    v.sigma_t_tex = sigma_t_tex; v.albedo_tex = albedo_tex;
+    const Texture3D &t = s->tex3d[sigma_t_tex];
+    v.max_sigma_t = t.type == TEX_CONSTANT ? t.value.x : s->tex.images[t.image].max_value[0];
+    s->volumes.push_back(v);
+    s->has_medium = true;  // core/scene.cpp:346-349
+    return (int)s->volumes.size() - 1;
+}
+
 // IBL + EnvirLightSampler::preprocess (light/ibl.cpp:27-36,89-102; light/env_sampler.cpp:22-122): per-tile mean luminance from
 // 256 Hammersley taps (utils/math/hammersley.h), tile solid angle, table = max(0, area * (lum - avg)), normalised; alias table.
 void orc_set_ibl(orc_scene *s, int tex, const float *up, int lut_w, int lut_h) {
@@ -1312,6 +1496,13 @@ void orc_commit(orc_scene *s) {
             hi = V3(std::fmax(hi.x, q.x), std::fmax(hi.y, q.y), std::fmax(hi.z, q.z));
         }
     }
+    for (const VolumePrim &v : s->volumes) {  // core/scene.cpp:233-237, core/volume.cpp:51-66 (box of o, o+x, o+y, o+z)
+        const V3 c[4] = {v.o, v.o + v.x, v.o + v.y, v.o + v.z};
+        for (const V3 &q : c) {
+            lo = V3(std::fmin(lo.x, q.x), std::fmin(lo.y, q.y), std::fmin(lo.z, q.z));
+            hi = V3(std::fmax(hi.x, q.x), std::fmax(hi.y, q.y), std::fmax(hi.z, q.z));
+        }
+    }
     lo = V3(std::fmin(lo.x, s->eye.x), std::fmin(lo.y, s->eye.y), std::fmin(lo.z, s->eye.z));
     hi = V3(std::fmax(hi.x, s->eye.x), std::fmax(hi.y, s->eye.y), std::fmax(hi.z, s->eye.z));
     s->bb_lo = lo; s->bb_hi = hi;
@@ -1329,6 +1520,7 @@ void orc_commit(orc_scene *s) {
 
 int orc_num_triangles(orc_scene *s) { return (int)s->tris.size(); }
 float orc_world_diagonal(orc_scene *s) { return s->world_diagonal; }
+uint32_t orc_vol_prim_medium_id(orc_scene *s) { return s->vol_prim_medium_id; }
 
 // Flattened world-space triangles as (p0, p1, p2) 9 floats + (inst, prim): lets tests feed the very
 // same triangles to oracle/_ref (lib/bvh).
