@@ -399,9 +399,20 @@ def run_ours(args):
         stages[name] = {"ms_total": ms, "launches": iters, "ms_per_launch": ms / iters, "alg_bytes_per_launch": nbytes / iters,
                         "achieved_gbs": gbs, "frac": gbs / peak, "share_of_step": ms / prof_ms}
     dom = max((k for k in stages if k != "bookkeeping"), key=lambda k: stages[k]["ms_total"])
+    # DRAM traffic of the dominant kernel: bytes per ray / state from the committed ncu --set full capture of this workload
+    # (profiles/traffic_<workload>.json, written by scripts/ncu_summary.py traffic), scaled to this run's units per launch
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
+    if os.path.exists(tpath):
+        t = json.load(open(tpath)).get(dom)
+        if t and t.get("dram_bytes_per_unit"):
+            units = {"trace": agg["n_closest"], "shadow": agg["n_shadow"], "shade": agg["n_hit"]}.get(dom)
+            if units:
+                traffic = t["dram_bytes_per_unit"] * units * scale / iters
     roofline = {"kernel": dom + "_kernel",
                 "bound": "hbm", "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"],
-                "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": stages[dom]["alg_bytes_per_launch"],
+                "traffic": traffic, "traffic_source": ("profiles/traffic_%s.json (ncu dram__bytes_read+write per ray x rays per launch)" % args.workload) if traffic else None,
+                "peak_source": peak_src, "alg_bytes_per_launch": stages[dom]["alg_bytes_per_launch"],
                 "ms_per_launch": stages[dom]["ms_per_launch"], "bvh_alg": bvh}
 
     # ---- CPU baseline: the oracle (port) on the host cores of this box, bounded sample of the same workload

@@ -124,6 +124,17 @@ void Renderer::render_range(long long begin, long long end) {
         }
         BTRC_CUDA(cudaEventRecord(prof_events_[n_prof++], stream_));
     };
+    // Diagnostics (BTRC_ITER_LOG=1): work counts of every launched iteration, in launch order across renders, so that a
+    // profiler capture of "the k-th trace_kernel launch" can be matched with the number of rays it processed
+    static const bool iter_log = std::getenv("BTRC_ITER_LOG") != nullptr;
+    static long long global_iter = 0;
+    long long logged = 0;
+    auto log_iter = [&](long long idx) {
+        const WaveCtl &c = ctl_host_[idx % 8];
+        std::fprintf(stderr, "[btrc iter] %lld n_active=%d n_new=%d n_next=%d n_shadow=%d classes=%d,%d,%d,%d,%d,%d,%d,%d\n", global_iter++, c.n_active,
+                     c.n_new, c.n_next, c.n_shadow, c.class_count[0], c.class_count[1], c.class_count[2], c.class_count[3], c.class_count[4],
+                     c.class_count[5], c.class_count[6], c.class_count[7]);
+    };
     while (!done) {
         launch_prepare(ctl_, stream_);
         mark();
@@ -146,6 +157,7 @@ void Renderer::render_range(long long begin, long long end) {
             const int old = (int)((iter - kLag) % 8);
             BTRC_CUDA(cudaEventSynchronize(snap_ev_[old]));
             last = ctl_host_[old];
+            if (iter_log) log_iter(logged++);
             // the snapshot is taken after shade: the wave is finished when nothing survived and nothing is left to generate
             if (last.n_next == 0 && last.cursor >= last.end) done = true;
         }
@@ -157,6 +169,7 @@ void Renderer::render_range(long long begin, long long end) {
     BTRC_CUDA(cudaStreamSynchronize(stream_));
     BTRC_CUDA(cudaGetLastError());
     const WaveCtl fin = ctl_host_[9];
+    if (iter_log) while (logged < iter) log_iter(logged++);
     float ms = 0;
     BTRC_CUDA(cudaEventElapsedTime(&ms, ev_begin_, ev_end_));
     stats_.n_gen += fin.n_gen;

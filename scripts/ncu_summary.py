@@ -102,5 +102,46 @@ def full(src, dst):
     print(open(dst).read())
 
 
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def traffic(src, iters_log, skip, stage, dst):
+    """DRAM traffic of the captured launches (dram__bytes_read.sum + dram__bytes_write.sum) next to the number of rays / states
+    each launch processed (BTRC_ITER_LOG lines of the same run; launch k of a stage kernel = iteration k).  Appends to a JSON
+    file that bench.py reads for `roofline.traffic`."""
+    import json
+    import os
+    import re
+
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+    iters = {}
+    for line in open(iters_log):
+        m = re.search(r"\[btrc iter\] (\d+) n_active=(\d+) n_new=(\d+) n_next=(\d+) n_shadow=(\d+) classes=([\d,]+)", line)
+        if m:
+            cls = [int(x) for x in m.group(6).split(",")]
+            iters[int(m.group(1))] = {"trace": int(m.group(2)), "shadow": int(m.group(5)), "shade": cls[3]}  # class 3 = 1 + MAT_DISNEY
+    launches_ = []
+    for k, r in enumerate(rows[2:]):
+        idx = int(skip) + k
+        units_of = iters.get(idx, {}).get(stage)
+        rd = float(r[ir].replace(",", "")) * UNIT[units[ir]]
+        wr = float(r[iw].replace(",", "")) * UNIT[units[iw]]
+        launches_.append({"launch": idx, "units": units_of, "dram_read_bytes": rd, "dram_write_bytes": wr,
+                          "time_us_under_ncu": float(r[it].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(units[it], 1.0)})
+    good = [l for l in launches_ if l["units"]]
+    entry = {"source": os.path.basename(src), "launches": launches_,
+             "dram_bytes_per_unit": (sum(l["dram_read_bytes"] + l["dram_write_bytes"] for l in good) / sum(l["units"] for l in good)) if good else None}
+    data = json.load(open(dst)) if os.path.exists(dst) else {}
+    data[stage] = entry
+    json.dump(data, open(dst, "w"), indent=1)
+    print(json.dumps(entry, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:7])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
