@@ -40,20 +40,19 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "c2_disney_1080p_256spp"
 
 
-def make_scene(workload, out_dir, spp=None):
+def make_scene(workload, out_dir, spp=None, tile=False):
     from btrc_b200 import scenes
 
     w = WORKLOADS[workload]
     os.makedirs(out_dir, exist_ok=True)
-    if w["kind"] == "cornell":
-        return scenes.make_cornell(out_dir, width=w["width"], height=w["height"], spp=spp or w["spp"])
-    if w["kind"] == "materials":
-        return scenes.make_material_test(out_dir, width=w["width"], height=w["height"], spp=spp or w["spp"])
-    if w["kind"] == "medium":
-        return scenes.make_medium_scene(out_dir, width=w["width"], height=w["height"], spp=spp or w["spp"])
-    if w["kind"] == "instanced":
-        return scenes.make_instanced_scene(out_dir, width=w["width"], height=w["height"], spp=spp or w["spp"])
-    raise ValueError(workload)
+    make = {"cornell": scenes.make_cornell, "materials": scenes.make_material_test, "medium": scenes.make_medium_scene,
+            "instanced": scenes.make_instanced_scene}[w["kind"]]
+    path = make(out_dir, width=w["width"], height=w["height"], spp=spp or w["spp"])
+    if tile:  # Tile-mode path indexing (renderer "tile": true, generate.cpp:56-60) for the image-tile partition
+        root = json.load(open(path))
+        root["renderer"]["tile"] = True
+        json.dump(root, open(path, "w"), indent=1)
+    return path
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -254,13 +253,16 @@ def run_ours(args):
         spp //= world
     npix = W * H
     tmp = tempfile.TemporaryDirectory()
-    path = make_scene(args.workload, tmp.name, spp=spp * world)  # weak scaling: every rank renders `spp` samples per pixel
+    tiles = args.partition == "tiles"
+    # samples partition: the scene holds spp * world samples per pixel and every rank renders `spp` of them;
+    # tiles partition: every rank renders all `spp * world` samples of its band of pixels (same number of paths per rank)
+    path = make_scene(args.workload, tmp.name, spp=spp * world, tile=tiles)
     s = api.Scene(path, state_count=args.state_count)
     s.set_profiling(False)  # the timed steps carry no per-stage events; the stage breakdown comes from a separate profiled pass
     stream = torch.cuda.ExternalStream(s.stream_handle())
     from btrc_b200 import partition
 
-    begin, end = partition.path_range(rank, world, spp * world, npix)
+    begin, end = (partition.tile_path_range if tiles else partition.path_range)(rank, world, spp * world, npix)
 
     rad = torch.zeros(H, W, 4, device="cuda")
     wgt = torch.zeros(H, W, device="cuda")
@@ -437,7 +439,8 @@ def run_ours(args):
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "mrays_per_s": mrays,
         "config": {"workload": args.workload, "width": W, "height": H, "spp_per_gpu": spp, "state_count": s.info.state_count,
-                   "partition": "sample index ranges per rank; NCCL sum-reduce of radiance+weight films to rank 0; resolve on rank 0" if world > 1 else "single GPU",
+                   "partition": (("image tiles (row bands of pixels, Tile-mode indexing) per rank" if tiles else "sample index ranges per rank") +
+                                 "; NCCL sum-reduce of radiance+weight films to rank 0; resolve on rank 0") if world > 1 else "single GPU",
                    "timing": "CUDA events on the renderer's stream per step, max over ranks; 256 MB L2 flush (untimed) between steps; "
                              "roofline_stages from a separate pass of %d identical steps with one CUDA event between kernels (%.1f ms/step)" % (prof_steps, prof_ms / prof_steps),
                    "wall_ms_per_step_incl_flush": wall / args.steps * 1e3},
@@ -486,6 +489,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--state-count", type=int, default=8388608,
                     help="path-state pool (the renderer's `state_count` parameter); 8 Mi states = 2.4 GB of queues (profiles/r1h_sweep_pool.log)")
+    ap.add_argument("--partition", default="samples", choices=["samples", "tiles"],
+                    help="multi-GPU split: sample-index ranges (default, load balanced) or image tiles (row bands, BASELINE config 5's wording)")
     ap.add_argument("--spp", type=int, default=0, help="override the workload's samples per pixel (profiling runs); reported in config")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (roofline bvh statistics, cpu_baseline): profiler runs")
     args = ap.parse_args()

@@ -22,6 +22,22 @@ def path_range(rank: int, world: int, spp: int, npix: int):
     return b * npix, e * npix
 
 
+def pixel_block(rank: int, world: int, npix: int):
+    """Pixels [begin, end) of `rank` in row-major order (a band of image rows, up to one partial row at each end)."""
+    base, rem = divmod(npix, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def tile_path_range(rank: int, world: int, spp: int, npix: int):
+    """Camera-path index range [begin, end) of `rank` in Tile mode (pixel-major index space, index = pixel * spp + sample:
+    generate.cpp:56-60; the scene's renderer must have "tile": true).  Image-tile partition of BASELINE config 5: every rank
+    renders all samples of its own band of pixels; the films of the other bands stay zero, so the same sum-reduce doubles as
+    the gather.  Bands are not load balanced (sky rows are cheap) -- the sample-stream partition is the default for that reason."""
+    b, e = pixel_block(rank, world, npix)
+    return b * spp, e * spp
+
+
 def reduce_films(tensors, dst: int = 0):
     """Sum-reduce the film buffers onto `dst` (torch.distributed; NCCL on GPUs, gloo in the CPU tests)."""
     import torch.distributed as dist

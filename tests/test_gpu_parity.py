@@ -259,6 +259,44 @@ def test_render_c1_full_size_properties(cornell_c1):
     s.close()
 
 
+def test_tile_partition_properties(tmp_path, built):
+    """Image-tile partition (BASELINE config 5's wording; partition.tile_path_range): in Tile mode a rank's path range covers
+    all samples of a band of pixels, the films of two ranks add up to the whole render, and the image equals the
+    Uniform-mode render of the same scene (same (pixel, sample) streams, different order)."""
+    import json
+
+    from btrc_b200 import api, partition, scenes
+
+    W, H, spp = 160, 96, 6
+    path = scenes.make_cornell(str(tmp_path), width=W, height=H, spp=spp, state_count=30000)
+    ref, _, _, stats_ref = api.Scene(path).render()
+    root = json.load(open(path))
+    root["renderer"]["tile"] = True
+    tpath = str(tmp_path / "scene_tile.json")
+    json.dump(root, open(tpath, "w"))
+    s = api.Scene(tpath)
+    color, _, _, stats = s.render()
+    for k in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss"):
+        assert stats[k] == stats_ref[k], k
+    assert np.allclose(color, ref, rtol=1e-4, atol=1e-5)
+    npix = W * H
+    total_r = np.zeros((H, W, 4), f32); total_w = np.zeros((H, W), f32)
+    for rank in range(3):  # 3 ranks: bands that end inside a row
+        b, e = partition.tile_path_range(rank, 3, spp, npix)
+        s.film_clear()
+        s.render_range(b, e)
+        r = np.zeros((H, W, 4), f32); w = np.zeros((H, W), f32)
+        s.film_export(r, w)
+        pb, pe = partition.pixel_block(rank, 3, npix)
+        mask = np.zeros(npix, bool); mask[pb:pe] = True
+        assert np.array_equal(w.reshape(-1), np.where(mask, f32(spp), f32(0)))  # exactly its own pixels, all their samples
+        assert not r.reshape(-1, 4)[~mask].any()
+        total_r += r; total_w += w
+    assert np.array_equal(total_w, np.full((H, W), f32(spp)))
+    assert np.allclose(total_r[..., :3] / spp, ref[..., :3], rtol=1e-4, atol=1e-5)
+    s.close()
+
+
 def test_render_vs_oracle_c1_reduced(tmp_path, built):
     """Config 1 geometry at 256x256 / 16 spp against the oracle (full 512x512 costs the CPU ~20 s; same code path)."""
     from btrc_b200 import api, scenes

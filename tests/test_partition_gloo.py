@@ -26,6 +26,19 @@ def test_sample_blocks_cover_the_range():
             assert partition.path_range(world - 1, world, spp, 100)[1] == spp * 100
 
 
+def test_pixel_blocks_cover_the_image():
+    from btrc_b200 import partition
+
+    for world in (1, 2, 3, 8):
+        for npix in (1, 97, 1920 * 1080):
+            blocks = [partition.pixel_block(r, world, npix) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == npix
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            assert max(e - b for b, e in blocks) - min(e - b for b, e in blocks) <= 1
+            for r in range(world):
+                assert partition.tile_path_range(r, world, 16, npix) == (blocks[r][0] * 16, blocks[r][1] * 16)
+
+
 def _worker(rank, world, path, port, out):
     sys.path.insert(0, ROOT)
     import torch
