@@ -57,6 +57,12 @@ struct MaterialDesc {
     int normal_tex;                 // -1: no normal map
     int shadow_terminator;
     int tex[SLOT_COUNT];            // texture ids, -1 where the type has no such parameter
+    // Parameters whose texture is a literal / "constant" node are folded into the table at upload: bit s of const_mask set
+    // <=> slot s needs no texture program (its value is scalar_const[s]; colour: color_const).  One struct read replaces a
+    // chain of three dependent loads per parameter (material -> texture desc -> program op).
+    uint32_t const_mask;
+    float color_const[3];
+    float scalar_const[SLOT_COUNT];
 };
 
 // 3-D textures: constant or a CUDA 3-D texture object (texture3d/array3d.cpp, core/texture3d.cpp)

@@ -169,7 +169,12 @@ __device__ __forceinline__ void class_append(const HitQueue &hq, WaveCtl *ctl, b
     hq.class_list[(size_t)c * hq.class_stride + base + __popc(peers & ((1u << lane_id()) - 1u))] = (uint32_t)i;
 }
 
-__global__ void __launch_bounds__(kBlock) trace_kernel(SceneDevice scene, PathQueue q, HitQueue hq, WaveCtl *ctl) {
+// Occupancy of the traversal kernels: 6 resident CTAs per SM (40 registers, 48 warps) measured 2.4 % faster on C2 than the
+// compiler's own 46 registers / 5 CTAs, 8 CTAs (32 registers, spills) 3 % slower (profiles/r1h_ab_occupancy.log)
+#ifndef BTRC_TRACE_MIN_BLOCKS
+#define BTRC_TRACE_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(kBlock, BTRC_TRACE_MIN_BLOCKS) trace_kernel(SceneDevice scene, PathQueue q, HitQueue hq, WaveCtl *ctl) {
     const int n = ctl->n_active;
     unsigned long long hits = 0;
     for (;;) {
@@ -377,8 +382,13 @@ __global__ void __launch_bounds__(kBlock) shade_miss_kernel(SceneDevice scene, P
 #ifndef BTRC_SHADE_BLOCKS_HEAVY
 #define BTRC_SHADE_BLOCKS_HEAVY 2
 #endif
+#ifndef BTRC_SHADE_BLOCK_HEAVY
+#define BTRC_SHADE_BLOCK_HEAVY 256
+#endif
+template <int MAT> constexpr bool shade_is_heavy() { return MAT == MAT_DISNEY || MAT == MAT_METAL; }
+template <int MAT> constexpr int shade_block() { return shade_is_heavy<MAT>() ? BTRC_SHADE_BLOCK_HEAVY : kBlock; }
 template <int MAT>
-__global__ void __launch_bounds__(kBlock, (MAT == MAT_DISNEY || MAT == MAT_METAL) ? BTRC_SHADE_BLOCKS_HEAVY : 3)
+__global__ void __launch_bounds__(shade_block<MAT>(), shade_is_heavy<MAT>() ? BTRC_SHADE_BLOCKS_HEAVY : 3)
 shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQueue nq, ShadowQueue sq, FilmDevice film, WaveCtl *ctl) {
     const int n = ctl->class_count[1 + MAT];
     const uint32_t *list = hq.class_list + (size_t)(1 + MAT) * hq.class_stride;
@@ -494,7 +504,7 @@ shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQu
 // ---------------------------------------------------------------------------------------------------------------
 // shadow rays (shadow.cpp:24-74): occlusion with early exit; unoccluded => splat beta_li * Tr
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) shadow_kernel(SceneDevice scene, RenderParams P, ShadowQueue sq, FilmDevice film, WaveCtl *ctl) {
+__global__ void __launch_bounds__(kBlock, BTRC_TRACE_MIN_BLOCKS) shadow_kernel(SceneDevice scene, RenderParams P, ShadowQueue sq, FilmDevice film, WaveCtl *ctl) {
     const int n = ctl->n_shadow;
     unsigned long long misses = 0;
     for (;;) {
@@ -576,7 +586,7 @@ void launch_trace(const LaunchCfg &cfg, const SceneDevice &scene, PathQueue cur,
 template <int MAT>
 static void launch_shade_class(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, HitQueue hit, PathQueue next,
                                ShadowQueue shadow, FilmDevice film, WaveCtl *ctl, cudaStream_t stream) {
-    shade_kernel<MAT><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
+    shade_kernel<MAT><<<persistent_blocks(cfg, 8 * kBlock / shade_block<MAT>()), shade_block<MAT>(), 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
 }
 
 int launch_shade(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, uint32_t material_mask, PathQueue cur, HitQueue hit,

@@ -269,25 +269,36 @@ __device__ __forceinline__ Shader<MAT> create_shader(const SceneDevice &scene, c
         const f3 world_nor = sh.frame.shading.local_to_global(local_nor);
         sh.frame.shading = sh.frame.shading.rotate_to_new_z(normalize(world_nor));
     }
+    const uint32_t cmask = mat.const_mask;
     if (MAT == MAT_DISNEY) {
-        const f3 base = eval_texture(scene, mat.tex[SLOT_COLOR], uv);
+        const f3 base = (cmask & (1u << SLOT_COLOR)) ? f3(mat.color_const[0], mat.color_const[1], mat.color_const[2])
+                                                     : eval_texture(scene, mat.tex[SLOT_COLOR], uv);
         float v[SLOT_COUNT];
-#pragma unroll 1
-        for (int slot = SLOT_METALLIC; slot < SLOT_COUNT; ++slot) v[slot] = eval_texture_float(scene, mat.tex[slot], uv);
+#pragma unroll
+        for (int slot = 0; slot < SLOT_COUNT; ++slot) v[slot] = mat.scalar_const[slot];  // independent loads, registers
+        // the few parameters that do have a texture graph: one pass of the (out-of-line) program each
+        for (uint32_t todo = ~cmask & ((1u << SLOT_COUNT) - 2u); todo; todo &= todo - 1u) {
+            const int slot = __ffs(todo) - 1;
+            const float val = eval_texture_float(scene, mat.tex[slot], uv);
+#pragma unroll
+            for (int k = SLOT_METALLIC; k < SLOT_COUNT; ++k) if (k == slot) v[k] = val;
+        }
         sh.disney = disney_make(base, v[SLOT_METALLIC], v[SLOT_ROUGHNESS], v[SLOT_SPECULAR], v[SLOT_SPECULAR_TINT], v[SLOT_ANISOTROPIC], v[SLOT_SHEEN],
                                 v[SLOT_SHEEN_TINT], v[SLOT_CLEARCOAT], v[SLOT_CLEARCOAT_GLOSS], v[SLOT_TRANSMISSION], v[SLOT_TRANSMISSION_ROUGHNESS],
                                 v[SLOT_IOR]);
     } else if (MAT == MAT_METAL) {
-        sh.metal.R0 = eval_texture(scene, mat.tex[SLOT_COLOR], uv);
-        const float roughness = eval_texture_float(scene, mat.tex[SLOT_ROUGHNESS], uv);
-        const float anisotropic = eval_texture_float(scene, mat.tex[SLOT_ANISOTROPIC], uv);
+        sh.metal.R0 = (cmask & (1u << SLOT_COLOR)) ? f3(mat.color_const[0], mat.color_const[1], mat.color_const[2])
+                                                   : eval_texture(scene, mat.tex[SLOT_COLOR], uv);
+        const float roughness = (cmask & (1u << SLOT_ROUGHNESS)) ? mat.scalar_const[SLOT_ROUGHNESS] : eval_texture_float(scene, mat.tex[SLOT_ROUGHNESS], uv);
+        const float anisotropic = (cmask & (1u << SLOT_ANISOTROPIC)) ? mat.scalar_const[SLOT_ANISOTROPIC] : eval_texture_float(scene, mat.tex[SLOT_ANISOTROPIC], uv);
         float aspect = 1.0f;
         if (anisotropic > 0.0f) aspect = sqrtf(1.0f - 0.9f * anisotropic);
         sh.metal.ax = fmaxf(0.001f, roughness * roughness / aspect);
         sh.metal.ay = fmaxf(0.001f, roughness * roughness * aspect);
     } else {
-        sh.color = eval_texture(scene, mat.tex[SLOT_COLOR], uv);
-        if (MAT == MAT_GLASS) sh.ior = eval_texture_float(scene, mat.tex[SLOT_IOR], uv);
+        sh.color = (cmask & (1u << SLOT_COLOR)) ? f3(mat.color_const[0], mat.color_const[1], mat.color_const[2])
+                                                : eval_texture(scene, mat.tex[SLOT_COLOR], uv);
+        if (MAT == MAT_GLASS) sh.ior = (cmask & (1u << SLOT_IOR)) ? mat.scalar_const[SLOT_IOR] : eval_texture_float(scene, mat.tex[SLOT_IOR], uv);
     }
     return sh;
 }

@@ -767,7 +767,6 @@ void Scene::upload_device() {
         dev.instance_class = upload(cls);
     }
     dev.geometries = upload(geos);
-    dev.materials = upload(materials);
     // ---- textures: CUDA texture objects for the "array" sources, postfix programs for the graph
     for (auto &src : sources) create_texture_object(src);
     std::vector<TextureDesc> tex_descs;
@@ -781,6 +780,20 @@ void Scene::upload_device() {
     }
     dev.textures = upload(tex_descs);
     dev.tex_ops = upload(tex_ops);
+    for (MaterialDesc &m : materials) {  // fold literal / "constant" parameters into the material table
+        m.const_mask = 0;
+        for (int slot = 0; slot < SLOT_COUNT; ++slot) {
+            m.scalar_const[slot] = 0.0f;
+            if (m.tex[slot] < 0) continue;
+            const TextureDesc &d = tex_descs[m.tex[slot]];
+            const TexOp &op = tex_ops[d.first_op];
+            if (d.n_ops != 1 || op.op != TEXOP_CONST) continue;
+            m.const_mask |= 1u << slot;
+            m.scalar_const[slot] = op.value[0];
+            if (slot == SLOT_COLOR) for (int c = 0; c < 3; ++c) m.color_const[c] = op.value[c];
+        }
+    }
+    dev.materials = upload(materials);
     std::vector<Texture3DDesc> t3;
     for (auto &t : textures3d) {
         Texture3DDesc d{};
