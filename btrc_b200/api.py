@@ -40,6 +40,12 @@ class RenderStats(ctypes.Structure):
 
 
 _lib = None
+PROGRESS_FN = ctypes.CFUNCTYPE(c_int, ctypes.c_float, c_void_p)
+BTRC_STOPPED = 2
+
+
+class RenderStopped(RuntimeError):
+    """The reporter asked the renderer to stop (Renderer::should_stop): no image was produced."""
 
 
 def lib():
@@ -75,12 +81,15 @@ def lib():
         L.btrc_geometry_tables.argtypes = [c_void_p, c_int32, POINTER(c_int32), c_void_p]
         L.btrc_instance_transform.argtypes = [c_void_p, c_int32, c_void_p, c_void_p]
         L.btrc_ibl_table.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]
+        L.btrc_set_reporter.argtypes = [c_void_p, PROGRESS_FN, c_void_p]
         L.btrc_device_sm_count.restype = c_int
         _lib = L
     return _lib
 
 
 def _check(rc):
+    if rc == BTRC_STOPPED:
+        raise RenderStopped(lib().btrc_last_error().decode())
     if rc != 0:
         raise BtrcError(lib().btrc_last_error().decode())
 
@@ -160,6 +169,16 @@ class Scene:
         st = RenderStats()
         _check(self.L.btrc_render(self.h, _mem(color), _p(color), _p(albedo), _p(normal), byref(st)))
         return color, albedo, normal, st.as_dict()
+
+    def set_reporter(self, fn=None):
+        """Reporter::progress + Renderer::should_stop: fn(percentage) is called from the rendering thread; a truthy return
+        value stops the render (render() / render_range() then raise RenderStopped).  None removes the reporter."""
+        if fn is None:
+            self._reporter = None
+            _check(self.L.btrc_set_reporter(self.h, ctypes.cast(None, PROGRESS_FN), None))
+            return
+        self._reporter = PROGRESS_FN(lambda pct, _user: 1 if fn(pct) else 0)  # kept alive with the scene
+        _check(self.L.btrc_set_reporter(self.h, self._reporter, None))
 
     def set_profiling(self, on=True):
         _check(self.L.btrc_set_profiling(self.h, 1 if on else 0))

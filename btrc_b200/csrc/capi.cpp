@@ -17,9 +17,23 @@ struct btrc_scene {
     std::unique_ptr<Scene> scene;
     std::unique_ptr<Renderer> renderer;
     int state_count_override = 0;
+    btrc_progress_fn progress_fn = nullptr;
+    void *progress_user = nullptr;
+    void apply_reporter() {
+        if (progress_fn) {
+            btrc_progress_fn fn = progress_fn;
+            void *user = progress_user;
+            renderer->set_reporter([fn, user](float pct) { return fn(pct, user) != 0; });
+        } else {
+            renderer->set_reporter(nullptr);
+        }
+    }
     Renderer &r() {
         scene->upload_device();
-        if (!renderer) renderer = std::make_unique<Renderer>(*scene, state_count_override);
+        if (!renderer) {
+            renderer = std::make_unique<Renderer>(*scene, state_count_override);
+            apply_reporter();
+        }
         return *renderer;
     }
 };
@@ -191,23 +205,40 @@ int btrc_film_clear(btrc_scene_t *s) {
 }
 
 int btrc_render_range(btrc_scene_t *s, int64_t begin, int64_t end, btrc_render_stats_t *stats) {
-    return guarded([&] {
+    bool stopped = false;
+    const int rc = guarded([&] {
         check_scene(s);
         s->r().render_range(begin, end);
+        stopped = s->r().stopped();
         fill_stats(s->r().stats(), stats);
+    });
+    if (rc == 0 && stopped) { g_last_error = "render stopped by the reporter"; return BTRC_STOPPED; }
+    return rc;
+}
+
+int btrc_set_reporter(btrc_scene_t *s, btrc_progress_fn fn, void *user) {
+    return guarded([&] {
+        check_scene(s);
+        s->progress_fn = fn;
+        s->progress_user = user;
+        if (s->renderer) s->apply_reporter();
     });
 }
 
 int btrc_render(btrc_scene_t *s, int memory, float *color, float *albedo, float *normal, btrc_render_stats_t *stats) {
     (void)memory;
-    return guarded([&] {
+    bool stopped = false;
+    const int rc = guarded([&] {
         check_scene(s);
         Renderer &r = s->r();
         r.clear_film();
         r.render_range(0, r.total_paths());
-        resolve_to(s, color, albedo, normal);
+        stopped = r.stopped();
+        if (!stopped) resolve_to(s, color, albedo, normal);
         fill_stats(r.stats(), stats);
     });
+    if (rc == 0 && stopped) { g_last_error = "render stopped by the reporter"; return BTRC_STOPPED; }
+    return rc;
 }
 
 int btrc_resolve(btrc_scene_t *s, int memory, float *color, float *albedo, float *normal) {

@@ -4,9 +4,21 @@
 #include <chrono>
 #include <cstdio>
 #include <iostream>
+#include <string>
 #include <vector>
 
 #include "../../../include/btrc_b200.h"
+
+// ConsoleReporter (builtin/reporter/console.cpp:5-33): an 80-column '=' bar redrawn whenever the percentage advanced by >= 1
+static int console_progress(float percentage, void *) {
+    const int width = 80, filled = (int)(percentage / 100.0f * width);
+    std::string bar(filled, '=');
+    bar.resize(width, ' ');
+    std::printf("\r[%s] %5.1f%%", bar.c_str(), percentage);
+    if (percentage >= 100.0f) std::printf("\n");
+    std::fflush(stdout);
+    return 0;
+}
 
 static int fail() {
     std::cerr << btrc_last_error() << std::endl;
@@ -30,6 +42,7 @@ int main(int argc, char *argv[]) {
     const size_t n = 4 * (size_t)info.width * info.height;
     std::vector<float> color(n), albedo(info.albedo ? n : 0), normal(info.normal ? n : 0);
     btrc_render_stats_t st;
+    if (btrc_set_reporter(scene, console_progress, nullptr)) return fail();  // main.cpp:62
     const auto t0 = std::chrono::steady_clock::now();
     if (btrc_render(scene, BTRC_HOST, color.data(), info.albedo ? albedo.data() : nullptr, info.normal ? normal.data() : nullptr, &st)) return fail();
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -135,7 +135,10 @@ void Renderer::render_range(long long begin, long long end) {
                      c.n_new, c.n_next, c.n_shadow, c.class_count[0], c.class_count[1], c.class_count[2], c.class_count[3], c.class_count[4],
                      c.class_count[5], c.class_count[6], c.class_count[7]);
     };
-    while (!done) {
+    stopped_ = false;
+    float reported = 0.0f;
+    if (reporter_ && reporter_(0.0f)) stopped_ = true;  // Reporter::new_stage
+    while (!done && !stopped_) {
         launch_prepare(ctl_, stream_);
         mark();
         launch_generate(cfg_, scene_.dev, params, q_[cur], film_, ctl_, stream_);
@@ -160,6 +163,13 @@ void Renderer::render_range(long long begin, long long end) {
             if (iter_log) log_iter(logged++);
             // the snapshot is taken after shade: the wave is finished when nothing survived and nothing is left to generate
             if (last.n_next == 0 && last.cursor >= last.end) done = true;
+            if (reporter_ && !done) {  // wavefront.cpp:286-287: finished = generated - still active; reported in steps of >= 1 % (console.cpp:26-33)
+                const float pct = 100.0f * float(double(last.n_gen - (unsigned long long)last.n_next) / double(std::max<long long>(end - begin, 1)));
+                if (pct - reported >= 1.0f) {
+                    reported = pct;
+                    if (reporter_(pct)) stopped_ = true;  // should_stop(): the waves in flight finish, nothing new is enqueued
+                }
+            }
         }
     }
     BTRC_CUDA(cudaEventRecord(ev_end_, stream_));
@@ -169,6 +179,7 @@ void Renderer::render_range(long long begin, long long end) {
     BTRC_CUDA(cudaStreamSynchronize(stream_));
     BTRC_CUDA(cudaGetLastError());
     const WaveCtl fin = ctl_host_[9];
+    if (reporter_ && !stopped_) reporter_(100.0f);  // Reporter::complete_stage
     if (iter_log) while (logged < iter) log_iter(logged++);
     float ms = 0;
     BTRC_CUDA(cudaEventElapsedTime(&ms, ev_begin_, ev_end_));

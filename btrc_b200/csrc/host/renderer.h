@@ -8,6 +8,7 @@
 //     partitioned across GPUs (the caller sum-reduces the film buffers and resolves once).
 #pragma once
 #include <cstdint>
+#include <functional>
 
 #include "../device/kernels.h"
 #include "scene.h"
@@ -30,6 +31,9 @@ public:
 
     void clear_film();
     void set_profiling(bool on) { profiling_ = on; }
+    // progress(percentage) -> true to stop (core/reporter.h + Renderer::should_stop); called from the rendering thread
+    void set_reporter(std::function<bool(float)> fn) { reporter_ = std::move(fn); }
+    bool stopped() const { return stopped_; }
     // Traces camera paths [begin, end) of the scene's path index space (Uniform mode: index = sample * W*H + pixel;
     // Tile mode: index = pixel * spp + sample) and accumulates them into the film.
     void render_range(long long begin, long long end);
@@ -78,6 +82,8 @@ private:
     cudaEvent_t snap_ev_[8]{};
     RenderStats stats_;
     bool profiling_ = false;
+    std::function<bool(float)> reporter_;
+    bool stopped_ = false;
     std::vector<cudaEvent_t> prof_events_;
     float *resolve_scratch_[3]{};   // lazily allocated W*H float4 images for host destinations
     template <typename T> T *alloc(size_t n);

@@ -74,6 +74,15 @@ int btrc_set_params(btrc_scene_t *scene, int32_t spp, int32_t state_count, int32
  * (the reference has no profiling hooks: SURVEY 5). */
 int btrc_set_profiling(btrc_scene_t *scene, int32_t on);
 
+/* Reporter (core/reporter.h:7-36, Renderer::set_reporter, core/renderer.h:28) + cancellation (Renderer::stop / should_stop,
+ * core/renderer.h:44-48): `fn` is called from the rendering thread only -- new_stage as fn(0), then after every wave whose
+ * counters have arrived with the percentage of finished camera paths (wavefront.cpp:286-287), complete_stage as fn(100).
+ * A non-zero return value stops the render after the waves in flight: btrc_render / btrc_render_range then return
+ * BTRC_STOPPED (2) and write no image, like the reference's empty RenderResult (wavefront.cpp:308-316).  NULL removes it. */
+#define BTRC_STOPPED 2
+typedef int (*btrc_progress_fn)(float percentage, void *user);
+int btrc_set_reporter(btrc_scene_t *scene, btrc_progress_fn fn, void *user);
+
 /* Renderer::render() (wavefront.cpp:205-325): clears the film, traces all spp*W*H camera paths and resolves
  * value/weight (preview.cpp:28-80).  color is W*H float4 (row 0 = top, .w = 1); albedo / normal may be NULL and
  * are written only when the renderer was created with "albedo"/"normal": true. */

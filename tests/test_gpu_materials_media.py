@@ -164,6 +164,45 @@ def test_render_matches_oracle_materials(pair_materials):
     assert abs(a.mean() - b.mean()) / b.mean() < 1e-2
 
 
+def test_render_c2_full_size_properties(tmp_path, built):
+    """BASELINE config 2 at its full geometry and resolution (15 x 19,800-triangle spheres, 1024^2 textures, 1920x1080, gaussian
+    filter), 4 of its 256 spp: size-independent properties -- every pixel's weight equals the number of samples whose filter
+    footprint chose it (sum of weights == paths exactly), counters close, linearity over sample ranges, pool-size independence."""
+    from btrc_b200 import api, scenes
+
+    W, H, spp = 1920, 1080, 4
+    path = scenes.make_material_test(str(tmp_path), width=W, height=H, spp=spp, state_count=4194304)
+    s = api.Scene(path)
+    color, _, _, stats = s.render()
+    npix = W * H
+    assert stats["n_gen"] == npix * spp
+    assert stats["n_closest"] == stats["n_gen"] + stats["n_next"]
+    assert stats["n_shadow_miss"] <= stats["n_shadow"] <= stats["n_hit"]
+    rad = np.zeros((H, W, 4), f32); wgt = np.zeros((H, W), f32)
+    s.film_export(rad, wgt)
+    assert wgt.astype(np.float64).sum() == npix * spp      # generate.cpp:62-68: one unit of weight per camera path, on its own pixel
+    assert np.array_equal(wgt, np.full((H, W), f32(spp)))
+    assert np.isfinite(color).all() and color[..., :3].min() >= 0
+    s.film_clear()
+    s.render_range(0, npix)
+    r0 = np.zeros_like(rad); w0 = np.zeros_like(wgt)
+    s.film_export(r0, w0)
+    s.film_clear()
+    st1 = s.render_range(npix, spp * npix)
+    r1 = np.zeros_like(rad); w1 = np.zeros_like(wgt)
+    s.film_export(r1, w1)
+    assert np.array_equal(w0 + w1, wgt)
+    close = np.isclose(r0 + r1, rad, rtol=1e-3, atol=1e-3)
+    assert close.mean() > 0.9999
+    s2 = api.Scene(path, state_count=500000)
+    color3, _, _, stats3 = s2.render()
+    for k in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss"):
+        assert stats3[k] == stats[k], k
+    assert np.isclose(color, color3, rtol=1e-3, atol=1e-4).mean() > 0.9999
+    s2.close()
+    s.close()
+
+
 def test_medium_stage_parity(pair_medium):
     s, o, _ = pair_medium
     assert s.info.has_medium == 1 and o.has_medium()

@@ -331,3 +331,28 @@ def test_gbuffers_and_tile_mode_and_gaussian(tmp_path, built):
     assert np.allclose(albedo[..., :3], ref["albedo"][..., :3], atol=2e-3)
     assert np.allclose(normal[..., :3], ref["normal"][..., :3], atol=2e-3)
     s.close()
+
+
+def test_reporter_progress_and_stop(tmp_path, built):
+    """Reporter / should_stop through the C ABI (core/reporter.h, core/renderer.h:44-48): monotone percentages from 0 to 100 on
+    the rendering thread; a truthy return value stops the render without an image."""
+    from btrc_b200 import api, scenes
+
+    path = scenes.make_cornell(str(tmp_path), width=256, height=256, spp=32, state_count=65536)
+    s = api.Scene(path)
+    seen = []
+    s.set_reporter(lambda pct: seen.append(pct) and False)
+    color, _, _, stats = s.render()
+    assert seen[0] == 0.0 and seen[-1] == 100.0 and len(seen) > 10
+    assert all(b >= a for a, b in zip(seen, seen[1:]))
+    assert all(b - a >= 1.0 for a, b in zip(seen[1:-2], seen[2:-1]))  # console.cpp:26-33: steps of at least one percent
+    ref = color.copy()
+    stop_at = []
+    s.set_reporter(lambda pct: (stop_at.append(pct) or True) if pct >= 30.0 else False)
+    with pytest.raises(api.RenderStopped):
+        s.render()
+    assert 30.0 <= stop_at[0] < 100.0 and len(stop_at) == 1
+    s.set_reporter(None)
+    color2, _, _, stats2 = s.render()  # the renderer is reusable after a stop
+    assert stats2["n_gen"] == stats["n_gen"] and np.allclose(color2, ref, rtol=1e-4, atol=1e-5)
+    s.close()
