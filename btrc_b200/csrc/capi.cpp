@@ -68,7 +68,14 @@ void fill_stats(const RenderStats &s, btrc_render_stats_t *out) {
 
 // copies between any two address spaces (unified virtual addressing)
 void copy_any(void *dst, const void *src, size_t bytes) {
-    if (bytes) BTRC_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    if (!bytes) return;
+    auto on_host = [](const void *p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }  // no device at all: plain host memory
+        return a.type == cudaMemoryTypeUnregistered || a.type == cudaMemoryTypeHost;
+    };
+    if (on_host(dst) && on_host(src)) { std::memcpy(dst, src, bytes); return; }  // post-processors on host images need no device
+    BTRC_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
 }
 
 void check_scene(btrc_scene_t *s) {

@@ -76,6 +76,182 @@ void write_hdr(const std::string &filename, int w, int h, const float *rgba) {
     }
 }
 
+// OpenEXR, what tinyexr's SaveEXRImageToFile writes for the reference (utils/image.cpp:50-111): single-part scanline file, three
+// 32-bit float channels named B, G, R, no compression (InitEXRHeader zero-fills compression_type), increasing-y line order.
+void write_exr(const std::string &filename, int w, int h, const float *rgba) {
+    std::vector<uint8_t> out;
+    auto put = [&](const void *p, size_t n) { const uint8_t *b = static_cast<const uint8_t *>(p); out.insert(out.end(), b, b + n); };
+    auto put_i32 = [&](int32_t v) { put(&v, 4); };
+    auto put_f32 = [&](float v) { put(&v, 4); };
+    auto put_str = [&](const char *z) { put(z, std::strlen(z) + 1); };
+    auto attr = [&](const char *name, const char *type, int32_t size) { put_str(name); put_str(type); put_i32(size); };
+    put_i32(20000630);  // magic
+    put_i32(2);         // version 2, no flags
+    attr("channels", "chlist", 3 * 18 + 1);
+    for (const char *c : {"B", "G", "R"}) {
+        put_str(c);
+        put_i32(2);  // FLOAT
+        const uint8_t plinear_reserved[4] = {0, 0, 0, 0};
+        put(plinear_reserved, 4);
+        put_i32(1); put_i32(1);  // sampling
+    }
+    out.push_back(0);
+    attr("compression", "compression", 1); out.push_back(0);
+    attr("dataWindow", "box2i", 16); put_i32(0); put_i32(0); put_i32(w - 1); put_i32(h - 1);
+    attr("displayWindow", "box2i", 16); put_i32(0); put_i32(0); put_i32(w - 1); put_i32(h - 1);
+    attr("lineOrder", "lineOrder", 1); out.push_back(0);
+    attr("pixelAspectRatio", "float", 4); put_f32(1.0f);
+    attr("screenWindowCenter", "v2f", 8); put_f32(0.0f); put_f32(0.0f);
+    attr("screenWindowWidth", "float", 4); put_f32(1.0f);
+    out.push_back(0);  // end of header
+    const uint64_t row_bytes = 8 + 12ull * (uint64_t)w;
+    uint64_t offset = out.size() + 8ull * (uint64_t)h;
+    for (int y = 0; y < h; ++y, offset += row_bytes) put(&offset, 8);
+    std::vector<float> plane((size_t)w);
+    for (int y = 0; y < h; ++y) {
+        put_i32(y);
+        put_i32(12 * w);
+        for (int c : {2, 1, 0}) {  // B, G, R planes
+            for (int x = 0; x < w; ++x) plane[x] = rgba[4 * ((size_t)y * w + x) + c];
+            put(plane.data(), 4 * (size_t)w);
+        }
+    }
+    std::ofstream f(filename, std::ios::binary);
+    if (!f) throw Error("failed to save exr file: " + filename);
+    f.write(reinterpret_cast<const char *>(out.data()), (std::streamsize)out.size());
+}
+
+// Baseline JPEG (ITU T.81 Annex K tables, quality 90 as stb_image_write picks for the reference's quality argument 0;
+// utils/image.cpp:28-38), YCbCr 4:4:4, one scan.
+void write_jpg_rgb8(const std::string &filename, int w, int h, const std::vector<uint8_t> &rgb) {
+    static const uint8_t zz[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                                   35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    static const uint8_t qy[64] = {16, 11, 10, 16, 24, 40, 51, 61, 12, 12, 14, 19, 26, 58, 60, 55, 14, 13, 16, 24, 40, 57, 69, 56, 14, 17, 22, 29, 51, 87, 80, 62,
+                                   18, 22, 37, 56, 68, 109, 103, 77, 24, 35, 55, 64, 81, 104, 113, 92, 49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+    static const uint8_t qc[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99, 24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99,
+                                   99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};
+    static const uint8_t dc_y_bits[17] = {0, 0, 1, 5, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0}, dc_c_bits[17] = {0, 0, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0};
+    static const uint8_t dc_vals[12] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11};
+    static const uint8_t ac_y_bits[17] = {0, 0, 2, 1, 3, 3, 2, 4, 3, 5, 5, 4, 4, 0, 0, 1, 0x7d}, ac_c_bits[17] = {0, 0, 2, 1, 2, 4, 4, 3, 4, 7, 5, 4, 4, 0, 1, 2, 0x77};
+    static const uint8_t ac_y_vals[162] = {
+        0x01, 0x02, 0x03, 0x00, 0x04, 0x11, 0x05, 0x12, 0x21, 0x31, 0x41, 0x06, 0x13, 0x51, 0x61, 0x07, 0x22, 0x71, 0x14, 0x32, 0x81, 0x91, 0xa1, 0x08, 0x23, 0x42, 0xb1,
+        0xc1, 0x15, 0x52, 0xd1, 0xf0, 0x24, 0x33, 0x62, 0x72, 0x82, 0x09, 0x0a, 0x16, 0x17, 0x18, 0x19, 0x1a, 0x25, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x34, 0x35, 0x36, 0x37,
+        0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46, 0x47, 0x48, 0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58, 0x59, 0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69, 0x6a,
+        0x73, 0x74, 0x75, 0x76, 0x77, 0x78, 0x79, 0x7a, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99, 0x9a, 0xa2, 0xa3,
+        0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba, 0xc2, 0xc3, 0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca, 0xd2, 0xd3,
+        0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda, 0xe1, 0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf1, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa};
+    static const uint8_t ac_c_vals[162] = {
+        0x00, 0x01, 0x02, 0x03, 0x11, 0x04, 0x05, 0x21, 0x31, 0x06, 0x12, 0x41, 0x51, 0x07, 0x61, 0x71, 0x13, 0x22, 0x32, 0x81, 0x08, 0x14, 0x42, 0x91, 0xa1, 0xb1, 0xc1,
+        0x09, 0x23, 0x33, 0x52, 0xf0, 0x15, 0x62, 0x72, 0xd1, 0x0a, 0x16, 0x24, 0x34, 0xe1, 0x25, 0xf1, 0x17, 0x18, 0x19, 0x1a, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x35, 0x36,
+        0x37, 0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46, 0x47, 0x48, 0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58, 0x59, 0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69,
+        0x6a, 0x73, 0x74, 0x75, 0x76, 0x77, 0x78, 0x79, 0x7a, 0x82, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99, 0x9a,
+        0xa2, 0xa3, 0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba, 0xc2, 0xc3, 0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca,
+        0xd2, 0xd3, 0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda, 0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa};
+    struct Huff { uint16_t code[256]; uint8_t len[256]; };
+    auto build = [](const uint8_t *bits, const uint8_t *vals, Huff &t) {
+        std::memset(&t, 0, sizeof(t));
+        int code = 0, k = 0;
+        for (int l = 1; l <= 16; ++l, code <<= 1)
+            for (int i = 0; i < bits[l]; ++i, ++k, ++code) { t.code[vals[k]] = (uint16_t)code; t.len[vals[k]] = (uint8_t)l; }
+    };
+    Huff hdc_y, hdc_c, hac_y, hac_c;
+    build(dc_y_bits, dc_vals, hdc_y); build(dc_c_bits, dc_vals, hdc_c); build(ac_y_bits, ac_y_vals, hac_y); build(ac_c_bits, ac_c_vals, hac_c);
+    const int quality = 90, scale = 200 - 2 * quality;
+    uint8_t tq[2][64];
+    for (int i = 0; i < 64; ++i) {
+        tq[0][i] = (uint8_t)std::min(std::max((qy[i] * scale + 50) / 100, 1), 255);
+        tq[1][i] = (uint8_t)std::min(std::max((qc[i] * scale + 50) / 100, 1), 255);
+    }
+    std::vector<uint8_t> out;
+    auto put = [&](std::initializer_list<int> b) { for (int v : b) out.push_back((uint8_t)v); };
+    put({0xff, 0xd8, 0xff, 0xe0, 0, 16, 'J', 'F', 'I', 'F', 0, 1, 1, 0, 0, 1, 0, 1, 0, 0});
+    for (int t = 0; t < 2; ++t) {
+        put({0xff, 0xdb, 0, 67, t});
+        for (int i = 0; i < 64; ++i) out.push_back(tq[t][zz[i]]);
+    }
+    put({0xff, 0xc0, 0, 17, 8, h >> 8, h & 255, w >> 8, w & 255, 3, 1, 0x11, 0, 2, 0x11, 1, 3, 0x11, 1});
+    auto dht = [&](int cls_id, const uint8_t *bits, const uint8_t *vals, int n) {
+        put({0xff, 0xc4, (19 + n) >> 8, (19 + n) & 255, cls_id});
+        for (int l = 1; l <= 16; ++l) out.push_back(bits[l]);
+        for (int i = 0; i < n; ++i) out.push_back(vals[i]);
+    };
+    dht(0x00, dc_y_bits, dc_vals, 12); dht(0x10, ac_y_bits, ac_y_vals, 162); dht(0x01, dc_c_bits, dc_vals, 12); dht(0x11, ac_c_bits, ac_c_vals, 162);
+    put({0xff, 0xda, 0, 12, 3, 1, 0x00, 2, 0x11, 3, 0x11, 0, 63, 0});
+    uint32_t acc = 0;
+    int nbits = 0;
+    auto emit = [&](uint32_t code, int len) {
+        acc = (acc << len) | (code & ((1u << len) - 1u));
+        nbits += len;
+        while (nbits >= 8) {
+            const uint8_t b = (uint8_t)(acc >> (nbits - 8));
+            out.push_back(b);
+            if (b == 0xff) out.push_back(0);
+            nbits -= 8;
+        }
+    };
+    auto magnitude = [](int v, int &size, uint32_t &bits) {
+        int a = v < 0 ? -v : v;
+        size = 0;
+        while (a) { ++size; a >>= 1; }
+        bits = (uint32_t)(v < 0 ? v - 1 : v) & ((1u << size) - 1u);
+    };
+    float cosv[8][8];
+    for (int u = 0; u < 8; ++u)
+        for (int x = 0; x < 8; ++x) cosv[u][x] = std::cos((2 * x + 1) * u * 3.14159265358979f / 16.0f) * (u == 0 ? 0.353553391f : 0.5f);
+    int pred[3] = {0, 0, 0};
+    for (int by = 0; by < h; by += 8)
+        for (int bx = 0; bx < w; bx += 8) {
+            float blk[3][64];
+            for (int y = 0; y < 8; ++y)
+                for (int x = 0; x < 8; ++x) {
+                    const uint8_t *p = &rgb[3 * ((size_t)std::min(by + y, h - 1) * w + std::min(bx + x, w - 1))];
+                    const float r = p[0], g = p[1], b = p[2];
+                    blk[0][8 * y + x] = 0.299f * r + 0.587f * g + 0.114f * b - 128.0f;
+                    blk[1][8 * y + x] = -0.168736f * r - 0.331264f * g + 0.5f * b;
+                    blk[2][8 * y + x] = 0.5f * r - 0.418688f * g - 0.081312f * b;
+                }
+            for (int c = 0; c < 3; ++c) {
+                float tmp[64], dct[64];
+                for (int y = 0; y < 8; ++y)
+                    for (int u = 0; u < 8; ++u) {
+                        float a = 0;
+                        for (int x = 0; x < 8; ++x) a += blk[c][8 * y + x] * cosv[u][x];
+                        tmp[8 * y + u] = a;
+                    }
+                for (int v = 0; v < 8; ++v)
+                    for (int u = 0; u < 8; ++u) {
+                        float a = 0;
+                        for (int y = 0; y < 8; ++y) a += tmp[8 * y + u] * cosv[v][y];
+                        dct[8 * v + u] = a;
+                    }
+                int q[64];
+                const uint8_t *tab = tq[c ? 1 : 0];
+                for (int i = 0; i < 64; ++i) q[i] = (int)std::lround(dct[zz[i]] / tab[zz[i]]);
+                const Huff &hd = c ? hdc_c : hdc_y, &ha = c ? hac_c : hac_y;
+                int size; uint32_t bits;
+                magnitude(q[0] - pred[c], size, bits);
+                pred[c] = q[0];
+                emit(hd.code[size], hd.len[size]);
+                if (size) emit(bits, size);
+                int run = 0;
+                for (int i = 1; i < 64; ++i) {
+                    if (q[i] == 0) { ++run; continue; }
+                    while (run > 15) { emit(ha.code[0xf0], ha.len[0xf0]); run -= 16; }
+                    magnitude(q[i], size, bits);
+                    emit(ha.code[(run << 4) | size], ha.len[(run << 4) | size]);
+                    emit(bits, size);
+                    run = 0;
+                }
+                if (run) emit(ha.code[0], ha.len[0]);
+            }
+        }
+    if (nbits) emit(0x7f, 8 - nbits);
+    put({0xff, 0xd9});
+    std::ofstream f(filename, std::ios::binary);
+    if (!f) throw Error("failed to write jpg file: " + filename);
+    f.write(reinterpret_cast<const char *>(out.data()), (std::streamsize)out.size());
+}
+
 uint32_t get_u32(const uint8_t *p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]; }
 
 int paeth(int a, int b, int c) {
@@ -158,8 +334,16 @@ void save_image_rgba32f(const std::string &filename, int width, int height, cons
         write_png_rgba8(filename, width, height, rgba);
     } else if (ext == "hdr") {
         write_hdr(filename, width, height, data);
-    } else if (ext == "jpg" || ext == "jpeg" || ext == "exr") {
-        throw Error("unsupported image format (use .png or .hdr): " + filename);
+    } else if (ext == "exr") {
+        write_exr(filename, width, height, data);
+    } else if (ext == "jpg" || ext == "jpeg") {
+        std::vector<uint8_t> rgb(3 * (size_t)width * height);
+        for (size_t i = 0; i < (size_t)width * height; ++i)
+            for (int c = 0; c < 3; ++c) {
+                const float v = data[4 * i + c];
+                rgb[3 * i + c] = (uint8_t)std::max(std::isfinite(v) ? std::min(static_cast<int>(v * 256), 255) : 0, 0);  // image.h:212-216
+            }
+        write_jpg_rgb8(filename, width, height, rgb);
     } else
         throw Error("unknown image format: " + filename);
 }
