@@ -134,12 +134,24 @@ struct InstanceInfo {
     uint32_t inner_medium_id;
     uint32_t outer_medium_id;
     uint32_t flag;
+    // copies of the mesh's table pointers (GeometryInfo): hit reconstruction goes flag -> instance -> tables, one dependent
+    // load less than through scene.geometries[geometry_id]
+    const float4 *gx_ua, *gy_uba, *gz_uca, *sn_va, *sn_vba, *sn_vca;
 };
 
 struct LightInfo {  // MeshLight (builtin/light/mesh_light.cpp)
     int instance_id;
     float intensity[3];
     float inv_scale2;  // 1 / (scale_ * scale_)
+    // copies of what light sampling needs from the instance and its mesh (sampling goes light -> alias entry -> triangle:
+    // three dependent loads instead of five through instances[] and geometries[])
+    int prim_count;
+    float total_area;
+    const float2 *area_alias;
+    const float *positions;
+    const float4 *gz_uca;
+    float mat[12];  // local_to_world of the instance
+    float inv[12];  // world_to_local
 };
 
 struct CameraInfo {  // builtin/camera/pinhole.cpp:55-77

@@ -294,8 +294,7 @@ __global__ void __launch_bounds__(kBlock) medium_kernel(SceneDevice scene, Rende
             if (flag & kFlagHasIntersection) {
                 const uint4 det = hq.detail[i];
                 const InstanceInfo &inst = scene.instances[flag & kFlagInstanceMask];
-                const GeometryInfo &geo = scene.geometries[inst.geometry_id];
-                const f3 inct_nor = xf_normal(inst.inv, xyz(ldg4(geo.gz_uca + det.y)));
+                const f3 inct_nor = xf_normal(inst.inv, xyz(ldg4(inst.gz_uca + det.y)));
                 const uint32_t inct_medium_id = dot(d, inct_nor) < 0.0f ? inst.outer_medium_id : inst.inner_medium_id;
                 medium_id = min(inct_medium_id, __float_as_uint(o4.w));  // resolve_mediums: smaller id = higher priority
                 medium_end = intersection_offset(o + __uint_as_float(det.x) * d, inct_nor, -d);
@@ -412,8 +411,7 @@ shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQu
             const float bsdf_pdf = ble4.w;
             const uint4 det = hq.detail[i];
             const InstanceInfo &inst = scene.instances[flag & kFlagInstanceMask];
-            const GeometryInfo &geo = scene.geometries[inst.geometry_id];
-            const SurfacePoint inct = get_hitinfo(o, d, inst, geo, __uint_as_float(det.x), det.y,
+            const SurfacePoint inct = get_hitinfo(o, d, inst, __uint_as_float(det.x), det.y,
                                                   make_float2(__uint_as_float(det.z), __uint_as_float(det.w)));
             const f3 le_rad = handle_intersected_light(scene, o, d, inct, beta_le, bsdf_pdf, inst.light_id);
             if (scattered) {

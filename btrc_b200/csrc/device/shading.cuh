@@ -61,11 +61,11 @@ struct SurfacePoint {
     float2 tex_coord;
 };
 
-__device__ __forceinline__ SurfacePoint get_hitinfo(f3 o, f3 d, const InstanceInfo &inst, const GeometryInfo &geo, float t, uint32_t prim, float2 uv) {
+__device__ __forceinline__ SurfacePoint get_hitinfo(f3 o, f3 d, const InstanceInfo &inst, float t, uint32_t prim, float2 uv) {
     SurfacePoint sp;
     sp.position = o + t * d;
-    const float4 gx = ldg4(geo.gx_ua + prim), gy = ldg4(geo.gy_uba + prim), gz = ldg4(geo.gz_uca + prim);
-    const float4 sa = ldg4(geo.sn_va + prim), sba = ldg4(geo.sn_vba + prim), sca = ldg4(geo.sn_vca + prim);
+    const float4 gx = ldg4(inst.gx_ua + prim), gy = ldg4(inst.gy_uba + prim), gz = ldg4(inst.gz_uca + prim);
+    const float4 sa = ldg4(inst.sn_va + prim), sba = ldg4(inst.sn_vba + prim), sca = ldg4(inst.sn_vca + prim);
     Frame3 gf(xyz(gx), xyz(gy), xyz(gz));
     gf.x = normalize(xf_vector(inst.mat, gf.x));
     gf.y = normalize(xf_vector(inst.mat, gf.y));
@@ -171,17 +171,15 @@ __device__ __forceinline__ LiSample sample_light_li(const SceneDevice &scene, f3
         return r;
     }
     const LightInfo &li = scene.lights[idx];
-    const InstanceInfo &linst = scene.instances[li.instance_id];
-    const GeometryInfo &geo = scene.geometries[linst.geometry_id];
-    const uint32_t prim = alias_sample(geo.area_alias, (uint32_t)geo.prim_count, s0);
+    const uint32_t prim = alias_sample(li.area_alias, (uint32_t)li.prim_count, s0);
     const float2 uv = sample_triangle_uniform(s1, s2);
-    const float *pp = geo.positions + 9 * (size_t)prim;
+    const float *pp = li.positions + 9 * (size_t)prim;
     const f3 a(__ldg(pp), __ldg(pp + 1), __ldg(pp + 2)), ba(__ldg(pp + 3), __ldg(pp + 4), __ldg(pp + 5)), ca(__ldg(pp + 6), __ldg(pp + 7), __ldg(pp + 8));
     const f3 pos = a + ba * uv.x + ca * uv.y;
-    const f3 ez = normalize(xyz(ldg4(geo.gz_uca + prim)));  // CFrame(ex, ey, ez).z
-    const float pdf_area = 1.0f / geo.total_area;
-    const f3 spos = xf_point(linst.mat, pos);
-    const f3 snor = normalize(xf_normal(linst.inv, ez));
+    const f3 ez = normalize(xyz(ldg4(li.gz_uca + prim)));  // CFrame(ex, ey, ez).z
+    const float pdf_area = 1.0f / li.total_area;
+    const f3 spos = xf_point(li.mat, pos);
+    const f3 snor = normalize(xf_normal(li.inv, ez));
     const f3 pos_to_ref = ref_pos - spos;
     const float dist2 = length_square(pos_to_ref);
     const float pdf_sa = li.inv_scale2 * pdf_area * dist2 / fabsf(dot(snor, normalize(pos_to_ref)));
@@ -221,8 +219,7 @@ __device__ __forceinline__ f3 handle_intersected_light(const SceneDevice &scene,
             const f3 nor = inct.frame.z, pos = inct.position;
             if (dot(nor, o - pos) <= 0.0f) light_dir_pdf = 0.0f;
             else {
-                const GeometryInfo &geo = scene.geometries[scene.instances[li.instance_id].geometry_id];
-                const float pdf_area = 1.0f / geo.total_area;
+                const float pdf_area = 1.0f / li.total_area;
                 const f3 spt_to_ref = o - pos;
                 const float dist2 = length_square(spt_to_ref);
                 const float dist3 = sqrtf(dist2) * dist2;

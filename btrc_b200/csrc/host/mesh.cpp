@@ -66,11 +66,11 @@ bool parse_corner(const char *&p, Corner &c, int nv, int nt, int nn) {
     return true;
 }
 
-Vec3 frame_from_z_x(Vec3 z) {  // Frame::from_z(nor).x -- utils/math/frame.cpp:45-57 (result is not normalised)
+Vec3 frame_from_z_x(Vec3 z) {  // Frame::from_z(nor).x -- utils/math/frame.cpp:45-57; the Frame constructor normalises its axes (frame.cpp:11-15)
     Vec3 nz = normalize(z), ny;
     if (1 - std::fabs(nz.x) < 0.1f) ny = cross(nz, Vec3(0, 1, 0));
     else ny = cross(nz, Vec3(1, 0, 0));
-    return cross(nz, ny);
+    return normalize(cross(nz, ny));
 }
 
 Vec3 triangle_dpdu(Vec3 B_A, Vec3 C_A, Vec2 b_a, Vec2 c_a, Vec3 nor) {  // utils/math/triangle.h:8-22
@@ -143,6 +143,9 @@ MeshData load_triangle_mesh(const std::string &filename, bool to_unit_cube) {
         if (*p == '\n') ++p;
     }
 
+    // geometry frames come from the positions as read: the reference computes them in the loader's constructor and
+    // rescales the positions afterwards (triangle_mesh_loader.cpp:80-123 vs 193-213; builtin/geometry/triangle_mesh.cpp:26-28)
+    const std::vector<Vec3> vs_read = to_unit_cube ? vs : std::vector<Vec3>();
     if (to_unit_cube) {  // triangle_mesh_loader.cpp:193-213
         Vec3 lower(3.402823466e+38f), upper(-3.402823466e+38f);
         for (auto &v : vs) { lower = vmin(lower, v); upper = vmax(upper, v); }
@@ -165,7 +168,8 @@ MeshData load_triangle_mesh(const std::string &filename, bool to_unit_cube) {
         const Corner *c = &corners[3 * i];
         const Vec3 a = vs[c[0].v], b = vs[c[1].v], cc = vs[c[2].v];
         m.pos[3 * i] = a; m.pos[3 * i + 1] = b; m.pos[3 * i + 2] = cc;
-        const Vec3 geo_z = normalize(cross(b - a, cc - a));  // loader.cpp:86
+        const Vec3 fa = to_unit_cube ? vs_read[c[0].v] : a, fb = to_unit_cube ? vs_read[c[1].v] : b, fc = to_unit_cube ? vs_read[c[2].v] : cc;
+        const Vec3 geo_z = normalize(cross(fb - fa, fc - fa));  // loader.cpp:86
         Vec3 sz[3];
         Vec2 tc[3];
         for (int k = 0; k < 3; ++k) {
@@ -181,7 +185,7 @@ MeshData load_triangle_mesh(const std::string &filename, bool to_unit_cube) {
                 tc[k] = vts[c[k].t];
             }
         }
-        const Vec3 gx = triangle_dpdu(b - a, cc - a, Vec2{tc[1].x - tc[0].x, tc[1].y - tc[0].y},
+        const Vec3 gx = triangle_dpdu(fb - fa, fc - fa, Vec2{tc[1].x - tc[0].x, tc[1].y - tc[0].y},
                                       Vec2{tc[2].x - tc[0].x, tc[2].y - tc[0].y}, geo_z);
         const Vec3 gz = geo_z;
         const Vec3 gy = normalize(cross(gz, gx));  // triangle_mesh.cpp:52

@@ -13,17 +13,20 @@ namespace btrc {
 // host_math.h: transform factories (mat4.cpp:108-184, transform.cpp:92-125)
 // ----------------------------------------------------------------------------------------------
 static Mat4 mat_rotate_axis(Vec3 axis, float rad) {  // mat4.cpp:117-145
+    // Drop-in quirk: the reference fills its column-major storage (Mat4::at(r, c) = data[c][r], mat4.cpp:98-106) with the
+    // textbook row-major entries, so "rotate" about an axis is the transpose of the usual matrix, i.e. it turns by -rad.
+    // Pinned against the reference's own code (tests/test_reference_host_pins_cpu.py); reproduced, not fixed.
     const Vec3 a = normalize(axis);
     const float sinv = std::sin(rad), cosv = std::cos(rad);
     Mat4 r = Mat4::identity();
     r.m[0][0] = a.x * a.x + (1 - a.x * a.x) * cosv;
-    r.m[0][1] = a.x * a.y * (1 - cosv) - a.z * sinv;
-    r.m[0][2] = a.x * a.z * (1 - cosv) + a.y * sinv;
-    r.m[1][0] = a.x * a.y * (1 - cosv) + a.z * sinv;
+    r.m[1][0] = a.x * a.y * (1 - cosv) - a.z * sinv;
+    r.m[2][0] = a.x * a.z * (1 - cosv) + a.y * sinv;
+    r.m[0][1] = a.x * a.y * (1 - cosv) + a.z * sinv;
     r.m[1][1] = a.y * a.y + (1 - a.y * a.y) * cosv;
-    r.m[1][2] = a.y * a.z * (1 - cosv) - a.x * sinv;
-    r.m[2][0] = a.x * a.z * (1 - cosv) - a.y * sinv;
-    r.m[2][1] = a.y * a.z * (1 - cosv) + a.x * sinv;
+    r.m[2][1] = a.y * a.z * (1 - cosv) - a.x * sinv;
+    r.m[0][2] = a.x * a.z * (1 - cosv) - a.y * sinv;
+    r.m[1][2] = a.y * a.z * (1 - cosv) + a.x * sinv;
     r.m[2][2] = a.z * a.z + (1 - a.z * a.z) * cosv;
     return r;
 }

@@ -760,6 +760,19 @@ void Scene::upload_device() {
     dev.bvh.root_ref = flat_bvh.root_ref;
     dev.bvh.n_tris = (int)world_tris.size();
     if (!filter_alias.empty()) dev.filter_alias = reinterpret_cast<const float2 *>(upload(filter_alias));
+    for (InstanceInfo &info : instance_info) {  // table pointers of the instance's mesh, denormalised (types.h)
+        const GeometryInfo &g = geos[info.geometry_id];
+        info.gx_ua = g.gx_ua; info.gy_uba = g.gy_uba; info.gz_uca = g.gz_uca;
+        info.sn_va = g.sn_va; info.sn_vba = g.sn_vba; info.sn_vca = g.sn_vca;
+    }
+    for (LightInfo &li : lights) {
+        const InstanceInfo &info = instance_info[li.instance_id];
+        const GeometryInfo &g = geos[info.geometry_id];
+        li.prim_count = g.prim_count; li.total_area = g.total_area;
+        li.area_alias = g.area_alias; li.positions = g.positions; li.gz_uca = g.gz_uca;
+        std::memcpy(li.mat, info.mat, sizeof(li.mat));
+        std::memcpy(li.inv, info.inv, sizeof(li.inv));
+    }
     dev.instances = upload(instance_info);
     {
         std::vector<uint8_t> cls(instance_info.size());

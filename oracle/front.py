@@ -74,7 +74,7 @@ def lib():
         L.orc_shadow_tr.argtypes = [c_void_p, c_int] + [POINTER(c_float)] * 3
         L.orc_has_medium.argtypes = [c_void_p]
         L.orc_bsdf_probe.argtypes = [c_void_p, c_int, POINTER(c_float), POINTER(c_float), c_int] + [POINTER(c_float)] * 8
-        L.orc_add_mesh.argtypes = [c_void_p, c_int, POINTER(c_float), POINTER(c_float), POINTER(c_uint8), POINTER(c_float)]
+        L.orc_add_mesh.argtypes = [c_void_p, c_int, POINTER(c_float), POINTER(c_float), POINTER(c_uint8), POINTER(c_float), POINTER(c_float)]
         L.orc_add_instance.argtypes = [c_void_p, c_int, c_int, POINTER(c_float), POINTER(c_float), c_int, POINTER(c_float), c_int, c_int]
         L.orc_set_camera.argtypes = [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float), c_float]
         L.orc_set_film.argtypes = [c_void_p, c_int, c_int]
@@ -412,7 +412,9 @@ def _rot_axis(axis, rad):  # mat4.cpp:117-145
     m[2, 1] = f32(f32(y * z) * f32(one - c)) + f32(x * s)
     m[2, 2] = f32(z * z) + f32(f32(one - f32(z * z)) * c)
     m[3, 3] = 1
-    return m
+    # Mat4 is column-major (at(r, c) = data[c][r], mat4.cpp:98-106) and Mat4::rotate writes data[i][j] with the textbook ROW-major
+    # entries: the matrix the reference uses is the transpose (a turn by -rad).  Pinned by tests/test_reference_host_pins_cpu.py.
+    return np.ascontiguousarray(m.T)
 
 
 def _rot_x(rad):
@@ -570,13 +572,16 @@ class OracleScene:
         return os.path.normpath(os.path.abspath(p.replace("$env{scene_directory}", self.scene_dir)))
 
     # -- construction helpers (usable without a JSON file, e.g. the lib/bvh golden test)
-    def add_mesh_arrays(self, pos, nor=None, has_nor=None, uv=None):
+    def add_mesh_arrays(self, pos, nor=None, has_nor=None, uv=None, frame_pos=None):
+        """frame_pos: the positions as read from the file when `pos` went through transform_to_unit_cube (the reference derives the
+        geometry frames before that rescale: triangle_mesh_loader.cpp:80-123 vs 193-213)."""
         pos = np.ascontiguousarray(pos, f32)
+        frame_pos = None if frame_pos is None else np.ascontiguousarray(frame_pos, f32)
         ntri = pos.shape[0] // 3
         nor = None if nor is None else np.ascontiguousarray(nor, f32)
         has_nor = None if has_nor is None else np.ascontiguousarray(has_nor, np.uint8)
         uv = None if uv is None else np.ascontiguousarray(uv, f32)
-        mid = self.L.orc_add_mesh(self.h, ntri, _ptr(pos, c_float), _ptr(nor, c_float), _ptr(has_nor, c_uint8), _ptr(uv, c_float))
+        mid = self.L.orc_add_mesh(self.h, ntri, _ptr(pos, c_float), _ptr(nor, c_float), _ptr(has_nor, c_uint8), _ptr(uv, c_float), _ptr(frame_pos, c_float))
         self.mesh_data.append((pos, nor, has_nor, uv))
         return mid
 
@@ -811,9 +816,10 @@ class OracleScene:
                 raise ValueError("unknown geometry type: " + g.child("type").as_str())
             if ("geo", id(g.raw)) not in pool:
                 pos, nor, has_nor, uv = load_obj(self.resolve(g.child("filename").as_str()))
+                read_pos = None
                 if g.bool_or("transform_to_unit_cube", False):
-                    pos = _to_unit_cube(pos)
-                pool[("geo", id(g.raw))] = self.add_mesh_arrays(pos, nor, has_nor, uv)
+                    read_pos, pos = pos, _to_unit_cube(pos)
+                pool[("geo", id(g.raw))] = self.add_mesh_arrays(pos, nor, has_nor, uv, read_pos)
             m = ent.child("material")
             if ("mat", id(m.raw)) not in pool:
                 pool[("mat", id(m.raw))] = self.add_material(m)

@@ -126,7 +126,9 @@ struct AliasTable {
     std::vector<AliasUnit> units;
     void initialize(const std::vector<float> &probs) {
         float sum = 0.0f;
-        for (float p : probs) sum = sum + p;  // std::reduce(.., 0.0f, plus) -- sequential in libstdc++
+        // std::reduce(.., 0.0f, plus) leaves the association order unspecified: MSVC, the reference's toolchain, adds sequentially
+        // under /fp:precise (libstdc++ adds in groups of four; tests/test_reference_host_pins_cpu.py pins both regimes)
+        for (float p : probs) sum = sum + p;
         const float ratio = probs.size() / sum;
         std::vector<uint32_t> overs, unders;
         units.resize(probs.size());
@@ -293,11 +295,12 @@ namespace {
 // Mesh tables: utils/triangle_mesh_loader.cpp:61-123, utils/math/triangle.h:8-22,
 // utils/math/frame.cpp:45-57, builtin/geometry/triangle_mesh.cpp:40-171
 // ------------------------------------------------------------------------------------------
-V3 host_frame_from_z_x(V3 z) {  // Frame::from_z(nor).x  (frame.cpp:45-57; NOT normalised)
+V3 host_frame_from_z_x(V3 z) {  // Frame::from_z(nor).x  (frame.cpp:45-57); Frame's constructor normalises the axes (frame.cpp:11-15) --
+                                // pinned against the reference's own code by tests/test_reference_host_pins_cpu.py
     V3 new_z = host_normalize(z), new_y;
     if (1 - std::fabs(new_z.x) < 0.1f) new_y = cross(new_z, V3(0, 1, 0));
     else new_y = cross(new_z, V3(1, 0, 0));
-    return cross(new_z, new_y);
+    return host_normalize(cross(new_z, new_y));
 }
 
 V3 triangle_dpdu(V3 B_A, V3 C_A, V2 b_a, V2 c_a, V3 nor) {  // triangle.h:8-22
@@ -308,7 +311,9 @@ V3 triangle_dpdu(V3 B_A, V3 C_A, V2 b_a, V2 c_a, V3 nor) {  // triangle.h:8-22
     return host_normalize(m11 * inv_det * B_A - m01 * inv_det * C_A);
 }
 
-void build_mesh(Mesh &m, int ntri, const float *pos, const float *nor, const uint8_t *has_nor, const float *uv) {
+// frame_pos: the positions as read from the file when `pos` was rescaled by transform_to_unit_cube -- the reference computes the
+// geometry frames in the loader's constructor, before the rescale (triangle_mesh_loader.cpp:80-123 vs 193-213); null = same as pos
+void build_mesh(Mesh &m, int ntri, const float *pos, const float *nor, const uint8_t *has_nor, const float *uv, const float *frame_pos) {
     m.ntri = ntri;
     m.pos.resize(3 * (size_t)ntri);
     for (size_t i = 0; i < 3 * (size_t)ntri; ++i) m.pos[i] = V3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
@@ -318,7 +323,9 @@ void build_mesh(Mesh &m, int ntri, const float *pos, const float *nor, const uin
     std::vector<float> areas(ntri);
     for (int i = 0; i < ntri; ++i) {
         const V3 a = m.pos[3 * i], b = m.pos[3 * i + 1], c = m.pos[3 * i + 2];
-        const V3 geo_z = host_normalize(cross(b - a, c - a));  // loader.cpp:86
+        const float *fp = frame_pos ? frame_pos + 9 * (size_t)i : nullptr;
+        const V3 fa = fp ? V3(fp[0], fp[1], fp[2]) : a, fb = fp ? V3(fp[3], fp[4], fp[5]) : b, fc = fp ? V3(fp[6], fp[7], fp[8]) : c;
+        const V3 geo_z = host_normalize(cross(fb - fa, fc - fa));  // loader.cpp:86
         V3 sz[3]; V2 tc[3];
         for (int k = 0; k < 3; ++k) {
             const size_t j = 3 * (size_t)i + k;
@@ -329,7 +336,7 @@ void build_mesh(Mesh &m, int ntri, const float *pos, const float *nor, const uin
             }
             tc[k] = uv ? V2{uv[2 * j], uv[2 * j + 1]} : V2{0, 0};
         }
-        const V3 gx = triangle_dpdu(b - a, c - a, V2{tc[1].x - tc[0].x, tc[1].y - tc[0].y},
+        const V3 gx = triangle_dpdu(fb - fa, fc - fa, V2{tc[1].x - tc[0].x, tc[1].y - tc[0].y},
                                     V2{tc[2].x - tc[0].x, tc[2].y - tc[0].y}, geo_z);
         const V3 gz = geo_z;
         const V3 gy = host_normalize(cross(gz, gx));  // triangle_mesh.cpp:52
@@ -1443,9 +1450,9 @@ void orc_set_gradient_sky(orc_scene *s, const float *lower, const float *upper, 
     s->sky_up = host_normalize(V3(up[0], up[1], up[2]));  // gradient_sky.cpp:15-18
 }
 
-int orc_add_mesh(orc_scene *s, int ntri, const float *pos, const float *nor, const uint8_t *has_nor, const float *uv) {
+int orc_add_mesh(orc_scene *s, int ntri, const float *pos, const float *nor, const uint8_t *has_nor, const float *uv, const float *frame_pos) {
     s->meshes.emplace_back();
-    build_mesh(s->meshes.back(), ntri, pos, nor, has_nor, uv);
+    build_mesh(s->meshes.back(), ntri, pos, nor, has_nor, uv, frame_pos);
     return (int)s->meshes.size() - 1;
 }
 

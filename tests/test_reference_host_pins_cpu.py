@@ -1,0 +1,218 @@
+"""Pins of the oracle (and of the product's host loader) against the REFERENCE'S OWN host-side code, compiled from
+/root/reference where it lies into oracle/_ref/libbtrcref.so (oracle/Makefile `ref`, oracle/ref_host.cpp):
+
+  * AliasTable::initialize (utils/math/alias.cpp)          -> the oracle's alias tables, bit for bit
+  * TriangleMeshLoader + vendored tinyobj                   -> triangle order (= primitive ids), positions, uv, normals,
+    (utils/triangle_mesh_loader.cpp)                           geometry frames: the oracle's and the product's mesh tables
+  * Transform3D factories and composition (utils/math/*.cpp) -> instance transforms, including the rotate_z quirk
+
+The .so is built in the dev container and travels to the GPU box; nothing here reads /root/reference at run time.  Skipped
+when the prebuilt library is absent."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import ROOT, f32
+
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libbtrcref.so")
+pytestmark = pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libbtrcref.so not built (reference tree absent)")
+
+
+@pytest.fixture(scope="module")
+def R():
+    L = ctypes.CDLL(REF_SO)
+    L.ref_last_error.restype = ctypes.c_char_p
+    L.ref_alias_build.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 3
+    L.ref_mesh_load.restype = ctypes.c_void_p
+    L.ref_mesh_load.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    L.ref_mesh_free.argtypes = [ctypes.c_void_p]
+    L.ref_mesh_prim_count.argtypes = [ctypes.c_void_p]
+    L.ref_mesh_get.argtypes = [ctypes.c_void_p] * 6
+    L.ref_transform_compose.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 4
+    return L
+
+
+def _ref_tables(R, path, unit_cube=False):
+    """The six float4 tables of builtin/geometry/triangle_mesh.cpp:40-67 from the reference loader's outputs."""
+    h = R.ref_mesh_load(path.encode(), 1 if unit_cube else 0)
+    assert h, R.ref_last_error()
+    n = R.ref_mesh_prim_count(h)
+    pos = np.zeros((n, 3, 3), f32); uv = np.zeros((n, 3, 2), f32); nz = np.zeros((n, 3, 3), f32)
+    ex = np.zeros((n, 3), f32); ez = np.zeros((n, 3), f32)
+    R.ref_mesh_get(h, pos.ctypes.data, uv.ctypes.data, nz.ctypes.data, ex.ctypes.data, ez.ctypes.data)
+    R.ref_mesh_free(h)
+
+    def cross(a, b):
+        return np.stack([(a[:, 1] * b[:, 2]).astype(f32) - (a[:, 2] * b[:, 1]).astype(f32),
+                         (a[:, 2] * b[:, 0]).astype(f32) - (a[:, 0] * b[:, 2]).astype(f32),
+                         (a[:, 0] * b[:, 1]).astype(f32) - (a[:, 1] * b[:, 0]).astype(f32)], axis=1).astype(f32)
+
+    c = cross(ez, ex)
+    ln = np.sqrt((((c[:, 0] * c[:, 0]).astype(f32) + (c[:, 1] * c[:, 1]).astype(f32)).astype(f32) + (c[:, 2] * c[:, 2]).astype(f32)).astype(f32)).astype(f32)
+    ey = (c * (f32(1) / ln)[:, None]).astype(f32)  # vec3.h:110-114: normalize = 1 / length * v
+    t = np.zeros((n, 24), f32)
+    t[:, 0:3] = ex; t[:, 3] = uv[:, 0, 0]
+    t[:, 4:7] = ey; t[:, 7] = uv[:, 1, 0] - uv[:, 0, 0]
+    t[:, 8:11] = ez; t[:, 11] = uv[:, 2, 0] - uv[:, 0, 0]
+    t[:, 12:15] = nz[:, 0]; t[:, 15] = uv[:, 0, 1]
+    t[:, 16:19] = nz[:, 1] - nz[:, 0]; t[:, 19] = uv[:, 1, 1] - uv[:, 0, 1]
+    t[:, 20:23] = nz[:, 2] - nz[:, 0]; t[:, 23] = uv[:, 2, 1] - uv[:, 0, 1]
+    return pos, t
+
+
+def test_alias_tables_match_reference(R, built):
+    """AliasTable::initialize.  The reference sums the weights with std::reduce, whose association order is unspecified: MSVC
+    (the toolchain the reference is written for) adds sequentially under /fp:precise, libstdc++ (this build of _ref) adds in
+    groups of four.  Weights whose partial sums are exact in fp32 (multiples of 2^-6 up to 1) make the order irrelevant, and
+    there the oracle reproduces the reference's table bit for bit; for arbitrary weights the two sums differ in the last bits,
+    so a pairing decision can flip; there both tables must encode the input distribution (to fp32 accuracy)."""
+    from oracle import front
+
+    L = front.lib()
+    rng = np.random.default_rng(17)
+
+    def both(probs):
+        n = probs.shape[0]
+        a0 = np.zeros(n, f32); i0 = np.zeros(n, np.uint32)
+        a1 = np.zeros(n, f32); i1 = np.zeros(n, np.uint32)
+        p0, p1 = probs.copy(), probs.copy()
+        R.ref_alias_build(n, p0.ctypes.data, a0.ctypes.data, i0.ctypes.data)
+        L.orc_alias_build(n, p1.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), a1.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                          i1.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+        return a0, i0, a1, i1
+
+    exact = [np.array([1.0], f32), np.array([0.25, 0.75], f32), np.full(64, 0.125, f32)]
+    for n in (3, 36, 1000, 4099, 65536):
+        w = rng.integers(0, 65, n).astype(f32) / f32(64)                # multiples of 2^-6 up to 1: every partial sum is exact (< 2^24 * 2^-6)
+        w[rng.random(n) < 0.2] = 0
+        w[0] = max(w[0], f32(1 / 64))
+        exact.append(w)
+    for probs in exact:
+        a0, i0, a1, i1 = both(np.ascontiguousarray(probs, f32))
+        assert np.array_equal(a0.view(np.uint32), a1.view(np.uint32)), probs.shape
+        assert np.array_equal(i0, i1), probs.shape
+
+    x = (np.arange(256, dtype=f32) + f32(0.5)) / f32(256) * f32(2.6) - f32(1.3)   # shape of the gaussian film filter's table (gaussian.cpp:27-52)
+    g = np.maximum(np.exp(-1.6 * x * x) - np.exp(-1.6 * 1.3 * 1.3), 0).astype(f32)
+    general = [rng.random(36).astype(f32), rng.random(4099).astype(f32) ** 4, np.outer(g, g).astype(f32).reshape(-1)]
+    for probs in general:
+        a0, i0, a1, i1 = both(np.ascontiguousarray(probs, f32))
+        n = probs.shape[0]
+        want = probs.astype(np.float64) / probs.astype(np.float64).sum()
+
+        def implied(acc, idx):  # the distribution the table samples from
+            p = acc.astype(np.float64).copy()
+            np.add.at(p, idx, 1.0 - acc.astype(np.float64))
+            return p / n
+
+        # the last entry left over collects the rounding of the weight sum and of every pairing step; a sequential fp32 sum
+        # of 65,536 weights (MSVC order) is less accurate than the grouped one
+        assert np.abs(implied(a0, i0) - want).max() < 1e-6
+        assert np.abs(implied(a1, i1) - want).max() < 2e-5
+        assert (i0 == i1).mean() > 0.9  # the pairing is chaotic in the last bits of the sum; most entries still agree
+
+
+def _write_tricky_obj(path):
+    """Triangles, quads (both diagonals), negative indices, mixed v / v/t / v//n / v/t/n corners, a zero normal, several groups."""
+    rng = np.random.default_rng(23)
+    lines = []
+    V = rng.uniform(-1, 1, (40, 3))
+    for v in V:
+        lines.append("v %.6f %.6f %.6f" % tuple(v))
+    for t in rng.uniform(0, 1, (25, 2)):
+        lines.append("vt %.6f %.6f" % tuple(t))
+    N = rng.normal(size=(12, 3)); N /= np.linalg.norm(N, axis=1, keepdims=True)
+    N[5] = 0
+    for nrm in N:
+        lines.append("vn %.6f %.6f %.6f" % tuple(nrm))
+    lines.append("g first")
+    lines += ["f 1 2 3", "f 4/1 5/2 6/3", "f 7//1 8//2 9//3", "f 10/4/4 11/5/5 12/6/6", "f 13/7/6 14/8/6 15/9/6"]
+    lines.append("o second")
+    lines += ["f 16 17 18 19", "f 20/10 21/11 22/12 23/13", "f -1 -2 -3", "f -4/-1/-1 -5/-2/-2 -6/-3/-3 -7/-4/-4"]
+    lines.append("g third")
+    lines += ["f 24/14/7 25/15/8 26/16/9 27/17/10", "f 28 29 30", "f 1/1/1 30/2/2 15/3/3"]
+    open(path, "w").write("\n".join(lines) + "\n")
+
+
+@pytest.mark.parametrize("case", ["cornell", "sphere", "tricky", "tricky_unit_cube"])
+def test_mesh_loader_matches_reference(R, built, tmp_path, case):
+    """Oracle front-end (oracle/front.py + liborc) and the product's host loader against TriangleMeshLoader: same triangles in
+    the same order, bit-identical positions and shading tables."""
+    from btrc_b200 import api, scenes
+    from oracle import front
+
+    unit = case.endswith("unit_cube")
+    if case == "cornell":
+        path = scenes.make_cornell(str(tmp_path), width=8, height=8, spp=1, state_count=64)
+        objs = [os.path.join(str(tmp_path), f) for f in sorted(os.listdir(tmp_path)) if f.endswith(".obj")]
+    elif case == "sphere":
+        v, f, uv, n = scenes.uv_sphere(9, 14)
+        objs = [os.path.join(str(tmp_path), "sphere.obj")]
+        scenes.write_obj(objs[0], v, f, uv, n)
+    else:
+        objs = [os.path.join(str(tmp_path), "tricky.obj")]
+        _write_tricky_obj(objs[0])
+    for obj in objs:
+        ref_pos, ref_tab = _ref_tables(R, obj, unit)
+        # a one-entity scene around the OBJ for both loaders
+        root = {"width": 8, "height": 8, "camera": {"type": "pinhole", "eye": [0, 0, 5], "dst": [0, 0, 0], "up": [0, 1, 0], "fov_y": {"deg": 40}},
+                "renderer": {"type": "wfpt", "spp": 1, "state_count": 64},
+                "scene": {"entities": [{"geometry": {"type": "triangle_mesh", "filename": obj, "transform_to_unit_cube": unit},
+                                        "material": {"type": "diffuse", "color": [0.5, 0.5, 0.5]}}]}}
+        sp = os.path.join(str(tmp_path), "one.json")
+        json.dump(root, open(sp, "w"))
+        o = front.OracleScene(sp)
+        verts, ids = o.triangles()
+        assert verts.shape[0] == ref_pos.shape[0]
+        assert np.array_equal(verts.reshape(-1, 3, 3).view(np.uint32), ref_pos.view(np.uint32))      # identity transform: world == local
+        assert np.array_equal(ids[:, 1], np.arange(ref_pos.shape[0], dtype=np.uint32))
+        got = o.mesh_tables(0)
+        assert np.array_equal(got.view(np.uint32), ref_tab.view(np.uint32)), os.path.basename(obj)
+        s = api.Scene(sp)                                                                            # product: host side only, no device call
+        assert np.array_equal(s.geometry_tables(0).view(np.uint32), ref_tab.view(np.uint32)), os.path.basename(obj)
+        s.close()
+
+
+def test_transform_composition_matches_reference(R, built, tmp_path):
+    """Scene-file transform arrays through the oracle front-end and the product loader against Transform3D::{translate, rotate,
+    rotate_x/y/z, scale} and operator* of the reference (mat and inv; rotate_z keeps the reference's sign quirk, transform.cpp:112-115)."""
+    from btrc_b200 import api, scenes
+    from oracle import front
+
+    chains = [
+        [("translate", [0.3, -1.25, 2.0])],
+        [("scale", [0.5, 1.25, 0.75]), ("rotate_y", 33.3), ("rotate_z", 11.0), ("translate", [0.1, 0.2, -0.3])],
+        [("rotate", ([0.3, 0.9, -0.2], 57.0)), ("rotate_x", -20.5), ("scale", [2.0, 2.0, 2.0])],
+        [("rotate_z", 90.0), ("rotate_z", -45.0), ("rotate", ([1.0, 1.0, 1.0], 120.0)), ("translate", [5, 6, 7]), ("rotate_x", 1.0)],
+    ]
+    base = scenes.make_cornell(str(tmp_path), width=8, height=8, spp=1, state_count=64)
+    for chain in chains:
+        ops, args, js = [], [], []
+        for kind, a in chain:
+            if kind == "translate":
+                ops.append(0); args.append(list(a) + [0]); js.append({"translate": a})
+            elif kind == "scale":
+                ops.append(5); args.append(list(a) + [0]); js.append({"scale": a})
+            elif kind == "rotate":  # angles are given in radians with six decimals: the same fp32 value reaches both sides
+                axis, deg = a
+                rad = round(float(np.radians(deg)), 6)
+                ops.append(1); args.append(list(axis) + [rad]); js.append({"rotate": {"axis": axis, "angle": {"rad": rad}}})
+            else:
+                rad = round(float(np.radians(a)), 6)
+                ops.append({"rotate_x": 2, "rotate_y": 3, "rotate_z": 4}[kind]); args.append([rad, 0, 0, 0]); js.append({kind: {"rad": rad}})
+        ops = np.array(ops, np.int32); args = np.array(args, f32)
+        mat = np.zeros((4, 4), f32); inv = np.zeros((4, 4), f32)
+        R.ref_transform_compose(len(ops), ops.ctypes.data, args.ctypes.data, mat.ctypes.data, inv.ctypes.data)
+        root = json.load(open(base))
+        root["scene"]["entities"][3]["local_to_world"] = js
+        sp = os.path.join(str(tmp_path), "xf.json")
+        json.dump(root, open(sp, "w"))
+        o = front.OracleScene(sp)
+        assert np.allclose(o.instances[3]["mat"], mat, rtol=0, atol=0) and np.allclose(o.instances[3]["inv"], inv, rtol=0, atol=0), chain
+        s = api.Scene(sp)
+        m3, i3 = s.instance_transform(3)
+        assert np.array_equal(m3, mat[:3]) and np.array_equal(i3, inv[:3]), chain
+        s.close()
