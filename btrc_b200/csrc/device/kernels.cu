@@ -18,6 +18,11 @@ namespace {
 
 constexpr int kBlock = 256;
 constexpr unsigned kFull = 0xffffffffu;
+template <bool ANY_HIT, bool IFIF>
+__device__ __forceinline__ HitRec traverse_warp(const BvhDevice &bvh, float4 o4, float4 d4, bool valid) {  // all 32 lanes call this together
+    if (IFIF) return traverse_bvh2_ifif<ANY_HIT, true>(bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w, valid);
+    return traverse_bvh2<ANY_HIT, true>(bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w, valid);
+}
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
@@ -174,6 +179,7 @@ __device__ __forceinline__ void class_append(const HitQueue &hq, WaveCtl *ctl, b
 #ifndef BTRC_TRACE_MIN_BLOCKS
 #define BTRC_TRACE_MIN_BLOCKS 6
 #endif
+template <bool IFIF>
 __global__ void __launch_bounds__(kBlock, BTRC_TRACE_MIN_BLOCKS) trace_kernel(SceneDevice scene, PathQueue q, HitQueue hq, WaveCtl *ctl) {
     const int n = ctl->n_active;
     unsigned long long hits = 0;
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(kBlock, BTRC_TRACE_MIN_BLOCKS) trace_kernel(Sc
         const bool valid = i < n;
         float4 o4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d4 = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
         if (valid) { o4 = q.ray_o[i]; d4 = q.ray_d[i]; }
-        const HitRec h = traverse_bvh2<false, true>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w, valid);
+        const HitRec h = traverse_warp<false, IFIF>(scene.bvh, o4, d4, valid);
         int cls = 0;
         if (valid) {
             const int inst = store_hit(scene.bvh, h, i, hq.flag, hq.detail);
@@ -502,6 +508,7 @@ shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQu
 // ---------------------------------------------------------------------------------------------------------------
 // shadow rays (shadow.cpp:24-74): occlusion with early exit; unoccluded => splat beta_li * Tr
 // ---------------------------------------------------------------------------------------------------------------
+template <bool IFIF>
 __global__ void __launch_bounds__(kBlock, BTRC_TRACE_MIN_BLOCKS) shadow_kernel(SceneDevice scene, RenderParams P, ShadowQueue sq, FilmDevice film, WaveCtl *ctl) {
     const int n = ctl->n_shadow;
     unsigned long long misses = 0;
@@ -514,7 +521,7 @@ __global__ void __launch_bounds__(kBlock, BTRC_TRACE_MIN_BLOCKS) shadow_kernel(S
         const bool valid = i < n;
         float4 o4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d4 = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
         if (valid) { o4 = sq.ray_o[i]; d4 = sq.ray_d[i]; }
-        const HitRec h = traverse_bvh2<true, true>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w, valid);
+        const HitRec h = traverse_warp<true, IFIF>(scene.bvh, o4, d4, valid);
         if (valid && h.slot < 0) {  // unoccluded: the reference's miss program (shadow.cpp:39-74)
             const float4 b4 = sq.beta_li[i];
             f3 v = xyz(b4);
@@ -578,7 +585,8 @@ void launch_generate(const LaunchCfg &cfg, const SceneDevice &scene, const Rende
 }
 
 void launch_trace(const LaunchCfg &cfg, const SceneDevice &scene, PathQueue cur, HitQueue hit, WaveCtl *ctl, cudaStream_t stream) {
-    trace_kernel<<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, cur, hit, ctl);
+    if (cfg.traverse_ifif) trace_kernel<true><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, cur, hit, ctl);
+    else trace_kernel<false><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, cur, hit, ctl);
 }
 
 template <int MAT>
@@ -620,7 +628,8 @@ void launch_medium(const LaunchCfg &cfg, const SceneDevice &scene, const RenderP
 
 void launch_shadow(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, ShadowQueue shadow, FilmDevice film, WaveCtl *ctl,
                    cudaStream_t stream) {
-    shadow_kernel<<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, shadow, film, ctl);
+    if (cfg.traverse_ifif) shadow_kernel<true><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, shadow, film, ctl);
+    else shadow_kernel<false><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, shadow, film, ctl);
 }
 
 void launch_resolve(int width, int height, const float *value, const float *weight, float *out, int normalise, cudaStream_t stream) {

@@ -15,6 +15,10 @@ namespace btrc {
 
 struct LaunchCfg {
     int sm_count = 148;
+    // Loop structure of the traversal kernels (traverse.cuh).  While-while is faster while the BVH lives in L2 (C2: 66.5 vs
+    // 67.8 ms), if-if when node fetches go to DRAM and the extra loads in flight per warp pay (C4, 0.7 GB of BVH: 136 vs 153 ms);
+    // profiles/r1h_ab_ifif.log.  The renderer picks by BVH size against the L2 capacity.
+    bool traverse_ifif = false;
 };
 
 void launch_prepare(WaveCtl *ctl, cudaStream_t stream);

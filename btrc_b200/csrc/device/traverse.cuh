@@ -140,4 +140,75 @@ BTRC_TRAV_QUAL HitRec traverse_bvh2(const BvhDevice &bvh, float ox, float oy, fl
 }
 
 
+// "if-if" form of the same walk: every iteration a lane does ONE thing -- a triangle of its current leaf, or one node step --
+// and all lanes vote once per iteration.  Lanes that are in a leaf no longer wait for the slowest lane to finish its descent
+// (and vice versa); a warp-level cost model on real C2 ray batches (experiments/simt_sim) gives 11-19 % fewer issue slots for
+// bounce and shadow rays than the while-while form.  Results are identical (same boxes, same triangle test, same tie rule).
+template <bool ANY_HIT, bool CONVERGE = false>
+BTRC_TRAV_QUAL HitRec traverse_bvh2_ifif(const BvhDevice &bvh, float ox, float oy, float oz, float dx, float dy, float dz, float tmax, bool active = true) {
+    HitRec best;
+    best.t = tmax; best.u = 0.0f; best.v = 0.0f; best.slot = -1;
+    constexpr float kTiny = 1e-20f;
+    const float idx = 1.0f / (fabsf(dx) > kTiny ? dx : copysignf(kTiny, dx));
+    const float idy = 1.0f / (fabsf(dy) > kTiny ? dy : copysignf(kTiny, dy));
+    const float idz = 1.0f / (fabsf(dz) > kTiny ? dz : copysignf(kTiny, dz));
+    const float oox = ox * idx, ooy = oy * idy, ooz = oz * idz;
+
+    int stack[kStackSize];
+    int sp = 0;
+    constexpr int SENTINEL = 0x7fffffff;
+    stack[sp++] = SENTINEL;
+    int cur = active ? bvh.root_ref : SENTINEL;
+    int tri = 0, tri_end = 0;  // triangles [tri, tri_end) of the current leaf are still to be tested
+    if (cur < 0) { const int ref = ~cur; tri = ref >> 3; tri_end = tri + (ref & 7) + 1; cur = stack[--sp]; }  // the root is a leaf
+
+    while (CONVERGE ? __any_sync(0xffffffffu, cur != SENTINEL || tri < tri_end) : (cur != SENTINEL || tri < tri_end)) {
+        if (tri < tri_end) {
+            const int s = tri++;
+            float t, u, v;
+            BTRC_TRAV_COUNT(1);
+            if (tri_test(bvh.tris + 3 * (size_t)s, ox, oy, oz, dx, dy, dz, best.t, t, u, v)) {
+                if (ANY_HIT) {
+                    best.slot = s;
+                    if (!CONVERGE) return best;
+                    tri = tri_end; cur = SENTINEL;  // finished; keeps voting until the warp is done
+                } else if (t < best.t || best.slot < 0 || id_less(bvh.tri_ids, s, best.slot)) {
+                    best.t = t; best.u = u; best.v = v; best.slot = s;
+                }
+            }
+        } else if (cur != SENTINEL) {
+            const float4 *node = bvh.nodes + 4 * (size_t)cur;
+            const float4 n0 = __ldg(node), n1 = __ldg(node + 1), nz = __ldg(node + 2), meta = __ldg(node + 3);
+            BTRC_TRAV_COUNT(0);
+            const float c0lox = fmaf(n0.x, idx, -oox), c0hix = fmaf(n0.y, idx, -oox);
+            const float c0loy = fmaf(n0.z, idy, -ooy), c0hiy = fmaf(n0.w, idy, -ooy);
+            const float c0loz = fmaf(nz.x, idz, -ooz), c0hiz = fmaf(nz.y, idz, -ooz);
+            const float c1lox = fmaf(n1.x, idx, -oox), c1hix = fmaf(n1.y, idx, -oox);
+            const float c1loy = fmaf(n1.z, idy, -ooy), c1hiy = fmaf(n1.w, idy, -ooy);
+            const float c1loz = fmaf(nz.z, idz, -ooz), c1hiz = fmaf(nz.w, idz, -ooz);
+            const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
+            const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), best.t));
+            const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
+            const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), best.t));
+            const bool h0 = c0min <= c0max, h1 = c1min <= c1max;
+            const int r0 = __float_as_int(meta.x), r1 = __float_as_int(meta.y);
+            if (!h0 && !h1) {
+                cur = stack[--sp];
+            } else if (h0 && h1) {
+                const bool swp = c1min < c0min;
+                cur = swp ? r1 : r0;
+                stack[sp++] = swp ? r0 : r1;
+            } else {
+                cur = h0 ? r0 : r1;
+            }
+        }
+        if (tri >= tri_end && cur < 0) {  // arrived at a leaf: take its triangle range and the next node from the stack
+            const int ref = ~cur;
+            tri = ref >> 3; tri_end = tri + (ref & 7) + 1;
+            cur = stack[--sp];
+        }
+    }
+    return best;
+}
+
 }  // namespace btrc

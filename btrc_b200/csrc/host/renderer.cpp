@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 
 namespace btrc {
 
@@ -40,6 +41,11 @@ Renderer::Renderer(Scene &scene, int state_count_override) : scene_(scene) {
     cudaDeviceProp prop;
     BTRC_CUDA(cudaGetDeviceProperties(&prop, dev));
     cfg_.sm_count = prop.multiProcessorCount;
+    {   // traversal loop form by BVH footprint against the L2 (kernels.h: LaunchCfg::traverse_ifif); BTRC_TRAVERSE=ww|ifif overrides
+        const size_t bvh_bytes = scene.flat_bvh.nodes.size() * sizeof(float) + scene.flat_bvh.tris.size() * sizeof(float);
+        cfg_.traverse_ifif = bvh_bytes > (size_t)prop.l2CacheSize;
+        if (const char *e = std::getenv("BTRC_TRAVERSE")) cfg_.traverse_ifif = std::string(e) == "ifif";
+    }
     pool_ = state_count_override > 0 ? state_count_override : scene.renderer.state_count;
     if (pool_ <= 0) throw Error("state_count must be positive");
     BTRC_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));

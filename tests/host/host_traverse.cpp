@@ -35,6 +35,10 @@ static thread_local uint64_t g_count[2];
 
 using namespace btrc;
 
+#ifndef HT_TRAVERSE
+#define HT_TRAVERSE traverse_bvh2   // -DHT_TRAVERSE=traverse_bvh2_ifif builds the if-if form
+#endif
+
 struct HostBvh {
     FlatBvh2 w;
     int n_inner = 0;
@@ -91,7 +95,7 @@ void ht_closest(void *hh, int n, const float *o_med, const float *d_t1, uint32_t
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : n_nodes, n_tests)
     for (int i = 0; i < n; ++i) {
         g_count[0] = g_count[1] = 0;
-        const HitRec r = traverse_bvh2<false, false>(b, o_med[4 * i], o_med[4 * i + 1], o_med[4 * i + 2], d_t1[4 * i], d_t1[4 * i + 1],
+        const HitRec r = HT_TRAVERSE<false, false>(b, o_med[4 * i], o_med[4 * i + 1], o_med[4 * i + 2], d_t1[4 * i], d_t1[4 * i + 1],
                                                      d_t1[4 * i + 2], d_t1[4 * i + 3]);
         if (r.slot < 0) {
             out_ids[2 * i] = out_ids[2 * i + 1] = 0xffffffffu;
@@ -112,7 +116,7 @@ void ht_any(void *hh, int n, const float *o_med, const float *d_t1, uint8_t *occ
     const BvhDevice b = view(h);
 #pragma omp parallel for schedule(dynamic, 256)
     for (int i = 0; i < n; ++i)
-        occluded[i] = traverse_bvh2<true, false>(b, o_med[4 * i], o_med[4 * i + 1], o_med[4 * i + 2], d_t1[4 * i], d_t1[4 * i + 1], d_t1[4 * i + 2],
+        occluded[i] = HT_TRAVERSE<true, false>(b, o_med[4 * i], o_med[4 * i + 1], o_med[4 * i + 2], d_t1[4 * i], d_t1[4 * i + 1], d_t1[4 * i + 2],
                                                  d_t1[4 * i + 3]).slot >= 0;
 }
 

@@ -12,14 +12,14 @@ from . import util
 from .util import ROOT, f32
 
 
-@pytest.fixture(scope="module")
-def ht():
+@pytest.fixture(scope="module", params=["traverse_bvh2", "traverse_bvh2_ifif"])
+def ht(request):
     src = os.path.join(ROOT, "tests", "host", "host_traverse.cpp")
-    out = os.path.join(ROOT, "tests", "host", "_libhosttrav.so")
+    out = os.path.join(ROOT, "tests", "host", "_libhosttrav_%s.so" % request.param)
     deps = [src, os.path.join(ROOT, "btrc_b200/csrc/host/bvh.cpp"), os.path.join(ROOT, "btrc_b200/csrc/host/bvh.h"),
             os.path.join(ROOT, "btrc_b200/csrc/device/traverse.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
-        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-I/usr/local/cuda/include", src, deps[1], "-o", out],
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-I/usr/local/cuda/include", "-DHT_TRAVERSE=" + request.param, src, deps[1], "-o", out],
                        check=True)
     L = ctypes.CDLL(out)
     L.ht_build.restype = ctypes.c_void_p
