@@ -27,9 +27,9 @@ def report(tag, om, dt, anyhit):
     om = np.ascontiguousarray(om, np.float32); dt = np.ascontiguousarray(dt, np.float32)
     n = om.shape[0]
     row = []
-    for name, order in (("asis", None), ("sorted", np.argsort(morton_key(om, dt), kind="stable"))):
+    for name, order in (("asis", None), ("octant", np.argsort(morton_key(om, dt) >> 15, kind="stable")), ("sorted", np.argsort(morton_key(om, dt), kind="stable"))):
         a, b = (om, dt) if order is None else (np.ascontiguousarray(om[order]), np.ascontiguousarray(dt[order]))
-        for mode, mname in ((0, "ww"), (1, "spec"), (2, "ifif")):
+        for mode, mname in ((0, "ww"), (2, "ifif")):
             out = np.zeros(4, np.float64)
             L.sim_run(h, n, a.ctypes.data, b.ctypes.data, 1 if anyhit else 0, mode, out.ctypes.data)
             cost = (C_NODE * out[0] + C_TRI * out[1]) / n * 32 / 32
