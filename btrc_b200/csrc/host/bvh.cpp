@@ -1,6 +1,7 @@
 #include "bvh.h"
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cstring>
 #include <numeric>
@@ -18,7 +19,10 @@ struct Builder {
     const std::vector<Vec3> &centers;
     int max_leaf;
     std::vector<BuildNode> nodes;
-    std::vector<int> order;
+    // primitive records are partitioned physically (box, centre, id together): every pass over a range streams memory
+    // instead of gathering boxes[order[i]] through a shuffled index array (10 M triangles: 14 s -> a few seconds)
+    struct Rec { AABB box; Vec3 c; int id; };
+    std::vector<Rec> recs;
     std::atomic<int> next_node{1};
 
     Builder(const std::vector<AABB> &b, const std::vector<Vec3> &c, int ml) : boxes(b), centers(c), max_leaf(ml) {}
@@ -30,13 +34,74 @@ struct Builder {
         nodes[ni].count = count;
     }
 
-    void build(int ni, int first, int count) {
+    // Bounds and per-axis bins of [first, first + count).  Large ranges (the top of the tree) are binned by all threads with
+    // thread-local bins; small ones serially inside their task.
+    struct Bins {
         AABB box, cbox;
-        for (int i = first; i < first + count; ++i) {
-            box.extend(boxes[order[i]]);
-            cbox.extend(centers[order[i]]);
+        AABB bin_box[3][kBins];
+        int bin_cnt[3][kBins];
+    };
+    void bin_range(int first, int count, bool parallel, Bins &out) const {
+        auto bounds = [&](int lo, int hi, AABB &box, AABB &cbox) {
+            for (int i = lo; i < hi; ++i) { box.extend(recs[i].box); cbox.extend(recs[i].c); }
+        };
+        out.box = AABB(); out.cbox = AABB();
+        if (!parallel) bounds(first, first + count, out.box, out.cbox);
+        else {
+#pragma omp parallel
+            {
+                AABB b, c;
+#pragma omp for nowait schedule(static)
+                for (int i = first; i < first + count; ++i) { b.extend(recs[i].box); c.extend(recs[i].c); }
+#pragma omp critical
+                { out.box.extend(b); out.cbox.extend(c); }
+            }
         }
-        if (count <= 1) { make_leaf(ni, first, count, box); return; }
+        for (int a = 0; a < 3; ++a) for (int k = 0; k < kBins; ++k) { out.bin_box[a][k] = AABB(); out.bin_cnt[a][k] = 0; }
+        const Vec3 cext = out.cbox.hi - out.cbox.lo;
+        float scale[3];
+        for (int a = 0; a < 3; ++a) scale[a] = cext[a] > 0 ? kBins / cext[a] : 0.0f;
+        auto bin = [&](int lo, int hi, Bins &dst) {
+            for (int i = lo; i < hi; ++i) {
+                const Rec &r = recs[i];
+                for (int a = 0; a < 3; ++a) {
+                    if (!(cext[a] > 0)) continue;
+                    int b = (int)((r.c[a] - out.cbox.lo[a]) * scale[a]);
+                    b = std::min(std::max(b, 0), kBins - 1);
+                    dst.bin_box[a][b].extend(r.box);
+                    dst.bin_cnt[a][b]++;
+                }
+            }
+        };
+        if (!parallel) bin(first, first + count, out);
+        else {
+#pragma omp parallel
+            {
+                Bins local;
+                for (int a = 0; a < 3; ++a) for (int k = 0; k < kBins; ++k) { local.bin_box[a][k] = AABB(); local.bin_cnt[a][k] = 0; }
+#pragma omp for nowait schedule(static)
+                for (int i = first; i < first + count; ++i) bin(i, i + 1, local);
+#pragma omp critical
+                for (int a = 0; a < 3; ++a) for (int k = 0; k < kBins; ++k) { out.bin_box[a][k].extend(local.bin_box[a][k]); out.bin_cnt[a][k] += local.bin_cnt[a][k]; }
+            }
+        }
+    }
+
+    // ranges below this size are built by one task each; above it the node itself is processed by all threads
+    static constexpr int kParallelNode = 1 << 18;
+    std::vector<std::array<int, 3>> pending;  // (node, first, count) subtrees collected by the parallel top phase
+
+    void build(int ni, int first, int count, bool top = false) {
+        if (count <= 1) {
+            AABB box;
+            for (int i = first; i < first + count; ++i) box.extend(recs[i].box);
+            make_leaf(ni, first, count, box);
+            return;
+        }
+        if (top && count < kParallelNode) { pending.push_back({ni, first, count}); return; }
+        Bins bins;
+        bin_range(first, count, top, bins);
+        const AABB &box = bins.box, &cbox = bins.cbox;
 
         // binned SAH over the three axes
         float best_cost = 3.402823466e+38f;
@@ -44,16 +109,8 @@ struct Builder {
         const Vec3 cext = cbox.hi - cbox.lo;
         for (int axis = 0; axis < 3; ++axis) {
             if (!(cext[axis] > 0)) continue;
-            AABB bin_box[kBins];
-            int bin_cnt[kBins] = {0};
-            const float scale = kBins / cext[axis];
-            for (int i = first; i < first + count; ++i) {
-                const int p = order[i];
-                int b = (int)((centers[p][axis] - cbox.lo[axis]) * scale);
-                b = std::min(std::max(b, 0), kBins - 1);
-                bin_box[b].extend(boxes[p]);
-                bin_cnt[b]++;
-            }
+            const AABB *bin_box = bins.bin_box[axis];
+            const int *bin_cnt = bins.bin_cnt[axis];
             float right_area[kBins];
             int right_cnt[kBins];
             AABB acc;
@@ -82,12 +139,12 @@ struct Builder {
             if (count <= max_leaf && leaf_cost <= split_cost) { make_leaf(ni, first, count, box); return; }
             const float scale = kBins / cext[best_axis];
             const float lo = cbox.lo[best_axis];
-            auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](int p) {
-                int b = (int)((centers[p][best_axis] - lo) * scale);
+            auto it = std::partition(recs.begin() + first, recs.begin() + first + count, [&](const Rec &r) {
+                int b = (int)((r.c[best_axis] - lo) * scale);
                 b = std::min(std::max(b, 0), kBins - 1);
                 return b <= best_bin;
             });
-            mid = (int)(it - order.begin());
+            mid = (int)(it - recs.begin());
         }
         if (mid <= first || mid >= first + count) {
             if (count <= max_leaf) { make_leaf(ni, first, count, box); return; }
@@ -101,10 +158,13 @@ struct Builder {
         nodes[ni].first = 0;
         nodes[ni].count = 0;
         const int lc = mid - first, rc = first + count - mid;
-        if (count > 8192) {
-#pragma omp task shared(nodes, order)
+        if (top) {
+            build(c, first, lc, true);
+            build(c + 1, mid, rc, true);
+        } else if (count > 8192) {
+#pragma omp task shared(nodes, recs)
             build(c, first, lc);
-#pragma omp task shared(nodes, order)
+#pragma omp task shared(nodes, recs)
             build(c + 1, mid, rc);
 #pragma omp taskwait
         } else {
@@ -121,15 +181,25 @@ BinaryBvh build_binary_bvh(const std::vector<AABB> &boxes, const std::vector<Vec
     if (n == 0) throw Error("bvh: no primitives");
     Builder b(boxes, centers, max_leaf);
     b.nodes.resize(2 * (size_t)n);
-    b.order.resize(n);
-    std::iota(b.order.begin(), b.order.end(), 0);
+    b.recs.resize(n);
+#pragma omp parallel for
+    for (int i = 0; i < n; ++i) { b.recs[i].box = boxes[i]; b.recs[i].c = centers[i]; b.recs[i].id = i; }
+    // top of the tree: every node above kParallelNode primitives is processed by all threads (bounds, binning); the subtrees
+    // below are then built by independent tasks
+    b.build(0, 0, n, true);
 #pragma omp parallel
 #pragma omp single
-    b.build(0, 0, n);
+    for (size_t k = 0; k < b.pending.size(); ++k) {
+        const std::array<int, 3> t = b.pending[k];
+#pragma omp task firstprivate(t) shared(b)
+        b.build(t[0], t[1], t[2]);
+    }
     BinaryBvh out;
     b.nodes.resize(b.next_node.load());
     out.nodes = std::move(b.nodes);
-    out.order = std::move(b.order);
+    out.order.resize(n);
+#pragma omp parallel for
+    for (int i = 0; i < n; ++i) out.order[i] = b.recs[i].id;
     return out;
 }
 
@@ -161,7 +231,8 @@ FlatBvh2 flatten_bvh2(const BinaryBvh &bvh, const std::vector<WorldTri> &tris) {
     const size_t n = bvh.order.size();
     out.tris.resize(12 * n);
     out.tri_ids.resize(2 * n);
-    for (size_t s = 0; s < n; ++s) {
+#pragma omp parallel for
+    for (long long s = 0; s < (long long)n; ++s) {
         const WorldTri &t = tris[bvh.order[s]];
         float *o = &out.tris[12 * s];
         o[0] = t.p0.x; o[1] = t.p0.y; o[2] = t.p0.z; o[3] = t.n.x;
@@ -191,7 +262,9 @@ FlatBvh2 flatten_bvh2(const BinaryBvh &bvh, const std::vector<WorldTri> &tris) {
     }
     out.nodes.assign(16 * (size_t)std::max(n_inner, 1), 0.0f);
     auto ref_of = [&](int ni) { return bvh.nodes[ni].left < 0 ? leaf_ref(bvh.nodes[ni]) : inner_index[ni]; };
-    for (int ni : dfs) {
+#pragma omp parallel for schedule(static)
+    for (long long k = 0; k < (long long)dfs.size(); ++k) {
+        const int ni = dfs[k];
         const BuildNode &nd = bvh.nodes[ni];
         const AABB &a = bvh.nodes[nd.left].box, &b = bvh.nodes[nd.right].box;
         float *o = &out.nodes[16 * (size_t)inner_index[ni]];
