@@ -168,6 +168,7 @@ struct RenderParams {  // builtin/renderer/wavefront.h:13-27
     float rr_threshold, rr_cont_prob;
     int tile;
     int albedo, normal;
+    int halton;       // 0: IndependentSampler (PCG), 1: HaltonSampler -- renderer "sampler": "independent" | "halton"
     int filter_type;  // 0 box, 1 gaussian
     float filter_radius;
     float filter_step;  // 2 * radius / GRID_SIZE
@@ -183,6 +184,11 @@ struct BvhDevice {
     const uint2 *tri_ids;    // (instance, primitive) per triangle slot
     int root_ref;            // reference of the root (a leaf ref when the scene has <= leaf-size triangles)
     int n_tris;
+};
+
+struct HaltonConsts {  // HaltonSampler::initialize_consts (builtin/sampler/halton.cpp:116-133)
+    int base_scales[2], base_exponents[2], mult_inverse[2];
+    const int *primes;  // the first 1000 primes (utils/prime.cpp)
 };
 
 struct SceneDevice {
@@ -206,6 +212,7 @@ struct SceneDevice {
     const float2 *filter_alias;  // gaussian filter alias table (256*256)
     uint32_t vol_prim_medium_id;
     float world_diagonal;
+    HaltonConsts halton;
 };
 
 // Path-state pool (one set = "current", one set = "next").

@@ -81,14 +81,16 @@ __global__ void prepare_kernel(WaveCtl *ctl) {
 // ---------------------------------------------------------------------------------------------------------------
 // generate (generate.cpp:39-86, film_filter/box.cpp:5-10, gaussian.cpp:54-66, camera/pinhole.cpp:84-99)
 // ---------------------------------------------------------------------------------------------------------------
+template <bool HALTON>
 struct GenOut {
     f3 o, d;
     uint32_t px, py;
-    Sampler sampler;
+    SamplerT<HALTON> sampler;
 };
 
-__device__ __forceinline__ GenOut generate_one(const SceneDevice &scene, const RenderParams &P, long long accu) {
-    GenOut g;
+template <bool HALTON>
+__device__ __forceinline__ GenOut<HALTON> generate_one(const SceneDevice &scene, const RenderParams &P, long long accu) {
+    GenOut<HALTON> g;
     const int W = P.width, H = P.height;
     int pixel_index, sample_index;
     if (!P.tile) {
@@ -100,7 +102,7 @@ __device__ __forceinline__ GenOut generate_one(const SceneDevice &scene, const R
     }
     const int pixel_x = pixel_index % W, pixel_y = pixel_index / W;
     g.px = pixel_x; g.py = pixel_y;
-    g.sampler.init((uint32_t)pixel_x, (uint32_t)pixel_y, sample_index);
+    g.sampler.init(scene.halton, (uint32_t)pixel_x, (uint32_t)pixel_y, sample_index);
     float fx, fy;
     if (P.filter_type == 0) {
         fx = g.sampler.get1d() - 0.5f;
@@ -129,12 +131,13 @@ __device__ __forceinline__ GenOut generate_one(const SceneDevice &scene, const R
     return g;
 }
 
+template <bool HALTON>
 __global__ void __launch_bounds__(kBlock) generate_kernel(SceneDevice scene, RenderParams P, PathQueue q, FilmDevice film, const WaveCtl *ctl) {
     const int n_new = ctl->n_new;
     const int base_slot = ctl->n_survivors;
     const long long gen_base = ctl->gen_base;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) {
-        GenOut g = generate_one(scene, P, gen_base + i);
+        GenOut<HALTON> g = generate_one<HALTON>(scene, P, gen_base + i);
         const uint32_t pixel = g.py * (uint32_t)P.width + g.px;
         atomicAdd(film.weight + pixel, 1.0f);
         const int s = base_slot + i;
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(SceneDevice scene, Ren
         q.ray_d[s] = make4(g.d, kMaxFloat);
         q.beta[s] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));
         q.rad[s] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(pixel));
-        q.rng[s] = make_ulonglong2(g.sampler.rng.state, g.sampler.rng.inc);
+        q.rng[s] = g.sampler.store();
         q.ble[s] = make_float4(1.0f, 1.0f, 1.0f, -1.0f);
     }
 }
@@ -276,6 +279,7 @@ __device__ __forceinline__ void emit_outputs(PathQueue &nq, ShadowQueue &sq, Fil
 // ---------------------------------------------------------------------------------------------------------------
 // medium (medium.cpp:36-164, 214-249): only launched when the scene has media (wavefront.cpp:254-268)
 // ---------------------------------------------------------------------------------------------------------------
+template <bool HALTON>
 __global__ void __launch_bounds__(kBlock) medium_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQueue nq, ShadowQueue sq,
                                                        FilmDevice film, WaveCtl *ctl) {
     const int n = ctl->n_active;
@@ -292,8 +296,8 @@ __global__ void __launch_bounds__(kBlock) medium_kernel(SceneDevice scene, Rende
             const ulonglong2 rng2 = q.rng[i];
             const f3 o = xyz(o4), d = xyz(d4);
             pixel = __float_as_uint(rad4.w);
-            Sampler sampler;
-            sampler.rng.state = rng2.x; sampler.rng.inc = rng2.y;
+            SamplerT<HALTON> sampler;
+            sampler.load(rng2, scene.halton);
             // get_medium_segment
             uint32_t medium_id;
             f3 medium_end;
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(kBlock) medium_kernel(SceneDevice scene, Rende
                 q.ble[i] = make4(xyz(ble4) * unscatter_tr, ble4.w);
             }
             if (!ms.scattered) {
-                if (tracked) q.rng[i] = make_ulonglong2(sampler.rng.state, sampler.rng.inc);
+                if (tracked) q.rng[i] = sampler.store();
             } else {
                 hq.flag[i] = flag | kFlagHasScattering;
                 f3 beta = xyz(beta4);  // throughput of both media is one
@@ -347,7 +351,7 @@ __global__ void __launch_bounds__(kBlock) medium_kernel(SceneDevice scene, Rende
                         ns.beta = ns.ble / ppdf;
                         ns.pdf = ppdf;
                         ns.o = ms.position; ns.med = medium_id; ns.L = L; ns.depth = depth + 1;
-                        ns.rng = make_ulonglong2(sampler.rng.state, sampler.rng.inc);
+                        ns.rng = sampler.store();
                         emit_next = true;
                     } else {
                         splat = true; splat_value = L;
@@ -392,7 +396,7 @@ __global__ void __launch_bounds__(kBlock) shade_miss_kernel(SceneDevice scene, P
 #endif
 template <int MAT> constexpr bool shade_is_heavy() { return MAT == MAT_DISNEY || MAT == MAT_METAL; }
 template <int MAT> constexpr int shade_block() { return shade_is_heavy<MAT>() ? BTRC_SHADE_BLOCK_HEAVY : kBlock; }
-template <int MAT>
+template <int MAT, bool HALTON>
 __global__ void __launch_bounds__(shade_block<MAT>(), shade_is_heavy<MAT>() ? BTRC_SHADE_BLOCKS_HEAVY : 3)
 shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQueue nq, ShadowQueue sq, FilmDevice film, WaveCtl *ctl) {
     const int n = ctl->class_count[1 + MAT];
@@ -428,8 +432,8 @@ shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQu
                 f3 beta = xyz(beta4);
                 const int depth = __float_as_int(beta4.w);
                 const uint32_t ray_medium = __float_as_uint(o4.w);
-                Sampler sampler;
-                sampler.rng.state = rng2.x; sampler.rng.inc = rng2.y;
+                SamplerT<HALTON> sampler;
+                sampler.load(rng2, scene.halton);
                 L = L + le_rad;
                 if (simple_russian_roulette(P, beta, depth, sampler)) {
                     splat = true; splat_value = L;
@@ -493,7 +497,7 @@ shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQu
                         ns.med = dot(inct.frame.z, dir) > 0.0f ? inst.outer_medium_id : inst.inner_medium_id;
                         ns.pdf = bs.is_delta ? -bs.pdf : bs.pdf;
                         ns.L = L; ns.depth = depth + 1;
-                        ns.rng = make_ulonglong2(sampler.rng.state, sampler.rng.inc);
+                        ns.rng = sampler.store();
                         emit_next = true;
                     } else {
                         splat = true; splat_value = L;
@@ -581,7 +585,8 @@ inline int persistent_blocks(const LaunchCfg &cfg, int per_sm) { return cfg.sm_c
 void launch_prepare(WaveCtl *ctl, cudaStream_t stream) { prepare_kernel<<<1, 1, 0, stream>>>(ctl); }
 
 void launch_generate(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, FilmDevice film, WaveCtl *ctl, cudaStream_t stream) {
-    generate_kernel<<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, cur, film, ctl);
+    if (params.halton) generate_kernel<true><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, cur, film, ctl);
+    else generate_kernel<false><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, cur, film, ctl);
 }
 
 void launch_trace(const LaunchCfg &cfg, const SceneDevice &scene, PathQueue cur, HitQueue hit, WaveCtl *ctl, cudaStream_t stream) {
@@ -592,7 +597,9 @@ void launch_trace(const LaunchCfg &cfg, const SceneDevice &scene, PathQueue cur,
 template <int MAT>
 static void launch_shade_class(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, HitQueue hit, PathQueue next,
                                ShadowQueue shadow, FilmDevice film, WaveCtl *ctl, cudaStream_t stream) {
-    shade_kernel<MAT><<<persistent_blocks(cfg, 8 * kBlock / shade_block<MAT>()), shade_block<MAT>(), 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
+    const int blocks = persistent_blocks(cfg, 8 * kBlock / shade_block<MAT>());
+    if (params.halton) shade_kernel<MAT, true><<<blocks, shade_block<MAT>(), 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
+    else shade_kernel<MAT, false><<<blocks, shade_block<MAT>(), 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
 }
 
 int launch_shade(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, uint32_t material_mask, PathQueue cur, HitQueue hit,
@@ -623,7 +630,8 @@ void launch_classify(const LaunchCfg &cfg, const SceneDevice &scene, HitQueue hi
 
 void launch_medium(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, HitQueue hit, PathQueue next,
                    ShadowQueue shadow, FilmDevice film, WaveCtl *ctl, cudaStream_t stream) {
-    medium_kernel<<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
+    if (params.halton) medium_kernel<true><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
+    else medium_kernel<false><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
 }
 
 void launch_shadow(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, ShadowQueue shadow, FilmDevice film, WaveCtl *ctl,

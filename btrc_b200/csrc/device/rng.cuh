@@ -7,6 +7,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "../common/types.h"
+
 namespace btrc {
 
 constexpr uint64_t kPcgDefaultState = 0x853c49e6748fea9bULL;
@@ -58,13 +60,114 @@ __device__ __forceinline__ uint64_t murmur_pixel(uint32_t px, uint32_t py) {
     return h;
 }
 
-struct Sampler {
+// ---------------------------------------------------------------------------------------------------------------
+// Halton sampler with Owen scrambling (builtin/sampler/halton.cpp:9-133, utils/low_discrepancy.cpp:10-120, after pbrt-v4).
+// The reference wires its wavefront renderer to IndependentSampler at compile time (wavefront/common.h:36-37); here the
+// renderer node's "sampler": "halton" selects this one (kernels are instantiated for both).  The state shares the PCG's
+// 16-byte queue slot: state = halton index, inc = dimension << 1 (a PCG increment is always odd).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kPrimeTableSize = 1000;     // utils/prime.h:9
+constexpr int kMaxHaltonResolution = 128;  // halton.cpp:10
+
+__device__ __forceinline__ uint64_t mix_bits(uint64_t v) {  // low_discrepancy.cpp:47-55
+    v ^= v >> 31; v *= 0x7fb5d329728ea185ull;
+    v ^= v >> 27; v *= 0x81dadef4bc2dd44dull;
+    v ^= v >> 33;
+    return v;
+}
+
+__device__ __forceinline__ int permutation_element(uint32_t i, uint32_t l, uint32_t p) {  // low_discrepancy.cpp:10-43
+    uint32_t w = l - 1;
+    w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+    do {
+        i ^= p; i *= 0xe170893du;
+        i ^= p >> 16;
+        i ^= (i & w) >> 4;
+        i ^= p >> 8; i *= 0x0929eb3fu;
+        i ^= p >> 23;
+        i ^= (i & w) >> 1; i *= 1u | p >> 27;
+        i *= 0x6935fa69u;
+        i ^= (i & w) >> 11; i *= 0x74dcb303u;
+        i ^= (i & w) >> 2; i *= 0x9e501cc3u;
+        i ^= (i & w) >> 2; i *= 0xc860a3dfu;
+        i &= w;
+        i ^= i >> 5;
+    } while (i >= l);
+    return int((i + p) % l);
+}
+
+__device__ __noinline__ float owen_scrambled_radical_inverse(const int *primes, int base_index, uint64_t a, uint64_t hash) {  // low_discrepancy.cpp:82-103
+    const uint64_t base = (uint64_t)__ldg(primes + base_index);
+    const float inv_base = __fdiv_rn(1.0f, float(base));
+    float inv_base_m = 1.0f;
+    uint64_t reversed_digits = 0;
+    while (__fsub_rn(1.0f, inv_base_m) < 1.0f) {
+        const uint64_t next = a / base;
+        uint64_t digit_value = a - next * base;
+        const uint64_t digit_hash = mix_bits(hash ^ reversed_digits);
+        digit_value = (uint64_t)permutation_element(uint32_t(digit_value), uint32_t(base), uint32_t(digit_hash));
+        reversed_digits = reversed_digits * base + digit_value;
+        inv_base_m = __fmul_rn(inv_base_m, inv_base);
+        a = next;
+    }
+    return fminf(__fmul_rn(inv_base_m, __ull2float_rn(reversed_digits)), 0x1.fffffep-1f);
+}
+
+__device__ __forceinline__ uint64_t inverse_radical_inverse(uint64_t inverse, int base, int digits) {  // low_discrepancy.cpp:105-117
+    uint64_t index = 0;
+    for (int i = 0; i < digits; ++i) {
+        const uint64_t digit = inverse % (uint64_t)base;
+        inverse = inverse / (uint64_t)base;
+        index = index * (uint64_t)base + digit;
+    }
+    return index;
+}
+
+template <bool HALTON>
+struct SamplerT;
+
+template <>
+struct SamplerT<false> {
     Pcg rng;
-    __device__ __forceinline__ void init(uint32_t px, uint32_t py, int sample_index) {
+    __device__ __forceinline__ void init(const HaltonConsts &, uint32_t px, uint32_t py, int sample_index) {
         rng.seed(murmur_pixel(px, py));
         rng.advance(uint64_t(int64_t(sample_index)) * 65536ull);
     }
+    __device__ __forceinline__ void load(ulonglong2 v, const HaltonConsts &) { rng.state = v.x; rng.inc = v.y; }
+    __device__ __forceinline__ ulonglong2 store() const { return make_ulonglong2(rng.state, rng.inc); }
     __device__ __forceinline__ float get1d() { return rng.uniform(); }
 };
+
+template <>
+struct SamplerT<true> {
+    uint64_t halton_index;
+    uint32_t dimension;
+    const int *primes;
+    __device__ __forceinline__ void init(const HaltonConsts &hc, uint32_t px, uint32_t py, int sample_index) {  // halton.cpp:46-67
+        primes = hc.primes;
+        halton_index = 0;
+        const int sample_stride = hc.base_scales[0] * hc.base_scales[1];
+        if (sample_stride > 1) {
+            const uint32_t pm[2] = {px % kMaxHaltonResolution, py % kMaxHaltonResolution};
+            for (int i = 0; i < 2; ++i) {
+                const uint64_t dim_offset = inverse_radical_inverse(uint64_t(pm[i]), i == 0 ? 2 : 3, hc.base_exponents[i]);
+                halton_index = halton_index + dim_offset * uint64_t(sample_stride / hc.base_scales[i]) * uint64_t(hc.mult_inverse[i]);
+            }
+            halton_index = halton_index % uint64_t(sample_stride);
+        }
+        halton_index = halton_index + uint64_t(int64_t(sample_index * sample_stride));
+        dimension = 2;  // the first two dimensions are left to the film position (filter importance sampling takes over)
+    }
+    __device__ __forceinline__ void load(ulonglong2 v, const HaltonConsts &hc) { halton_index = v.x; dimension = uint32_t(v.y >> 1); primes = hc.primes; }
+    __device__ __forceinline__ ulonglong2 store() const { return make_ulonglong2(halton_index, uint64_t(dimension) << 1); }
+    __device__ __forceinline__ float get1d() {  // halton.cpp:80-89 (get2d / get3d differ only in where they wrap beyond dimension 997)
+        if (dimension >= (uint32_t)kPrimeTableSize) dimension = 2;
+        const float r = owen_scrambled_radical_inverse(primes, int(dimension), halton_index, mix_bits(uint64_t(1u + (dimension << 4))));
+        dimension = dimension + 1;
+        return r;
+    }
+};
+
+using Sampler = SamplerT<false>;  // shadow-ray transmittance streams stay PCG in both modes (keyed on the ray, shading.cuh)
 
 }  // namespace btrc

@@ -150,8 +150,8 @@ struct LiSample {
 };
 
 // SURFACE: o = intersection_offset(ref_pos, ref_nor, dir) (sample_surface_light_li); otherwise o = ref_pos (medium)
-template <bool SURFACE>
-__device__ __forceinline__ LiSample sample_light_li(const SceneDevice &scene, f3 ref_pos, f3 ref_nor, Sampler &sampler) {
+template <bool SURFACE, typename S>
+__device__ __forceinline__ LiSample sample_light_li(const SceneDevice &scene, f3 ref_pos, f3 ref_nor, S &sampler) {
     LiSample r;
     r.success = false;
     const float s0 = sampler.get1d(), s1 = sampler.get1d(), s2 = sampler.get1d();
@@ -233,7 +233,8 @@ __device__ __forceinline__ f3 handle_intersected_light(const SceneDevice &scene,
 }
 
 // helper.cpp:67-95
-__device__ __forceinline__ bool simple_russian_roulette(const RenderParams &P, f3 &beta, int depth, Sampler &sampler) {
+template <typename S>
+__device__ __forceinline__ bool simple_russian_roulette(const RenderParams &P, f3 &beta, int depth, S &sampler) {
     bool ret = false;
     if (depth >= P.min_depth) {
         if (depth >= P.max_depth) ret = true;
@@ -439,7 +440,8 @@ struct MediumSample {
 };
 
 // aggregate.cpp:129-199 (delta tracking over the summed densities; albedo = density-weighted mix, g = 0)
-__device__ __forceinline__ void vol_sample_scattering(const SceneDevice &scene, const VolOverlap &ov, f3 a, f3 b, Sampler &sampler, MediumSample &r) {
+template <typename S>
+__device__ __forceinline__ void vol_sample_scattering(const SceneDevice &scene, const VolOverlap &ov, f3 a, f3 b, S &sampler, MediumSample &r) {
     const float inv_max_density = vol_overlap_inv_max_density(scene, ov);
     const float t_max = length(b - a);
     float t = 0.0f;
@@ -467,7 +469,8 @@ __device__ __forceinline__ void vol_sample_scattering(const SceneDevice &scene, 
 }
 
 // aggregate.cpp:201-253 (ratio tracking)
-__device__ __forceinline__ float vol_tr_in_overlap(const SceneDevice &scene, const VolOverlap &ov, f3 a, f3 b, Sampler &sampler) {
+template <typename S>
+__device__ __forceinline__ float vol_tr_in_overlap(const SceneDevice &scene, const VolOverlap &ov, f3 a, f3 b, S &sampler) {
     const float inv_max_density = vol_overlap_inv_max_density(scene, ov);
     const float t_max = length(b - a);
     float result = 1.0f, t = 0.0f;
@@ -480,7 +483,8 @@ __device__ __forceinline__ float vol_tr_in_overlap(const SceneDevice &scene, con
     return result;
 }
 
-__device__ __noinline__ MediumSample volprim_sample(const SceneDevice &scene, f3 a, f3 b, Sampler &sampler) {  // core/volume.cpp:112-160
+template <typename S>
+__device__ __noinline__ MediumSample volprim_sample(const SceneDevice &scene, f3 a, f3 b, S &sampler) {  // core/volume.cpp:112-160
     MediumSample r;
     r.scattered = false;
     if (scene.n_vol_prims == 0) return r;
@@ -500,7 +504,8 @@ __device__ __noinline__ MediumSample volprim_sample(const SceneDevice &scene, f3
     return r;
 }
 
-__device__ __noinline__ float volprim_tr(const SceneDevice &scene, f3 a, f3 b, Sampler &sampler) {  // core/volume.cpp:162-195
+template <typename S>
+__device__ __noinline__ float volprim_tr(const SceneDevice &scene, f3 a, f3 b, S &sampler) {  // core/volume.cpp:162-195
     float result = 1.0f;
     if (scene.n_vol_prims == 0) return result;
     f3 o = a;
@@ -516,7 +521,8 @@ __device__ __noinline__ float volprim_tr(const SceneDevice &scene, f3 a, f3 b, S
     return result;
 }
 
-__device__ __forceinline__ MediumSample medium_sample(const SceneDevice &scene, const MediumDesc &m, f3 a, f3 b, Sampler &sampler) {
+template <typename S>
+__device__ __forceinline__ MediumSample medium_sample(const SceneDevice &scene, const MediumDesc &m, f3 a, f3 b, S &sampler) {
     MediumSample r;
     r.scattered = false;
     if (m.type == MED_VOLPRIM) return volprim_sample(scene, a, b, sampler);
@@ -557,7 +563,8 @@ __device__ __forceinline__ MediumSample medium_sample(const SceneDevice &scene, 
     return r;
 }
 
-__device__ __forceinline__ f3 medium_tr(const SceneDevice &scene, const MediumDesc &m, f3 a, f3 b, Sampler &sampler) {
+template <typename S>
+__device__ __forceinline__ f3 medium_tr(const SceneDevice &scene, const MediumDesc &m, f3 a, f3 b, S &sampler) {
     if (m.type == MED_VOLPRIM) return f3(volprim_tr(scene, a, b, sampler));
     if (m.type == MED_HOMOGENEOUS) {  // homogeneous.cpp:60-73: sigma_a = sigma_t * (1 - albedo)
         const f3 sigma_a = m.sigma_t * (f3(1.0f) - f3(m.albedo[0], m.albedo[1], m.albedo[2]));

@@ -458,6 +458,11 @@ void Scene::create(const NodeP &root) {
         renderer.type = r->child("type")->as_string();
         if (renderer.type != "wfpt" && renderer.type != "pt") throw Error("unknown renderer type: " + renderer.type);
         renderer.tile = r->bool_or("tile", renderer.tile);
+        if (auto sn = r->find("sampler")) {  // wavefront/common.h:36-37 chooses at compile time; here it is a renderer parameter
+            const std::string st = sn->as_string();
+            if (st != "independent" && st != "halton") throw Error("unknown sampler type: " + st);
+            renderer.halton = st == "halton";
+        }
         renderer.spp = r->int_or("spp", renderer.spp);
         renderer.min_depth = r->int_or("min_depth", renderer.min_depth);
         renderer.max_depth = r->int_or("max_depth", renderer.max_depth);
@@ -509,6 +514,7 @@ RenderParams Scene::render_params() const {
     p.min_depth = renderer.min_depth; p.max_depth = renderer.max_depth;
     p.rr_threshold = renderer.rr_threshold; p.rr_cont_prob = renderer.rr_cont_prob;
     p.tile = renderer.tile ? 1 : 0;
+    p.halton = renderer.halton ? 1 : 0;
     p.albedo = renderer.albedo ? 1 : 0; p.normal = renderer.normal ? 1 : 0;
     p.filter_type = renderer.filter_type;
     p.filter_radius = renderer.filter_radius;
@@ -816,6 +822,31 @@ void Scene::upload_device() {
         t3.push_back(d);
     }
     dev.textures3d = upload(t3);
+    {   // HaltonSampler::initialize_consts (builtin/sampler/halton.cpp:116-133) + the prime table (utils/prime.cpp)
+        const int res[2] = {width, height};
+        for (int i = 0; i < 2; ++i) {
+            const int base = i == 0 ? 2 : 3;
+            int scale = 1, exp = 0;
+            while (scale < std::min(res[i], 128)) { scale *= base; ++exp; }
+            dev.halton.base_scales[i] = scale;
+            dev.halton.base_exponents[i] = exp;
+        }
+        auto mult_inverse = [](long long a, long long n) {  // extended Euclid (halton.cpp:12-37)
+            long long x0 = 1, x1 = 0, r0 = a, r1 = n;
+            while (r1 != 0) { const long long q = r0 / r1, t = r0 - q * r1; r0 = r1; r1 = t; const long long u = x0 - q * x1; x0 = x1; x1 = u; }
+            const long long m = x0 - x0 / n * n;
+            return (int)(m < 0 ? m + n : m);
+        };
+        dev.halton.mult_inverse[0] = mult_inverse(dev.halton.base_scales[1], dev.halton.base_scales[0]);
+        dev.halton.mult_inverse[1] = mult_inverse(dev.halton.base_scales[0], dev.halton.base_scales[1]);
+        std::vector<int> primes;
+        for (int v = 2; (int)primes.size() < 1000; ++v) {
+            bool is_prime = true;
+            for (int q : primes) { if (q * q > v) break; if (v % q == 0) { is_prime = false; break; } }
+            if (is_prime) primes.push_back(v);
+        }
+        dev.halton.primes = upload(primes);
+    }
     dev.media = upload(medium_table);
     dev.vol_prims = volume_prims.empty() ? nullptr : upload(volume_prims);
     dev.n_vol_prims = (int)volume_prims.size();

@@ -100,6 +100,7 @@ struct EnvLightDesc {
 struct RendererDesc {  // builtin/renderer/wavefront.cpp:375-398
     std::string type = "wfpt";
     bool tile = false;
+    bool halton = false;  // "sampler": "independent" (default, what the reference's wavefront renderer is compiled with) | "halton"
     int spp = 128;
     int min_depth = 5, max_depth = 10;
     float rr_threshold = 0.1f, rr_cont_prob = 0.5f;

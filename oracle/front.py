@@ -80,6 +80,11 @@ def lib():
         L.orc_set_film.argtypes = [c_void_p, c_int, c_int]
         L.orc_set_renderer.argtypes = [c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_int, c_float, c_float]
         L.orc_commit.argtypes = [c_void_p]
+        L.orc_set_sampler.argtypes = [c_void_p, c_int]
+        L.orc_owen_scrambled_radical_inverse.argtypes = [c_int, c_uint64, c_uint64]
+        L.orc_owen_scrambled_radical_inverse.restype = c_float
+        L.orc_prime.argtypes = [c_int]
+        L.orc_prime.restype = c_int
         L.orc_num_triangles.argtypes = [c_void_p]
         L.orc_vol_prim_medium_id.argtypes = [c_void_p]
         L.orc_vol_prim_medium_id.restype = c_uint32
@@ -867,6 +872,11 @@ class OracleScene:
                           rr_threshold=r.float_or("rr_threshold", 0.1), rr_cont_prob=r.float_or("rr_cont_prob", 0.5),
                           tile=r.bool_or("tile", False), albedo=r.bool_or("albedo", False), normal=r.bool_or("normal", False),
                           filter_type=ftype, radius=radius, alpha=alpha)
+        sn = r.find("sampler")
+        if sn is not None:
+            if sn.as_str() not in ("independent", "halton"):
+                raise ValueError("unknown sampler type: " + sn.as_str())
+            self.L.orc_set_sampler(self.h, 1 if sn.as_str() == "halton" else 0)
         self.commit()
 
     # -- queries

@@ -4,6 +4,7 @@
 //   * AliasTable::initialize                    (src/common/btrc/utils/math/alias.cpp:13-71)   -> filter / light / IBL tables
 //   * TriangleMeshLoader                        (src/common/btrc/utils/triangle_mesh_loader.cpp:10-149, vendored tinyobj)
 //                                               -> triangle order (= primitive ids), positions, geometry ex / ez, normals, uv
+//   * PRIME_TABLE                              (src/common/btrc/utils/prime.cpp)              -> Halton bases
 //   * Transform3D factories and operator*        (src/common/btrc/utils/math/{transform,mat4,mat3}.cpp) -> instance transforms
 // (factory/node/node.cpp does not compile with gcc -- it reaches CUJ class macros with in-class explicit specialisations -- so the
 // JSON parser stays pinned by the oracle's own restatement and tests.)
@@ -15,6 +16,7 @@
 
 #include <btrc/utils/math/alias.h>
 #include <btrc/utils/math/transform.h>
+#include <btrc/utils/prime.h>
 #include <btrc/utils/triangle_mesh_loader.h>
 
 using namespace btrc;
@@ -25,6 +27,9 @@ static thread_local std::string g_err;
 extern "C" {
 
 const char *ref_last_error() { return g_err.c_str(); }
+
+int ref_prime_table_size() { return (int)PRIME_TABLE_SIZE; }
+int ref_prime(int i) { return PRIME_TABLE[i]; }  // utils/prime.cpp (bases of the Halton sampler)
 
 void ref_alias_build(int n, const float *probs, float *accept, uint32_t *another) {
     std::vector<float> p(probs, probs + n);

@@ -107,13 +107,135 @@ uint64_t hash_pixel(uint32_t px, uint32_t py) {  // hash.h:88-96 with (u32,u32) 
     return murmur_hash64A(buf, 8, 0);
 }
 
-struct Sampler {  // independent.cpp:11-25, core/sampler.h:22-28
+// ------------------------------------------------------------------------------------------
+// Halton sampler with Owen scrambling: builtin/sampler/halton.cpp:9-133, utils/low_discrepancy.cpp:10-120, utils/prime.cpp.
+// The reference's wavefront renderer is compiled with IndependentSampler (wavefront/common.h:36-37); "sampler": "halton" in the
+// renderer node selects this one here.  Its state rides in the PCG's two words: state = halton index, inc = dimension << 1 (a
+// PCG increment is odd), so the SoA layout of the stages is unchanged.
+// ------------------------------------------------------------------------------------------
+constexpr int PRIME_TABLE_SIZE = 1000;      // utils/prime.h:9
+constexpr int MAX_HALTON_RESOLUTION = 128;  // halton.cpp:10
+
+const std::vector<int> &prime_table() {  // the first 1000 primes (utils/prime.cpp lists them; pinned by tests against the reference's array)
+    static const std::vector<int> primes = [] {
+        std::vector<int> p;
+        for (int v = 2; (int)p.size() < PRIME_TABLE_SIZE; ++v) {
+            bool ok = true;
+            for (int q : p) { if (q * q > v) break; if (v % q == 0) { ok = false; break; } }
+            if (ok) p.push_back(v);
+        }
+        return p;
+    }();
+    return primes;
+}
+
+uint64_t mix_bits(uint64_t v) {  // low_discrepancy.cpp:47-55
+    v = v ^ (v >> 31); v = v * 0x7fb5d329728ea185ull;
+    v = v ^ (v >> 27); v = v * 0x81dadef4bc2dd44dull;
+    v = v ^ (v >> 33);
+    return v;
+}
+
+int32_t permutation_element(uint32_t i, uint32_t l, uint32_t p) {  // low_discrepancy.cpp:10-43
+    uint32_t w = l - 1;
+    w = w | (w >> 1); w = w | (w >> 2); w = w | (w >> 4); w = w | (w >> 8); w = w | (w >> 16);
+    for (;;) {
+        i = i ^ p; i = i * 0xe170893du;
+        i = i ^ (p >> 16);
+        i = i ^ ((i & w) >> 4);
+        i = i ^ (p >> 8); i = i * 0x0929eb3fu;
+        i = i ^ (p >> 23);
+        i = i ^ ((i & w) >> 1); i = i * (1u | p >> 27);
+        i = i * 0x6935fa69u;
+        i = i ^ ((i & w) >> 11); i = i * 0x74dcb303u;
+        i = i ^ ((i & w) >> 2); i = i * 0x9e501cc3u;
+        i = i ^ ((i & w) >> 2); i = i * 0xc860a3dfu;
+        i = i & w;
+        i = i ^ (i >> 5);
+        if (i < l) break;
+    }
+    return int32_t((i + p) % l);
+}
+
+float owen_scrambled_radical_inverse(int base_index, uint64_t a, uint64_t hash) {  // low_discrepancy.cpp:82-103
+    const uint64_t base = (uint64_t)prime_table()[base_index];
+    const float inv_base = 1.0f / float(base);
+    float inv_base_m = 1.0f;
+    uint64_t reversed_digits = 0;
+    while (1.0f - inv_base_m < 1) {
+        uint64_t next = a / base;
+        uint64_t digit_value = a - next * base;
+        uint64_t digit_hash = mix_bits(hash ^ reversed_digits);
+        digit_value = (uint64_t)permutation_element(uint32_t(digit_value), uint32_t(base), uint32_t(digit_hash));
+        reversed_digits = reversed_digits * base + digit_value;
+        inv_base_m = inv_base_m * inv_base;
+        a = next;
+    }
+    return std::fmin(inv_base_m * float(reversed_digits), 0x1.fffffep-1f);
+}
+
+uint64_t inverse_radical_inverse(uint64_t inverse, int base, int digits) {  // low_discrepancy.cpp:105-117
+    uint64_t index = 0;
+    for (int i = 0; i < digits; ++i) {
+        uint64_t digit = inverse % uint64_t(base);
+        inverse = inverse / uint64_t(base);
+        index = index * uint64_t(base) + digit;
+    }
+    return index;
+}
+
+struct HaltonConsts {  // HaltonSampler::initialize_consts (halton.cpp:116-133)
+    int base_scales[2] = {1, 1}, base_exponents[2] = {0, 0}, mult_inverse[2] = {0, 0};
+    void initialize(int res_x, int res_y) {
+        const int res[2] = {res_x, res_y};
+        for (int i = 0; i < 2; ++i) {
+            const int base = i == 0 ? 2 : 3;
+            int scale = 1, exp = 0;
+            while (scale < std::min(res[i], MAX_HALTON_RESOLUTION)) { scale *= base; ++exp; }
+            base_scales[i] = scale; base_exponents[i] = exp;
+        }
+        mult_inverse[0] = (int)multiplicative_inverse(base_scales[1], base_scales[0]);
+        mult_inverse[1] = (int)multiplicative_inverse(base_scales[0], base_scales[1]);
+    }
+    static int64_t mod(int64_t a, int64_t b) { const int64_t r = a - a / b * b; return r < 0 ? r + b : r; }  // halton.cpp:12-16
+    static void extended_gcd(uint64_t a, uint64_t b, int64_t *x, int64_t *y) {                                  // halton.cpp:18-30
+        if (b == 0) { *x = 1; *y = 0; return; }
+        int64_t d = a / b, xp, yp;
+        extended_gcd(b, a % b, &xp, &yp);
+        *x = yp; *y = xp - (d * yp);
+    }
+    static uint64_t multiplicative_inverse(int64_t a, int64_t n) { int64_t x, y; extended_gcd(a, n, &x, &y); return mod(x, n); }
+};
+
+struct Sampler {  // independent.cpp:11-25, core/sampler.h:22-28; halton.cpp:46-114 when rng.inc is even
     PCG rng;
     void init(uint32_t px, uint32_t py, int sample_index) {
         rng.seed(hash_pixel(px, py));
         rng.advance(int64_t(sample_index) * 65536);
     }
-    float get1d() { return rng.uniform_float(); }
+    void init_halton(const HaltonConsts &hc, uint32_t px, uint32_t py, int sample_index) {  // halton.cpp:46-67
+        uint64_t halton_index = 0;
+        const int sample_stride = hc.base_scales[0] * hc.base_scales[1];
+        if (sample_stride > 1) {
+            const uint32_t pm[2] = {px % MAX_HALTON_RESOLUTION, py % MAX_HALTON_RESOLUTION};
+            for (int i = 0; i < 2; ++i) {
+                uint64_t dim_offset = inverse_radical_inverse(uint64_t(pm[i]), i == 0 ? 2 : 3, hc.base_exponents[i]);
+                halton_index = halton_index + dim_offset * uint64_t(sample_stride / hc.base_scales[i]) * uint64_t(hc.mult_inverse[i]);
+            }
+            halton_index = halton_index % uint64_t(sample_stride);
+        }
+        halton_index = halton_index + uint64_t(int64_t(sample_index * sample_stride));
+        rng.state = halton_index;
+        rng.inc = uint64_t(2) << 1;  // dimension 2: the first two are skipped (filter importance sampling)
+    }
+    float get1d() {
+        if (rng.inc & 1) return rng.uniform_float();
+        uint32_t dimension = uint32_t(rng.inc >> 1);  // halton.cpp:80-89
+        if (dimension >= (uint32_t)PRIME_TABLE_SIZE) dimension = 2;
+        float r = owen_scrambled_radical_inverse(int(dimension), rng.state, mix_bits(uint64_t(1u + (dimension << 4))));
+        rng.inc = uint64_t(dimension + 1) << 1;
+        return r;
+    }
     V3 get3d() { float a = get1d(); float b = get1d(); float c = get1d(); return {a, b, c}; }
 };
 
@@ -278,6 +400,7 @@ struct orc_scene {
     // renderer params (builtin/renderer/wavefront.h:13-27)
     int spp = 1, min_depth = 5, max_depth = 10; float rr_threshold = 0.1f, rr_cont_prob = 0.5f;
     bool tile = false, want_albedo = false, want_normal = false;
+    bool halton = false; HaltonConsts halton_consts;  // renderer "sampler": "halton"
     int filter_type = 0; float filter_radius = 1.3f, filter_alpha = 1.6f;
     AliasTable gauss_alias;
     // accel
@@ -590,7 +713,8 @@ void generate_path(const orc_scene &s, int64_t accu_state_index, PathState &ps) 
         sample_index = int(accu_state_index % s.spp);
     }
     int pixel_x = pixel_index % W, pixel_y = pixel_index / W;
-    ps.sampler.init((uint32_t)pixel_x, (uint32_t)pixel_y, sample_index);
+    if (s.halton) ps.sampler.init_halton(s.halton_consts, (uint32_t)pixel_x, (uint32_t)pixel_y, sample_index);
+    else ps.sampler.init((uint32_t)pixel_x, (uint32_t)pixel_y, sample_index);
     V2 fs = filter_sample(s, ps.sampler);
     float pixel_xf = float(pixel_x) + 0.5f + fs.x;
     float pixel_yf = float(pixel_y) + 0.5f + fs.y;
@@ -1488,7 +1612,14 @@ void orc_set_renderer(orc_scene *s, int spp, int min_depth, int max_depth, float
     s->filter_type = filter_type; s->filter_radius = radius; s->filter_alpha = alpha;
 }
 
+void orc_set_sampler(orc_scene *s, int halton) { s->halton = halton != 0; }
+
+// known-answer access to the Halton machinery
+float orc_owen_scrambled_radical_inverse(int base_index, uint64_t a, uint64_t hash) { return owen_scrambled_radical_inverse(base_index, a, hash); }
+int orc_prime(int i) { return prime_table()[i]; }
+
 void orc_commit(orc_scene *s) {
+    s->halton_consts.initialize(s->width, s->height);
     camera_commit(*s);
     if (s->filter_type == 1) build_gaussian(*s);
     build_accel(*s);

@@ -356,3 +356,51 @@ def test_reporter_progress_and_stop(tmp_path, built):
     color2, _, _, stats2 = s.render()  # the renderer is reusable after a stop
     assert stats2["n_gen"] == stats["n_gen"] and np.allclose(color2, ref, rtol=1e-4, atol=1e-5)
     s.close()
+
+
+def test_halton_sampler_parity(tmp_path, built):
+    """renderer "sampler": "halton" (builtin/sampler/halton.cpp; the reference picks its sampler at compile time): the kernels'
+    Owen-scrambled Halton draws are bit-identical to the oracle's -- sampler states after generate and after a bounce, and the
+    whole render."""
+    import json
+
+    from btrc_b200 import api, scenes
+    from oracle import front
+
+    W, H, spp = 96, 64, 8
+    base = scenes.make_cornell(str(tmp_path), width=W, height=H, spp=spp, state_count=20000)
+    root = json.load(open(base))
+    root["renderer"]["sampler"] = "halton"
+    path = str(tmp_path / "halton.json")
+    json.dump(root, open(path, "w"))
+    s = api.Scene(path)
+    o = front.OracleScene(path)
+    n = W * H * 2 + 777
+    a, b = s.generate(0, n), o.generate(0, n)
+    assert np.array_equal(a["rng"], b["rng"]) and np.array_equal(a["pixel"], b["pixel"])      # (halton index, dimension << 1)
+    assert (a["rng"][:, 1] == 5 << 1).all()
+    assert np.abs(a["d_t1"][:, :3] - b["d_t1"][:, :3]).max() < 1e-6                          # same film offsets => same rays
+    # one shade step on identical states: the continuation states carry identical sampler states and matching throughput
+    flag, detail = o.closest_hit(b["o_med"], b["d_t1"])
+    ref = o.shade(b, flag, detail)
+    nxt, shd = s.shade(b, flag, detail)
+    keep = (ref["status"] & 1) != 0
+    assert abs(nxt["rng"].shape[0] - int(keep.sum())) <= 2
+    ka = {(int(p[0]), int(p[1]), int(r[0])): i for i, (p, r) in enumerate(zip(nxt["pixel"], nxt["rng"]))}
+    hits = 0
+    for j in np.nonzero(keep)[0][:5000]:
+        key = (int(ref["next"]["pixel"][j][0]), int(ref["next"]["pixel"][j][1]), int(ref["next"]["rng"][j][0]))
+        i = ka.get(key)
+        if i is None:
+            continue
+        hits += 1
+        assert nxt["rng"][i][1] == ref["next"]["rng"][j][1]                                   # same number of draws
+        assert np.allclose(nxt["beta_depth"][i, :3], ref["next"]["beta_depth"][j, :3], rtol=2e-3, atol=1e-5)
+    assert hits > 4000
+    color, _, _, stats = s.render()
+    r = o.render()
+    assert stats["n_gen"] == r["stats"]["n_gen"]
+    for k in ("n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss"):
+        assert abs(stats[k] - r["stats"][k]) <= 2e-3 * r["stats"][k] + 4, k
+    assert util.rel_mse(color[..., :3], r["color"][..., :3]) < 2e-3
+    s.close()
