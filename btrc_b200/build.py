@@ -25,7 +25,7 @@ NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 HOST_SRCS = ["host/node.cpp", "host/mesh.cpp", "host/bvh.cpp", "host/scene.cpp", "host/renderer.cpp", "host/image_io.cpp", "capi.cpp"]
-DEVICE_SRCS = ["device/kernels.cu"]
+DEVICE_SRCS = ["device/kernels.cu", "device/lbvh.cu"]
 
 HOST_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-Wall", "-Wno-unknown-pragmas", f"-I{CUDA_HOME}/include"]
 # -ftz / -prec-div / -prec-sqrt: the reference's own floating-point contract (fast_math => div.approx, sqrt.approx,

@@ -21,6 +21,11 @@ struct LaunchCfg {
     bool traverse_ifif = false;
 };
 
+// Device-side LBVH build (lbvh.cu): tris_in / ids_in are device arrays in input order; tris_out / ids_out (caller allocated) receive
+// the sorted triangles, *nodes_out (cudaMalloc'ed here, 64 bytes per node) the hierarchy.  Returns the root reference.
+int build_lbvh_device(int n, const float4 *tris_in, const uint2 *ids_in, const float scene_lo[3], const float scene_hi[3], float coord_max,
+                      float4 *tris_out, uint2 *ids_out, float4 **nodes_out, int *n_nodes_out, cudaStream_t stream);
+
 void launch_prepare(WaveCtl *ctl, cudaStream_t stream);
 void launch_generate(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, FilmDevice film,
                      WaveCtl *ctl, cudaStream_t stream);

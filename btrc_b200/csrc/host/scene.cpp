@@ -458,6 +458,11 @@ void Scene::create(const NodeP &root) {
         renderer.type = r->child("type")->as_string();
         if (renderer.type != "wfpt" && renderer.type != "pt") throw Error("unknown renderer type: " + renderer.type);
         renderer.tile = r->bool_or("tile", renderer.tile);
+        if (auto bn = r->find("bvh_builder")) {  // the reference always builds with OptiX; here: host SAH or device LBVH
+            const std::string bt = bn->as_string();
+            if (bt != "sah" && bt != "lbvh") throw Error("unknown bvh builder: " + bt);
+            renderer.lbvh = bt == "lbvh";
+        }
         if (auto sn = r->find("sampler")) {  // wavefront/common.h:36-37 chooses at compile time; here it is a renderer parameter
             const std::string st = sn->as_string();
             if (st != "independent" && st != "halton") throw Error("unknown sampler type: " + st);
@@ -627,7 +632,13 @@ void Scene::commit() {
 
     // ---- BVH
     auto t0 = std::chrono::steady_clock::now();
-    {
+    scene_coord_max = 0;
+    for (int a = 0; a < 3; ++a) scene_coord_max = std::max(scene_coord_max, std::max(std::fabs(wb.lo[a]), std::fabs(wb.hi[a])));
+    scene_box = wb;
+    if (renderer.lbvh) {  // built on the device at upload (device/lbvh.cu): only the unsorted triangle arrays are prepared here
+        flat_bvh = FlatBvh2();
+        bvh_depth = 0;
+    } else {
         std::vector<AABB> boxes;
         std::vector<Vec3> centers;
         float coord_max = 0;
@@ -760,11 +771,51 @@ void Scene::upload_device() {
         g.total_area = m.total_area;
         geos.push_back(g);
     }
-    dev.bvh.nodes = reinterpret_cast<const float4 *>(upload(flat_bvh.nodes));
-    dev.bvh.tris = reinterpret_cast<const float4 *>(upload(flat_bvh.tris));
-    dev.bvh.tri_ids = reinterpret_cast<const uint2 *>(upload(flat_bvh.tri_ids));
-    dev.bvh.root_ref = flat_bvh.root_ref;
-    dev.bvh.n_tris = (int)world_tris.size();
+    if (renderer.lbvh) {
+        const size_t n = world_tris.size();
+        std::vector<float> tin(12 * n);
+        std::vector<uint32_t> iin(2 * n);
+#pragma omp parallel for
+        for (long long i = 0; i < (long long)n; ++i) {
+            const WorldTri &t = world_tris[i];
+            float *o = &tin[12 * (size_t)i];
+            o[0] = t.p0.x; o[1] = t.p0.y; o[2] = t.p0.z; o[3] = t.n.x;
+            o[4] = t.e1.x; o[5] = t.e1.y; o[6] = t.e1.z; o[7] = t.n.y;
+            o[8] = t.e2.x; o[9] = t.e2.y; o[10] = t.e2.z; o[11] = t.n.z;
+            iin[2 * (size_t)i] = t.inst; iin[2 * (size_t)i + 1] = t.prim;
+        }
+        DeviceBuffer d_tin(tin.size() * 4), d_iin(iin.size() * 4);
+        d_tin.upload(tin.data(), tin.size() * 4);
+        d_iin.upload(iin.data(), iin.size() * 4);
+        buffers_.emplace_back(tin.size() * 4);
+        float4 *d_tris = buffers_.back().as<float4>();
+        buffers_.emplace_back(iin.size() * 4);
+        uint2 *d_ids = buffers_.back().as<uint2>();
+        float4 *d_nodes = nullptr;
+        int n_nodes = 0;
+        const float lo[3] = {scene_box.lo.x, scene_box.lo.y, scene_box.lo.z}, hi[3] = {scene_box.hi.x, scene_box.hi.y, scene_box.hi.z};
+        const auto t0 = std::chrono::steady_clock::now();
+        try {
+            dev.bvh.root_ref = build_lbvh_device((int)n, d_tin.as<float4>(), d_iin.as<uint2>(), lo, hi, scene_coord_max, d_tris, d_ids, &d_nodes,
+                                                 &n_nodes, nullptr);
+        } catch (const std::exception &e) { throw Error(e.what()); }
+        bvh_build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        buffers_.emplace_back();
+        buffers_.back().ptr = d_nodes;  // adopted: freed with the scene's other device buffers
+        buffers_.back().bytes = 64 * (size_t)std::max(n_nodes, 1);
+        if (!d_nodes) buffers_.back().alloc(64);
+        dev.bvh.nodes = buffers_.back().as<float4>();
+        dev.bvh.tris = d_tris;
+        dev.bvh.tri_ids = d_ids;
+        dev.bvh.n_tris = (int)n;
+        lbvh_nodes = n_nodes;
+    } else {
+        dev.bvh.nodes = reinterpret_cast<const float4 *>(upload(flat_bvh.nodes));
+        dev.bvh.tris = reinterpret_cast<const float4 *>(upload(flat_bvh.tris));
+        dev.bvh.tri_ids = reinterpret_cast<const uint2 *>(upload(flat_bvh.tri_ids));
+        dev.bvh.root_ref = flat_bvh.root_ref;
+        dev.bvh.n_tris = (int)world_tris.size();
+    }
     if (!filter_alias.empty()) dev.filter_alias = reinterpret_cast<const float2 *>(upload(filter_alias));
     for (InstanceInfo &info : instance_info) {  // table pointers of the instance's mesh, denormalised (types.h)
         const GeometryInfo &g = geos[info.geometry_id];

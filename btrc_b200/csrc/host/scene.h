@@ -100,6 +100,7 @@ struct EnvLightDesc {
 struct RendererDesc {  // builtin/renderer/wavefront.cpp:375-398
     std::string type = "wfpt";
     bool tile = false;
+    bool lbvh = false;    // "bvh_builder": "sah" (host binned SAH, default) | "lbvh" (device-side Morton-code build at upload)
     bool halton = false;  // "sampler": "independent" (default, what the reference's wavefront renderer is compiled with) | "halton"
     int spp = 128;
     int min_depth = 5, max_depth = 10;
@@ -143,6 +144,9 @@ public:
     std::vector<float> ibl_tile_probs;      // EnvirLightSampler tile table (light/env_sampler.cpp:72-122)
     std::vector<AliasUnit> ibl_alias;
     double bvh_build_seconds = 0;
+    float scene_coord_max = 0;   // largest |coordinate| of the world box (BVH box padding)
+    AABB scene_box;              // world box incl. the camera (Morton grid of the device builder)
+    int lbvh_nodes = 0;          // nodes produced by the device builder
     int bvh_depth = 0;
 
     Scene() = default;

@@ -30,8 +30,15 @@ template <typename T> static inline T __ldg(const T *p) { return *p; }
 static thread_local uint64_t g_count[2];
 #define BTRC_TRAV_COUNT(which) (++g_count[which])
 #define BTRC_TRAV_QUAL static inline
+#define BTRC_LBVH_FENCE() ((void)0)
+#define BTRC_LBVH_ATOMIC_INC(p) ((*(p))++)
+#define BTRC_LBVH_LOAD(p) (*(p))
+static inline float __int_as_float(int x) { float f; std::memcpy(&f, &x, 4); return f; }
 #include "../../btrc_b200/csrc/device/traverse.cuh"
+#include "../../btrc_b200/csrc/device/lbvh.cuh"
 #include "../../btrc_b200/csrc/host/bvh.h"
+#include <algorithm>
+#include <numeric>
 
 using namespace btrc;
 
@@ -81,6 +88,59 @@ void *ht_build(int n, const float *verts, const uint32_t *ids) {
     auto *h = new HostBvh;
     h->w = flatten_bvh2(bb, tris);
     h->n_inner = (int)(h->w.nodes.size() / 16);
+    return h;
+}
+
+// The device LBVH builder (device/lbvh.cuh) run in host loops: same per-element functions, std::stable_sort for the radix sort
+void *ht_build_lbvh(int n, const float *verts, const uint32_t *ids) {
+    std::vector<float4> tris_in(3 * (size_t)n);
+    std::vector<uint2> ids_in(n);
+    AABB wb;
+    for (int i = 0; i < n; ++i) {
+        const Vec3 p0(verts[9 * i], verts[9 * i + 1], verts[9 * i + 2]), p1(verts[9 * i + 3], verts[9 * i + 4], verts[9 * i + 5]),
+            p2(verts[9 * i + 6], verts[9 * i + 7], verts[9 * i + 8]);
+        const Vec3 e1 = p0 - p1, e2 = p2 - p0, nn = cross(e1, e2);
+        tris_in[3 * i] = make_float4(p0.x, p0.y, p0.z, nn.x);
+        tris_in[3 * i + 1] = make_float4(e1.x, e1.y, e1.z, nn.y);
+        tris_in[3 * i + 2] = make_float4(e2.x, e2.y, e2.z, nn.z);
+        ids_in[i] = make_uint2(ids[2 * i], ids[2 * i + 1]);
+        wb.extend(p0); wb.extend(p1); wb.extend(p2);
+    }
+    float cm = 0;
+    for (int a = 0; a < 3; ++a) cm = std::max(cm, std::max(std::fabs(wb.lo[a]), std::fabs(wb.hi[a])));
+    const int ni = std::max(n - 1, 1);
+    std::vector<uint32_t> code(n), index(n);
+    std::vector<LbvhBox> box_in(n), node_box(ni);
+    std::vector<int2> child(ni), range(ni);
+    std::vector<int> parent(2 * (size_t)n), visit(ni), live(ni), new_index(ni);
+    auto *h = new HostBvh;
+    h->w.tris.resize(12 * (size_t)n);
+    h->w.tri_ids.resize(2 * (size_t)n);
+    LbvhBuild b{};
+    b.n = n; b.tris_in = tris_in.data(); b.ids_in = ids_in.data(); b.coord_max = cm;
+    for (int k = 0; k < 3; ++k) { b.scene_lo[k] = wb.lo[k]; const float e = wb.hi[k] - wb.lo[k]; b.scene_inv_ext[k] = e > 0 ? 1.0f / e : 0.0f; }
+    b.code = code.data(); b.index = index.data(); b.box_in = box_in.data();
+    b.tris = reinterpret_cast<float4 *>(h->w.tris.data()); b.ids = reinterpret_cast<uint2 *>(h->w.tri_ids.data());
+    b.child = child.data(); b.range = range.data(); b.parent = parent.data(); b.node_box = node_box.data();
+    b.visit = visit.data(); b.live = live.data(); b.new_index = new_index.data();
+    for (int i = 0; i < n; ++i) lbvh_box_and_code(b, i);
+    std::vector<uint32_t> perm(n);
+    std::iota(perm.begin(), perm.end(), 0u);
+    std::stable_sort(perm.begin(), perm.end(), [&](uint32_t x, uint32_t y) { return code[x] < code[y]; });
+    std::vector<uint32_t> code2(n), index2(n);
+    for (int s = 0; s < n; ++s) { code2[s] = code[perm[s]]; index2[s] = index[perm[s]]; }
+    b.code = code2.data(); b.index = index2.data();
+    for (int s = 0; s < n; ++s) lbvh_gather(b, s);
+    if (n <= kLbvhLeaf) { h->w.root_ref = ~(n - 1); h->w.nodes.assign(16, 0.0f); return h; }
+    for (int i = 0; i < n - 1; ++i) lbvh_build_node(b, i);
+    for (int s = 0; s < n; ++s) lbvh_fit_from_leaf(b, s);
+    int acc = 0;
+    for (int i = 0; i < n - 1; ++i) { new_index[i] = acc; acc += live[i]; }
+    h->w.nodes.assign(16 * (size_t)std::max(acc, 1), 0.0f);
+    b.nodes_out = reinterpret_cast<float4 *>(h->w.nodes.data());
+    for (int i = 0; i < n - 1; ++i) lbvh_emit_node(b, i);
+    h->w.root_ref = 0;
+    h->n_inner = acc;
     return h;
 }
 

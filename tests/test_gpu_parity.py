@@ -404,3 +404,44 @@ def test_halton_sampler_parity(tmp_path, built):
         assert abs(stats[k] - r["stats"][k]) <= 2e-3 * r["stats"][k] + 4, k
     assert util.rel_mse(color[..., :3], r["color"][..., :3]) < 2e-3
     s.close()
+
+
+def test_device_lbvh_builder(tmp_path, built):
+    """renderer "bvh_builder": "lbvh" (device/lbvh.cu: Morton codes, radix sort, Karras radix tree, bottom-up fit) -- the hits do not
+    depend on the hierarchy: the 777,600 golden rays and a whole render give exactly what the host SAH tree gives."""
+    import json
+
+    from btrc_b200 import api, scenes
+    from oracle import front
+
+    path, tris = util.write_fan_cornell_scene(str(tmp_path))[:2]
+    root = json.load(open(path))
+    root["renderer"]["bvh_builder"] = "lbvh"
+    lpath = str(tmp_path / "fan_lbvh.json")
+    json.dump(root, open(lpath, "w"))
+    s = api.Scene(lpath)
+    o = front.OracleScene(path)
+    o_med, d_t1 = util.bvh_benchmark_rays()
+    f0, d0 = o.closest_hit(o_med, d_t1)
+    f1, d1 = s.closest_hit(o_med, d_t1)
+    assert np.array_equal(f0, f1) and np.array_equal(d0, d1)
+    s.close()
+    # a scene with many triangles: materials test (15 spheres), render with both builders
+    base = scenes.make_material_test(str(tmp_path / "m"), width=160, height=90, spp=4, rings=40, segments=40, tex_res=64, state_count=40000)
+    root = json.load(open(base))
+    root["renderer"]["bvh_builder"] = "lbvh"
+    lbase = os.path.join(os.path.dirname(base), "scene_lbvh.json")
+    json.dump(root, open(lbase, "w"))
+    a = api.Scene(base)
+    b = api.Scene(lbase)
+    ca, _, _, sa = a.render()
+    cb, _, _, sb = b.render()
+    for k in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss", "n_splat"):
+        assert sa[k] == sb[k], k
+    assert np.allclose(ca, cb, rtol=1e-4, atol=1e-5)
+    assert b.info.bvh_build_seconds > 0
+    st = front.OracleScene(base).generate(0, 160 * 90)
+    fa, da = a.closest_hit(st["o_med"], st["d_t1"])
+    fb, db = b.closest_hit(st["o_med"], st["d_t1"])
+    assert np.array_equal(fa, fb) and np.array_equal(da, db)
+    a.close(); b.close()

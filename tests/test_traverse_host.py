@@ -17,13 +17,15 @@ def ht(request):
     src = os.path.join(ROOT, "tests", "host", "host_traverse.cpp")
     out = os.path.join(ROOT, "tests", "host", "_libhosttrav_%s.so" % request.param)
     deps = [src, os.path.join(ROOT, "btrc_b200/csrc/host/bvh.cpp"), os.path.join(ROOT, "btrc_b200/csrc/host/bvh.h"),
-            os.path.join(ROOT, "btrc_b200/csrc/device/traverse.cuh")]
+            os.path.join(ROOT, "btrc_b200/csrc/device/traverse.cuh"), os.path.join(ROOT, "btrc_b200/csrc/device/lbvh.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-I/usr/local/cuda/include", "-DHT_TRAVERSE=" + request.param, src, deps[1], "-o", out],
                        check=True)
     L = ctypes.CDLL(out)
     L.ht_build.restype = ctypes.c_void_p
     L.ht_build.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    L.ht_build_lbvh.restype = ctypes.c_void_p
+    L.ht_build_lbvh.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     L.ht_free.argtypes = [ctypes.c_void_p]
     L.ht_num_nodes.argtypes = [ctypes.c_void_p]
     L.ht_closest.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 5
@@ -31,11 +33,21 @@ def ht(request):
     return L
 
 
+BUILDER = ["sah"]  # which of the product's builders _build uses: the host SAH builder or the device LBVH functions run on the host
+
+
+@pytest.fixture(params=["sah", "lbvh"])
+def builder(request):
+    BUILDER[0] = request.param
+    yield request.param
+    BUILDER[0] = "sah"
+
+
 def _build(L, orc):
     verts, ids = orc.triangles()
     verts = np.ascontiguousarray(verts, f32)
     ids = np.ascontiguousarray(ids, np.uint32)
-    h = L.ht_build(verts.shape[0], verts.ctypes.data, ids.ctypes.data)
+    h = (L.ht_build_lbvh if BUILDER[0] == "lbvh" else L.ht_build)(verts.shape[0], verts.ctypes.data, ids.ctypes.data)
     assert h
     return h
 
@@ -79,7 +91,7 @@ def _walk(orc, st, bounces, visit):
         st = {k: np.ascontiguousarray(np.concatenate([p[k] for p in parts])) for k in parts[0]}
 
 
-def test_golden_rays_cornell(ht, built, tmp_path):
+def test_golden_rays_cornell(ht, builder, built, tmp_path):
     """777,600 primary rays of lib/bvh's benchmark on the fan-triangulated Cornell box (tests/golden): same hits as the oracle."""
     from oracle import front
 
@@ -92,7 +104,7 @@ def test_golden_rays_cornell(ht, built, tmp_path):
 
 
 @pytest.mark.parametrize("kind", ["cornell", "materials"])
-def test_bounce_and_shadow_rays(ht, built, tmp_path, kind):
+def test_bounce_and_shadow_rays(ht, builder, built, tmp_path, kind):
     from btrc_b200 import scenes
     from oracle import front
 
@@ -122,7 +134,7 @@ def test_bounce_and_shadow_rays(ht, built, tmp_path, kind):
     ht.ht_free(h)
 
 
-def test_edge_cases(ht, built, tmp_path):
+def test_edge_cases(ht, builder, built, tmp_path):
     """Axis-parallel rays (zero direction components), zero-length and negative intervals, rays starting on geometry."""
     from btrc_b200 import scenes
     from oracle import front
