@@ -1,0 +1,50 @@
+"""The `btrc` executable keeps BtrcCLI's contract (src/cli/main.cpp:83-105): banner, one argument, exit code 0 on usage and on
+success, -1 with the chained error messages on stderr on failure; images are written by the scene's `save` post-processors."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from tests.util import ROOT
+
+CLI = os.path.join(ROOT, "btrc_b200", "btrc")
+
+
+def test_usage_and_errors(built, tmp_path):
+    from btrc_b200 import scenes
+
+    r = subprocess.run([CLI], capture_output=True, text=True)
+    assert r.returncode == 0 and ">>> Btrc Renderer" in r.stdout and "usage:" in r.stdout
+    r = subprocess.run([CLI, "a.json", "b.json"], capture_output=True, text=True)
+    assert r.returncode == 0 and "usage:" in r.stdout
+    r = subprocess.run([CLI, str(tmp_path / "missing.json")], capture_output=True, text=True)
+    assert r.returncode == 255 and r.stderr.strip() != ""          # -1
+    path = scenes.make_cornell(str(tmp_path), width=8, height=8, spp=1, state_count=64)
+    root = json.load(open(path))
+    root["scene"]["entities"][0]["material"]["type"] = "velvet"
+    bad = str(tmp_path / "bad.json")
+    json.dump(root, open(bad, "w"))
+    r = subprocess.run([CLI, bad], capture_output=True, text=True)
+    assert r.returncode == 255
+    lines = [l for l in r.stderr.splitlines() if l.strip()]
+    assert any("unknown material type: velvet" in l for l in lines)   # factory/context.h:190-196 wording
+    assert len(lines) >= 2                                            # chained: the context lines of the nested exceptions
+
+
+@pytest.mark.gpu
+def test_cli_renders_and_saves(built, tmp_path):
+    from btrc_b200 import api, scenes
+
+    out = str(tmp_path / "out.png")
+    path = scenes.make_cornell(str(tmp_path), width=96, height=64, spp=16, state_count=20000, save=out)
+    r = subprocess.run([CLI, path], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "100.0%" in r.stdout and "Msamples/s" in r.stdout
+    img = np.asarray(Image.open(out)).astype(np.float64) / 255.0
+    assert img.shape == (64, 96, 4)
+    color, _, _, _ = api.Scene(path).render()
+    want = np.minimum(np.clip(color[..., :3], 0, None) ** (1 / 2.2), 1.0)
+    assert np.abs(img[..., :3] - want).mean() < 0.01
