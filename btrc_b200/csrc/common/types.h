@@ -212,6 +212,7 @@ struct SceneDevice {
     const float2 *filter_alias;  // gaussian filter alias table (256*256)
     uint32_t vol_prim_medium_id;
     float world_diagonal;
+    float sort_lo[3], sort_scale[3];  // ray-sort grid: cell = (p - sort_lo) * sort_scale, 8 cells per axis over the world box
     HaltonConsts halton;
 };
 
@@ -223,6 +224,7 @@ struct PathQueue {
     float4 *rad;     // path radiance rgb | pixel index bits (y * W + x)
     ulonglong2 *rng; // PCG state, inc
     float4 *ble;     // beta_le.rgb | bsdf pdf (negative: delta)
+    uint32_t *key;   // ray-sort key of the state: direction octant << 9 | 8x8x8 cell of the origin (scratch of the sort kernels)
 };
 
 // Shade classes: 0 = miss, 1 + MaterialType = hit on an instance of that material type.  The closest-hit kernel
@@ -240,6 +242,15 @@ struct ShadowQueue {
     float4 *ray_o;   // o.xyz | medium id bits
     float4 *ray_d;   // d.xyz | t1
     float4 *beta_li; // beta_li.rgb | pixel index bits
+    uint32_t *key;   // ray-sort key (as PathQueue::key)
+};
+
+// Binned ray order (counting sort by key, 4096 bins): the traversal kernels visit surviving paths and shadow rays bin by bin, so that
+// the 32 rays of a warp start in the same region of the scene and head into the same octant.
+constexpr int kSortBins = 4096;
+struct RaySort {
+    uint32_t *order;   // sorted ray indices
+    int *bin;          // kSortBins + 1 counters: histogram, then exclusive offsets / scatter cursors
 };
 
 struct FilmDevice {
@@ -265,6 +276,9 @@ struct WaveCtl {
     long long end;        // one past the last camera-path index of this render
     int pool;             // state_count
     int done;
+    int sort_enabled;     // the renderer sorts surviving paths and shadow rays before tracing them
+    int n_sorted;         // surviving paths whose visiting order comes from RaySort::order (0: queue order)
+    int n_shadow_sorted;  // shadow rays visited through the shadow RaySort (0: queue order)
     // statistics (SURVEY 8d event counts)
     unsigned long long n_gen, n_closest, n_hit, n_next_total, n_shadow_total, n_shadow_miss, n_splat, n_iter;
 };

@@ -65,6 +65,8 @@ __global__ void prepare_kernel(WaveCtl *ctl) {
     ctl->gen_base = ctl->cursor;
     ctl->cursor += n_new;
     ctl->n_survivors = survivors;
+    ctl->n_sorted = ctl->sort_enabled ? survivors : 0;
+    ctl->n_shadow_sorted = 0;
     ctl->n_new = n_new;
     ctl->n_active = survivors + n_new;
     ctl->n_next = 0;
@@ -182,17 +184,88 @@ __device__ __forceinline__ void class_append(const HitQueue &hq, WaveCtl *ctl, b
 #ifndef BTRC_TRACE_MIN_BLOCKS
 #define BTRC_TRACE_MIN_BLOCKS 6
 #endif
-template <bool IFIF>
-__global__ void __launch_bounds__(kBlock, BTRC_TRACE_MIN_BLOCKS) trace_kernel(SceneDevice scene, PathQueue q, HitQueue hq, WaveCtl *ctl) {
+// direction octant << 9 | 8x8x8 cell of the origin over the world box
+__device__ __forceinline__ uint32_t ray_sort_key(const SceneDevice &scene, f3 o, f3 d) {
+    const int cx = min(max(int((o.x - scene.sort_lo[0]) * scene.sort_scale[0]), 0), 7);
+    const int cy = min(max(int((o.y - scene.sort_lo[1]) * scene.sort_scale[1]), 0), 7);
+    const int cz = min(max(int((o.z - scene.sort_lo[2]) * scene.sort_scale[2]), 0), 7);
+    const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+    return (oct << 9) | uint32_t(cx | (cy << 3) | (cz << 6));
+}
+
+// ---- binned ray order: histogram of the keys, exclusive scan of the 4096 bins, scatter of the indices --------------------------
+// block-private histograms in shared memory: rays cluster in a few bins, global atomics on those would serialise
+constexpr int kSortBlock = 512;
+// (the keys are computed here from the rays, not by the shade kernels that wrote them: those run at their register limit)
+__global__ void __launch_bounds__(kSortBlock) sort_hist_kernel(SceneDevice scene, const float4 *__restrict__ ray_o, const float4 *__restrict__ ray_d,
+                                                              uint32_t *__restrict__ key, const int *count, int *bin) {
+    __shared__ int sh[kSortBins];
+    for (int b = threadIdx.x; b < kSortBins; b += kSortBlock) sh[b] = 0;
+    __syncthreads();
+    const int n = *count;
+    for (int i = blockIdx.x * kSortBlock + threadIdx.x; i < n; i += gridDim.x * kSortBlock) {
+        const uint32_t k = ray_sort_key(scene, xyz(ray_o[i]), xyz(ray_d[i]));
+        key[i] = k;
+        atomicAdd(&sh[k], 1);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kSortBins; b += kSortBlock) if (sh[b]) atomicAdd(&bin[b], sh[b]);
+}
+__global__ void __launch_bounds__(1024) sort_scan_kernel(int *bin) {  // one block: exclusive scan of kSortBins counters (4 per thread)
+    __shared__ int part[1024];
+    const int t = threadIdx.x;
+    int v[4], sum = 0;
+    for (int k = 0; k < 4; ++k) { v[k] = bin[4 * t + k]; sum += v[k]; }
+    part[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const int add = t >= off ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += add;
+        __syncthreads();
+    }
+    int base = part[t] - sum;
+    for (int k = 0; k < 4; ++k) { bin[4 * t + k] = base; base += v[k]; }
+}
+// every block ranks one contiguous chunk of the keys: counts in shared memory, one global reservation per (block, bin), local ranks
+__global__ void __launch_bounds__(kSortBlock) sort_scatter_kernel(const uint32_t *__restrict__ key, const int *count, int *bin, uint32_t *order, int *n_sorted_out) {
+    __shared__ int sh_cnt[kSortBins];
+    __shared__ int sh_base[kSortBins];
+    const int n = *count;
+    const int chunk = (n + gridDim.x - 1) / gridDim.x;
+    const int lo = min(blockIdx.x * chunk, n), hi = min(lo + chunk, n);
+    for (int b = threadIdx.x; b < kSortBins; b += kSortBlock) sh_cnt[b] = 0;
+    __syncthreads();
+    for (int i = lo + threadIdx.x; i < hi; i += kSortBlock) atomicAdd(&sh_cnt[key[i]], 1);
+    __syncthreads();
+    for (int b = threadIdx.x; b < kSortBins; b += kSortBlock) {
+        const int c = sh_cnt[b];
+        sh_base[b] = c ? atomicAdd(&bin[b], c) : 0;
+        sh_cnt[b] = 0;
+    }
+    __syncthreads();
+    for (int i = lo + threadIdx.x; i < hi; i += kSortBlock) {
+        const uint32_t k = key[i];
+        order[sh_base[k] + atomicAdd(&sh_cnt[k], 1)] = (uint32_t)i;
+    }
+    if (n_sorted_out && blockIdx.x == 0 && threadIdx.x == 0) *n_sorted_out = n;
+}
+
+// SORTED: surviving paths are visited through RaySort::order and the class lists are left to classify_kernel (state order)
+template <bool IFIF, bool SORTED>
+__global__ void __launch_bounds__(kBlock, BTRC_TRACE_MIN_BLOCKS) trace_kernel(SceneDevice scene, PathQueue q, HitQueue hq, RaySort rs, WaveCtl *ctl) {
     const int n = ctl->n_active;
+    const int n_sorted = SORTED ? ctl->n_sorted : 0;
+    const bool append = !SORTED || ctl->sort_enabled != 2;
     unsigned long long hits = 0;
     for (;;) {
         int base = 0;
         if (lane_id() == 0) base = atomicAdd(&ctl->trace_cursor, 32);
         base = __shfl_sync(kFull, base, 0);
         if (base >= n) break;
-        const int i = base + lane_id();
-        const bool valid = i < n;
+        const int j = base + lane_id();
+        const bool valid = j < n;
+        const int i = (SORTED && valid && j < n_sorted) ? (int)rs.order[j] : j;  // survivors bin by bin, new camera paths in pixel order
         float4 o4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d4 = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
         if (valid) { o4 = q.ray_o[i]; d4 = q.ray_d[i]; }
         const HitRec h = traverse_warp<false, IFIF>(scene.bvh, o4, d4, valid);
@@ -201,7 +274,7 @@ __global__ void __launch_bounds__(kBlock, BTRC_TRACE_MIN_BLOCKS) trace_kernel(Sc
             const int inst = store_hit(scene.bvh, h, i, hq.flag, hq.detail);
             if (inst >= 0) { cls = __ldg(scene.instance_class + inst); hits += 1; }
         }
-        class_append(hq, ctl, valid, cls, i);
+        if (append) class_append(hq, ctl, valid, cls, i);
     }
     for (int off = 16; off; off >>= 1) hits += __shfl_down_sync(kFull, hits, off);
     if (lane_id() == 0 && hits) atomicAdd(&ctl->n_hit, hits);
@@ -512,17 +585,19 @@ shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQu
 // ---------------------------------------------------------------------------------------------------------------
 // shadow rays (shadow.cpp:24-74): occlusion with early exit; unoccluded => splat beta_li * Tr
 // ---------------------------------------------------------------------------------------------------------------
-template <bool IFIF>
-__global__ void __launch_bounds__(kBlock, BTRC_TRACE_MIN_BLOCKS) shadow_kernel(SceneDevice scene, RenderParams P, ShadowQueue sq, FilmDevice film, WaveCtl *ctl) {
+template <bool IFIF, bool SORTED>
+__global__ void __launch_bounds__(kBlock, BTRC_TRACE_MIN_BLOCKS) shadow_kernel(SceneDevice scene, RenderParams P, ShadowQueue sq, RaySort rs, FilmDevice film, WaveCtl *ctl) {
     const int n = ctl->n_shadow;
+    const int n_sorted = SORTED ? ctl->n_shadow_sorted : 0;
     unsigned long long misses = 0;
     for (;;) {
         int base = 0;
         if (lane_id() == 0) base = atomicAdd(&ctl->shadow_cursor, 32);
         base = __shfl_sync(kFull, base, 0);
         if (base >= n) break;
-        const int i = base + lane_id();
-        const bool valid = i < n;
+        const int j = base + lane_id();
+        const bool valid = j < n;
+        const int i = (SORTED && valid && j < n_sorted) ? (int)rs.order[j] : j;
         float4 o4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d4 = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
         if (valid) { o4 = sq.ray_o[i]; d4 = sq.ray_d[i]; }
         const HitRec h = traverse_warp<true, IFIF>(scene.bvh, o4, d4, valid);
@@ -589,9 +664,24 @@ void launch_generate(const LaunchCfg &cfg, const SceneDevice &scene, const Rende
     else generate_kernel<false><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, cur, film, ctl);
 }
 
-void launch_trace(const LaunchCfg &cfg, const SceneDevice &scene, PathQueue cur, HitQueue hit, WaveCtl *ctl, cudaStream_t stream) {
-    if (cfg.traverse_ifif) trace_kernel<true><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, cur, hit, ctl);
-    else trace_kernel<false><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, cur, hit, ctl);
+// counting sort of `count` keys into rs.order; *n_sorted_out (a WaveCtl field) is set to the count by the scatter kernel
+void launch_ray_sort(const LaunchCfg &cfg, const SceneDevice &scene, const float4 *ray_o, const float4 *ray_d, uint32_t *key, const int *count, RaySort rs,
+                     int *n_sorted_out, cudaStream_t stream) {
+    cudaMemsetAsync(rs.bin, 0, sizeof(int) * (kSortBins + 1), stream);
+    sort_hist_kernel<<<persistent_blocks(cfg, 2), kSortBlock, 0, stream>>>(scene, ray_o, ray_d, key, count, rs.bin);
+    sort_scan_kernel<<<1, 1024, 0, stream>>>(rs.bin);
+    sort_scatter_kernel<<<persistent_blocks(cfg, 2), kSortBlock, 0, stream>>>(key, count, rs.bin, rs.order, n_sorted_out);
+}
+
+void launch_trace(const LaunchCfg &cfg, const SceneDevice &scene, PathQueue cur, HitQueue hit, RaySort rs, WaveCtl *ctl, cudaStream_t stream) {
+    const int blocks = persistent_blocks(cfg, 8);
+    if (cfg.sorted_rays) {
+        if (cfg.traverse_ifif) trace_kernel<true, true><<<blocks, kBlock, 0, stream>>>(scene, cur, hit, rs, ctl);
+        else trace_kernel<false, true><<<blocks, kBlock, 0, stream>>>(scene, cur, hit, rs, ctl);
+    } else {
+        if (cfg.traverse_ifif) trace_kernel<true, false><<<blocks, kBlock, 0, stream>>>(scene, cur, hit, rs, ctl);
+        else trace_kernel<false, false><<<blocks, kBlock, 0, stream>>>(scene, cur, hit, rs, ctl);
+    }
 }
 
 template <int MAT>
@@ -634,10 +724,16 @@ void launch_medium(const LaunchCfg &cfg, const SceneDevice &scene, const RenderP
     else medium_kernel<false><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
 }
 
-void launch_shadow(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, ShadowQueue shadow, FilmDevice film, WaveCtl *ctl,
+void launch_shadow(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, ShadowQueue shadow, RaySort rs, FilmDevice film, WaveCtl *ctl,
                    cudaStream_t stream) {
-    if (cfg.traverse_ifif) shadow_kernel<true><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, shadow, film, ctl);
-    else shadow_kernel<false><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, shadow, film, ctl);
+    const int blocks = persistent_blocks(cfg, 8);
+    if (cfg.sorted_rays) {
+        if (cfg.traverse_ifif) shadow_kernel<true, true><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
+        else shadow_kernel<false, true><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
+    } else {
+        if (cfg.traverse_ifif) shadow_kernel<true, false><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
+        else shadow_kernel<false, false><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
+    }
 }
 
 void launch_resolve(int width, int height, const float *value, const float *weight, float *out, int normalise, cudaStream_t stream) {

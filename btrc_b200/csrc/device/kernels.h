@@ -19,6 +19,7 @@ struct LaunchCfg {
     // 67.8 ms), if-if when node fetches go to DRAM and the extra loads in flight per warp pay (C4, 0.7 GB of BVH: 136 vs 153 ms);
     // profiles/r1h_ab_ifif.log.  The renderer picks by BVH size against the L2 capacity.
     bool traverse_ifif = false;
+    bool sorted_rays = false;  // the traversal kernels visit rays through RaySort::order (types.h); set with the renderer's sort mode
 };
 
 // Device-side LBVH build (lbvh.cu): tris_in / ids_in are device arrays in input order; tris_out / ids_out (caller allocated) receive
@@ -29,7 +30,9 @@ int build_lbvh_device(int n, const float4 *tris_in, const uint2 *ids_in, const f
 void launch_prepare(WaveCtl *ctl, cudaStream_t stream);
 void launch_generate(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, FilmDevice film,
                      WaveCtl *ctl, cudaStream_t stream);
-void launch_trace(const LaunchCfg &cfg, const SceneDevice &scene, PathQueue cur, HitQueue hit, WaveCtl *ctl, cudaStream_t stream);
+void launch_ray_sort(const LaunchCfg &cfg, const SceneDevice &scene, const float4 *ray_o, const float4 *ray_d, uint32_t *key, const int *count, RaySort rs,
+                     int *n_sorted_out, cudaStream_t stream);
+void launch_trace(const LaunchCfg &cfg, const SceneDevice &scene, PathQueue cur, HitQueue hit, RaySort rs, WaveCtl *ctl, cudaStream_t stream);
 // One kernel per shade class: misses + one instantiation per material type present in the scene (bit m of material_mask
 // = a material of MaterialType m exists).  Returns the number of kernels launched.
 int launch_shade(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, uint32_t material_mask, PathQueue cur,
@@ -39,7 +42,7 @@ void launch_classify(const LaunchCfg &cfg, const SceneDevice &scene, HitQueue hi
 // sample_medium_scattering_kernel (medium.cpp:28-164): runs between trace and shade when the scene has media
 void launch_medium(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, HitQueue hit,
                    PathQueue next, ShadowQueue shadow, FilmDevice film, WaveCtl *ctl, cudaStream_t stream);
-void launch_shadow(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, ShadowQueue shadow, FilmDevice film,
+void launch_shadow(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, ShadowQueue shadow, RaySort rs, FilmDevice film,
                    WaveCtl *ctl, cudaStream_t stream);
 // out = value.xyz / weight (normalise == 1: renormalise as a direction); out.w = 1
 void launch_resolve(int width, int height, const float *value, const float *weight, float *out, int normalise, cudaStream_t stream);

@@ -46,6 +46,10 @@ Renderer::Renderer(Scene &scene, int state_count_override) : scene_(scene) {
                                                      : scene.flat_bvh.nodes.size() * sizeof(float) + scene.flat_bvh.tris.size() * sizeof(float);
         cfg_.traverse_ifif = bvh_bytes > (size_t)prop.l2CacheSize;
         if (const char *e = std::getenv("BTRC_TRAVERSE")) cfg_.traverse_ifif = std::string(e) == "ifif";
+        // Binned ray order (types.h: RaySort) under the same criterion: on C4 (0.7 GB of BVH) visiting surviving paths and shadow rays
+        // bin by bin makes traversal 9-13 % faster for 2 ms of sorting per render (-7.7 % overall); while the BVH sits in L2 the gain
+        // does not pay for the sort and the gather (C2 +4 %, C3 +11 %, C1 +17 %; profiles/r1j_ab_ray_sort.log).  BTRC_SORT_RAYS=0|1|2 overrides.
+        sort_rays_ = bvh_bytes > (size_t)prop.l2CacheSize ? 2 : 0;
     }
     pool_ = state_count_override > 0 ? state_count_override : scene.renderer.state_count;
     if (pool_ <= 0) throw Error("state_count must be positive");
@@ -62,6 +66,7 @@ Renderer::Renderer(Scene &scene, int state_count_override) : scene_(scene) {
         q_[k].rad = alloc<float4>(P);
         q_[k].rng = alloc<ulonglong2>(P);
         q_[k].ble = alloc<float4>(P);
+        q_[k].key = alloc<uint32_t>(P);
     }
     hit_.flag = alloc<uint32_t>(P);
     hit_.detail = alloc<uint4>(P);
@@ -71,6 +76,11 @@ Renderer::Renderer(Scene &scene, int state_count_override) : scene_(scene) {
     shadow_.ray_o = alloc<float4>(P);
     shadow_.ray_d = alloc<float4>(P);
     shadow_.beta_li = alloc<float4>(P);
+    shadow_.key = alloc<uint32_t>(P);
+    sort_path_.order = alloc<uint32_t>(P); sort_path_.bin = alloc<int>(kSortBins + 1);
+    sort_shadow_.order = alloc<uint32_t>(P); sort_shadow_.bin = alloc<int>(kSortBins + 1);
+    if (const char *e = std::getenv("BTRC_SORT_RAYS")) sort_rays_ = std::atoi(e);
+    cfg_.sorted_rays = sort_rays_ != 0;
 
     const size_t npix = (size_t)scene.width * scene.height;
     film_.radiance = alloc<float>(4 * npix);
@@ -110,6 +120,7 @@ void Renderer::render_range(long long begin, long long end) {
     init.cursor = begin;
     init.end = end;
     init.pool = pool_;
+    init.sort_enabled = sort_rays_;
     ctl_host_[8] = init;  // pinned staging slot: the upload is a true async copy on the renderer's stream
     BTRC_CUDA(cudaMemcpyAsync(ctl_, &ctl_host_[8], sizeof(init), cudaMemcpyHostToDevice, stream_));
     BTRC_CUDA(cudaEventRecord(ev_begin_, stream_));
@@ -148,15 +159,18 @@ void Renderer::render_range(long long begin, long long end) {
     while (!done && !stopped_) {
         launch_prepare(ctl_, stream_);
         mark();
+        if (sort_rays_) launch_ray_sort(cfg_, scene_.dev, q_[cur].ray_o, q_[cur].ray_d, q_[cur].key, &ctl_->n_survivors, sort_path_, nullptr, stream_);
         launch_generate(cfg_, scene_.dev, params, q_[cur], film_, ctl_, stream_);
         mark();
-        launch_trace(cfg_, scene_.dev, q_[cur], hit_, ctl_, stream_);
+        launch_trace(cfg_, scene_.dev, q_[cur], hit_, sort_path_, ctl_, stream_);
+        if (sort_rays_ == 2) launch_classify(cfg_, scene_.dev, hit_, ctl_, stream_);
         mark();
         if (has_medium) launch_medium(cfg_, scene_.dev, params, q_[cur], hit_, q_[cur ^ 1], shadow_, film_, ctl_, stream_);
         mark();
         n_kernels += launch_shade(cfg_, scene_.dev, params, material_mask_, q_[cur], hit_, q_[cur ^ 1], shadow_, film_, ctl_, stream_);
         mark();
-        launch_shadow(cfg_, scene_.dev, params, shadow_, film_, ctl_, stream_);
+        if (sort_rays_) launch_ray_sort(cfg_, scene_.dev, shadow_.ray_o, shadow_.ray_d, shadow_.key, &ctl_->n_shadow, sort_shadow_, &ctl_->n_shadow_sorted, stream_);
+        launch_shadow(cfg_, scene_.dev, params, shadow_, sort_shadow_, film_, ctl_, stream_);
         mark();
         const int slot = (int)(iter % 8);
         BTRC_CUDA(cudaMemcpyAsync(&ctl_host_[slot], ctl_, sizeof(WaveCtl), cudaMemcpyDeviceToHost, stream_));
@@ -231,7 +245,7 @@ void Renderer::stage_trace(int n) {
     std::memset(&c, 0, sizeof(c));
     c.n_active = n; c.pool = pool_;
     BTRC_CUDA(cudaMemcpyAsync(ctl_, &c, sizeof(c), cudaMemcpyHostToDevice, stream_));
-    launch_trace(cfg_, scene_.dev, q_[0], hit_, ctl_, stream_);
+    launch_trace(cfg_, scene_.dev, q_[0], hit_, sort_path_, ctl_, stream_);
     BTRC_CUDA(cudaStreamSynchronize(stream_));
     BTRC_CUDA(cudaGetLastError());
 }
@@ -271,7 +285,7 @@ void Renderer::stage_shadow(int n) {
     std::memset(&c, 0, sizeof(c));
     c.n_shadow = n; c.pool = pool_;
     BTRC_CUDA(cudaMemcpyAsync(ctl_, &c, sizeof(c), cudaMemcpyHostToDevice, stream_));
-    launch_shadow(cfg_, scene_.dev, scene_.render_params(), shadow_, film_, ctl_, stream_);
+    launch_shadow(cfg_, scene_.dev, scene_.render_params(), shadow_, sort_shadow_, film_, ctl_, stream_);
     BTRC_CUDA(cudaStreamSynchronize(stream_));
     BTRC_CUDA(cudaGetLastError());
 }

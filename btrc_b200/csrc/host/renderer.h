@@ -75,6 +75,8 @@ private:
     PathQueue q_[2]{};
     HitQueue hit_{};
     ShadowQueue shadow_{};
+    RaySort sort_path_{}, sort_shadow_{};  // binned visiting order of surviving paths / shadow rays (types.h)
+    int sort_rays_ = 1;  // 0: off; 1: sorted traversal, shade lists in traversal order; 2: sorted traversal, shade lists in state order
     FilmDevice film_{};
     uint32_t material_mask_ = 0;    // bit m: a material of MaterialType m exists (one shade kernel per set bit)
     WaveCtl *ctl_ = nullptr;        // device

@@ -898,6 +898,11 @@ void Scene::upload_device() {
         }
         dev.halton.primes = upload(primes);
     }
+    for (int a = 0; a < 3; ++a) {  // ray-sort grid: 8 cells per axis over the world box
+        const float ext = scene_box.hi[a] - scene_box.lo[a];
+        dev.sort_lo[a] = scene_box.lo[a];
+        dev.sort_scale[a] = ext > 0 ? 8.0f / ext : 0.0f;
+    }
     dev.media = upload(medium_table);
     dev.vol_prims = volume_prims.empty() ? nullptr : upload(volume_prims);
     dev.n_vol_prims = (int)volume_prims.size();

@@ -13,23 +13,24 @@ verts, ids = o.triangles(); verts = np.ascontiguousarray(verts, np.float32)
 h = L.sim_build(verts.shape[0], verts.ctypes.data)
 C_NODE, C_TRI = 45.0, 60.0
 
-def morton_key(om, dt):
+def morton_key(om, dt, bits=5):
     p = om[:, :3]; lo = p.min(0); ext = np.maximum(p.max(0) - lo, 1e-6)
-    q = np.clip(((p - lo) / ext * 31).astype(np.uint32), 0, 31)
+    q = np.clip(((p - lo) / ext * (2 ** bits - 1)).astype(np.uint32), 0, 2 ** bits - 1)
     key = np.zeros(len(p), np.uint32)
-    for b in range(5):
+    for b in range(bits):
         for a in range(3):
             key |= ((q[:, a] >> b) & 1) << (3 * b + a)
     octant = ((dt[:, 0] < 0).astype(np.uint32) | ((dt[:, 1] < 0).astype(np.uint32) << 1) | ((dt[:, 2] < 0).astype(np.uint32) << 2))
-    return (octant << 15) | key
+    return (octant << (3 * bits)) | key
 
 def report(tag, om, dt, anyhit):
     om = np.ascontiguousarray(om, np.float32); dt = np.ascontiguousarray(dt, np.float32)
     n = om.shape[0]
     row = []
-    for name, order in (("asis", None), ("octant", np.argsort(morton_key(om, dt) >> 15, kind="stable")), ("sorted", np.argsort(morton_key(om, dt), kind="stable"))):
+    for name, order in (("asis", None), ("m2+oct", np.argsort(morton_key(om, dt, 2), kind="stable")), ("m3+oct", np.argsort(morton_key(om, dt, 3), kind="stable")),
+                        ("m4+oct", np.argsort(morton_key(om, dt, 4), kind="stable")), ("m5+oct", np.argsort(morton_key(om, dt, 5), kind="stable"))):
         a, b = (om, dt) if order is None else (np.ascontiguousarray(om[order]), np.ascontiguousarray(dt[order]))
-        for mode, mname in ((0, "ww"), (2, "ifif")):
+        for mode, mname in ((0, "ww"),):
             out = np.zeros(4, np.float64)
             L.sim_run(h, n, a.ctypes.data, b.ctypes.data, 1 if anyhit else 0, mode, out.ctypes.data)
             cost = (C_NODE * out[0] + C_TRI * out[1]) / n * 32 / 32

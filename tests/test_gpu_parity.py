@@ -445,3 +445,23 @@ def test_device_lbvh_builder(tmp_path, built):
     fb, db = b.closest_hit(st["o_med"], st["d_t1"])
     assert np.array_equal(fa, fb) and np.array_equal(da, db)
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_binned_ray_order_is_transparent(tmp_path, built, mode, monkeypatch):
+    """The binned visiting order of surviving paths and shadow rays (types.h: RaySort; on by default only when the BVH exceeds the
+    L2) changes no result: same event counts, same image up to float-atomic ordering, same traversal form or the other."""
+    from btrc_b200 import api, scenes
+
+    path = scenes.make_material_test(str(tmp_path), width=160, height=90, spp=8, rings=24, segments=32, tex_res=64, state_count=30000)
+    monkeypatch.setenv("BTRC_SORT_RAYS", "0")
+    a = api.Scene(path)
+    ca, _, _, sa = a.render()
+    monkeypatch.setenv("BTRC_SORT_RAYS", mode)
+    monkeypatch.setenv("BTRC_TRAVERSE", "ifif" if mode == "2" else "ww")
+    b = api.Scene(path)
+    cb, _, _, sb = b.render()
+    for k in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss", "n_splat"):
+        assert sa[k] == sb[k], k
+    assert np.allclose(ca, cb, rtol=1e-4, atol=1e-5)
+    a.close(); b.close()
