@@ -27,10 +27,9 @@ def report(tag, om, dt, anyhit):
     om = np.ascontiguousarray(om, np.float32); dt = np.ascontiguousarray(dt, np.float32)
     n = om.shape[0]
     row = []
-    for name, order in (("asis", None), ("m2+oct", np.argsort(morton_key(om, dt, 2), kind="stable")), ("m3+oct", np.argsort(morton_key(om, dt, 3), kind="stable")),
-                        ("m4+oct", np.argsort(morton_key(om, dt, 4), kind="stable")), ("m5+oct", np.argsort(morton_key(om, dt, 5), kind="stable"))):
+    for name, order in (("asis", None),):
         a, b = (om, dt) if order is None else (np.ascontiguousarray(om[order]), np.ascontiguousarray(dt[order]))
-        for mode, mname in ((0, "ww"),):
+        for mode, mname in ((0, "ww"), (3, "ww+refill<32"), (4, "ww+refill<24"), (5, "ww+refill<16")):
             out = np.zeros(4, np.float64)
             L.sim_run(h, n, a.ctypes.data, b.ctypes.data, 1 if anyhit else 0, mode, out.ctypes.data)
             cost = (C_NODE * out[0] + C_TRI * out[1]) / n * 32 / 32

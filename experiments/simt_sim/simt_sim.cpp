@@ -114,19 +114,33 @@ void sim_free(void *s) { delete static_cast<Sim *>(s); }
 void sim_run(void *sp, int n, const float *o_med, const float *d_t1, int any_hit, int mode, double *out) {
     const Sim &s = *static_cast<Sim *>(sp);
     double wn = 0, wt = 0, ln = 0, lt = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(+ : wn, wt, ln, lt)
-    for (int w = 0; w < (n + 31) / 32; ++w) {
+    const bool refill = mode >= 3;       // 3: ww + refill (threshold in mode - 3 ... see below)
+    const int thresh = refill ? (mode == 3 ? 32 : (mode == 4 ? 24 : 16)) : 0;   // refill when fewer than `thresh` lanes are busy
+    if (refill) mode = 0;
+    const int per_warp = refill ? 32 * 64 : 32;  // a persistent warp works through a chunk of rays
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : wn, wt, ln, lt)
+    for (int w = 0; w < (n + per_warp - 1) / per_warp; ++w) {
         Lane L[32];
-        int m = std::min(32, n - 32 * w);
+        int next = per_warp * w;
+        const int end = std::min(n, per_warp * (w + 1));
         for (int i = 0; i < 32; ++i) {
-            if (i < m) init(L[i], o_med + 4 * (size_t)(32 * w + i), d_t1 + 4 * (size_t)(32 * w + i), s.b.root_ref, any_hit != 0);
+            if (next < end) { init(L[i], o_med + 4 * (size_t)next, d_t1 + 4 * (size_t)next, s.b.root_ref, any_hit != 0); ++next; }
             else { L[i].done = true; L[i].cur = SENT; L[i].leaf_left = L[i].post_left = 0; }
         }
         auto alive = [&](const Lane &l) { return !l.done && (l.cur != SENT || l.leaf_left > 0 || l.post_left > 0); };
         for (;;) {
             bool any = false;
             for (int i = 0; i < 32; ++i) any |= alive(L[i]);
-            if (!any) break;
+            if (!any && next >= end) break;
+            if (refill && next < end) {
+                int busy = 0;
+                for (int i = 0; i < 32; ++i) busy += alive(L[i]) ? 1 : 0;
+                if (busy < thresh) {
+                    for (int i = 0; i < 32 && next < end; ++i)
+                        if (!alive(L[i])) { init(L[i], o_med + 4 * (size_t)next, d_t1 + 4 * (size_t)next, s.b.root_ref, any_hit != 0); ++next; }
+                    wt += 0.5;  // the refill itself: ballot, cursor, two 16-byte loads, set-up (counted as half a triangle step)
+                }
+            }
             if (mode == 0 || mode == 1) {
                 // ---- descend phase
                 for (;;) {
