@@ -198,6 +198,7 @@ def run_reference(args):
     from oracle import front
 
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    front.lib().orc_use_all_cores()  # torchrun exports OMP_NUM_THREADS=1 to every rank
     w = WORKLOADS[args.workload]
     with tempfile.TemporaryDirectory() as d:
         path = make_scene(args.workload, d)
@@ -422,6 +423,7 @@ def run_ours(args):
 
     cpu = None
     if not args.no_cpu_baseline:
+        front.lib().orc_use_all_cores()
         o = front.OracleScene(make_scene(args.workload, os.path.join(tmp.name, "cpu")))
         t0 = time.perf_counter()
         o.render(0, 1)  # calibration pass: 1 spp

@@ -1957,6 +1957,13 @@ void orc_intersection_offset(int n, const float *pos, const float *nor, const fl
         out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
     }
 }
+// all host cores regardless of OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1 to its ranks: the CPU arm of bench.py must not inherit it)
+void orc_use_all_cores() {
+#ifdef _OPENMP
+    omp_set_num_threads(omp_get_num_procs());
+#endif
+}
+
 int orc_num_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();
