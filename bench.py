@@ -447,7 +447,7 @@ def run_ours(args):
                              "roofline_stages from a separate pass of %d identical steps with one CUDA event between kernels (%.1f ms/step)" % (prof_steps, prof_ms / prof_steps),
                    "wall_ms_per_step_incl_flush": wall / args.steps * 1e3},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": 176, "d2h_bytes_per_step": int(npix * 16 + 176 * (n_iter / args.steps / world)),
+        "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": 208, "d2h_bytes_per_step": int(npix * 16 + 208 * (n_iter / args.steps / world)),
                 "note": "api.Scene.render() into pinned host memory: film clear, waves, resolve, D2H of the W*H float4 image; the scene (BVH, tables) stays resident like model weights; H2D per step is the wave control block"},
         "gpu_launches": int(n_launch + args.steps * (3 + 1)),
         "events": {"n_gen": n_gen, "n_closest": n_closest, "n_hit": n_hit, "n_next": n_next, "n_shadow": n_shadow, "n_shadow_miss": n_shadow_miss,

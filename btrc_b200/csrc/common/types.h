@@ -271,6 +271,7 @@ struct WaveCtl {
     int trace_cursor;   // dynamic work cursors for the persistent traversal kernels
     int shadow_cursor;
     int class_count[8]; // entries of each shade class list this iteration (kNumShadeClasses <= 8)
+    int class_cursor[8]; // dynamic work cursors of the shade kernels (one 32-entry batch per grab)
     long long gen_base;   // first camera-path index generated this iteration
     long long cursor;     // next camera-path index
     long long end;        // one past the last camera-path index of this render

@@ -73,7 +73,7 @@ __global__ void prepare_kernel(WaveCtl *ctl) {
     ctl->n_shadow = 0;
     ctl->trace_cursor = 0;
     ctl->shadow_cursor = 0;
-    for (int c = 0; c < 8; ++c) ctl->class_count[c] = 0;
+    for (int c = 0; c < 8; ++c) { ctl->class_count[c] = 0; ctl->class_cursor[c] = 0; }
     ctl->n_gen += (unsigned long long)n_new;
     ctl->n_closest += (unsigned long long)(survivors + n_new);
     ctl->n_iter += (survivors + n_new) > 0 ? 1 : 0;
@@ -482,8 +482,21 @@ __global__ void __launch_bounds__(shade_block<MAT>(), shade_is_heavy<MAT>() ? BT
 shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQueue nq, ShadowQueue sq, FilmDevice film, WaveCtl *ctl) {
     const int n = ctl->class_count[1 + MAT];
     const uint32_t *list = hq.class_list + (size_t)(1 + MAT) * hq.class_stride;
-    const int n_round = (n + 31) & ~31;  // whole warps take part in the aggregated allocations
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
+    // Whole warps take part in the aggregated allocations.  The Disney kernel hands out batches of 32 list entries dynamically: its
+    // states differ a lot in cost (a path ended by roulette against a full evaluation) and a fixed grid-stride split leaves a tail
+    // (C2 -2.1 %); the light kernels keep the static split (dynamic: C4 +4 %, the atomic per batch shows).  profiles/r1k_ab_shade_fetch.log
+    constexpr bool kDynamic = MAT == MAT_DISNEY;
+    const int n_round = (n + 31) & ~31;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x;; j += gridDim.x * blockDim.x) {
+        if (kDynamic) {
+            int base = 0;
+            if (lane_id() == 0) base = atomicAdd(&ctl->class_cursor[1 + MAT], 32);
+            base = __shfl_sync(kFull, base, 0);
+            if (base >= n) break;
+            j = base + lane_id();
+        } else if (j >= n_round) {
+            break;
+        }
         bool emit_next = false, emit_shadow = false, splat = false;
         f3 splat_value(0.0f);
         uint32_t pixel = 0;
