@@ -5,6 +5,7 @@
 // (src/builtin/btrc/builtin/renderer/wavefront/soa.h:8-37) is kept field for field, except that the
 // pixel coordinate (uint2 there) rides in the spare .w lane of the radiance vector.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -264,9 +265,10 @@ struct FilmDevice {
 struct WaveCtl {
     int n_active;       // states processed by trace/shade this iteration
     int n_survivors;    // states carried over from the previous iteration (slots [0, n_survivors))
+    // the two output counters share one aligned 64-bit word: a warp reserves its slots in both queues with ONE atomic
+    int n_next;         // shade's output counter (reference: StateCounters::active_state_counter)         -- low half
+    int n_shadow;       // shade's shadow-ray counter (reference: StateCounters::shadow_ray_counter)       -- high half
     int n_new;          // camera paths generated this iteration (slots [n_survivors, n_active))
-    int n_next;         // shade's output counter (reference: StateCounters::active_state_counter)
-    int n_shadow;       // shade's shadow-ray counter (reference: StateCounters::shadow_ray_counter)
     int n_shadow_cur;   // shadow rays to trace this iteration
     int trace_cursor;   // dynamic work cursors for the persistent traversal kernels
     int shadow_cursor;
@@ -283,5 +285,8 @@ struct WaveCtl {
     // statistics (SURVEY 8d event counts)
     unsigned long long n_gen, n_closest, n_hit, n_next_total, n_shadow_total, n_shadow_miss, n_splat, n_iter;
 };
+
+static_assert(offsetof(WaveCtl, n_next) % 8 == 0 && offsetof(WaveCtl, n_shadow) == offsetof(WaveCtl, n_next) + 4,
+              "n_next | n_shadow must form one aligned 64-bit word (emit_outputs reserves both with one atomic)");
 
 }  // namespace btrc

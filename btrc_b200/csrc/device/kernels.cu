@@ -330,7 +330,14 @@ struct ShadowOut {
 
 __device__ __forceinline__ void emit_outputs(PathQueue &nq, ShadowQueue &sq, FilmDevice &film, WaveCtl *ctl, uint32_t pixel, bool emit_next,
                                              const NextState &ns, bool emit_shadow, const ShadowOut &so, bool splat, f3 splat_value) {
-    const int next_slot = warp_alloc(&ctl->n_next, emit_next);
+    // one 64-bit atomic per warp reserves the slots of both queues (n_next | n_shadow << 32 share an aligned word in WaveCtl)
+    const unsigned m_next = __ballot_sync(kFull, emit_next), m_shadow = __ballot_sync(kFull, emit_shadow);
+    unsigned long long both = 0;
+    if ((m_next | m_shadow) && lane_id() == 0)
+        both = atomicAdd(reinterpret_cast<unsigned long long *>(&ctl->n_next), (unsigned long long)__popc(m_next) | ((unsigned long long)__popc(m_shadow) << 32));
+    both = __shfl_sync(kFull, both, 0);
+    const unsigned below = (1u << lane_id()) - 1u;
+    const int next_slot = int(both & 0xffffffffull) + __popc(m_next & below);
     if (emit_next) {
         nq.ray_o[next_slot] = make4(ns.o, __uint_as_float(ns.med));
         nq.ray_d[next_slot] = make4(ns.d, kMaxFloat);
@@ -339,7 +346,7 @@ __device__ __forceinline__ void emit_outputs(PathQueue &nq, ShadowQueue &sq, Fil
         nq.rng[next_slot] = ns.rng;
         nq.ble[next_slot] = make4(ns.ble, ns.pdf);
     }
-    const int shadow_slot = warp_alloc(&ctl->n_shadow, emit_shadow);
+    const int shadow_slot = int(both >> 32) + __popc(m_shadow & below);
     if (emit_shadow) {
         sq.ray_o[shadow_slot] = make4(so.o, __uint_as_float(so.med));
         sq.ray_d[shadow_slot] = make4(so.d, so.t1);
