@@ -328,7 +328,7 @@ struct ShadowOut {
     uint32_t med;
 };
 
-__device__ __forceinline__ void emit_outputs(PathQueue &nq, ShadowQueue &sq, FilmDevice &film, WaveCtl *ctl, uint32_t pixel, bool emit_next,
+__device__ __forceinline__ void emit_outputs(PathQueue &nq, ShadowQueue &sq, FilmDevice &film, WaveCtl *ctl, unsigned long long &n_splat, uint32_t pixel, bool emit_next,
                                              const NextState &ns, bool emit_shadow, const ShadowOut &so, bool splat, f3 splat_value) {
     // one 64-bit atomic per warp reserves the slots of both queues (n_next | n_shadow << 32 share an aligned word in WaveCtl)
     const unsigned m_next = __ballot_sync(kFull, emit_next), m_shadow = __ballot_sync(kFull, emit_shadow);
@@ -352,8 +352,12 @@ __device__ __forceinline__ void emit_outputs(PathQueue &nq, ShadowQueue &sq, Fil
         sq.ray_d[shadow_slot] = make4(so.d, so.t1);
         sq.beta_li[shadow_slot] = make4(so.beta, __uint_as_float(pixel));
     }
-    if (splat) film_splat3(film.radiance, pixel, splat_value);
-    warp_count(&ctl->n_splat, splat);
+    if (splat) { film_splat3(film.radiance, pixel, splat_value); n_splat += 1; }  // the statistic is summed per thread, one atomic per warp at kernel end
+}
+
+__device__ __forceinline__ void flush_splat_count(WaveCtl *ctl, unsigned long long n_splat) {
+    for (int off = 16; off; off >>= 1) n_splat += __shfl_down_sync(kFull, n_splat, off);
+    if (lane_id() == 0 && n_splat) atomicAdd(&ctl->n_splat, n_splat);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -364,6 +368,7 @@ __global__ void __launch_bounds__(kBlock) medium_kernel(SceneDevice scene, Rende
                                                        FilmDevice film, WaveCtl *ctl) {
     const int n = ctl->n_active;
     const int n_round = (n + 31) & ~31;
+    unsigned long long n_splat = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         bool emit_next = false, emit_shadow = false, splat = false;
         f3 splat_value(0.0f);
@@ -447,8 +452,9 @@ __global__ void __launch_bounds__(kBlock) medium_kernel(SceneDevice scene, Rende
                 }
             }
         }
-        emit_outputs(nq, sq, film, ctl, pixel, emit_next, ns, emit_shadow, so, splat, splat_value);
+        emit_outputs(nq, sq, film, ctl, n_splat, pixel, emit_next, ns, emit_shadow, so, splat, splat_value);
     }
+    flush_splat_count(ctl, n_splat);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -494,6 +500,7 @@ shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQu
     // (C2 -2.1 %); the light kernels keep the static split (dynamic: C4 +4 %, the atomic per batch shows).  profiles/r1k_ab_shade_fetch.log
     constexpr bool kDynamic = MAT == MAT_DISNEY;
     const int n_round = (n + 31) & ~31;
+    unsigned long long n_splat = 0;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x;; j += gridDim.x * blockDim.x) {
         if (kDynamic) {
             int base = 0;
@@ -606,8 +613,9 @@ shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQu
                 }
             }
         }
-        emit_outputs(nq, sq, film, ctl, pixel, emit_next, ns, emit_shadow, so, splat, splat_value);
+        emit_outputs(nq, sq, film, ctl, n_splat, pixel, emit_next, ns, emit_shadow, so, splat, splat_value);
     }
+    flush_splat_count(ctl, n_splat);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
