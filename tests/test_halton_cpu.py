@@ -101,3 +101,15 @@ def test_unknown_sampler_is_an_error(built, tmp_path):
 
     with pytest.raises(api.BtrcError, match="unknown sampler type: sobol"):
         api.Scene(_halton_scene(tmp_path, 8, 8, 1, "sobol"))
+
+
+def test_halton_known_answer_vectors(built):
+    """Frozen vectors (tests/golden/halton_kat.json, written by tests/golden/make_golden_halton.py)."""
+    from oracle import front
+
+    L = front.lib()
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "halton_kat.json")))
+    assert [L.orc_prime(i) for i in (0, 1, 2, 10, 100, 500, 999)] == kat["primes_tail"]
+    for e in kat["radical_inverse"]:
+        v = f32(L.orc_owen_scrambled_radical_inverse(e["base_index"], int(e["a"]), int(e["hash"])))
+        assert int(np.array([v], f32).view(np.uint32)[0]) == e["bits"], e
