@@ -86,3 +86,22 @@ def test_sheared_box_and_scatter_rate(built, tmp_path):
     assert tot > 300
     p = scat / tot
     assert abs(p - (1 - np.exp(-1.5 * 1.0))) < 0.08
+
+
+def test_volume_known_answer_vectors(built, tmp_path):
+    """Frozen transmittances (tests/golden/volumes_kat.json, written by tests/golden/make_golden_volumes.py)."""
+    import importlib.util
+
+    from oracle import front
+    from tests.util import ROOT
+
+    spec = importlib.util.spec_from_file_location("make_golden_volumes", os.path.join(ROOT, "tests", "golden", "make_golden_volumes.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "volumes_kat.json")))
+    o = front.OracleScene(mg.scene(str(tmp_path)))
+    o_med = np.array(kat["o_med_bits"], np.uint32).view(f32)
+    d_t1 = np.array(kat["d_t1_bits"], np.uint32).view(f32)
+    tr = o.shadow_tr(o_med, d_t1)
+    assert tr.view(np.uint32).tolist() == kat["tr_bits"]
+    assert tr.min() >= 0.0 and tr.max() <= 1.0 and len(np.unique(tr)) > 4  # constant boxes give 0 / 1 (density == majorant), the grid box fractions
