@@ -82,6 +82,7 @@ def lib():
         L.btrc_instance_transform.argtypes = [c_void_p, c_int32, c_void_p, c_void_p]
         L.btrc_ibl_table.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]
         L.btrc_set_reporter.argtypes = [c_void_p, PROGRESS_FN, c_void_p]
+        L.btrc_image_load.argtypes = [c_char_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_void_p, c_uint64]
         L.btrc_device_sm_count.restype = c_int
         _lib = L
     return _lib
@@ -281,6 +282,16 @@ class Scene:
         inv = np.zeros((3, 4), np.float32)
         _check(self.L.btrc_instance_transform(self.h, instance_id, _p(mat), _p(inv)))
         return mat, inv
+
+
+def load_image(path):
+    """ImageDynamic::load: (H, W, C) uint8 for .png / .jpg, (H, W, 3) float32 for .hdr."""
+    L = lib()
+    w, h, c, isf = c_int32(0), c_int32(0), c_int32(0), c_int32(0)
+    _check(L.btrc_image_load(path.encode(), byref(w), byref(h), byref(c), byref(isf), None, 0))
+    out = np.zeros((h.value, w.value, c.value), np.float32 if isf.value else np.uint8)
+    _check(L.btrc_image_load(path.encode(), byref(w), byref(h), byref(c), byref(isf), out.ctypes.data, out.nbytes))
+    return out
 
 
 def render_file(path, **kw):

@@ -271,6 +271,21 @@ int btrc_film_import(btrc_scene_t *s, int memory, const float *radiance, const f
     });
 }
 
+int btrc_image_load(const char *path, int32_t *width, int32_t *height, int32_t *channels, int32_t *is_float, void *out, uint64_t out_bytes) {
+    return guarded([&] {
+        if (!path) throw Error("null path");
+        const LoadedImage img = load_image(path);
+        if (width) *width = img.width;
+        if (height) *height = img.height;
+        if (channels) *channels = img.is_float ? 3 : img.channels;
+        if (is_float) *is_float = img.is_float ? 1 : 0;
+        if (!out) return;
+        const size_t need = img.is_float ? img.f32.size() * sizeof(float) : img.u8.size();
+        if (out_bytes < need) throw Error("btrc_image_load: buffer too small");
+        std::memcpy(out, img.is_float ? (const void *)img.f32.data() : (const void *)img.u8.data(), need);
+    });
+}
+
 int btrc_run_post_processors(btrc_scene_t *s, int memory, float *color, float *albedo, float *normal) {
     (void)memory;
     return guarded([&] {

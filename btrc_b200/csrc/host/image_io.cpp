@@ -409,11 +409,243 @@ static LoadedImage load_hdr(const std::string &filename) {
     return img;
 }
 
+// Baseline / extended-sequential Huffman JPEG (ITU T.81: SOF0, SOF1 with 8-bit samples), 1 or 3 components, any 1x/2x sampling
+// factors, restart intervals.  The reference reads .jpg textures through stb_image (utils/image.cpp:135-143); progressive and
+// arithmetic-coded files are reported as unsupported.  Chroma is upsampled with libjpeg's triangle filter, the IDCT is separable floating point:
+// decoded values agree with libjpeg to 1-3 eight-bit levels (tests/test_postprocess_cpu.py).
+static LoadedImage load_jpg(const std::string &filename) {
+    std::ifstream f(filename, std::ios::binary);
+    if (!f) throw Error("failed to open file: " + filename);
+    const std::vector<uint8_t> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    auto fail = [&](const std::string &why) -> Error { return Error("failed to load image: " + filename + " (" + why + ")"); };
+    if (buf.size() < 4 || buf[0] != 0xff || buf[1] != 0xd8) throw fail("not a JPEG file");
+    static const uint8_t zz[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                                   35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    struct Huff {
+        uint8_t bits[17] = {0};
+        uint8_t vals[256] = {0};
+        int mincode[17], maxcode[18], valptr[17];
+        bool ok = false;
+        void build() {
+            int code = 0, k = 0;
+            for (int l = 1; l <= 16; ++l) {
+                valptr[l] = k; mincode[l] = code;
+                code += bits[l]; k += bits[l];
+                maxcode[l] = bits[l] ? code - 1 : -1;
+                code <<= 1;
+            }
+            maxcode[17] = 0x7fffffff;
+            ok = true;
+        }
+    };
+    struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0; int bw = 0, bh = 0; std::vector<uint8_t> px; };
+    uint16_t qt[4][64] = {{0}};
+    Huff hdc[4], hac[4];
+    std::vector<Comp> comps;
+    int width = 0, height = 0, restart = 0;
+    size_t p = 2;
+    auto u16 = [&](size_t at) { if (at + 1 >= buf.size()) throw fail("truncated"); return (int)buf[at] << 8 | buf[at + 1]; };
+    size_t scan_at = 0;
+    while (p + 4 <= buf.size()) {
+        if (buf[p] != 0xff) throw fail("marker expected");
+        const int m = buf[p + 1];
+        p += 2;
+        if (m == 0xd8 || (m >= 0xd0 && m <= 0xd7) || m == 0x01 || m == 0xff) { if (m == 0xff) --p; continue; }
+        if (m == 0xd9) break;
+        const int len = u16(p);
+        if (len < 2 || p + len > buf.size()) throw fail("bad segment length");
+        const size_t q = p + 2, end = p + len;
+        if (m == 0xdb) {
+            for (size_t a = q; a < end;) {
+                const int pq = buf[a] >> 4, id = buf[a] & 15;
+                ++a;
+                if (id > 3) throw fail("bad quantisation table");
+                for (int i = 0; i < 64; ++i) { qt[id][zz[i]] = pq ? (uint16_t)u16(a) : buf[a]; a += pq ? 2 : 1; }
+            }
+        } else if (m == 0xc0 || m == 0xc1) {
+            if (buf[q] != 8) throw fail("only 8-bit samples");
+            height = u16(q + 1); width = u16(q + 3);
+            const int nc = buf[q + 5];
+            if (nc != 1 && nc != 3) throw fail("unsupported component count " + std::to_string(nc));
+            comps.resize(nc);
+            for (int c = 0; c < nc; ++c) {
+                comps[c].id = buf[q + 6 + 3 * c];
+                comps[c].h = buf[q + 7 + 3 * c] >> 4; comps[c].v = buf[q + 7 + 3 * c] & 15;
+                comps[c].tq = buf[q + 8 + 3 * c];
+                if (comps[c].h < 1 || comps[c].h > 2 || comps[c].v < 1 || comps[c].v > 2 || comps[c].tq > 3) throw fail("unsupported sampling");
+            }
+        } else if (m == 0xc2 || (m >= 0xc3 && m <= 0xcf && m != 0xc4 && m != 0xc8 && m != 0xcc)) {
+            throw fail("progressive / lossless / arithmetic JPEG is not supported");
+        } else if (m == 0xc4) {
+            for (size_t a = q; a < end;) {
+                const int tc = buf[a] >> 4, id = buf[a] & 15;
+                ++a;
+                if (id > 3 || tc > 1) throw fail("bad Huffman table");
+                Huff &h = tc ? hac[id] : hdc[id];
+                int n = 0;
+                for (int l = 1; l <= 16; ++l) { h.bits[l] = buf[a + l - 1]; n += h.bits[l]; }
+                a += 16;
+                if (n > 256 || a + n > end) throw fail("bad Huffman table");
+                for (int i = 0; i < n; ++i) h.vals[i] = buf[a + i];
+                a += n;
+                h.build();
+            }
+        } else if (m == 0xdd) {
+            restart = u16(q);
+        } else if (m == 0xda) {
+            const int ns = buf[q];
+            if (ns != (int)comps.size()) throw fail("non-interleaved scans are not supported");
+            for (int i = 0; i < ns; ++i) {
+                const int cid = buf[q + 1 + 2 * i], t = buf[q + 2 + 2 * i];
+                for (auto &c : comps) if (c.id == cid) { c.td = t >> 4; c.ta = t & 15; }
+            }
+            scan_at = end;
+            break;
+        }
+        p = end;
+    }
+    if (!scan_at || comps.empty() || width <= 0 || height <= 0) throw fail("no image data");
+    int hmax = 1, vmax = 1;
+    for (auto &c : comps) { hmax = std::max(hmax, c.h); vmax = std::max(vmax, c.v); }
+    const int mcux = (width + 8 * hmax - 1) / (8 * hmax), mcuy = (height + 8 * vmax - 1) / (8 * vmax);
+    for (auto &c : comps) {
+        if (!hdc[c.td].ok || !hac[c.ta].ok) throw fail("missing Huffman table");
+        c.bw = mcux * c.h * 8; c.bh = mcuy * c.v * 8;
+        c.px.assign((size_t)c.bw * c.bh, 0);
+    }
+    // entropy-coded data
+    size_t bp = scan_at;
+    uint32_t acc = 0;
+    int nb = 0;
+    auto fill = [&]() {
+        while (nb <= 24) {
+            int b = 0;
+            if (bp < buf.size()) {
+                b = buf[bp];
+                if (b == 0xff) {
+                    const int n2 = bp + 1 < buf.size() ? buf[bp + 1] : 0xd9;
+                    if (n2 == 0) bp += 2;
+                    else b = 0;  // a marker: feed zeros, do not advance
+                } else ++bp;
+            }
+            acc |= (uint32_t)b << (24 - nb);
+            nb += 8;
+        }
+    };
+    auto getbits = [&](int n) -> int {
+        if (n == 0) return 0;
+        fill();
+        const int v = (int)(acc >> (32 - n));
+        acc <<= n; nb -= n;
+        return v;
+    };
+    auto decode = [&](const Huff &h) -> int {
+        fill();
+        int code = 0;
+        for (int l = 1; l <= 16; ++l) {
+            code = (code << 1) | (int)(acc >> 31);
+            acc <<= 1; --nb;
+            if (h.maxcode[l] >= 0 && code <= h.maxcode[l] && code >= h.mincode[l]) return h.vals[h.valptr[l] + code - h.mincode[l]];
+        }
+        throw fail("bad Huffman code");
+    };
+    auto extend = [](int v, int t) { return t && v < (1 << (t - 1)) ? v - (1 << t) + 1 : v; };
+    float cs[8][8];
+    for (int x = 0; x < 8; ++x)
+        for (int u = 0; u < 8; ++u) cs[x][u] = std::cos((2 * x + 1) * u * 3.14159265358979f / 16.0f) * (u == 0 ? 0.353553391f : 0.5f);
+    int mcu_count = 0;
+    for (int my = 0; my < mcuy; ++my)
+        for (int mx = 0; mx < mcux; ++mx) {
+            if (restart && mcu_count && mcu_count % restart == 0) {  // RSTn: byte align, skip the marker, reset the predictors
+                acc = 0; nb = 0;
+                while (bp + 1 < buf.size() && !(buf[bp] == 0xff && buf[bp + 1] >= 0xd0 && buf[bp + 1] <= 0xd7)) ++bp;
+                bp += 2;
+                for (auto &c : comps) c.pred = 0;
+            }
+            ++mcu_count;
+            for (auto &c : comps)
+                for (int by = 0; by < c.v; ++by)
+                    for (int bx = 0; bx < c.h; ++bx) {
+                        float blk[64] = {0};
+                        const int t = decode(hdc[c.td]);
+                        c.pred += extend(getbits(t), t);
+                        blk[0] = (float)c.pred * qt[c.tq][0];
+                        for (int k = 1; k < 64;) {
+                            const int rs = decode(hac[c.ta]), r = rs >> 4, sz = rs & 15;
+                            if (sz == 0) { if (r != 15) break; k += 16; continue; }
+                            k += r;
+                            if (k > 63) throw fail("bad coefficient index");
+                            blk[zz[k]] = (float)extend(getbits(sz), sz) * qt[c.tq][zz[k]];
+                            ++k;
+                        }
+                        float tmp[64];
+                        for (int v = 0; v < 8; ++v)
+                            for (int x = 0; x < 8; ++x) {
+                                float a = 0;
+                                for (int u = 0; u < 8; ++u) a += blk[8 * v + u] * cs[x][u];
+                                tmp[8 * v + x] = a;
+                            }
+                        const int ox = (mx * c.h + bx) * 8, oy = (my * c.v + by) * 8;
+                        for (int y = 0; y < 8; ++y)
+                            for (int x = 0; x < 8; ++x) {
+                                float a = 0;
+                                for (int v = 0; v < 8; ++v) a += tmp[8 * v + x] * cs[y][v];
+                                c.px[(size_t)(oy + y) * c.bw + ox + x] = (uint8_t)std::min(std::max((int)std::lround(a + 128.0f), 0), 255);
+                            }
+                    }
+        }
+    // chroma upsampling: the triangle filter of libjpeg / stb_image ("fancy upsampling") for 2x factors, replication otherwise
+    const int fw = mcux * hmax * 8, fh = mcuy * vmax * 8;
+    for (auto &c : comps) {
+        const int sx = hmax / c.h, sy = vmax / c.v;
+        if (sx == 1 && sy == 1) continue;
+        std::vector<uint8_t> full((size_t)fw * fh);
+        const int cw = c.bw, chh = c.bh;
+        auto in = [&](int x, int y) { return (int)c.px[(size_t)std::min(std::max(y, 0), chh - 1) * cw + std::min(std::max(x, 0), cw - 1)]; };
+        for (int y = 0; y < fh; ++y)
+            for (int x = 0; x < fw; ++x) {
+                int v;
+                if (sx == 2 && sy == 2) {       // h2v2: 9/3/3/1 sixteenths, rounding 8 / 7 on even / odd columns
+                    const int r = y >> 1, rf = (y & 1) ? r + 1 : r - 1, i = x >> 1, jf = (x & 1) ? i + 1 : i - 1;
+                    const int cs = 3 * in(i, r) + in(i, rf), cf = 3 * in(jf, r) + in(jf, rf);
+                    const bool edge = jf < 0 || jf >= cw;
+                    v = edge ? (4 * cs + ((x & 1) ? 7 : 8)) >> 4 : (3 * cs + cf + ((x & 1) ? 7 : 8)) >> 4;
+                } else if (sx == 2 && sy == 1) {  // h2v1: 3/1 quarters, rounding 1 / 2
+                    const int i = x >> 1, jf = (x & 1) ? i + 1 : i - 1;
+                    v = (jf < 0 || jf >= cw) ? in(i, y) : (3 * in(i, y) + in(jf, y) + ((x & 1) ? 2 : 1)) >> 2;
+                } else if (sx == 1 && sy == 2) {  // h1v2
+                    const int r = y >> 1, rf = (y & 1) ? r + 1 : r - 1;
+                    v = (3 * in(x, r) + in(x, rf) + ((y & 1) ? 2 : 1)) >> 2;
+                } else {
+                    v = in(x / sx, y / sy);
+                }
+                full[(size_t)y * fw + x] = (uint8_t)v;
+            }
+        c.px.swap(full);
+        c.bw = fw; c.bh = fh; c.h = hmax; c.v = vmax;
+    }
+    LoadedImage img;
+    img.width = width; img.height = height;
+    img.channels = comps.size() == 1 ? 1 : 3;
+    img.u8.resize((size_t)width * height * img.channels);
+    for (int y = 0; y < height; ++y)
+        for (int x = 0; x < width; ++x) {
+            auto at = [&](const Comp &c) { return (float)c.px[(size_t)(y * c.v / vmax) * c.bw + x * c.h / hmax]; };
+            uint8_t *o = &img.u8[((size_t)y * width + x) * img.channels];
+            if (img.channels == 1) { o[0] = (uint8_t)at(comps[0]); continue; }
+            const float Y = at(comps[0]), cb = at(comps[1]) - 128.0f, cr = at(comps[2]) - 128.0f;
+            const float rgb[3] = {Y + 1.402f * cr, Y - 0.344136f * cb - 0.714136f * cr, Y + 1.772f * cb};
+            for (int k = 0; k < 3; ++k) o[k] = (uint8_t)std::min(std::max((int)std::lround(rgb[k]), 0), 255);
+        }
+    return img;
+}
+
 LoadedImage load_image(const std::string &filename) {
     const std::string ext = lower_ext(filename);
     if (ext == "png") return load_png(filename);
     if (ext == "hdr") return load_hdr(filename);
-    throw Error("unsupported image format (use .png or .hdr): " + filename);
+    if (ext == "jpg" || ext == "jpeg") return load_jpg(filename);
+    throw Error("unsupported image format (use .png, .jpg or .hdr): " + filename);
 }
 
 }  // namespace btrc

@@ -104,6 +104,11 @@ int btrc_resolve(btrc_scene_t *scene, int memory, float *color, float *albedo, f
  * format by extension -- postprocess/save_to_image.cpp:30-62; "tonemap": ACES * exposure -- tonemap.cpp:14-51). */
 int btrc_run_post_processors(btrc_scene_t *scene, int memory, float *color, float *albedo, float *normal);
 
+/* ImageDynamic::load (utils/image.cpp:116-215; formats by extension: .png .jpg/.jpeg .hdr): the decoder the texture creators use.
+ * First call with out = NULL to get the size, then with a buffer of width*height*channels bytes (8-bit formats) or
+ * width*height*3 floats (.hdr, *is_float = 1).  Host memory, no device involved. */
+int btrc_image_load(const char *path, int32_t *width, int32_t *height, int32_t *channels, int32_t *is_float, void *out, uint64_t out_bytes);
+
 /* ---- stage-level entry points on explicit batches, in the reference's SoA layout (wavefront/soa.h:8-37) ----
  * ray: o_med = float4(o.xyz, bit-cast medium id), d_t1 = float4(d.xyz, t1).
  * hit: flag = instance id | bit30 on hit (common.h:12-14); detail = uint4(t bits, primitive id, u bits, v bits).

@@ -106,3 +106,56 @@ def test_unknown_format_is_an_error(built, tmp_path):
     with pytest.raises(api.BtrcError, match="unknown image format"):
         s.run_post_processors(np.zeros((8, 8, 4), f32))
     s.close()
+
+
+def test_jpeg_decoder_against_libjpeg(built, tmp_path):
+    """ImageDynamic::load for .jpg (the reference goes through stb_image): baseline files with 4:4:4 / 4:2:2 / 4:2:0 chroma, grayscale
+    and restart intervals decode to within 3 eight-bit levels of libjpeg (PIL); progressive files are refused with a clear error."""
+    from btrc_b200 import api
+
+    rng = np.random.default_rng(3)
+    yy, xx = np.mgrid[0:67, 0:101]
+    img = np.stack([127 + 100 * np.sin(xx / 9.0) * np.cos(yy / 7.0), 30 + xx * 2.0, 200 - yy * 2.5], -1) + rng.normal(0, 6, (67, 101, 3))
+    img = np.clip(img, 0, 255).astype(np.uint8)
+    cases = {"q90_420.jpg": dict(quality=90), "q75_444.jpg": dict(quality=75, subsampling=0), "q95_422.jpg": dict(quality=95, subsampling=1),
+             "gray.jpg": dict(quality=85), "rst.jpg": dict(quality=80, restart_marker_blocks=5)}
+    for name, kw in cases.items():
+        p = str(tmp_path / name)
+        Image.fromarray(img[..., 0] if name == "gray.jpg" else img).save(p, **kw)
+        ref = np.asarray(Image.open(p))
+        ref = ref if ref.ndim == 3 else ref[..., None]
+        got = api.load_image(p)
+        assert got.shape == ref.shape and got.dtype == np.uint8, name
+        err = np.abs(got.astype(int) - ref.astype(int))
+        assert err.max() <= 3 and err.mean() < 0.1, (name, err.max(), err.mean())
+    p = str(tmp_path / "progressive.jpg")
+    Image.fromarray(img).save(p, progressive=True)
+    with pytest.raises(api.BtrcError, match="progressive"):
+        api.load_image(p)
+    # the product's own writer -> its own reader (and PIL's): what `save` writes can be used as a texture
+    from btrc_b200 import scenes
+    path = scenes.make_cornell(str(tmp_path), width=101, height=67, spp=1, state_count=64)
+    root = json.load(open(path))
+    root["post_processors"] = [{"type": "save", "color": "$env{scene_directory}/own.jpg"}]
+    json.dump(root, open(path, "w"))
+    s = api.Scene(path)
+    color = np.concatenate([img.astype(f32) / f32(256) + f32(0.5 / 256), np.ones((67, 101, 1), f32)], -1)
+    s.run_post_processors(np.ascontiguousarray(color))
+    own = api.load_image(str(tmp_path / "own.jpg"))
+    pil = np.asarray(Image.open(tmp_path / "own.jpg"))
+    assert np.abs(own.astype(int) - pil.astype(int)).max() <= 3
+    assert np.abs(own.astype(int) - img.astype(int)).mean() < 6.0   # quality-90 quantisation of an image with sigma-6 noise
+    s.close()
+
+
+def test_png_and_hdr_load(built, tmp_path):
+    from btrc_b200 import api
+
+    rng = np.random.default_rng(4)
+    rgba = rng.integers(0, 256, (13, 17, 4), dtype=np.uint8)
+    Image.fromarray(rgba, "RGBA").save(tmp_path / "a.png")
+    assert np.array_equal(api.load_image(str(tmp_path / "a.png")), rgba)
+    Image.fromarray(rgba[..., 0], "L").save(tmp_path / "g.png")
+    assert np.array_equal(api.load_image(str(tmp_path / "g.png"))[..., 0], rgba[..., 0])
+    with pytest.raises(api.BtrcError, match="unsupported image format"):
+        api.load_image(str(tmp_path / "x.exr"))
