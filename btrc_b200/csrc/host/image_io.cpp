@@ -259,63 +259,126 @@ int paeth(int a, int b, int c) {
     return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
 }
 
+// PNG reader for ImageDynamic::load (utils/image.cpp:116-147 reads through stb_image's 8-bit interface).  Covers what that
+// interface covers: colour types 0/2/3/4/6, bit depths 1/2/4/8/16, Adam7 interlacing, tRNS.  Conventions follow stb_image:
+// 16-bit samples are reduced to their high byte, 1/2/4-bit grey is scaled to 0..255 (x 255 / (2^depth - 1)), a palette image
+// becomes RGB (RGBA when it has a tRNS chunk), a colour-keyed grey / RGB image gains an alpha channel (0 for the key, 255 otherwise).
 LoadedImage load_png(const std::string &filename) {
     std::ifstream f(filename, std::ios::binary);
     if (!f) throw Error("failed to open file: " + filename);
     std::vector<uint8_t> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    const Error bad("failed to load image: " + filename);
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
-    if (buf.size() < 8 || std::memcmp(buf.data(), sig, 8) != 0) throw Error("failed to load image: " + filename);
+    if (buf.size() < 8 || std::memcmp(buf.data(), sig, 8) != 0) throw bad;
     size_t p = 8;
     int w = 0, h = 0, depth = 0, ctype = 0, interlace = 0;
-    std::vector<uint8_t> idat, plte;
+    std::vector<uint8_t> idat, plte, trns;
     while (p + 8 <= buf.size()) {
         const uint32_t len = get_u32(&buf[p]);
         const std::string type(reinterpret_cast<const char *>(&buf[p + 4]), 4);
         const uint8_t *d = &buf[p + 8];
-        if (p + 12 + len > buf.size()) throw Error("failed to load image: " + filename);
-        if (type == "IHDR") { w = (int)get_u32(d); h = (int)get_u32(d + 4); depth = d[8]; ctype = d[9]; interlace = d[12]; }
+        if (p + 12 + (size_t)len > buf.size()) throw bad;
+        if (type == "IHDR") {
+            if (len < 13) throw bad;
+            w = (int)get_u32(d); h = (int)get_u32(d + 4); depth = d[8]; ctype = d[9]; interlace = d[12];
+        }
         else if (type == "PLTE") plte.assign(d, d + len);
+        else if (type == "tRNS") trns.assign(d, d + len);
         else if (type == "IDAT") idat.insert(idat.end(), d, d + len);
         else if (type == "IEND") break;
         p += 12 + len;
     }
-    if (interlace != 0 || depth != 8) throw Error("unsupported png (only 8-bit non-interlaced): " + filename);
-    int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
-    if (!ch) throw Error("failed to load image: " + filename);
-    const size_t stride = (size_t)w * ch;
-    std::vector<uint8_t> raw((stride + 1) * (size_t)h);
+    const int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+    const bool depth_ok = ctype == 0 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)
+                        : ctype == 3 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8) : (depth == 8 || depth == 16);
+    if (!ch || !depth_ok || w <= 0 || h <= 0 || interlace > 1 || (ctype == 3 && plte.empty())) throw bad;
+
+    // the passes of the image: one for a sequential file, seven for Adam7 (x0, y0, dx, dy)
+    struct Pass { int x0, y0, dx, dy; };
+    static const Pass adam7[7] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+    static const Pass whole = {0, 0, 1, 1};
+    const int npass = interlace ? 7 : 1;
+    const int bits = depth * ch;            // per pixel
+    const size_t fbpp = (size_t)std::max(1, bits / 8);  // filter distance in bytes
+    auto pass_dim = [&](const Pass &ps, int &pw, int &ph) { pw = (w - ps.x0 + ps.dx - 1) / ps.dx; ph = (h - ps.y0 + ps.dy - 1) / ps.dy; };
+    size_t total = 0;
+    for (int i = 0; i < npass; ++i) {
+        int pw, ph;
+        pass_dim(interlace ? adam7[i] : whole, pw, ph);
+        if (pw > 0 && ph > 0) total += (((size_t)pw * bits + 7) / 8 + 1) * ph;
+    }
+    std::vector<uint8_t> raw(total);
     uLongf rawlen = (uLongf)raw.size();
-    if (uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size()) != Z_OK || rawlen != raw.size())
-        throw Error("failed to load image: " + filename);
-    std::vector<uint8_t> px(stride * (size_t)h);
-    for (int y = 0; y < h; ++y) {
-        const uint8_t ft = raw[(stride + 1) * y];
-        const uint8_t *src = &raw[(stride + 1) * y + 1];
-        uint8_t *dst = &px[stride * y];
-        const uint8_t *up = y ? &px[stride * (y - 1)] : nullptr;
-        for (size_t x = 0; x < stride; ++x) {
-            const int a = x >= (size_t)ch ? dst[x - ch] : 0, b = up ? up[x] : 0, c = (up && x >= (size_t)ch) ? up[x - ch] : 0;
-            int v = src[x];
-            switch (ft) {
-            case 1: v += a; break;
-            case 2: v += b; break;
-            case 3: v += (a + b) / 2; break;
-            case 4: v += paeth(a, b, c); break;
-            default: break;
+    if (uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size()) != Z_OK || rawlen != raw.size()) throw bad;
+
+    std::vector<uint16_t> smp((size_t)w * h * ch);  // raw sample values, unscaled
+    size_t at = 0;
+    std::vector<uint8_t> cur, prev;
+    for (int i = 0; i < npass; ++i) {
+        const Pass &ps = interlace ? adam7[i] : whole;
+        int pw, ph;
+        pass_dim(ps, pw, ph);
+        if (pw <= 0 || ph <= 0) continue;
+        const size_t rb = ((size_t)pw * bits + 7) / 8;
+        cur.assign(rb, 0); prev.assign(rb, 0);
+        for (int y = 0; y < ph; ++y) {
+            const uint8_t ft = raw[at];
+            const uint8_t *src = &raw[at + 1];
+            at += rb + 1;
+            if (ft > 4) throw bad;
+            for (size_t x = 0; x < rb; ++x) {
+                const int a = x >= fbpp ? cur[x - fbpp] : 0, b = prev[x], c = x >= fbpp ? prev[x - fbpp] : 0;
+                int v = src[x];
+                switch (ft) {
+                case 1: v += a; break;
+                case 2: v += b; break;
+                case 3: v += (a + b) / 2; break;
+                case 4: v += paeth(a, b, c); break;
+                default: break;
+                }
+                cur[x] = (uint8_t)v;
             }
-            dst[x] = (uint8_t)v;
+            const int oy = ps.y0 + y * ps.dy;
+            for (int x = 0; x < pw; ++x) {
+                uint16_t *o = &smp[((size_t)oy * w + ps.x0 + (size_t)x * ps.dx) * ch];
+                for (int k = 0; k < ch; ++k) {
+                    const size_t s = (size_t)x * ch + k;
+                    if (depth == 8) o[k] = cur[s];
+                    else if (depth == 16) o[k] = (uint16_t)(cur[2 * s] << 8 | cur[2 * s + 1]);
+                    else { const size_t bit = s * depth; o[k] = (cur[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1); }
+                }
+            }
+            cur.swap(prev);
         }
     }
+
     LoadedImage img;
     img.width = w; img.height = h;
-    if (ctype == 3) {  // palette -> rgb
-        img.channels = 3;
-        img.u8.resize((size_t)w * h * 3);
-        for (size_t i = 0; i < (size_t)w * h; ++i)
-            for (int k = 0; k < 3; ++k) img.u8[3 * i + k] = 3 * (size_t)px[i] + k < plte.size() ? plte[3 * px[i] + k] : 0;
-    } else {
-        img.channels = ch;
-        img.u8 = std::move(px);
+    const size_t npx = (size_t)w * h;
+    if (ctype == 3) {  // palette -> rgb(a)
+        img.channels = trns.empty() ? 3 : 4;
+        img.u8.resize(npx * img.channels);
+        for (size_t i = 0; i < npx; ++i) {
+            const size_t e = smp[i];
+            for (int k = 0; k < 3; ++k) img.u8[img.channels * i + k] = 3 * e + k < plte.size() ? plte[3 * e + k] : 0;
+            if (img.channels == 4) img.u8[4 * i + 3] = e < trns.size() ? trns[e] : 255;
+        }
+        return img;
+    }
+    const bool keyed = (ctype == 0 && trns.size() >= 2) || (ctype == 2 && trns.size() >= 6);
+    uint16_t key[3] = {0, 0, 0};
+    if (keyed) for (int k = 0; k < ch; ++k) key[k] = (uint16_t)(trns[2 * k] << 8 | trns[2 * k + 1]);
+    img.channels = ch + (keyed ? 1 : 0);
+    img.u8.resize(npx * img.channels);
+    const int scale = depth < 8 ? 255 / ((1 << depth) - 1) : 1;
+    for (size_t i = 0; i < npx; ++i) {
+        bool is_key = keyed;
+        for (int k = 0; k < ch; ++k) {
+            const uint16_t v = smp[i * ch + k];
+            if (keyed && v != key[k]) is_key = false;
+            img.u8[i * img.channels + k] = depth == 16 ? (uint8_t)(v >> 8) : (uint8_t)(v * scale);
+        }
+        if (keyed) img.u8[i * img.channels + ch] = is_key ? 0 : 255;
     }
     return img;
 }
@@ -409,10 +472,13 @@ static LoadedImage load_hdr(const std::string &filename) {
     return img;
 }
 
-// Baseline / extended-sequential Huffman JPEG (ITU T.81: SOF0, SOF1 with 8-bit samples), 1 or 3 components, any 1x/2x sampling
-// factors, restart intervals.  The reference reads .jpg textures through stb_image (utils/image.cpp:135-143); progressive and
-// arithmetic-coded files are reported as unsupported.  Chroma is upsampled with libjpeg's triangle filter, the IDCT is separable floating point:
-// decoded values agree with libjpeg to 1-3 eight-bit levels (tests/test_postprocess_cpu.py).
+// Huffman-coded JPEG (ITU T.81: SOF0 baseline, SOF1 extended sequential, SOF2 progressive; 8-bit samples), 1 or 3 components, any
+// 1x/2x sampling factors, restart intervals, interleaved and single-component scans.  The reference reads .jpg textures through
+// stb_image (utils/image.cpp:135-143), which covers the same set; arithmetic-coded and lossless files are reported as unsupported
+// (stb_image rejects them too).  Every scan is decoded into per-component coefficient arrays (spectral selection and successive
+// approximation as in T.81 annex G); dequantisation and the IDCT run once after the last scan.  Chroma is upsampled with
+// libjpeg's triangle filter, the IDCT is separable floating point: decoded values agree with libjpeg to 1-3 eight-bit levels
+// (tests/test_postprocess_cpu.py).
 static LoadedImage load_jpg(const std::string &filename) {
     std::ifstream f(filename, std::ios::binary);
     if (!f) throw Error("failed to open file: " + filename);
@@ -438,83 +504,23 @@ static LoadedImage load_jpg(const std::string &filename) {
             ok = true;
         }
     };
-    struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0; int bw = 0, bh = 0; std::vector<uint8_t> px; };
+    struct Comp {
+        int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0;
+        int bw = 0, bh = 0;    // padded size in pixels (whole MCUs)
+        int nbx = 0, nby = 0;  // padded size in blocks: the layout of coef
+        int cbx = 0, cby = 0;  // blocks that cover the component itself: what a single-component scan codes (T.81 A.2.2)
+        std::vector<int16_t> coef;
+        std::vector<uint8_t> px;
+    };
     uint16_t qt[4][64] = {{0}};
     Huff hdc[4], hac[4];
     std::vector<Comp> comps;
-    int width = 0, height = 0, restart = 0;
-    size_t p = 2;
+    int width = 0, height = 0, restart = 0, hmax = 1, vmax = 1, mcux = 0, mcuy = 0, scans = 0;
+    bool progressive = false;
     auto u16 = [&](size_t at) { if (at + 1 >= buf.size()) throw fail("truncated"); return (int)buf[at] << 8 | buf[at + 1]; };
-    size_t scan_at = 0;
-    while (p + 4 <= buf.size()) {
-        if (buf[p] != 0xff) throw fail("marker expected");
-        const int m = buf[p + 1];
-        p += 2;
-        if (m == 0xd8 || (m >= 0xd0 && m <= 0xd7) || m == 0x01 || m == 0xff) { if (m == 0xff) --p; continue; }
-        if (m == 0xd9) break;
-        const int len = u16(p);
-        if (len < 2 || p + len > buf.size()) throw fail("bad segment length");
-        const size_t q = p + 2, end = p + len;
-        if (m == 0xdb) {
-            for (size_t a = q; a < end;) {
-                const int pq = buf[a] >> 4, id = buf[a] & 15;
-                ++a;
-                if (id > 3) throw fail("bad quantisation table");
-                for (int i = 0; i < 64; ++i) { qt[id][zz[i]] = pq ? (uint16_t)u16(a) : buf[a]; a += pq ? 2 : 1; }
-            }
-        } else if (m == 0xc0 || m == 0xc1) {
-            if (buf[q] != 8) throw fail("only 8-bit samples");
-            height = u16(q + 1); width = u16(q + 3);
-            const int nc = buf[q + 5];
-            if (nc != 1 && nc != 3) throw fail("unsupported component count " + std::to_string(nc));
-            comps.resize(nc);
-            for (int c = 0; c < nc; ++c) {
-                comps[c].id = buf[q + 6 + 3 * c];
-                comps[c].h = buf[q + 7 + 3 * c] >> 4; comps[c].v = buf[q + 7 + 3 * c] & 15;
-                comps[c].tq = buf[q + 8 + 3 * c];
-                if (comps[c].h < 1 || comps[c].h > 2 || comps[c].v < 1 || comps[c].v > 2 || comps[c].tq > 3) throw fail("unsupported sampling");
-            }
-        } else if (m == 0xc2 || (m >= 0xc3 && m <= 0xcf && m != 0xc4 && m != 0xc8 && m != 0xcc)) {
-            throw fail("progressive / lossless / arithmetic JPEG is not supported");
-        } else if (m == 0xc4) {
-            for (size_t a = q; a < end;) {
-                const int tc = buf[a] >> 4, id = buf[a] & 15;
-                ++a;
-                if (id > 3 || tc > 1) throw fail("bad Huffman table");
-                Huff &h = tc ? hac[id] : hdc[id];
-                int n = 0;
-                for (int l = 1; l <= 16; ++l) { h.bits[l] = buf[a + l - 1]; n += h.bits[l]; }
-                a += 16;
-                if (n > 256 || a + n > end) throw fail("bad Huffman table");
-                for (int i = 0; i < n; ++i) h.vals[i] = buf[a + i];
-                a += n;
-                h.build();
-            }
-        } else if (m == 0xdd) {
-            restart = u16(q);
-        } else if (m == 0xda) {
-            const int ns = buf[q];
-            if (ns != (int)comps.size()) throw fail("non-interleaved scans are not supported");
-            for (int i = 0; i < ns; ++i) {
-                const int cid = buf[q + 1 + 2 * i], t = buf[q + 2 + 2 * i];
-                for (auto &c : comps) if (c.id == cid) { c.td = t >> 4; c.ta = t & 15; }
-            }
-            scan_at = end;
-            break;
-        }
-        p = end;
-    }
-    if (!scan_at || comps.empty() || width <= 0 || height <= 0) throw fail("no image data");
-    int hmax = 1, vmax = 1;
-    for (auto &c : comps) { hmax = std::max(hmax, c.h); vmax = std::max(vmax, c.v); }
-    const int mcux = (width + 8 * hmax - 1) / (8 * hmax), mcuy = (height + 8 * vmax - 1) / (8 * vmax);
-    for (auto &c : comps) {
-        if (!hdc[c.td].ok || !hac[c.ta].ok) throw fail("missing Huffman table");
-        c.bw = mcux * c.h * 8; c.bh = mcuy * c.v * 8;
-        c.px.assign((size_t)c.bw * c.bh, 0);
-    }
-    // entropy-coded data
-    size_t bp = scan_at;
+
+    // entropy-coded segment reader: stops feeding at a marker (zeros from there on), never steps over one
+    size_t bp = 0;
     uint32_t acc = 0;
     int nb = 0;
     auto fill = [&]() {
@@ -550,50 +556,225 @@ static LoadedImage load_jpg(const std::string &filename) {
         throw fail("bad Huffman code");
     };
     auto extend = [](int v, int t) { return t && v < (1 << (t - 1)) ? v - (1 << t) + 1 : v; };
+
+    // one scan: `sc` = the components it codes, spectral band [ss, se], successive-approximation bits ah / al
+    auto decode_scan = [&](const std::vector<Comp *> &sc, int ss, int se, int ah, int al) {
+        acc = 0; nb = 0;
+        int eobrun = 0;
+        for (Comp *c : sc) c->pred = 0;
+        const int bit = 1 << al;
+        auto refine = [&](int16_t &q) {  // correction bit of an already non-zero coefficient (G.1.2.3)
+            if (getbits(1) && (q & bit) == 0) q = (int16_t)(q > 0 ? q + bit : q - bit);
+        };
+        auto block = [&](Comp &c, int16_t *q) {
+            if (!progressive) {
+                if (!hdc[c.td].ok || !hac[c.ta].ok) throw fail("missing Huffman table");
+                const int t = decode(hdc[c.td]);
+                c.pred += extend(getbits(t), t);
+                q[0] = (int16_t)c.pred;
+                for (int k = 1; k < 64;) {
+                    const int rs = decode(hac[c.ta]), r = rs >> 4, sz = rs & 15;
+                    if (sz == 0) { if (r != 15) break; k += 16; continue; }
+                    k += r;
+                    if (k > 63) throw fail("bad coefficient index");
+                    q[zz[k]] = (int16_t)extend(getbits(sz), sz);
+                    ++k;
+                }
+                return;
+            }
+            if (ss == 0) {  // DC scan: first pass sends the value >> al, refinement one more bit
+                if (ah == 0) {
+                    if (!hdc[c.td].ok) throw fail("missing Huffman table");
+                    const int t = decode(hdc[c.td]);
+                    c.pred += extend(getbits(t), t);
+                    q[0] = (int16_t)(c.pred * bit);
+                } else if (getbits(1)) q[0] = (int16_t)(q[0] | bit);
+                return;
+            }
+            if (!hac[c.ta].ok) throw fail("missing Huffman table");
+            if (ah == 0) {  // AC first pass (G.1.2.2): run/size symbols with end-of-band runs
+                if (eobrun) { --eobrun; return; }
+                for (int k = ss; k <= se;) {
+                    const int rs = decode(hac[c.ta]), r = rs >> 4, sz = rs & 15;
+                    if (sz == 0) {
+                        if (r < 15) { eobrun = (1 << r) - 1 + (r ? getbits(r) : 0); break; }
+                        k += 16;
+                        continue;
+                    }
+                    k += r;
+                    if (k > se) throw fail("bad coefficient index");
+                    q[zz[k]] = (int16_t)(extend(getbits(sz), sz) * bit);
+                    ++k;
+                }
+                return;
+            }
+            // AC refinement (G.1.2.3): new +-1 coefficients are placed after skipping r *zero* coefficients; every non-zero
+            // coefficient passed on the way takes one correction bit
+            if (eobrun) {
+                --eobrun;
+                for (int k = ss; k <= se; ++k) if (q[zz[k]]) refine(q[zz[k]]);
+                return;
+            }
+            for (int k = ss; k <= se;) {
+                const int rs = decode(hac[c.ta]), sz = rs & 15;
+                int r = rs >> 4, val = 0;
+                if (sz == 0) {
+                    if (r < 15) { eobrun = (1 << r) - 1 + (r ? getbits(r) : 0); r = 64; }  // rest of the band: corrections only
+                } else {
+                    if (sz != 1) throw fail("bad refinement symbol");
+                    val = getbits(1) ? bit : -bit;
+                }
+                while (k <= se) {
+                    int16_t &cq = q[zz[k++]];
+                    if (cq) refine(cq);
+                    else if (r == 0) { cq = (int16_t)val; break; }
+                    else --r;
+                }
+            }
+        };
+        auto at_restart = [&](int done) {
+            if (!(restart && done && done % restart == 0)) return;
+            acc = 0; nb = 0; eobrun = 0;  // RSTn: byte align, skip the marker, reset the predictors
+            while (bp + 1 < buf.size() && !(buf[bp] == 0xff && buf[bp + 1] >= 0xd0 && buf[bp + 1] <= 0xd7)) ++bp;
+            bp += 2;
+            for (Comp *c : sc) c->pred = 0;
+        };
+        int done = 0;
+        if (sc.size() == 1) {
+            Comp &c = *sc[0];
+            for (int j = 0; j < c.cby; ++j)
+                for (int i = 0; i < c.cbx; ++i) {
+                    at_restart(done++);
+                    block(c, &c.coef[((size_t)j * c.nbx + i) * 64]);
+                }
+        } else {
+            for (int my = 0; my < mcuy; ++my)
+                for (int mx = 0; mx < mcux; ++mx) {
+                    at_restart(done++);
+                    for (Comp *c : sc)
+                        for (int by = 0; by < c->v; ++by)
+                            for (int bx = 0; bx < c->h; ++bx) block(*c, &c->coef[((size_t)(my * c->v + by) * c->nbx + mx * c->h + bx) * 64]);
+                }
+        }
+    };
+
+    size_t p = 2;
+    bool eoi = false;
+    while (!eoi && p + 4 <= buf.size()) {
+        if (buf[p] != 0xff) throw fail("marker expected");
+        const int m = buf[p + 1];
+        p += 2;
+        if (m == 0xd8 || (m >= 0xd0 && m <= 0xd7) || m == 0x01 || m == 0xff) { if (m == 0xff) --p; continue; }
+        if (m == 0xd9) break;
+        const int len = u16(p);
+        if (len < 2 || p + len > buf.size()) throw fail("bad segment length");
+        const size_t q = p + 2, end = p + len;
+        if (m == 0xdb) {
+            for (size_t a = q; a < end;) {
+                const int pq = buf[a] >> 4, id = buf[a] & 15;
+                ++a;
+                if (id > 3) throw fail("bad quantisation table");
+                for (int i = 0; i < 64; ++i) { qt[id][zz[i]] = pq ? (uint16_t)u16(a) : buf[a]; a += pq ? 2 : 1; }
+            }
+        } else if (m == 0xc0 || m == 0xc1 || m == 0xc2) {
+            if (!comps.empty()) throw fail("more than one frame");
+            progressive = m == 0xc2;
+            if (buf[q] != 8) throw fail("only 8-bit samples");
+            height = u16(q + 1); width = u16(q + 3);
+            const int nc = buf[q + 5];
+            if (nc != 1 && nc != 3) throw fail("unsupported component count " + std::to_string(nc));
+            if (width <= 0 || height <= 0) throw fail("no image data");
+            comps.resize(nc);
+            for (int c = 0; c < nc; ++c) {
+                comps[c].id = buf[q + 6 + 3 * c];
+                comps[c].h = buf[q + 7 + 3 * c] >> 4; comps[c].v = buf[q + 7 + 3 * c] & 15;
+                comps[c].tq = buf[q + 8 + 3 * c];
+                if (comps[c].h < 1 || comps[c].h > 2 || comps[c].v < 1 || comps[c].v > 2 || comps[c].tq > 3) throw fail("unsupported sampling");
+            }
+            if (nc == 1) comps[0].h = comps[0].v = 1;  // a single component is never interleaved: its sampling factors do not matter
+            for (auto &c : comps) { hmax = std::max(hmax, c.h); vmax = std::max(vmax, c.v); }
+            mcux = (width + 8 * hmax - 1) / (8 * hmax); mcuy = (height + 8 * vmax - 1) / (8 * vmax);
+            for (auto &c : comps) {
+                c.nbx = mcux * c.h; c.nby = mcuy * c.v;
+                c.bw = c.nbx * 8; c.bh = c.nby * 8;
+                c.cbx = ((width * c.h + hmax - 1) / hmax + 7) / 8; c.cby = ((height * c.v + vmax - 1) / vmax + 7) / 8;
+                c.coef.assign((size_t)c.nbx * c.nby * 64, 0);
+            }
+        } else if (m >= 0xc3 && m <= 0xcf && m != 0xc4 && m != 0xc8 && m != 0xcc) {
+            throw fail("lossless / hierarchical / arithmetic-coded JPEG is not supported");
+        } else if (m == 0xc4) {
+            for (size_t a = q; a < end;) {
+                const int tc = buf[a] >> 4, id = buf[a] & 15;
+                ++a;
+                if (id > 3 || tc > 1 || a + 16 > end) throw fail("bad Huffman table");
+                Huff &h = tc ? hac[id] : hdc[id];
+                int n = 0;
+                for (int l = 1; l <= 16; ++l) { h.bits[l] = buf[a + l - 1]; n += h.bits[l]; }
+                a += 16;
+                if (n > 256 || a + n > end) throw fail("bad Huffman table");
+                for (int i = 0; i < n; ++i) h.vals[i] = buf[a + i];
+                a += n;
+                h.build();
+            }
+        } else if (m == 0xdd) {
+            restart = u16(q);
+        } else if (m == 0xda) {
+            if (comps.empty()) throw fail("scan before frame header");
+            const int ns = buf[q];
+            if (ns < 1 || ns > (int)comps.size() || q + 1 + 2 * (size_t)ns + 3 > end) throw fail("bad scan header");
+            std::vector<Comp *> sc;
+            for (int i = 0; i < ns; ++i) {
+                const int cid = buf[q + 1 + 2 * i], t = buf[q + 2 + 2 * i];
+                Comp *found = nullptr;
+                for (auto &c : comps) if (c.id == cid) found = &c;
+                if (!found || (t >> 4) > 3 || (t & 15) > 3) throw fail("bad scan header");
+                found->td = t >> 4; found->ta = t & 15;
+                sc.push_back(found);
+            }
+            int ss = buf[q + 1 + 2 * ns], se = buf[q + 2 + 2 * ns];
+            const int ah = buf[q + 3 + 2 * ns] >> 4, al = buf[q + 3 + 2 * ns] & 15;
+            if (!progressive) { ss = 0; se = 63; }
+            else if (ss > se || se > 63 || (ss == 0 && se != 0) || (ss > 0 && ns != 1) || al > 13 || ah > 13) throw fail("bad progressive scan parameters");
+            bp = end;
+            decode_scan(sc, ss, se, progressive ? ah : 0, progressive ? al : 0);
+            ++scans;
+            // next marker that is not a restart marker / stuffed byte
+            size_t n = bp;
+            while (n + 1 < buf.size() && !(buf[n] == 0xff && buf[n + 1] != 0 && buf[n + 1] != 0xff && !(buf[n + 1] >= 0xd0 && buf[n + 1] <= 0xd7))) ++n;
+            if (n + 1 >= buf.size()) eoi = true;  // truncated file: keep what was decoded (stb_image does the same)
+            p = n;
+            continue;
+        }
+        p = end;
+    }
+    if (!scans || comps.empty()) throw fail("no image data");
+
+    // dequantisation + inverse DCT of every block
     float cs[8][8];
     for (int x = 0; x < 8; ++x)
         for (int u = 0; u < 8; ++u) cs[x][u] = std::cos((2 * x + 1) * u * 3.14159265358979f / 16.0f) * (u == 0 ? 0.353553391f : 0.5f);
-    int mcu_count = 0;
-    for (int my = 0; my < mcuy; ++my)
-        for (int mx = 0; mx < mcux; ++mx) {
-            if (restart && mcu_count && mcu_count % restart == 0) {  // RSTn: byte align, skip the marker, reset the predictors
-                acc = 0; nb = 0;
-                while (bp + 1 < buf.size() && !(buf[bp] == 0xff && buf[bp + 1] >= 0xd0 && buf[bp + 1] <= 0xd7)) ++bp;
-                bp += 2;
-                for (auto &c : comps) c.pred = 0;
-            }
-            ++mcu_count;
-            for (auto &c : comps)
-                for (int by = 0; by < c.v; ++by)
-                    for (int bx = 0; bx < c.h; ++bx) {
-                        float blk[64] = {0};
-                        const int t = decode(hdc[c.td]);
-                        c.pred += extend(getbits(t), t);
-                        blk[0] = (float)c.pred * qt[c.tq][0];
-                        for (int k = 1; k < 64;) {
-                            const int rs = decode(hac[c.ta]), r = rs >> 4, sz = rs & 15;
-                            if (sz == 0) { if (r != 15) break; k += 16; continue; }
-                            k += r;
-                            if (k > 63) throw fail("bad coefficient index");
-                            blk[zz[k]] = (float)extend(getbits(sz), sz) * qt[c.tq][zz[k]];
-                            ++k;
-                        }
-                        float tmp[64];
-                        for (int v = 0; v < 8; ++v)
-                            for (int x = 0; x < 8; ++x) {
-                                float a = 0;
-                                for (int u = 0; u < 8; ++u) a += blk[8 * v + u] * cs[x][u];
-                                tmp[8 * v + x] = a;
-                            }
-                        const int ox = (mx * c.h + bx) * 8, oy = (my * c.v + by) * 8;
-                        for (int y = 0; y < 8; ++y)
-                            for (int x = 0; x < 8; ++x) {
-                                float a = 0;
-                                for (int v = 0; v < 8; ++v) a += tmp[8 * v + x] * cs[y][v];
-                                c.px[(size_t)(oy + y) * c.bw + ox + x] = (uint8_t)std::min(std::max((int)std::lround(a + 128.0f), 0), 255);
-                            }
+    for (auto &c : comps) {
+        c.px.assign((size_t)c.bw * c.bh, 0);
+        for (int bj = 0; bj < c.nby; ++bj)
+            for (int bi = 0; bi < c.nbx; ++bi) {
+                const int16_t *q = &c.coef[((size_t)bj * c.nbx + bi) * 64];
+                float blk[64], tmp[64];
+                for (int i = 0; i < 64; ++i) blk[i] = (float)q[i] * qt[c.tq][i];
+                for (int v = 0; v < 8; ++v)
+                    for (int x = 0; x < 8; ++x) {
+                        float a = 0;
+                        for (int u = 0; u < 8; ++u) a += blk[8 * v + u] * cs[x][u];
+                        tmp[8 * v + x] = a;
                     }
-        }
+                for (int y = 0; y < 8; ++y)
+                    for (int x = 0; x < 8; ++x) {
+                        float a = 0;
+                        for (int v = 0; v < 8; ++v) a += tmp[8 * v + x] * cs[y][v];
+                        c.px[(size_t)(bj * 8 + y) * c.bw + bi * 8 + x] = (uint8_t)std::min(std::max((int)std::lround(a + 128.0f), 0), 255);
+                    }
+            }
+        std::vector<int16_t>().swap(c.coef);
+    }
     // chroma upsampling: the triangle filter of libjpeg / stb_image ("fancy upsampling") for 2x factors, replication otherwise
     const int fw = mcux * hmax * 8, fh = mcuy * vmax * 8;
     for (auto &c : comps) {

@@ -109,8 +109,9 @@ def test_unknown_format_is_an_error(built, tmp_path):
 
 
 def test_jpeg_decoder_against_libjpeg(built, tmp_path):
-    """ImageDynamic::load for .jpg (the reference goes through stb_image): baseline files with 4:4:4 / 4:2:2 / 4:2:0 chroma, grayscale
-    and restart intervals decode to within 3 eight-bit levels of libjpeg (PIL); progressive files are refused with a clear error."""
+    """ImageDynamic::load for .jpg (the reference goes through stb_image): baseline and progressive files with 4:4:4 / 4:2:2 / 4:2:0
+    chroma, grayscale and restart intervals decode to within 3 eight-bit levels of libjpeg (PIL); arithmetic-coded files (which
+    stb_image does not read either) are refused with a clear error."""
     from btrc_b200 import api
 
     rng = np.random.default_rng(3)
@@ -118,20 +119,33 @@ def test_jpeg_decoder_against_libjpeg(built, tmp_path):
     img = np.stack([127 + 100 * np.sin(xx / 9.0) * np.cos(yy / 7.0), 30 + xx * 2.0, 200 - yy * 2.5], -1) + rng.normal(0, 6, (67, 101, 3))
     img = np.clip(img, 0, 255).astype(np.uint8)
     cases = {"q90_420.jpg": dict(quality=90), "q75_444.jpg": dict(quality=75, subsampling=0), "q95_422.jpg": dict(quality=95, subsampling=1),
-             "gray.jpg": dict(quality=85), "rst.jpg": dict(quality=80, restart_marker_blocks=5)}
+             "gray.jpg": dict(quality=85), "rst.jpg": dict(quality=80, restart_marker_blocks=5),
+             # progressive (SOF2): DC first + refinement, AC bands with end-of-band runs, AC refinement, single-component scans
+             "prog_420.jpg": dict(quality=90, progressive=True), "prog_444.jpg": dict(quality=97, progressive=True, subsampling=0),
+             "prog_422.jpg": dict(quality=60, progressive=True, subsampling=1), "prog_gray.jpg": dict(quality=85, progressive=True),
+             "prog_rst.jpg": dict(quality=80, progressive=True, restart_marker_blocks=3), "prog_lowq.jpg": dict(quality=10, progressive=True)}
     for name, kw in cases.items():
         p = str(tmp_path / name)
-        Image.fromarray(img[..., 0] if name == "gray.jpg" else img).save(p, **kw)
+        Image.fromarray(img[..., 0] if "gray" in name else img).save(p, **kw)
         ref = np.asarray(Image.open(p))
         ref = ref if ref.ndim == 3 else ref[..., None]
         got = api.load_image(p)
         assert got.shape == ref.shape and got.dtype == np.uint8, name
         err = np.abs(got.astype(int) - ref.astype(int))
         assert err.max() <= 3 and err.mean() < 0.1, (name, err.max(), err.mean())
-    p = str(tmp_path / "progressive.jpg")
-    Image.fromarray(img).save(p, progressive=True)
-    with pytest.raises(api.BtrcError, match="progressive"):
-        api.load_image(p)
+        if "prog" in name:
+            assert b"\xff\xc2" in open(p, "rb").read()  # really a progressive frame
+    # a file whose frame header says SOF9 (arithmetic coding): refused, as by stb_image
+    data = open(tmp_path / "q90_420.jpg", "rb").read().replace(b"\xff\xc0", b"\xff\xc9", 1)
+    open(tmp_path / "arith.jpg", "wb").write(data)
+    with pytest.raises(api.BtrcError, match="arithmetic"):
+        api.load_image(str(tmp_path / "arith.jpg"))
+    # truncated entropy data: an error or a partial picture, never a crash
+    open(tmp_path / "cut.jpg", "wb").write(open(tmp_path / "prog_420.jpg", "rb").read()[:900])
+    try:
+        assert api.load_image(str(tmp_path / "cut.jpg")).shape == (67, 101, 3)
+    except api.BtrcError:
+        pass
     # the product's own writer -> its own reader (and PIL's): what `save` writes can be used as a texture
     from btrc_b200 import scenes
     path = scenes.make_cornell(str(tmp_path), width=101, height=67, spp=1, state_count=64)
@@ -159,3 +173,122 @@ def test_png_and_hdr_load(built, tmp_path):
     assert np.array_equal(api.load_image(str(tmp_path / "g.png"))[..., 0], rgba[..., 0])
     with pytest.raises(api.BtrcError, match="unsupported image format"):
         api.load_image(str(tmp_path / "x.exr"))
+
+
+def _png_bytes(samples, depth, ctype, interlace=False, plte=None, trns=None):
+    """A PNG file from an (H, W, C) array of raw sample values: any bit depth / colour type, optional Adam7, the five filter
+    types in rotation (test-side writer: PIL writes neither interlaced files nor 16-bit RGB)."""
+    import struct
+    import zlib
+
+    h, w, ch = samples.shape
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+
+    def pack_row(row):  # (pw, ch) raw samples -> bytes
+        flat = row.reshape(-1).astype(np.uint32)
+        if depth == 16:
+            return flat.astype(">u2").tobytes()
+        if depth == 8:
+            return flat.astype(np.uint8).tobytes()
+        bits = np.zeros((flat.size * depth + 7) // 8 * 8, np.uint8)
+        for b in range(depth):
+            bits[b:flat.size * depth:depth] = (flat >> (depth - 1 - b)) & 1
+        return np.packbits(bits).tobytes()
+
+    def paeth(a, b, c):
+        pp = a + b - c
+        pa, pb, pc = abs(pp - a), abs(pp - b), abs(pp - c)
+        return a if pa <= pb and pa <= pc else (b if pb <= pc else c)
+
+    bpp = max(1, depth * ch // 8)
+    raw = bytearray()
+    nrow = 0
+    passes = [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)] if interlace else [(0, 0, 1, 1)]
+    for x0, y0, dx, dy in passes:
+        sub = samples[y0::dy, x0::dx]
+        if sub.shape[0] == 0 or sub.shape[1] == 0:
+            continue
+        prev = None
+        for r in range(sub.shape[0]):
+            cur = pack_row(sub[r])
+            up = prev if prev is not None else bytes(len(cur))
+            ft = nrow % 5
+            nrow += 1
+            out = bytearray([ft])
+            for i, v in enumerate(cur):
+                a = cur[i - bpp] if i >= bpp else 0
+                b = up[i]
+                c = up[i - bpp] if i >= bpp else 0
+                pred = (0, a, b, (a + b) // 2, paeth(a, b, c))[ft]
+                out.append((v - pred) & 255)
+            raw += out
+            prev = cur
+    data = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 1 if interlace else 0))
+    if plte is not None:
+        data += chunk(b"PLTE", bytes(plte))
+    if trns is not None:
+        data += chunk(b"tRNS", bytes(trns))
+    z = zlib.compress(bytes(raw))
+    data += chunk(b"IDAT", z[:len(z) // 2]) + chunk(b"IDAT", z[len(z) // 2:]) + chunk(b"IEND", b"")
+    return data
+
+
+def test_png_every_variant_stb_reads(built, tmp_path):
+    """ImageDynamic::load for .png goes through stb_image's 8-bit interface (utils/image.cpp:116-147): every colour type and bit
+    depth, Adam7 interlacing, palettes and tRNS colour keys, with stb_image's conversions (high byte of 16-bit samples, grey
+    scaled by 255 / (2^depth - 1), palette -> RGB / RGBA, colour key -> alpha 0 / 255).  Files are also opened with PIL to make
+    sure the test-side writer produced valid PNGs."""
+    from btrc_b200 import api
+
+    rng = np.random.default_rng(8)
+    H, W = 19, 23   # not multiples of 8: ragged Adam7 passes and ragged packed rows
+    pal = rng.integers(0, 256, (16, 3), dtype=np.uint8)
+    n = 0
+    for interlace in (False, True):
+        for ctype, ch, depths in ((0, 1, (1, 2, 4, 8, 16)), (2, 3, (8, 16)), (3, 1, (1, 2, 4, 8)), (4, 2, (8, 16)), (6, 4, (8, 16))):
+            for depth in depths:
+                hi = min(1 << depth, 16) if ctype == 3 else 1 << depth
+                smp = rng.integers(0, hi, (H, W, ch)).astype(np.uint32)
+                name = str(tmp_path / f"t{ctype}_d{depth}_i{int(interlace)}.png")
+                open(name, "wb").write(_png_bytes(smp, depth, ctype, interlace, plte=pal.reshape(-1) if ctype == 3 else None))
+                if ctype == 3:
+                    want = pal[smp[..., 0]]
+                elif depth == 16:
+                    want = (smp >> 8).astype(np.uint8)
+                else:
+                    want = (smp * (255 // ((1 << depth) - 1))).astype(np.uint8)
+                got = api.load_image(name)
+                assert got.shape == want.shape and np.array_equal(got, want), name
+                pil = Image.open(name)
+                pil.load()
+                assert pil.size == (W, H)
+                if depth <= 8 and ctype in (2, 3, 6):
+                    assert np.array_equal(np.asarray(pil.convert("RGBA" if ctype == 6 else "RGB")), want), name  # PIL agrees where it has no 16-bit modes in the way
+                n += 1
+    assert n == 30
+    # tRNS: palette alpha, grey and RGB colour keys (8- and 16-bit)
+    idx = rng.integers(0, 16, (H, W, 1)).astype(np.uint32)
+    alpha = rng.integers(0, 256, 10, dtype=np.uint8)  # shorter than the palette: the rest is opaque
+    open(tmp_path / "pt.png", "wb").write(_png_bytes(idx, 4, 3, True, plte=pal.reshape(-1), trns=alpha))
+    got = api.load_image(str(tmp_path / "pt.png"))
+    assert got.shape == (H, W, 4) and np.array_equal(got[..., :3], pal[idx[..., 0]])
+    assert np.array_equal(got[..., 3], np.concatenate([alpha, np.full(6, 255, np.uint8)])[idx[..., 0]])
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "pt.png").convert("RGBA")), got)
+    g = rng.integers(0, 4, (H, W, 1)).astype(np.uint32)
+    open(tmp_path / "gk.png", "wb").write(_png_bytes(g, 2, 0, False, trns=[0, 2]))
+    got = api.load_image(str(tmp_path / "gk.png"))
+    assert got.shape == (H, W, 2) and np.array_equal(got[..., 0], g[..., 0] * 85) and np.array_equal(got[..., 1], np.where(g[..., 0] == 2, 0, 255))
+    c16 = rng.integers(0, 3, (H, W, 3)).astype(np.uint32) * 0x0101 + 0x1000
+    open(tmp_path / "ck.png", "wb").write(_png_bytes(c16, 16, 2, True, trns=[0x11, 0x01, 0x10, 0x00, 0x12, 0x02]))
+    got = api.load_image(str(tmp_path / "ck.png"))
+    key = (c16[..., 0] == 0x1101) & (c16[..., 1] == 0x1000) & (c16[..., 2] == 0x1202)
+    assert key.any() and got.shape == (H, W, 4)
+    assert np.array_equal(got[..., :3], (c16 >> 8).astype(np.uint8)) and np.array_equal(got[..., 3], np.where(key, 0, 255))
+    # malformed files: errors, not crashes
+    good = _png_bytes(rng.integers(0, 256, (H, W, 3)).astype(np.uint32), 8, 2)
+    for label, bad in (("cut", good[:60]), ("depth", good[:24] + b"\x03" + good[25:]), ("sig", b"\x00" + good[1:])):
+        open(tmp_path / f"{label}.png", "wb").write(bad)
+        with pytest.raises(api.BtrcError, match="failed to load image"):
+            api.load_image(str(tmp_path / f"{label}.png"))
