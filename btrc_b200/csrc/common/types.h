@@ -66,9 +66,13 @@ struct MaterialDesc {
     float scalar_const[SLOT_COUNT];
 };
 
-// 3-D textures: constant or a CUDA 3-D texture object (texture3d/array3d.cpp, core/texture3d.cpp)
+// 3-D textures: constant, a CUDA 3-D texture object (texture3d/array3d.cpp, core/texture3d.cpp) or the sum / product of two
+// (texture3d/binary.cpp).  Node table entry: TEX3D_CONST / TEX3D_ARRAY, or TEX3D_PROGRAM with tex = first | count << 32 naming a
+// postfix program of TEX3D_CONST / ARRAY / ADD / MUL entries in the same table (behind the nodes).
+enum Tex3DKind : int { TEX3D_CONST = 0, TEX3D_ARRAY = 1, TEX3D_ADD = 2, TEX3D_MUL = 3, TEX3D_PROGRAM = 4 };
+constexpr int TEX3D_STACK = 4;
 struct Texture3DDesc {
-    int is_array;
+    int is_array;  // Tex3DKind
     float value[3];
     unsigned long long tex;
 };
@@ -207,7 +211,7 @@ struct SceneDevice {
     const uint8_t *instance_class;  // shade class of each instance (1 + material type)
     int n_instances;
     int n_lights;                   // area lights + (environment light ? 1 : 0)   (core/light_sampler.cpp:24-33)
-    int has_medium;                 // Scene::has_medium (core/scene.cpp:346-356)
+    int has_medium;                 // Scene::has_medium (core/scene.cpp:346-356); 2 = and some 3-D texture is an add / mul program
     EnvLight env;
     CameraInfo camera;
     const float2 *filter_alias;  // gaussian filter alias table (256*256)

@@ -363,7 +363,7 @@ __device__ __forceinline__ void flush_splat_count(WaveCtl *ctl, unsigned long lo
 // ---------------------------------------------------------------------------------------------------------------
 // medium (medium.cpp:36-164, 214-249): only launched when the scene has media (wavefront.cpp:254-268)
 // ---------------------------------------------------------------------------------------------------------------
-template <bool HALTON>
+template <bool HALTON, bool T3P>
 __global__ void __launch_bounds__(kBlock) medium_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQueue nq, ShadowQueue sq,
                                                        FilmDevice film, WaveCtl *ctl) {
     const int n = ctl->n_active;
@@ -406,8 +406,8 @@ __global__ void __launch_bounds__(kBlock) medium_kernel(SceneDevice scene, Rende
             if (tracked) {
                 beta4 = q.beta[i]; rad4 = q.rad[i];
                 sampler.load(q.rng[i], scene.halton);
-                ms = medium_sample(scene, medium, o, medium_end, sampler);
-                unscatter_tr = medium_tr(scene, medium, o, medium_end, sampler);
+                ms = medium_sample<T3P>(scene, medium, o, medium_end, sampler);
+                unscatter_tr = medium_tr<T3P>(scene, medium, o, medium_end, sampler);
             }
             pixel = __float_as_uint(rad4.w);
             if (tracked) {
@@ -621,7 +621,7 @@ shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQu
 // ---------------------------------------------------------------------------------------------------------------
 // shadow rays (shadow.cpp:24-74): occlusion with early exit; unoccluded => splat beta_li * Tr
 // ---------------------------------------------------------------------------------------------------------------
-template <bool IFIF, bool SORTED>
+template <bool IFIF, bool SORTED, bool T3P>
 __global__ void __launch_bounds__(kBlock, BTRC_TRACE_MIN_BLOCKS) shadow_kernel(SceneDevice scene, RenderParams P, ShadowQueue sq, RaySort rs, FilmDevice film, WaveCtl *ctl) {
     const int n = ctl->n_shadow;
     const int n_sorted = SORTED ? ctl->n_shadow_sorted : 0;
@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(kBlock, BTRC_TRACE_MIN_BLOCKS) shadow_kernel(S
         if (valid && h.slot < 0) {  // unoccluded: the reference's miss program (shadow.cpp:39-74)
             const float4 b4 = sq.beta_li[i];
             f3 v = xyz(b4);
-            if (scene.has_medium) v = v * shadow_tr(scene, o4, d4);
+            if (scene.has_medium) v = v * shadow_tr<T3P>(scene, o4, d4);
             film_splat3(film.radiance, __float_as_uint(b4.w), v);
             misses += 1;
         }
@@ -756,19 +756,35 @@ void launch_classify(const LaunchCfg &cfg, const SceneDevice &scene, HitQueue hi
 
 void launch_medium(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, HitQueue hit, PathQueue next,
                    ShadowQueue shadow, FilmDevice film, WaveCtl *ctl, cudaStream_t stream) {
-    if (params.halton) medium_kernel<true><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
-    else medium_kernel<false><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
+    const int blocks = persistent_blocks(cfg, 8);
+    if (scene.has_medium == 2) {  // the scene has "add" / "mul" 3-D textures (postfix programs): instantiations that can run them
+        if (params.halton) medium_kernel<true, true><<<blocks, kBlock, 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
+        else medium_kernel<false, true><<<blocks, kBlock, 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
+        return;
+    }
+    if (params.halton) medium_kernel<true, false><<<blocks, kBlock, 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
+    else medium_kernel<false, false><<<blocks, kBlock, 0, stream>>>(scene, params, cur, hit, next, shadow, film, ctl);
 }
 
 void launch_shadow(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, ShadowQueue shadow, RaySort rs, FilmDevice film, WaveCtl *ctl,
                    cudaStream_t stream) {
     const int blocks = persistent_blocks(cfg, 8);
+    if (scene.has_medium == 2) {  // 3-D texture programs in the transmittance: see launch_medium
+        if (cfg.sorted_rays) {
+            if (cfg.traverse_ifif) shadow_kernel<true, true, true><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
+            else shadow_kernel<false, true, true><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
+        } else {
+            if (cfg.traverse_ifif) shadow_kernel<true, false, true><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
+            else shadow_kernel<false, false, true><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
+        }
+        return;
+    }
     if (cfg.sorted_rays) {
-        if (cfg.traverse_ifif) shadow_kernel<true, true><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
-        else shadow_kernel<false, true><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
+        if (cfg.traverse_ifif) shadow_kernel<true, true, false><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
+        else shadow_kernel<false, true, false><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
     } else {
-        if (cfg.traverse_ifif) shadow_kernel<true, false><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
-        else shadow_kernel<false, false><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
+        if (cfg.traverse_ifif) shadow_kernel<true, false, false><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
+        else shadow_kernel<false, false, false><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
     }
 }
 

@@ -46,9 +46,33 @@ __device__ __forceinline__ f3 eval_texture(const SceneDevice &scene, int tex, fl
 }
 __device__ __forceinline__ float eval_texture_float(const SceneDevice &scene, int tex, float2 uv) { return eval_texture(scene, tex, uv).x; }
 
+// texture3d/binary.cpp:17-42 as a postfix program; out of line, only reached by scenes that use "add" / "mul" 3-D textures
+__device__ __noinline__ f3 eval_texture3d_program(const Texture3DDesc *__restrict__ ops, int n_ops, f3 uvw) {
+    f3 stack[TEX3D_STACK];
+    int sp = 0;
+    for (int k = 0; k < n_ops; ++k) {
+        const Texture3DDesc &op = ops[k];
+        const int code = op.is_array;
+        if (code == TEX3D_CONST) {
+            stack[sp++] = f3(op.value[0], op.value[1], op.value[2]);
+        } else if (code == TEX3D_ARRAY) {
+            const float4 v = tex3D<float4>((cudaTextureObject_t)op.tex, uvw.x, uvw.y, uvw.z);
+            stack[sp++] = f3(v.x, v.y, v.z);
+        } else {
+            const f3 b = stack[--sp], a = stack[--sp];
+            stack[sp++] = code == TEX3D_ADD ? a + b : a * b;
+        }
+    }
+    return stack[0];
+}
+
+// T3P: the scene has "add" / "mul" 3-D textures (SceneDevice::has_medium == 2).  The kernels are instantiated for both cases so
+// that scenes without them run the code they ran before the programs existed (no call, same registers).
+template <bool T3P = false>
 __device__ __forceinline__ f3 eval_texture3d(const SceneDevice &scene, int tex, f3 uvw) {
     const Texture3DDesc &t = scene.textures3d[tex];
-    if (!t.is_array) return f3(t.value[0], t.value[1], t.value[2]);
+    if (t.is_array == TEX3D_CONST) return f3(t.value[0], t.value[1], t.value[2]);
+    if (T3P && t.is_array == TEX3D_PROGRAM) return eval_texture3d_program(scene.textures3d + (unsigned)t.tex, (int)(t.tex >> 32), uvw);
     const float4 v = tex3D<float4>((cudaTextureObject_t)t.tex, uvw.x, uvw.y, uvw.z);
     return f3(v.x, v.y, v.z);
 }
@@ -468,12 +492,13 @@ __device__ __forceinline__ float vol_overlap_inv_max_density(const SceneDevice &
 }
 
 // density sum of the overlap's members at parameter tf of segment a -> b (members' uvw are affine in the position)
+template <bool T3P = false>
 __device__ __forceinline__ float vol_density_sum(const SceneDevice &scene, const VolOverlap &ov, f3 a, f3 b, float tf) {
     float density_sum = 0.0f;
     for (int k = 0; k < ov.count; ++k) {
         const VolumePrim &v = scene.vol_prims[vol_member(ov, k)];
         const f3 uvw = vol_world_to_uvw(v, a) * (1.0f - tf) + vol_world_to_uvw(v, b) * tf;
-        density_sum = density_sum + eval_texture3d(scene, v.sigma_t_tex, uvw).x;
+        density_sum = density_sum + eval_texture3d<T3P>(scene, v.sigma_t_tex, uvw).x;
     }
     return density_sum;
 }
@@ -485,7 +510,7 @@ struct MediumSample {
 };
 
 // aggregate.cpp:129-199 (delta tracking over the summed densities; albedo = density-weighted mix, g = 0)
-template <typename S>
+template <bool T3P = false, typename S>
 __device__ __forceinline__ void vol_sample_scattering(const SceneDevice &scene, const VolOverlap &ov, f3 a, f3 b, S &sampler, MediumSample &r) {
     const float inv_max_density = vol_overlap_inv_max_density(scene, ov);
     const float t_max = length(b - a);
@@ -495,7 +520,7 @@ __device__ __forceinline__ void vol_sample_scattering(const SceneDevice &scene, 
         t = t + dt;
         if (t >= t_max) { r.scattered = false; return; }
         const float tf = t / t_max;
-        const float density_sum = vol_density_sum(scene, ov, a, b, tf);
+        const float density_sum = vol_density_sum<T3P>(scene, ov, a, b, tf);
         if (sampler.get1d() < density_sum * inv_max_density) {
             r.scattered = true;
             r.position = a * (1.0f - tf) + b * tf;
@@ -503,8 +528,8 @@ __device__ __forceinline__ void vol_sample_scattering(const SceneDevice &scene, 
             for (int k = 0; k < ov.count; ++k) {
                 const VolumePrim &v = scene.vol_prims[vol_member(ov, k)];
                 const f3 uvw = vol_world_to_uvw(v, a) * (1.0f - tf) + vol_world_to_uvw(v, b) * tf;
-                const float weight = eval_texture3d(scene, v.sigma_t_tex, uvw).x / density_sum;
-                albedo = albedo + weight * eval_texture3d(scene, v.albedo_tex, uvw);
+                const float weight = eval_texture3d<T3P>(scene, v.sigma_t_tex, uvw).x / density_sum;
+                albedo = albedo + weight * eval_texture3d<T3P>(scene, v.albedo_tex, uvw);
             }
             r.shader.g = 0.0f;
             r.shader.color = albedo;
@@ -514,7 +539,7 @@ __device__ __forceinline__ void vol_sample_scattering(const SceneDevice &scene, 
 }
 
 // aggregate.cpp:201-253 (ratio tracking)
-template <typename S>
+template <bool T3P = false, typename S>
 __device__ __forceinline__ float vol_tr_in_overlap(const SceneDevice &scene, const VolOverlap &ov, f3 a, f3 b, S &sampler) {
     const float inv_max_density = vol_overlap_inv_max_density(scene, ov);
     const float t_max = length(b - a);
@@ -523,12 +548,12 @@ __device__ __forceinline__ float vol_tr_in_overlap(const SceneDevice &scene, con
         const float dt = -logf(1.0f - sampler.get1d()) * inv_max_density;
         t = t + dt;
         if (t >= t_max) break;
-        result = result * (1.0f - vol_density_sum(scene, ov, a, b, t / t_max) * inv_max_density);
+        result = result * (1.0f - vol_density_sum<T3P>(scene, ov, a, b, t / t_max) * inv_max_density);
     }
     return result;
 }
 
-template <typename S>
+template <bool T3P = false, typename S>
 __device__ __noinline__ MediumSample volprim_sample(const SceneDevice &scene, f3 a, f3 b, S &sampler) {  // core/volume.cpp:112-160
     MediumSample r;
     r.scattered = false;
@@ -541,7 +566,7 @@ __device__ __noinline__ MediumSample volprim_sample(const SceneDevice &scene, f3
         if (!vol_find_closest_intersection(scene, o, b, inct_pos)) inct_pos = b;
         const VolOverlap ov = vol_get_overlap(scene, 0.5f * (o + inct_pos));
         if (ov.count != 0) {
-            vol_sample_scattering(scene, ov, o, inct_pos, sampler, r);
+            vol_sample_scattering<T3P>(scene, ov, o, inct_pos, sampler, r);
             if (r.scattered) break;
         }
         o = inct_pos + 0.001f * d;
@@ -549,7 +574,7 @@ __device__ __noinline__ MediumSample volprim_sample(const SceneDevice &scene, f3
     return r;
 }
 
-template <typename S>
+template <bool T3P = false, typename S>
 __device__ __noinline__ float volprim_tr(const SceneDevice &scene, f3 a, f3 b, S &sampler) {  // core/volume.cpp:162-195
     float result = 1.0f;
     if (scene.n_vol_prims == 0) return result;
@@ -560,17 +585,17 @@ __device__ __noinline__ float volprim_tr(const SceneDevice &scene, f3 a, f3 b, S
         f3 inct_pos;
         if (!vol_find_closest_intersection(scene, o, b, inct_pos)) inct_pos = b;
         const VolOverlap ov = vol_get_overlap(scene, 0.5f * (o + inct_pos));
-        if (ov.count != 0) result = result * vol_tr_in_overlap(scene, ov, o, inct_pos, sampler);
+        if (ov.count != 0) result = result * vol_tr_in_overlap<T3P>(scene, ov, o, inct_pos, sampler);
         o = inct_pos + 0.001f * d;
     }
     return result;
 }
 
-template <typename S>
+template <bool T3P = false, typename S>
 __device__ __forceinline__ MediumSample medium_sample(const SceneDevice &scene, const MediumDesc &m, f3 a, f3 b, S &sampler) {
     MediumSample r;
     r.scattered = false;
-    if (m.type == MED_VOLPRIM) return volprim_sample(scene, a, b, sampler);
+    if (m.type == MED_VOLPRIM) return volprim_sample<T3P>(scene, a, b, sampler);
     if (m.type == MED_HOMOGENEOUS) {  // homogeneous.cpp:25-58
         const float t_max = length(b - a);
         const float st = -logf(1.0f - sampler.get1d()) / m.sigma_t;
@@ -596,21 +621,21 @@ __device__ __forceinline__ MediumSample medium_sample(const SceneDevice &scene, 
         t = t + dt;
         if (t >= t_max) break;
         const f3 uvw = local_a + t * local_ba_div_t_max;
-        const float density = eval_texture3d(scene, m.sigma_t_tex, uvw).x;
+        const float density = eval_texture3d<T3P>(scene, m.sigma_t_tex, uvw).x;
         if (sampler.get1d() < density * inv_max_density) {
             r.scattered = true;
             r.position = a + t * ba_div_t_max;
-            r.shader.color = eval_texture3d(scene, m.albedo_tex, uvw);
-            r.shader.g = eval_texture3d(scene, m.g_tex, uvw).x;
+            r.shader.color = eval_texture3d<T3P>(scene, m.albedo_tex, uvw);
+            r.shader.g = eval_texture3d<T3P>(scene, m.g_tex, uvw).x;
             break;
         }
     }
     return r;
 }
 
-template <typename S>
+template <bool T3P = false, typename S>
 __device__ __forceinline__ f3 medium_tr(const SceneDevice &scene, const MediumDesc &m, f3 a, f3 b, S &sampler) {
-    if (m.type == MED_VOLPRIM) return f3(volprim_tr(scene, a, b, sampler));
+    if (m.type == MED_VOLPRIM) return f3(volprim_tr<T3P>(scene, a, b, sampler));
     if (m.type == MED_HOMOGENEOUS) {  // homogeneous.cpp:60-73: sigma_a = sigma_t * (1 - albedo)
         const f3 sigma_a = m.sigma_t * (f3(1.0f) - f3(m.albedo[0], m.albedo[1], m.albedo[2]));
         const f3 e = -length(a - b) * sigma_a;
@@ -628,7 +653,7 @@ __device__ __forceinline__ f3 medium_tr(const SceneDevice &scene, const MediumDe
         t = t + dt;
         if (t >= t_max) break;
         const f3 uvw = local_a + t * local_ba_div_t_max;
-        const float density = eval_texture3d(scene, m.sigma_t_tex, uvw).x;
+        const float density = eval_texture3d<T3P>(scene, m.sigma_t_tex, uvw).x;
         result = result * (1.0f - density * inv_max_density);
     }
     return f3(result);
@@ -657,11 +682,12 @@ __device__ __forceinline__ Sampler shadow_sampler(float4 o_med, float4 d_t1) {
 }
 
 // shadow.cpp:39-74: transmittance of an unoccluded shadow ray
+template <bool T3P = false>
 __device__ __forceinline__ f3 shadow_tr(const SceneDevice &scene, float4 o_med, float4 d_t1) {
     Sampler sm = shadow_sampler(o_med, d_t1);
     const f3 o = xyz(o_med), d = xyz(d_t1);
-    if (d_t1.w > 1.0f) return medium_tr(scene, scene.media[scene.vol_prim_medium_id], o, o + normalize(d) * scene.world_diagonal, sm);
-    return medium_tr(scene, scene.media[__float_as_uint(o_med.w)], o, o + d * d_t1.w, sm);
+    if (d_t1.w > 1.0f) return medium_tr<T3P>(scene, scene.media[scene.vol_prim_medium_id], o, o + normalize(d) * scene.world_diagonal, sm);
+    return medium_tr<T3P>(scene, scene.media[__float_as_uint(o_med.w)], o, o + d * d_t1.w, sm);
 }
 
 }  // namespace btrc

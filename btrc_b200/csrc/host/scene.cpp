@@ -208,7 +208,7 @@ static void load_text_grid(const std::string &filename, TextureSource &src) {
     src.is_float = true;
     src.channels = channels == 1 ? 1 : 4;
     src.f32.resize(n * src.channels);
-    for (int k = 0; k < 3; ++k) src.max_value[k] = -3.402823466e+38f;
+    for (int k = 0; k < 3; ++k) { src.max_value[k] = -3.402823466e+38f; src.min_value[k] = 3.402823466e+38f; }
     for (size_t i = 0; i < n; ++i) {
         for (int c = 0; c < channels; ++c) {
             char *end = nullptr;
@@ -216,10 +216,25 @@ static void load_text_grid(const std::string &filename, TextureSource &src) {
             if (end == p) throw Error("failed to load " + filename);
             p = end;
             src.f32[i * src.channels + c] = v;
-            if (c < 3) src.max_value[c] = std::max(src.max_value[c], v);
+            if (c < 3) { src.max_value[c] = std::max(src.max_value[c], v); src.min_value[c] = std::min(src.min_value[c], v); }
         }
         if (channels == 3) src.f32[i * 4 + 3] = 1.0f;
     }
+}
+
+// Texture3D::get_min_float / get_max_float: constant, array (texel extrema of the grid), add / mul by interval arithmetic on the
+// operands' extrema (texture3d/binary.cpp:95-137)
+float Scene::texture3d_extremum(int tex, bool want_max) const {
+    const Tex3DNode &t = textures3d[tex];
+    if (t.op == 0) {
+        if (!t.is_array) return t.value.x;
+        return want_max ? sources[t.source].max_value[0] : sources[t.source].min_value[0];
+    }
+    const float lmax = texture3d_extremum(t.lhs, true), lmin = texture3d_extremum(t.lhs, false);
+    const float rmax = texture3d_extremum(t.rhs, true), rmin = texture3d_extremum(t.rhs, false);
+    if (t.op == TEX3D_ADD) return want_max ? lmax + rmax : lmin + rmin;
+    if (want_max) return std::max(std::max(lmax * rmax, lmax * rmin), std::max(lmin * rmax, lmin * rmin));
+    return std::min(std::min(lmax * rmax, lmax * rmin), std::min(lmin * rmax, lmin * rmin));
 }
 
 int Scene::create_texture3d(const NodeP &node) {
@@ -240,6 +255,10 @@ int Scene::create_texture3d(const NodeP &node) {
                 sources.push_back(std::move(src));
                 t.is_array = true;
                 t.source = (int)sources.size() - 1;
+            } else if (type == "add" || type == "mul") {  // texture3d/binary.cpp:150-160 (lhs is created first)
+                t.op = type == "add" ? TEX3D_ADD : TEX3D_MUL;
+                t.lhs = create_texture3d(node->child("lhs"));
+                t.rhs = create_texture3d(node->child("rhs"));
             } else
                 throw Error("unknown texture3d type: " + type);
         }
@@ -341,8 +360,7 @@ int Scene::create_medium(const NodeP &node, const Mat4 *outer) {
                 m.desc.g_tex = (int)textures3d.size() - 1;
             }
             if (outer) { m.desc.has_transform = 1; mat4_to_3x4(*outer, m.desc.world_to_local); }
-            const Tex3DNode &st = textures3d[m.desc.sigma_t_tex];
-            const float mx = st.is_array ? sources[st.source].max_value[0] : st.value.x;
+            const float mx = texture3d_extremum(m.desc.sigma_t_tex, true);
             m.desc.inv_max_density = 1.0f / std::max(mx, 0.001f);  // hetergeneous.cpp:33-34
             media.push_back(m);
             handle = (int)media.size() - 1;
@@ -433,8 +451,7 @@ void Scene::create(const NodeP &root) {
                 vp.inv_x2 = 1.0f / x2; vp.inv_y2 = 1.0f / y2; vp.inv_z2 = 1.0f / z2;
                 vp.sigma_t_tex = create_texture3d(vol->child("sigma_t"));
                 vp.albedo_tex = create_texture3d(vol->child("albedo"));
-                const Tex3DNode &st = textures3d[vp.sigma_t_tex];
-                vp.max_sigma_t = st.is_array ? sources[st.source].max_value[0] : st.value.x;
+                vp.max_sigma_t = texture3d_extremum(vp.sigma_t_tex, true);
                 volume_prims.push_back(vp);
             }
         }
@@ -864,14 +881,35 @@ void Scene::upload_device() {
         }
     }
     dev.materials = upload(materials);
-    std::vector<Texture3DDesc> t3;
-    for (auto &t : textures3d) {
+    // 3-D textures: one descriptor per node; an add / mul node points at its postfix program, stored behind the node table
+    std::vector<Texture3DDesc> t3, t3_ops;
+    auto leaf3 = [&](const Tex3DNode &t) {
         Texture3DDesc d{};
-        d.is_array = t.is_array ? 1 : 0;
+        d.is_array = t.is_array ? TEX3D_ARRAY : TEX3D_CONST;
         d.value[0] = t.value.x; d.value[1] = t.value.y; d.value[2] = t.value.z;
         d.tex = t.is_array ? (unsigned long long)sources[t.source].tex : 0ull;
+        return d;
+    };
+    std::function<int(int, int)> emit3 = [&](int i, int depth) -> int {  // returns the value-stack depth the subtree needs
+        const Tex3DNode &t = textures3d[i];
+        if (t.op == 0) { t3_ops.push_back(leaf3(t)); return depth + 1; }
+        const int dl = emit3(t.lhs, depth), dr = emit3(t.rhs, depth + 1);
+        Texture3DDesc d{};
+        d.is_array = t.op;
+        t3_ops.push_back(d);
+        return std::max(dl, dr);
+    };
+    for (size_t i = 0; i < textures3d.size(); ++i) {
+        const Tex3DNode &t = textures3d[i];
+        if (t.op == 0) { t3.push_back(leaf3(t)); continue; }
+        const size_t first = t3_ops.size();
+        if (emit3((int)i, 0) > TEX3D_STACK) throw Error("texture3d expression is nested too deeply");
+        Texture3DDesc d{};
+        d.is_array = TEX3D_PROGRAM;
+        d.tex = (unsigned long long)(textures3d.size() + first) | ((unsigned long long)(t3_ops.size() - first) << 32);
         t3.push_back(d);
     }
+    t3.insert(t3.end(), t3_ops.begin(), t3_ops.end());
     dev.textures3d = upload(t3);
     {   // HaltonSampler::initialize_consts (builtin/sampler/halton.cpp:116-133) + the prime table (utils/prime.cpp)
         const int res[2] = {width, height};
@@ -907,6 +945,8 @@ void Scene::upload_device() {
     dev.vol_prims = volume_prims.empty() ? nullptr : upload(volume_prims);
     dev.n_vol_prims = (int)volume_prims.size();
     dev.has_medium = has_medium ? 1 : 0;
+    if (has_medium)  // 2: some 3-D texture is an "add" / "mul" node, the medium / shadow kernels must be the instantiations that run programs
+        for (const Tex3DNode &t : textures3d) if (t.op != 0) dev.has_medium = 2;
     dev.lights = upload(lights);
     dev.n_instances = (int)instance_info.size();
     // ---- environment light (core/light_sampler.cpp:24-33: appended after the area lights)

@@ -65,7 +65,7 @@ struct TextureSource {
     int address[3] = {0, 0, 0};  // 0 clamp, 1 wrap, 2 mirror, 3 border
     bool linear = true, srgb = false;
     float border[4] = {0, 0, 0, 0};
-    float max_value[3] = {0, 0, 0};  // Array::find_minmax_values
+    float max_value[3] = {0, 0, 0}, min_value[3] = {0, 0, 0};  // Array::find_minmax_values
     cudaArray_t array = nullptr;
     cudaTextureObject_t tex = 0;
 };
@@ -83,6 +83,8 @@ struct Tex3DNode {
     bool is_array = false;
     Vec3 value;
     int source = -1;
+    int op = 0;  // 0: leaf (constant / array); TEX3D_ADD / TEX3D_MUL: texture3d/binary.cpp
+    int lhs = -1, rhs = -1;
 };
 
 struct HostMedium {
@@ -165,6 +167,7 @@ private:
     int create_texture2d(const NodeP &node);
     int constant_texture2d(float v);
     int create_texture3d(const NodeP &node);
+    float texture3d_extremum(int tex, bool want_max) const;
     int create_material(const NodeP &node);
     int create_medium(const NodeP &node, const Mat4 *outer_world_to_local);
     void create_envir_light(const NodeP &node);

@@ -61,6 +61,9 @@ def lib():
         L.orc_eval_texture2d.argtypes = [c_void_p, c_int, c_int, POINTER(c_float), POINTER(c_float)]
         L.orc_add_texture3d_constant.argtypes = [c_void_p, c_float, c_float, c_float]
         L.orc_add_texture3d_array.argtypes = [c_void_p, c_int]
+        L.orc_add_texture3d_binary.argtypes = [c_void_p, c_int, c_int, c_int]
+        L.orc_texture3d_extremum.argtypes = [c_void_p, c_int, c_int]
+        L.orc_texture3d_extremum.restype = c_float
         L.orc_add_medium_homogeneous.argtypes = [c_void_p, c_float, POINTER(c_float), c_float]
         L.orc_add_medium_heterogeneous.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_float)]
         L.orc_add_volume.argtypes = [c_void_p] + [POINTER(c_float)] * 4 + [c_int, c_int]
@@ -732,6 +735,10 @@ class OracleScene:
                 vals = np.ascontiguousarray(vals, f32)
                 img = self.L.orc_add_image(self.h, w, h, d, 1 if ch == 1 else 4, _ptr(vals, c_float), 0, au, av, aw, linear, _ptr(border, c_float))
                 t = self.L.orc_add_texture3d_array(self.h, img)
+            elif ty in ("add", "mul"):  # texture3d/binary.cpp:150-160 (lhs is created first)
+                lhs = self.add_texture3d(node.child("lhs"))
+                rhs = self.add_texture3d(node.child("rhs"))
+                t = self.L.orc_add_texture3d_binary(self.h, 0 if ty == "add" else 1, lhs, rhs)
             else:
                 raise ValueError(f"unknown texture3d type: {ty}")
         self._pool[key] = t

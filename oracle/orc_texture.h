@@ -135,11 +135,12 @@ struct TextureSet {
     }
 };
 
-// ---- 3-D textures (constant or array; texture3d/array3d.cpp:29-41) -------------------------------------------
+// ---- 3-D textures (constant, array, add / mul of two; texture3d/array3d.cpp:29-41, texture3d/binary.cpp) -------
 struct Texture3D {
-    int type = TEX_CONSTANT;
+    int type = TEX_CONSTANT;  // TEX_CONSTANT, TEX_ARRAY, TEX_ADD, TEX_MUL
     V3 value{0, 0, 0};
     int image = -1;
+    int lhs = -1, rhs = -1;
 };
 
 }  // namespace orc

@@ -763,6 +763,10 @@ float eval_texture_float(const orc_scene &s, int tex, const SurfacePoint &sp) { 
 V3 eval_texture3d(const orc_scene &s, int tex, V3 uvw) {  // texture3d/array3d.cpp:29-41, core/texture3d.cpp (constant)
     const Texture3D &t = s.tex3d[tex];
     if (t.type == TEX_CONSTANT) return t.value;
+    if (t.type == TEX_ADD || t.type == TEX_MUL) {  // texture3d/binary.cpp:17-29
+        V3 a = eval_texture3d(s, t.lhs, uvw), b = eval_texture3d(s, t.rhs, uvw);
+        return t.type == TEX_ADD ? a + b : a * b;
+    }
     float o[4];
     sample_image(s.tex.images[t.image], uvw.x, uvw.y, uvw.z, o);
     return V3(o[0], o[1], o[2]);
@@ -1477,6 +1481,26 @@ int orc_add_texture3d_array(orc_scene *s, int image) {
     return (int)s->tex3d.size() - 1;
 }
 
+// Texture3DBinaryOperatorCreator (texture3d/binary.cpp:150-160): op 0 = "add", 1 = "mul"
+int orc_add_texture3d_binary(orc_scene *s, int op, int lhs, int rhs) {
+    Texture3D t; t.type = op == 0 ? TEX_ADD : TEX_MUL; t.lhs = lhs; t.rhs = rhs;
+    s->tex3d.push_back(t);
+    return (int)s->tex3d.size() - 1;
+}
+
+// Texture3D::get_min_float / get_max_float: constant (core/texture3d.cpp), array (texel extrema of the grid), add / mul by
+// interval arithmetic on the operands' extrema (texture3d/binary.cpp:95-137).  which = 0: min, 1: max.
+float orc_texture3d_extremum(const orc_scene *s, int tex, int which) {
+    const Texture3D &t = s->tex3d[tex];
+    if (t.type == TEX_CONSTANT) return t.value.x;
+    if (t.type == TEX_ARRAY) return which ? s->tex.images[t.image].max_value[0] : s->tex.images[t.image].min_value[0];
+    const float lmax = orc_texture3d_extremum(s, t.lhs, 1), lmin = orc_texture3d_extremum(s, t.lhs, 0);
+    const float rmax = orc_texture3d_extremum(s, t.rhs, 1), rmin = orc_texture3d_extremum(s, t.rhs, 0);
+    if (t.type == TEX_ADD) return which ? lmax + rmax : lmin + rmin;
+    if (which) return std::max(std::max(lmax * rmax, lmax * rmin), std::max(lmin * rmax, lmin * rmin));
+    return std::min(std::min(lmax * rmax, lmax * rmin), std::min(lmin * rmax, lmin * rmin));
+}
+
 // tex13: texture id per MatSlot (-1 where the material type has no such parameter)
 int orc_add_material(orc_scene *s, int type, const int *tex13, int normal_tex, int shadow_terminator) {
     Material m; m.type = type; m.normal_tex = normal_tex; m.shadow_terminator = shadow_terminator != 0;
@@ -1496,8 +1520,7 @@ int orc_add_medium_homogeneous(orc_scene *s, float sigma_t, const float *albedo,
 int orc_add_medium_heterogeneous(orc_scene *s, int sigma_t_tex, int albedo_tex, int g_tex, const float *world_to_local16) {
     Medium m; m.type = MED_HETEROGENEOUS; m.sigma_t_tex = sigma_t_tex; m.albedo_tex = albedo_tex; m.g_tex = g_tex;
     if (world_to_local16) { m.has_transform = true; std::memcpy(m.world_to_local.m, world_to_local16, 64); }
-    const Texture3D &t = s->tex3d[sigma_t_tex];
-    const float mx = t.type == TEX_CONSTANT ? t.value.x : s->tex.images[t.image].max_value[0];
+    const float mx = orc_texture3d_extremum(s, sigma_t_tex, 1);
     m.max_density = std::fmax(mx, 0.001f);  // hetergeneous.cpp:33
     s->media.push_back(m);
     return (int)s->media.size() - 1;
@@ -1511,8 +1534,7 @@ int orc_add_volume(orc_scene *s, const float *o, const float *x, const float *y,
     v.x_div_x2 = v.x / x2; v.y_div_y2 = v.y / y2; v.z_div_z2 = v.z / z2;
     v.inv_x2 = 1.0f / x2; v.inv_y2 = 1.0f / y2; v.inv_z2 = 1.0f / z2;
     v.sigma_t_tex = sigma_t_tex; v.albedo_tex = albedo_tex;
-    const Texture3D &t = s->tex3d[sigma_t_tex];
-    v.max_sigma_t = t.type == TEX_CONSTANT ? t.value.x : s->tex.images[t.image].max_value[0];
+    v.max_sigma_t = orc_texture3d_extremum(s, sigma_t_tex, 1);
     s->volumes.push_back(v);
     s->has_medium = true;  // core/scene.cpp:346-349
     return (int)s->volumes.size() - 1;
