@@ -307,6 +307,8 @@ LoadedImage load_png(const std::string &filename) {
         pass_dim(interlace ? adam7[i] : whole, pw, ph);
         if (pw > 0 && ph > 0) total += (((size_t)pw * bits + 7) / 8 + 1) * ph;
     }
+    // deflate expands by at most ~1030x: a size the IDAT data cannot fill is a damaged header, not a reason to allocate it
+    if (total > 1100ull * idat.size() + 64 || (uint64_t)w * (uint64_t)h > (1ull << 32)) throw bad;
     std::vector<uint8_t> raw(total);
     uLongf rawlen = (uLongf)raw.size();
     if (uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size()) != Z_OK || rawlen != raw.size()) throw bad;
@@ -429,6 +431,8 @@ static LoadedImage load_hdr(const std::string &filename) {
     l = getline();
     int w = 0, h = 0;
     if (std::sscanf(l.c_str(), "-Y %d +X %d", &h, &w) != 2 || w <= 0 || h <= 0) throw Error("unsupported hdr orientation: " + filename);
+    // a scanline takes at least 8 bytes per 127 pixels (run-length coded): sizes the file cannot hold are a damaged header
+    if ((uint64_t)w * (uint64_t)h > 64ull * buf.size() + 64) throw Error("failed to load image: " + filename);
     LoadedImage img;
     img.width = w; img.height = h; img.channels = 3; img.is_float = true;
     img.f32.resize((size_t)w * h * 3);
@@ -540,6 +544,7 @@ static LoadedImage load_jpg(const std::string &filename) {
     };
     auto getbits = [&](int n) -> int {
         if (n == 0) return 0;
+        if (n > 16) throw fail("bad bit count");  // a magnitude category from a damaged Huffman table
         fill();
         const int v = (int)(acc >> (32 - n));
         acc <<= n; nb -= n;
@@ -694,6 +699,8 @@ static LoadedImage load_jpg(const std::string &filename) {
             if (nc == 1) comps[0].h = comps[0].v = 1;  // a single component is never interleaved: its sampling factors do not matter
             for (auto &c : comps) { hmax = std::max(hmax, c.h); vmax = std::max(vmax, c.v); }
             mcux = (width + 8 * hmax - 1) / (8 * hmax); mcuy = (height + 8 * vmax - 1) / (8 * vmax);
+            // every block costs at least one bit in its first scan: more blocks than bits is a damaged header
+            if ((uint64_t)mcux * (uint64_t)mcuy > 8ull * buf.size()) throw fail("image size does not fit the file");
             for (auto &c : comps) {
                 c.nbx = mcux * c.h; c.nby = mcuy * c.v;
                 c.bw = c.nbx * 8; c.bh = c.nby * 8;
