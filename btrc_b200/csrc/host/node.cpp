@@ -131,7 +131,15 @@ struct JsonReader {
         ++i;
         return out;
     }
+    int depth = 0;
+    struct DepthGuard {
+        int &d;
+        explicit DepthGuard(int &dd) : d(dd) { ++d; }
+        ~DepthGuard() { --d; }
+    };
     NodeP parse_value() {
+        DepthGuard guard(depth);
+        if (depth > 512) fail("nesting too deep");  // recursion bound: a damaged file must not overflow the stack
         skip_ws();
         if (i >= s.size()) fail("unexpected end of input");
         auto n = std::make_shared<Node>();
@@ -216,7 +224,7 @@ bool parse_index(const std::string &s, size_t &out) {
     return true;
 }
 
-NodeP find_node(std::vector<NodeP> &cur_path, const std::string &path);
+NodeP find_node(std::vector<NodeP> &cur_path, const std::string &path, int hops = 0);
 
 void resolve_references(std::vector<NodeP> &cur_path, NodeP &node) {  // parser.cpp:135-165
     if (node->is_group()) {
@@ -231,12 +239,16 @@ void resolve_references(std::vector<NodeP> &cur_path, NodeP &node) {  // parser.
         const std::string &str = node->value;
         if (str.rfind("$reference{", 0) == 0) {
             if (str.back() != '}') throw Error("'}' for '$reference{' is not found");
-            node = find_node(cur_path, str.substr(11, str.size() - 12));
+            NodeP target = find_node(cur_path, str.substr(11, str.size() - 12));
+            // a reference to one of its own ancestors would make the tree cyclic (the reference recurses until it crashes)
+            for (const NodeP &a : cur_path) if (a == target) throw Error("cyclic $reference: " + str);
+            node = target;
         }
     }
 }
 
-NodeP find_node(std::vector<NodeP> &cur_path, const std::string &path) {  // parser.cpp:167-252
+NodeP find_node(std::vector<NodeP> &cur_path, const std::string &path, int hops) {  // parser.cpp:167-252
+    if (hops > 64) throw Error("cyclic $reference: " + path);
     const auto secs = split_path(path);
     if (secs.empty()) throw Error("invalid node path: " + path);
     const std::string &start = secs.front();
@@ -269,7 +281,7 @@ NodeP find_node(std::vector<NodeP> &cur_path, const std::string &path) {  // par
     if (node->is_value() && node->value.find("$reference{") != std::string::npos) {
         const std::string &str = node->value;
         if (str.back() != '}') throw Error("'}' for '$reference{' is not found");
-        node = find_node(cur_path, str.substr(11, str.size() - 12));
+        node = find_node(cur_path, str.substr(11, str.size() - 12), hops + 1);
     }
     return node;
 }
@@ -286,9 +298,10 @@ std::string read_text_file(const std::string &filename) {
 
 NodeP parse_scene_text(std::string src, const std::string &include_dir) {
     namespace fs = std::filesystem;
-    for (;;) {  // parser.cpp:106-133
+    for (int expansions = 0;; ++expansions) {  // parser.cpp:106-133
         size_t beg = src.find("\"$include{");
         if (beg == std::string::npos) break;
+        if (expansions > 4096 || src.size() > (1u << 28)) throw Error("too many '$include's (a file that includes itself?)");
         beg += 10;
         const size_t end = src.find("}\"", beg);
         if (end == std::string::npos) throw Error("failed to find the enclosing '}' of a '$include{'");

@@ -203,7 +203,9 @@ static void load_text_grid(const std::string &filename, TextureSource &src) {
     if (channels != 1 && channels != 3 && channels != 4) throw Error("unsupported channel count: " + std::to_string(channels));
     if (std::string(comp) == "byte") throw Error("byte text grids are not supported (the reference reads them as characters into SNorm8: SURVEY B.5)");
     if (std::string(comp) != "float") throw Error(std::string("unknown component type: ") + comp);
+    if (w <= 0 || h <= 0 || d <= 0) throw Error("Array::load_from_text: failed to parse file head");
     const size_t n = (size_t)w * h * d;
+    if (n * (size_t)channels > text.size()) throw Error("failed to load " + filename);  // every value takes at least two characters: the file cannot hold that grid
     src.width = w; src.height = h; src.depth = d;
     src.is_float = true;
     src.channels = channels == 1 ? 1 : 4;

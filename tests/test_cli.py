@@ -34,6 +34,40 @@ def test_usage_and_errors(built, tmp_path):
     assert len(lines) >= 2                                            # chained: the context lines of the nested exceptions
 
 
+def test_damaged_scene_files_are_errors_not_crashes(built, tmp_path):
+    """Scene files are outside input: unbounded nesting, a $reference to itself or to an ancestor, a file that $includes itself and a
+    grid header larger than its file all end in exit code -1 with a message (the reference recurses until the stack overflows)."""
+    from btrc_b200 import scenes
+
+    def run(path):
+        r = subprocess.run([CLI, str(path)], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 255, (path, r.returncode, r.stderr[-300:])   # -1, not a signal
+        return r.stderr
+
+    (tmp_path / "deep.json").write_text("[" * 200000)
+    assert "nesting too deep" in run(tmp_path / "deep.json")
+    (tmp_path / "deep2.json").write_text('{"a":' * 100000 + "1" + "}" * 100000)
+    assert "nesting too deep" in run(tmp_path / "deep2.json")
+    (tmp_path / "self.json").write_text('{"a": "$reference{a}"}')
+    assert "cyclic $reference" in run(tmp_path / "self.json")
+    (tmp_path / "anc.json").write_text('{"c": {"d": "$reference{c}"}}')
+    assert "cyclic $reference" in run(tmp_path / "anc.json")
+    (tmp_path / "inc.json").write_text('{"a": "$include{inc.json}"}')
+    assert "$include" in run(tmp_path / "inc.json")
+    path = scenes.make_medium_scene(str(tmp_path / "m"), width=8, height=8, spp=1, grid_res=4, state_count=64)
+    grid = tmp_path / "m" / "density.txt"
+    grid.write_text("float 1 4000 4000 4000\n" + grid.read_text().split("\n", 1)[1])
+    assert "failed to load" in run(path)
+    # shared subtrees are not cycles: two entities referencing one material still load (and then fail only for want of a GPU, or render)
+    path = scenes.make_cornell(str(tmp_path / "c"), width=8, height=8, spp=1, state_count=64)
+    root = json.load(open(path))
+    root["scene"]["entities"][1]["material"] = "$reference{$root/scene/entities/0/material}"
+    root["scene"]["entities"][2]["material"] = "$reference{entities/1/material}"   # a reference to a reference
+    json.dump(root, open(path, "w"))
+    r = subprocess.run([CLI, path], capture_output=True, text=True, timeout=120)
+    assert "cyclic" not in r.stderr and "invalid node path" not in r.stderr
+
+
 @pytest.mark.gpu
 def test_cli_renders_and_saves(built, tmp_path):
     from btrc_b200 import api, scenes
