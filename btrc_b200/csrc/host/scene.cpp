@@ -520,6 +520,11 @@ void Scene::create(const NodeP &root) {
                     d.normal = nn.empty() ? "" : resolve_path(nn);
                 } else if (d.type == "tonemap") {
                     d.exposure = n->float_or("exposure", 1.0f);
+                } else if (d.type == "denoise") {
+                    // postprocess/optix_denoiser.cpp: NVIDIA's closed-source OptiX AI denoiser.  There is no OptiX in this renderer
+                    // (out of scope); say so instead of "unknown", the name is a registered creator in the reference.
+                    throw Error("post_processor 'denoise' is the OptiX AI denoiser, which this OptiX-free renderer does not provide; "
+                                "remove it from \"post_processors\" (albedo / normal outputs for an external denoiser: \"save\")");
                 } else
                     throw Error("unknown post_processor type: " + d.type);
                 post_processors.push_back(d);

@@ -32,6 +32,12 @@ def test_usage_and_errors(built, tmp_path):
     lines = [l for l in r.stderr.splitlines() if l.strip()]
     assert any("unknown material type: velvet" in l for l in lines)   # factory/context.h:190-196 wording
     assert len(lines) >= 2                                            # chained: the context lines of the nested exceptions
+    # the one registered creator that is out of scope (postprocess/optix_denoiser.h:34) is named as such, not as "unknown"
+    root["scene"]["entities"][0]["material"]["type"] = "diffuse"
+    root["post_processors"] = [{"type": "denoise"}, {"type": "save", "color": "x.png"}]
+    json.dump(root, open(bad, "w"))
+    r = subprocess.run([CLI, bad], capture_output=True, text=True)
+    assert r.returncode == 255 and "OptiX AI denoiser" in r.stderr
 
 
 def test_damaged_scene_files_are_errors_not_crashes(built, tmp_path):
