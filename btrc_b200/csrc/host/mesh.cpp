@@ -81,6 +81,65 @@ Vec3 triangle_dpdu(Vec3 B_A, Vec3 C_A, Vec2 b_a, Vec2 c_a, Vec3 nor) {  // utils
     return normalize(m11 * inv_det * B_A - m01 * inv_det * C_A);
 }
 
+// Polygons with more than four corners: tinyobj's built-in ear clipping (lib/tinyobjloader/tiny_obj_loader.h:1521-1813), restated
+// so that triangle order and corner order - the primitive ids - are the reference's.  The polygon is projected on two coordinate
+// axes chosen from its first non-degenerate corner; a candidate ear (three consecutive corners from a moving start) is taken
+// when its turn agrees in sign with tinyobj's "area" term and no other remaining corner lies inside it (even-odd test); the
+// middle corner is then removed.  The search gives up after a full round without progress, as tinyobj does (the rest of such a
+// polygon is dropped).  Arithmetic in float, in tinyobj's order.
+bool point_in_triangle_2d(const float *vx, const float *vy, float tx, float ty) {  // pnpoly, tiny_obj_loader.h:1387-1398
+    bool inside = false;
+    for (int i = 0, j = 2; i < 3; j = i++)
+        if (((vy[i] > ty) != (vy[j] > ty)) && (tx < (vx[j] - vx[i]) * (ty - vy[i]) / (vy[j] - vy[i]) + vx[i])) inside = !inside;
+    return inside;
+}
+
+void ear_clip(const std::vector<Corner> &face, const std::vector<Vec3> &vs, std::vector<Corner> &out) {
+    const size_t n = face.size();
+    int ax0 = 1, ax1 = 2;
+    for (size_t k = 0; k < n; ++k) {
+        const Vec3 a = vs[face[k].v], b = vs[face[(k + 1) % n].v], c = vs[face[(k + 2) % n].v];
+        const Vec3 e0 = b - a, e1 = c - b;
+        const float cx = std::fabs(e0.y * e1.z - e0.z * e1.y), cy = std::fabs(e0.z * e1.x - e0.x * e1.z), cz = std::fabs(e0.x * e1.y - e0.y * e1.x);
+        const float eps = 1.1920928955078125e-07f;
+        if (cx > eps || cy > eps || cz > eps) {
+            if (!(cx > cy && cx > cz)) {
+                ax0 = 0;
+                if (cz > cx && cz > cy) ax1 = 1;
+            }
+            break;
+        }
+    }
+    auto coord = [&](const Corner &c, int axis) { const Vec3 &v = vs[c.v]; return axis == 0 ? v.x : axis == 1 ? v.y : v.z; };
+    std::vector<Corner> rem = face;
+    size_t start = 0, budget = n, last_count = n;
+    while (rem.size() > 3 && budget > 0) {
+        const size_t m = rem.size();
+        if (start >= m) start -= m;
+        if (last_count != m) { last_count = m; budget = m; }
+        else --budget;
+        Corner tri[3];
+        float vx[3], vy[3];
+        for (int k = 0; k < 3; ++k) {
+            tri[k] = rem[(start + k) % m];
+            vx[k] = coord(tri[k], ax0); vy[k] = coord(tri[k], ax1);
+        }
+        const float e0x = vx[1] - vx[0], e0y = vy[1] - vy[0], e1x = vx[2] - vx[1], e1y = vy[2] - vy[1];
+        const float turn = e0x * e1y - e0y * e1x;
+        const float area = (vx[0] * vy[1] - vy[0] * vx[1]) * 0.5f;
+        if (turn * area < 0.0f) { ++start; continue; }
+        bool blocked = false;
+        for (size_t other = 3; other < m && !blocked; ++other) {
+            const Corner &q = rem[(start + other) % m];
+            blocked = point_in_triangle_2d(vx, vy, coord(q, ax0), coord(q, ax1));
+        }
+        if (blocked) { ++start; continue; }
+        out.push_back(tri[0]); out.push_back(tri[1]); out.push_back(tri[2]);
+        rem.erase(rem.begin() + (long)((start + 1) % m));
+    }
+    if (rem.size() == 3) out.insert(out.end(), rem.begin(), rem.end());
+}
+
 }  // namespace
 
 MeshData load_triangle_mesh(const std::string &filename, bool to_unit_cube) {
@@ -133,10 +192,7 @@ MeshData load_triangle_mesh(const std::string &filename, bool to_unit_cube) {
                     for (int k : {0, 1, 3, 1, 2, 3}) corners.push_back(face[k]);
                 }
             } else if (face.size() > 4) {
-                // The reference ear-clips larger polygons; a fan gives the same surface for convex faces.
-                for (size_t k = 1; k + 1 < face.size(); ++k) {
-                    corners.push_back(face[0]); corners.push_back(face[k]); corners.push_back(face[k + 1]);
-                }
+                ear_clip(face, vs, corners);
             }
         }
         while (*p && *p != '\n') ++p;

@@ -484,13 +484,73 @@ def load_obj(filename: str):
     return _OBJ_CACHE[key]
 
 
+def _ear_clip(face, vs):
+    """tinyobj's built-in ear clipping for polygons with more than four corners (tiny_obj_loader.h:1521-1813), float arithmetic
+    in its order: projection axes from the first non-degenerate corner, candidate ears from a moving start, accepted when
+    turn * "area" >= 0 and no other remaining corner is inside (pnpoly, :1387-1398); gives up after a round without progress."""
+    n = len(face)
+    P = [np.array(vs[c[0]], f32) for c in face]
+    ax0, ax1 = 1, 2
+    eps = f32(np.finfo(f32).eps)
+    for k in range(n):
+        a, b, c = P[k], P[(k + 1) % n], P[(k + 2) % n]
+        e0, e1 = (b - a).astype(f32), (c - b).astype(f32)
+        cx = abs(f32(f32(e0[1] * e1[2]) - f32(e0[2] * e1[1])))
+        cy = abs(f32(f32(e0[2] * e1[0]) - f32(e0[0] * e1[2])))
+        cz = abs(f32(f32(e0[0] * e1[1]) - f32(e0[1] * e1[0])))
+        if cx > eps or cy > eps or cz > eps:
+            if not (cx > cy and cx > cz):
+                ax0 = 0
+                if cz > cx and cz > cy:
+                    ax1 = 1
+            break
+
+    def inside(vx, vy, tx, ty):
+        c = False
+        j = 2
+        for i in range(3):
+            if (vy[i] > ty) != (vy[j] > ty):
+                if tx < f32(f32(f32(f32(vx[j] - vx[i]) * f32(ty - vy[i])) / f32(vy[j] - vy[i])) + vx[i]):
+                    c = not c
+            j = i
+        return c
+
+    rem = list(range(n))
+    out = []
+    start, budget, last = 0, n, n
+    while len(rem) > 3 and budget > 0:
+        m = len(rem)
+        if start >= m:
+            start -= m
+        if last != m:
+            last, budget = m, m
+        else:
+            budget -= 1
+        tri = [rem[(start + k) % m] for k in range(3)]
+        vx = [f32(P[t][ax0]) for t in tri]
+        vy = [f32(P[t][ax1]) for t in tri]
+        e0x, e0y, e1x, e1y = f32(vx[1] - vx[0]), f32(vy[1] - vy[0]), f32(vx[2] - vx[1]), f32(vy[2] - vy[1])
+        turn = f32(f32(e0x * e1y) - f32(e0y * e1x))
+        area = f32(f32(f32(vx[0] * vy[1]) - f32(vy[0] * vx[1])) * f32(0.5))
+        if f32(turn * area) < 0:
+            start += 1
+            continue
+        if any(inside(vx, vy, f32(P[rem[(start + o) % m]][ax0]), f32(P[rem[(start + o) % m]][ax1])) for o in range(3, m)):
+            start += 1
+            continue
+        out += [face[t] for t in tri]
+        del rem[(start + 1) % m]
+    if len(rem) == 3:
+        out += [face[t] for t in rem]
+    return out
+
+
 def _load_obj(filename: str):
     """tinyobj (triangulate=true) + TriangleMeshLoader: returns per-corner arrays in face order.
 
     pos (ntri*3, 3) f32, nor (ntri*3, 3) f32, has_nor (ntri*3) u8, uv (ntri*3, 2) f32.
     Triangles stay as they are, quads split along the shorter diagonal (tiny_obj_loader.h:1429-1520);
-    larger polygons are fan-triangulated (the reference ear-clips; convex polygons give the same set
-    of triangles only up to ordering, so the synthetic scenes never contain them).
+    larger polygons go through tinyobj's ear clipping (_ear_clip).
     """
     vs, vns, vts = [], [], []
     corners = []  # (vi, ti, ni)
@@ -529,8 +589,7 @@ def _load_obj(filename: str):
                     else:
                         corners += [face[0], face[1], face[3], face[1], face[2], face[3]]
                 elif len(face) > 4:
-                    for k in range(1, len(face) - 1):
-                        corners += [face[0], face[k], face[k + 1]]
+                    corners += _ear_clip(face, vs)
     n = len(corners)
     pos = np.zeros((n, 3), f32)
     nor = np.zeros((n, 3), f32)

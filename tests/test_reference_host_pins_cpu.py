@@ -137,7 +137,47 @@ def _write_tricky_obj(path):
     open(path, "w").write("\n".join(lines) + "\n")
 
 
-@pytest.mark.parametrize("case", ["cornell", "sphere", "tricky", "tricky_unit_cube"])
+def _write_polygon_obj(path):
+    """Faces with 5-12 corners, the ones tinyobj ear-clips: star-shaped (concave) outlines in random planes with a little
+    out-of-plane noise, convex ones, outlines with collinear runs and repeated points, and random (self-intersecting) loops that
+    make the ear search give up part of the way."""
+    rng = np.random.default_rng(31)
+    lines, nv = [], 0
+    for t in rng.uniform(0, 1, (16, 2)):
+        lines.append("vt %.6f %.6f" % tuple(t))
+    for f in range(60):
+        n = int(rng.integers(5, 13))
+        kind = f % 5
+        ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+        if kind == 0:      # concave star
+            r = rng.uniform(0.3, 1.0, n)
+        elif kind == 1:    # convex
+            r = np.ones(n)
+        elif kind == 2:    # clockwise star
+            r = rng.uniform(0.3, 1.0, n); ang = ang[::-1]
+        else:
+            r = rng.uniform(0.3, 1.0, n)
+        pts2 = np.stack([r * np.cos(ang), r * np.sin(ang)], 1)
+        if kind == 3:      # collinear run + a repeated point
+            pts2[1] = 0.5 * (pts2[0] + pts2[2]); pts2[-1] = pts2[-2]
+        if kind == 4:      # random loop
+            pts2 = rng.uniform(-1, 1, (n, 2))
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        pts = pts2 @ q[:2] + rng.normal(0, 0.02, (n, 1)) * q[2] + rng.uniform(-2, 2, 3)
+        for v in pts:
+            lines.append("v %.6f %.6f %.6f" % tuple(v))
+        idx = [nv + 1 + k for k in range(n)]
+        nv += n
+        if f % 3 == 0:
+            lines.append("f " + " ".join("%d/%d" % (i, 1 + (i % 16)) for i in idx))
+        elif f % 3 == 1:
+            lines.append("f " + " ".join(str(i - nv - 1) for i in idx))   # negative indices
+        else:
+            lines.append("f " + " ".join(str(i) for i in idx))
+    open(path, "w").write("\n".join(lines) + "\n")
+
+
+@pytest.mark.parametrize("case", ["cornell", "sphere", "tricky", "tricky_unit_cube", "polygons"])
 def test_mesh_loader_matches_reference(R, built, tmp_path, case):
     """Oracle front-end (oracle/front.py + liborc) and the product's host loader against TriangleMeshLoader: same triangles in
     the same order, bit-identical positions and shading tables."""
@@ -152,6 +192,9 @@ def test_mesh_loader_matches_reference(R, built, tmp_path, case):
         v, f, uv, n = scenes.uv_sphere(9, 14)
         objs = [os.path.join(str(tmp_path), "sphere.obj")]
         scenes.write_obj(objs[0], v, f, uv, n)
+    elif case == "polygons":
+        objs = [os.path.join(str(tmp_path), "polygons.obj")]
+        _write_polygon_obj(objs[0])
     else:
         objs = [os.path.join(str(tmp_path), "tricky.obj")]
         _write_tricky_obj(objs[0])
