@@ -568,7 +568,7 @@ def _load_obj(filename: str):
             elif tok[0] == "vn":
                 vns.append([f32(float(t)) for t in tok[1:4]])
             elif tok[0] == "vt":
-                vts.append([f32(float(t)) for t in tok[1:3]])
+                vts.append(([f32(float(t)) for t in tok[1:3]] + [f32(0), f32(0)])[:2])  # a missing v is 0 (tinyobj parseReal2 default)
             elif tok[0] == "f":
                 face = []
                 for t in tok[1:]:

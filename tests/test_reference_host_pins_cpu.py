@@ -177,7 +177,17 @@ def _write_polygon_obj(path):
     open(path, "w").write("\n".join(lines) + "\n")
 
 
-@pytest.mark.parametrize("case", ["cornell", "sphere", "tricky", "tricky_unit_cube", "polygons"])
+SYNTAX_CASES = {  # OBJ spellings tinyobj accepts: CRLF, tabs and trailing blanks, exponents, ignored statements, no final newline, short / long vt and v
+    "crlf": "# comment\r\nv 0 0 0\r\nv 1 0 0\r\nv 0 1 0\r\nv 1 1 0.5\r\nvt 0.1 0.2\r\nvn 0 0 1\r\nf 1/1/1 2/1/1 3/1/1\r\nf 2 4 3\r\n",
+    "tabs": "v\t0 0 0\nv 1\t0 0   \nv  0   1 0\nv 1 1 1 0.5 0.5 0.5\nf\t1 2 3  \nf 2  4\t3\n\n\n",
+    "exp": "v 1e-1 2.5E+0 -3.e0\nv +1 .5 0\nv 0 1 0\nf 1 2 3\n",
+    "extra": "mtllib x.mtl\no obj\ng grp\nusemtl m\ns 1\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvp 0.1 0.2\nl 1 2\np 1\nf 1 2 3\ns off\nf 3 2 1\n",
+    "noeol": "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3",
+    "vtw": "v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0.25 0.5 0.75\nvt 1\nf 1/1 2/2 3/1\n",
+}
+
+
+@pytest.mark.parametrize("case", ["cornell", "sphere", "tricky", "tricky_unit_cube", "polygons", "syntax"])
 def test_mesh_loader_matches_reference(R, built, tmp_path, case):
     """Oracle front-end (oracle/front.py + liborc) and the product's host loader against TriangleMeshLoader: same triangles in
     the same order, bit-identical positions and shading tables."""
@@ -192,6 +202,11 @@ def test_mesh_loader_matches_reference(R, built, tmp_path, case):
         v, f, uv, n = scenes.uv_sphere(9, 14)
         objs = [os.path.join(str(tmp_path), "sphere.obj")]
         scenes.write_obj(objs[0], v, f, uv, n)
+    elif case == "syntax":
+        objs = []
+        for name, text in SYNTAX_CASES.items():
+            objs.append(os.path.join(str(tmp_path), name + ".obj"))
+            open(objs[-1], "wb").write(text.encode())
     elif case == "polygons":
         objs = [os.path.join(str(tmp_path), "polygons.obj")]
         _write_polygon_obj(objs[0])
