@@ -83,6 +83,8 @@ def lib():
         L.btrc_ibl_table.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]
         L.btrc_set_reporter.argtypes = [c_void_p, PROGRESS_FN, c_void_p]
         L.btrc_image_load.argtypes = [c_char_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_void_p, c_uint64]
+        L.btrc_scene_file_dump.argtypes = [c_char_p, c_void_p, c_uint64, POINTER(c_uint64)]
+        L.btrc_scene_file_parse.argtypes = [c_char_p, c_char_p, c_int32, c_void_p, POINTER(c_int32)]
         L.btrc_device_sm_count.restype = c_int
         _lib = L
     return _lib
@@ -292,6 +294,27 @@ def load_image(path):
     out = np.zeros((h.value, w.value, c.value), np.float32 if isf.value else np.uint8)
     _check(L.btrc_image_load(path.encode(), byref(w), byref(h), byref(c), byref(isf), out.ctypes.data, out.nbytes))
     return out
+
+
+def scene_file_dump(path):
+    """The parsed + resolved scene file as canonical text (factory/node/parser.cpp; host only)."""
+    L = lib()
+    need = c_uint64(0)
+    _check(L.btrc_scene_file_dump(path.encode(), None, 0, byref(need)))
+    buf = ctypes.create_string_buffer(need.value)
+    _check(L.btrc_scene_file_dump(path.encode(), buf, need.value, byref(need)))
+    return buf.value.decode()
+
+
+PARSE_KINDS = {"int": 0, "float": 1, "bool": 2, "vec3": 3, "spectrum": 4, "degree": 5, "radian": 6, "transform3d": 7, "transform2d": 8}
+
+
+def scene_file_parse(path, node_path, kind):
+    """Node::parse<T> of the node at node_path (factory/node/node.cpp:276-325; host only). Returns a float32 array."""
+    out = np.zeros(16, np.float32)
+    n = c_int32(0)
+    _check(lib().btrc_scene_file_parse(path.encode(), node_path.encode(), PARSE_KINDS[kind], out.ctypes.data, byref(n)))
+    return out[:n.value].copy()
 
 
 def render_file(path, **kw):

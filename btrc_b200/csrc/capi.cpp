@@ -286,6 +286,79 @@ int btrc_image_load(const char *path, int32_t *width, int32_t *height, int32_t *
     });
 }
 
+namespace {
+// Canonical text of a parsed + resolved scene file: groups in first-insertion key order {"k":v,...}, arrays [v,...], values "text"
+void dump_node(const NodeP &n, std::string &out, int depth) {
+    if (depth > 200) { out += "<deep>"; return; }
+    if (n->is_group()) {
+        out += "{";
+        bool first = true;
+        for (const auto &kv : n->children) {
+            if (!first) out += ",";
+            first = false;
+            out += "\"" + kv.first + "\":";
+            dump_node(kv.second, out, depth + 1);
+        }
+        out += "}";
+    } else if (n->is_array()) {
+        out += "[";
+        for (size_t i = 0; i < n->elements.size(); ++i) {
+            if (i) out += ",";
+            dump_node(n->elements[i], out, depth + 1);
+        }
+        out += "]";
+    } else
+        out += "\"" + n->value + "\"";
+}
+}  // namespace
+
+int btrc_scene_file_dump(const char *path, char *out, uint64_t out_bytes, uint64_t *needed) {
+    return guarded([&] {
+        if (!path) throw Error("null path");
+        std::string text;
+        dump_node(parse_scene_file(path), text, 0);
+        if (needed) *needed = text.size() + 1;
+        if (!out) return;
+        if (out_bytes < text.size() + 1) throw Error("btrc_scene_file_dump: buffer too small");
+        std::memcpy(out, text.c_str(), text.size() + 1);
+    });
+}
+
+int btrc_scene_file_parse(const char *path, const char *node_path, int32_t kind, float *out, int32_t *count) {
+    return guarded([&] {
+        if (!path || !node_path || !out) throw Error("null argument");
+        NodeP n = parse_scene_file(path);
+        std::string cur;
+        auto step = [&](const std::string &sec) {
+            if (sec.empty()) return;
+            if (n->is_array()) {
+                const size_t i = std::stoul(sec);
+                if (i >= n->elements.size()) throw Error("invalid node path: " + std::string(node_path));
+                n = n->elements[i];
+            } else
+                n = n->child(sec);
+        };
+        for (const char *p = node_path; *p; ++p) {
+            if (*p == '/') { step(cur); cur.clear(); }
+            else cur += *p;
+        }
+        step(cur);
+        int c = 1;
+        switch (kind) {
+        case 0: out[0] = (float)n->as_int(); break;
+        case 1: out[0] = n->as_float(); break;
+        case 2: out[0] = n->as_bool() ? 1.0f : 0.0f; break;
+        case 3: case 4: { const Vec3 v = n->as_vec3(); out[0] = v.x; out[1] = v.y; out[2] = v.z; c = 3; break; }
+        case 5: out[0] = n->as_degree(); break;
+        case 6: out[0] = n->as_radian(); break;
+        case 7: { const Transform3D t = n->as_transform3d(); for (int r = 0; r < 4; ++r) for (int k = 0; k < 4; ++k) out[4 * r + k] = t.mat.m[r][k]; c = 16; break; }
+        case 8: { const Mat3 t = n->as_transform2d(); for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) out[3 * r + k] = t.m[r][k]; c = 9; break; }
+        default: throw Error("btrc_scene_file_parse: unknown kind");
+        }
+        if (count) *count = c;
+    });
+}
+
 int btrc_run_post_processors(btrc_scene_t *s, int memory, float *color, float *albedo, float *normal) {
     (void)memory;
     return guarded([&] {

@@ -109,6 +109,15 @@ int btrc_run_post_processors(btrc_scene_t *scene, int memory, float *color, floa
  * width*height*3 floats (.hdr, *is_float = 1).  Host memory, no device involved. */
 int btrc_image_load(const char *path, int32_t *width, int32_t *height, int32_t *channels, int32_t *is_float, void *out, uint64_t out_bytes);
 
+/* The scene-file layer on its own (factory/node/parser.cpp:16-252: comments, "$include{..}", "$reference{..}", the std::to_string(float)
+ * round trip; factory/node/node.cpp:14-325: typed values), host only - what the parity tests compare with the reference's own parser
+ * built under oracle/_ref.  btrc_scene_file_dump writes the resolved tree as text: groups {"key":v,...} in first-insertion key order,
+ * arrays [v,...], values "text"; call with out = NULL to get the size in *needed.  btrc_scene_file_parse reads the node at node_path
+ * ("a/b/0/c" from the root) as Node::parse<T>: kind 0 int, 1 float, 2 bool, 3 Vec3f, 4 Spectrum, 5 Degree, 6 Radian,
+ * 7 Transform3D (16 floats, row-major forward matrix), 8 Transform2D (9 floats, row-major); *count = floats written. */
+int btrc_scene_file_dump(const char *path, char *out, uint64_t out_bytes, uint64_t *needed);
+int btrc_scene_file_parse(const char *path, const char *node_path, int32_t kind, float *out, int32_t *count);
+
 /* ---- stage-level entry points on explicit batches, in the reference's SoA layout (wavefront/soa.h:8-37) ----
  * ray: o_med = float4(o.xyz, bit-cast medium id), d_t1 = float4(d.xyz, t1).
  * hit: flag = instance id | bit30 on hit (common.h:12-14); detail = uint4(t bits, primitive id, u bits, v bits).
