@@ -121,8 +121,8 @@ void write_exr(const std::string &filename, int w, int h, const float *rgba) {
     f.write(reinterpret_cast<const char *>(out.data()), (std::streamsize)out.size());
 }
 
-// Baseline JPEG (ITU T.81 Annex K tables, quality 90 as stb_image_write picks for the reference's quality argument 0;
-// utils/image.cpp:28-38), YCbCr 4:4:4, one scan.
+// Baseline JPEG as stb_image_write produces it for the reference's quality argument 0 (utils/image.cpp:28-38): quality 90, which
+// in stb_image_write also means 2x2 chroma subsampling (16x16 MCUs, chroma averaged over 2x2 pixels); ITU T.81 Annex K tables, one scan.
 void write_jpg_rgb8(const std::string &filename, int w, int h, const std::vector<uint8_t> &rgb) {
     static const uint8_t zz[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
                                    35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
@@ -169,7 +169,7 @@ void write_jpg_rgb8(const std::string &filename, int w, int h, const std::vector
         put({0xff, 0xdb, 0, 67, t});
         for (int i = 0; i < 64; ++i) out.push_back(tq[t][zz[i]]);
     }
-    put({0xff, 0xc0, 0, 17, 8, h >> 8, h & 255, w >> 8, w & 255, 3, 1, 0x11, 0, 2, 0x11, 1, 3, 0x11, 1});
+    put({0xff, 0xc0, 0, 17, 8, h >> 8, h & 255, w >> 8, w & 255, 3, 1, 0x22, 0, 2, 0x11, 1, 3, 0x11, 1});
     auto dht = [&](int cls_id, const uint8_t *bits, const uint8_t *vals, int n) {
         put({0xff, 0xc4, (19 + n) >> 8, (19 + n) & 255, cls_id});
         for (int l = 1; l <= 16; ++l) out.push_back(bits[l]);
@@ -199,51 +199,62 @@ void write_jpg_rgb8(const std::string &filename, int w, int h, const std::vector
     for (int u = 0; u < 8; ++u)
         for (int x = 0; x < 8; ++x) cosv[u][x] = std::cos((2 * x + 1) * u * 3.14159265358979f / 16.0f) * (u == 0 ? 0.353553391f : 0.5f);
     int pred[3] = {0, 0, 0};
-    for (int by = 0; by < h; by += 8)
-        for (int bx = 0; bx < w; bx += 8) {
-            float blk[3][64];
+    // one 8x8 data unit: separable DCT, quantisation, Huffman coding (stride = row pitch of `src`)
+    auto code_block = [&](const float *src, int stride, int c) {
+        float tmp[64], dct[64];
+        for (int y = 0; y < 8; ++y)
+            for (int u = 0; u < 8; ++u) {
+                float a = 0;
+                for (int x = 0; x < 8; ++x) a += src[stride * y + x] * cosv[u][x];
+                tmp[8 * y + u] = a;
+            }
+        for (int v = 0; v < 8; ++v)
+            for (int u = 0; u < 8; ++u) {
+                float a = 0;
+                for (int y = 0; y < 8; ++y) a += tmp[8 * y + u] * cosv[v][y];
+                dct[8 * v + u] = a;
+            }
+        int q[64];
+        const uint8_t *tab = tq[c ? 1 : 0];
+        for (int i = 0; i < 64; ++i) q[i] = (int)std::lround(dct[zz[i]] / tab[zz[i]]);
+        const Huff &hd = c ? hdc_c : hdc_y, &ha = c ? hac_c : hac_y;
+        int size; uint32_t bits;
+        magnitude(q[0] - pred[c], size, bits);
+        pred[c] = q[0];
+        emit(hd.code[size], hd.len[size]);
+        if (size) emit(bits, size);
+        int run = 0;
+        for (int i = 1; i < 64; ++i) {
+            if (q[i] == 0) { ++run; continue; }
+            while (run > 15) { emit(ha.code[0xf0], ha.len[0xf0]); run -= 16; }
+            magnitude(q[i], size, bits);
+            emit(ha.code[(run << 4) | size], ha.len[(run << 4) | size]);
+            emit(bits, size);
+            run = 0;
+        }
+        if (run) emit(ha.code[0], ha.len[0]);
+    };
+    // 16x16 MCUs: four luma units, then Cb and Cr averaged over 2x2 pixels; pixels beyond the image repeat the last row / column
+    for (int my = 0; my < h; my += 16)
+        for (int mx = 0; mx < w; mx += 16) {
+            float Y[256], U[256], V[256];
+            for (int y = 0; y < 16; ++y)
+                for (int x = 0; x < 16; ++x) {
+                    const uint8_t *p = &rgb[3 * ((size_t)std::min(my + y, h - 1) * w + std::min(mx + x, w - 1))];
+                    const float r = p[0], g = p[1], b = p[2];
+                    Y[16 * y + x] = 0.299f * r + 0.587f * g + 0.114f * b - 128.0f;
+                    U[16 * y + x] = -0.16874f * r - 0.33126f * g + 0.5f * b;
+                    V[16 * y + x] = 0.5f * r - 0.41869f * g - 0.08131f * b;
+                }
+            code_block(Y, 16, 0); code_block(Y + 8, 16, 0); code_block(Y + 128, 16, 0); code_block(Y + 136, 16, 0);
+            float su[64], sv[64];
             for (int y = 0; y < 8; ++y)
                 for (int x = 0; x < 8; ++x) {
-                    const uint8_t *p = &rgb[3 * ((size_t)std::min(by + y, h - 1) * w + std::min(bx + x, w - 1))];
-                    const float r = p[0], g = p[1], b = p[2];
-                    blk[0][8 * y + x] = 0.299f * r + 0.587f * g + 0.114f * b - 128.0f;
-                    blk[1][8 * y + x] = -0.168736f * r - 0.331264f * g + 0.5f * b;
-                    blk[2][8 * y + x] = 0.5f * r - 0.418688f * g - 0.081312f * b;
+                    const int j = 32 * y + 2 * x;
+                    su[8 * y + x] = (U[j] + U[j + 1] + U[j + 16] + U[j + 17]) * 0.25f;
+                    sv[8 * y + x] = (V[j] + V[j + 1] + V[j + 16] + V[j + 17]) * 0.25f;
                 }
-            for (int c = 0; c < 3; ++c) {
-                float tmp[64], dct[64];
-                for (int y = 0; y < 8; ++y)
-                    for (int u = 0; u < 8; ++u) {
-                        float a = 0;
-                        for (int x = 0; x < 8; ++x) a += blk[c][8 * y + x] * cosv[u][x];
-                        tmp[8 * y + u] = a;
-                    }
-                for (int v = 0; v < 8; ++v)
-                    for (int u = 0; u < 8; ++u) {
-                        float a = 0;
-                        for (int y = 0; y < 8; ++y) a += tmp[8 * y + u] * cosv[v][y];
-                        dct[8 * v + u] = a;
-                    }
-                int q[64];
-                const uint8_t *tab = tq[c ? 1 : 0];
-                for (int i = 0; i < 64; ++i) q[i] = (int)std::lround(dct[zz[i]] / tab[zz[i]]);
-                const Huff &hd = c ? hdc_c : hdc_y, &ha = c ? hac_c : hac_y;
-                int size; uint32_t bits;
-                magnitude(q[0] - pred[c], size, bits);
-                pred[c] = q[0];
-                emit(hd.code[size], hd.len[size]);
-                if (size) emit(bits, size);
-                int run = 0;
-                for (int i = 1; i < 64; ++i) {
-                    if (q[i] == 0) { ++run; continue; }
-                    while (run > 15) { emit(ha.code[0xf0], ha.len[0xf0]); run -= 16; }
-                    magnitude(q[i], size, bits);
-                    emit(ha.code[(run << 4) | size], ha.len[(run << 4) | size]);
-                    emit(bits, size);
-                    run = 0;
-                }
-                if (run) emit(ha.code[0], ha.len[0]);
-            }
+            code_block(su, 8, 1); code_block(sv, 8, 2);
         }
     if (nbits) emit(0x7f, 8 - nbits);
     put({0xff, 0xd9});
@@ -480,9 +491,9 @@ static LoadedImage load_hdr(const std::string &filename) {
 // 1x/2x sampling factors, restart intervals, interleaved and single-component scans.  The reference reads .jpg textures through
 // stb_image (utils/image.cpp:135-143), which covers the same set; arithmetic-coded and lossless files are reported as unsupported
 // (stb_image rejects them too).  Every scan is decoded into per-component coefficient arrays (spectral selection and successive
-// approximation as in T.81 annex G); dequantisation and the IDCT run once after the last scan.  Chroma is upsampled with
-// libjpeg's triangle filter, the IDCT is separable floating point: decoded values agree with libjpeg to 1-3 eight-bit levels
-// (tests/test_postprocess_cpu.py).
+// approximation as in T.81 annex G); dequantisation and the IDCT run once after the last scan, in stb_image's integer arithmetic:
+// the decoded bytes are those of the reference's loader (tests/test_reference_host_pins_cpu.py) and within 1-3 eight-bit levels of
+// libjpeg (tests/test_postprocess_cpu.py).
 static LoadedImage load_jpg(const std::string &filename) {
     std::ifstream f(filename, std::ios::binary);
     if (!f) throw Error("failed to open file: " + filename);
@@ -520,7 +531,8 @@ static LoadedImage load_jpg(const std::string &filename) {
     Huff hdc[4], hac[4];
     std::vector<Comp> comps;
     int width = 0, height = 0, restart = 0, hmax = 1, vmax = 1, mcux = 0, mcuy = 0, scans = 0;
-    bool progressive = false;
+    bool progressive = false, jfif = false;
+    int adobe_transform = -1;
     auto u16 = [&](size_t at) { if (at + 1 >= buf.size()) throw fail("truncated"); return (int)buf[at] << 8 | buf[at + 1]; };
 
     // entropy-coded segment reader: stops feeding at a marker (zeros from there on), never steps over one
@@ -723,6 +735,10 @@ static LoadedImage load_jpg(const std::string &filename) {
                 a += n;
                 h.build();
             }
+        } else if (m == 0xe0 && len >= 7) {  // APP0 "JFIF"
+            if (std::memcmp(&buf[q], "JFIF\0", 5) == 0) jfif = true;
+        } else if (m == 0xee && len >= 14) {  // APP14 "Adobe": colour transform flag
+            if (std::memcmp(&buf[q], "Adobe\0", 6) == 0) adobe_transform = buf[q + 11];
         } else if (m == 0xdd) {
             restart = u16(q);
         } else if (m == 0xda) {
@@ -756,83 +772,141 @@ static LoadedImage load_jpg(const std::string &filename) {
     }
     if (!scans || comps.empty()) throw fail("no image data");
 
-    // dequantisation + inverse DCT of every block
-    float cs[8][8];
-    for (int x = 0; x < 8; ++x)
-        for (int u = 0; u < 8; ++u) cs[x][u] = std::cos((2 * x + 1) * u * 3.14159265358979f / 16.0f) * (u == 0 ? 0.353553391f : 0.5f);
+    // ---- reconstruction, in the integer arithmetic of stb_image (the decoder the reference calls: lib/stb/stb/stb_image.h) so that a
+    // texture decodes to the bytes the reference uploads.  Dequantisation in 16 bits (stbi__jpeg_dequantize), the jidctint-style
+    // 12-bit fixed-point IDCT with 2 extra bits between the passes (stbi__idct_block), chroma rows / columns by the 3:1 and 9:3:3:1
+    // filters with stb's edge rules (stbi__resample_row_*), 20-bit fixed-point YCbCr -> RGB (stbi__YCbCr_to_RGB_row).
+    auto fx = [](double x) { return (int)(x * 4096 + 0.5); };  // stbi__f2f
+    const int c0 = fx(0.5411961f), c1 = fx(-1.847759065f), c2 = fx(0.765366865f), c3 = fx(1.175875602f), c4 = fx(0.298631336f), c5 = fx(2.053119869f),
+              c6 = fx(3.072711026f), c7 = fx(1.501321110f), c8 = fx(-0.899976223f), c9 = fx(-2.562915447f), c10 = fx(-1.961570560f), c11 = fx(-0.390180644f);
+    struct Pass { int x0, x1, x2, x3, t0, t1, t2, t3; };
+    auto idct_1d = [&](int s0, int s1, int s2, int s3, int s4, int s5, int s6, int s7) {  // even part -> x*, odd part -> t*
+        Pass r;
+        int p1 = (s2 + s6) * c0;
+        int e2 = p1 + s6 * c1, e3 = p1 + s2 * c2;
+        int e0 = (s0 + s4) * 4096, e1 = (s0 - s4) * 4096;
+        r.x0 = e0 + e3; r.x3 = e0 - e3; r.x1 = e1 + e2; r.x2 = e1 - e2;
+        int t0 = s7, t1 = s5, t2 = s3, t3 = s1;
+        int p3 = t0 + t2, p4 = t1 + t3, q1 = t0 + t3, q2 = t1 + t2;
+        const int p5 = (p3 + p4) * c3;
+        t0 *= c4; t1 *= c5; t2 *= c6; t3 *= c7;
+        q1 = p5 + q1 * c8; q2 = p5 + q2 * c9; p3 *= c10; p4 *= c11;
+        r.t3 = t3 + q1 + p4; r.t2 = t2 + q2 + p3; r.t1 = t1 + q2 + p4; r.t0 = t0 + q1 + p3;
+        return r;
+    };
+    auto clamp8 = [](int x) { return (uint8_t)(x < 0 ? 0 : x > 255 ? 255 : x); };
     for (auto &c : comps) {
         c.px.assign((size_t)c.bw * c.bh, 0);
         for (int bj = 0; bj < c.nby; ++bj)
             for (int bi = 0; bi < c.nbx; ++bi) {
                 const int16_t *q = &c.coef[((size_t)bj * c.nbx + bi) * 64];
-                float blk[64], tmp[64];
-                for (int i = 0; i < 64; ++i) blk[i] = (float)q[i] * qt[c.tq][i];
-                for (int v = 0; v < 8; ++v)
-                    for (int x = 0; x < 8; ++x) {
-                        float a = 0;
-                        for (int u = 0; u < 8; ++u) a += blk[8 * v + u] * cs[x][u];
-                        tmp[8 * v + x] = a;
+                int16_t d[64];
+                for (int i = 0; i < 64; ++i) d[i] = (int16_t)(q[i] * qt[c.tq][i]);
+                int v[64];
+                for (int i = 0; i < 8; ++i) {  // columns
+                    if (!(d[8 + i] | d[16 + i] | d[24 + i] | d[32 + i] | d[40 + i] | d[48 + i] | d[56 + i])) {
+                        for (int k = 0; k < 8; ++k) v[8 * k + i] = d[i] * 4;
+                        continue;
                     }
-                for (int y = 0; y < 8; ++y)
-                    for (int x = 0; x < 8; ++x) {
-                        float a = 0;
-                        for (int v = 0; v < 8; ++v) a += tmp[8 * v + x] * cs[y][v];
-                        c.px[(size_t)(bj * 8 + y) * c.bw + bi * 8 + x] = (uint8_t)std::min(std::max((int)std::lround(a + 128.0f), 0), 255);
-                    }
+                    Pass r = idct_1d(d[i], d[8 + i], d[16 + i], d[24 + i], d[32 + i], d[40 + i], d[48 + i], d[56 + i]);
+                    r.x0 += 512; r.x1 += 512; r.x2 += 512; r.x3 += 512;
+                    v[i] = (r.x0 + r.t3) >> 10; v[56 + i] = (r.x0 - r.t3) >> 10;
+                    v[8 + i] = (r.x1 + r.t2) >> 10; v[48 + i] = (r.x1 - r.t2) >> 10;
+                    v[16 + i] = (r.x2 + r.t1) >> 10; v[40 + i] = (r.x2 - r.t1) >> 10;
+                    v[24 + i] = (r.x3 + r.t0) >> 10; v[32 + i] = (r.x3 - r.t0) >> 10;
+                }
+                for (int y = 0; y < 8; ++y) {  // rows: >> 17 removes 12 + 2 + 3 bits; + 128 level shift, rounded
+                    const int *w = &v[8 * y];
+                    Pass r = idct_1d(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+                    const int bias = 65536 + (128 << 17);
+                    r.x0 += bias; r.x1 += bias; r.x2 += bias; r.x3 += bias;
+                    uint8_t *o = &c.px[(size_t)(bj * 8 + y) * c.bw + bi * 8];
+                    o[0] = clamp8((r.x0 + r.t3) >> 17); o[7] = clamp8((r.x0 - r.t3) >> 17);
+                    o[1] = clamp8((r.x1 + r.t2) >> 17); o[6] = clamp8((r.x1 - r.t2) >> 17);
+                    o[2] = clamp8((r.x2 + r.t1) >> 17); o[5] = clamp8((r.x2 - r.t1) >> 17);
+                    o[3] = clamp8((r.x3 + r.t0) >> 17); o[4] = clamp8((r.x3 - r.t0) >> 17);
+                }
             }
         std::vector<int16_t>().swap(c.coef);
     }
-    // chroma upsampling: the triangle filter of libjpeg / stb_image ("fancy upsampling") for 2x factors, replication otherwise
-    const int fw = mcux * hmax * 8, fh = mcuy * vmax * 8;
-    for (auto &c : comps) {
-        const int sx = hmax / c.h, sy = vmax / c.v;
-        if (sx == 1 && sy == 1) continue;
-        std::vector<uint8_t> full((size_t)fw * fh);
-        const int cw = c.bw, chh = c.bh;
-        auto in = [&](int x, int y) { return (int)c.px[(size_t)std::min(std::max(y, 0), chh - 1) * cw + std::min(std::max(x, 0), cw - 1)]; };
-        for (int y = 0; y < fh; ++y)
-            for (int x = 0; x < fw; ++x) {
-                int v;
-                if (sx == 2 && sy == 2) {       // h2v2: 9/3/3/1 sixteenths, rounding 8 / 7 on even / odd columns
-                    const int r = y >> 1, rf = (y & 1) ? r + 1 : r - 1, i = x >> 1, jf = (x & 1) ? i + 1 : i - 1;
-                    const int cs = 3 * in(i, r) + in(i, rf), cf = 3 * in(jf, r) + in(jf, rf);
-                    const bool edge = jf < 0 || jf >= cw;
-                    v = edge ? (4 * cs + ((x & 1) ? 7 : 8)) >> 4 : (3 * cs + cf + ((x & 1) ? 7 : 8)) >> 4;
-                } else if (sx == 2 && sy == 1) {  // h2v1: 3/1 quarters, rounding 1 / 2
-                    const int i = x >> 1, jf = (x & 1) ? i + 1 : i - 1;
-                    v = (jf < 0 || jf >= cw) ? in(i, y) : (3 * in(i, y) + in(jf, y) + ((x & 1) ? 2 : 1)) >> 2;
-                } else if (sx == 1 && sy == 2) {  // h1v2
-                    const int r = y >> 1, rf = (y & 1) ? r + 1 : r - 1;
-                    v = (3 * in(x, r) + in(x, rf) + ((y & 1) ? 2 : 1)) >> 2;
-                } else {
-                    v = in(x / sx, y / sy);
-                }
-                full[(size_t)y * fw + x] = (uint8_t)v;
-            }
-        c.px.swap(full);
-        c.bw = fw; c.bh = fh; c.h = hmax; c.v = vmax;
-    }
+    // One output row at a time: every component's row is brought to full width from its near / far source rows.
+    // Vertical 2x: output row j reads source row j >> 1 ("near") and the row above (even j) or below (odd j), held at the first row
+    // and at the component's own last row.  Horizontal 2x over w = ceil(width / 2) samples.
+    std::vector<std::vector<uint8_t>> line(comps.size(), std::vector<uint8_t>((size_t)width + 8));
     LoadedImage img;
     img.width = width; img.height = height;
     img.channels = comps.size() == 1 ? 1 : 3;
     img.u8.resize((size_t)width * height * img.channels);
-    for (int y = 0; y < height; ++y)
-        for (int x = 0; x < width; ++x) {
-            auto at = [&](const Comp &c) { return (float)c.px[(size_t)(y * c.v / vmax) * c.bw + x * c.h / hmax]; };
-            uint8_t *o = &img.u8[((size_t)y * width + x) * img.channels];
-            if (img.channels == 1) { o[0] = (uint8_t)at(comps[0]); continue; }
-            const float Y = at(comps[0]), cb = at(comps[1]) - 128.0f, cr = at(comps[2]) - 128.0f;
-            const float rgb[3] = {Y + 1.402f * cr, Y - 0.344136f * cb - 0.714136f * cr, Y + 1.772f * cb};
-            for (int k = 0; k < 3; ++k) o[k] = (uint8_t)std::min(std::max((int)std::lround(rgb[k]), 0), 255);
+    // an RGB file: component ids 'R' 'G' 'B', or an Adobe APP14 marker with transform 0 and no JFIF header (load_jpeg_image's is_rgb)
+    const bool is_rgb = comps.size() == 3 && ((comps[0].id == 'R' && comps[1].id == 'G' && comps[2].id == 'B') || (adobe_transform == 0 && !jfif));
+    for (int j = 0; j < height; ++j) {
+        for (size_t k = 0; k < comps.size(); ++k) {
+            const Comp &c = comps[k];
+            const int hs = hmax / c.h, vs = vmax / c.v;
+            const int w = (width + hs - 1) / hs, rows = (height * c.v + vmax - 1) / vmax;
+            int rn = j, rf = j;
+            if (vs == 2) {
+                rn = j >> 1;
+                rf = (j & 1) ? std::min(rn + 1, rows - 1) : std::max(rn - 1, 0);
+                // stb advances its far pointer only while rows remain: beyond the last row near and far coincide
+                if (rn > rows - 1) rn = rows - 1;
+            }
+            const uint8_t *near_ = &c.px[(size_t)rn * c.bw], *far_ = &c.px[(size_t)rf * c.bw];
+            uint8_t *out = line[k].data();
+            if (hs == 1 && vs == 1) {
+                std::memcpy(out, near_, (size_t)w);
+            } else if (hs == 1) {  // stbi__resample_row_v_2
+                for (int i = 0; i < w; ++i) out[i] = (uint8_t)((3 * near_[i] + far_[i] + 2) >> 2);
+            } else if (vs == 1) {  // stbi__resample_row_h_2, including its asymmetric last pair
+                if (w == 1) { out[0] = out[1] = near_[0]; continue; }
+                out[0] = near_[0];
+                out[1] = (uint8_t)((near_[0] * 3 + near_[1] + 2) >> 2);
+                for (int i = 1; i < w - 1; ++i) {
+                    const int n3 = 3 * near_[i] + 2;
+                    out[2 * i] = (uint8_t)((n3 + near_[i - 1]) >> 2);
+                    out[2 * i + 1] = (uint8_t)((n3 + near_[i + 1]) >> 2);
+                }
+                out[2 * (w - 1)] = (uint8_t)((near_[w - 2] * 3 + near_[w - 1] + 2) >> 2);
+                out[2 * (w - 1) + 1] = near_[w - 1];
+            } else {  // stbi__resample_row_hv_2
+                if (w == 1) { out[0] = out[1] = (uint8_t)((3 * near_[0] + far_[0] + 2) >> 2); continue; }
+                int t1 = 3 * near_[0] + far_[0];
+                out[0] = (uint8_t)((t1 + 2) >> 2);
+                for (int i = 1; i < w; ++i) {
+                    const int t0 = t1;
+                    t1 = 3 * near_[i] + far_[i];
+                    out[2 * i - 1] = (uint8_t)((3 * t0 + t1 + 8) >> 4);
+                    out[2 * i] = (uint8_t)((3 * t1 + t0 + 8) >> 4);
+                }
+                out[2 * w - 1] = (uint8_t)((t1 + 2) >> 2);
+            }
         }
+        uint8_t *o = &img.u8[(size_t)j * width * img.channels];
+        if (img.channels == 1) { std::memcpy(o, line[0].data(), (size_t)width); continue; }
+        for (int x = 0; x < width; ++x, o += 3) {
+            if (is_rgb) { o[0] = line[0][x]; o[1] = line[1][x]; o[2] = line[2][x]; continue; }
+            auto f2f = [](float v) { return ((int)(v * 4096.0f + 0.5f)) << 8; };  // stbi__float2fixed
+            const int y_fixed = (line[0][x] << 20) + (1 << 19);
+            const int cr = line[2][x] - 128, cb = line[1][x] - 128;
+            int r = y_fixed + cr * f2f(1.40200f);
+            int g = y_fixed + (cr * -f2f(0.71414f)) + ((cb * -f2f(0.34414f)) & 0xffff0000);
+            int bl = y_fixed + cb * f2f(1.77200f);
+            r >>= 20; g >>= 20; bl >>= 20;
+            o[0] = clamp8(r); o[1] = clamp8(g); o[2] = clamp8(bl);
+        }
+    }
     return img;
 }
 
 LoadedImage load_image(const std::string &filename) {
     const std::string ext = lower_ext(filename);
-    if (ext == "png") return load_png(filename);
+    if (ext == "png" || ext == "jpg" || ext == "jpeg") {
+        LoadedImage img = ext == "png" ? load_png(filename) : load_jpg(filename);
+        // utils/image.cpp:313-335: one, three or four channels become Image<uint8_t / Vec3b / Vec4b>; grey + alpha is refused
+        if (img.channels != 1 && img.channels != 3 && img.channels != 4) throw Error("ImageDynamic::load: unsupported channels: " + std::to_string(img.channels));
+        return img;
+    }
     if (ext == "hdr") return load_hdr(filename);
-    if (ext == "jpg" || ext == "jpeg") return load_jpg(filename);
     throw Error("unsupported image format (use .png, .jpg or .hdr): " + filename);
 }
 

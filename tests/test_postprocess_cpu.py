@@ -91,7 +91,7 @@ def test_save_all_formats_and_tonemap(built, tmp_path):
     jpg = np.asarray(Image.open(tmp_path / "out.jpg").convert("RGB"))
     assert jpg.shape == (H, W, 3)
     err = np.abs(jpg.astype(int) - want8.astype(int))
-    assert err.mean() < 3.0 and err.max() < 40  # quality-90 baseline JPEG
+    assert err.mean() < 5.0 and err.max() < 60  # quality-90 baseline JPEG with 2x2 chroma subsampling, as stb_image_write writes it (pinned in test_reference_host_pins_cpu.py)
     s.close()
 
 
@@ -110,8 +110,9 @@ def test_unknown_format_is_an_error(built, tmp_path):
 
 def test_jpeg_decoder_against_libjpeg(built, tmp_path):
     """ImageDynamic::load for .jpg (the reference goes through stb_image): baseline and progressive files with 4:4:4 / 4:2:2 / 4:2:0
-    chroma, grayscale and restart intervals decode to within 3 eight-bit levels of libjpeg (PIL); arithmetic-coded files (which
-    stb_image does not read either) are refused with a clear error."""
+    chroma, grayscale and restart intervals decode close to libjpeg (PIL; the byte-exact pin is against stb_image itself, in
+    tests/test_reference_host_pins_cpu.py, which also runs without the reference tree's prebuilt library being rebuilt); arithmetic-coded
+    files (which stb_image does not read either) are refused with a clear error."""
     from btrc_b200 import api
 
     rng = np.random.default_rng(3)
@@ -132,7 +133,9 @@ def test_jpeg_decoder_against_libjpeg(built, tmp_path):
         got = api.load_image(p)
         assert got.shape == ref.shape and got.dtype == np.uint8, name
         err = np.abs(got.astype(int) - ref.astype(int))
-        assert err.max() <= 3 and err.mean() < 0.1, (name, err.max(), err.mean())
+        # the decoder reproduces stb_image, the reference's decoder, byte for byte (tests/test_reference_host_pins_cpu.py); libjpeg differs from
+        # stb_image in its IDCT rounding and in the chroma filter at the right edge (stb's last 4:2:2 pair): a sanity bound, not the parity bar
+        assert err.max() <= 12 and err.mean() < 0.5, (name, err.max(), err.mean())
         if "prog" in name:
             assert b"\xff\xc2" in open(p, "rb").read()  # really a progressive frame
     # a file whose frame header says SOF9 (arithmetic coding): refused, as by stb_image
@@ -259,6 +262,11 @@ def test_png_every_variant_stb_reads(built, tmp_path):
                     want = (smp >> 8).astype(np.uint8)
                 else:
                     want = (smp * (255 // ((1 << depth) - 1))).astype(np.uint8)
+                if ctype == 4:   # grey + alpha: ImageDynamic::load has no two-channel image type (utils/image.cpp:333-334)
+                    with pytest.raises(api.BtrcError, match="unsupported channels: 2"):
+                        api.load_image(name)
+                    n += 1
+                    continue
                 got = api.load_image(name)
                 assert got.shape == want.shape and np.array_equal(got, want), name
                 pil = Image.open(name)
@@ -278,8 +286,8 @@ def test_png_every_variant_stb_reads(built, tmp_path):
     assert np.array_equal(np.asarray(Image.open(tmp_path / "pt.png").convert("RGBA")), got)
     g = rng.integers(0, 4, (H, W, 1)).astype(np.uint32)
     open(tmp_path / "gk.png", "wb").write(_png_bytes(g, 2, 0, False, trns=[0, 2]))
-    got = api.load_image(str(tmp_path / "gk.png"))
-    assert got.shape == (H, W, 2) and np.array_equal(got[..., 0], g[..., 0] * 85) and np.array_equal(got[..., 1], np.where(g[..., 0] == 2, 0, 255))
+    with pytest.raises(api.BtrcError, match="unsupported channels: 2"):   # a colour-keyed grey image becomes grey + alpha in stb_image
+        api.load_image(str(tmp_path / "gk.png"))
     c16 = rng.integers(0, 3, (H, W, 3)).astype(np.uint32) * 0x0101 + 0x1000
     open(tmp_path / "ck.png", "wb").write(_png_bytes(c16, 16, 2, True, trns=[0x11, 0x01, 0x10, 0x00, 0x12, 0x02]))
     got = api.load_image(str(tmp_path / "ck.png"))

@@ -375,3 +375,146 @@ def test_scene_file_layer_matches_reference(R, built, tmp_path):
         assert R.ref_json_dump(path.encode()) is None
         with pytest.raises(api.BtrcError):
             api.scene_file_dump(path)
+
+
+# ---------------------------------------------------------------------------------------------------- image layer
+def _image_api(R):
+    R.ref_image_last_error.restype = ctypes.c_char_p
+    R.ref_image_load.argtypes = [ctypes.c_char_p] + [ctypes.POINTER(ctypes.c_int)] * 4 + [ctypes.c_void_p, ctypes.c_ulonglong]
+    R.ref_image_save.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_float]
+    return R
+
+
+def _ref_image_load(R, path):
+    w, h, c, f = (ctypes.c_int(0) for _ in range(4))
+    if R.ref_image_load(path.encode(), w, h, c, f, None, 0) != 0:
+        raise RuntimeError(R.ref_image_last_error().decode())
+    out = np.zeros((h.value, w.value, c.value), f32 if f.value else np.uint8)
+    assert R.ref_image_load(path.encode(), w, h, c, f, out.ctypes.data, out.nbytes) == 0
+    return out
+
+
+def test_texture_readers_match_reference_image_layer(R, built, tmp_path):
+    """ImageDynamic::load of the reference (utils/image.cpp over the vendored stb_image, compiled where they lie into oracle/_ref)
+    against the product's readers (C ABI btrc_image_load): every PNG colour type / bit depth / interlacing, baseline and progressive
+    JPEG at every chroma layout and at sizes that hit the resamplers' edge rules, Radiance HDR flat and run-length coded -
+    byte for byte (bit for bit for HDR), and the same refusals."""
+    from PIL import Image
+
+    from btrc_b200 import api
+    from tests.test_postprocess_cpu import _png_bytes
+
+    R = _image_api(R)
+    rng = np.random.default_rng(12)
+    n = 0
+    pal = rng.integers(0, 256, (16, 3), dtype=np.uint8)
+    for interlace in (False, True):
+        for ctype, ch, depths in ((0, 1, (1, 2, 4, 8, 16)), (2, 3, (8, 16)), (3, 1, (1, 2, 4, 8)), (4, 2, (8,)), (6, 4, (8, 16))):
+            for depth in depths:
+                hi = min(1 << depth, 16) if ctype == 3 else 1 << depth
+                smp = rng.integers(0, hi, (13, 21, ch)).astype(np.uint32)
+                trns = None
+                if ctype == 3 and depth == 4:
+                    trns = list(rng.integers(0, 256, 9))
+                if ctype == 2 and depth == 8:
+                    trns = [0, int(smp[0, 0, 0]), 0, int(smp[0, 0, 1]), 0, int(smp[0, 0, 2])]
+                name = str(tmp_path / f"t{ctype}_d{depth}_i{int(interlace)}.png")
+                open(name, "wb").write(_png_bytes(smp, depth, ctype, interlace, plte=pal.reshape(-1) if ctype == 3 else None, trns=trns))
+                if ctype == 4:
+                    with pytest.raises(RuntimeError, match="unsupported channels: 2"):
+                        _ref_image_load(R, name)
+                    with pytest.raises(api.BtrcError, match="unsupported channels: 2"):
+                        api.load_image(name)
+                else:
+                    want = _ref_image_load(R, name)
+                    got = api.load_image(name)
+                    assert got.shape == want.shape and np.array_equal(got, want), name
+                n += 1
+    assert n == 28
+    for (W, H) in ((101, 67), (16, 16), (17, 9), (1, 1), (2, 3), (3, 2), (33, 1), (1, 40)):
+        yy, xx = np.mgrid[0:H, 0:W]
+        img = np.stack([127 + 100 * np.sin(xx / 9.0) * np.cos(yy / 7.0), 30 + xx * 2.0, 200 - yy * 2.5], -1) + rng.normal(0, 12, (H, W, 3))
+        img = np.clip(img, 0, 255).astype(np.uint8)
+        cases = {"444": dict(quality=75, subsampling=0), "422": dict(quality=95, subsampling=1), "420": dict(quality=90, subsampling=2), "gray": dict(quality=85),
+                 "p420": dict(quality=90, progressive=True), "p422": dict(quality=40, progressive=True, subsampling=1), "p444": dict(quality=98, progressive=True, subsampling=0),
+                 "pgray": dict(quality=70, progressive=True), "rst": dict(quality=80, restart_marker_blocks=2), "prst": dict(quality=80, progressive=True, restart_marker_blocks=1)}
+        for tag, kw in cases.items():
+            p = str(tmp_path / f"{tag}_{W}x{H}.jpg")
+            Image.fromarray(img[..., 0] if "gray" in tag else img).save(p, **kw)
+            want = _ref_image_load(R, p)
+            got = api.load_image(p)
+            assert got.shape == want.shape and np.array_equal(got, want), (tag, W, H, int(np.abs(got.astype(int) - want.astype(int)).max()))
+    # an RGB-coded JPEG (Adobe marker, transform 0, no JFIF header) and a 4:4:0 file (vertical-only chroma subsampling)
+    p = str(tmp_path / "rgb.jpg")
+    Image.fromarray(img).save(p, quality=90, subsampling=0)
+    d = open(p, "rb").read()
+    app0 = d.index(b"\xff\xe0")
+    app0_len = (d[app0 + 2] << 8) | d[app0 + 3]
+    adobe = b"\xff\xee\x00\x0eAdobe\x00\x64\x00\x00\x00\x00\x00"
+    open(p, "wb").write(d[:app0] + adobe + d[app0 + 2 + app0_len:])
+    assert np.array_equal(api.load_image(p), _ref_image_load(R, p))
+    p = str(tmp_path / "v2.jpg")
+    Image.fromarray(np.ascontiguousarray(img.transpose(1, 0, 2))).save(p, quality=85, subsampling=1)
+    d = bytearray(open(p, "rb").read())
+    sof = d.index(b"\xff\xc0")
+    assert d[sof + 11] == 0x21
+    d[sof + 11] = 0x12                      # luma sampling 2x1 -> 1x2: same block count per MCU, a valid if differently shaped picture
+    d[sof + 5:sof + 9] = bytes([d[sof + 7], d[sof + 8], d[sof + 5], d[sof + 6]])  # swap height and width
+    open(p, "wb").write(bytes(d))
+    assert np.array_equal(api.load_image(p), _ref_image_load(R, p))
+    # HDR: flat and run-length coded scanlines, written by the reference's own writer and by hand
+    rad = (rng.random((11, 40, 4)) ** 3 * 50).astype(f32)
+    rad[2, 5:30] = rad[2, 5]                # a run
+    p = str(tmp_path / "a.hdr")
+    assert R.ref_image_save(p.encode(), 40, 11, rad.ctypes.data, 0, 1.0) == 0, R.ref_image_last_error()
+    want = _ref_image_load(R, p)
+    got = api.load_image(p)
+    assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    p = str(tmp_path / "flat.hdr")
+    open(p, "wb").write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 5 +X 7\n" + bytes(rng.integers(1, 256, 5 * 7 * 4, dtype=np.uint8)))
+    assert np.array_equal(api.load_image(p).view(np.uint32), _ref_image_load(R, p).view(np.uint32))
+    for bad in ("missing.png", "x.tga"):
+        with pytest.raises(RuntimeError):
+            _ref_image_load(R, str(tmp_path / bad))
+        with pytest.raises(api.BtrcError):
+            api.load_image(str(tmp_path / bad))
+
+
+def test_save_post_processor_matches_reference_writers(R, built, tmp_path):
+    """`save` (postprocess/save_to_image.cpp:30-62: Image<Vec4f>::pow_(1 / gamma) on the colour output, then Image::save by extension)
+    through the reference's own image layer and through the product's C ABI (btrc_run_post_processors, host only): the PNG files decode
+    to identical bytes, the HDR files to identical floats, the JPEG files (both quality 90 baseline) to within a few levels."""
+    from PIL import Image
+
+    from btrc_b200 import api, scenes
+
+    R = _image_api(R)
+    W, H = 37, 23
+    rng = np.random.default_rng(5)
+    color = (rng.random((H, W, 4)) ** 2 * 1.6).astype(f32)      # some values above 1: the writers clamp
+    color[0, 0] = [0, 1, 0.999999, 1]
+    color[..., 3] = 1
+    aux = rng.random((H, W, 4)).astype(f32)
+    for ext in ("png", "hdr", "jpg"):
+        path = scenes.make_cornell(str(tmp_path / ext), width=W, height=H, spp=1, state_count=64)
+        root = json.load(open(path))
+        root["renderer"]["albedo"] = True
+        root["post_processors"] = [{"type": "save", "color": f"$env{{scene_directory}}/c.{ext}", "albedo": f"$env{{scene_directory}}/a.{ext}", "gamma": 2.2}]
+        json.dump(root, open(path, "w"))
+        s = api.Scene(path)
+        s.run_post_processors(color.copy(), aux.copy())
+        s.close()
+        d = str(tmp_path / ext)
+        assert R.ref_image_save(f"{d}/rc.{ext}".encode(), W, H, color.ctypes.data, 1, 2.2) == 0, R.ref_image_last_error()
+        assert R.ref_image_save(f"{d}/ra.{ext}".encode(), W, H, aux.ctypes.data, 0, 1.0) == 0, R.ref_image_last_error()
+        for ours, ref in (("c", "rc"), ("a", "ra")):
+            if ext == "hdr":
+                a, b = api.load_image(f"{d}/{ours}.hdr"), api.load_image(f"{d}/{ref}.hdr")
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+            else:
+                a, b = np.asarray(Image.open(f"{d}/{ours}.{ext}")).astype(int), np.asarray(Image.open(f"{d}/{ref}.{ext}")).astype(int)
+                assert a.shape == b.shape
+                if ext == "png":
+                    assert np.array_equal(a, b)
+                else:
+                    assert np.abs(a - b).max() <= 6 and np.abs(a - b).mean() < 0.6, (np.abs(a - b).max(), np.abs(a - b).mean())
