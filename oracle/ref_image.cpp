@@ -7,6 +7,7 @@
 #include <variant>
 
 #include <btrc/utils/image.h>
+#include <tinyexr.h>
 
 using namespace btrc;
 
@@ -65,3 +66,25 @@ int ref_image_save(const char *path, int width, int height, const float *rgba, i
 // tinyexr's deflate: the vendored miniz (lib/tinyexr/deps/miniz/miniz.c), compiled where it lies as part of this translation unit
 // (a .c file on the g++ command line would be compiled as C with the C++-only force-includes of the `ref` recipe).
 #include <miniz.c>
+
+// The reference cannot *read* EXR through ImageDynamic::load (utils/image.cpp:344), but its vendored tinyexr can: used to compare
+// what the reference's save_exr wrote with what the product's EXR writer wrote.  out: width*height*4 floats (RGBA).
+extern "C" int ref_exr_load(const char *path, int *width, int *height, float *out, unsigned long long out_floats) {
+    float *rgba = nullptr;
+    const char *err = nullptr;
+    int w = 0, h = 0;
+    if (LoadEXR(&rgba, &w, &h, path, &err) != TINYEXR_SUCCESS) {
+        g_img_err = err ? err : "LoadEXR failed";
+        if (err) FreeEXRErrorMessage(err);
+        return -1;
+    }
+    if (width) *width = w;
+    if (height) *height = h;
+    int rc = 0;
+    if (out) {
+        if (out_floats < 4ull * w * h) { g_img_err = "buffer too small"; rc = -1; }
+        else std::memcpy(out, rgba, sizeof(float) * 4 * (size_t)w * h);
+    }
+    free(rgba);
+    return rc;
+}

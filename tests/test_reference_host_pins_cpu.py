@@ -483,7 +483,7 @@ def test_texture_readers_match_reference_image_layer(R, built, tmp_path):
 def test_save_post_processor_matches_reference_writers(R, built, tmp_path):
     """`save` (postprocess/save_to_image.cpp:30-62: Image<Vec4f>::pow_(1 / gamma) on the colour output, then Image::save by extension)
     through the reference's own image layer and through the product's C ABI (btrc_run_post_processors, host only): the PNG files decode
-    to identical bytes, the HDR files to identical floats, the JPEG files (both quality 90 baseline) to within a few levels."""
+    to identical bytes, the HDR and EXR files to identical floats, the JPEG files (both quality 90 baseline) to within a few levels."""
     from PIL import Image
 
     from btrc_b200 import api, scenes
@@ -495,7 +495,16 @@ def test_save_post_processor_matches_reference_writers(R, built, tmp_path):
     color[0, 0] = [0, 1, 0.999999, 1]
     color[..., 3] = 1
     aux = rng.random((H, W, 4)).astype(f32)
-    for ext in ("png", "hdr", "jpg"):
+    R.ref_exr_load.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.c_void_p, ctypes.c_ulonglong]
+
+    def exr(p):  # through the reference's vendored tinyexr
+        w, h = ctypes.c_int(0), ctypes.c_int(0)
+        assert R.ref_exr_load(p.encode(), w, h, None, 0) == 0, R.ref_image_last_error()
+        out = np.zeros((h.value, w.value, 4), f32)
+        assert R.ref_exr_load(p.encode(), w, h, out.ctypes.data, out.size) == 0
+        return out
+
+    for ext in ("png", "hdr", "jpg", "exr"):
         path = scenes.make_cornell(str(tmp_path / ext), width=W, height=H, spp=1, state_count=64)
         root = json.load(open(path))
         root["renderer"]["albedo"] = True
@@ -508,7 +517,13 @@ def test_save_post_processor_matches_reference_writers(R, built, tmp_path):
         assert R.ref_image_save(f"{d}/rc.{ext}".encode(), W, H, color.ctypes.data, 1, 2.2) == 0, R.ref_image_last_error()
         assert R.ref_image_save(f"{d}/ra.{ext}".encode(), W, H, aux.ctypes.data, 0, 1.0) == 0, R.ref_image_last_error()
         for ours, ref in (("c", "rc"), ("a", "ra")):
-            if ext == "hdr":
+            if ext == "exr":   # uncompressed here, ZIP-compressed there: the same float pixels (B, G, R channels; alpha absent -> 1)
+                a, b = exr(f"{d}/{ours}.exr"), exr(f"{d}/{ref}.exr")
+                assert a.shape == (H, W, 4) and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+                src = color.copy() if ours == "c" else aux
+                if ours == "a":
+                    assert np.array_equal(a[..., :3], src[..., :3])
+            elif ext == "hdr":
                 a, b = api.load_image(f"{d}/{ours}.hdr"), api.load_image(f"{d}/{ref}.hdr")
                 assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
             else:
