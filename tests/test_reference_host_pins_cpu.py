@@ -533,3 +533,72 @@ def test_save_post_processor_matches_reference_writers(R, built, tmp_path):
                     assert np.array_equal(a, b)
                 else:
                     assert np.abs(a - b).max() <= 6 and np.abs(a - b).mean() < 0.6, (np.abs(a - b).max(), np.abs(a - b).mean())
+
+
+def test_scene_file_layer_random_trees(R, built, tmp_path):
+    """300 generated scene files - random nesting, keys, number spellings (integers, fractions, exponents, tiny and huge magnitudes), strings,
+    booleans, comments, and $references (absolute, relative, by index) into a definitions subtree - parsed by the reference's own parser, by the
+    product and by the oracle's front end: identical resolved trees."""
+    from btrc_b200 import api
+    from oracle import front
+
+    R = _json_api(R)
+    rng = np.random.default_rng(77)
+
+    def number():
+        k = rng.integers(0, 9)
+        if k == 0:
+            return str(int(rng.integers(-1000, 1000)))
+        if k == 1:
+            return "%.*f" % (int(rng.integers(1, 9)), rng.normal(0, 10 ** float(rng.integers(-3, 4))))
+        if k == 2:
+            return "%.*e" % (int(rng.integers(0, 8)), rng.normal(0, 10 ** float(rng.integers(-12, 12))))
+        if k == 3:
+            return "%dE%+d" % (rng.integers(1, 99), rng.integers(-8, 8))
+        if k == 4:
+            return str(int(rng.integers(-2 ** 31, 2 ** 31)))
+        if k == 5:
+            return "%.10g" % (float(rng.integers(1, 2 ** 24)) + 0.5)
+        if k == 6:
+            return rng.choice(["0", "-0", "0.0", "-0.0", "1e-7", "4.9e-7", "5.1e-7", "0.1", "16777216", "16777217.0", "1e38", "-3.4e38", "123456.789"])
+        if k == 7:
+            return "%.7f" % rng.random()
+        return "%d.%d" % (rng.integers(0, 50), rng.integers(0, 1000000))
+
+    def scalar():
+        k = rng.integers(0, 6)
+        if k <= 2:
+            return number()
+        if k == 3:
+            return rng.choice(["true", "false"])
+        return '"%s"' % "".join(rng.choice(list("abcXYZ 019_-./")) for _ in range(int(rng.integers(0, 9))))
+
+    def tree(depth, refs):
+        k = rng.integers(0, 10)
+        if depth >= 4 or k < 4:
+            if refs and rng.random() < 0.25:
+                return '"$reference{%s}"' % rng.choice(refs)
+            return scalar()
+        if k < 7:
+            return "[" + ", ".join(tree(depth + 1, refs) for _ in range(int(rng.integers(0, 5)))) + "]"
+        keys = ["k%d" % i for i in rng.permutation(8)[:int(rng.integers(0, 6))]]
+        if keys and rng.random() < 0.2:
+            keys.append(keys[0])                      # duplicate key: the later value wins, the first position stays
+        body = ", ".join('"%s": %s%s' % (key, "/* c */ " if rng.random() < 0.1 else "", tree(depth + 1, refs)) for key in keys)
+        return "{" + body + "}"
+
+    for i in range(300):
+        defs = {"d%d" % j: tree(2, []) for j in range(4)}
+        refs = ["$root/defs/d%d" % j for j in range(4)] + ["defs/d%d" % j for j in range(4)]
+        text = "// generated %d\n{\n  \"defs\": {%s},\n  \"list\": [%s, \"$reference{0}\"],\n  \"body\": %s,\n  \"tail\": %s\n}\n" % (
+            i, ", ".join('"%s": %s' % kv for kv in defs.items()), scalar(), tree(0, refs), tree(1, refs + ["list/0", "body"]))
+        path = str(tmp_path / ("g%d.json" % i))
+        open(path, "w").write(text)
+        want = R.ref_json_dump(path.encode())
+        if want is None:   # e.g. a number the JSON library refuses: the product must refuse it too
+            with pytest.raises(api.BtrcError):
+                api.scene_file_dump(path)
+            continue
+        want = want.decode()
+        assert api.scene_file_dump(path) == want, (i, text)
+        assert _front_dump(front.parse_scene_file(path)) == want, (i, text)
