@@ -79,6 +79,7 @@ def lib():
         L.btrc_medium.argtypes = L.btrc_shade.argtypes
         L.btrc_shadow.argtypes = [c_void_p, c_int, c_int32] + [c_void_p] * 4
         L.btrc_geometry_tables.argtypes = [c_void_p, c_int32, POINTER(c_int32), c_void_p]
+        L.btrc_geometry_positions.argtypes = [c_void_p, c_int32, POINTER(c_int32), c_void_p]
         L.btrc_instance_transform.argtypes = [c_void_p, c_int32, c_void_p, c_void_p]
         L.btrc_ibl_table.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]
         L.btrc_set_reporter.argtypes = [c_void_p, PROGRESS_FN, c_void_p]
@@ -270,6 +271,14 @@ class Scene:
         _check(self.L.btrc_geometry_tables(self.h, geometry_id, byref(n), None))
         out = np.zeros((n.value, 24), np.float32)
         _check(self.L.btrc_geometry_tables(self.h, geometry_id, byref(n), _p(out)))
+        return out
+
+    def geometry_positions(self, geometry_id):
+        """Local-space corner positions, (ntri, 3, 3) float32 (host side only)."""
+        n = c_int32(0)
+        _check(self.L.btrc_geometry_positions(self.h, geometry_id, byref(n), None))
+        out = np.zeros((n.value, 3, 3), np.float32)
+        _check(self.L.btrc_geometry_positions(self.h, geometry_id, byref(n), _p(out)))
         return out
 
     def ibl_table(self):

@@ -550,6 +550,17 @@ int btrc_geometry_tables(btrc_scene_t *s, int32_t geometry_id, int32_t *n_triang
     });
 }
 
+int btrc_geometry_positions(btrc_scene_t *s, int32_t geometry_id, int32_t *n_triangles, float *out9) {
+    return guarded([&] {
+        check_scene(s);
+        if (geometry_id < 0 || geometry_id >= (int)s->scene->meshes.size()) throw Error("geometry id out of range");
+        const MeshData &m = s->scene->meshes[geometry_id];
+        if (n_triangles) *n_triangles = m.ntri;
+        if (!out9) return;
+        for (size_t i = 0; i < m.pos.size(); ++i) { out9[3 * i] = m.pos[i].x; out9[3 * i + 1] = m.pos[i].y; out9[3 * i + 2] = m.pos[i].z; }
+    });
+}
+
 int btrc_ibl_table(btrc_scene_t *s, int32_t *lut_w, int32_t *lut_h, float *probs) {
     return guarded([&] {
         check_scene(s);

@@ -157,6 +157,9 @@ int btrc_shadow(btrc_scene_t *scene, int memory, int32_t n, const uint32_t *shad
 /* Table access for parity tests: the six float4 shading tables of geometry `geometry_id` (24 floats per triangle,
  * geometry/triangle_mesh.cpp:40-106) and the instance transforms (local_to_world, world_to_local; 3x4 row-major). */
 int btrc_geometry_tables(btrc_scene_t *scene, int32_t geometry_id, int32_t *n_triangles, float *out24);
+/* TriangleMeshLoader::get_positions (utils/triangle_mesh_loader.cpp:61-123, after transform_to_unit_cube :193-213 when the geometry asks for it):
+ * the local-space corner positions of the mesh, 9 floats per triangle in primitive order.  Host side only. */
+int btrc_geometry_positions(btrc_scene_t *scene, int32_t geometry_id, int32_t *n_triangles, float *out9);
 int btrc_instance_transform(btrc_scene_t *scene, int32_t instance_id, float *mat12, float *inv12);
 /* EnvirLightSampler::preprocess result (light/env_sampler.cpp:72-122): the normalised lut_w * lut_h tile table of the "ibl"
  * environment light, computed on the device at commit.  probs may be NULL to query the size. */

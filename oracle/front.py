@@ -474,6 +474,7 @@ class Transform3D:
 
 # --------------------------------------------------------------------------- OBJ
 _OBJ_CACHE = {}
+_OBJ_VERTICES = {}  # every "v" of the file, used or not: what transform_to_unit_cube takes its bounding box from
 
 
 def load_obj(filename: str):
@@ -602,6 +603,7 @@ def _load_obj(filename: str):
             has_nor[i] = 1
         if ti >= 0:
             uv[i] = vts[ti]
+    _OBJ_VERTICES[filename] = np.array(vs, f32).reshape(-1, 3)
     return pos, nor, has_nor, uv
 
 
@@ -889,7 +891,7 @@ class OracleScene:
                 pos, nor, has_nor, uv = load_obj(self.resolve(g.child("filename").as_str()))
                 read_pos = None
                 if g.bool_or("transform_to_unit_cube", False):
-                    read_pos, pos = pos, _to_unit_cube(pos)
+                    read_pos, pos = pos, _to_unit_cube(pos, _OBJ_VERTICES[self.resolve(g.child("filename").as_str())])
                 pool[("geo", id(g.raw))] = self.add_mesh_arrays(pos, nor, has_nor, uv, read_pos)
             m = ent.child("material")
             if ("mat", id(m.raw)) not in pool:
@@ -1064,8 +1066,10 @@ def state_ptrs(st):
             _ptr(st["path_rad"], c_float), _ptr(st["rng"], c_uint64), _ptr(st["ble"], c_float)]
 
 
-def _to_unit_cube(pos):  # triangle_mesh_loader.cpp:193-213 (applied to the position list)
-    lo, hi = pos.min(axis=0), pos.max(axis=0)
+def _to_unit_cube(pos, vertices):
+    """triangle_mesh_loader.cpp:193-213.  The loader still holds the file's indexed vertex list when this runs, so the bounding box is that
+    of EVERY "v" line, referenced by a face or not (pinned against the reference's loader: tests/test_reference_host_pins_cpu.py, "random_unit_cube")."""
+    lo, hi = vertices.min(axis=0), vertices.max(axis=0)
     ext = hi - lo
     m = ext.max()
     scale = f32(1) / m if m > 0 else f32(1)

@@ -187,7 +187,29 @@ SYNTAX_CASES = {  # OBJ spellings tinyobj accepts: CRLF, tabs and trailing blank
 }
 
 
-@pytest.mark.parametrize("case", ["cornell", "sphere", "tricky", "tricky_unit_cube", "polygons", "syntax"])
+def _write_random_obj(path, seed):
+    """25 faces of 3-8 corners over a random vertex pool (arbitrary non-planar loops, sometimes with repeated vertices, sometimes nearly flat
+    in z), every corner spelling (v, v/t, v//n, v/t/n), a third of the faces with negative indices."""
+    rng = np.random.default_rng(1000 + seed)
+    nv, nt, nn = 30, 12, 9
+    lines = ["v %.5f %.5f %.5f" % tuple(v) for v in rng.uniform(-1, 1, (nv, 3)) * (1 if seed % 3 else [1, 1, 0.01])]
+    lines += ["vt %.5f %.5f" % tuple(t) for t in rng.uniform(0, 1, (nt, 2))]
+    lines += ["vn %.5f %.5f %.5f" % tuple(n) for n in rng.normal(size=(nn, 3))]
+    for _ in range(25):
+        k = int(rng.integers(3, 9))
+        vs = rng.choice(nv, k, replace=(seed % 5 == 0)) + 1
+        fmt = int(rng.integers(0, 4))
+        neg = rng.random() < 0.3
+        toks = []
+        for v in vs:
+            vi = int(v) - nv - 1 if neg else int(v)
+            ti, ni = int(rng.integers(1, nt + 1)), int(rng.integers(1, nn + 1))
+            toks.append([f"{vi}", f"{vi}/{ti}", f"{vi}//{ni}", f"{vi}/{ti}/{ni}"][fmt])
+        lines.append("f " + " ".join(toks))
+    open(path, "w").write("\n".join(lines) + "\n")
+
+
+@pytest.mark.parametrize("case", ["cornell", "sphere", "tricky", "tricky_unit_cube", "polygons", "syntax", "random", "random_unit_cube"])
 def test_mesh_loader_matches_reference(R, built, tmp_path, case):
     """Oracle front-end (oracle/front.py + liborc) and the product's host loader against TriangleMeshLoader: same triangles in
     the same order, bit-identical positions and shading tables."""
@@ -202,6 +224,11 @@ def test_mesh_loader_matches_reference(R, built, tmp_path, case):
         v, f, uv, n = scenes.uv_sphere(9, 14)
         objs = [os.path.join(str(tmp_path), "sphere.obj")]
         scenes.write_obj(objs[0], v, f, uv, n)
+    elif case.startswith("random"):
+        objs = []
+        for seed in range(20):
+            objs.append(os.path.join(str(tmp_path), "r%d.obj" % seed))
+            _write_random_obj(objs[-1], seed)
     elif case == "syntax":
         objs = []
         for name, text in SYNTAX_CASES.items():
@@ -231,6 +258,7 @@ def test_mesh_loader_matches_reference(R, built, tmp_path, case):
         assert np.array_equal(got.view(np.uint32), ref_tab.view(np.uint32)), os.path.basename(obj)
         s = api.Scene(sp)                                                                            # product: host side only, no device call
         assert np.array_equal(s.geometry_tables(0).view(np.uint32), ref_tab.view(np.uint32)), os.path.basename(obj)
+        assert np.array_equal(s.geometry_positions(0).view(np.uint32), ref_pos.view(np.uint32)), os.path.basename(obj)
         s.close()
 
 
