@@ -82,7 +82,7 @@ def run(per_seed=1500, seed=1):
                         f"{d}/main.cpp", os.path.join(host, "mesh.cpp"), os.path.join(host, "node.cpp"), "-o", f"{d}/fuzz"], check=True)
         a = scenes.make_material_test(f"{d}/m", width=32, height=18, spp=1, rings=4, segments=6, tex_res=8, state_count=1000)
         b = scenes.make_medium_scene(f"{d}/v", width=32, height=18, spp=1, grid_res=4, state_count=1000)
-        open(f"{d}/q.obj", "w").write("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvn 0 0 1\nvt 0 0\nvt 1 0\nvt 1 1\nf 1/1/1 2/2/1 3/3/1 4//1\nf -4 -3 -2\nf 1//1 2//1 3//1\n")
+        open(f"{d}/q.obj", "w").write("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvn 0 0 1\nvt 0 0\nvt 1 0\nvt 1 1\nf 1/1/1 2/2/1 3/3/1 4//1\nf -4 -3 -2\nf 1//1 2//1 3//1\nv 2 0.5 0\nv 0.5 0.4 0.1\nf 1 2 5 3 6 4\nf 1 2 3 4 5 6 1 2\n")
         seeds = [a, b, os.path.join(f"{d}/m", sorted(f for f in os.listdir(f"{d}/m") if f.endswith(".obj"))[0]),
                  os.path.join(ROOT, "scenes", "assets", "cornell_box.obj"), f"{d}/q.obj"]
         os.makedirs(f"{d}/mut")
