@@ -62,11 +62,15 @@ class ReferenceScene:
         if not self.h:
             raise RuntimeError("reference failed on %s: %s" % (filename, self.L.refcpu_last_error().decode()))
         self.h = c_void_p(self.h)
-        info = np.zeros(8, np.int64)
+        info = np.zeros(9, np.int64)
         self.L.refcpu_info(self.h, _ptr(info, c_int64))
         self.width, self.height, self.spp, self.state_count = (int(v) for v in info[:4])
         self._has_medium = bool(info[4])
         self.ntri, self.ninst, self._vol_prim_medium_id = int(info[5]), int(info[6]), int(info[7])
+        # core/scene.cpp:136-161: instances without a medium get the id `medium_indices.size() - 1`, evaluated after the nullptr key
+        # exists: one PAST the table (access_medium's `unreachable` default).  Oracle and product give such rays the
+        # volume-primitive medium, the id just below it.
+        self.null_medium_id = int(info[8])
 
     def close(self):
         if self.h:
@@ -76,6 +80,12 @@ class ReferenceScene:
     def _check(self, rc):
         if rc != 0:
             raise RuntimeError(self.L.refcpu_last_error().decode())
+
+    def to_oracle_ids(self, o_med):
+        """Reference medium ids -> the oracle's convention, in place on an (n, 4) o_med array (see null_medium_id)."""
+        w = o_med[:, 3].view(np.uint32)
+        w[w == self.null_medium_id] = self._vol_prim_medium_id
+        return o_med
 
     def has_medium(self): return self._has_medium
     def vol_prim_medium_id(self): return self._vol_prim_medium_id

@@ -16,7 +16,7 @@ OUT=$HERE/../_ref
 OBJ=$OUT/obj_refcpu
 CXX=/usr/bin/g++
 test -d $REF/src/builtin || { echo "reference tree not present; keeping prebuilt _ref"; exit 1; }
-mkdir -p $OBJ $OUT/gen_inc/cuj/dsl $OUT/jit
+mkdir -p $OBJ $OUT/gen_inc/cuj/dsl
 CLS=$REF/lib/cuj/cuj/inc/cuj/dsl/class.h
 python3 - "$CLS" "$OUT/gen_inc/cuj/dsl/class.h" <<'PY'
 import sys

@@ -572,13 +572,14 @@ refcpu_scene *refcpu_open(const char *scene_filename)
 
 void refcpu_close(refcpu_scene *s) { delete s; }
 
-// out[0..7] = width, height, spp, state_count, has_medium, triangle count, instance count, volume-primitive medium id
+// out[0..8] = width, height, spp, state_count, has_medium, triangle count, instance count, volume-primitive medium id, medium count
 void refcpu_info(refcpu_scene *s, int64_t *out)
 {
     out[0] = s->width; out[1] = s->height; out[2] = s->params.spp; out[3] = s->params.state_count; out[4] = s->has_medium;
     out[5] = (int64_t)refcpu::world_triangles(s->scene->get_tlas()).inst_prim.size() / 2;
     out[6] = s->scene->get_instance_count();
     out[7] = (int64_t)s->scene->get_volume_primitive_medium_id();
+    out[8] = s->scene->get_medium_count();
 }
 double refcpu_jit_seconds(refcpu_scene *s) { return s->jit_seconds; }
 float refcpu_world_diagonal(refcpu_scene *s) { return s->world_diagonal; }

@@ -152,7 +152,10 @@ void PTXGenerator::generate(const dsl::Module &mod) {
     llvm_ir_ = text;  // get_llvm_ir(): the generated source, for inspection
 
     const std::string base = lib_dir();
-    const std::string jit_dir = env_or("REFCPU_JIT_DIR", base + "/jit");
+    // generated text is reproducible only for scenes whose objects the reference does not order by address (its material / geometry /
+    // medium ids follow std::map<RC<...>> pointer order, core/scene.cpp:112-158), so the cache mostly serves repeated opens of one
+    // scene inside a process and the small fixed kernels (preview, tonemap); it lives outside the repo
+    const std::string jit_dir = env_or("REFCPU_JIT_DIR", "/tmp/refcpu_jit_" + std::to_string(getuid()));
     const std::string inc_dir = env_or("REFCPU_PRELUDE_DIR", base + "/../refcpu");
     const std::string opt = env_or("REFCPU_JIT_OPT", "-O1");
     mkdir(jit_dir.c_str(), 0755);

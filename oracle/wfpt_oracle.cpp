@@ -244,13 +244,24 @@ struct Sampler {  // independent.cpp:11-25, core/sampler.h:22-28; halton.cpp:46-
 // ------------------------------------------------------------------------------------------
 struct AliasUnit { float accept_prob; uint32_t another_idx; };
 
+// 0: sequential sum (MSVC /fp:precise, the reference's toolchain); 1: libstdc++'s std::reduce (groups of four) -- the order
+// the reference has when it is compiled HERE (oracle/_ref/libbtrcrefcpu.so), selected by tests that compare against it
+static int g_reduce_order = 0;
+
 struct AliasTable {
     std::vector<AliasUnit> units;
     void initialize(const std::vector<float> &probs) {
         float sum = 0.0f;
         // std::reduce(.., 0.0f, plus) leaves the association order unspecified: MSVC, the reference's toolchain, adds sequentially
         // under /fp:precise (libstdc++ adds in groups of four; tests/test_reference_host_pins_cpu.py pins both regimes)
-        for (float p : probs) sum = sum + p;
+        size_t first = 0;
+        if (g_reduce_order == 1)  // libstdc++ <numeric> std::reduce, random-access branch
+            for (; probs.size() - first >= 4; first += 4) {
+                const float v1 = probs[first] + probs[first + 1], v2 = probs[first + 2] + probs[first + 3];
+                const float v3 = v1 + v2;
+                sum = sum + v3;
+            }
+        for (; first < probs.size(); ++first) sum = sum + probs[first];
         const float ratio = probs.size() / sum;
         std::vector<uint32_t> overs, unders;
         units.resize(probs.size());
@@ -1968,6 +1979,7 @@ void orc_pcg_stream(uint32_t px, uint32_t py, int sample_index, int n, uint32_t 
         out_f32[i] = sm.get1d();
     }
 }
+void orc_set_reduce_order(int mode) { g_reduce_order = mode; }
 void orc_alias_build(int n, const float *probs, float *accept, uint32_t *alias) {
     AliasTable t; t.initialize(std::vector<float>(probs, probs + n));
     for (int i = 0; i < n; ++i) { accept[i] = t.units[i].accept_prob; alias[i] = t.units[i].another_idx; }
