@@ -55,6 +55,16 @@ def make_scene(workload, out_dir, spp=None, tile=False):
     return path
 
 
+def workload_config(workload):
+    """The `config` object both arms print (same keys, so the driver can tell they ran the same workload)."""
+    w = WORKLOADS[workload]
+    return {"workload": workload, "width": w["width"], "height": w["height"], "spp": w["spp"]}
+
+
+def scaling_of(args):
+    return "strong" if WORKLOADS[args.workload].get("strong") else "weak"
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """Samples SM clocks / throttle reasons during the timed region (B200_PROFILING.md recipe) through NVML in a
@@ -189,42 +199,76 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+class CpuArm:
+    """The reference's wavefront renderer on the host cores.  kind "reference": oracle/_ref/libbtrcrefcpu.so -- Btrc's own
+    scene loading, kernels (through CUJ's LLVM-free C++ generator) and host loop compiled from /root/reference where it lies,
+    lib/bvh standing in for OptiX (oracle/refcpu/refcpu.cpp); the kernels of a scene are compiled with g++ when the scene is
+    opened (the reference compiles its kernels per scene too, wavefront.cpp:141-179).  kind "port": the oracle restatement
+    (oracle/liborc.so), used when that library or the host compiler is not there."""
+
+    def __init__(self, scene_path):
+        from oracle import front
+
+        self.kind, self.note = "port", ""
+        self.ref = None
+        try:
+            from oracle import refcpu
+
+            if refcpu.available():
+                os.environ.pop("OMP_NUM_THREADS", None)  # torchrun exports OMP_NUM_THREADS=1 to every rank
+                t0 = time.perf_counter()
+                self.ref = refcpu.ReferenceScene(scene_path)
+                self.kind = "reference"
+                self.note = "oracle/_ref/libbtrcrefcpu.so (reference sources + CUJ C++ back end, g++ -O1; kernels compiled in %.0f s, untimed)" % (time.perf_counter() - t0)
+        except Exception as e:  # no host compiler on this box, or a scene feature the host build lacks
+            self.note = "reference host build unavailable (%s); " % str(e).strip().splitlines()[-1][:120]
+        if self.ref is None:
+            subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+            front.lib().orc_use_all_cores()
+            self.orc = front.OracleScene(scene_path)
+            self.note += "oracle/liborc.so (restatement), OpenMP"
+        self.cores = os.cpu_count() if self.ref is not None else front.lib().orc_num_threads()
+
+    def render(self, spp):
+        """Renders `spp` samples per pixel; returns (seconds, rays)."""
+        t0 = time.perf_counter()
+        if self.ref is not None:
+            self.ref.set_spp(spp)
+            r = self.ref.render()
+        else:
+            r = self.orc.render(0, spp)
+        return time.perf_counter() - t0, r["stats"]["n_closest"] + r["stats"]["n_shadow"]
+
+
 def run_reference(args):
-    """The reference has no CPU path and cannot be built here (LLVM 11 + OptiX): this arm times the ORACLE restatement
-    (kind "port") on all host cores, each step a bounded sample of the workload (2 of its spp)."""
+    """Times the reference's own CPU execution of the path (CpuArm) on all host cores, each step a bounded sample of the
+    workload (as many of its spp as fit the time budget)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import front
-
-    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
-    front.lib().orc_use_all_cores()  # torchrun exports OMP_NUM_THREADS=1 to every rank
     w = WORKLOADS[args.workload]
     with tempfile.TemporaryDirectory() as d:
         path = make_scene(args.workload, d)
-        o = front.OracleScene(path)
-        t0 = time.perf_counter()
+        arm = CpuArm(path)
+        t1 = 0.0
         for _ in range(max(args.warmup, 1)):
-            o.render(0, 1)
-        t1 = (time.perf_counter() - t0) / max(args.warmup, 1)
+            t1 = arm.render(1)[0]
         # each step = a bounded sample of the workload: as many spp as fit in ~60 s / steps of CPU time
         sample_spp = int(max(1, min(w["spp"], 60.0 / max(args.steps, 1) / max(t1, 1e-3))))
-        t0 = time.perf_counter()
-        rays = 0
+        dt, rays = 0.0, 0
         for k in range(args.steps):
-            r = o.render(0, sample_spp)
-            rays += r["stats"]["n_closest"] + r["stats"]["n_shadow"]
-        dt = time.perf_counter() - t0
+            a, b = arm.render(sample_spp)
+            dt += a
+            rays += b
     paths = w["width"] * w["height"] * sample_spp * args.steps
     value = paths / dt / 1e6
-    cores = front.lib().orc_num_threads()
     line = {
         "impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": scaling_of(args), "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "mrays_per_s": rays / dt / 1e6,
-        "config": {"workload": args.workload, "width": w["width"], "height": w["height"], "spp": w["spp"]},
-        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample_spp} of {w['spp']} spp per step ({w['width']}x{w['height']}), oracle/liborc.so, OpenMP"},
+        "config": workload_config(args.workload),
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": arm.cores, "kind": arm.kind,
+                         "sample": f"{sample_spp} of {w['spp']} spp per step ({w['width']}x{w['height']}); " + arm.note},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -418,22 +462,15 @@ def run_ours(args):
                 "peak_source": peak_src, "alg_bytes_per_launch": stages[dom]["alg_bytes_per_launch"],
                 "ms_per_launch": stages[dom]["ms_per_launch"], "bvh_alg": bvh}
 
-    # ---- CPU baseline: the oracle (port) on the host cores of this box, bounded sample of the same workload
-    from oracle import front
-
+    # ---- CPU baseline: the reference's own CPU execution of the path (CpuArm) on the host cores of this box, bounded sample
     cpu = None
     if not args.no_cpu_baseline:
-        front.lib().orc_use_all_cores()
-        o = front.OracleScene(make_scene(args.workload, os.path.join(tmp.name, "cpu")))
-        t0 = time.perf_counter()
-        o.render(0, 1)  # calibration pass: 1 spp
-        t1 = time.perf_counter() - t0
+        arm = CpuArm(make_scene(args.workload, os.path.join(tmp.name, "cpu")))
+        t1, _ = arm.render(1)  # calibration pass: 1 spp
         cpu_spp = int(max(1, min(spp, 15.0 / max(t1, 1e-3))))  # ~15 s of CPU work
-        t0 = time.perf_counter()
-        o.render(0, cpu_spp)
-        cpu_s = time.perf_counter() - t0
-        cpu = {"value": npix * cpu_spp / cpu_s / 1e6, "unit": "Msamples/s", "cores": front.lib().orc_num_threads(), "kind": "port",
-               "sample": f"{cpu_spp} of {spp} spp of the workload ({W}x{H}), oracle/liborc.so on all host cores, {cpu_s:.1f} s"}
+        cpu_s, _ = arm.render(cpu_spp)
+        cpu = {"value": npix * cpu_spp / cpu_s / 1e6, "unit": "Msamples/s", "cores": arm.cores, "kind": arm.kind,
+               "sample": f"{cpu_spp} of {spp} spp of the workload ({W}x{H}), {cpu_s:.1f} s on all host cores; " + arm.note}
 
     e2e_value = n_gen / e2e_s / 1e6
     line = {

@@ -27,7 +27,10 @@ def test_reference_arm_line(built):
     assert d["metric"] == "Msamples/s" and d["unit"] == "Msamples/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["config"]["workload"] == "c1_cornell_512_16spp" and d["steps"] == 2 and d["warmup"] == 1
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "spp" in cb["sample"]
+    from oracle import refcpu
+
+    # "reference" = the reference's own sources built for the host (oracle/_ref/libbtrcrefcpu.so); "port" only where that is absent
+    assert cb["kind"] == ("reference" if refcpu.available() else "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "spp" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["value"] > 0 and d["ms_per_step"] > 0
 
@@ -44,5 +47,5 @@ def test_our_arm_line(built):
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] >= 512 * 512 * 16
     assert d["gpu_launches"] > 0 and d["value"] > 0
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["value"] > 0 and cb["cores"] >= 1
+    assert cb["kind"] in ("reference", "port") and cb["value"] > 0 and cb["cores"] >= 1
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
