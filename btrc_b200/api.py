@@ -108,6 +108,22 @@ def _p(a):
     return c_void_p(a.ctypes.data)
 
 
+def _img(a, what, count, dtype="float32"):
+    """Caller-supplied image / film buffers go to the library as raw pointers: refuse anything whose element type or size is
+    not what the entry point will read or write (numpy arrays and torch tensors)."""
+    if a is None:
+        return None
+    n = a.numel() if hasattr(a, "numel") else a.size
+    dt = str(a.dtype).replace("torch.", "")
+    if dt != dtype:
+        raise BtrcError("%s: expected %s elements, got %s" % (what, dtype, dt))
+    if n != count:
+        raise BtrcError("%s: expected %d elements, got %d" % (what, count, n))
+    if hasattr(a, "is_contiguous") and not a.is_contiguous():
+        raise BtrcError("%s: tensor is not contiguous" % what)
+    return a
+
+
 def _mem(*arrays):
     for a in arrays:
         if a is not None and hasattr(a, "is_cuda") and a.is_cuda:
@@ -124,6 +140,21 @@ def new_state(n):
 
 
 _STATE_KEYS = ("o_med", "d_t1", "pixel", "beta_depth", "path_rad", "rng", "ble")
+_STATE_TYPES = dict(o_med=(np.float32, 4), d_t1=(np.float32, 4), pixel=(np.uint32, 2), beta_depth=(np.float32, 4), path_rad=(np.float32, 4),
+                    rng=(np.uint64, 2), ble=(np.float32, 4))
+
+
+def _state(st, copy=False):
+    """A caller's path-state batch with the element types and row widths the C ABI reads (raw pointers carry neither)."""
+    n = np.asarray(st["o_med"]).shape[0]
+    out = {}
+    for k in _STATE_KEYS:
+        ty, w = _STATE_TYPES[k]
+        a = np.asarray(st[k])
+        if a.dtype != ty or a.shape != (n, w):
+            raise BtrcError("state array %r: expected %s[%d, %d], got %s%r" % (k, np.dtype(ty).name, n, w, a.dtype, a.shape))
+        out[k] = np.array(a, order="C", copy=True) if copy else np.ascontiguousarray(a)
+    return out
 
 
 class Scene:
@@ -170,6 +201,8 @@ class Scene:
             albedo = np.zeros((i.height, i.width, 4), np.float32)
         if normal is None and i.normal:
             normal = np.zeros((i.height, i.width, 4), np.float32)
+        n4 = 4 * i.width * i.height
+        _img(color, "render color", n4); _img(albedo, "render albedo", n4); _img(normal, "render normal", n4)
         st = RenderStats()
         _check(self.L.btrc_render(self.h, _mem(color), _p(color), _p(albedo), _p(normal), byref(st)))
         return color, albedo, normal, st.as_dict()
@@ -202,13 +235,23 @@ class Scene:
         _check(self.L.btrc_render_range(self.h, int(begin), int(end), byref(st)))
         return st.as_dict()
 
+    def _film_args(self, radiance, weight, albedo, normal):
+        i = self.info
+        npix = i.width * i.height
+        _img(radiance, "film radiance", 4 * npix); _img(weight, "film weight", npix)
+        _img(albedo, "film albedo", 4 * npix); _img(normal, "film normal", 4 * npix)
+
     def film_export(self, radiance, weight, albedo=None, normal=None):
+        self._film_args(radiance, weight, albedo, normal)
         _check(self.L.btrc_film_export(self.h, _mem(radiance, weight), _p(radiance), _p(weight), _p(albedo), _p(normal)))
 
     def film_import(self, radiance, weight, albedo=None, normal=None):
+        self._film_args(radiance, weight, albedo, normal)
         _check(self.L.btrc_film_import(self.h, _mem(radiance, weight), _p(radiance), _p(weight), _p(albedo), _p(normal)))
 
     def resolve(self, color, albedo=None, normal=None):
+        n4 = 4 * self.info.width * self.info.height
+        _img(color, "resolve color", n4); _img(albedo, "resolve albedo", n4); _img(normal, "resolve normal", n4)
         _check(self.L.btrc_resolve(self.h, _mem(color), _p(color), _p(albedo), _p(normal)))
 
     def run_post_processors(self, color, albedo=None, normal=None):
@@ -234,6 +277,7 @@ class Scene:
         return st
 
     def shade(self, st, flag, detail):
+        st = _state(st)
         n = st["o_med"].shape[0]
         nxt = new_state(n)
         sh = dict(pixel=np.zeros((n, 2), np.uint32), beta_li=np.zeros((n, 4), np.float32), o_med=np.zeros((n, 4), np.float32),
@@ -248,8 +292,8 @@ class Scene:
 
     def medium(self, st, flag, detail):
         """Medium stage; returns (state updated in place, flag with the scattered bit, next states, shadow rays)."""
+        st = _state(st, copy=True)
         n = st["o_med"].shape[0]
-        st = {k: np.ascontiguousarray(v.copy()) for k, v in st.items()}
         flag = np.ascontiguousarray(flag.copy(), np.uint32)
         detail = np.ascontiguousarray(detail, np.uint32)
         nxt = new_state(n)
@@ -263,8 +307,8 @@ class Scene:
 
     def shadow(self, sh):
         n = sh["pixel"].shape[0]
-        _check(self.L.btrc_shadow(self.h, HOST, n, _p(np.ascontiguousarray(sh["pixel"])), _p(np.ascontiguousarray(sh["beta_li"])),
-                                  _p(np.ascontiguousarray(sh["o_med"])), _p(np.ascontiguousarray(sh["d_t1"]))))
+        _check(self.L.btrc_shadow(self.h, HOST, n, _p(np.ascontiguousarray(sh["pixel"], np.uint32)), _p(np.ascontiguousarray(sh["beta_li"], np.float32)),
+                                  _p(np.ascontiguousarray(sh["o_med"], np.float32)), _p(np.ascontiguousarray(sh["d_t1"], np.float32))))
 
     def geometry_tables(self, geometry_id):
         n = c_int32(0)

@@ -75,7 +75,16 @@ void copy_any(void *dst, const void *src, size_t bytes) {
         return a.type == cudaMemoryTypeUnregistered || a.type == cudaMemoryTypeHost;
     };
     if (on_host(dst) && on_host(src)) { std::memcpy(dst, src, bytes); return; }  // post-processors on host images need no device
+    // The renderer's stream is non-blocking: it does not order itself against the legacy default stream, and a pageable
+    // host-to-device cudaMemcpy may return once the data is staged.  Copy, then wait for the device, so that a stage kernel
+    // launched next on the renderer's stream can never read a queue before its upload has landed.
     BTRC_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    BTRC_CUDA(cudaStreamSynchronize(0));
+}
+
+// stage entry points write caller batches into pool-sized device queues: refuse before the first copy
+void check_batch(Renderer &r, long long n) {
+    if (n > (long long)r.state_count()) throw Error("stage batch larger than state_count");
 }
 
 void check_scene(btrc_scene_t *s) {
@@ -454,6 +463,7 @@ static void run_state_stage(btrc_scene_t *s, bool medium, int32_t n, float *o_me
     *n_next = 0; *n_shadow = 0;
     if (n <= 0) return;
     Renderer &r = s->r();
+    check_batch(r, n);
     const int W = s->scene->width;
     upload_paths(r, 0, n, W, o_med, d_t1, pixel, beta_depth, path_rad, rng, ble);
     copy_any(r.hits().flag, flag, 4 * (size_t)n);
@@ -518,6 +528,7 @@ int btrc_shadow(btrc_scene_t *s, int memory, int32_t n, const uint32_t *shadow_p
         check_scene(s);
         if (n <= 0) return;
         Renderer &r = s->r();
+        check_batch(r, n);
         const size_t N = (size_t)n;
         const int W = s->scene->width;
         std::vector<float4> b(N);

@@ -46,6 +46,11 @@ int build_lbvh_device(int n, const float4 *tris_in, const uint2 *ids_in, const f
     *nodes_out = nullptr;
     *n_nodes_out = 0;
     if (n <= 0) throw std::runtime_error("lbvh: no primitives");
+    // Leaf references pack `first << 3` into an int, and the traversal kernels walk with a 64-entry stack (traverse.cuh kStackSize).
+    // A radix tree over 30-bit codes with the input index as tie-break is at most 30 + ceil(log2 n) levels deep: below 2^28
+    // primitives that is 58 levels plus the sentinel, inside the stack; beyond it both bounds fail, so refuse (the SAH builder's
+    // counterpart is the `bvh_depth > 60` check in host/scene.cpp).
+    if (n >= (1 << 28)) throw std::runtime_error("lbvh: more than 2^28 - 1 primitives are not supported (leaf reference width, traversal stack depth)");
     const int ni = n - 1;  // internal nodes of the radix tree
     Scratch code(4 * (size_t)n), code2(4 * (size_t)n), index(4 * (size_t)n), index2(4 * (size_t)n), box_in(sizeof(LbvhBox) * (size_t)n);
     Scratch child(sizeof(int2) * (size_t)std::max(ni, 1)), range(sizeof(int2) * (size_t)std::max(ni, 1)), parent(4 * (size_t)(2 * n)),
