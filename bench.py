@@ -37,7 +37,8 @@ WORKLOADS = {
     # BASELINE.json configs[4]: the C2 scene at 4K, 1024 spp in total, split over the ranks (strong scaling: --gpus 2/4/8)
     "c5_disney_4k_1024spp": dict(kind="materials", width=3840, height=2160, spp=1024, strong=True),
 }
-DEFAULT_WORKLOAD = "c2_disney_1080p_256spp"
+DEFAULT_WORKLOAD = "c2_disney_1080p_256spp"   # --gpus 1: the configuration the metric is quoted on
+SCALING_WORKLOAD = "c5_disney_4k_1024spp"     # --gpus N > 1: BASELINE configs[4], total work fixed (strong scaling)
 
 
 def make_scene(workload, out_dir, spp=None, tile=False):
@@ -275,60 +276,108 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Dist:
+    """Process-group facts + the renderer's own NCCL communicator (created once, shared by every workload of the run)."""
 
-    from btrc_b200 import api
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the render path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    w = WORKLOADS[args.workload]
-    W, H, spp = w["width"], w["height"], (args.spp or w["spp"])
-    strong = bool(w.get("strong"))
-    if strong:  # total work fixed: every rank renders spp / world samples per pixel
-        if spp % world:
-            raise SystemExit(f"bench.py: {spp} spp do not split evenly over {world} ranks")
-        spp //= world
-    npix = W * H
-    tmp = tempfile.TemporaryDirectory()
-    tiles = args.partition == "tiles"
-    # samples partition: the scene holds spp * world samples per pixel and every rank renders `spp` of them;
-    # tiles partition: every rank renders all `spp * world` samples of its band of pixels (same number of paths per rank)
-    path = make_scene(args.workload, tmp.name, spp=spp * world, tile=tiles)
-    s = api.Scene(path, state_count=args.state_count)
-    s.set_profiling(False)  # the timed steps carry no per-stage events; the stage breakdown comes from a separate profiled pass
-    stream = torch.cuda.ExternalStream(s.stream_handle())
-    from btrc_b200 import partition
+        from btrc_b200 import api
 
-    begin, end = (partition.tile_path_range if tiles else partition.path_range)(rank, world, spp * world, npix)
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the render path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        api.set_device(self.local_rank)
+        self.comm = None
+        if self.world > 1:
+            # torch.distributed is the plumbing (rendezvous, barrier, max over ranks); the data path's one collective -- the film
+            # reduce -- runs inside the library on its own communicator (btrc_reduce_films), whose id travels over this group
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            box = [api.nccl_unique_id() if self.rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            self.comm = api.Comm(self.world, self.rank, box[0])
 
-    rad = torch.zeros(H, W, 4, device="cuda")
-    wgt = torch.zeros(H, W, device="cuda")
-    color_dev = torch.zeros(H, W, 4, device="cuda")
-    color_host = torch.zeros(H, W, 4).pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
 
-    def barrier():
-        if world > 1:
+        if self.world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max(self, x):
+        import torch
+        import torch.distributed as dist
+
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, xs):
+        import torch
+        import torch.distributed as dist
+
+        t = torch.tensor(list(xs), device="cuda", dtype=torch.float64)
+        if self.world > 1:
+            dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+    def close(self):
+        import torch.distributed as dist
+
+        if self.comm is not None:
+            self.comm.close()
+        if self.world > 1:
+            dist.destroy_process_group()
+
+
+def dram_traffic(workload):
+    """DRAM bytes per ray / state of the traversal and shade kernels from the committed `ncu --set full` capture of this
+    workload (profiles/traffic_<workload>.json, written by scripts/ncu_summary.py traffic)."""
+    tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % workload)
+    return json.load(open(tpath)) if os.path.exists(tpath) else {}
+
+
+def measure(args, D, workload, steps, warmup, spp_override=0, e2e=True, cpu=True, scaling=None, partition=None):
+    """Times `steps` renders of `workload` on the process group D and returns rank 0's result line (None on other ranks)."""
+    import torch
+
+    from btrc_b200 import api
+
+    rank, world = D.rank, D.world
+    w = WORKLOADS[workload]
+    W, H = w["width"], w["height"]
+    scaling = scaling or ("strong" if w.get("strong") else "weak")
+    partition = partition or ("tiles" if w.get("strong") and world > 1 and args.partition == "auto" else (args.partition if args.partition != "auto" else "samples"))
+    tiles = partition == "tiles"
+    spp_total = spp_override or w["spp"]
+    if scaling == "weak":        # per-GPU work fixed: the scene holds spp * world samples per pixel, every rank renders `spp` of them
+        spp_scene = spp_total * world
+    else:                        # total work fixed
+        spp_scene = spp_total
+        if not tiles and spp_scene % world:
+            raise SystemExit(f"bench.py: {spp_scene} spp do not split evenly over {world} ranks")
+    npix = W * H
+    tmp = tempfile.TemporaryDirectory()
+    path = make_scene(workload, tmp.name, spp=spp_scene, tile=tiles)
+    s = api.Scene(path, state_count=args.state_count)
+    s.set_profiling(False)  # the timed steps carry no per-stage events; the stage breakdown comes from a separate profiled pass
+    stream = torch.cuda.ExternalStream(s.stream_handle())
+    color_dev = torch.zeros(H, W, 4, device="cuda") if rank == 0 else None
+    color_host = torch.zeros(H, W, 4).pin_memory() if rank == 0 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
     def step():
-        """One device-resident step: returns the render statistics of this rank."""
+        """One device-resident step: film clear -> this rank's share of the waves -> [ncclReduce of the films] -> resolve on rank 0."""
         s.film_clear()
-        st = s.render_range(begin, end)
-        if world > 1:  # the one collective of the path: sum of the film buffers (radiance float4 + weight), then resolve on rank 0
-            s.film_export(rad, wgt)
-            partition.reduce_films([rad, wgt], 0)
-            if rank == 0:
-                s.film_import(rad, wgt)
+        st = s.render_part(world, rank)
+        if world > 1:
+            s.reduce_films(D.comm, 0)
         if rank == 0:
             s.resolve(color_dev)
         return st
@@ -338,26 +387,28 @@ def run_ours(args):
         if world == 1:
             _, _, _, st = s.render(color_host.numpy())
             return st
-        st = step()
+        s.film_clear()
+        st = s.render_part(world, rank)
+        s.reduce_films(D.comm, 0)
         if rank == 0:
-            color_host.copy_(color_dev, non_blocking=False)
+            s.resolve(color_host.numpy())
         return st
 
     # NVML is initialised before the warm-up steps (its start-up takes driver locks that stall launches for ~100 ms)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(D.local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step()
     if rank == 0:
         sampler.reset()
 
     # ---- timed region: K device-resident steps, CUDA events on the renderer's stream, L2 flushed between steps
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     agg = None
-    barrier()
+    D.barrier()
     t_wall0 = time.perf_counter()
-    for k in range(args.steps):
+    for k in range(steps):
         flush.fill_(k & 0xff)
         torch.cuda.synchronize()
         ev[k][0].record(stream)
@@ -365,24 +416,17 @@ def run_ours(args):
         ev[k][1].record(stream)
         if agg is None:
             agg = {key: 0 for key in st if key != "stage_ms"}
-            agg["stage_ms"] = {key: 0.0 for key in st["stage_ms"]}
         for key, v in st.items():
-            if key == "stage_ms":
-                for kk, vv in v.items():
-                    agg["stage_ms"][kk] += vv
-            else:
+            if key != "stage_ms":
                 agg[key] += v
-    barrier()
+    D.barrier()
     wall = time.perf_counter() - t_wall0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
+    dev_ms = D.max(sum(a.elapsed_time(b) for a, b in ev))
+    render_ms_max = D.max(agg["render_ms"])           # slowest rank's time inside the waves: what the partition balances
 
     # ---- stage breakdown: the same steps again with one CUDA event between consecutive kernels (not part of `value`)
     s.set_profiling(True)
-    prof_steps = min(args.steps, 3)
+    prof_steps = min(steps, 3)
     pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(prof_steps)]
     stage_ms = None
     prof_iters = 0
@@ -402,100 +446,139 @@ def run_ours(args):
     s.set_profiling(False)
 
     # ---- end to end through the public API with host buffers
-    barrier()
-    e2e_t0 = time.perf_counter()
-    for k in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - e2e_t0
-    t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    e2e_s = None
+    if e2e:
+        D.barrier()
+        e2e_t0 = time.perf_counter()
+        for k in range(steps):
+            step_e2e()
+        D.barrier()
+        e2e_s = D.max(time.perf_counter() - e2e_t0)
     clocks = sampler.stop() if rank == 0 else None
 
     # whole-job event counts
-    counts = torch.tensor([agg[k] for k in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss", "n_splat", "n_iter", "n_launches")],
-                          device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(counts)
+    keys = ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss", "n_splat", "n_iter", "n_launches")
+    n_gen, n_closest, n_hit, n_next, n_shadow, n_shadow_miss, n_splat, n_iter, n_launch = D.sum(agg[k] for k in keys)
+    render_ms_sum = D.sum([agg["render_ms"]])[0]
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    n_gen, n_closest, n_hit, n_next, n_shadow, n_shadow_miss, n_splat, n_iter, n_launch = [float(x) for x in counts.tolist()]
+        s.close()
+        return None
     secs = dev_ms / 1e3
     value = n_gen / secs / 1e6
     mrays = (n_closest + n_shadow) / secs / 1e6
 
     # ---- roofline of the dominant kernel (rank 0's stage times; algorithmic bytes per SURVEY 8d)
-    bvh = None if args.no_cpu_baseline else bvh_alg_per_ray(path)
+    bvh = bvh_alg_per_ray(path) if cpu else None
     peak, peak_src = measured_peak()
     sb = stage_bytes({k: agg[k] for k in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss", "n_splat")}, bvh,
                      has_medium=bool(s.info.has_medium))
     iters = max(prof_iters, 1)
     stages = {}
     sb["bookkeeping"] = 0
-    scale = prof_steps / args.steps  # the byte totals cover K timed steps, the stage times `prof_steps` identical ones
+    scale = prof_steps / steps  # the byte totals cover K timed steps, the stage times `prof_steps` identical ones
+    traffic_db = dram_traffic(workload)
+    units_of = {"trace": agg["n_closest"], "shadow": agg["n_shadow"], "shade": agg["n_hit"], "medium": agg["n_closest"], "generate": agg["n_gen"]}
     for name in ("generate", "trace", "medium", "shade", "shadow", "bookkeeping"):
         ms = stage_ms[name]
         if name == "medium" and not s.info.has_medium:
             continue
         nbytes = sb[name] * scale
         gbs = nbytes / (ms / 1e3) / 1e9 if ms > 0 else 0.0
-        stages[name] = {"ms_total": ms, "launches": iters, "ms_per_launch": ms / iters, "alg_bytes_per_launch": nbytes / iters,
-                        "achieved_gbs": gbs, "frac": gbs / peak, "share_of_step": ms / prof_ms}
+        st_line = {"ms_total": ms, "launches": iters, "ms_per_launch": ms / iters, "alg_bytes_per_launch": nbytes / iters,
+                   "achieved_gbs": gbs, "frac": gbs / peak, "share_of_step": ms / prof_ms}
+        t = traffic_db.get(name)
+        if t and t.get("dram_bytes_per_unit") and ms > 0:
+            dram = t["dram_bytes_per_unit"] * units_of[name] * scale
+            # measured DRAM bytes (ncu, per ray / state) x this run's units over this run's stage time: the fraction of the HBM
+            # peak the kernel really moves, next to the SURVEY 8d figure whose BVH term is served by L1 / L2 when the tree fits
+            st_line["dram_gbs"] = dram / (ms / 1e3) / 1e9
+            st_line["dram_frac"] = st_line["dram_gbs"] / peak
+            st_line["dram_bytes_per_launch"] = dram / iters
+        stages[name] = st_line
     dom = max((k for k in stages if k != "bookkeeping"), key=lambda k: stages[k]["ms_total"])
-    # DRAM traffic of the dominant kernel: bytes per ray / state from the committed ncu --set full capture of this workload
-    # (profiles/traffic_<workload>.json, written by scripts/ncu_summary.py traffic), scaled to this run's units per launch
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
-    if os.path.exists(tpath):
-        t = json.load(open(tpath)).get(dom)
-        if t and t.get("dram_bytes_per_unit"):
-            units = {"trace": agg["n_closest"], "shadow": agg["n_shadow"], "shade": agg["n_hit"]}.get(dom)
-            if units:
-                traffic = t["dram_bytes_per_unit"] * units * scale / iters
+    info = s.info
+    bvh_bytes = int(info.bvh_bytes) if hasattr(info, "bvh_bytes") else None
+    L2 = 126 << 20
+    resident = bvh_bytes is not None and bvh_bytes < L2
     roofline = {"kernel": dom + "_kernel",
                 "bound": "hbm", "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"],
-                "traffic": traffic, "traffic_source": ("profiles/traffic_%s.json (ncu dram__bytes_read+write per ray x rays per launch)" % args.workload) if traffic else None,
+                "traffic": stages[dom].get("dram_bytes_per_launch"),
+                "traffic_source": ("profiles/traffic_%s.json (ncu dram__bytes_read+write per ray x rays per launch)" % workload) if stages[dom].get("dram_bytes_per_launch") else None,
+                "dram_frac": stages[dom].get("dram_frac"),
+                "limiter": ("L1/L2 latency and SIMT divergence: the BVH (%.0f MB) is resident in the 126 MB L2, so `frac` (SURVEY 8d algorithmic bytes, 96 %% of them "
+                            "BVH nodes) is the rate at which the caches serve the walk, `dram_frac` what reaches HBM" % (bvh_bytes / 1e6)) if resident else
+                           ("HBM latency: the BVH (%.0f MB) exceeds the L2" % (bvh_bytes / 1e6) if bvh_bytes else None),
                 "peak_source": peak_src, "alg_bytes_per_launch": stages[dom]["alg_bytes_per_launch"],
                 "ms_per_launch": stages[dom]["ms_per_launch"], "bvh_alg": bvh}
 
     # ---- CPU baseline: the reference's own CPU execution of the path (CpuArm) on the host cores of this box, bounded sample
-    cpu = None
-    if not args.no_cpu_baseline:
-        arm = CpuArm(make_scene(args.workload, os.path.join(tmp.name, "cpu")))
+    cpu_line = None
+    if cpu:
+        arm = CpuArm(make_scene(workload, os.path.join(tmp.name, "cpu")))
         t1, _ = arm.render(1)  # calibration pass: 1 spp
-        cpu_spp = int(max(1, min(spp, 15.0 / max(t1, 1e-3))))  # ~15 s of CPU work
+        cpu_spp = int(max(1, min(w["spp"], 15.0 / max(t1, 1e-3))))  # ~15 s of CPU work
         cpu_s, _ = arm.render(cpu_spp)
-        cpu = {"value": npix * cpu_spp / cpu_s / 1e6, "unit": "Msamples/s", "cores": arm.cores, "kind": arm.kind,
-               "sample": f"{cpu_spp} of {spp} spp of the workload ({W}x{H}), {cpu_s:.1f} s on all host cores; " + arm.note}
+        cpu_line = {"value": npix * cpu_spp / cpu_s / 1e6, "unit": "Msamples/s", "cores": arm.cores, "kind": arm.kind,
+                    "sample": f"{cpu_spp} of {w['spp']} spp of the workload ({W}x{H}), {cpu_s:.1f} s on all host cores; " + arm.note}
 
-    e2e_value = n_gen / e2e_s / 1e6
+    cfg = workload_config(workload)
+    cfg.update({"spp_rendered_per_step": spp_scene, "gpus": world, "state_count": s.info.state_count,
+                "partition": (("image tiles: strips of %d pixel rows dealt round-robin to the ranks (tile-mode indexing)" % __import__("btrc_b200.partition", fromlist=["x"]).strip_rows(world, H)
+                               if tiles else "sample-index ranges per rank") +
+                              "; ncclReduce(sum) of the radiance+weight films onto rank 0 inside the library (btrc_reduce_films), resolve on rank 0") if world > 1 else "single GPU",
+                "timing": "CUDA events on the renderer's stream per step, max over ranks; 256 MB L2 flush (untimed) between steps; "
+                          "roofline_stages from a separate pass of %d identical steps with one CUDA event between kernels (%.1f ms/step)" % (prof_steps, prof_ms / prof_steps),
+                "wall_ms_per_step_incl_flush": wall / steps * 1e3})
     line = {
-        "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "mrays_per_s": mrays,
-        "config": {"workload": args.workload, "width": W, "height": H, "spp_per_gpu": spp, "state_count": s.info.state_count,
-                   "partition": (("image tiles (row bands of pixels, Tile-mode indexing) per rank" if tiles else "sample index ranges per rank") +
-                                 "; NCCL sum-reduce of radiance+weight films to rank 0; resolve on rank 0") if world > 1 else "single GPU",
-                   "timing": "CUDA events on the renderer's stream per step, max over ranks; 256 MB L2 flush (untimed) between steps; "
-                             "roofline_stages from a separate pass of %d identical steps with one CUDA event between kernels (%.1f ms/step)" % (prof_steps, prof_ms / prof_steps),
-                   "wall_ms_per_step_incl_flush": wall / args.steps * 1e3},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": 208, "d2h_bytes_per_step": int(npix * 16 + 208 * (n_iter / args.steps / world)),
-                "note": "api.Scene.render() into pinned host memory: film clear, waves, resolve, D2H of the W*H float4 image; the scene (BVH, tables) stays resident like model weights; H2D per step is the wave control block"},
-        "gpu_launches": int(n_launch + args.steps * (3 + 1)),
+        "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
+        "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "mrays_per_s": mrays, "config": cfg, "clocks": clocks,
+        "gpu_launches": int(n_launch + steps * (3 + 1)),
         "events": {"n_gen": n_gen, "n_closest": n_closest, "n_hit": n_hit, "n_next": n_next, "n_shadow": n_shadow, "n_shadow_miss": n_shadow_miss,
-                   "n_splat": n_splat, "iterations_per_step": n_iter / args.steps / world},
+                   "n_splat": n_splat, "iterations_per_step": n_iter / steps / world},
         "roofline": roofline,
         "roofline_stages": stages,
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu_line,
     }
-    emit(line)
+    if e2e_s is not None:
+        line["e2e"] = {"value": n_gen / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 208,
+                       "d2h_bytes_per_step": int(npix * 16 + 208 * (n_iter / steps / world)),
+                       "note": "api.Scene.render() into pinned host memory: film clear, waves, resolve, D2H of the W*H float4 image; the scene (BVH, tables) stays "
+                               "resident like model weights; H2D per step is the wave control block"}
     if world > 1:
-        dist.destroy_process_group()
+        # what limits the curve: the slowest rank's wave time against the mean (partition balance), and what is left of the step
+        # after the waves (film reduce + resolve + launch gaps)
+        line["multi_gpu"] = {"render_ms_per_step_slowest_rank": render_ms_max / steps, "render_ms_per_step_mean_rank": render_ms_sum / steps / world,
+                             "imbalance": render_ms_max / (render_ms_sum / world) - 1.0,
+                             "reduce_resolve_and_gaps_ms_per_step": dev_ms / steps - render_ms_max / steps}
+    s.close()
+    return line
+
+
+def run_ours(args):
+    D = Dist()
+    workload = args.workload or (DEFAULT_WORKLOAD if D.world == 1 else SCALING_WORKLOAD)
+    line = measure(args, D, workload, args.steps, args.warmup, spp_override=args.spp, cpu=not args.no_cpu_baseline)
+    if D.world == 1 and not args.spp and not args.no_workloads and args.workload is None:
+        # the other BASELINE configurations, short runs (value, clocks, per-stage shares and roofline fractions): BENCH carries all five
+        extra = {}
+        for wl, k, spp in (("c1_cornell_512_16spp", 10, 0), ("c3_medium_1080p_128spp", 3, 0), ("c4_instanced_10m_1080p_128spp", 2, 0),
+                           ("c5_disney_4k_1024spp", 2, 128)):
+            try:
+                r = measure(args, D, wl, k, 3, spp_override=spp, e2e=False, cpu=False, scaling="weak")
+                extra[wl] = {"value": r["value"], "unit": "Msamples/s", "mrays_per_s": r["mrays_per_s"], "ms_per_step": r["ms_per_step"], "steps": k,
+                             "spp_rendered_per_step": r["config"]["spp_rendered_per_step"], "clocks": r["clocks"],
+                             "stages": {n: {"share_of_step": v["share_of_step"], "frac": v["frac"], "dram_frac": v.get("dram_frac"), "ms_per_launch": v["ms_per_launch"]}
+                                        for n, v in r["roofline_stages"].items()}}
+                if wl == "c5_disney_4k_1024spp":
+                    extra[wl]["note"] = "one GPU's share (128 spp) of the 8-GPU strong-scaling run of this configuration: `bench.py --gpus 8` renders all 1024 spp"
+            except Exception as e:  # a side measurement must not take the headline line with it
+                extra[wl] = {"error": str(e)[:200]}
+        if line is not None:
+            line["workloads"] = extra
+    if line is not None:
+        emit(line)
+    D.close()
 
 
 _REAL_STDOUT = None
@@ -525,16 +608,21 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: %s on one GPU, %s (strong scaling) on several" % (DEFAULT_WORKLOAD, SCALING_WORKLOAD))
+    ap.add_argument("--no-workloads", action="store_true", help="skip the short side runs of the other BASELINE configurations")
     ap.add_argument("--state-count", type=int, default=8388608,
                     help="path-state pool (the renderer's `state_count` parameter); 8 Mi states = 2.4 GB of queues (profiles/r1h_sweep_pool.log)")
-    ap.add_argument("--partition", default="samples", choices=["samples", "tiles"],
-                    help="multi-GPU split: sample-index ranges (default, load balanced) or image tiles (row bands, BASELINE config 5's wording)")
+    ap.add_argument("--partition", default="auto", choices=["auto", "samples", "tiles"],
+                    help="multi-GPU split: sample-index ranges or image tiles (interleaved strips of pixel rows); auto = tiles for the "
+                         "strong-scaling configuration (BASELINE config 5's wording), samples otherwise")
     ap.add_argument("--spp", type=int, default=0, help="override the workload's samples per pixel (profiling runs); reported in config")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (roofline bvh statistics, cpu_baseline): profiler runs")
     args = ap.parse_args()
     quiet_stdout()
     if args.impl == "reference":
+        if args.workload is None:
+            args.workload = DEFAULT_WORKLOAD if int(os.environ.get("WORLD_SIZE", "1")) == 1 else SCALING_WORKLOAD
         run_reference(args)
     else:
         run_ours(args)

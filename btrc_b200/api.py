@@ -26,7 +26,7 @@ class BtrcError(RuntimeError):
 class SceneInfo(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in ("width", "height", "spp", "min_depth", "max_depth", "state_count", "tile", "albedo", "normal",
                                        "n_instances", "n_lights", "n_triangles", "n_materials", "bvh_depth", "n_media", "has_medium", "n_textures")] + \
-               [("world_diagonal", c_float), ("bvh_build_seconds", c_float)]
+               [("world_diagonal", c_float), ("bvh_build_seconds", c_float), ("bvh_bytes", c_uint64)]
 
 
 class RenderStats(ctypes.Structure):
@@ -87,6 +87,14 @@ def lib():
         L.btrc_scene_file_dump.argtypes = [c_char_p, c_void_p, c_uint64, POINTER(c_uint64)]
         L.btrc_scene_file_parse.argtypes = [c_char_p, c_char_p, c_int32, c_void_p, POINTER(c_int32)]
         L.btrc_device_sm_count.restype = c_int
+        L.btrc_device_count.restype = c_int
+        L.btrc_set_device.argtypes = [c_int32]
+        L.btrc_render_part.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(RenderStats)]
+        L.btrc_nccl_unique_id.argtypes = [c_void_p]
+        L.btrc_comm_create.argtypes = [c_int32, c_int32, c_void_p, POINTER(c_void_p)]
+        L.btrc_comm_destroy.argtypes = [c_void_p]
+        L.btrc_comm_destroy.restype = None
+        L.btrc_reduce_films.argtypes = [c_void_p, c_void_p, c_int32]
         _lib = L
     return _lib
 
@@ -241,6 +249,16 @@ class Scene:
         _img(radiance, "film radiance", 4 * npix); _img(weight, "film weight", npix)
         _img(albedo, "film albedo", 4 * npix); _img(normal, "film normal", 4 * npix)
 
+    def render_part(self, n_parts, part, rows_per_strip=0):
+        """This device's share of the render (sample ranges, or interleaved row strips when the renderer is in tile mode)."""
+        st = RenderStats()
+        _check(self.L.btrc_render_part(self.h, int(n_parts), int(part), int(rows_per_strip), byref(st)))
+        return st.as_dict()
+
+    def reduce_films(self, comm, root=0):
+        """ncclReduce(sum) of the film planes onto `root`, on the renderer's stream (comm: Comm)."""
+        _check(self.L.btrc_reduce_films(self.h, comm.h, int(root)))
+
     def film_export(self, radiance, weight, albedo=None, normal=None):
         self._film_args(radiance, weight, albedo, normal)
         _check(self.L.btrc_film_export(self.h, _mem(radiance, weight), _p(radiance), _p(weight), _p(albedo), _p(normal)))
@@ -337,6 +355,31 @@ class Scene:
         inv = np.zeros((3, 4), np.float32)
         _check(self.L.btrc_instance_transform(self.h, instance_id, _p(mat), _p(inv)))
         return mat, inv
+
+
+def nccl_unique_id() -> bytes:
+    """128 bytes of an ncclUniqueId (create on one rank, hand to every rank's Comm)."""
+    buf = ctypes.create_string_buffer(128)
+    _check(lib().btrc_nccl_unique_id(buf))
+    return buf.raw
+
+
+class Comm:
+    """The renderer's own NCCL communicator (one rank per process / GPU)."""
+
+    def __init__(self, n_ranks, rank, unique_id: bytes | None):
+        self.h = c_void_p()
+        buf = ctypes.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        _check(lib().btrc_comm_create(int(n_ranks), int(rank), buf, byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().btrc_comm_destroy(self.h)
+            self.h = c_void_p()
+
+
+def set_device(index):
+    _check(lib().btrc_set_device(int(index)))
 
 
 def load_image(path):

@@ -24,7 +24,7 @@ CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
-HOST_SRCS = ["host/node.cpp", "host/mesh.cpp", "host/bvh.cpp", "host/scene.cpp", "host/renderer.cpp", "host/image_io.cpp", "capi.cpp"]
+HOST_SRCS = ["host/node.cpp", "host/mesh.cpp", "host/bvh.cpp", "host/scene.cpp", "host/renderer.cpp", "host/image_io.cpp", "host/comm.cpp", "capi.cpp"]
 DEVICE_SRCS = ["device/kernels.cu", "device/lbvh.cu"]
 
 HOST_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-Wall", "-Wno-unknown-pragmas", f"-I{CUDA_HOME}/include"]
@@ -80,7 +80,7 @@ def build(force=False, verbose=False):
             if verbose and out.strip():
                 print(out)
     if force or jobs or _newer(LIB, objs):
-        _run([NVCC, "-shared", "-cudart", "static", "-ccbin", CXX, "-o", LIB] + objs + ["-Xcompiler", "-fopenmp", "-lz", "-lgomp"])
+        _run([NVCC, "-shared", "-cudart", "static", "-ccbin", CXX, "-o", LIB] + objs + ["-Xcompiler", "-fopenmp", "-lz", "-lgomp", "-ldl"])
     cli_src = os.path.join(CSRC, "cli", "main.cpp")
     if force or _newer(CLI, [cli_src, LIB]):
         _run([CXX, "-std=c++17", "-O2", cli_src, "-o", CLI, f"-L{HERE}", "-lbtrc_b200", "-Wl,-rpath,$ORIGIN"])

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "host/image_io.h"
+#include "host/comm.h"
 #include "host/renderer.h"
 #include "host/scene.h"
 
@@ -156,6 +157,16 @@ int btrc_device_sm_count(void) {
     return n;
 }
 
+int btrc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int btrc_set_device(int32_t device) {
+    return guarded([&] { BTRC_CUDA(cudaSetDevice(device)); });
+}
+
 int btrc_scene_load_json(const char *path, btrc_scene_t **out) {
     return guarded([&] {
         if (!path || !out) throw Error("null argument");
@@ -192,6 +203,8 @@ int btrc_scene_info_get(btrc_scene_t *s, btrc_scene_info_t *o) {
         o->bvh_depth = sc.bvh_depth;
         o->world_diagonal = sc.world_diagonal;
         o->bvh_build_seconds = (float)sc.bvh_build_seconds;
+        o->bvh_bytes = sc.renderer.lbvh ? 64ull * (uint64_t)sc.lbvh_nodes + 48ull * sc.world_tris.size()
+                                        : (uint64_t)(sc.flat_bvh.nodes.size() + sc.flat_bvh.tris.size()) * sizeof(float);
     });
 }
 
@@ -230,6 +243,46 @@ int btrc_render_range(btrc_scene_t *s, int64_t begin, int64_t end, btrc_render_s
     });
     if (rc == 0 && stopped) { g_last_error = "render stopped by the reporter"; return BTRC_STOPPED; }
     return rc;
+}
+
+int btrc_render_part(btrc_scene_t *s, int32_t n_parts, int32_t part, int32_t rows_per_strip, btrc_render_stats_t *stats) {
+    bool stopped = false;
+    const int rc = guarded([&] {
+        check_scene(s);
+        s->r().render_part(n_parts, part, rows_per_strip);
+        stopped = s->r().stopped();
+        fill_stats(s->r().stats(), stats);
+    });
+    if (rc == 0 && stopped) { g_last_error = "render stopped by the reporter"; return BTRC_STOPPED; }
+    return rc;
+}
+
+int btrc_nccl_unique_id(uint8_t *out128) {
+    return guarded([&] { if (!out128) throw Error("null id buffer"); nccl_unique_id(out128); });
+}
+
+int btrc_comm_create(int32_t n_ranks, int32_t rank, const uint8_t *id128, btrc_comm_t **out) {
+    return guarded([&] {
+        if (!out) throw Error("null output handle");
+        *out = nullptr;
+        if (n_ranks > 1 && !id128) throw Error("null NCCL id");
+        static const uint8_t zero[kNcclIdBytes] = {0};
+        *out = reinterpret_cast<btrc_comm_t *>(comm_create(n_ranks, rank, id128 ? id128 : zero));
+    });
+}
+
+void btrc_comm_destroy(btrc_comm_t *comm) { comm_destroy(reinterpret_cast<Comm *>(comm)); }
+
+int btrc_reduce_films(btrc_scene_t *s, btrc_comm_t *comm, int32_t root) {
+    return guarded([&] {
+        check_scene(s);
+        Renderer &r = s->r();
+        const size_t npix = (size_t)s->scene->width * s->scene->height;
+        FilmDevice &f = r.film();
+        float *bufs[4] = {f.radiance, f.weight, f.albedo, f.normal};
+        const size_t counts[4] = {4 * npix, npix, 4 * npix, 4 * npix};
+        comm_reduce_sum(reinterpret_cast<Comm *>(comm), bufs, counts, 4, root, r.stream());
+    });
 }
 
 int btrc_set_reporter(btrc_scene_t *s, btrc_progress_fn fn, void *user) {

@@ -286,6 +286,12 @@ struct WaveCtl {
     int sort_enabled;     // the renderer sorts surviving paths and shadow rays before tracing them
     int n_sorted;         // surviving paths whose visiting order comes from RaySort::order (0: queue order)
     int n_shadow_sorted;  // shadow rays visited through the shadow RaySort (0: queue order)
+    // Strided partition of the path index space (multi-GPU image tiles, interleaved): the render walks VIRTUAL indices
+    // [cursor, end); virtual index v stands for the camera path ((v / stride_block) * stride_parts + stride_part) * stride_block
+    // + v % stride_block.  stride_block == 0: identity (one contiguous range).
+    long long stride_block;
+    int stride_parts, stride_part;
+    int weight_prefilled;  // the film's weight plane was filled in closed form for this render: generate skips its atomic
     // statistics (SURVEY 8d event counts)
     unsigned long long n_gen, n_closest, n_hit, n_next_total, n_shadow_total, n_shadow_miss, n_splat, n_iter;
 };

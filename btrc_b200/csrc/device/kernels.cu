@@ -138,10 +138,17 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(SceneDevice scene, Ren
     const int n_new = ctl->n_new;
     const int base_slot = ctl->n_survivors;
     const long long gen_base = ctl->gen_base;
+    const long long sblock = ctl->stride_block;
+    const int sparts = ctl->stride_parts, spart = ctl->stride_part;
+    const bool splat_weight = ctl->weight_prefilled == 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) {
-        GenOut<HALTON> g = generate_one<HALTON>(scene, P, gen_base + i);
+        long long accu = gen_base + i;
+        if (sblock > 0) accu = ((accu / sblock) * sparts + spart) * sblock + accu % sblock;
+        GenOut<HALTON> g = generate_one<HALTON>(scene, P, accu);
         const uint32_t pixel = g.py * (uint32_t)P.width + g.px;
-        atomicAdd(film.weight + pixel, 1.0f);
+        // generate.cpp:79: film.splat_atomic(pixel, weight, 1).  A render over a known index range fills the plane beforehand
+        // (weight_fill_kernel: the filter keeps every sample inside its own pixel, so the count per pixel is a closed form)
+        if (splat_weight) atomicAdd(film.weight + pixel, 1.0f);
         const int s = base_slot + i;
         q.ray_o[s] = make4(g.o, __uint_as_float(scene.vol_prim_medium_id));
         q.ray_d[s] = make4(g.d, kMaxFloat);
@@ -149,6 +156,37 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(SceneDevice scene, Ren
         q.rad[s] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(pixel));
         q.rng[s] = g.sampler.store();
         q.ble[s] = make_float4(1.0f, 1.0f, 1.0f, -1.0f);
+    }
+}
+
+// Weight plane of a render over the (virtual, see WaveCtl) path index range [begin, end): adds to every pixel the number of
+// camera paths of that range that start in it -- the sum of generate.cpp:79's splats of 1.0f, exact in fp32 below 2^24.
+__global__ void __launch_bounds__(kBlock) weight_fill_kernel(float *weight, int npix, int spp, int tile, long long begin, long long end,
+                                                             long long sblock, int sparts, int spart) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+        long long count = 0;
+        if (sblock <= 0) {
+            if (!tile) {  // index = sample * npix + pixel: samples s with begin <= s * npix + p < end
+                const long long lo = begin - p, hi = end - p;  // s * npix in [lo, hi)
+                const long long s0 = lo <= 0 ? 0 : (lo + npix - 1) / npix, s1 = hi <= 0 ? 0 : (hi + npix - 1) / npix;
+                count = s1 > s0 ? s1 - s0 : 0;
+            } else {      // index = pixel * spp + sample
+                const long long a = (long long)p * spp, b = a + spp;
+                const long long lo = a > begin ? a : begin, hi = b < end ? b : end;
+                count = hi > lo ? hi - lo : 0;
+            }
+        } else {
+            // strided partitions are made of whole pixels in tile mode (stride_block is a multiple of spp): pixel p is ours when
+            // its block belongs to this part and its virtual index lies inside [begin, end)
+            const long long a = (long long)p * spp;
+            const long long blk = a / sblock;
+            if (blk % sparts == spart) {
+                const long long v = (blk / sparts) * sblock + a % sblock;
+                const long long lo = v > begin ? v : begin, hi = v + spp < end ? v + spp : end;
+                count = hi > lo ? hi - lo : 0;
+            }
+        }
+        if (count) weight[p] += (float)count;
     }
 }
 
@@ -698,6 +736,12 @@ void launch_prepare(WaveCtl *ctl, cudaStream_t stream) { prepare_kernel<<<1, 1, 
 void launch_generate(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, FilmDevice film, WaveCtl *ctl, cudaStream_t stream) {
     if (params.halton) generate_kernel<true><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, cur, film, ctl);
     else generate_kernel<false><<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(scene, params, cur, film, ctl);
+}
+
+void launch_weight_fill(const LaunchCfg &cfg, const RenderParams &params, FilmDevice film, long long begin, long long end, long long stride_block,
+                        int stride_parts, int stride_part, cudaStream_t stream) {
+    weight_fill_kernel<<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(film.weight, params.width * params.height, params.spp, params.tile ? 1 : 0,
+                                                                         begin, end, stride_block, stride_parts, stride_part);
 }
 
 // counting sort of `count` keys into rs.order; *n_sorted_out (a WaveCtl field) is set to the count by the scatter kernel

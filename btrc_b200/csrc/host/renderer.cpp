@@ -111,7 +111,33 @@ void Renderer::clear_film() {
     stats_ = RenderStats();
 }
 
-void Renderer::render_range(long long begin, long long end) {
+void Renderer::render_part(int parts, int part, int rows_per_strip) {
+    if (parts < 1 || part < 0 || part >= parts) throw Error("render_part: part out of range");
+    const long long W = scene_.width, H = scene_.height, spp = scene_.renderer.spp;
+    if (!scene_.renderer.tile) {  // sample streams: sample indices [part * spp / parts, ...) of every pixel (partition A)
+        const long long base = spp / parts, rem = spp % parts;
+        const long long b = part * base + std::min<long long>(part, rem), e = b + base + (part < rem ? 1 : 0);
+        render_range(b * W * H, e * W * H);
+        return;
+    }
+    // image tiles (partition B): strips of `rows` image rows dealt round-robin, so that cheap and expensive image regions
+    // are spread over all devices; tile-mode indexing makes a strip one contiguous block of the index space
+    if (rows_per_strip <= 0) rows_per_strip = (int)std::max<long long>(1, std::min<long long>(16, H / (8LL * parts)));
+    const long long rows = rows_per_strip;
+    const long long block = rows * W * spp, total = W * H * spp;
+    const long long strips = (H + rows - 1) / rows;
+    const long long owned = part < strips ? (strips - 1 - part) / parts + 1 : 0;
+    if (owned == 0) { render_range(0, 0); return; }
+    const bool owns_last = (strips - 1) % parts == part;
+    const long long last_paths = total - (strips - 1) * block;
+    const long long n_virtual = owns_last ? (owned - 1) * block + last_paths : owned * block;
+    render_range(0, n_virtual, block, parts, part);
+}
+
+void Renderer::render_range(long long begin, long long end, long long stride_block, int stride_parts, int stride_part) {
+    if (stride_block < 0 || stride_parts < 1 || stride_part < 0 || stride_part >= stride_parts) throw Error("render_range: bad stride");
+    if (stride_block > 0 && (!scene_.renderer.tile || stride_block % scene_.renderer.spp != 0))
+        throw Error("render_range: a strided partition needs tile-mode indexing and whole pixels per block");
     if (begin < 0 || end < begin || end > total_paths()) throw Error("render_range: path range out of bounds");
     HostSpan span_all("render_range");
     const RenderParams params = scene_.render_params();
@@ -121,9 +147,14 @@ void Renderer::render_range(long long begin, long long end) {
     init.end = end;
     init.pool = pool_;
     init.sort_enabled = sort_rays_;
+    init.stride_block = stride_block;
+    init.stride_parts = stride_parts;
+    init.stride_part = stride_part;
+    init.weight_prefilled = 1;
     ctl_host_[8] = init;  // pinned staging slot: the upload is a true async copy on the renderer's stream
     BTRC_CUDA(cudaMemcpyAsync(ctl_, &ctl_host_[8], sizeof(init), cudaMemcpyHostToDevice, stream_));
     BTRC_CUDA(cudaEventRecord(ev_begin_, stream_));
+    launch_weight_fill(cfg_, params, film_, begin, end, stride_block, stride_parts, stride_part, stream_);
 
     const bool has_medium = scene_.dev.has_medium != 0;
     const int kernels_per_iter = has_medium ? 5 : 4;  // prepare, generate, trace, [medium], shadow; shade adds its own count
@@ -213,7 +244,7 @@ void Renderer::render_range(long long begin, long long end) {
     stats_.n_splat += fin.n_splat;
     stats_.n_iter += fin.n_iter;
     stats_.render_ms = ms;
-    stats_.n_launches = (unsigned long long)kernels_per_iter * (unsigned long long)iter + n_kernels;
+    stats_.n_launches = (unsigned long long)kernels_per_iter * (unsigned long long)iter + n_kernels + 1;  // + weight_fill_kernel
     for (double &v : stats_.stage_ms) v = 0;
     // events per iteration: after prepare, generate, trace, medium, shade, shadow  => intervals gen, trace, medium, shade, shadow
     // the sixth interval (after shadow -> after the next prepare) is the iteration bookkeeping: counter snapshot + prepare kernel

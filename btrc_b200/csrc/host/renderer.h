@@ -36,7 +36,13 @@ public:
     bool stopped() const { return stopped_; }
     // Traces camera paths [begin, end) of the scene's path index space (Uniform mode: index = sample * W*H + pixel;
     // Tile mode: index = pixel * spp + sample) and accumulates them into the film.
-    void render_range(long long begin, long long end);
+    // renders camera paths [begin, end) of the path index space; with stride_block > 0 the range is VIRTUAL (types.h WaveCtl:
+    // interleaved blocks of `stride_block` paths, this renderer taking block `stride_part` of every `stride_parts`)
+    void render_range(long long begin, long long end, long long stride_block = 0, int stride_parts = 1, int stride_part = 0);
+    // this renderer's share of the whole render when `parts` devices split it (partition chosen by the renderer's "tile" flag:
+    // sample-index ranges, or interleaved strips of `rows_per_strip` image rows)
+    void render_part(int parts, int part, int rows_per_strip);
+    FilmDevice &film() { return film_; }
     // value / weight into caller-provided DEVICE buffers of W*H float4 (albedo/normal may be null).
     void resolve(float *d_color, float *d_albedo, float *d_normal);
     // The same into buffers in ANY address space: device destinations are written by the resolve kernel itself, host

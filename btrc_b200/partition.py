@@ -38,6 +38,25 @@ def tile_path_range(rank: int, world: int, spp: int, npix: int):
     return b * spp, e * spp
 
 
+def strip_rows(world: int, height: int) -> int:
+    """Default strip height of the interleaved tile partition (Renderer::render_part): at most 16 rows, at least 8 strips per rank."""
+    return max(1, min(16, height // (8 * world)))
+
+
+def tile_path_ranges(rank: int, world: int, spp: int, width: int, height: int, rows: int = 0):
+    """Camera-path index ranges [(begin, end), ...] of `rank` in the INTERLEAVED tile partition (Tile mode, "tile": true): the
+    image is cut into strips of `rows` pixel rows and strip k belongs to rank k % world, so sky and geometry rows are spread
+    over all ranks (contiguous bands scaled 1.46x at 2 GPUs on C5, profiles/bench_c5_n2_tiles_r1h.json).  The C ABI renders the
+    same set in one call (btrc_render_part); this list form is what tests check it against."""
+    rows = rows or strip_rows(world, height)
+    strips = (height + rows - 1) // rows
+    out = []
+    for k in range(rank, strips, world):
+        y0, y1 = k * rows, min((k + 1) * rows, height)
+        out.append((y0 * width * spp, y1 * width * spp))
+    return out
+
+
 def reduce_films(tensors, dst: int = 0):
     """Sum-reduce the film buffers onto `dst` (torch.distributed; NCCL on GPUs, gloo in the CPU tests)."""
     import torch.distributed as dist

@@ -37,6 +37,7 @@ typedef struct btrc_scene_info {
     int32_t n_textures;
     float world_diagonal;         /* 1.2 * |bbox(scene + eye)|                (wavefront.cpp:138-139)       */
     float bvh_build_seconds;
+    uint64_t bvh_bytes;           /* nodes + triangles the traversal kernels walk (compare with the 126 MB L2)           */
 } btrc_scene_info_t;
 
 typedef struct btrc_render_stats {
@@ -94,6 +95,20 @@ int btrc_render(btrc_scene_t *scene, int memory, float *color, float *albedo, fl
  * (generate.cpp:49-60). */
 int btrc_film_clear(btrc_scene_t *scene);
 int btrc_render_range(btrc_scene_t *scene, int64_t path_begin, int64_t path_end, btrc_render_stats_t *stats);
+/* This device's share of the render when n_parts devices split it (the reference is single-GPU, cli/main.cpp:23).
+ * The partition follows the renderer's "tile" flag: sample-index ranges of every pixel ("tile": false, generate.cpp:49-55), or
+ * image tiles -- strips of rows_per_strip pixel rows dealt round-robin to the parts ("tile": true, the pixel-major index space of
+ * generate.cpp:56-60; rows_per_strip <= 0 picks a default).  Adds to this device's film like btrc_render_range. */
+int btrc_render_part(btrc_scene_t *scene, int32_t n_parts, int32_t part, int32_t rows_per_strip, btrc_render_stats_t *stats);
+/* The path's one collective: ncclReduce(sum) of the film planes (radiance, weight [, albedo, normal]) onto rank `root`, in
+ * place, on the renderer's stream -- btrc_resolve on the root then follows in stream order.  btrc_nccl_unique_id fills the 128
+ * bytes of an ncclUniqueId on one rank; every rank passes them to btrc_comm_create (ncclCommInitRank).  NCCL is loaded at first
+ * use; with n_ranks == 1 no NCCL is needed and the reduce is a no-op. */
+typedef struct btrc_comm btrc_comm_t;
+int btrc_nccl_unique_id(uint8_t *out128);
+int btrc_comm_create(int32_t n_ranks, int32_t rank, const uint8_t *id128, btrc_comm_t **out);
+void btrc_comm_destroy(btrc_comm_t *comm);
+int btrc_reduce_films(btrc_scene_t *scene, btrc_comm_t *comm, int32_t root);
 /* Film::get_float3_output / get_float_output (core/film.cpp): radiance W*H*4 floats, weight W*H floats,
  * albedo / normal W*H*4 floats or NULL. */
 int btrc_film_export(btrc_scene_t *scene, int memory, float *radiance, float *weight, float *albedo, float *normal);
@@ -169,8 +184,11 @@ int btrc_ibl_table(btrc_scene_t *scene, int32_t *lut_w, int32_t *lut_h, float *p
  * with its own events on the launching stream. */
 void *btrc_stream(btrc_scene_t *scene);
 
-/* Library / device facts. */
+/* Library / device facts.  btrc_set_device = cuda::Context(device_index) of cli/main.cpp:23 (one process per GPU: call it
+ * before the scene is loaded). */
 int btrc_device_sm_count(void);
+int btrc_device_count(void);
+int btrc_set_device(int32_t device);
 const char *btrc_version(void);
 
 #ifdef __cplusplus

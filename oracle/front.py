@@ -1055,6 +1055,19 @@ class OracleScene:
                     stats={k: int(v) for k, v in zip(names, stats)})
 
 
+def _render_pixels(self, pixel_index, spp_begin=0, spp_end=None):
+    """Raw film (radiance sum rgb, weight) of the listed pixels (index = y * width + x) over sample indices [spp_begin, spp_end)."""
+    spp_end = self.spp if spp_end is None else spp_end
+    idx = np.ascontiguousarray(pixel_index, np.uint32)
+    out = np.zeros((idx.shape[0], 4), f32)
+    stats = np.zeros(7, np.uint64)
+    self.L.orc_render_pixels(self.h, c_int(idx.shape[0]), _ptr(idx, c_uint32), c_int(spp_begin), c_int(spp_end), _ptr(out, c_float), _ptr(stats, c_uint64))
+    return out, {k: int(v) for k, v in zip(["n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss", "n_splat"], stats)}
+
+
+OracleScene.render_pixels = _render_pixels
+
+
 def new_state(n):
     return dict(o_med=np.zeros((n, 4), f32), d_t1=np.zeros((n, 4), f32), pixel=np.zeros((n, 2), np.uint32),
                 beta_depth=np.zeros((n, 4), f32), path_rad=np.zeros((n, 4), f32), rng=np.zeros((n, 2), np.uint64),

@@ -1967,6 +1967,71 @@ void orc_render(orc_scene *s, int spp_begin, int spp_end, float *out_color, floa
     }
 }
 
+// Renders only the listed pixels (index = y * width + x): out_rad[4 * k .. + 2] = the film's radiance sum of pixel k over sample
+// indices [spp_begin, spp_end), out_rad[4 * k + 3] = its weight.  Every path of the render is a function of (pixel, sample index)
+// alone and splats into its own pixel only, so this equals those pixels of orc_render's raw film: it lets tests
+// compare a full-size GPU render with the oracle on a strided pixel subset in seconds.
+void orc_render_pixels(orc_scene *s, int n, const uint32_t *pixel_index, int spp_begin, int spp_end, float *out_rad, uint64_t *stats_out) {
+    const int W = s->width, H = s->height;
+    const size_t npix = (size_t)W * H;
+    Stats total;
+#pragma omp parallel
+    {
+        Stats st;
+#pragma omp for schedule(dynamic, 16)
+        for (int k = 0; k < n; ++k) {
+            const long long pix = pixel_index[k];
+            float *rad = out_rad + 4 * (size_t)k;
+            rad[0] = rad[1] = rad[2] = rad[3] = 0.0f;
+            for (int sidx = spp_begin; sidx < spp_end; ++sidx) {
+                int64_t accu = s->tile ? (int64_t)pix * s->spp + sidx : (int64_t)sidx * (int64_t)npix + pix;
+                PathState ps;
+                generate_path(*s, accu, ps);
+                rad[3] += 1.0f; st.n_gen++;
+                auto do_shadow = [&](const ShadowRay &sr) {
+                    st.n_shadow++;
+                    bool occluded = traverse<true>(*s, sr.o, sr.d, sr.t1).hit;
+                    if (!occluded) { st.n_shadow_miss++; st.n_splat++; film_add(rad, sr.beta_li * shadow_tr(*s, sr)); }
+                };
+                for (;;) {
+                    Hit h = traverse<false>(*s, ps.o, ps.d, ps.t1);
+                    st.n_closest++; if (h.hit) st.n_hit++;
+                    bool scattered = false;
+                    MediumOut mo;
+                    if (s->has_medium) {
+                        medium_stage(*s, ps, h, mo);
+                        scattered = mo.scattered;
+                        if (mo.shadow.valid) do_shadow(mo.shadow);
+                        if (mo.radiance.valid) { st.n_splat++; film_add(rad, mo.radiance.value); }
+                    }
+                    ShadeOut out;
+                    shade(*s, ps, h, scattered, out);
+                    if (out.shadow.valid) do_shadow(out.shadow);
+                    if (out.radiance.valid) { st.n_splat++; film_add(rad, out.radiance.value); }
+                    if (scattered) {
+                        if (!mo.has_next) break;
+                        st.n_next++;
+                        ps = mo.next;
+                        continue;
+                    }
+                    if (!out.has_next) break;
+                    st.n_next++;
+                    ps = out.next;
+                }
+            }
+        }
+#pragma omp critical
+        {
+            total.n_gen += st.n_gen; total.n_closest += st.n_closest; total.n_hit += st.n_hit; total.n_next += st.n_next;
+            total.n_shadow += st.n_shadow; total.n_shadow_miss += st.n_shadow_miss; total.n_splat += st.n_splat;
+        }
+    }
+    if (stats_out) {
+        stats_out[0] = total.n_gen; stats_out[1] = total.n_closest; stats_out[2] = total.n_hit; stats_out[3] = total.n_next;
+        stats_out[4] = total.n_shadow; stats_out[5] = total.n_shadow_miss; stats_out[6] = total.n_splat;
+    }
+}
+
 // --- known-answer helpers for RNG / hash / alias / offset tests -------------------------------
 uint64_t orc_murmur_pixel(uint32_t px, uint32_t py) { return hash_pixel(px, py); }
 void orc_pcg_stream(uint32_t px, uint32_t py, int sample_index, int n, uint32_t *out_u32, float *out_f32, uint64_t *state_inc) {
