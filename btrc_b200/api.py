@@ -81,6 +81,7 @@ def lib():
         L.btrc_geometry_tables.argtypes = [c_void_p, c_int32, POINTER(c_int32), c_void_p]
         L.btrc_geometry_positions.argtypes = [c_void_p, c_int32, POINTER(c_int32), c_void_p]
         L.btrc_instance_transform.argtypes = [c_void_p, c_int32, c_void_p, c_void_p]
+        L.btrc_instance_geometry.argtypes = [c_void_p, c_int32, POINTER(c_int32)]
         L.btrc_ibl_table.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]
         L.btrc_set_reporter.argtypes = [c_void_p, PROGRESS_FN, c_void_p]
         L.btrc_image_load.argtypes = [c_char_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_void_p, c_uint64]
@@ -349,6 +350,11 @@ class Scene:
         t = np.zeros((h.value, w.value), np.float32)
         _check(self.L.btrc_ibl_table(self.h, byref(w), byref(h), _p(t)))
         return t
+
+    def instance_geometry(self, instance_id):
+        g = c_int32(0)
+        _check(self.L.btrc_instance_geometry(self.h, int(instance_id), byref(g)))
+        return g.value
 
     def instance_transform(self, instance_id):
         mat = np.zeros((3, 4), np.float32)

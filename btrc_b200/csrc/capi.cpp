@@ -636,6 +636,14 @@ int btrc_ibl_table(btrc_scene_t *s, int32_t *lut_w, int32_t *lut_h, float *probs
     });
 }
 
+int btrc_instance_geometry(btrc_scene_t *s, int32_t instance_id, int32_t *geometry_id) {
+    return guarded([&] {
+        check_scene(s);
+        if (instance_id < 0 || instance_id >= (int)s->scene->instance_info.size()) throw Error("instance id out of range");
+        *geometry_id = s->scene->instance_info[instance_id].geometry_id;
+    });
+}
+
 int btrc_instance_transform(btrc_scene_t *s, int32_t instance_id, float *mat12, float *inv12) {
     return guarded([&] {
         check_scene(s);

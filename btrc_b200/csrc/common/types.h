@@ -189,6 +189,12 @@ struct BvhDevice {
     const uint2 *tri_ids;    // (instance, primitive) per triangle slot
     int root_ref;            // reference of the root (a leaf ref when the scene has <= leaf-size triangles)
     int n_tris;
+    // two-level layout (host/bvh.h TwoLevelBvh): `nodes` then holds the object-space trees of the meshes, `tl_nodes` the tree over
+    // the instances (root_ref refers to it; its leaf reference ~(instance << 3) names one InstanceBlas record of 4 float4),
+    // `tris` / `tri_ids` the world-space triangles per instance in its mesh tree's leaf order
+    const float4 *tl_nodes;
+    const float4 *inst_blas;
+    int two_level;
 };
 
 struct HaltonConsts {  // HaltonSampler::initialize_consts (builtin/sampler/halton.cpp:116-133)

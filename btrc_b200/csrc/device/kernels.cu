@@ -18,9 +18,11 @@ namespace {
 
 constexpr int kBlock = 256;
 constexpr unsigned kFull = 0xffffffffu;
-template <bool ANY_HIT, bool IFIF>
+// TRAV: loop form / hierarchy of the walk (kernels.h LaunchCfg::traverse): 0 while-while, 1 if-if, 2 two-level (instanced scenes)
+template <bool ANY_HIT, int TRAV>
 __device__ __forceinline__ HitRec traverse_warp(const BvhDevice &bvh, float4 o4, float4 d4, bool valid) {  // all 32 lanes call this together
-    if (IFIF) return traverse_bvh2_ifif<ANY_HIT, true>(bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w, valid);
+    if (TRAV == 2) return traverse_two_level<ANY_HIT, true>(bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w, valid);
+    if (TRAV == 1) return traverse_bvh2_ifif<ANY_HIT, true>(bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w, valid);
     return traverse_bvh2<ANY_HIT, true>(bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w, valid);
 }
 
@@ -222,6 +224,11 @@ __device__ __forceinline__ void class_append(const HitQueue &hq, WaveCtl *ctl, b
 #ifndef BTRC_TRACE_MIN_BLOCKS
 #define BTRC_TRACE_MIN_BLOCKS 6
 #endif
+// the two-level walk keeps the world ray next to the object-space slab constants: 5 CTAs (51 registers) instead of 6 (40)
+#ifndef BTRC_TRACE_MIN_BLOCKS_2L
+#define BTRC_TRACE_MIN_BLOCKS_2L 5
+#endif
+template <int TRAV> constexpr int trace_min_blocks() { return TRAV == 2 ? BTRC_TRACE_MIN_BLOCKS_2L : BTRC_TRACE_MIN_BLOCKS; }
 // direction octant << 9 | 8x8x8 cell of the origin over the world box
 __device__ __forceinline__ uint32_t ray_sort_key(const SceneDevice &scene, f3 o, f3 d) {
     const int cx = min(max(int((o.x - scene.sort_lo[0]) * scene.sort_scale[0]), 0), 7);
@@ -290,8 +297,8 @@ __global__ void __launch_bounds__(kSortBlock) sort_scatter_kernel(const uint32_t
 }
 
 // SORTED: surviving paths are visited through RaySort::order and the class lists are left to classify_kernel (state order)
-template <bool IFIF, bool SORTED>
-__global__ void __launch_bounds__(kBlock, BTRC_TRACE_MIN_BLOCKS) trace_kernel(SceneDevice scene, PathQueue q, HitQueue hq, RaySort rs, WaveCtl *ctl) {
+template <int TRAV, bool SORTED>
+__global__ void __launch_bounds__(kBlock, trace_min_blocks<TRAV>()) trace_kernel(SceneDevice scene, PathQueue q, HitQueue hq, RaySort rs, WaveCtl *ctl) {
     const int n = ctl->n_active;
     const int n_sorted = SORTED ? ctl->n_sorted : 0;
     const bool append = !SORTED || ctl->sort_enabled != 2;
@@ -306,7 +313,7 @@ __global__ void __launch_bounds__(kBlock, BTRC_TRACE_MIN_BLOCKS) trace_kernel(Sc
         const int i = (SORTED && valid && j < n_sorted) ? (int)rs.order[j] : j;  // survivors bin by bin, new camera paths in pixel order
         float4 o4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d4 = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
         if (valid) { o4 = q.ray_o[i]; d4 = q.ray_d[i]; }
-        const HitRec h = traverse_warp<false, IFIF>(scene.bvh, o4, d4, valid);
+        const HitRec h = traverse_warp<false, TRAV>(scene.bvh, o4, d4, valid);
         int cls = 0;
         if (valid) {
             const int inst = store_hit(scene.bvh, h, i, hq.flag, hq.detail);
@@ -336,7 +343,8 @@ __global__ void __launch_bounds__(kBlock) trace_batch_kernel(SceneDevice scene, 
                                                             uint32_t *flag, uint4 *detail) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 o4 = ray_o[i], d4 = ray_d[i];
-        const HitRec h = traverse_bvh2<false>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w);
+        const HitRec h = scene.bvh.two_level ? traverse_two_level<false>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w)
+                                             : traverse_bvh2<false>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w);
         if (h.slot < 0) detail[i] = make_uint4(0, 0, 0, 0);
         store_hit(scene.bvh, h, i, flag, detail);
     }
@@ -345,7 +353,9 @@ __global__ void __launch_bounds__(kBlock) trace_batch_kernel(SceneDevice scene, 
 __global__ void __launch_bounds__(kBlock) anyhit_batch_kernel(SceneDevice scene, const float4 *ray_o, const float4 *ray_d, int n, uint8_t *occluded) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 o4 = ray_o[i], d4 = ray_d[i];
-        occluded[i] = traverse_bvh2<true>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w).slot >= 0 ? 1 : 0;
+        const HitRec h = scene.bvh.two_level ? traverse_two_level<true>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w)
+                                             : traverse_bvh2<true>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w);
+        occluded[i] = h.slot >= 0 ? 1 : 0;
     }
 }
 
@@ -659,8 +669,8 @@ shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQu
 // ---------------------------------------------------------------------------------------------------------------
 // shadow rays (shadow.cpp:24-74): occlusion with early exit; unoccluded => splat beta_li * Tr
 // ---------------------------------------------------------------------------------------------------------------
-template <bool IFIF, bool SORTED, bool T3P>
-__global__ void __launch_bounds__(kBlock, BTRC_TRACE_MIN_BLOCKS) shadow_kernel(SceneDevice scene, RenderParams P, ShadowQueue sq, RaySort rs, FilmDevice film, WaveCtl *ctl) {
+template <int TRAV, bool SORTED, bool T3P>
+__global__ void __launch_bounds__(kBlock, trace_min_blocks<TRAV>()) shadow_kernel(SceneDevice scene, RenderParams P, ShadowQueue sq, RaySort rs, FilmDevice film, WaveCtl *ctl) {
     const int n = ctl->n_shadow;
     const int n_sorted = SORTED ? ctl->n_shadow_sorted : 0;
     unsigned long long misses = 0;
@@ -674,7 +684,7 @@ __global__ void __launch_bounds__(kBlock, BTRC_TRACE_MIN_BLOCKS) shadow_kernel(S
         const int i = (SORTED && valid && j < n_sorted) ? (int)rs.order[j] : j;
         float4 o4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d4 = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
         if (valid) { o4 = sq.ray_o[i]; d4 = sq.ray_d[i]; }
-        const HitRec h = traverse_warp<true, IFIF>(scene.bvh, o4, d4, valid);
+        const HitRec h = traverse_warp<true, TRAV>(scene.bvh, o4, d4, valid);
         if (valid && h.slot < 0) {  // unoccluded: the reference's miss program (shadow.cpp:39-74)
             const float4 b4 = sq.beta_li[i];
             f3 v = xyz(b4);
@@ -755,13 +765,11 @@ void launch_ray_sort(const LaunchCfg &cfg, const SceneDevice &scene, const float
 
 void launch_trace(const LaunchCfg &cfg, const SceneDevice &scene, PathQueue cur, HitQueue hit, RaySort rs, WaveCtl *ctl, cudaStream_t stream) {
     const int blocks = persistent_blocks(cfg, 8);
-    if (cfg.sorted_rays) {
-        if (cfg.traverse_ifif) trace_kernel<true, true><<<blocks, kBlock, 0, stream>>>(scene, cur, hit, rs, ctl);
-        else trace_kernel<false, true><<<blocks, kBlock, 0, stream>>>(scene, cur, hit, rs, ctl);
-    } else {
-        if (cfg.traverse_ifif) trace_kernel<true, false><<<blocks, kBlock, 0, stream>>>(scene, cur, hit, rs, ctl);
-        else trace_kernel<false, false><<<blocks, kBlock, 0, stream>>>(scene, cur, hit, rs, ctl);
-    }
+#define BTRC_TRACE(T, S) trace_kernel<T, S><<<blocks, kBlock, 0, stream>>>(scene, cur, hit, rs, ctl)
+    const int trav = scene.bvh.two_level ? 2 : (cfg.traverse_ifif ? 1 : 0);
+    if (cfg.sorted_rays) { if (trav == 2) BTRC_TRACE(2, true); else if (trav == 1) BTRC_TRACE(1, true); else BTRC_TRACE(0, true); }
+    else { if (trav == 2) BTRC_TRACE(2, false); else if (trav == 1) BTRC_TRACE(1, false); else BTRC_TRACE(0, false); }
+#undef BTRC_TRACE
 }
 
 template <int MAT>
@@ -813,23 +821,16 @@ void launch_medium(const LaunchCfg &cfg, const SceneDevice &scene, const RenderP
 void launch_shadow(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, ShadowQueue shadow, RaySort rs, FilmDevice film, WaveCtl *ctl,
                    cudaStream_t stream) {
     const int blocks = persistent_blocks(cfg, 8);
+#define BTRC_SHADOW(T, S, P) shadow_kernel<T, S, P><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl)
+#define BTRC_SHADOW_T(S, P) do { if (trav == 2) BTRC_SHADOW(2, S, P); else if (trav == 1) BTRC_SHADOW(1, S, P); else BTRC_SHADOW(0, S, P); } while (0)
+    const int trav = scene.bvh.two_level ? 2 : (cfg.traverse_ifif ? 1 : 0);
     if (scene.has_medium == 2) {  // 3-D texture programs in the transmittance: see launch_medium
-        if (cfg.sorted_rays) {
-            if (cfg.traverse_ifif) shadow_kernel<true, true, true><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
-            else shadow_kernel<false, true, true><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
-        } else {
-            if (cfg.traverse_ifif) shadow_kernel<true, false, true><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
-            else shadow_kernel<false, false, true><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
-        }
-        return;
-    }
-    if (cfg.sorted_rays) {
-        if (cfg.traverse_ifif) shadow_kernel<true, true, false><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
-        else shadow_kernel<false, true, false><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
+        if (cfg.sorted_rays) BTRC_SHADOW_T(true, true); else BTRC_SHADOW_T(false, true);
     } else {
-        if (cfg.traverse_ifif) shadow_kernel<true, false, false><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
-        else shadow_kernel<false, false, false><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl);
+        if (cfg.sorted_rays) BTRC_SHADOW_T(true, false); else BTRC_SHADOW_T(false, false);
     }
+#undef BTRC_SHADOW_T
+#undef BTRC_SHADOW
 }
 
 void launch_resolve(int width, int height, const float *value, const float *weight, float *out, int normalise, cudaStream_t stream) {

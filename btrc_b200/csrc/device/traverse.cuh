@@ -211,4 +211,109 @@ BTRC_TRAV_QUAL HitRec traverse_bvh2_ifif(const BvhDevice &bvh, float ox, float o
     return best;
 }
 
+// Two-level walk (host/bvh.h TwoLevelBvh; replaces the reference's IAS -> GAS traversal, utils/optix/context.cpp:217-294): the
+// instance tree in world space, then the mesh's tree in OBJECT space -- the ray is transformed for the box tests only
+// (o' = W2O * o, d' = W2O * d without renormalising, so t is the same parameter in both spaces and best.t culls directly) --
+// while every triangle is still tested in WORLD space on the instance's own world-space record.  t / u / v, the accepted hit
+// and the tie rule are therefore the flat tree's, bit for bit; the mesh trees' boxes carry the extra padding that makes the
+// fp32 transform conservative.  Same if-if iteration shape as traverse_bvh2_ifif: one triangle, one node step or one level
+// switch per lane and iteration, one vote per iteration.
+template <bool ANY_HIT, bool CONVERGE = false>
+BTRC_TRAV_QUAL HitRec traverse_two_level(const BvhDevice &bvh, float ox, float oy, float oz, float dx, float dy, float dz, float tmax, bool active = true) {
+    HitRec best;
+    best.t = tmax; best.u = 0.0f; best.v = 0.0f; best.slot = -1;
+    constexpr float kTiny = 1e-20f;
+    // slab constants of the space the walk is in (world at the top, the instance's object space below)
+    float idx = 1.0f / (fabsf(dx) > kTiny ? dx : copysignf(kTiny, dx));
+    float idy = 1.0f / (fabsf(dy) > kTiny ? dy : copysignf(kTiny, dy));
+    float idz = 1.0f / (fabsf(dz) > kTiny ? dz : copysignf(kTiny, dz));
+    float oox = ox * idx, ooy = oy * idy, ooz = oz * idz;
+
+    int stack[kStackSize];
+    int sp = 0;
+    constexpr int SENTINEL = 0x7fffffff, LEAVE = 0x7ffffffe;  // LEAVE: everything above it on the stack belongs to a mesh tree
+    stack[sp++] = SENTINEL;
+    int cur = active ? bvh.root_ref : SENTINEL;
+    bool below = false;        // walking a mesh tree
+    int tri = 0, tri_end = 0;  // world triangle slots [tri, tri_end) of the current leaf are still to be tested
+    int tri_base = 0;
+    const float4 *nodes = bvh.tl_nodes;
+
+    while (CONVERGE ? __any_sync(0xffffffffu, cur != SENTINEL || tri < tri_end) : (cur != SENTINEL || tri < tri_end)) {
+        if (tri < tri_end) {
+            const int s = tri++;
+            float t, u, v;
+            BTRC_TRAV_COUNT(1);
+            if (tri_test(bvh.tris + 3 * (size_t)s, ox, oy, oz, dx, dy, dz, best.t, t, u, v)) {
+                if (ANY_HIT) {
+                    best.slot = s;
+                    if (!CONVERGE) return best;
+                    tri = tri_end; cur = SENTINEL;
+                } else if (t < best.t || best.slot < 0 || id_less(bvh.tri_ids, s, best.slot)) {
+                    best.t = t; best.u = u; best.v = v; best.slot = s;
+                }
+            }
+        } else if (cur == LEAVE) {  // the mesh tree is exhausted: back to world space
+            idx = 1.0f / (fabsf(dx) > kTiny ? dx : copysignf(kTiny, dx));
+            idy = 1.0f / (fabsf(dy) > kTiny ? dy : copysignf(kTiny, dy));
+            idz = 1.0f / (fabsf(dz) > kTiny ? dz : copysignf(kTiny, dz));
+            oox = ox * idx; ooy = oy * idy; ooz = oz * idz;
+            below = false;
+            nodes = bvh.tl_nodes;
+            cur = stack[--sp];
+        } else if (cur >= 0 && cur != SENTINEL) {
+            const float4 *node = nodes + 4 * (size_t)cur;
+            const float4 n0 = __ldg(node), n1 = __ldg(node + 1), nz = __ldg(node + 2), meta = __ldg(node + 3);
+            BTRC_TRAV_COUNT(0);
+            const float c0lox = fmaf(n0.x, idx, -oox), c0hix = fmaf(n0.y, idx, -oox);
+            const float c0loy = fmaf(n0.z, idy, -ooy), c0hiy = fmaf(n0.w, idy, -ooy);
+            const float c0loz = fmaf(nz.x, idz, -ooz), c0hiz = fmaf(nz.y, idz, -ooz);
+            const float c1lox = fmaf(n1.x, idx, -oox), c1hix = fmaf(n1.y, idx, -oox);
+            const float c1loy = fmaf(n1.z, idy, -ooy), c1hiy = fmaf(n1.w, idy, -ooy);
+            const float c1loz = fmaf(nz.z, idz, -ooz), c1hiz = fmaf(nz.w, idz, -ooz);
+            const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
+            const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), best.t));
+            const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
+            const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), best.t));
+            const bool h0 = c0min <= c0max, h1 = c1min <= c1max;
+            const int r0 = __float_as_int(meta.x), r1 = __float_as_int(meta.y);
+            if (!h0 && !h1) {
+                cur = stack[--sp];
+            } else if (h0 && h1) {
+                const bool swp = c1min < c0min;
+                cur = swp ? r1 : r0;
+                stack[sp++] = swp ? r0 : r1;
+            } else {
+                cur = h0 ? r0 : r1;
+            }
+        }
+        if (tri >= tri_end && cur < 0) {  // arrived at a leaf
+            const int ref = ~cur;
+            if (below) {  // triangles of the mesh: slots of this instance's world-space records
+                tri = tri_base + (ref >> 3); tri_end = tri + (ref & 7) + 1;
+                cur = stack[--sp];
+            } else {      // an instance: enter its mesh tree
+                const float4 *rec = bvh.inst_blas + 4 * (size_t)(ref >> 3);
+                const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2), meta = __ldg(rec + 3);
+                const float lox = fmaf(m0.x, ox, fmaf(m0.y, oy, fmaf(m0.z, oz, m0.w)));
+                const float loy = fmaf(m1.x, ox, fmaf(m1.y, oy, fmaf(m1.z, oz, m1.w)));
+                const float loz = fmaf(m2.x, ox, fmaf(m2.y, oy, fmaf(m2.z, oz, m2.w)));
+                const float ldx = fmaf(m0.x, dx, fmaf(m0.y, dy, m0.z * dz));
+                const float ldy = fmaf(m1.x, dx, fmaf(m1.y, dy, m1.z * dz));
+                const float ldz = fmaf(m2.x, dx, fmaf(m2.y, dy, m2.z * dz));
+                idx = 1.0f / (fabsf(ldx) > kTiny ? ldx : copysignf(kTiny, ldx));
+                idy = 1.0f / (fabsf(ldy) > kTiny ? ldy : copysignf(kTiny, ldy));
+                idz = 1.0f / (fabsf(ldz) > kTiny ? ldz : copysignf(kTiny, ldz));
+                oox = lox * idx; ooy = loy * idy; ooz = loz * idz;
+                tri_base = __float_as_int(meta.y);
+                stack[sp++] = LEAVE;
+                below = true;
+                nodes = bvh.nodes;
+                cur = __float_as_int(meta.x);
+            }
+        }
+    }
+    return best;
+}
+
 }  // namespace btrc

@@ -279,4 +279,153 @@ FlatBvh2 flatten_bvh2(const BinaryBvh &bvh, const std::vector<WorldTri> &tris) {
     return out;
 }
 
+int tree_depth(const BinaryBvh &bvh) {
+    if (bvh.nodes.empty()) return 0;
+    int best = 0;
+    std::vector<std::pair<int, int>> stack = {{0, 1}};
+    while (!stack.empty()) {
+        auto [ni, d] = stack.back();
+        stack.pop_back();
+        best = std::max(best, d);
+        const BuildNode &nd = bvh.nodes[ni];
+        if (nd.left >= 0) { stack.push_back({nd.left, d + 1}); stack.push_back({nd.right, d + 1}); }
+    }
+    return best;
+}
+
+// nodes of a binary tree over arbitrary primitives in the kernels' 64-byte layout; leaf_ref(node) encodes the leaf
+template <typename LeafRef>
+static std::vector<float> flatten_nodes(const BinaryBvh &bvh, LeafRef leaf_ref, int &root_ref) {
+    std::vector<int> inner_index(bvh.nodes.size(), -1), stack = {0}, dfs;
+    int n_inner = 0;
+    while (!stack.empty()) {
+        const int ni = stack.back();
+        stack.pop_back();
+        const BuildNode &nd = bvh.nodes[ni];
+        if (nd.left < 0) continue;
+        inner_index[ni] = n_inner++;
+        dfs.push_back(ni);
+        stack.push_back(nd.right);
+        stack.push_back(nd.left);
+    }
+    std::vector<float> out(16 * (size_t)std::max(n_inner, 1), 0.0f);
+    auto ref_of = [&](int ni) { return bvh.nodes[ni].left < 0 ? leaf_ref(bvh.nodes[ni]) : inner_index[ni]; };
+    for (size_t k = 0; k < dfs.size(); ++k) {
+        const BuildNode &nd = bvh.nodes[dfs[k]];
+        const AABB &a = bvh.nodes[nd.left].box, &b = bvh.nodes[nd.right].box;
+        float *o = &out[16 * (size_t)inner_index[dfs[k]]];
+        o[0] = next_down(a.lo.x); o[1] = next_up(a.hi.x); o[2] = next_down(a.lo.y); o[3] = next_up(a.hi.y);
+        o[4] = next_down(b.lo.x); o[5] = next_up(b.hi.x); o[6] = next_down(b.lo.y); o[7] = next_up(b.hi.y);
+        o[8] = next_down(a.lo.z); o[9] = next_up(a.hi.z); o[10] = next_down(b.lo.z); o[11] = next_up(b.hi.z);
+        const int r0 = ref_of(nd.left), r1 = ref_of(nd.right);
+        std::memcpy(&o[12], &r0, 4);
+        std::memcpy(&o[13], &r1, 4);
+    }
+    root_ref = ref_of(0);
+    return out;
+}
+
+TwoLevelBvh build_two_level_bvh(const std::vector<std::vector<WorldTri>> &mesh_tris, const std::vector<InstanceRef> &insts,
+                                const std::vector<WorldTri> &world_tris, float coord_max) {
+    TwoLevelBvh out;
+    const size_t n_mesh = mesh_tris.size();
+    // Object-space boxes must contain the pre-image of the WORLD triangle the kernel tests, seen by a ray that was itself
+    // transformed in fp32: both errors are a few ulp of the world coordinates, mapped back by the inverse transform.  Pad every
+    // mesh's boxes by 4e-6 * (largest world coordinate) * (largest row norm of any of its instances' world -> object matrices).
+    std::vector<float> extra_pad(n_mesh, 0.0f);
+    std::vector<char> used(n_mesh, 0);
+    for (const InstanceRef &in : insts) {
+        float norm = 0;
+        for (int r = 0; r < 3; ++r) norm = std::max(norm, std::fabs(in.inv[4 * r]) + std::fabs(in.inv[4 * r + 1]) + std::fabs(in.inv[4 * r + 2]));
+        extra_pad[in.mesh] = std::max(extra_pad[in.mesh], 4e-6f * coord_max * norm);
+        used[in.mesh] = 1;
+    }
+    std::vector<BinaryBvh> trees(n_mesh);
+    std::vector<int> mesh_root(n_mesh, 0), mesh_depth(n_mesh, 0);
+    int deepest = 0;
+    for (size_t m = 0; m < n_mesh; ++m) {
+        if (!used[m] || mesh_tris[m].empty()) continue;
+        std::vector<AABB> boxes;
+        std::vector<Vec3> centers;
+        float obj_max = 0;
+        for (const WorldTri &t : mesh_tris[m])
+            for (const Vec3 &p : {t.p0, t.p1, t.p2})
+                obj_max = std::max(obj_max, std::max(std::fabs(p.x), std::max(std::fabs(p.y), std::fabs(p.z))));
+        padded_triangle_boxes(mesh_tris[m], obj_max, boxes, centers);
+        for (AABB &b : boxes) { b.lo = b.lo - Vec3(extra_pad[m]); b.hi = b.hi + Vec3(extra_pad[m]); }
+        trees[m] = build_binary_bvh(boxes, centers, 4);
+        mesh_depth[m] = tree_depth(trees[m]);
+        deepest = std::max(deepest, mesh_depth[m]);
+        int root = 0;
+        std::vector<float> nodes = flatten_nodes(trees[m], [](const BuildNode &nd) {
+            if (nd.count < 1 || nd.count > 8) throw Error("bvh: leaf size out of range");
+            return ~((nd.first << 3) | (nd.count - 1));
+        }, root);
+        const int base = (int)(out.bl_nodes.size() / 16);
+        for (size_t k = 0; k + 15 < nodes.size(); k += 16)  // inner references become indices into the concatenated array
+            for (int c = 12; c <= 13; ++c) {
+                int r;
+                std::memcpy(&r, &nodes[k + c], 4);
+                if (r >= 0) { r += base; std::memcpy(&nodes[k + c], &r, 4); }
+            }
+        mesh_root[m] = root >= 0 ? root + base : root;
+        out.bl_nodes.insert(out.bl_nodes.end(), nodes.begin(), nodes.end());
+    }
+    // world-space triangle records per instance, in its mesh tree's leaf order
+    size_t total = 0;
+    for (const InstanceRef &in : insts) total += mesh_tris[in.mesh].size();
+    if (total >= (1ull << 31)) throw Error("bvh: more than 2^31 - 1 instanced triangles");
+    out.tris.resize(12 * total);
+    out.tri_ids.resize(2 * total);
+    out.inst.resize(insts.size());
+    size_t base = 0;
+    for (size_t i = 0; i < insts.size(); ++i) {
+        const InstanceRef &in = insts[i];
+        InstanceBlas &ib = out.inst[i];
+        std::memcpy(ib.w2o, in.inv, sizeof(ib.w2o));
+        ib.root_ref = mesh_root[in.mesh];
+        ib.tri_base = (int)base;
+        ib.pad[0] = ib.pad[1] = 0;
+        const std::vector<int> &order = trees[in.mesh].order;
+        const long long n = (long long)order.size();
+#pragma omp parallel for if (n > 4096)
+        for (long long s = 0; s < n; ++s) {
+            const WorldTri &t = world_tris[in.first_tri + order[s]];
+            float *o = &out.tris[12 * (base + s)];
+            o[0] = t.p0.x; o[1] = t.p0.y; o[2] = t.p0.z; o[3] = t.n.x;
+            o[4] = t.e1.x; o[5] = t.e1.y; o[6] = t.e1.z; o[7] = t.n.y;
+            o[8] = t.e2.x; o[9] = t.e2.y; o[10] = t.e2.z; o[11] = t.n.z;
+            out.tri_ids[2 * (base + s)] = t.inst;
+            out.tri_ids[2 * (base + s) + 1] = t.prim;
+        }
+        base += (size_t)n;
+    }
+    // instance tree over the world boxes of the instances' (padded) world triangles
+    std::vector<AABB> tri_boxes;
+    std::vector<Vec3> tri_centers;
+    padded_triangle_boxes(world_tris, coord_max, tri_boxes, tri_centers);
+    std::vector<AABB> ibox(insts.size());
+    std::vector<Vec3> icen(insts.size());
+    std::vector<int> live;  // instances with geometry
+    for (size_t i = 0; i < insts.size(); ++i) {
+        AABB b;
+        const size_t n = mesh_tris[insts[i].mesh].size();
+        for (size_t k = 0; k < n; ++k) { b.extend(tri_boxes[insts[i].first_tri + k].lo); b.extend(tri_boxes[insts[i].first_tri + k].hi); }
+        ibox[i] = b;
+        icen[i] = 0.5f * (b.lo + b.hi);
+        if (n) live.push_back((int)i);
+    }
+    if (live.empty()) throw Error("bvh: no geometry");
+    std::vector<AABB> lb;
+    std::vector<Vec3> lc;
+    for (int i : live) { lb.push_back(ibox[i]); lc.push_back(icen[i]); }
+    BinaryBvh top = build_binary_bvh(lb, lc, 1);
+    out.tl_nodes = flatten_nodes(top, [&](const BuildNode &nd) {
+        if (nd.count != 1) throw Error("bvh: instance leaves hold one instance");
+        return ~(live[top.order[nd.first]] << 3);
+    }, out.tl_root_ref);
+    out.depth = tree_depth(top) + deepest + 1;
+    return out;
+}
+
 }  // namespace btrc

@@ -47,4 +47,39 @@ struct FlatBvh2 {
 
 FlatBvh2 flatten_bvh2(const BinaryBvh &bvh, const std::vector<WorldTri> &tris);
 
+// ---- two-level hierarchy for instanced scenes --------------------------------------------------------------------------------
+// The reference builds one GAS per mesh and an IAS over the instances (utils/optix/context.cpp:158-294, core/scene.cpp:196-209).
+// Flattening instances to world space multiplies the node array by the instance count (BASELINE config 4: 250 x 40,000 triangles
+// = 0.6 GB of nodes, five times the L2); here every mesh keeps ONE object-space tree (config 4: 4.5 MB, L2-resident) under a small
+// tree over the instances' world boxes.  The walk transforms the ray into object space for the BOX tests only; triangles are
+// still tested in world space on the flattened world-space triangle records (48 B per instance triangle, laid out per instance in
+// the mesh tree's leaf order), so t / u / v and the tie rule stay bit-identical to the flat tree and to the oracle.
+struct InstanceBlas {      // 64 bytes = 4 float4 on the device
+    float w2o[12];         // rows of the world -> object matrix (3 x 4)
+    int root_ref;          // root of the mesh's tree (inner index into `bl_nodes`, or a leaf reference)
+    int tri_base;          // first world-space triangle slot of this instance
+    int pad[2];
+};
+
+struct InstanceRef {
+    int mesh;
+    float inv[12];         // world -> object, 3 x 4 rows
+    size_t first_tri;      // index of the instance's first triangle in the world triangle list (mesh order)
+};
+
+struct TwoLevelBvh {
+    std::vector<float> tl_nodes;   // 16 floats per inner node of the instance tree
+    int tl_root_ref = 0;           // leaf reference = ~(instance << 3)
+    std::vector<float> bl_nodes;   // mesh trees, concatenated
+    std::vector<InstanceBlas> inst;
+    std::vector<float> tris;       // 12 floats per world-space triangle slot
+    std::vector<uint32_t> tri_ids;
+    int depth = 0;                 // instance-tree depth + deepest mesh tree + 1 (the level marker)
+};
+
+// mesh_tris[m]: object-space triangles of mesh m (prim order); world_tris: all instances' world-space triangles, instance-major.
+TwoLevelBvh build_two_level_bvh(const std::vector<std::vector<WorldTri>> &mesh_tris, const std::vector<InstanceRef> &insts,
+                                const std::vector<WorldTri> &world_tris, float coord_max);
+int tree_depth(const BinaryBvh &bvh);
+
 }  // namespace btrc

@@ -482,6 +482,11 @@ void Scene::create(const NodeP &root) {
             if (bt != "sah" && bt != "lbvh") throw Error("unknown bvh builder: " + bt);
             renderer.lbvh = bt == "lbvh";
         }
+        if (auto ln = r->find("bvh_layout")) {
+            const std::string lt = ln->as_string();
+            if (lt != "auto" && lt != "flat" && lt != "instanced") throw Error("unknown bvh layout: " + lt);
+            renderer.bvh_layout = lt == "flat" ? 1 : lt == "instanced" ? 2 : 0;
+        }
         if (auto sn = r->find("sampler")) {  // wavefront/common.h:36-37 chooses at compile time; here it is a renderer parameter
             const std::string st = sn->as_string();
             if (st != "independent" && st != "halton") throw Error("unknown sampler type: " + st);
@@ -552,18 +557,6 @@ RenderParams Scene::render_params() const {
 }
 
 static void to_3x4(const Mat4 &m, float *out) { mat4_to_3x4(m, out); }
-
-static int tree_depth(const BinaryBvh &b) {
-    int best = 0;
-    std::vector<std::pair<int, int>> st = {{0, 1}};
-    while (!st.empty()) {
-        auto [ni, d] = st.back();
-        st.pop_back();
-        best = std::max(best, d);
-        if (b.nodes[ni].left >= 0) { st.push_back({b.nodes[ni].left, d + 1}); st.push_back({b.nodes[ni].right, d + 1}); }
-    }
-    return best;
-}
 
 void Scene::commit() {
     if (width <= 0 || height <= 0) throw Error("invalid film size");
@@ -659,9 +652,49 @@ void Scene::commit() {
     scene_coord_max = 0;
     for (int a = 0; a < 3; ++a) scene_coord_max = std::max(scene_coord_max, std::max(std::fabs(wb.lo[a]), std::fabs(wb.hi[a])));
     scene_box = wb;
+    // layout: two-level when it pays -- meshes are reused (the flat tree repeats a mesh's nodes per instance) and the flat tree
+    // (64 B of nodes per ~2 triangles + 56 B per triangle) would not fit the 126 MB L2 (measured on B200: DESIGN.md, "instanced BVH")
+    instanced_bvh = false;
+    two_level = TwoLevelBvh();
+    {
+        std::vector<int> uses(meshes.size(), 0);
+        size_t unique_tris = 0;
+        for (const HostInstance &inst : instances) if (uses[inst.geometry_id]++ == 0) unique_tris += (size_t)meshes[inst.geometry_id].ntri;
+        const bool reused = world_tris.size() >= 2 * std::max<size_t>(unique_tris, 1);
+        const size_t flat_bytes = world_tris.size() * (56 + 32);
+        int layout = renderer.bvh_layout;
+        if (const char *e = std::getenv("BTRC_BVH_LAYOUT")) layout = std::string(e) == "flat" ? 1 : std::string(e) == "instanced" ? 2 : 0;
+        instanced_bvh = !renderer.lbvh && (layout == 2 || (layout == 0 && reused && flat_bytes > (size_t)120 << 20));
+    }
     if (renderer.lbvh) {  // built on the device at upload (device/lbvh.cu): only the unsorted triangle arrays are prepared here
         flat_bvh = FlatBvh2();
         bvh_depth = 0;
+    } else if (instanced_bvh) {
+        flat_bvh = FlatBvh2();
+        std::vector<std::vector<WorldTri>> mesh_tris(meshes.size());
+        for (size_t m = 0; m < meshes.size(); ++m) {
+            const MeshData &md = meshes[m];
+            mesh_tris[m].resize((size_t)md.ntri);
+            for (int k = 0; k < md.ntri; ++k) {
+                WorldTri &t = mesh_tris[m][k];
+                t.p0 = md.pos[3 * k]; t.p1 = md.pos[3 * k + 1]; t.p2 = md.pos[3 * k + 2];
+                t.e1 = t.p0 - t.p1; t.e2 = t.p2 - t.p0; t.n = cross(t.e1, t.e2);
+                t.inst = 0; t.prim = (uint32_t)k;
+            }
+        }
+        std::vector<InstanceRef> refs(instances.size());
+        size_t first = 0;
+        for (size_t i = 0; i < instances.size(); ++i) {
+            refs[i].mesh = instances[i].geometry_id;
+            to_3x4(instances[i].transform.inv, refs[i].inv);
+            refs[i].first_tri = first;
+            first += (size_t)meshes[instances[i].geometry_id].ntri;
+        }
+        float coord_max = 0;
+        for (int a = 0; a < 3; ++a) coord_max = std::max(coord_max, std::max(std::fabs(wb.lo[a]), std::fabs(wb.hi[a])));
+        two_level = build_two_level_bvh(mesh_tris, refs, world_tris, coord_max);
+        bvh_depth = two_level.depth;
+        if (bvh_depth > 60) throw Error("bvh too deep for the traversal stack: " + std::to_string(bvh_depth));
     } else {
         std::vector<AABB> boxes;
         std::vector<Vec3> centers;
@@ -833,6 +866,16 @@ void Scene::upload_device() {
         dev.bvh.tri_ids = d_ids;
         dev.bvh.n_tris = (int)n;
         lbvh_nodes = n_nodes;
+    } else if (instanced_bvh) {
+        dev.bvh.nodes = reinterpret_cast<const float4 *>(upload(two_level.bl_nodes));
+        dev.bvh.tl_nodes = reinterpret_cast<const float4 *>(upload(two_level.tl_nodes));
+        static_assert(sizeof(InstanceBlas) == 64, "InstanceBlas is read as 4 float4");
+        dev.bvh.inst_blas = reinterpret_cast<const float4 *>(upload(two_level.inst));
+        dev.bvh.tris = reinterpret_cast<const float4 *>(upload(two_level.tris));
+        dev.bvh.tri_ids = reinterpret_cast<const uint2 *>(upload(two_level.tri_ids));
+        dev.bvh.root_ref = two_level.tl_root_ref;
+        dev.bvh.two_level = 1;
+        dev.bvh.n_tris = (int)world_tris.size();
     } else {
         dev.bvh.nodes = reinterpret_cast<const float4 *>(upload(flat_bvh.nodes));
         dev.bvh.tris = reinterpret_cast<const float4 *>(upload(flat_bvh.tris));

@@ -103,6 +103,9 @@ struct RendererDesc {  // builtin/renderer/wavefront.cpp:375-398
     std::string type = "wfpt";
     bool tile = false;
     bool lbvh = false;    // "bvh_builder": "sah" (host binned SAH, default) | "lbvh" (device-side Morton-code build at upload)
+    // "bvh_layout": "flat" (instances flattened into one world-space tree) | "instanced" (one object-space tree per mesh under a tree
+    // over the instances: bvh.h) | "auto" (default: instanced when meshes are reused and the flat tree would exceed the L2)
+    int bvh_layout = 0;   // 0 auto, 1 flat, 2 instanced
     bool halton = false;  // "sampler": "independent" (default, what the reference's wavefront renderer is compiled with) | "halton"
     int spp = 128;
     int min_depth = 5, max_depth = 10;
@@ -142,6 +145,8 @@ public:
     float world_diagonal = 0;
     SceneDevice dev{};
     FlatBvh2 flat_bvh;
+    TwoLevelBvh two_level;       // used instead of flat_bvh when `instanced_bvh`
+    bool instanced_bvh = false;
     std::vector<AliasUnit> filter_alias;
     std::vector<float> ibl_tile_probs;      // EnvirLightSampler tile table (light/env_sampler.cpp:72-122)
     std::vector<AliasUnit> ibl_alias;

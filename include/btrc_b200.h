@@ -176,6 +176,8 @@ int btrc_geometry_tables(btrc_scene_t *scene, int32_t geometry_id, int32_t *n_tr
  * the local-space corner positions of the mesh, 9 floats per triangle in primitive order.  Host side only. */
 int btrc_geometry_positions(btrc_scene_t *scene, int32_t geometry_id, int32_t *n_triangles, float *out9);
 int btrc_instance_transform(btrc_scene_t *scene, int32_t instance_id, float *mat12, float *inv12);
+/* InstanceInfo::geometry_id (core/scene.h:21-30): which mesh the entity instantiates.  Host side only. */
+int btrc_instance_geometry(btrc_scene_t *scene, int32_t instance_id, int32_t *geometry_id);
 /* EnvirLightSampler::preprocess result (light/env_sampler.cpp:72-122): the normalised lut_w * lut_h tile table of the "ibl"
  * environment light, computed on the device at commit.  probs may be NULL to query the size. */
 int btrc_ibl_table(btrc_scene_t *scene, int32_t *lut_w, int32_t *lut_h, float *probs);

@@ -52,7 +52,7 @@ struct HostBvh {
 };
 
 static BvhDevice view(const HostBvh *h) {
-    BvhDevice b;
+    BvhDevice b{};
     b.nodes = reinterpret_cast<const float4 *>(h->w.nodes.data());
     b.tris = reinterpret_cast<const float4 *>(h->w.tris.data());
     b.tri_ids = reinterpret_cast<const uint2 *>(h->w.tri_ids.data());
@@ -142,6 +142,97 @@ void *ht_build_lbvh(int n, const float *verts, const uint32_t *ids) {
     h->w.root_ref = 0;
     h->n_inner = acc;
     return h;
+}
+
+// The two-level layout of instanced scenes (host/bvh.h build_two_level_bvh + traverse_two_level), from what Scene::commit hands
+// the builder: object-space meshes, the instances' mesh ids and world -> object matrices, and the world-space triangles.
+struct HostTwoLevel { TwoLevelBvh w; };
+
+static WorldTri make_tri(const float *v, uint32_t inst, uint32_t prim) {
+    WorldTri t;
+    t.p0 = Vec3(v[0], v[1], v[2]); t.p1 = Vec3(v[3], v[4], v[5]); t.p2 = Vec3(v[6], v[7], v[8]);
+    t.e1 = t.p0 - t.p1; t.e2 = t.p2 - t.p0; t.n = cross(t.e1, t.e2);
+    t.inst = inst; t.prim = prim;
+    return t;
+}
+
+void *ht2_build(int n_mesh, const int *mesh_ntri, const float *mesh_verts, int n_inst, const int *inst_mesh, const float *inst_inv,
+                int n_world, const float *world_verts, const uint32_t *world_ids) {
+    std::vector<std::vector<WorldTri>> mesh_tris(n_mesh);
+    size_t off = 0;
+    for (int m = 0; m < n_mesh; ++m) {
+        for (int k = 0; k < mesh_ntri[m]; ++k) mesh_tris[m].push_back(make_tri(mesh_verts + 9 * (off + k), 0, (uint32_t)k));
+        off += (size_t)mesh_ntri[m];
+    }
+    std::vector<WorldTri> world(n_world);
+    AABB wb;
+    for (int i = 0; i < n_world; ++i) {
+        world[i] = make_tri(world_verts + 9 * (size_t)i, world_ids[2 * i], world_ids[2 * i + 1]);
+        wb.extend(world[i].p0); wb.extend(world[i].p1); wb.extend(world[i].p2);
+    }
+    std::vector<InstanceRef> refs(n_inst);
+    size_t first = 0;
+    for (int i = 0; i < n_inst; ++i) {
+        refs[i].mesh = inst_mesh[i];
+        std::memcpy(refs[i].inv, inst_inv + 12 * (size_t)i, 48);
+        refs[i].first_tri = first;
+        first += mesh_tris[inst_mesh[i]].size();
+    }
+    if ((int)first != n_world) return nullptr;
+    float coord_max = 0;
+    for (int a = 0; a < 3; ++a) coord_max = std::max(coord_max, std::max(std::fabs(wb.lo[a]), std::fabs(wb.hi[a])));
+    auto *h = new HostTwoLevel;
+    h->w = build_two_level_bvh(mesh_tris, refs, world, coord_max);
+    return h;
+}
+void ht2_free(void *h) { delete static_cast<HostTwoLevel *>(h); }
+int ht2_info(void *hh, int which) {
+    const HostTwoLevel *h = static_cast<HostTwoLevel *>(hh);
+    return which == 0 ? (int)(h->w.tl_nodes.size() / 16) : which == 1 ? (int)(h->w.bl_nodes.size() / 16) : h->w.depth;
+}
+
+static BvhDevice view2(const HostTwoLevel *h) {
+    BvhDevice b{};
+    b.nodes = reinterpret_cast<const float4 *>(h->w.bl_nodes.data());
+    b.tl_nodes = reinterpret_cast<const float4 *>(h->w.tl_nodes.data());
+    b.inst_blas = reinterpret_cast<const float4 *>(h->w.inst.data());
+    b.tris = reinterpret_cast<const float4 *>(h->w.tris.data());
+    b.tri_ids = reinterpret_cast<const uint2 *>(h->w.tri_ids.data());
+    b.root_ref = h->w.tl_root_ref;
+    b.n_tris = (int)(h->w.tri_ids.size() / 2);
+    b.two_level = 1;
+    return b;
+}
+
+void ht2_closest(void *hh, int n, const float *o_med, const float *d_t1, uint32_t *out_ids, float *out_tuv, uint64_t *steps) {
+    const HostTwoLevel *h = static_cast<HostTwoLevel *>(hh);
+    const BvhDevice b = view2(h);
+    uint64_t n_nodes = 0, n_tests = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : n_nodes, n_tests)
+    for (int i = 0; i < n; ++i) {
+        g_count[0] = g_count[1] = 0;
+        const HitRec r = traverse_two_level<false, false>(b, o_med[4 * i], o_med[4 * i + 1], o_med[4 * i + 2], d_t1[4 * i], d_t1[4 * i + 1],
+                                                          d_t1[4 * i + 2], d_t1[4 * i + 3]);
+        if (r.slot < 0) {
+            out_ids[2 * i] = out_ids[2 * i + 1] = 0xffffffffu;
+            out_tuv[3 * i] = out_tuv[3 * i + 1] = out_tuv[3 * i + 2] = 0;
+        } else {
+            out_ids[2 * i] = h->w.tri_ids[2 * r.slot];
+            out_ids[2 * i + 1] = h->w.tri_ids[2 * r.slot + 1];
+            out_tuv[3 * i] = r.t; out_tuv[3 * i + 1] = r.u; out_tuv[3 * i + 2] = r.v;
+        }
+        n_nodes += g_count[0];
+        n_tests += g_count[1];
+    }
+    if (steps) { steps[0] = n_nodes; steps[1] = n_tests; }
+}
+
+void ht2_any(void *hh, int n, const float *o_med, const float *d_t1, uint8_t *occluded) {
+    const BvhDevice b = view2(static_cast<HostTwoLevel *>(hh));
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int i = 0; i < n; ++i)
+        occluded[i] = traverse_two_level<true, false>(b, o_med[4 * i], o_med[4 * i + 1], o_med[4 * i + 2], d_t1[4 * i], d_t1[4 * i + 1], d_t1[4 * i + 2],
+                                                      d_t1[4 * i + 3]).slot >= 0;
 }
 
 void ht_free(void *h) { delete static_cast<HostBvh *>(h); }

@@ -21,8 +21,10 @@ from tests.util import f32
 
 pytestmark = pytest.mark.gpu
 
-REL_TOL = 2e-3       # per-pixel relative difference that still counts as "same paths" (fp32 fast-math vs IEEE, texture unit weights)
-OUTLIER_BUDGET = {   # fraction of subset pixels per bucket whose radiance differs by more than REL_TOL (at 2 spp, depth <= 10 / 16)
+REL_TOL = 2e-3       # per-pixel relative difference that still counts as "same paths" (fp32 fast-math vs IEEE arithmetic)
+REL_TOL_TEXTURED = 1e-2  # scenes with image textures: the texture unit filters with 8-bit weights (1e-3 typical, 6e-3 at the 99th
+                         # percentile per fetch against the oracle's exact weights), and most paths meet the textured ground
+OUTLIER_BUDGET = {   # fraction of subset pixels per bucket whose radiance differs by more than the tolerance (2 spp, depth <= 10 / 16)
     "default": 0.02,
 }
 
@@ -79,7 +81,7 @@ def _primary_buckets(o, path, idx):
     return out
 
 
-def _compare_subset(rad, wgt, ref, buckets, spp, what, budget=None, image_tol=2e-2):
+def _compare_subset(rad, wgt, ref, buckets, spp, what, budget=None, image_tol=2e-2, rel_tol=REL_TOL, median_tol=1e-4):
     """rad, wgt: GPU raw film at the subset pixels; ref: oracle (n, 4) = radiance sum + weight."""
     budget = budget or {}
     assert np.array_equal(wgt, ref[:, 3]) and (wgt == spp).all(), what + ": film weights"
@@ -90,16 +92,16 @@ def _compare_subset(rad, wgt, ref, buckets, spp, what, budget=None, image_tol=2e
     report = {}
     for name in sorted(set(buckets)):
         m = buckets == name
-        frac = float((rel[m] > REL_TOL).mean())
+        frac = float((rel[m] > rel_tol).mean())
         report[name] = (int(m.sum()), frac, float(np.median(rel[m])))
-    print("\n%s: outliers per primary-hit bucket (pixels, fraction > %.0e, median rel. diff):" % (what, REL_TOL))
+    print("\n%s: outliers per primary-hit bucket (pixels, fraction > %.0e, median rel. diff):" % (what, rel_tol))
     for name, (cnt, frac, med) in report.items():
         print("   %-28s %7d  %.4f  %.2e" % (name, cnt, frac, med))
     for name, (cnt, frac, med) in report.items():
         if cnt < 50:
             continue
         assert frac <= budget.get(name, OUTLIER_BUDGET["default"]), (what, name, cnt, frac)
-        assert med <= 1e-4, (what, name, med)  # the typical pixel agrees to fp32 shading accuracy
+        assert med <= median_tol, (what, name, med)  # the typical pixel agrees to fp32 shading (/ texture filtering) accuracy
     # image-level: the subset's mean radiance and its relative MSE (outliers included: flipped paths are still valid samples)
     assert abs(a.mean() - b.mean()) <= 5e-3 * b.mean() + 1e-7, (what, a.mean(), b.mean())
     rel_mse = ((a - b) ** 2).mean() / (b.mean() ** 2 + 1e-12)
@@ -137,7 +139,8 @@ def test_c2_disney_1080p_full_geometry(tmp_path, built):
     idx = _subset(1920 * 1080, 61)
     ref, _ = o.render_pixels(idx)
     buckets = _primary_buckets(o, path, idx)
-    _compare_subset(rad[idx], wgt[idx], ref, buckets, 2, "C2")
+    _compare_subset(rad[idx], wgt[idx], ref, buckets, 2, "C2", rel_tol=REL_TOL_TEXTURED, median_tol=3e-3,
+                    budget={"default": 0.04, "glass": 0.08, "disney_transmission": 0.08})
     s.close()
 
 
@@ -199,7 +202,8 @@ def test_c5_4k_two_rank_partitions(tmp_path, built):
     o = front.OracleScene(path)
     idx = _subset(npix, 211)
     ref, _ = o.render_pixels(idx)
-    _compare_subset(full[idx], wfull[idx], ref, _primary_buckets(o, path, idx), spp, "C5")
+    _compare_subset(full[idx], wfull[idx], ref, _primary_buckets(o, path, idx), spp, "C5", rel_tol=REL_TOL_TEXTURED, median_tol=3e-3,
+                    budget={"default": 0.04, "glass": 0.08, "disney_transmission": 0.08})
     s.close()
 
     # tile split: tile-mode indexing (generate.cpp:56-60), every rank renders all samples of its strips of pixel rows
