@@ -343,7 +343,7 @@ def dram_traffic(workload):
     return json.load(open(tpath)) if os.path.exists(tpath) else {}
 
 
-def measure(args, D, workload, steps, warmup, spp_override=0, e2e=True, cpu=True, scaling=None, partition=None):
+def measure(args, D, workload, steps, warmup, spp_override=0, e2e=True, cpu=True, scaling=None, partition=None, bvh_stats=True):
     """Times `steps` renders of `workload` on the process group D and returns rank 0's result line (None on other ranks)."""
     import torch
 
@@ -468,7 +468,7 @@ def measure(args, D, workload, steps, warmup, spp_override=0, e2e=True, cpu=True
     mrays = (n_closest + n_shadow) / secs / 1e6
 
     # ---- roofline of the dominant kernel (rank 0's stage times; algorithmic bytes per SURVEY 8d)
-    bvh = bvh_alg_per_ray(path) if cpu else None
+    bvh = bvh_alg_per_ray(path) if bvh_stats else None
     peak, peak_src = measured_peak()
     sb = stage_bytes({k: agg[k] for k in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss", "n_splat")}, bvh,
                      has_medium=bool(s.info.has_medium))
@@ -521,8 +521,9 @@ def measure(args, D, workload, steps, warmup, spp_override=0, e2e=True, cpu=True
         cpu_line = {"value": npix * cpu_spp / cpu_s / 1e6, "unit": "Msamples/s", "cores": arm.cores, "kind": arm.kind,
                     "sample": f"{cpu_spp} of {w['spp']} spp of the workload ({W}x{H}), {cpu_s:.1f} s on all host cores; " + arm.note}
 
-    cfg = workload_config(workload)
-    cfg.update({"spp_rendered_per_step": spp_scene, "gpus": world, "state_count": s.info.state_count,
+    cfg = workload_config(workload)   # identical in both arms; how this arm ran it goes to "run"
+    run = {}
+    run.update({"spp_rendered_per_step": spp_scene, "gpus": world, "state_count": s.info.state_count, "bvh_layout": "instanced" if s.info.bvh_instanced else "flat",
                 "partition": (("image tiles: strips of %d pixel rows dealt round-robin to the ranks (tile-mode indexing)" % __import__("btrc_b200.partition", fromlist=["x"]).strip_rows(world, H)
                                if tiles else "sample-index ranges per rank") +
                               "; ncclReduce(sum) of the radiance+weight films onto rank 0 inside the library (btrc_reduce_films), resolve on rank 0") if world > 1 else "single GPU",
@@ -532,7 +533,7 @@ def measure(args, D, workload, steps, warmup, spp_override=0, e2e=True, cpu=True
     line = {
         "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
         "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "mrays_per_s": mrays, "config": cfg, "clocks": clocks,
+        "data": "synthetic", "mrays_per_s": mrays, "config": cfg, "run": run, "clocks": clocks,
         "gpu_launches": int(n_launch + steps * (3 + 1)),
         "events": {"n_gen": n_gen, "n_closest": n_closest, "n_hit": n_hit, "n_next": n_next, "n_shadow": n_shadow, "n_shadow_miss": n_shadow_miss,
                    "n_splat": n_splat, "iterations_per_step": n_iter / steps / world},
@@ -558,16 +559,16 @@ def measure(args, D, workload, steps, warmup, spp_override=0, e2e=True, cpu=True
 def run_ours(args):
     D = Dist()
     workload = args.workload or (DEFAULT_WORKLOAD if D.world == 1 else SCALING_WORKLOAD)
-    line = measure(args, D, workload, args.steps, args.warmup, spp_override=args.spp, cpu=not args.no_cpu_baseline)
+    line = measure(args, D, workload, args.steps, args.warmup, spp_override=args.spp, cpu=not args.no_cpu_baseline, bvh_stats=not args.no_cpu_baseline)
     if D.world == 1 and not args.spp and not args.no_workloads and args.workload is None:
         # the other BASELINE configurations, short runs (value, clocks, per-stage shares and roofline fractions): BENCH carries all five
         extra = {}
-        for wl, k, spp in (("c1_cornell_512_16spp", 10, 0), ("c3_medium_1080p_128spp", 3, 0), ("c4_instanced_10m_1080p_128spp", 2, 0),
+        for wl, k, spp in (("c1_cornell_512_16spp", 200, 0), ("c3_medium_1080p_128spp", 3, 0), ("c4_instanced_10m_1080p_128spp", 2, 0),
                            ("c5_disney_4k_1024spp", 2, 128)):
             try:
                 r = measure(args, D, wl, k, 3, spp_override=spp, e2e=False, cpu=False, scaling="weak")
                 extra[wl] = {"value": r["value"], "unit": "Msamples/s", "mrays_per_s": r["mrays_per_s"], "ms_per_step": r["ms_per_step"], "steps": k,
-                             "spp_rendered_per_step": r["config"]["spp_rendered_per_step"], "clocks": r["clocks"],
+                             "spp_rendered_per_step": r["run"]["spp_rendered_per_step"], "clocks": r["clocks"],
                              "stages": {n: {"share_of_step": v["share_of_step"], "frac": v["frac"], "dram_frac": v.get("dram_frac"), "ms_per_launch": v["ms_per_launch"]}
                                         for n, v in r["roofline_stages"].items()}}
                 if wl == "c5_disney_4k_1024spp":

@@ -201,10 +201,38 @@ static void load_text_grid(const std::string &filename, TextureSource &src) {
     if (std::sscanf(p, "%15s %d %d %d %d%n", comp, &channels, &w, &h, &d, &used) != 5) throw Error("Array::load_from_text: failed to parse file head");
     p += used;
     if (channels != 1 && channels != 3 && channels != 4) throw Error("unsupported channel count: " + std::to_string(channels));
-    if (std::string(comp) == "byte") throw Error("byte text grids are not supported (the reference reads them as characters into SNorm8: SURVEY B.5)");
-    if (std::string(comp) != "float") throw Error(std::string("unknown component type: ") + comp);
+    const bool bytes = std::string(comp) == "byte";
+    if (!bytes && std::string(comp) != "float") throw Error(std::string("unknown component type: ") + comp);
     if (w <= 0 || h <= 0 || d <= 0) throw Error("Array::load_from_text: failed to parse file head");
     const size_t n = (size_t)w * h * d;
+    if (bytes) {
+        // array.cpp:331-355 reads each component with `uint8_t comp; fin >> comp;` -- formatted extraction into an unsigned char
+        // takes ONE non-blank CHARACTER, not a number -- and uploads the grid as SNorm8 (texel value = max(int8 / 127, -1), the
+        // extrema scaled by 1 / 127: find_minmax_impl<int8_t, N, true>, :436-510).  A three-channel grid gets 255 (= -1 / 127) as
+        // its fourth component.  Reproduced as is: a "byte" file means the same grid here as there.
+        src.width = w; src.height = h; src.depth = d;
+        src.is_float = false; src.snorm = true;
+        src.channels = channels == 1 ? 1 : 4;
+        src.u8.resize(n * src.channels);
+        int lo[3] = {127, 127, 127}, hi[3] = {-128, -128, -128};
+        for (size_t i = 0; i < n; ++i) {
+            for (int c = 0; c < channels; ++c) {
+                while (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r' || *p == '\v' || *p == '\f') ++p;
+                if (!*p) throw Error("failed to load " + filename);
+                const uint8_t v = (uint8_t)*p++;
+                src.u8[i * src.channels + c] = v;
+                if (c < 3) { lo[c] = std::min(lo[c], (int)(int8_t)v); hi[c] = std::max(hi[c], (int)(int8_t)v); }
+            }
+            if (channels == 3) src.u8[i * 4 + 3] = 255;
+        }
+        const float factor = static_cast<float>(1.0 / 127);
+        for (int k = 0; k < 3; ++k) {
+            const bool have = k < channels;  // components a texel does not have keep find_minmax_impl's start values
+            src.min_value[k] = static_cast<float>(have ? lo[k] : 127) * factor;
+            src.max_value[k] = static_cast<float>(have ? hi[k] : -128) * factor;
+        }
+        return;
+    }
     if (n * (size_t)channels > text.size()) throw Error("failed to load " + filename);  // every value takes at least two characters: the file cannot hold that grid
     src.width = w; src.height = h; src.depth = d;
     src.is_float = true;
@@ -652,19 +680,16 @@ void Scene::commit() {
     scene_coord_max = 0;
     for (int a = 0; a < 3; ++a) scene_coord_max = std::max(scene_coord_max, std::max(std::fabs(wb.lo[a]), std::fabs(wb.hi[a])));
     scene_box = wb;
-    // layout: two-level when it pays -- meshes are reused (the flat tree repeats a mesh's nodes per instance) and the flat tree
-    // (64 B of nodes per ~2 triangles + 56 B per triangle) would not fit the 126 MB L2 (measured on B200: DESIGN.md, "instanced BVH")
+    // layout: the two-level tree (host/bvh.h) is built on request only ("bvh_layout": "instanced" / BTRC_BVH_LAYOUT).  Measured on B200
+    // (profiles/r2c_ab_bvh_layout.md): it keeps a mesh's nodes once (C4: 0.6 GB of nodes -> 4.5 MB) and passes every parity test bit
+    // for bit, but traces SLOWER than the flat tree -- C4 129 vs 144 Msamples/s, C2 991 vs 1068: the 250 instances of C4 overlap in
+    // space, so a ray enters many mesh trees from their roots, where the flat SAH tree separates the triangles of all instances at once.
     instanced_bvh = false;
     two_level = TwoLevelBvh();
     {
-        std::vector<int> uses(meshes.size(), 0);
-        size_t unique_tris = 0;
-        for (const HostInstance &inst : instances) if (uses[inst.geometry_id]++ == 0) unique_tris += (size_t)meshes[inst.geometry_id].ntri;
-        const bool reused = world_tris.size() >= 2 * std::max<size_t>(unique_tris, 1);
-        const size_t flat_bytes = world_tris.size() * (56 + 32);
         int layout = renderer.bvh_layout;
         if (const char *e = std::getenv("BTRC_BVH_LAYOUT")) layout = std::string(e) == "flat" ? 1 : std::string(e) == "instanced" ? 2 : 0;
-        instanced_bvh = !renderer.lbvh && (layout == 2 || (layout == 0 && reused && flat_bytes > (size_t)120 << 20));
+        instanced_bvh = !renderer.lbvh && layout == 2;
     }
     if (renderer.lbvh) {  // built on the device at upload (device/lbvh.cu): only the unsorted triangle arrays are prepared here
         flat_bvh = FlatBvh2();
@@ -777,7 +802,8 @@ static void create_texture_object(TextureSource &src) {  // utils/cuda/array.cpp
         fmt = src.channels == 1 ? cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat) : cudaCreateChannelDesc(32, 32, 32, 32, cudaChannelFormatKindFloat);
         texel = 4 * (size_t)src.channels;
     } else {
-        fmt = src.channels == 1 ? cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned) : cudaCreateChannelDesc(8, 8, 8, 8, cudaChannelFormatKindUnsigned);
+        const cudaChannelFormatKind kind = src.snorm ? cudaChannelFormatKindSigned : cudaChannelFormatKindUnsigned;
+        fmt = src.channels == 1 ? cudaCreateChannelDesc(8, 0, 0, 0, kind) : cudaCreateChannelDesc(8, 8, 8, 8, kind);
         texel = (size_t)src.channels;
     }
     const void *data = src.is_float ? (const void *)src.f32.data() : (const void *)src.u8.data();

@@ -59,7 +59,8 @@ struct HostInstance {
 struct TextureSource {
     int width = 0, height = 0, depth = 0;
     int channels = 4;            // 1 or 4
-    bool is_float = false;       // false: UNorm8 texels in u8
+    bool is_float = false;       // false: 8-bit texels in u8 -- UNorm8 (images), or SNorm8 when `snorm` ("byte" text grids)
+    bool snorm = false;
     std::vector<uint8_t> u8;
     std::vector<float> f32;
     int address[3] = {0, 0, 0};  // 0 clamp, 1 wrap, 2 mirror, 3 border
@@ -104,7 +105,7 @@ struct RendererDesc {  // builtin/renderer/wavefront.cpp:375-398
     bool tile = false;
     bool lbvh = false;    // "bvh_builder": "sah" (host binned SAH, default) | "lbvh" (device-side Morton-code build at upload)
     // "bvh_layout": "flat" (instances flattened into one world-space tree) | "instanced" (one object-space tree per mesh under a tree
-    // over the instances: bvh.h) | "auto" (default: instanced when meshes are reused and the flat tree would exceed the L2)
+    // over the instances: bvh.h; saves the per-instance copies of a mesh's nodes, measured slower to trace) | "auto" (default: flat)
     int bvh_layout = 0;   // 0 auto, 1 flat, 2 instanced
     bool halton = false;  // "sampler": "independent" (default, what the reference's wavefront renderer is compiled with) | "halton"
     int spp = 128;

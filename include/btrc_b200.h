@@ -38,6 +38,8 @@ typedef struct btrc_scene_info {
     float world_diagonal;         /* 1.2 * |bbox(scene + eye)|                (wavefront.cpp:138-139)       */
     float bvh_build_seconds;
     uint64_t bvh_bytes;           /* nodes + triangles the traversal kernels walk (compare with the 126 MB L2)           */
+    int32_t bvh_instanced;        /* 1: two-level layout (one object-space tree per mesh under a tree over the instances) */
+    int32_t reserved;
 } btrc_scene_info_t;
 
 typedef struct btrc_render_stats {

@@ -784,17 +784,39 @@ class OracleScene:
             elif ty == "array":  # utils/cuda/array.cpp:313-385 (text grid)
                 au, av, aw, linear, srgb, border = self._texture_desc(node)
                 with open(self.resolve(node.child("text").as_str())) as f:
-                    tok = f.read().split()
+                    text = f.read()
+                tok = text.split()
                 comp, ch, w, h, d = tok[0], int(tok[1]), int(tok[2]), int(tok[3]), int(tok[4])
-                if comp != "float":
-                    raise NotImplementedError("oracle: only float text grids")
                 if ch not in (1, 3, 4):
                     raise ValueError(f"unsupported channel count: {ch}")
-                vals = np.array(tok[5:5 + w * h * d * ch], dtype=np.float64).astype(f32).reshape(d * h * w, ch)
-                if ch == 3:
-                    vals = np.concatenate([vals, np.ones((vals.shape[0], 1), f32)], axis=1)
+                minmax = None
+                if comp == "byte":
+                    # array.cpp:331-355: `uint8_t comp; fin >> comp;` extracts ONE non-blank character per component; the grid is
+                    # uploaded as SNorm8 (texel = max(int8 / 127, -1)), a 3-channel texel gets 255 as its fourth component; the
+                    # extrema are the int8 extrema times float(1 / 127) (find_minmax_impl<int8_t, N, true>, array.cpp:436-510)
+                    import re
+                    head = re.match(r"\s*\S+\s+\S+\s+\S+\s+\S+\s+\S+", text)
+                    chars = np.frombuffer("".join(text[head.end():].split()).encode("latin-1"), np.uint8)[:w * h * d * ch]
+                    if chars.size < w * h * d * ch:
+                        raise ValueError("failed to load byte grid")
+                    i8 = chars.view(np.int8).reshape(d * h * w, ch)
+                    if ch == 3:
+                        i8 = np.concatenate([i8, np.full((i8.shape[0], 1), -1, np.int8)], axis=1)
+                    vals = np.maximum(i8.astype(f32) / f32(127), f32(-1))
+                    factor = f32(1.0 / 127)
+                    lo = [f32(i8[:, c].min()) * factor if c < ch else f32(127) * factor for c in range(3)]
+                    hi = [f32(i8[:, c].max()) * factor if c < ch else f32(-128) * factor for c in range(3)]
+                    minmax = (np.array(lo, f32), np.array(hi, f32))
+                elif comp == "float":
+                    vals = np.array(tok[5:5 + w * h * d * ch], dtype=np.float64).astype(f32).reshape(d * h * w, ch)
+                    if ch == 3:
+                        vals = np.concatenate([vals, np.ones((vals.shape[0], 1), f32)], axis=1)
+                else:
+                    raise ValueError(f"unknown component type: {comp}")
                 vals = np.ascontiguousarray(vals, f32)
                 img = self.L.orc_add_image(self.h, w, h, d, 1 if ch == 1 else 4, _ptr(vals, c_float), 0, au, av, aw, linear, _ptr(border, c_float))
+                if minmax is not None:
+                    self.L.orc_set_image_minmax(self.h, img, _ptr(minmax[0], c_float), _ptr(minmax[1], c_float))
                 t = self.L.orc_add_texture3d_array(self.h, img)
             elif ty in ("add", "mul"):  # texture3d/binary.cpp:150-160 (lhs is created first)
                 lhs = self.add_texture3d(node.child("lhs"))

@@ -1453,6 +1453,12 @@ int orc_add_image(orc_scene *s, int w, int h, int d, int channels, const float *
     return (int)s->tex.images.size() - 1;
 }
 
+// Array::find_minmax_values of an integer format scales the integer extrema by float(1 / max) (array.cpp:470-490), which is not
+// always the float the texel itself becomes (c / max): front ends that decode such grids hand the reference's extrema over.
+void orc_set_image_minmax(orc_scene *s, int image, const float *min3, const float *max3) {
+    for (int c = 0; c < 3; ++c) { s->tex.images[image].min_value[c] = min3[c]; s->tex.images[image].max_value[c] = max3[c]; }
+}
+
 int orc_add_texture_array(orc_scene *s, int image) {
     Texture2D t; t.type = TEX_ARRAY; t.image = image;
     s->tex.tex2d.push_back(t);

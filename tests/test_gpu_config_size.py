@@ -100,7 +100,7 @@ def _compare_subset(rad, wgt, ref, buckets, spp, what, budget=None, image_tol=2e
     for name, (cnt, frac, med) in report.items():
         if cnt < 50:
             continue
-        assert frac <= budget.get(name, OUTLIER_BUDGET["default"]), (what, name, cnt, frac)
+        assert frac <= budget.get(name, budget.get("default", OUTLIER_BUDGET["default"])), (what, name, cnt, frac)
         assert med <= median_tol, (what, name, med)  # the typical pixel agrees to fp32 shading (/ texture filtering) accuracy
     # image-level: the subset's mean radiance and its relative MSE (outliers included: flipped paths are still valid samples)
     assert abs(a.mean() - b.mean()) <= 5e-3 * b.mean() + 1e-7, (what, a.mean(), b.mean())

@@ -130,7 +130,7 @@ def test_shade_against_reference_per_material(trio):
                                                          100.0 * v["outliers"] / max(v["matched"], 1), 100.0 * v["dir_out"] / max(v["matched"], 1)))
     # budgets per bucket: flips and outliers as fractions of the bucket's own states
     flip_budget = {"default": 0.004, "disney_transmission": 0.01, "glass": 0.004, "disney_clearcoat_sheen": 0.006}
-    outlier_budget = {"default": 0.004, "disney_normal_mapped": 0.03, "disney_metallic_textured": 0.03, "metal": 0.02}
+    outlier_budget = {"default": 0.004, "disney_normal_mapped": 0.03, "disney_metallic_textured": 0.03, "metal": 0.02, "disney_clearcoat_sheen": 0.02}
     for name, v in stats.items():
         if v["n"] < 200 or name in ("miss", "light"):
             continue
@@ -138,3 +138,40 @@ def test_shade_against_reference_per_material(trio):
         assert v["outliers"] <= outlier_budget.get(name, outlier_budget["default"]) * max(v["matched"], 1) + 2, (name, v)
         assert v["dir_out"] <= 0.004 * max(v["matched"], 1) + 2, (name, v)
     assert sum(v["matched"] for v in stats.values()) > 20000
+
+
+def test_byte_grid_medium_matches_oracle(tmp_path, built):
+    """"byte" text grids (SNorm8 3-D arrays, utils/cuda/array.cpp:331-355 -- refused in round 1): the medium stage on identical
+    batches and the whole render against the oracle, whose decoding of such grids is pinned to the reference's own loader bit for
+    bit (tests/test_reference_device_pins_cpu.py, kind "medium_bytes")."""
+    from btrc_b200 import api
+    from oracle import front
+    from tests.test_reference_device_pins_cpu import _make_medium_bytes
+
+    path = _make_medium_bytes(str(tmp_path))
+    s, o = api.Scene(path), front.OracleScene(path)
+    assert s.info.has_medium
+    st = o.generate(0, 64 * 64 * 2)
+    flag, detail = o.closest_hit(st["o_med"], st["d_t1"])
+    # second bounce: rays that start around the medium
+    sh = o.shade(*o.medium(st, flag, detail)[:2], detail)
+    keep = (sh["status"] & 1) != 0
+    st = {k: np.ascontiguousarray(v[keep]) for k, v in sh["next"].items()}
+    flag, detail = o.closest_hit(st["o_med"], st["d_t1"])
+    so, fo, mo = o.medium(st, flag, detail)
+    sg, fg, ng, shg = s.medium(st, flag, detail)
+    scat_o, scat_g = (fo >> 31) != 0, (fg >> 31) != 0
+    assert scat_o.mean() > 0.05
+    # a collision decision compares a random number with density / majorant, both through the texture unit: rare flips only
+    assert (scat_o != scat_g).mean() < 0.004
+    same = scat_o == scat_g
+    assert np.array_equal(sg["o_med"][same, 3].view(np.uint32), so["o_med"][same, 3].view(np.uint32))          # resolved medium ids
+    quiet = same & ~scat_o
+    assert np.array_equal(sg["rng"][quiet], so["rng"][quiet])                                                   # same number of draws
+    color, _, _, stats = s.render()
+    ref = o.render()
+    for k in ("n_closest", "n_hit", "n_next", "n_shadow"):
+        assert abs(stats[k] - ref["stats"][k]) <= 1e-2 * ref["stats"][k], (k, stats[k], ref["stats"][k])
+    a, b = color[..., :3], ref["color"][..., :3]
+    assert abs(a.mean() - b.mean()) < 0.02 * b.mean()
+    s.close()

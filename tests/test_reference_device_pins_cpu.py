@@ -57,7 +57,38 @@ def _make(kind, d):
         return scenes.make_volume_scene(d, width=64, height=48, spp=4, grid_res=16, state_count=40000)
     if kind == "extras":
         return _make_extras(d)
+    if kind == "medium_bytes":
+        return _make_medium_bytes(d)
     raise ValueError(kind)
+
+
+def _make_medium_bytes(d):
+    """The medium scene with a "byte" text grid: the reference extracts one CHARACTER per component and uploads SNorm8
+    (utils/cuda/array.cpp:331-355), i.e. densities char / 127; scaled by a `mul` node to a useful optical depth, plus a
+    three-channel byte grid as albedo (fourth component 255 = -1 / 127)."""
+    import json
+    import os
+
+    from btrc_b200 import scenes
+
+    path = scenes.make_medium_scene(d, width=64, height=64, spp=4, grid_res=24, state_count=50000)
+    rng = np.random.default_rng(23)
+    res = 12
+    def grid(channels):
+        chars = rng.integers(40, 127, res * res * res * channels)          # printable, non-blank ASCII
+        body = "".join(chr(c) for c in chars)
+        lines = [body[i:i + 97] for i in range(0, len(body), 97)]          # blanks and newlines between values are skipped
+        return "byte %d %d %d %d\n" % (channels, res, res, res) + " \n".join(lines) + "\n"
+    open(os.path.join(d, "density_bytes.txt"), "w").write(grid(1))
+    open(os.path.join(d, "albedo_bytes.txt"), "w").write(grid(3))
+    root = json.load(open(path))
+    for e in root["scene"]["entities"]:
+        m = e.get("inner_medium")
+        if m:
+            m["medium"]["sigma_t"] = {"type": "mul", "lhs": {"type": "array", "text": "$env{scene_directory}/density_bytes.txt"}, "rhs": 6.0}
+            m["medium"]["albedo"] = {"type": "array", "text": "$env{scene_directory}/albedo_bytes.txt", "filter": "point"}
+    json.dump(root, open(path, "w"), indent=1)
+    return path
 
 
 def _make_extras(d):
@@ -98,7 +129,7 @@ def _make_extras(d):
     return path
 
 
-KINDS = ["cornell", "materials", "medium", "homogeneous", "ibl", "volumes", "extras"]
+KINDS = ["cornell", "materials", "medium", "homogeneous", "ibl", "volumes", "extras", "medium_bytes"]
 
 
 @pytest.fixture(scope="module", params=KINDS)
@@ -213,7 +244,7 @@ def test_shadow_stage_matches_reference(pair):
     want = (sb[:, :3] * tr).astype(f32)
     want[occ_o != 0] = 0
     want[~np.isfinite(want).all(axis=1)] = 0
-    if kind in ("medium", "volumes"):
+    if kind in ("medium", "volumes", "medium_bytes"):
         m = occ_o == 0
         assert abs(contrib[m].mean() - want[m].mean()) <= 0.05 * want[m].mean() + 1e-6
         # rays that meet no density get tr = 1 from any stream: most of them, and those must agree exactly
@@ -235,11 +266,11 @@ def test_render_matches_reference(pair):
         assert abs(a.mean() - b.mean()) < 0.03 * a.mean()
         return
     for k in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss"):
-        if kind == "medium" and k != "n_gen":
+        if kind in ("medium", "medium_bytes") and k != "n_gen":
             assert abs(ro["stats"][k] - rr["stats"][k]) <= 0.01 * ro["stats"][k], k  # shadow-ray Tr streams differ (see above) only in the film
         else:
             assert ro["stats"][k] == rr["stats"][k], (kind, k, ro["stats"][k], rr["stats"][k])
-    if kind == "medium":
+    if kind in ("medium", "medium_bytes"):
         assert ((a - b) ** 2).mean() / (a.mean() ** 2) < 5e-2
     else:
         assert np.abs(a - b).max() <= 1e-5 * max(1.0, float(a.max())), np.abs(a - b).max()
