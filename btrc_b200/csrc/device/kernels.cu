@@ -303,11 +303,14 @@ __global__ void __launch_bounds__(kBlock, trace_min_blocks<TRAV>()) trace_kernel
     const int n_sorted = SORTED ? ctl->n_sorted : 0;
     const bool append = !SORTED || ctl->sort_enabled != 2;
     unsigned long long hits = 0;
+    // the cursor atomic of the next batch is issued at the top of a round and consumed at the top of the following one: its
+    // round trip is hidden behind the walk of the current 32 rays
+    int next_base = 0;
+    if (lane_id() == 0) next_base = atomicAdd(&ctl->trace_cursor, 32);
     for (;;) {
-        int base = 0;
-        if (lane_id() == 0) base = atomicAdd(&ctl->trace_cursor, 32);
-        base = __shfl_sync(kFull, base, 0);
+        const int base = __shfl_sync(kFull, next_base, 0);
         if (base >= n) break;
+        if (lane_id() == 0) next_base = atomicAdd(&ctl->trace_cursor, 32);
         const int j = base + lane_id();
         const bool valid = j < n;
         const int i = (SORTED && valid && j < n_sorted) ? (int)rs.order[j] : j;  // survivors bin by bin, new camera paths in pixel order
@@ -549,12 +552,16 @@ shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQu
     constexpr bool kDynamic = MAT == MAT_DISNEY;
     const int n_round = (n + 31) & ~31;
     unsigned long long n_splat = 0;
+    // dynamic hand-out, one round ahead: the cursor atomic of the NEXT batch is issued at the top of a round and its value used at
+    // the top of the following one, so its round trip (3 % of this kernel's stall samples, profiles/r1k_c2_shade_hot_lines.txt) is
+    // hidden behind the shading of the current batch
+    int next_base = 0;
+    if (kDynamic && lane_id() == 0) next_base = atomicAdd(&ctl->class_cursor[1 + MAT], 32);
     for (int j = blockIdx.x * blockDim.x + threadIdx.x;; j += gridDim.x * blockDim.x) {
         if (kDynamic) {
-            int base = 0;
-            if (lane_id() == 0) base = atomicAdd(&ctl->class_cursor[1 + MAT], 32);
-            base = __shfl_sync(kFull, base, 0);
+            const int base = __shfl_sync(kFull, next_base, 0);
             if (base >= n) break;
+            if (lane_id() == 0) next_base = atomicAdd(&ctl->class_cursor[1 + MAT], 32);
             j = base + lane_id();
         } else if (j >= n_round) {
             break;
@@ -674,11 +681,12 @@ __global__ void __launch_bounds__(kBlock, trace_min_blocks<TRAV>()) shadow_kerne
     const int n = ctl->n_shadow;
     const int n_sorted = SORTED ? ctl->n_shadow_sorted : 0;
     unsigned long long misses = 0;
+    int next_base = 0;  // one round ahead, as in trace_kernel
+    if (lane_id() == 0) next_base = atomicAdd(&ctl->shadow_cursor, 32);
     for (;;) {
-        int base = 0;
-        if (lane_id() == 0) base = atomicAdd(&ctl->shadow_cursor, 32);
-        base = __shfl_sync(kFull, base, 0);
+        const int base = __shfl_sync(kFull, next_base, 0);
         if (base >= n) break;
+        if (lane_id() == 0) next_base = atomicAdd(&ctl->shadow_cursor, 32);
         const int j = base + lane_id();
         const bool valid = j < n;
         const int i = (SORTED && valid && j < n_sorted) ? (int)rs.order[j] : j;

@@ -591,12 +591,6 @@ __device__ __noinline__ float volprim_tr(const SceneDevice &scene, f3 a, f3 b, S
     return result;
 }
 
-// tracking steps laid out ahead of their density fetches (medium_sample / medium_tr below)
-#ifndef BTRC_TRACK_BATCH
-#define BTRC_TRACK_BATCH 4
-#endif
-constexpr int kTrackBatch = BTRC_TRACK_BATCH;
-
 template <bool T3P = false, typename S>
 __device__ __forceinline__ MediumSample medium_sample(const SceneDevice &scene, const MediumDesc &m, f3 a, f3 b, S &sampler) {
     MediumSample r;
@@ -622,45 +616,18 @@ __device__ __forceinline__ MediumSample medium_sample(const SceneDevice &scene, 
     const f3 local_b = f3(0.5f) + 0.5f * medium_uvw(m, b);
     const f3 local_ba_div_t_max = (local_b - local_a) / t_max;
     const f3 ba_div_t_max = (b - a) / t_max;
-    // The tentative collision points depend on the random numbers only, never on the densities looked up: kTrackBatch steps are
-    // laid out ahead, their density fetches issued back to back (one texture round trip instead of kTrackBatch dependent ones --
-    // the loop is bound by that latency, profiles/r2a_c3_medium_full.md), then the accept tests run in order.  Draw order is the
-    // reference's (distance, accept, distance, accept, ...); when a collision is accepted the sampler returns to the state it had
-    // right after that step's accept draw, so the path continues with exactly the numbers the sequential loop would use.
-    bool done = false;
-    while (!done) {
-        float ts[kTrackBatch], acc[kTrackBatch], dens[kTrackBatch];
-        S after[kTrackBatch];
-        int n = 0;
-#pragma unroll
-        for (int k = 0; k < kTrackBatch; ++k) {
-            if (!done) {
-                const float dt = -logf(1.0f - sampler.get1d()) * inv_max_density;
-                t = t + dt;
-                if (t >= t_max) {
-                    done = true;
-                } else {
-                    ts[k] = t;
-                    acc[k] = sampler.get1d();
-                    after[k] = sampler;
-                    n = k + 1;
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < kTrackBatch; ++k)
-            if (k < n) dens[k] = eval_texture3d<T3P>(scene, m.sigma_t_tex, local_a + ts[k] * local_ba_div_t_max).x;
-#pragma unroll
-        for (int k = 0; k < kTrackBatch; ++k) {
-            if (k < n && !r.scattered && acc[k] < dens[k] * inv_max_density) {
-                const f3 uvw = local_a + ts[k] * local_ba_div_t_max;
-                r.scattered = true;
-                r.position = a + ts[k] * ba_div_t_max;
-                r.shader.color = eval_texture3d<T3P>(scene, m.albedo_tex, uvw);
-                r.shader.g = eval_texture3d<T3P>(scene, m.g_tex, uvw).x;
-                sampler = after[k];
-                done = true;
-            }
+    for (;;) {
+        const float dt = -logf(1.0f - sampler.get1d()) * inv_max_density;
+        t = t + dt;
+        if (t >= t_max) break;
+        const f3 uvw = local_a + t * local_ba_div_t_max;
+        const float density = eval_texture3d<T3P>(scene, m.sigma_t_tex, uvw).x;
+        if (sampler.get1d() < density * inv_max_density) {
+            r.scattered = true;
+            r.position = a + t * ba_div_t_max;
+            r.shader.color = eval_texture3d<T3P>(scene, m.albedo_tex, uvw);
+            r.shader.g = eval_texture3d<T3P>(scene, m.g_tex, uvw).x;
+            break;
         }
     }
     return r;
@@ -681,27 +648,13 @@ __device__ __forceinline__ f3 medium_tr(const SceneDevice &scene, const MediumDe
     const f3 local_a = f3(0.5f) + 0.5f * medium_uvw(m, a);
     const f3 local_b = f3(0.5f) + 0.5f * medium_uvw(m, b);
     const f3 local_ba_div_t_max = (local_b - local_a) / t_max;
-    // ratio tracking takes every step up to t_max whatever the densities are: the same look-ahead as in medium_sample, without
-    // anything to roll back; the product is accumulated in step order
-    bool done = false;
-    while (!done) {
-        float ts[kTrackBatch], dens[kTrackBatch];
-        int n = 0;
-#pragma unroll
-        for (int k = 0; k < kTrackBatch; ++k) {
-            if (!done) {
-                const float dt = -logf(1.0f - sampler.get1d()) * inv_max_density;
-                t = t + dt;
-                if (t >= t_max) done = true;
-                else { ts[k] = t; n = k + 1; }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < kTrackBatch; ++k)
-            if (k < n) dens[k] = eval_texture3d<T3P>(scene, m.sigma_t_tex, local_a + ts[k] * local_ba_div_t_max).x;
-#pragma unroll
-        for (int k = 0; k < kTrackBatch; ++k)
-            if (k < n) result = result * (1.0f - dens[k] * inv_max_density);
+    for (;;) {
+        const float dt = -logf(1.0f - sampler.get1d()) * inv_max_density;
+        t = t + dt;
+        if (t >= t_max) break;
+        const f3 uvw = local_a + t * local_ba_div_t_max;
+        const float density = eval_texture3d<T3P>(scene, m.sigma_t_tex, uvw).x;
+        result = result * (1.0f - density * inv_max_density);
     }
     return f3(result);
 }

@@ -122,7 +122,7 @@ def test_c1_cornell_512_16spp(cornell_c1):
     for k in ("n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss"):
         assert abs(st[k] - rst[k]) <= 1e-3 * rst[k], (k, st[k], rst[k])
     buckets = np.full(idx.shape[0], "diffuse", dtype=object)
-    _compare_subset(rad, wgt, ref, buckets, 16, "C1", budget={"diffuse": 0.01}, image_tol=1e-3)
+    _compare_subset(rad, wgt, ref, buckets, 16, "C1", budget={"diffuse": 0.001}, image_tol=1e-3)   # measured: 0.0001
     s.close()
 
 
@@ -140,7 +140,7 @@ def test_c2_disney_1080p_full_geometry(tmp_path, built):
     ref, _ = o.render_pixels(idx)
     buckets = _primary_buckets(o, path, idx)
     _compare_subset(rad[idx], wgt[idx], ref, buckets, 2, "C2", rel_tol=REL_TOL_TEXTURED, median_tol=3e-3,
-                    budget={"default": 0.04, "glass": 0.08, "disney_transmission": 0.08})
+                    budget={"default": 0.02})   # measured (profiles/r2d_pytest_gpu.log): at most 0.9 % in any bucket
     s.close()
 
 
@@ -159,9 +159,9 @@ def test_c3_medium_1080p_full_grid(tmp_path, built):
     idx = _subset(1920 * 1080, 61)
     ref, _ = o.render_pixels(idx)
     buckets = _primary_buckets(o, path, idx)
-    # tracking loops multiply many (1 - sigma / sigma_max) factors fetched through the texture unit (8-bit filter weights): the
-    # typical pixel still agrees to 1e-4, but more paths change their collision sequence than on surfaces
-    _compare_subset(rad[idx], wgt[idx], ref, buckets, 2, "C3", budget={"default": 0.05}, image_tol=5e-2)
+    # the density grid is a float 3-D texture: fetched exactly (the 8-bit filter weights apply to the interpolation, and both sides
+    # see the same lattice), and the shadow-ray transmittance streams are keyed on the ray in oracle and kernels alike
+    _compare_subset(rad[idx], wgt[idx], ref, buckets, 2, "C3", budget={"default": 0.005}, image_tol=1e-2)   # measured: no outlier at all
     s.close()
 
 
@@ -178,7 +178,9 @@ def test_c4_instanced_10m_full_geometry(tmp_path, built):
     idx = _subset(1920 * 1080, 43)
     ref, _ = o.render_pixels(idx)
     buckets = _primary_buckets(o, path, idx)
-    _compare_subset(rad[idx], wgt[idx], ref, buckets, 1, "C4", budget={"default": 0.03}, image_tol=5e-2)
+    # measured: 1.7 % (diffuse) / 2.6 % (metal) of the pixels differ by more than 2e-3 -- paths are up to 16 bounces deep and most
+    # of them meet a GGX lobe whose value is ill-conditioned in fp32; medians 7e-7 / 1.3e-6
+    _compare_subset(rad[idx], wgt[idx], ref, buckets, 1, "C4", budget={"default": 0.05}, image_tol=5e-2)
     s.close()
 
 
@@ -203,7 +205,7 @@ def test_c5_4k_two_rank_partitions(tmp_path, built):
     idx = _subset(npix, 211)
     ref, _ = o.render_pixels(idx)
     _compare_subset(full[idx], wfull[idx], ref, _primary_buckets(o, path, idx), spp, "C5", rel_tol=REL_TOL_TEXTURED, median_tol=3e-3,
-                    budget={"default": 0.04, "glass": 0.08, "disney_transmission": 0.08})
+                    budget={"default": 0.025})  # measured: at most 1.1 % in any bucket
     s.close()
 
     # tile split: tile-mode indexing (generate.cpp:56-60), every rank renders all samples of its strips of pixel rows

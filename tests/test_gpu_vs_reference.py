@@ -129,8 +129,12 @@ def test_shade_against_reference_per_material(trio):
         print("%-28s %7d  %7d  %6d  %5.2f   %8.2f   %8.2f" % (name, v["n"], v["matched"], v["flips"], 100.0 * v["flips"] / max(v["n"], 1),
                                                          100.0 * v["outliers"] / max(v["matched"], 1), 100.0 * v["dir_out"] / max(v["matched"], 1)))
     # budgets per bucket: flips and outliers as fractions of the bucket's own states
-    flip_budget = {"default": 0.004, "disney_transmission": 0.01, "glass": 0.004, "disney_clearcoat_sheen": 0.006}
-    outlier_budget = {"default": 0.004, "disney_normal_mapped": 0.03, "disney_metallic_textured": 0.03, "metal": 0.02, "disney_clearcoat_sheen": 0.02}
+    # Measured on B200 against the reference's own code (profiles/r2d_pytest_gpu.log): 3 flips in 46,000 states (all on the
+    # normal-mapped ground); throughput outliers 1.3 % clearcoat (gloss 0.9: a GGX lobe with alpha ~ 1e-2 whose D term moves by
+    # percents under a 1e-7 change of the half vector), 0.7 % / 1.6 % for the textured buckets (8-bit texture filter weights), 0.07 %
+    # transmission, none for glass / metal / mirror.  Budgets: about twice the measured rates, per bucket.
+    flip_budget = {"default": 0.001}
+    outlier_budget = {"default": 0.003, "disney_normal_mapped": 0.03, "disney_metallic_textured": 0.015, "disney_clearcoat_sheen": 0.03}
     for name, v in stats.items():
         if v["n"] < 200 or name in ("miss", "light"):
             continue
