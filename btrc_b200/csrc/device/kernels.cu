@@ -328,6 +328,46 @@ __global__ void __launch_bounds__(kBlock, trace_min_blocks<TRAV>()) trace_kernel
     if (lane_id() == 0 && hits) atomicAdd(&ctl->n_hit, hits);
 }
 
+// PROFILING ONLY (BTRC_PROBE_TOP_LEVELS=<depth>, never launched otherwise): replays the closest-hit walk of the current wave but
+// touches only the nodes of the first `max_depth` levels of the tree -- subtrees below are skipped, triangles never fetched, nothing
+// is written.  Under ncu its lts__t_sector_hit_rate / l1tex__t_sector_hit_rate are the cache hit rates of the TOP BVH LEVELS on real
+// ray batches (the counters cannot be split by address inside trace_kernel itself); profiles/README.md.
+__global__ void __launch_bounds__(kBlock) top_levels_probe_kernel(SceneDevice scene, PathQueue q, const WaveCtl *ctl, int max_depth, unsigned long long *sink) {
+    const int n = ctl->n_active;
+    unsigned long long visited = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o4 = q.ray_o[i], d4 = q.ray_d[i];
+        constexpr float kTiny = 1e-20f;
+        const float idx = 1.0f / (fabsf(d4.x) > kTiny ? d4.x : copysignf(kTiny, d4.x));
+        const float idy = 1.0f / (fabsf(d4.y) > kTiny ? d4.y : copysignf(kTiny, d4.y));
+        const float idz = 1.0f / (fabsf(d4.z) > kTiny ? d4.z : copysignf(kTiny, d4.z));
+        const float oox = o4.x * idx, ooy = o4.y * idy, ooz = o4.z * idz;
+        int stack[64], depth_of[64];
+        int sp = 0;
+        if (scene.bvh.root_ref >= 0) { stack[sp] = scene.bvh.root_ref; depth_of[sp++] = 1; }
+        while (sp > 0) {
+            const int cur = stack[--sp], depth = depth_of[sp];
+            const float4 *node = scene.bvh.nodes + 4 * (size_t)cur;
+            const float4 n0 = __ldg(node), n1 = __ldg(node + 1), nz = __ldg(node + 2), meta = __ldg(node + 3);
+            ++visited;
+            const float c0min = fmaxf(fmaxf(fminf(fmaf(n0.x, idx, -oox), fmaf(n0.y, idx, -oox)), fminf(fmaf(n0.z, idy, -ooy), fmaf(n0.w, idy, -ooy))),
+                                      fmaxf(fminf(fmaf(nz.x, idz, -ooz), fmaf(nz.y, idz, -ooz)), 0.0f));
+            const float c0max = fminf(fminf(fmaxf(fmaf(n0.x, idx, -oox), fmaf(n0.y, idx, -oox)), fmaxf(fmaf(n0.z, idy, -ooy), fmaf(n0.w, idy, -ooy))),
+                                      fminf(fmaxf(fmaf(nz.x, idz, -ooz), fmaf(nz.y, idz, -ooz)), d4.w));
+            const float c1min = fmaxf(fmaxf(fminf(fmaf(n1.x, idx, -oox), fmaf(n1.y, idx, -oox)), fminf(fmaf(n1.z, idy, -ooy), fmaf(n1.w, idy, -ooy))),
+                                      fmaxf(fminf(fmaf(nz.z, idz, -ooz), fmaf(nz.w, idz, -ooz)), 0.0f));
+            const float c1max = fminf(fminf(fmaxf(fmaf(n1.x, idx, -oox), fmaf(n1.y, idx, -oox)), fmaxf(fmaf(n1.z, idy, -ooy), fmaf(n1.w, idy, -ooy))),
+                                      fminf(fmaxf(fmaf(nz.z, idz, -ooz), fmaf(nz.w, idz, -ooz)), d4.w));
+            const int r0 = __float_as_int(meta.x), r1 = __float_as_int(meta.y);
+            if (depth < max_depth) {
+                if (c1min <= c1max && r1 >= 0) { stack[sp] = r1; depth_of[sp++] = depth + 1; }
+                if (c0min <= c0max && r0 >= 0) { stack[sp] = r0; depth_of[sp++] = depth + 1; }
+            }
+        }
+    }
+    if (visited == 0xffffffffffffffffull) *sink = visited;  // keeps the loads alive
+}
+
 // Builds the class lists from hit flags (stage-level entry points: the hits come from the caller, not from trace_kernel)
 __global__ void __launch_bounds__(kBlock) classify_kernel(SceneDevice scene, HitQueue hq, WaveCtl *ctl) {
     const int n = ctl->n_active;
@@ -486,6 +526,7 @@ __global__ void __launch_bounds__(kBlock) medium_kernel(SceneDevice scene, Rende
                     }
                     f3 phase, pdir;
                     float ppdf;
+                    sampler.begin3d();  // phase sample: get3d (medium.cpp:117)
                     const float p0 = sampler.get1d(), p1 = sampler.get1d();
                     (void)sampler.get1d();
                     ms.shader.sample(wo, p0, p1, phase, pdir, ppdf);
@@ -608,6 +649,7 @@ shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQu
                         if (film.normal) film_splat3(film.normal, pixel, shader.normal());
                     }
                     const f3 wo = -d;
+                    sampler.begin3d();  // bsdf sample: get3d (shade.cpp:143-144)
                     const float b0 = sampler.get1d(), b1 = sampler.get1d(), b2 = sampler.get1d();
                     BsdfSample bs = bsdf_none();
                     if (!shader.is_aggregate()) {
@@ -773,6 +815,8 @@ void launch_ray_sort(const LaunchCfg &cfg, const SceneDevice &scene, const float
 
 void launch_trace(const LaunchCfg &cfg, const SceneDevice &scene, PathQueue cur, HitQueue hit, RaySort rs, WaveCtl *ctl, cudaStream_t stream) {
     const int blocks = persistent_blocks(cfg, 8);
+    if (cfg.probe_top_levels > 0 && !scene.bvh.two_level)
+        top_levels_probe_kernel<<<blocks, kBlock, 0, stream>>>(scene, cur, ctl, cfg.probe_top_levels, reinterpret_cast<unsigned long long *>(&ctl->n_iter));
 #define BTRC_TRACE(T, S) trace_kernel<T, S><<<blocks, kBlock, 0, stream>>>(scene, cur, hit, rs, ctl)
     const int trav = scene.bvh.two_level ? 2 : (cfg.traverse_ifif ? 1 : 0);
     if (cfg.sorted_rays) { if (trav == 2) BTRC_TRACE(2, true); else if (trav == 1) BTRC_TRACE(1, true); else BTRC_TRACE(0, true); }

@@ -19,6 +19,7 @@ struct LaunchCfg {
     // 67.8 ms), if-if when node fetches go to DRAM and the extra loads in flight per warp pay (C4, 0.7 GB of BVH: 136 vs 153 ms);
     // profiles/r1h_ab_ifif.log.  The renderer picks by BVH size against the L2 capacity.
     bool traverse_ifif = false;
+    int probe_top_levels = 0;  // profiling only (BTRC_PROBE_TOP_LEVELS): also launch top_levels_probe_kernel on every wave
     bool sorted_rays = false;  // the traversal kernels visit rays through RaySort::order (types.h); set with the renderer's sort mode
 };
 

@@ -136,6 +136,7 @@ struct SamplerT<false> {
     __device__ __forceinline__ void load(ulonglong2 v, const HaltonConsts &) { rng.state = v.x; rng.inc = v.y; }
     __device__ __forceinline__ ulonglong2 store() const { return make_ulonglong2(rng.state, rng.inc); }
     __device__ __forceinline__ float get1d() { return rng.uniform(); }
+    __device__ __forceinline__ void begin3d() {}  // get3d = three get1d (core/sampler.h:22-28); see SamplerT<true>
 };
 
 template <>
@@ -160,7 +161,12 @@ struct SamplerT<true> {
     }
     __device__ __forceinline__ void load(ulonglong2 v, const HaltonConsts &hc) { halton_index = v.x; dimension = uint32_t(v.y >> 1); primes = hc.primes; }
     __device__ __forceinline__ ulonglong2 store() const { return make_ulonglong2(halton_index, uint64_t(dimension) << 1); }
-    __device__ __forceinline__ float get1d() {  // halton.cpp:80-89 (get2d / get3d differ only in where they wrap beyond dimension 997)
+    // HaltonSampler::get3d (halton.cpp:106-118) wraps the dimension counter BEFORE the triple when it would run past the prime
+    // table, so that the three values never straddle the wrap; call this before three consecutive get1d() that stand for a get3d
+    __device__ __forceinline__ void begin3d() {
+        if (dimension + 2 >= (uint32_t)kPrimeTableSize) dimension = 2;
+    }
+    __device__ __forceinline__ float get1d() {  // halton.cpp:80-89
         if (dimension >= (uint32_t)kPrimeTableSize) dimension = 2;
         const float r = owen_scrambled_radical_inverse(primes, int(dimension), halton_index, mix_bits(uint64_t(1u + (dimension << 4))));
         dimension = dimension + 1;

@@ -205,6 +205,7 @@ template <bool SURFACE, typename S>
 __device__ __forceinline__ LiSample sample_light_li(const SceneDevice &scene, f3 ref_pos, f3 ref_nor, S &sampler) {
     LiSample r;
     r.success = false;
+    sampler.begin3d();  // light sample: get3d, then the light choice get1d (helper.cpp:21-22)
     const float s0 = sampler.get1d(), s1 = sampler.get1d(), s2 = sampler.get1d();
     const float sel = sampler.get1d();
     const int n = scene.n_lights;

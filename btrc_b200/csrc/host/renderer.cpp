@@ -51,6 +51,7 @@ Renderer::Renderer(Scene &scene, int state_count_override) : scene_(scene) {
         // does not pay for the sort and the gather (C2 +4 %, C3 +11 %, C1 +17 %; profiles/r1j_ab_ray_sort.log).  BTRC_SORT_RAYS=0|1|2 overrides.
         sort_rays_ = bvh_bytes > (size_t)prop.l2CacheSize ? 2 : 0;
     }
+    if (const char *e = std::getenv("BTRC_PROBE_TOP_LEVELS")) cfg_.probe_top_levels = std::atoi(e);
     pool_ = state_count_override > 0 ? state_count_override : scene.renderer.state_count;
     if (pool_ <= 0) throw Error("state_count must be positive");
     BTRC_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));

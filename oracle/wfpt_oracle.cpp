@@ -236,7 +236,10 @@ struct Sampler {  // independent.cpp:11-25, core/sampler.h:22-28; halton.cpp:46-
         rng.inc = uint64_t(dimension + 1) << 1;
         return r;
     }
-    V3 get3d() { float a = get1d(); float b = get1d(); float c = get1d(); return {a, b, c}; }
+    V3 get3d() {  // independent: three get1d (core/sampler.h:22-28); halton.cpp:106-118 wraps the dimension before the triple
+        if (!(rng.inc & 1) && uint32_t(rng.inc >> 1) + 2 >= (uint32_t)PRIME_TABLE_SIZE) rng.inc = uint64_t(2) << 1;
+        float a = get1d(); float b = get1d(); float c = get1d(); return {a, b, c};
+    }
 };
 
 // ------------------------------------------------------------------------------------------

@@ -39,6 +39,32 @@ def test_pixel_blocks_cover_the_image():
                 assert partition.tile_path_range(r, world, 16, npix) == (blocks[r][0] * 16, blocks[r][1] * 16)
 
 
+def test_interleaved_strips_tile_the_image():
+    """The tile partition of `btrc_render_part` (strips of pixel rows dealt round-robin): every pixel row belongs to exactly one
+    rank, strips are whole rows, and no rank's share exceeds another's by more than one strip."""
+    from btrc_b200 import partition
+
+    for world in (1, 2, 3, 4, 8):
+        for (w, h) in ((64, 48), (1920, 1080), (3840, 2160), (7, 5)):
+            for spp in (1, 16):
+                rows = partition.strip_rows(world, h)
+                assert 1 <= rows <= 16
+                owner = [-1] * h
+                sizes = []
+                for r in range(world):
+                    n = 0
+                    for b, e in partition.tile_path_ranges(r, world, spp, w, h):
+                        assert b % (w * spp) == 0 and e % (w * spp) == 0 and e > b
+                        for y in range(b // (w * spp), e // (w * spp)):
+                            assert owner[y] == -1
+                            owner[y] = r
+                        n += e - b
+                    sizes.append(n)
+                assert all(o >= 0 for o in owner)
+                assert sum(sizes) == w * h * spp
+                assert max(sizes) - min(sizes) <= rows * w * spp
+
+
 def _worker(rank, world, path, port, out):
     sys.path.insert(0, ROOT)
     import torch
