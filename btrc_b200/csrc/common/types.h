@@ -298,6 +298,14 @@ struct WaveCtl {
     long long stride_block;
     int stride_parts, stride_part;
     int weight_prefilled;  // the film's weight plane was filled in closed form for this render: generate skips its atomic
+    // Generation ORDER (not a partition): when the range is whole sample planes [order_s0, order_s0 + order_ns) of every pixel in
+    // Uniform indexing, the walk visits them pixel block by pixel block (order_bw x order_bh pixels, all samples of a pixel
+    // consecutively) instead of plane by plane.  Every path keeps its (pixel, sample index) and with it its random stream
+    // (results are order independent up to the film's float additions); what changes is that the rays of a wave --
+    // and the 32 rays of a warp -- start in one image region.  order_ns == 0: queue order = index order.
+    int order_s0, order_ns;
+    int order_bw, order_bh;   // pixel block of the generation order
+    int order_sample_major;   // inside a block: 0 = all samples of a pixel consecutively, 1 = all pixels of the block sample by sample
     // statistics (SURVEY 8d event counts)
     unsigned long long n_gen, n_closest, n_hit, n_next_total, n_shadow_total, n_shadow_miss, n_splat, n_iter;
 };

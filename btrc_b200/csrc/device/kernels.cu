@@ -17,6 +17,12 @@ namespace btrc {
 namespace {
 
 constexpr int kBlock = 256;
+// 1: the dynamic work cursors are advanced one round ahead of their use, to hide the atomic's round trip.  Measured on B200 and NOT
+// adopted (profiles/r2h_ab_kernel_variants.md: C2 1123 with, 1159 Msamples/s without -- the value carried across the round costs the
+// register-capped kernels more than the hidden latency returns); kept as a build switch for the record.
+#ifndef BTRC_CURSOR_AHEAD
+#define BTRC_CURSOR_AHEAD 0
+#endif
 constexpr unsigned kFull = 0xffffffffu;
 // TRAV: loop form / hierarchy of the walk (kernels.h LaunchCfg::traverse): 0 while-while, 1 if-if, 2 two-level (instanced scenes)
 template <bool ANY_HIT, int TRAV>
@@ -143,9 +149,37 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(SceneDevice scene, Ren
     const long long sblock = ctl->stride_block;
     const int sparts = ctl->stride_parts, spart = ctl->stride_part;
     const bool splat_weight = ctl->weight_prefilled == 0;
+    const int order_ns = ctl->order_ns, order_s0 = ctl->order_s0, osm = ctl->order_sample_major;
+    const long long obw = ctl->order_bw, obh = ctl->order_bh;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) {
         long long accu = gen_base + i;
         if (sblock > 0) accu = ((accu / sblock) * sparts + spart) * sblock + accu % sblock;
+        if (order_ns > 0) {  // block-coherent order over whole sample planes (types.h WaveCtl::order_ns): virtual -> (pixel, sample)
+            const long long W = P.width, H = P.height;
+            const long long per_block_row = W * obh * order_ns;
+            const long long br = accu / per_block_row;
+            const long long in_row = accu - br * per_block_row;
+            const long long hr = (br + 1) * obh <= H ? obh : H - br * obh;   // the last block row may be lower
+            long long q;   // pixel ordinal inside the block row (blocks side by side, row-major inside a block)
+            int sample;
+            if (!osm) {    // all samples of a pixel consecutively
+                q = in_row / order_ns;
+                sample = order_s0 + int(in_row - q * order_ns);
+            } else {       // block by block, inside a block sample plane by sample plane
+                const long long full = obw * hr * order_ns;                  // paths of a full-width block of this row
+                const long long bc0 = in_row / full;
+                const long long wc0 = (bc0 + 1) * obw <= W ? obw : W - bc0 * obw;
+                const long long in_block = in_row - bc0 * full;
+                const long long npb = wc0 * hr;                              // pixels of this block
+                sample = order_s0 + int(in_block / npb);
+                q = bc0 * obw * hr + in_block % npb;
+            }
+            const long long bc = q / (obw * hr);
+            const long long within = q - bc * obw * hr;
+            const long long wc = (bc + 1) * obw <= W ? obw : W - bc * obw;
+            const long long y = br * obh + within / wc, x = bc * obw + within % wc;
+            accu = (long long)sample * (W * H) + (y * W + x);       // Uniform index of that (pixel, sample): generate.cpp:49-55
+        }
         GenOut<HALTON> g = generate_one<HALTON>(scene, P, accu);
         const uint32_t pixel = g.py * (uint32_t)P.width + g.px;
         // generate.cpp:79: film.splat_atomic(pixel, weight, 1).  A render over a known index range fills the plane beforehand
@@ -303,14 +337,13 @@ __global__ void __launch_bounds__(kBlock, trace_min_blocks<TRAV>()) trace_kernel
     const int n_sorted = SORTED ? ctl->n_sorted : 0;
     const bool append = !SORTED || ctl->sort_enabled != 2;
     unsigned long long hits = 0;
-    // the cursor atomic of the next batch is issued at the top of a round and consumed at the top of the following one: its
-    // round trip is hidden behind the walk of the current 32 rays
     int next_base = 0;
-    if (lane_id() == 0) next_base = atomicAdd(&ctl->trace_cursor, 32);
+    if (BTRC_CURSOR_AHEAD && lane_id() == 0) next_base = atomicAdd(&ctl->trace_cursor, 32);
     for (;;) {
+        if (!BTRC_CURSOR_AHEAD && lane_id() == 0) next_base = atomicAdd(&ctl->trace_cursor, 32);
         const int base = __shfl_sync(kFull, next_base, 0);
         if (base >= n) break;
-        if (lane_id() == 0) next_base = atomicAdd(&ctl->trace_cursor, 32);
+        if (BTRC_CURSOR_AHEAD && lane_id() == 0) next_base = atomicAdd(&ctl->trace_cursor, 32);
         const int j = base + lane_id();
         const bool valid = j < n;
         const int i = (SORTED && valid && j < n_sorted) ? (int)rs.order[j] : j;  // survivors bin by bin, new camera paths in pixel order
@@ -577,6 +610,9 @@ __global__ void __launch_bounds__(kBlock) shade_miss_kernel(SceneDevice scene, P
 #ifndef BTRC_SHADE_BLOCKS_HEAVY
 #define BTRC_SHADE_BLOCKS_HEAVY 2
 #endif
+#ifndef BTRC_SHADE_CTA_SYNC
+#define BTRC_SHADE_CTA_SYNC 0
+#endif
 #ifndef BTRC_SHADE_BLOCK_HEAVY
 #define BTRC_SHADE_BLOCK_HEAVY 256
 #endif
@@ -593,17 +629,33 @@ shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQu
     constexpr bool kDynamic = MAT == MAT_DISNEY;
     const int n_round = (n + 31) & ~31;
     unsigned long long n_splat = 0;
-    // dynamic hand-out, one round ahead: the cursor atomic of the NEXT batch is issued at the top of a round and its value used at
-    // the top of the following one, so its round trip (3 % of this kernel's stall samples, profiles/r1k_c2_shade_hot_lines.txt) is
-    // hidden behind the shading of the current batch
     int next_base = 0;
-    if (kDynamic && lane_id() == 0) next_base = atomicAdd(&ctl->class_cursor[1 + MAT], 32);
+#if BTRC_SHADE_CTA_SYNC
+    // experiment (profiles/r2h_ab_kernel_variants.md, not adopted: no gain): the CTA takes 256 states per round and its warps start every round together, so
+    // that they run the same stretch of this 64 KB kernel at about the same time (instruction-cache sharing)
+    __shared__ int s_base[2];
+    if (kDynamic && threadIdx.x == 0) s_base[0] = atomicAdd(&ctl->class_cursor[1 + MAT], (int)blockDim.x);
+    int round = 0;
+#else
+    if (BTRC_CURSOR_AHEAD && kDynamic && lane_id() == 0) next_base = atomicAdd(&ctl->class_cursor[1 + MAT], 32);
+#endif
     for (int j = blockIdx.x * blockDim.x + threadIdx.x;; j += gridDim.x * blockDim.x) {
         if (kDynamic) {
+#if BTRC_SHADE_CTA_SYNC
+            __syncthreads();
+            const int base = s_base[round & 1];
+            if (base >= n) break;
+            if (threadIdx.x == 0) s_base[(round + 1) & 1] = atomicAdd(&ctl->class_cursor[1 + MAT], (int)blockDim.x);
+            ++round;
+            j = base + (int)threadIdx.x;
+            (void)next_base;
+#else
+            if (!BTRC_CURSOR_AHEAD && lane_id() == 0) next_base = atomicAdd(&ctl->class_cursor[1 + MAT], 32);
             const int base = __shfl_sync(kFull, next_base, 0);
             if (base >= n) break;
-            if (lane_id() == 0) next_base = atomicAdd(&ctl->class_cursor[1 + MAT], 32);
+            if (BTRC_CURSOR_AHEAD && lane_id() == 0) next_base = atomicAdd(&ctl->class_cursor[1 + MAT], 32);
             j = base + lane_id();
+#endif
         } else if (j >= n_round) {
             break;
         }
@@ -723,12 +775,13 @@ __global__ void __launch_bounds__(kBlock, trace_min_blocks<TRAV>()) shadow_kerne
     const int n = ctl->n_shadow;
     const int n_sorted = SORTED ? ctl->n_shadow_sorted : 0;
     unsigned long long misses = 0;
-    int next_base = 0;  // one round ahead, as in trace_kernel
-    if (lane_id() == 0) next_base = atomicAdd(&ctl->shadow_cursor, 32);
+    int next_base = 0;
+    if (BTRC_CURSOR_AHEAD && lane_id() == 0) next_base = atomicAdd(&ctl->shadow_cursor, 32);
     for (;;) {
+        if (!BTRC_CURSOR_AHEAD && lane_id() == 0) next_base = atomicAdd(&ctl->shadow_cursor, 32);
         const int base = __shfl_sync(kFull, next_base, 0);
         if (base >= n) break;
-        if (lane_id() == 0) next_base = atomicAdd(&ctl->shadow_cursor, 32);
+        if (BTRC_CURSOR_AHEAD && lane_id() == 0) next_base = atomicAdd(&ctl->shadow_cursor, 32);
         const int j = base + lane_id();
         const bool valid = j < n;
         const int i = (SORTED && valid && j < n_sorted) ? (int)rs.order[j] : j;

@@ -152,6 +152,22 @@ void Renderer::render_range(long long begin, long long end, long long stride_blo
     init.stride_parts = stride_parts;
     init.stride_part = stride_part;
     init.weight_prefilled = 1;
+    {   // block-coherent generation order for ranges made of whole sample planes (types.h WaveCtl::order_ns); BTRC_GEN_ORDER=0 turns it off
+        static const bool coherent = !(std::getenv("BTRC_GEN_ORDER") && std::atoi(std::getenv("BTRC_GEN_ORDER")) == 0);
+        const long long npix = (long long)scene_.width * scene_.height;
+        if (coherent && !scene_.renderer.tile && stride_block == 0 && end > begin && begin % npix == 0 && end % npix == 0) {
+            init.order_s0 = (int)(begin / npix);
+            init.order_ns = (int)((end - begin) / npix);
+            init.order_bw = 32; init.order_bh = 16; init.order_sample_major = 0;
+            if (const char *e = std::getenv("BTRC_GEN_BLOCK")) {  // tuning: "<width>x<height>[s]" (s: sample-major inside a block)
+                int bw = 0, bh = 0;
+                char mode = 0;
+                if (std::sscanf(e, "%dx%d%c", &bw, &bh, &mode) >= 2 && bw > 0 && bh > 0) { init.order_bw = bw; init.order_bh = bh; init.order_sample_major = mode == 's'; }
+            }
+            init.cursor = 0;
+            init.end = end - begin;
+        }
+    }
     ctl_host_[8] = init;  // pinned staging slot: the upload is a true async copy on the renderer's stream
     BTRC_CUDA(cudaMemcpyAsync(ctl_, &ctl_host_[8], sizeof(init), cudaMemcpyHostToDevice, stream_));
     BTRC_CUDA(cudaEventRecord(ev_begin_, stream_));
