@@ -158,7 +158,7 @@ void Renderer::render_range(long long begin, long long end, long long stride_blo
         if (coherent && !scene_.renderer.tile && stride_block == 0 && end > begin && begin % npix == 0 && end % npix == 0) {
             init.order_s0 = (int)(begin / npix);
             init.order_ns = (int)((end - begin) / npix);
-            init.order_bw = 32; init.order_bh = 16; init.order_sample_major = 0;
+            init.order_bw = 64; init.order_bh = 32; init.order_sample_major = 0;  // profiles/r2i_sweep_gen_order.md
             if (const char *e = std::getenv("BTRC_GEN_BLOCK")) {  // tuning: "<width>x<height>[s]" (s: sample-major inside a block)
                 int bw = 0, bh = 0;
                 char mode = 0;

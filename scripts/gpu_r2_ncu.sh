@@ -1,0 +1,45 @@
+#!/bin/bash
+# Round-2 profiler session: ncu launch list + `--set full` captures of every hot kernel on its workload, DRAM traffic per ray /
+# state for bench.py's dram_frac, and the top-BVH-levels cache probe.  Numbers printed by runs under ncu are never bench values.
+TAG=${1:-r2n}
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -2
+export BTRC_ITER_LOG=1
+prof() {  # workload, short name, kernel regex (mangled base), stage key, skip, count, [extra env]
+  WL=$1; N=$2; K=$3; STAGE=$4; SKIP=$5; CNT=$6; shift 6
+  env "$@" timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:$K -s $SKIP -c $CNT -f -o gpurun_out/prof_${N}_$TAG \
+      python bench.py --workload $WL --steps 1 --warmup 3 --spp ${SPP:-8} --no-cpu-baseline --no-workloads > gpurun_out/ncu_${N}_$TAG.log 2>&1
+  grep "btrc iter" gpurun_out/ncu_${N}_$TAG.log > gpurun_out/iters_${N}_$TAG.log
+  [ -n "$STAGE" ] && env "$@" python scripts/ncu_summary.py traffic gpurun_out/prof_${N}_$TAG.ncu-rep gpurun_out/iters_${N}_$TAG.log $SKIP $STAGE gpurun_out/traffic_$WL.json > /dev/null
+  python scripts/ncu_summary.py full gpurun_out/prof_${N}_$TAG.ncu-rep gpurun_out/${TAG}_${N}_full.md > /dev/null 2>&1
+  python scripts/ncu_hot_lines.py gpurun_out/prof_${N}_$TAG.ncu-rep 30 > gpurun_out/${TAG}_${N}_hot_lines.txt 2>/dev/null
+  ls -la gpurun_out/prof_${N}_$TAG.ncu-rep 2>&1 | tail -1
+  # the merged-back directory is capped at 64 MiB: only the two headline captures travel as .ncu-rep, the rest as summaries
+  case $N in c2_trace|c2_shade) ;; *) rm -f gpurun_out/prof_${N}_$TAG.ncu-rep ;; esac
+}
+C2=c2_disney_1080p_256spp; C3=c3_medium_1080p_128spp; C4=c4_instanced_10m_1080p_128spp; C1=c1_cornell_512_16spp
+# launch list of one C2 step (every kernel, in order)
+SPP=8 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_c2_$TAG.csv \
+    python bench.py --workload $C2 --steps 1 --warmup 3 --spp 8 --no-cpu-baseline --no-workloads > gpurun_out/ncu_launch_c2_$TAG.log 2>&1
+# C2 at 32 spp (4 full waves of 8 Mi states before the tail): launches 12.. are steady-state waves of mixed depth
+SPP=32 prof $C2 c2_trace trace_kernel trace 12 4
+SPP=32 prof $C2 c2_shade shade_kernelILi2E shade 12 4
+SPP=32 prof $C2 c2_shadow shadow_kernel shadow 12 4
+SPP=32 prof $C2 c2_generate generate_kernel generate 3 3
+SPP=32 prof $C2 c2_toplevels top_levels_probe "" 12 3 BTRC_PROBE_TOP_LEVELS=8
+SPP=32 prof $C2 c2_toplevels12 top_levels_probe "" 12 3 BTRC_PROBE_TOP_LEVELS=12
+# C3: the medium kernel and its neighbours
+SPP=32 prof $C3 c3_medium medium_kernel medium 12 4
+SPP=32 prof $C3 c3_shade shade_kernelILi0E shade 12 3 SHADE_CLASS=1
+SPP=32 prof $C3 c3_shadow shadow_kernel shadow 12 3
+SPP=32 prof $C3 c3_trace trace_kernel trace 12 3
+# C4: BVH larger than the L2
+SPP=16 prof $C4 c4_trace trace_kernel trace 6 3
+SPP=16 prof $C4 c4_shadow shadow_kernel shadow 6 3
+SPP=16 prof $C4 c4_toplevels top_levels_probe "" 6 2 BTRC_PROBE_TOP_LEVELS=8
+SPP=16 prof $C4 c4_toplevels16 top_levels_probe "" 6 2 BTRC_PROBE_TOP_LEVELS=16
+# C1
+SPP=16 prof $C1 c1_trace trace_kernel trace 4 3
+SPP=16 prof $C1 c1_shade shade_kernelILi0E shade 4 3 SHADE_CLASS=1
+SPP=16 prof $C1 c1_shadow shadow_kernel shadow 4 3
+ls gpurun_out/*.json | head -20; du -sh gpurun_out

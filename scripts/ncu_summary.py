@@ -122,7 +122,9 @@ def traffic(src, iters_log, skip, stage, dst):
         m = re.search(r"\[btrc iter\] (\d+) n_active=(\d+) n_new=(\d+) n_next=(\d+) n_shadow=(\d+) classes=([\d,]+)", line)
         if m:
             cls = [int(x) for x in m.group(6).split(",")]
-            iters[int(m.group(1))] = {"trace": int(m.group(2)), "shadow": int(m.group(5)), "shade": cls[3]}  # class 3 = 1 + MAT_DISNEY
+            # class 3 = 1 + MAT_DISNEY; SHADE_CLASS selects another material's list (e.g. 1 = diffuse for C1 / C3 / C4)
+            iters[int(m.group(1))] = {"trace": int(m.group(2)), "shadow": int(m.group(5)), "shade": cls[int(os.environ.get("SHADE_CLASS", "3"))],
+                                      "medium": int(m.group(2)), "generate": int(m.group(3))}
     launches_ = []
     for k, r in enumerate(rows[2:]):
         idx = int(skip) + k
