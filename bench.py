@@ -479,7 +479,7 @@ def measure(args, D, workload, steps, warmup, spp_override=0, e2e=True, cpu=True
     mrays = (n_closest + n_shadow) / secs / 1e6
 
     # ---- roofline of the dominant kernel (rank 0's stage times; algorithmic bytes per SURVEY 8d)
-    bvh = bvh_alg_per_ray(path, workload=(workload if not spp_override or workload in WORKLOADS else None)) if bvh_stats else None
+    bvh = bvh_alg_per_ray(path, workload=workload) if bvh_stats else None   # per ray: independent of the spp override
     peak, peak_src = measured_peak()
     sb = stage_bytes({k: agg[k] for k in ("n_gen", "n_closest", "n_hit", "n_next", "n_shadow", "n_shadow_miss", "n_splat")}, bvh,
                      has_medium=bool(s.info.has_medium))
@@ -624,8 +624,9 @@ def main():
                     help="default: %s on one GPU, %s (strong scaling) on several" % (DEFAULT_WORKLOAD, SCALING_WORKLOAD))
     ap.add_argument("--write-bvh-alg", action="store_true", help="(CPU only) measure the lib/bvh statistics of every workload scene into profiles/bvh_alg.json")
     ap.add_argument("--no-workloads", action="store_true", help="skip the short side runs of the other BASELINE configurations")
-    ap.add_argument("--state-count", type=int, default=8388608,
-                    help="path-state pool (the renderer's `state_count` parameter); 8 Mi states = 2.4 GB of queues (profiles/r1h_sweep_pool.log)")
+    ap.add_argument("--state-count", type=int, default=33554432,
+                    help="path-state pool (the renderer's `state_count` parameter); 32 Mi states = 9.4 GB of queues.  C2 with the block-coherent "
+                         "generation order: 1192 / 1242 / 1273 Msamples/s at 8 / 16 / 32 Mi (profiles/r2j_sweep_pool.md)")
     ap.add_argument("--partition", default="auto", choices=["auto", "samples", "tiles"],
                     help="multi-GPU split: sample-index ranges or image tiles (interleaved strips of pixel rows); auto = tiles for the "
                          "strong-scaling configuration (BASELINE config 5's wording), samples otherwise")

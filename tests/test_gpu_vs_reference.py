@@ -46,13 +46,18 @@ def _bucket_names(path):
     return [name(e) for e in ents]
 
 
-@pytest.fixture(scope="module")
-def trio(tmp_path_factory, built):
+@pytest.fixture(scope="module", params=["materials", "extras"])
+def trio(request, tmp_path_factory, built):
     from btrc_b200 import api, scenes
     from oracle import front
 
-    d = tmp_path_factory.mktemp("c2_vs_ref")
-    path = scenes.make_material_test(str(d), width=W2, height=H2, spp=8, rings=12, segments=16, tex_res=64, state_count=60000)
+    d = tmp_path_factory.mktemp("vs_ref_" + request.param)
+    if request.param == "materials":
+        path = scenes.make_material_test(str(d), width=W2, height=H2, spp=8, rings=12, segments=16, tex_res=64, state_count=60000)
+    else:  # black / invisible surfaces, texture graphs (mul, add, transform), mirror / border / point addressing, box filter + tile indexing
+        from tests.test_reference_device_pins_cpu import _make_extras
+
+        path = _make_extras(str(d))
     s = api.Scene(path)
     o = front.OracleScene(path)
     ref, kind = o, "oracle (reference host build unavailable here)"
@@ -75,7 +80,7 @@ def test_shade_against_reference_per_material(trio):
     names = _bucket_names(path)
     print("\nreference side:", kind)
     stats = {}
-    st = o.generate(0, W2 * H2 * 8)
+    st = o.generate(0, min(o.width * o.height * o.spp, 40000))
     for bounce in range(5):
         flag, detail = o.closest_hit(st["o_med"], st["d_t1"])
         want = ref.shade(st, flag, detail)
@@ -135,13 +140,15 @@ def test_shade_against_reference_per_material(trio):
     # transmission, none for glass / metal / mirror.  Budgets: about twice the measured rates, per bucket.
     flip_budget = {"default": 0.001}
     outlier_budget = {"default": 0.003, "disney_normal_mapped": 0.03, "disney_metallic_textured": 0.015, "disney_clearcoat_sheen": 0.03}
+    if "vs_ref_extras" in path:  # this scene textures its diffuse and metal surfaces (texture graph over 32^2 images, point / mirror / border addressing)
+        outlier_budget.update({"diffuse": 0.03, "metal": 0.03})
     for name, v in stats.items():
         if v["n"] < 200 or name in ("miss", "light"):
             continue
         assert v["flips"] <= flip_budget.get(name, flip_budget["default"]) * v["n"] + 2, (name, v)
         assert v["outliers"] <= outlier_budget.get(name, outlier_budget["default"]) * max(v["matched"], 1) + 2, (name, v)
         assert v["dir_out"] <= 0.004 * max(v["matched"], 1) + 2, (name, v)
-    assert sum(v["matched"] for v in stats.values()) > 20000
+    assert sum(v["matched"] for v in stats.values()) > 5000
 
 
 def test_byte_grid_medium_matches_oracle(tmp_path, built):
