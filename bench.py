@@ -577,7 +577,14 @@ def run_ours(args):
         for wl, k, spp in (("c1_cornell_512_16spp", 200, 0), ("c3_medium_1080p_128spp", 3, 0), ("c4_instanced_10m_1080p_128spp", 2, 0),
                            ("c5_disney_4k_1024spp", 2, 128)):
             try:
-                r = measure(args, D, wl, k, 3, spp_override=spp, e2e=False, cpu=False, scaling="weak")
+                # the medium workload peaks at a 16 Mi pool (profiles/r2j_sweep_pool.md: 747 vs 716 Msamples/s at 32 Mi)
+                pool = args.state_count
+                if wl == "c3_medium_1080p_128spp":
+                    args.state_count = min(pool, 16777216)
+                try:
+                    r = measure(args, D, wl, k, 3, spp_override=spp, e2e=False, cpu=False, scaling="weak")
+                finally:
+                    args.state_count = pool
                 extra[wl] = {"value": r["value"], "unit": "Msamples/s", "mrays_per_s": r["mrays_per_s"], "ms_per_step": r["ms_per_step"], "steps": k,
                              "spp_rendered_per_step": r["run"]["spp_rendered_per_step"], "clocks": r["clocks"],
                              "stages": {n: {"share_of_step": v["share_of_step"], "frac": v["frac"], "dram_frac": v.get("dram_frac"), "ms_per_launch": v["ms_per_launch"]}

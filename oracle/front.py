@@ -701,7 +701,10 @@ class OracleScene:
                 ch = 4
         data = np.ascontiguousarray(data, f32)
         h, w = data.shape[:2]
-        return self.L.orc_add_image(self.h, w, h, 0, ch, _ptr(data, c_float), int(bool(srgb)), au, av, aw, linear, _ptr(border, c_float))
+        img = self.L.orc_add_image(self.h, w, h, 0, ch, _ptr(data, c_float), int(bool(srgb)), au, av, aw, linear, _ptr(border, c_float))
+        if not filename.lower().endswith(".hdr"):
+            self.L.orc_set_image_border_levels(self.h, img, 255)   # UNorm8 storage: the border colour is held in the texel format
+        return img
 
     def add_texture(self, node: Node):
         key = ("tex2d", id(node.raw))
@@ -817,6 +820,7 @@ class OracleScene:
                 img = self.L.orc_add_image(self.h, w, h, d, 1 if ch == 1 else 4, _ptr(vals, c_float), 0, au, av, aw, linear, _ptr(border, c_float))
                 if minmax is not None:
                     self.L.orc_set_image_minmax(self.h, img, _ptr(minmax[0], c_float), _ptr(minmax[1], c_float))
+                    self.L.orc_set_image_border_levels(self.h, img, 127)   # SNorm8 storage
                 t = self.L.orc_add_texture3d_array(self.h, img)
             elif ty in ("add", "mul"):  # texture3d/binary.cpp:150-160 (lhs is created first)
                 lhs = self.add_texture3d(node.child("lhs"))

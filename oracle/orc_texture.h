@@ -26,6 +26,7 @@ struct TexImage {
     int addr[3] = {ADDR_CLAMP, ADDR_CLAMP, ADDR_CLAMP};
     bool linear = true;
     float border[4] = {0, 0, 0, 0};
+    int border_levels = 0;        // 255: UNorm8 storage, 127: SNorm8, 0: float texels (the border colour is used as given)
     float max_value[3] = {0, 0, 0}, min_value[3] = {0, 0, 0};  // Array::find_minmax_values
 };
 
@@ -61,8 +62,26 @@ inline float address_coord(float u, int n, int mode) {
     }
 }
 
+// Border colour as the texture unit returns it -- measured on B200 (scripts/diag_border.py, round 2): it is stored in the TEXEL
+// FORMAT, so for 8-bit textures it is quantised (0.1 -> 25/255, 0.25 -> 64/255, 0.3 -> 76/255, 0.5 -> 127/255, 0.7 -> 178/255: the fp32
+// product b * 255 rounded to nearest with ties DOWN, clamped to the format's range), and a one-channel texture has no second and
+// third component to put it in: (b, 0, 0, 1), like any of its texels.
+inline float border_component(const TexImage &t, int c) {
+    const float b = t.border[c];
+    if (t.border_levels == 0) return b;
+    const float lv = (float)t.border_levels;
+    float q = std::ceil(b * lv - 0.5f);
+    const float lo = t.border_levels == 127 ? -127.0f : 0.0f;
+    q = q < lo ? lo : (q > lv ? lv : q);
+    return q / lv;
+}
+
 inline void fetch_texel(const TexImage &t, int x, int y, int z, float out[4]) {
-    if (x < 0 || y < 0 || z < 0) { for (int c = 0; c < 4; ++c) out[c] = t.border[c]; return; }
+    if (x < 0 || y < 0 || z < 0) {
+        if (t.channels == 1) { out[0] = border_component(t, 0); out[1] = 0; out[2] = 0; out[3] = 1; }
+        else for (int c = 0; c < 4; ++c) out[c] = border_component(t, c);
+        return;
+    }
     const size_t idx = ((size_t)z * t.h + y) * t.w + x;
     if (t.channels == 1) { out[0] = t.data[idx]; out[1] = 0; out[2] = 0; out[3] = 1; }
     else for (int c = 0; c < 4; ++c) out[c] = t.data[4 * idx + c];

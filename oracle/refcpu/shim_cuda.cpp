@@ -150,6 +150,7 @@ cudaError_t cudaCreateTextureObject(cudaTextureObject_t *out, const cudaResource
     const size_t n = a->w * (a->h ? a->h : 1) * (a->d ? a->d : 1) * nch;
     t->data.resize(n);
     const int bits = a->desc.x;
+    t->border_levels = a->desc.f == cudaChannelFormatKindFloat ? 0 : (a->desc.f == cudaChannelFormatKindSigned ? 127 : 255);
     if (a->desc.f == cudaChannelFormatKindFloat && bits == 32) {
         memcpy(t->data.data(), a->bytes.data(), n * 4);
     } else if (bits == 8 && td->readMode == cudaReadModeNormalizedFloat && a->desc.f == cudaChannelFormatKindUnsigned) {

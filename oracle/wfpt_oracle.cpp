@@ -1462,6 +1462,9 @@ void orc_set_image_minmax(orc_scene *s, int image, const float *min3, const floa
     for (int c = 0; c < 3; ++c) { s->tex.images[image].min_value[c] = min3[c]; s->tex.images[image].max_value[c] = max3[c]; }
 }
 
+// storage format of the image's texels as far as the texture unit's border colour is concerned (orc_texture.h border_component)
+void orc_set_image_border_levels(orc_scene *s, int image, int levels) { s->tex.images[image].border_levels = levels; }
+
 int orc_add_texture_array(orc_scene *s, int image) {
     Texture2D t; t.type = TEX_ARRAY; t.image = image;
     s->tex.tex2d.push_back(t);
