@@ -141,7 +141,7 @@ def test_shade_against_reference_per_material(trio):
     flip_budget = {"default": 0.001}
     outlier_budget = {"default": 0.003, "disney_normal_mapped": 0.03, "disney_metallic_textured": 0.015, "disney_clearcoat_sheen": 0.03}
     if "vs_ref_extras" in path:  # this scene textures its diffuse and metal surfaces (texture graph over 32^2 images, point / mirror / border addressing)
-        outlier_budget.update({"diffuse": 0.03, "metal": 0.03})
+        outlier_budget.update({"diffuse": 0.01, "metal": 0.01})   # measured 0.29 % / 0.45 %
     for name, v in stats.items():
         if v["n"] < 200 or name in ("miss", "light"):
             continue
