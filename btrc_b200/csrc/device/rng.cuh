@@ -14,6 +14,11 @@ namespace btrc {
 constexpr uint64_t kPcgDefaultState = 0x853c49e6748fea9bULL;
 constexpr uint64_t kPcgMult = 0x5851f42d4c957f2dULL;
 
+// LCG skip-ahead constants for 2^j steps at once: the step map is x -> M x + c; 2^j steps are x -> M^(2^j) x + c S_j with
+// S_0 = 1, S_(j+1) = (M^(2^j) + 1) S_j (all mod 2^64) -- what the loop of Pcg::advance reaches after j halvings of delta
+constexpr uint64_t pcg_mult_pow2(int j) { uint64_t m = 0x5851f42d4c957f2dULL; for (int i = 0; i < j; ++i) m *= m; return m; }
+constexpr uint64_t pcg_plus_sum2(int j) { uint64_t m = 0x5851f42d4c957f2dULL, s = 1; for (int i = 0; i < j; ++i) { s = (m + 1) * s; m *= m; } return s; }
+
 struct Pcg {
     uint64_t state, inc;
 
@@ -41,6 +46,23 @@ struct Pcg {
             cur_plus = (cur_mult + 1) * cur_plus;
             cur_mult *= cur_mult;
             delta >>= 1;
+        }
+        state = acc_mult * state + acc_plus;
+    }
+    // advance(blocks << 16): the first 16 rounds of the loop above see zero bits only and square the step map; they are folded
+    // into compile-time constants, the remaining rounds are the same arithmetic -- the resulting state is bit-identical
+    // (independent.cpp:11-15 advances by sample_index * 65536; a 256-spp render then loops 8 times instead of 24)
+    __device__ __forceinline__ void advance_blocks_of_65536(uint64_t blocks) {
+        constexpr uint64_t kM16 = pcg_mult_pow2(16), kS16 = pcg_plus_sum2(16);
+        uint64_t cur_mult = kM16, cur_plus = kS16 * inc, acc_mult = 1, acc_plus = 0;
+        while (blocks > 0) {
+            if (blocks & 1) {
+                acc_mult *= cur_mult;
+                acc_plus = acc_plus * cur_mult + cur_plus;
+            }
+            cur_plus = (cur_mult + 1) * cur_plus;
+            cur_mult *= cur_mult;
+            blocks >>= 1;
         }
         state = acc_mult * state + acc_plus;
     }
@@ -131,7 +153,9 @@ struct SamplerT<false> {
     Pcg rng;
     __device__ __forceinline__ void init(const HaltonConsts &, uint32_t px, uint32_t py, int sample_index) {
         rng.seed(murmur_pixel(px, py));
-        rng.advance(uint64_t(int64_t(sample_index)) * 65536ull);
+        // advance(sample_index * 65536); a negative index (never generated) would wrap like the reference's i64 product
+        if (sample_index >= 0 && sample_index < (1 << 30)) rng.advance_blocks_of_65536(uint64_t(sample_index));
+        else rng.advance(uint64_t(int64_t(sample_index)) * 65536ull);
     }
     __device__ __forceinline__ void load(ulonglong2 v, const HaltonConsts &) { rng.state = v.x; rng.inc = v.y; }
     __device__ __forceinline__ ulonglong2 store() const { return make_ulonglong2(rng.state, rng.inc); }

@@ -19,27 +19,24 @@ prof() {  # workload, short name, kernel regex (mangled base), stage key, skip, 
 }
 C2=c2_disney_1080p_256spp; C3=c3_medium_1080p_128spp; C4=c4_instanced_10m_1080p_128spp; C1=c1_cornell_512_16spp
 # launch list of one C2 step (every kernel, in order)
-SPP=8 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_c2_$TAG.csv \
+SPP=8 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_c2_$TAG.csv \
     python bench.py --workload $C2 --steps 1 --warmup 3 --spp 8 --no-cpu-baseline --no-workloads > gpurun_out/ncu_launch_c2_$TAG.log 2>&1
-# C2 at 32 spp (4 full waves of 8 Mi states before the tail): launches 12.. are steady-state waves of mixed depth
-SPP=32 prof $C2 c2_trace trace_kernel trace 12 4
-SPP=32 prof $C2 c2_shade shade_kernelILi2E shade 12 4
-SPP=32 prof $C2 c2_shadow shadow_kernel shadow 12 4
-SPP=32 prof $C2 c2_generate generate_kernel generate 3 3
-SPP=32 prof $C2 c2_toplevels top_levels_probe "" 12 3 BTRC_PROBE_TOP_LEVELS=8
-SPP=32 prof $C2 c2_toplevels12 top_levels_probe "" 12 3 BTRC_PROBE_TOP_LEVELS=12
+# Launch k of a stage kernel = wave k of the first (warm-up) render: with a 32 Mi pool wave 0 is all camera rays, waves 1-3 are full
+# pools of mixed depth (the steady state of a long render); the tail waves after them are nearly empty.
+SPP=64 prof $C2 c2_trace trace_kernel trace 1 3
+SPP=64 prof $C2 c2_shade shade_kernelILi2E shade 1 3
+SPP=64 prof $C2 c2_shadow shadow_kernel shadow 1 3
+SPP=64 prof $C2 c2_generate generate_kernel generate 0 2
+SPP=64 prof $C2 c2_toplevels top_levels_probe "" 1 2 BTRC_PROBE_TOP_LEVELS=8
+SPP=64 prof $C2 c2_toplevels12 top_levels_probe "" 1 2 BTRC_PROBE_TOP_LEVELS=12
 # C3: the medium kernel and its neighbours
-SPP=32 prof $C3 c3_medium medium_kernel medium 12 4
-SPP=32 prof $C3 c3_shade shade_kernelILi0E shade 12 3 SHADE_CLASS=1
-SPP=32 prof $C3 c3_shadow shadow_kernel shadow 12 3
-SPP=32 prof $C3 c3_trace trace_kernel trace 12 3
+SPP=64 prof $C3 c3_medium medium_kernel medium 1 3
+SPP=64 prof $C3 c3_shade shade_kernelILi0E shade 1 3 SHADE_CLASS=1
+SPP=64 prof $C3 c3_shadow shadow_kernel shadow 1 3
+SPP=64 prof $C3 c3_trace trace_kernel trace 1 3
 # C4: BVH larger than the L2
-SPP=16 prof $C4 c4_trace trace_kernel trace 6 3
-SPP=16 prof $C4 c4_shadow shadow_kernel shadow 6 3
-SPP=16 prof $C4 c4_toplevels top_levels_probe "" 6 2 BTRC_PROBE_TOP_LEVELS=8
-SPP=16 prof $C4 c4_toplevels16 top_levels_probe "" 6 2 BTRC_PROBE_TOP_LEVELS=16
-# C1
-SPP=16 prof $C1 c1_trace trace_kernel trace 4 3
-SPP=16 prof $C1 c1_shade shade_kernelILi0E shade 4 3 SHADE_CLASS=1
-SPP=16 prof $C1 c1_shadow shadow_kernel shadow 4 3
+SPP=32 prof $C4 c4_trace trace_kernel trace 1 3
+SPP=32 prof $C4 c4_shadow shadow_kernel shadow 1 3
+SPP=32 prof $C4 c4_toplevels top_levels_probe "" 1 2 BTRC_PROBE_TOP_LEVELS=8
+SPP=32 prof $C4 c4_toplevels16 top_levels_probe "" 1 2 BTRC_PROBE_TOP_LEVELS=16
 ls gpurun_out/*.json | head -20; du -sh gpurun_out
