@@ -105,3 +105,15 @@ def test_two_rank_render_equals_single_process(tmp_path, built):
     got = np.load(out)
     ref = front.OracleScene(path).render()["color"]
     assert np.allclose(got, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_single_rank_comm_needs_no_nccl(built):
+    """btrc_comm_create with one rank builds no communicator (a 1-GPU host needs no NCCL); bad ranks are refused."""
+    from btrc_b200 import api
+
+    c = api.Comm(1, 0, None)
+    c.close()
+    with pytest.raises(api.BtrcError):
+        api.Comm(2, 5, bytes(128))
+    with pytest.raises(api.BtrcError):
+        api.Comm(2, 0, None)
