@@ -487,8 +487,12 @@ __device__ __forceinline__ void flush_splat_count(WaveCtl *ctl, unsigned long lo
 // ---------------------------------------------------------------------------------------------------------------
 // medium (medium.cpp:36-164, 214-249): only launched when the scene has media (wavefront.cpp:254-268)
 // ---------------------------------------------------------------------------------------------------------------
+// CTAs per SM the medium kernel is compiled for (A/B: profiles/r2o_ab_medium_occupancy.md)
+#ifndef BTRC_MEDIUM_MIN_BLOCKS
+#define BTRC_MEDIUM_MIN_BLOCKS 2
+#endif
 template <bool HALTON, bool T3P>
-__global__ void __launch_bounds__(kBlock) medium_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQueue nq, ShadowQueue sq,
+__global__ void __launch_bounds__(kBlock, BTRC_MEDIUM_MIN_BLOCKS) medium_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQueue nq, ShadowQueue sq,
                                                        FilmDevice film, WaveCtl *ctl) {
     const int n = ctl->n_active;
     const int n_round = (n + 31) & ~31;
