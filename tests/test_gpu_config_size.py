@@ -244,3 +244,46 @@ def test_c5_4k_two_rank_partitions(tmp_path, built):
     # tile-mode and uniform-mode indexing enumerate the same (pixel, sample) pairs: same image up to addition order
     assert np.abs(tfull - full).max() <= 1e-5 * max(1.0, float(full.max()))
     t.close()
+
+
+@pytest.mark.parametrize("tile", [False, True])
+def test_partitions_with_ragged_edges(tmp_path, built, tile):
+    """The closed-form film weights and the partitions on sizes that divide nothing: an image whose height is no multiple of the strip
+    height split over 3 parts (tile mode), sample ranges over 3 parts of 7 spp (uniform mode), and arbitrary index ranges that cut
+    through sample planes / pixels -- parts sum to the whole render, weights exactly."""
+    import torch
+
+    from btrc_b200 import api, scenes
+
+    W, H, spp = 150, 77, 7
+    path = scenes.make_cornell(str(tmp_path), width=W, height=H, spp=spp, state_count=30000)
+    if tile:
+        root = json.load(open(path)); root["renderer"]["tile"] = True; json.dump(root, open(path, "w"))
+    s = api.Scene(path)
+    full, wfull, _ = _raw_film(s)
+    assert (wfull == spp).all()
+
+    def film_of(call):
+        s.film_clear()
+        call()
+        rad = torch.zeros(H, W, 4, device="cuda"); wgt = torch.zeros(H, W, device="cuda")
+        s.film_export(rad, wgt)
+        return rad.cpu().numpy().reshape(-1, 4)[:, :3], wgt.cpu().numpy().reshape(-1)
+
+    tol = 1e-5 * max(1.0, float(full.max()))
+    for rows in (0, 5):
+        acc, wacc = np.zeros_like(full), np.zeros_like(wfull)
+        for part in range(3):
+            rad, wgt = film_of(lambda: s.render_part(3, part, rows))
+            if tile:
+                assert set(np.unique(wgt)) <= {0.0, float(spp)}            # a part owns whole pixels
+            acc += rad; wacc += wgt
+        assert np.array_equal(wacc, wfull) and np.abs(acc - full).max() <= tol
+    total = W * H * spp
+    cuts = [0, 12345, total // 2 + 3, total - 1, total]
+    acc, wacc = np.zeros_like(full), np.zeros_like(wfull)
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        rad, wgt = film_of(lambda: s.render_range(b, e))
+        acc += rad; wacc += wgt
+    assert np.array_equal(wacc, wfull) and np.abs(acc - full).max() <= tol
+    s.close()
