@@ -56,6 +56,15 @@ def make_scene(workload, out_dir, spp=None, tile=False):
     return path
 
 
+def _partition_text(tiles, world, W, H):
+    from btrc_b200 import partition as P
+    if not tiles:
+        return "sample-index ranges per rank"
+    rows = P.strip_rows(world, H)
+    shape = "%d x %d pixel tiles" % (P.tile_width(world, W), rows) if P.tiles_are_2d(world, W, H, rows) else "strips of %d pixel rows" % rows
+    return "image tiles: " + shape + " dealt round-robin to the ranks (tile-mode indexing)"
+
+
 def workload_config(workload):
     """The `config` object both arms print (same keys, so the driver can tell they ran the same workload)."""
     w = WORKLOADS[workload]
@@ -535,8 +544,7 @@ def measure(args, D, workload, steps, warmup, spp_override=0, e2e=True, cpu=True
     cfg = workload_config(workload)   # identical in both arms; how this arm ran it goes to "run"
     run = {}
     run.update({"spp_rendered_per_step": spp_scene, "gpus": world, "state_count": s.info.state_count, "bvh_layout": "instanced" if s.info.bvh_instanced else "flat",
-                "partition": (("image tiles: strips of %d pixel rows dealt round-robin to the ranks (tile-mode indexing)" % __import__("btrc_b200.partition", fromlist=["x"]).strip_rows(world, H)
-                               if tiles else "sample-index ranges per rank") +
+                "partition": (_partition_text(tiles, world, W, H) +
                               "; ncclReduce(sum) of the radiance+weight films onto rank 0 inside the library (btrc_reduce_films), resolve on rank 0") if world > 1 else "single GPU",
                 "timing": "CUDA events on the renderer's stream per step, max over ranks; 256 MB L2 flush (untimed) between steps; "
                           "roofline_stages from a separate pass of %d identical steps with one CUDA event between kernels (%.1f ms/step)" % (prof_steps, prof_ms / prof_steps),
@@ -635,7 +643,7 @@ def main():
                     help="path-state pool (the renderer's `state_count` parameter); 32 Mi states = 9.4 GB of queues.  C2 with the block-coherent "
                          "generation order: 1192 / 1242 / 1273 Msamples/s at 8 / 16 / 32 Mi (profiles/r2j_sweep_pool.md)")
     ap.add_argument("--partition", default="auto", choices=["auto", "samples", "tiles"],
-                    help="multi-GPU split: sample-index ranges or image tiles (interleaved strips of pixel rows); auto = tiles for the "
+                    help="multi-GPU split: sample-index ranges or image tiles (64-pixel-wide tiles or strips of pixel rows, dealt round-robin); auto = tiles for the "
                          "strong-scaling configuration (BASELINE config 5's wording), samples otherwise")
     ap.add_argument("--spp", type=int, default=0, help="override the workload's samples per pixel (profiling runs); reported in config")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (roofline bvh statistics, cpu_baseline): profiler runs")

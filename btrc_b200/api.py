@@ -251,7 +251,7 @@ class Scene:
         _img(albedo, "film albedo", 4 * npix); _img(normal, "film normal", 4 * npix)
 
     def render_part(self, n_parts, part, rows_per_strip=0):
-        """This device's share of the render (sample ranges, or interleaved row strips when the renderer is in tile mode)."""
+        """This device's share of the render (sample ranges, or interleaved image tiles when the renderer is in tile mode: partition.tile_owner)."""
         st = RenderStats()
         _check(self.L.btrc_render_part(self.h, int(n_parts), int(part), int(rows_per_strip), byref(st)))
         return st.as_dict()

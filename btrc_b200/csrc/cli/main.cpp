@@ -4,7 +4,7 @@
 //
 // `btrc --ranks N <config.json>` renders the same scene on N GPUs of this box (new work: the reference is single-GPU,
 // main.cpp:23): the driver starts one process per GPU (`--rank r`, internal), every rank loads the scene, renders its share
-// (btrc_render_part: sample ranges, or interleaved image strips when the renderer has "tile": true), the films are summed onto
+// (btrc_render_part: sample ranges, or interleaved image tiles when the renderer has "tile": true), the films are summed onto
 // rank 0 with one ncclReduce over NVLink (btrc_reduce_films) and rank 0 resolves and runs the post-processors.
 #include <chrono>
 #include <cstdio>

@@ -297,6 +297,10 @@ struct WaveCtl {
     // + v % stride_block.  stride_block == 0: identity (one contiguous range).
     long long stride_block;
     int stride_parts, stride_part;
+    // 2-D form of the same partition: stride_bw > 0 makes a block a TILE of stride_bw x stride_rows pixels (both divide the image,
+    // stride_block = their pixels * spp); tiles are numbered row-major over the tile grid and dealt round-robin, and inside a tile
+    // pixels run row-major with all samples of a pixel consecutively.  stride_bw == 0: a block is a contiguous index range (strip).
+    int stride_bw, stride_rows;
     int weight_prefilled;  // the film's weight plane was filled in closed form for this render: generate skips its atomic
     // Generation ORDER (not a partition): when the range is whole sample planes [order_s0, order_s0 + order_ns) of every pixel in
     // Uniform indexing, the walk visits them pixel block by pixel block (order_bw x order_bh pixels, all samples of a pixel
@@ -305,7 +309,8 @@ struct WaveCtl {
     // and the 32 rays of a warp -- start in one image region.  order_ns == 0: queue order = index order.
     int order_s0, order_ns;
     int order_bw, order_bh;   // pixel block of the generation order
-    int order_sample_major;   // inside a block: 0 = all samples of a pixel consecutively, 1 = all pixels of the block sample by sample
+    int order_sample_major;   // inside a block: 0 = all samples of a pixel consecutively, 1 = all pixels of the block sample by sample,
+                              // 2 = 32 samples of a pixel (one warp), next pixel, ..., then the next 32 samples (needs order_ns % 32 == 0)
     // statistics (SURVEY 8d event counts)
     unsigned long long n_gen, n_closest, n_hit, n_next_total, n_shadow_total, n_shadow_miss, n_splat, n_iter;
 };

@@ -147,13 +147,27 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(SceneDevice scene, Ren
     const int base_slot = ctl->n_survivors;
     const long long gen_base = ctl->gen_base;
     const long long sblock = ctl->stride_block;
-    const int sparts = ctl->stride_parts, spart = ctl->stride_part;
+    const int sparts = ctl->stride_parts, spart = ctl->stride_part, sbw = ctl->stride_bw, srows = ctl->stride_rows;
     const bool splat_weight = ctl->weight_prefilled == 0;
     const int order_ns = ctl->order_ns, order_s0 = ctl->order_s0, osm = ctl->order_sample_major;
     const long long obw = ctl->order_bw, obh = ctl->order_bh;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) {
         long long accu = gen_base + i;
-        if (sblock > 0) accu = ((accu / sblock) * sparts + spart) * sblock + accu % sblock;
+        if (sblock > 0 && sbw > 0) {  // 2-D tiles of the tile-mode index space (types.h WaveCtl::stride_bw)
+            const long long blk = (accu / sblock) * sparts + spart, within = accu % sblock;
+            long long q, smp;
+            if (P.spp % 32 == 0) {  // 32 samples of a pixel (one warp), then the next pixel of the tile, ... then the next 32 samples
+                const long long per_chunk = (long long)sbw * srows * 32, chunk = within / per_chunk, rem = within - chunk * per_chunk;
+                q = rem >> 5; smp = chunk * 32 + (rem & 31);
+            } else {
+                q = within / P.spp; smp = within - q * P.spp;
+            }
+            const long long tiles_x = P.width / sbw;
+            const long long y = (blk / tiles_x) * srows + q / sbw, x = (blk % tiles_x) * sbw + q % sbw;
+            accu = (y * P.width + x) * P.spp + smp;
+        } else if (sblock > 0) {
+            accu = ((accu / sblock) * sparts + spart) * sblock + accu % sblock;
+        }
         if (order_ns > 0) {  // block-coherent order over whole sample planes (types.h WaveCtl::order_ns): virtual -> (pixel, sample)
             const long long W = P.width, H = P.height;
             const long long per_block_row = W * obh * order_ns;
@@ -165,6 +179,15 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(SceneDevice scene, Ren
             if (!osm) {    // all samples of a pixel consecutively
                 q = in_row / order_ns;
                 sample = order_s0 + int(in_row - q * order_ns);
+            } else if (osm == 2) {  // block by block; inside a block 32 samples of a pixel (one warp), then the next pixel, ... then the next 32 samples
+                const long long full = obw * hr * order_ns;
+                const long long bc0 = in_row / full;
+                const long long wc0 = (bc0 + 1) * obw <= W ? obw : W - bc0 * obw;
+                const long long in_block = in_row - bc0 * full;
+                const long long npb = wc0 * hr;
+                const long long chunk = in_block / (npb * 32), rem = in_block - chunk * npb * 32;
+                sample = order_s0 + int(chunk * 32 + (rem & 31));
+                q = bc0 * obw * hr + (rem >> 5);
             } else {       // block by block, inside a block sample plane by sample plane
                 const long long full = obw * hr * order_ns;                  // paths of a full-width block of this row
                 const long long bc0 = in_row / full;
@@ -198,7 +221,7 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(SceneDevice scene, Ren
 // Weight plane of a render over the (virtual, see WaveCtl) path index range [begin, end): adds to every pixel the number of
 // camera paths of that range that start in it -- the sum of generate.cpp:79's splats of 1.0f, exact in fp32 below 2^24.
 __global__ void __launch_bounds__(kBlock) weight_fill_kernel(float *weight, int npix, int spp, int tile, long long begin, long long end,
-                                                             long long sblock, int sparts, int spart) {
+                                                             long long sblock, int sparts, int spart, int sbw, int srows, int width) {
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
         long long count = 0;
         if (sblock <= 0) {
@@ -214,8 +237,13 @@ __global__ void __launch_bounds__(kBlock) weight_fill_kernel(float *weight, int 
         } else {
             // strided partitions are made of whole pixels in tile mode (stride_block is a multiple of spp): pixel p is ours when
             // its block belongs to this part and its virtual index lies inside [begin, end)
-            const long long a = (long long)p * spp;
-            const long long blk = a / sblock;
+            long long a = (long long)p * spp;
+            long long blk = a / sblock;
+            if (sbw > 0) {  // 2-D tiles: tile of the pixel and the pixel's ordinal inside it
+                const long long x = p % width, y = p / width;
+                blk = (y / srows) * (width / sbw) + x / sbw;
+                a = blk * sblock + ((y % srows) * sbw + x % sbw) * (long long)spp;
+            }
             if (blk % sparts == spart) {
                 const long long v = (blk / sparts) * sblock + a % sblock;
                 const long long lo = v > begin ? v : begin, hi = v + spp < end ? v + spp : end;
@@ -856,9 +884,9 @@ void launch_generate(const LaunchCfg &cfg, const SceneDevice &scene, const Rende
 }
 
 void launch_weight_fill(const LaunchCfg &cfg, const RenderParams &params, FilmDevice film, long long begin, long long end, long long stride_block,
-                        int stride_parts, int stride_part, cudaStream_t stream) {
+                        int stride_parts, int stride_part, int stride_bw, int stride_rows, cudaStream_t stream) {
     weight_fill_kernel<<<persistent_blocks(cfg, 8), kBlock, 0, stream>>>(film.weight, params.width * params.height, params.spp, params.tile ? 1 : 0,
-                                                                         begin, end, stride_block, stride_parts, stride_part);
+                                                                         begin, end, stride_block, stride_parts, stride_part, stride_bw, stride_rows, params.width);
 }
 
 // counting sort of `count` keys into rs.order; *n_sorted_out (a WaveCtl field) is set to the count by the scatter kernel

@@ -32,7 +32,7 @@ void launch_prepare(WaveCtl *ctl, cudaStream_t stream);
 void launch_generate(const LaunchCfg &cfg, const SceneDevice &scene, const RenderParams &params, PathQueue cur, FilmDevice film,
                      WaveCtl *ctl, cudaStream_t stream);
 void launch_weight_fill(const LaunchCfg &cfg, const RenderParams &params, FilmDevice film, long long begin, long long end, long long stride_block,
-                        int stride_parts, int stride_part, cudaStream_t stream);
+                        int stride_parts, int stride_part, int stride_bw, int stride_rows, cudaStream_t stream);
 void launch_ray_sort(const LaunchCfg &cfg, const SceneDevice &scene, const float4 *ray_o, const float4 *ray_d, uint32_t *key, const int *count, RaySort rs,
                      int *n_sorted_out, cudaStream_t stream);
 void launch_trace(const LaunchCfg &cfg, const SceneDevice &scene, PathQueue cur, HitQueue hit, RaySort rs, WaveCtl *ctl, cudaStream_t stream);

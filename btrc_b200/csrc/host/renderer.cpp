@@ -121,10 +121,32 @@ void Renderer::render_part(int parts, int part, int rows_per_strip) {
         render_range(b * W * H, e * W * H);
         return;
     }
-    // image tiles (partition B): strips of `rows` image rows dealt round-robin, so that cheap and expensive image regions
-    // are spread over all devices; tile-mode indexing makes a strip one contiguous block of the index space
-    if (rows_per_strip <= 0) rows_per_strip = (int)std::max<long long>(1, std::min<long long>(16, H / (8LL * parts)));
+    // image tiles (partition B), dealt round-robin so that cheap and expensive image regions are spread over all devices.  When the
+    // image divides into 64 (128, 256, 32) x rows tiles the split is 2-D (compact tiles: the rays of a wave start in one image region, like the
+    // generation order of uniform-mode renders); otherwise strips of `rows` whole image rows, which tile-mode indexing makes
+    // contiguous blocks of the index space.  rows: at most 16, at least 8 strips per device, a divisor of the height if one is near.
+    if (rows_per_strip <= 0) {
+        rows_per_strip = (int)std::max<long long>(1, std::min<long long>(16, H / (8LL * parts)));
+        for (int r = rows_per_strip; r >= std::max(1, rows_per_strip / 2); --r)
+            if (H % r == 0) { rows_per_strip = r; break; }
+    }
     const long long rows = rows_per_strip;
+    // tile width: 64 pixels, or the first of 128 / 256 / 32 that makes the number of tiles per row coprime to the number of parts --
+    // then "tile k belongs to part k % parts" walks diagonally over the image instead of giving every part fixed columns
+    long long kTileW = 64;
+    {
+        auto gcd = [](long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; };
+        for (long long tw : {64LL, 128LL, 256LL, 32LL})
+            if (W % tw == 0 && gcd(W / tw, parts) == 1) { kTileW = tw; break; }
+        if (const char *e = std::getenv("BTRC_TILE_W")) if (std::atoi(e) > 0) kTileW = std::atoi(e);
+    }
+    static const bool tiles_2d = !(std::getenv("BTRC_TILES_2D") && std::atoi(std::getenv("BTRC_TILES_2D")) == 0);
+    if (tiles_2d && W % kTileW == 0 && H % rows == 0) {
+        const long long block = kTileW * rows * spp, tiles = (W / kTileW) * (H / rows);
+        const long long owned = part < tiles ? (tiles - 1 - part) / parts + 1 : 0;
+        render_range(0, owned * block, block, parts, part, (int)kTileW, (int)rows);
+        return;
+    }
     const long long block = rows * W * spp, total = W * H * spp;
     const long long strips = (H + rows - 1) / rows;
     const long long owned = part < strips ? (strips - 1 - part) / parts + 1 : 0;
@@ -135,7 +157,10 @@ void Renderer::render_part(int parts, int part, int rows_per_strip) {
     render_range(0, n_virtual, block, parts, part);
 }
 
-void Renderer::render_range(long long begin, long long end, long long stride_block, int stride_parts, int stride_part) {
+void Renderer::render_range(long long begin, long long end, long long stride_block, int stride_parts, int stride_part, int stride_bw, int stride_rows) {
+    if (stride_bw > 0 && (stride_rows <= 0 || scene_.width % stride_bw || scene_.height % stride_rows ||
+                          stride_block != (long long)stride_bw * stride_rows * scene_.renderer.spp))
+        throw Error("render_range: 2-D tiles must divide the image");
     if (stride_block < 0 || stride_parts < 1 || stride_part < 0 || stride_part >= stride_parts) throw Error("render_range: bad stride");
     if (stride_block > 0 && (!scene_.renderer.tile || stride_block % scene_.renderer.spp != 0))
         throw Error("render_range: a strided partition needs tile-mode indexing and whole pixels per block");
@@ -151,6 +176,8 @@ void Renderer::render_range(long long begin, long long end, long long stride_blo
     init.stride_block = stride_block;
     init.stride_parts = stride_parts;
     init.stride_part = stride_part;
+    init.stride_bw = stride_bw;
+    init.stride_rows = stride_rows;
     init.weight_prefilled = 1;
     {   // block-coherent generation order for ranges made of whole sample planes (types.h WaveCtl::order_ns); BTRC_GEN_ORDER=0 turns it off
         static const bool coherent = !(std::getenv("BTRC_GEN_ORDER") && std::atoi(std::getenv("BTRC_GEN_ORDER")) == 0);
@@ -158,11 +185,17 @@ void Renderer::render_range(long long begin, long long end, long long stride_blo
         if (coherent && !scene_.renderer.tile && stride_block == 0 && end > begin && begin % npix == 0 && end % npix == 0) {
             init.order_s0 = (int)(begin / npix);
             init.order_ns = (int)((end - begin) / npix);
-            init.order_bw = 64; init.order_bh = 32; init.order_sample_major = 0;  // profiles/r2i_sweep_gen_order.md
-            if (const char *e = std::getenv("BTRC_GEN_BLOCK")) {  // tuning: "<width>x<height>[s]" (s: sample-major inside a block)
+            // profiles/r2i_sweep_gen_order.md, r2r_ab_chunked_order.md: 64 x 32 blocks with all samples of a pixel in a row; when the
+            // sample count is a multiple of the warp size, 32 x 32 blocks walked warp by warp (32 samples of a pixel, next pixel, ...)
+            init.order_bw = 64; init.order_bh = 32; init.order_sample_major = 0;
+            if (init.order_ns % 32 == 0) { init.order_bw = 32; init.order_sample_major = 2; }
+            if (const char *e = std::getenv("BTRC_GEN_BLOCK")) {  // tuning: "<width>x<height>[s|c]" (s: sample planes inside a block, c: 32-sample chunks)
                 int bw = 0, bh = 0;
                 char mode = 0;
-                if (std::sscanf(e, "%dx%d%c", &bw, &bh, &mode) >= 2 && bw > 0 && bh > 0) { init.order_bw = bw; init.order_bh = bh; init.order_sample_major = mode == 's'; }
+                if (std::sscanf(e, "%dx%d%c", &bw, &bh, &mode) >= 2 && bw > 0 && bh > 0) {
+                    init.order_bw = bw; init.order_bh = bh;
+                    init.order_sample_major = mode == 's' ? 1 : (mode == 'c' && init.order_ns % 32 == 0) ? 2 : 0;  // c: 32-sample chunks
+                }
             }
             init.cursor = 0;
             init.end = end - begin;
@@ -171,7 +204,7 @@ void Renderer::render_range(long long begin, long long end, long long stride_blo
     ctl_host_[8] = init;  // pinned staging slot: the upload is a true async copy on the renderer's stream
     BTRC_CUDA(cudaMemcpyAsync(ctl_, &ctl_host_[8], sizeof(init), cudaMemcpyHostToDevice, stream_));
     BTRC_CUDA(cudaEventRecord(ev_begin_, stream_));
-    launch_weight_fill(cfg_, params, film_, begin, end, stride_block, stride_parts, stride_part, stream_);
+    launch_weight_fill(cfg_, params, film_, begin, end, stride_block, stride_parts, stride_part, stride_bw, stride_rows, stream_);
 
     const bool has_medium = scene_.dev.has_medium != 0;
     const int kernels_per_iter = has_medium ? 5 : 4;  // prepare, generate, trace, [medium], shadow; shade adds its own count

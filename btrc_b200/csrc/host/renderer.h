@@ -38,7 +38,7 @@ public:
     // Tile mode: index = pixel * spp + sample) and accumulates them into the film.
     // renders camera paths [begin, end) of the path index space; with stride_block > 0 the range is VIRTUAL (types.h WaveCtl:
     // interleaved blocks of `stride_block` paths, this renderer taking block `stride_part` of every `stride_parts`)
-    void render_range(long long begin, long long end, long long stride_block = 0, int stride_parts = 1, int stride_part = 0);
+    void render_range(long long begin, long long end, long long stride_block = 0, int stride_parts = 1, int stride_part = 0, int stride_bw = 0, int stride_rows = 0);
     // this renderer's share of the whole render when `parts` devices split it (partition chosen by the renderer's "tile" flag:
     // sample-index ranges, or interleaved strips of `rows_per_strip` image rows)
     void render_part(int parts, int part, int rows_per_strip);

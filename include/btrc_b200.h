@@ -99,8 +99,9 @@ int btrc_film_clear(btrc_scene_t *scene);
 int btrc_render_range(btrc_scene_t *scene, int64_t path_begin, int64_t path_end, btrc_render_stats_t *stats);
 /* This device's share of the render when n_parts devices split it (the reference is single-GPU, cli/main.cpp:23).
  * The partition follows the renderer's "tile" flag: sample-index ranges of every pixel ("tile": false, generate.cpp:49-55), or
- * image tiles -- strips of rows_per_strip pixel rows dealt round-robin to the parts ("tile": true, the pixel-major index space of
- * generate.cpp:56-60; rows_per_strip <= 0 picks a default).  Adds to this device's film like btrc_render_range. */
+ * image tiles dealt round-robin to the parts ("tile": true, the pixel-major index space of generate.cpp:56-60): tiles of
+ * 64 x rows_per_strip pixels when they divide the image, strips of rows_per_strip whole pixel rows otherwise; rows_per_strip <= 0
+ * picks a default (at most 16).  Adds to this device's film like btrc_render_range. */
 int btrc_render_part(btrc_scene_t *scene, int32_t n_parts, int32_t part, int32_t rows_per_strip, btrc_render_stats_t *stats);
 /* The path's one collective: ncclReduce(sum) of the film planes (radiance, weight [, albedo, normal]) onto rank `root`, in
  * place, on the renderer's stream -- btrc_resolve on the root then follows in stream order.  btrc_nccl_unique_id fills the 128

@@ -185,7 +185,7 @@ def test_c4_instanced_10m_full_geometry(tmp_path, built):
 
 
 def test_c5_4k_two_rank_partitions(tmp_path, built):
-    """configs[4] at 3840 x 2160: the film of a 2-rank SAMPLE split and of a 2-rank TILE split (interleaved strips) each sums to
+    """configs[4] at 3840 x 2160: the film of a 2-rank SAMPLE split and of a 2-rank TILE split (interleaved 256 x 16 tiles) each sums to
     the single render (what the NCCL reduce computes), and the single render matches the oracle on a pixel subset; 2 spp."""
     from btrc_b200 import api, partition, scenes
     from oracle import front
@@ -208,7 +208,7 @@ def test_c5_4k_two_rank_partitions(tmp_path, built):
                     budget={"default": 0.025})  # measured: at most 1.1 % in any bucket
     s.close()
 
-    # tile split: tile-mode indexing (generate.cpp:56-60), every rank renders all samples of its strips of pixel rows
+    # tile split: tile-mode indexing (generate.cpp:56-60), every rank renders all samples of its tiles
     tpath = scenes.make_material_test(str(tmp_path / "tiles"), width=W, height=H, spp=spp, state_count=8388608)
     root = json.load(open(tpath)); root["renderer"]["tile"] = True; json.dump(root, open(tpath, "w"))
     t = api.Scene(tpath)
@@ -223,22 +223,16 @@ def test_c5_4k_two_rank_partitions(tmp_path, built):
         return rad.cpu().numpy().reshape(-1, 4)[:, :3], wgt.cpu().numpy().reshape(-1)
 
     acc, wacc = np.zeros_like(tfull), np.zeros_like(twfull)
-    covered = np.zeros(npix, np.int32)
+    owner = partition.tile_owner(2, W, H).reshape(-1)  # 256 x 16 tiles at this geometry (15 per row), tile k of the row-major tile order -> rank k % 2
+    assert partition.tiles_are_2d(2, W, H, partition.strip_rows(2, H)) and partition.tile_width(2, W) == 256
+    tol = 1e-5 * max(1.0, float(tfull.max()))
     for r in range(2):
-        mine, wmine = np.zeros_like(tfull), np.zeros_like(twfull)
-        for k, (begin, end) in enumerate(partition.tile_path_ranges(r, 2, spp, W, H)):
-            covered[begin // spp:end // spp] += 1
-            if k % 16 == 0:                          # every 16th strip through the plain range call: the strided call must agree on it
-                rad, wgt, _ = _raw_film(t, begin, end)
-                mine[begin // spp:end // spp] = rad[begin // spp:end // spp]
-                wmine[begin // spp:end // spp] = wgt[begin // spp:end // spp]
         prad, pwgt = part_film(r)
-        own = wmine > 0
-        assert np.array_equal(pwgt[own], wmine[own]) and np.abs(prad[own] - mine[own]).max() <= 1e-5 * max(1.0, float(tfull.max()))
-        rows_of = (pwgt.reshape(H, W) > 0).all(axis=1)
-        assert np.array_equal(rows_of, (pwgt.reshape(H, W) > 0).any(axis=1))      # whole rows only
+        own = owner == r
+        # the rank renders every sample of exactly its own tiles: the same (pixel, sample) paths as the single render there
+        assert np.array_equal(pwgt[own], twfull[own]) and not pwgt[~own].any() and not prad[~own].any()
+        assert np.abs(prad[own] - tfull[own]).max() <= tol
         acc += prad; wacc += pwgt
-    assert (covered == 1).all()                      # the strips of the two ranks tile the image exactly once
     assert np.array_equal(wacc, twfull)
     assert np.abs(acc - tfull).max() <= 1e-5 * max(1.0, float(tfull.max()))
     # tile-mode and uniform-mode indexing enumerate the same (pixel, sample) pairs: same image up to addition order
@@ -286,4 +280,39 @@ def test_partitions_with_ragged_edges(tmp_path, built, tile):
         rad, wgt = film_of(lambda: s.render_range(b, e))
         acc += rad; wacc += wgt
     assert np.array_equal(wacc, wfull) and np.abs(acc - full).max() <= tol
+    s.close()
+
+
+@pytest.mark.parametrize("spp", [7, 64])
+def test_partitions_with_2d_tiles(tmp_path, built, spp):
+    """btrc_render_part on an image that divides into 2-D tiles (64 wide for 2 and 8 parts, 3 tiles per row; 64 wide for 3 parts: no width is coprime) (the C5 case in small): every part renders exactly the pixels
+    partition.tile_owner gives it, all samples of them (7 spp: pixel-major inside a tile; 64 spp: warps of 32 samples of one pixel,
+    pixel after pixel), and the parts sum to the single render."""
+    import torch
+
+    from btrc_b200 import api, partition, scenes
+
+    W, H = 192, 96
+    path = scenes.make_cornell(str(tmp_path), width=W, height=H, spp=spp, state_count=50000)
+    root = json.load(open(path)); root["renderer"]["tile"] = True; json.dump(root, open(path, "w"))
+    s = api.Scene(path)
+    full, wfull, _ = _raw_film(s)
+    assert (wfull == spp).all()
+    tol = 1e-5 * max(1.0, float(full.max()))
+    for parts in (2, 3, 8):
+        rows = partition.strip_rows(parts, H)
+        assert partition.tiles_are_2d(parts, W, H, rows)
+        owner = partition.tile_owner(parts, W, H).reshape(-1)
+        acc, wacc = np.zeros_like(full), np.zeros_like(wfull)
+        for part in range(parts):
+            s.film_clear()
+            s.render_part(parts, part)
+            rad = torch.zeros(H, W, 4, device="cuda"); wgt = torch.zeros(H, W, device="cuda")
+            s.film_export(rad, wgt)
+            rad = rad.cpu().numpy().reshape(-1, 4)[:, :3]; wgt = wgt.cpu().numpy().reshape(-1)
+            own = owner == part
+            assert np.array_equal(wgt[own], wfull[own]) and not wgt[~own].any() and not rad[~own].any()
+            assert np.abs(rad[own] - full[own]).max() <= tol
+            acc += rad; wacc += wgt
+        assert np.array_equal(wacc, wfull) and np.abs(acc - full).max() <= tol
     s.close()

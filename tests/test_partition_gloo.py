@@ -65,6 +65,37 @@ def test_interleaved_strips_tile_the_image():
                 assert max(sizes) - min(sizes) <= rows * w * spp
 
 
+def test_tile_owner_map():
+    """partition.tile_owner (the map GPU tests hold btrc_render_part to): every pixel has one owner; where the image does not divide
+    into 64 x rows tiles it agrees with the strip list; where it does, tiles are tile_width x rows rectangles dealt round-robin in row-major
+    tile order and no rank owns more than one tile more than another."""
+    import numpy as np
+
+    from btrc_b200 import partition
+
+    for world in (1, 2, 3, 4, 8):
+        for (w, h) in ((64, 48), (1920, 1080), (3840, 2160), (7, 5), (150, 77), (192, 96)):
+            rows = partition.strip_rows(world, h)
+            assert rows >= 1 and (h % rows == 0 or not any(h % r == 0 for r in range(max(1, rows // 2), rows + 1)))
+            owner = partition.tile_owner(world, w, h)
+            assert owner.shape == (h, w) and owner.min() >= 0 and owner.max() < world
+            if partition.tiles_are_2d(world, w, h, rows):
+                tw = partition.tile_width(world, w)
+                tx, ty = w // tw, h // rows
+                tiles = owner.reshape(ty, rows, tx, tw)
+                assert (tiles == tiles[:, :1, :, :1]).all()                      # constant inside a tile
+                k = np.arange(tx * ty).reshape(ty, tx)
+                assert np.array_equal(tiles[:, 0, :, 0], k % world)
+                counts = np.bincount(owner.reshape(-1), minlength=world)
+                assert counts.max() - counts.min() <= tw * rows
+            else:
+                for r in range(world):
+                    mine = np.zeros(h, bool)
+                    for b, e in partition.tile_path_ranges(r, world, 1, w, h, rows):
+                        mine[b // w:e // w] = True
+                    assert np.array_equal((owner == r).all(axis=1), mine) and np.array_equal((owner == r).any(axis=1), mine)
+
+
 def _worker(rank, world, path, port, out):
     sys.path.insert(0, ROOT)
     import torch
