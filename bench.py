@@ -543,7 +543,7 @@ def measure(args, D, workload, steps, warmup, spp_override=0, e2e=True, cpu=True
 
     cfg = workload_config(workload)   # identical in both arms; how this arm ran it goes to "run"
     run = {}
-    run.update({"spp_rendered_per_step": spp_scene, "gpus": world, "state_count": s.info.state_count, "bvh_layout": "instanced" if s.info.bvh_instanced else "flat",
+    run.update({"spp_rendered_per_step": spp_scene, "gpus": world, "state_count": s.info.state_count, "bvh_layout": "instanced" if s.info.bvh_instanced else "wide8" if s.info.bvh_wide else "flat",
                 "partition": (_partition_text(tiles, world, W, H) +
                               "; ncclReduce(sum) of the radiance+weight films onto rank 0 inside the library (btrc_reduce_films), resolve on rank 0") if world > 1 else "single GPU",
                 "timing": "CUDA events on the renderer's stream per step, max over ranks; 256 MB L2 flush (untimed) between steps; "

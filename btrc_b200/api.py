@@ -26,7 +26,7 @@ class BtrcError(RuntimeError):
 class SceneInfo(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in ("width", "height", "spp", "min_depth", "max_depth", "state_count", "tile", "albedo", "normal",
                                        "n_instances", "n_lights", "n_triangles", "n_materials", "bvh_depth", "n_media", "has_medium", "n_textures")] + \
-               [("world_diagonal", c_float), ("bvh_build_seconds", c_float), ("bvh_bytes", c_uint64), ("bvh_instanced", c_int32), ("reserved", c_int32)]
+               [("world_diagonal", c_float), ("bvh_build_seconds", c_float), ("bvh_bytes", c_uint64), ("bvh_instanced", c_int32), ("bvh_wide", c_int32)]
 
 
 class RenderStats(ctypes.Structure):

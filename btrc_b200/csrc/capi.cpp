@@ -205,9 +205,10 @@ int btrc_scene_info_get(btrc_scene_t *s, btrc_scene_info_t *o) {
         o->bvh_build_seconds = (float)sc.bvh_build_seconds;
         o->bvh_bytes = sc.renderer.lbvh ? 64ull * (uint64_t)sc.lbvh_nodes + 48ull * sc.world_tris.size()
                        : sc.instanced_bvh ? (uint64_t)(sc.two_level.bl_nodes.size() + sc.two_level.tl_nodes.size() + sc.two_level.tris.size()) * sizeof(float)
+                       : sc.wide_bvh8     ? (uint64_t)(sc.wide_bvh.nodes.size() + sc.wide_bvh.tris.size()) * sizeof(float)
                                           : (uint64_t)(sc.flat_bvh.nodes.size() + sc.flat_bvh.tris.size()) * sizeof(float);
         o->bvh_instanced = sc.instanced_bvh ? 1 : 0;
-        o->reserved = 0;
+        o->bvh_wide = sc.wide_bvh8 ? 1 : 0;
     });
 }
 

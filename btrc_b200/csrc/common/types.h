@@ -195,6 +195,10 @@ struct BvhDevice {
     const float4 *tl_nodes;
     const float4 *inst_blas;
     int two_level;
+    // compressed 8-wide layout (host/bvh.h WideBvh8, "bvh_layout": "wide8"): 5 uint4 per node, node 0 = root; `tris` / `tri_ids` are
+    // then in the wide tree's leaf order and `nodes` is unused
+    const uint4 *wide_nodes;
+    int wide;
 };
 
 struct HaltonConsts {  // HaltonSampler::initialize_consts (builtin/sampler/halton.cpp:116-133)

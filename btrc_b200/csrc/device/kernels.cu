@@ -24,9 +24,10 @@ constexpr int kBlock = 256;
 #define BTRC_CURSOR_AHEAD 0
 #endif
 constexpr unsigned kFull = 0xffffffffu;
-// TRAV: loop form / hierarchy of the walk (kernels.h LaunchCfg::traverse): 0 while-while, 1 if-if, 2 two-level (instanced scenes)
+// TRAV: loop form / hierarchy of the walk (kernels.h LaunchCfg::traverse): 0 while-while, 1 if-if, 2 two-level (instanced scenes), 3 compressed 8-wide
 template <bool ANY_HIT, int TRAV>
 __device__ __forceinline__ HitRec traverse_warp(const BvhDevice &bvh, float4 o4, float4 d4, bool valid) {  // all 32 lanes call this together
+    if (TRAV == 3) return traverse_bvh8<ANY_HIT, true>(bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w, valid);
     if (TRAV == 2) return traverse_two_level<ANY_HIT, true>(bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w, valid);
     if (TRAV == 1) return traverse_bvh2_ifif<ANY_HIT, true>(bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w, valid);
     return traverse_bvh2<ANY_HIT, true>(bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w, valid);
@@ -290,7 +291,11 @@ __device__ __forceinline__ void class_append(const HitQueue &hq, WaveCtl *ctl, b
 #ifndef BTRC_TRACE_MIN_BLOCKS_2L
 #define BTRC_TRACE_MIN_BLOCKS_2L 5
 #endif
-template <int TRAV> constexpr int trace_min_blocks() { return TRAV == 2 ? BTRC_TRACE_MIN_BLOCKS_2L : BTRC_TRACE_MIN_BLOCKS; }
+// the 8-wide walk tests eight quantised boxes per step in registers: 4 CTAs (64 registers)
+#ifndef BTRC_TRACE_MIN_BLOCKS_W8
+#define BTRC_TRACE_MIN_BLOCKS_W8 4
+#endif
+template <int TRAV> constexpr int trace_min_blocks() { return TRAV == 3 ? BTRC_TRACE_MIN_BLOCKS_W8 : TRAV == 2 ? BTRC_TRACE_MIN_BLOCKS_2L : BTRC_TRACE_MIN_BLOCKS; }
 // direction octant << 9 | 8x8x8 cell of the origin over the world box
 __device__ __forceinline__ uint32_t ray_sort_key(const SceneDevice &scene, f3 o, f3 d) {
     const int cx = min(max(int((o.x - scene.sort_lo[0]) * scene.sort_scale[0]), 0), 7);
@@ -447,8 +452,9 @@ __global__ void __launch_bounds__(kBlock) trace_batch_kernel(SceneDevice scene, 
                                                             uint32_t *flag, uint4 *detail) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 o4 = ray_o[i], d4 = ray_d[i];
-        const HitRec h = scene.bvh.two_level ? traverse_two_level<false>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w)
-                                             : traverse_bvh2<false>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w);
+        const HitRec h = scene.bvh.wide        ? traverse_bvh8<false, false>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w)
+                         : scene.bvh.two_level ? traverse_two_level<false>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w)
+                                               : traverse_bvh2<false>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w);
         if (h.slot < 0) detail[i] = make_uint4(0, 0, 0, 0);
         store_hit(scene.bvh, h, i, flag, detail);
     }
@@ -457,8 +463,9 @@ __global__ void __launch_bounds__(kBlock) trace_batch_kernel(SceneDevice scene, 
 __global__ void __launch_bounds__(kBlock) anyhit_batch_kernel(SceneDevice scene, const float4 *ray_o, const float4 *ray_d, int n, uint8_t *occluded) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 o4 = ray_o[i], d4 = ray_d[i];
-        const HitRec h = scene.bvh.two_level ? traverse_two_level<true>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w)
-                                             : traverse_bvh2<true>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w);
+        const HitRec h = scene.bvh.wide        ? traverse_bvh8<true, false>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w)
+                         : scene.bvh.two_level ? traverse_two_level<true>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w)
+                                               : traverse_bvh2<true>(scene.bvh, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, d4.w);
         occluded[i] = h.slot >= 0 ? 1 : 0;
     }
 }
@@ -900,12 +907,12 @@ void launch_ray_sort(const LaunchCfg &cfg, const SceneDevice &scene, const float
 
 void launch_trace(const LaunchCfg &cfg, const SceneDevice &scene, PathQueue cur, HitQueue hit, RaySort rs, WaveCtl *ctl, cudaStream_t stream) {
     const int blocks = persistent_blocks(cfg, 8);
-    if (cfg.probe_top_levels > 0 && !scene.bvh.two_level)
+    if (cfg.probe_top_levels > 0 && !scene.bvh.two_level && !scene.bvh.wide)
         top_levels_probe_kernel<<<blocks, kBlock, 0, stream>>>(scene, cur, ctl, cfg.probe_top_levels, reinterpret_cast<unsigned long long *>(&ctl->n_iter));
 #define BTRC_TRACE(T, S) trace_kernel<T, S><<<blocks, kBlock, 0, stream>>>(scene, cur, hit, rs, ctl)
-    const int trav = scene.bvh.two_level ? 2 : (cfg.traverse_ifif ? 1 : 0);
-    if (cfg.sorted_rays) { if (trav == 2) BTRC_TRACE(2, true); else if (trav == 1) BTRC_TRACE(1, true); else BTRC_TRACE(0, true); }
-    else { if (trav == 2) BTRC_TRACE(2, false); else if (trav == 1) BTRC_TRACE(1, false); else BTRC_TRACE(0, false); }
+    const int trav = scene.bvh.wide ? 3 : scene.bvh.two_level ? 2 : (cfg.traverse_ifif ? 1 : 0);
+    if (cfg.sorted_rays) { if (trav == 3) BTRC_TRACE(3, true); else if (trav == 2) BTRC_TRACE(2, true); else if (trav == 1) BTRC_TRACE(1, true); else BTRC_TRACE(0, true); }
+    else { if (trav == 3) BTRC_TRACE(3, false); else if (trav == 2) BTRC_TRACE(2, false); else if (trav == 1) BTRC_TRACE(1, false); else BTRC_TRACE(0, false); }
 #undef BTRC_TRACE
 }
 
@@ -959,8 +966,8 @@ void launch_shadow(const LaunchCfg &cfg, const SceneDevice &scene, const RenderP
                    cudaStream_t stream) {
     const int blocks = persistent_blocks(cfg, 8);
 #define BTRC_SHADOW(T, S, P) shadow_kernel<T, S, P><<<blocks, kBlock, 0, stream>>>(scene, params, shadow, rs, film, ctl)
-#define BTRC_SHADOW_T(S, P) do { if (trav == 2) BTRC_SHADOW(2, S, P); else if (trav == 1) BTRC_SHADOW(1, S, P); else BTRC_SHADOW(0, S, P); } while (0)
-    const int trav = scene.bvh.two_level ? 2 : (cfg.traverse_ifif ? 1 : 0);
+#define BTRC_SHADOW_T(S, P) do { if (trav == 3) BTRC_SHADOW(3, S, P); else if (trav == 2) BTRC_SHADOW(2, S, P); else if (trav == 1) BTRC_SHADOW(1, S, P); else BTRC_SHADOW(0, S, P); } while (0)
+    const int trav = scene.bvh.wide ? 3 : scene.bvh.two_level ? 2 : (cfg.traverse_ifif ? 1 : 0);
     if (scene.has_medium == 2) {  // 3-D texture programs in the transmittance: see launch_medium
         if (cfg.sorted_rays) BTRC_SHADOW_T(true, true); else BTRC_SHADOW_T(false, true);
     } else {

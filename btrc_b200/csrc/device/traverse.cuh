@@ -316,4 +316,118 @@ BTRC_TRAV_QUAL HitRec traverse_two_level(const BvhDevice &bvh, float ox, float o
     return best;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Compressed 8-wide BVH (host/bvh.h WideBvh8; selected by "bvh_layout": "wide8").  One traversal step = one 80-byte node (five
+// LDG.128) and eight quantised child boxes tested in registers; the children that were hit are kept as a bit mask ordered front to
+// back by the ray octant, so the stack holds one 8-byte entry per level instead of one per child.  Node boxes are conservative
+// supersets of the padded triangle boxes, the triangle test and the tie rule are the binary walk's: results are bit-identical.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kStack8 = 32;  // one entry per level of wide nodes (the host refuses deeper trees)
+
+// byte j of x as the float 2^23 + q: one PRMT builds 0x4B0000qq (no I2F); the 2^23 is folded into the plane offset
+BTRC_TRAV_QUAL float u8f(unsigned x, unsigned sel) { return __uint_as_float(__byte_perm(x, 0x4B000000u, sel)); }
+
+// CONVERGE: all 32 lanes of the warp call this together (lanes without a ray pass active = false) and vote before
+// every node step, which keeps the warp on one instruction stream (node step, then its triangles).
+template <bool ANY_HIT, bool CONVERGE>
+BTRC_TRAV_QUAL HitRec traverse_bvh8(const BvhDevice &bvh, float ox, float oy, float oz, float dx, float dy, float dz, float tmax, bool active = true) {
+    HitRec best;
+    best.t = tmax; best.u = 0.0f; best.v = 0.0f; best.slot = -1;
+
+    // A zero direction component would give inf * 0 = NaN in the slab test; clamp it to a tiny finite slope instead
+    // (the slab then evaluates to +-huge with the sign of (plane - origin), which is the exact answer for a parallel ray).
+    constexpr float kTiny = 1e-20f;
+    const float idx = 1.0f / (fabsf(dx) > kTiny ? dx : copysignf(kTiny, dx));
+    const float idy = 1.0f / (fabsf(dy) > kTiny ? dy : copysignf(kTiny, dy));
+    const float idz = 1.0f / (fabsf(dz) > kTiny ? dz : copysignf(kTiny, dz));
+    const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
+    // slot bit a set <=> child on the + side of axis a; (slot ^ octinv) is large for children on the near side
+    const unsigned octinv = (negx ? 0u : 1u) | (negy ? 0u : 2u) | (negz ? 0u : 4u);
+    const unsigned octinv4 = octinv * 0x01010101u;
+
+    uint2 stack[kStack8];
+    int sp = 0;
+    // node group: x = index of the first inner child, y = hit bits of the children still to visit (bits 31..24,
+    // priority order) | imask of the parent (bits 7..0).  The root is "the only child" of a virtual parent.
+    uint2 ngroup = make_uint2(0u, 0x80000000u);
+    bool alive = active;
+
+    while (CONVERGE ? __any_sync(0xffffffffu, alive) : alive) {
+        if (alive) {
+            // ---- next child in front-to-back order
+            const unsigned hits = ngroup.y;
+            const unsigned bit = 31u - (unsigned)__clz(hits);
+            ngroup.y = hits & ~(1u << bit);
+            if (ngroup.y > 0x00ffffffu) stack[sp++] = ngroup;
+            const unsigned slot = (bit - 24u) ^ octinv;
+            const unsigned rel = (unsigned)__popc(hits & ~(0xffffffffu << slot));  // inner children stored before this one
+            const uint4 *node = bvh.wide_nodes + 5 * (size_t)(ngroup.x + rel);
+            BTRC_TRAV_COUNT(0);
+            const uint4 v0 = __ldg(node), v1 = __ldg(node + 1), v2 = __ldg(node + 2), v3 = __ldg(node + 3), v4 = __ldg(node + 4);
+
+            // ---- eight quantised child boxes: plane = p + q * 2^e  =>  t = q * (2^e / d) + (p - o) / d
+            //      evaluated as (2^23 + q) * s + (b - 2^23 * s): the rounding of the offset moves a plane by at most half a
+            //      quantum, which the builder's one-quantum widening of every child box covers
+            const float sx = __uint_as_float((v0.w & 0xffu) << 23) * idx;
+            const float sy = __uint_as_float(((v0.w >> 8) & 0xffu) << 23) * idy;
+            const float sz = __uint_as_float(((v0.w >> 16) & 0xffu) << 23) * idz;
+            const float bx = fmaf(-8388608.0f, sx, (__uint_as_float(v0.x) - ox) * idx);
+            const float by = fmaf(-8388608.0f, sy, (__uint_as_float(v0.y) - oy) * idy);
+            const float bz = fmaf(-8388608.0f, sz, (__uint_as_float(v0.z) - oz) * idz);
+            unsigned hitmask = 0;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const unsigned meta4 = half ? v1.w : v1.z;
+                const unsigned is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+                const unsigned inner_mask4 = (is_inner4 >> 4) * 0xffu;
+                const unsigned bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+                const unsigned child_bits4 = (meta4 >> 5) & 0x07070707u;
+                const unsigned qlox = half ? v2.y : v2.x, qloy = half ? v2.w : v2.z, qloz = half ? v3.y : v3.x;
+                const unsigned qhix = half ? v3.w : v3.z, qhiy = half ? v4.y : v4.x, qhiz = half ? v4.w : v4.z;
+                const unsigned nx = negx ? qhix : qlox, fx = negx ? qlox : qhix;
+                const unsigned ny = negy ? qhiy : qloy, fy = negy ? qloy : qhiy;
+                const unsigned nz = negz ? qhiz : qloz, fz = negz ? qloz : qhiz;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned sel = 0x7650u + (unsigned)j;
+                    const float tnx = fmaf(u8f(nx, sel), sx, bx), tfx = fmaf(u8f(fx, sel), sx, bx);
+                    const float tny = fmaf(u8f(ny, sel), sy, by), tfy = fmaf(u8f(fy, sel), sy, by);
+                    const float tnz = fmaf(u8f(nz, sel), sz, bz), tfz = fmaf(u8f(fz, sel), sz, bz);
+                    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+                    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, best.t));
+                    if (tn <= tf) hitmask |= ((child_bits4 >> (8 * j)) & 0xffu) << ((bit_index4 >> (8 * j)) & 0xffu);
+                }
+            }
+            ngroup.x = v1.x;
+            ngroup.y = (hitmask & 0xff000000u) | (v0.w >> 24);
+            unsigned tmask = hitmask & 0x00ffffffu;
+
+            // ---- triangles of the leaf children that were hit
+            while (tmask) {
+                const int j = 31 - __clz(tmask);
+                tmask &= ~(1u << j);
+                const int s = (int)v1.y + j;
+                float t, u, v;
+                BTRC_TRAV_COUNT(1);
+                if (tri_test(bvh.tris + 3 * (size_t)s, ox, oy, oz, dx, dy, dz, best.t, t, u, v)) {
+                    if (ANY_HIT) {
+                        best.slot = s;
+                        alive = false;
+                        break;
+                    }
+                    if (t < best.t || best.slot < 0 || id_less(bvh.tri_ids, s, best.slot)) {
+                        best.t = t; best.u = u; best.v = v; best.slot = s;
+                    }
+                }
+            }
+            if (alive && ngroup.y <= 0x00ffffffu) {
+                if (sp == 0) alive = false;
+                else ngroup = stack[--sp];
+            }
+        }
+    }
+    return best;
+}
+
+
 }  // namespace btrc

@@ -18,6 +18,7 @@ struct Builder {
     const std::vector<AABB> &boxes;
     const std::vector<Vec3> &centers;
     int max_leaf;
+    bool force_leaf = false;  // every range of <= max_leaf primitives becomes a leaf (wide BVH: the triangles of a node's leaf children are tested in one step)
     std::vector<BuildNode> nodes;
     // primitive records are partitioned physically (box, centre, id together): every pass over a range streams memory
     // instead of gathering boxes[order[i]] through a shuffled index array (10 M triangles: 14 s -> a few seconds)
@@ -92,7 +93,7 @@ struct Builder {
     std::vector<std::array<int, 3>> pending;  // (node, first, count) subtrees collected by the parallel top phase
 
     void build(int ni, int first, int count, bool top = false) {
-        if (count <= 1) {
+        if (count <= 1 || (force_leaf && count <= max_leaf)) {
             AABB box;
             for (int i = first; i < first + count; ++i) box.extend(recs[i].box);
             make_leaf(ni, first, count, box);
@@ -176,10 +177,11 @@ struct Builder {
 
 }  // namespace
 
-BinaryBvh build_binary_bvh(const std::vector<AABB> &boxes, const std::vector<Vec3> &centers, int max_leaf) {
+BinaryBvh build_binary_bvh(const std::vector<AABB> &boxes, const std::vector<Vec3> &centers, int max_leaf, bool force_leaf) {
     const int n = (int)boxes.size();
     if (n == 0) throw Error("bvh: no primitives");
     Builder b(boxes, centers, max_leaf);
+    b.force_leaf = force_leaf;
     b.nodes.resize(2 * (size_t)n);
     b.recs.resize(n);
 #pragma omp parallel for
@@ -425,6 +427,197 @@ TwoLevelBvh build_two_level_bvh(const std::vector<std::vector<WorldTri>> &mesh_t
         return ~(live[top.order[nd.first]] << 3);
     }, out.tl_root_ref);
     out.depth = tree_depth(top) + deepest + 1;
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 8-wide collapse + quantisation
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct WideTask {
+    int binary;  // binary node this wide node is collapsed from
+    int index;   // wide node index
+    int depth;
+};
+
+// SAH-optimal collapse of the binary hierarchy into 8-wide nodes (dynamic programme of Ylitie et al. 2017, section 4.1,
+// restricted to the binary leaves as the only leaves): cost[n][i-1] = cheapest way to represent the subtree of n by at
+// most i wide-node children; i = 1 means "n becomes a wide node of its own" (or is a leaf).
+struct Collapse {
+    static constexpr float kNodeCost = 1.0f, kPrimCost = 0.3f;
+    const BinaryBvh &bvh;
+    std::vector<float> cost;      // 7 per binary node
+    std::vector<uint8_t> split;   // 8 per binary node: [i-1] for i = 2..7: children given to the left subtree (0 = same as i-1);
+                                  // [7]: left share when the node is opened as a wide node (8 slots)
+    explicit Collapse(const BinaryBvh &b) : bvh(b), cost(7 * b.nodes.size()), split(8 * b.nodes.size(), 0) {
+        // children are always created after their parent (Builder::build), so a reverse sweep sees children first
+        for (long long ni = (long long)b.nodes.size() - 1; ni >= 0; --ni) {
+            const BuildNode &nd = b.nodes[ni];
+            float *c = &cost[7 * ni];
+            const float area = nd.box.half_area();
+            if (nd.left < 0) {
+                for (int i = 0; i < 7; ++i) c[i] = area * nd.count * kPrimCost;
+                continue;
+            }
+            const float *cl = &cost[7 * (size_t)nd.left], *cr = &cost[7 * (size_t)nd.right];
+            auto distribute = [&](int j, int &best_k) {
+                float best = 3.402823466e+38f;
+                for (int k = 1; k < j; ++k) {
+                    if (k > 7 || j - k > 7) continue;
+                    const float v = cl[k - 1] + cr[j - k - 1];
+                    if (v < best) { best = v; best_k = k; }
+                }
+                return best;
+            };
+            int k = 1;
+            c[0] = distribute(8, k) + area * kNodeCost;
+            split[8 * ni + 7] = (uint8_t)k;
+            for (int i = 2; i <= 7; ++i) {
+                const float d = distribute(i, k);
+                if (d < c[i - 2]) { c[i - 1] = d; split[8 * ni + i - 1] = (uint8_t)k; }
+                else { c[i - 1] = c[i - 2]; split[8 * ni + i - 1] = 0; }
+            }
+        }
+    }
+    void expand(int ni, int j, int *out, int &n) const {
+        const BuildNode &nd = bvh.nodes[ni];
+        if (nd.left < 0 || j == 1) { out[n++] = ni; return; }
+        const int k = split[8 * (size_t)ni + j - 1];
+        if (k == 0) { expand(ni, j - 1, out, n); return; }
+        expand(nd.left, k, out, n);
+        expand(nd.right, j - k, out, n);
+    }
+    // children of the wide node made from binary node ni
+    int children(int ni, int *out) const {
+        const BuildNode &root = bvh.nodes[ni];
+        int n = 0;
+        if (root.left < 0) { out[n++] = ni; return n; }  // a scene of <= 3 triangles: the root is a leaf
+        const int k = split[8 * (size_t)ni + 7];
+        expand(root.left, k, out, n);
+        expand(root.right, 8 - k, out, n);
+        return n;
+    }
+};
+
+// Greedy octant assignment: slot bit a set <=> the child lies on the + side of the node centre along axis a.
+void assign_slots(const BinaryBvh &bvh, const AABB &box, const int *children, int n, int *slot_child) {
+    const Vec3 centre = 0.5f * (box.lo + box.hi);
+    float cost[8][8];
+    for (int c = 0; c < n; ++c) {
+        const AABB &b = bvh.nodes[children[c]].box;
+        const Vec3 d = 0.5f * (b.lo + b.hi) - centre;
+        for (int s = 0; s < 8; ++s) cost[c][s] = (s & 1 ? d.x : -d.x) + (s & 2 ? d.y : -d.y) + (s & 4 ? d.z : -d.z);
+    }
+    bool child_done[8] = {false}, slot_done[8] = {false};
+    for (int s = 0; s < 8; ++s) slot_child[s] = -1;
+    for (int k = 0; k < n; ++k) {
+        int bc = -1, bs = -1;
+        float best = -3.402823466e+38f;
+        for (int c = 0; c < n; ++c) {
+            if (child_done[c]) continue;
+            for (int s = 0; s < 8; ++s)
+                if (!slot_done[s] && cost[c][s] > best) { best = cost[c][s]; bc = c; bs = s; }
+        }
+        child_done[bc] = true;
+        slot_done[bs] = true;
+        slot_child[bs] = children[bc];
+    }
+}
+
+}  // namespace
+
+WideBvh8 build_wide_bvh8(const BinaryBvh &bvh, const std::vector<WorldTri> &tris) {
+    WideBvh8 out;
+    const size_t n_tris = bvh.order.size();
+    out.tris.resize(12 * n_tris);
+    out.tri_ids.resize(2 * n_tris);
+    out.nodes.assign(20, 0u);
+    size_t tri_cursor = 0;
+    const Collapse collapse(bvh);
+    std::vector<WideTask> queue = {{0, 0, 1}};
+    for (size_t qi = 0; qi < queue.size(); ++qi) {  // breadth first: siblings are contiguous, the top levels are packed together
+        const WideTask task = queue[qi];
+        out.depth = std::max(out.depth, task.depth);
+        int children[8], slot_child[8];
+        const int n = collapse.children(task.binary, children);
+        AABB box;
+        for (int c = 0; c < n; ++c) box.extend(bvh.nodes[children[c]].box);
+        assign_slots(bvh, box, children, n, slot_child);
+
+        // quantisation frame: plane = p + q * 2^e with q in [0, 255].  The kernel evaluates t = (2^23 + q) * s + (b - 2^23 * s)
+        // (one PRMT + one FFMA per plane), whose rounding can move a plane by half a quantum: every child box is widened
+        // by one quantum on each side, and the frame leaves room for that (children occupy quanta 1..254).
+        int e[3];
+        float p[3];
+        for (int a = 0; a < 3; ++a) {
+            const double lo = box.lo[a], hi = box.hi[a];
+            int ea = hi > lo ? (int)std::ceil(std::log2((hi - lo) / 253.0)) : -100;
+            ea = std::min(std::max(ea, -100), 100);
+            for (;;) {
+                const double sc = std::ldexp(1.0, ea);
+                float pf = (float)(lo - sc);
+                if ((double)pf > lo - sc) pf = std::nextafter(pf, -3.402823466e+38f);
+                if (std::floor((lo - (double)pf) / sc) >= 1.0 && std::ceil((hi - (double)pf) / sc) <= 254.0) { p[a] = pf; break; }
+                ++ea;
+            }
+            e[a] = ea;
+        }
+        uint32_t imask = 0;
+        uint8_t meta[8] = {0}, qlo[3][8], qhi[3][8];
+        const uint32_t child_base = (uint32_t)(out.nodes.size() / 20);
+        const uint32_t tri_base = (uint32_t)tri_cursor;
+        int n_inner = 0;
+        for (int s = 0; s < 8; ++s) {
+            for (int a = 0; a < 3; ++a) { qlo[a][s] = 255; qhi[a][s] = 0; }  // empty slots can never be hit
+            const int ci = slot_child[s];
+            if (ci < 0) continue;
+            const BuildNode &c = bvh.nodes[ci];
+            for (int a = 0; a < 3; ++a) {
+                const double sc = std::ldexp(1.0, e[a]);
+                const double lo = std::floor(((double)c.box.lo[a] - (double)p[a]) / sc) - 1.0;
+                const double hi = std::ceil(((double)c.box.hi[a] - (double)p[a]) / sc) + 1.0;
+                if (lo < 0.0 || hi > 255.0) throw Error("bvh8: child box outside the quantisation frame");
+                qlo[a][s] = (uint8_t)lo;
+                qhi[a][s] = (uint8_t)hi;
+            }
+            if (c.left >= 0) {
+                imask |= 1u << s;
+                meta[s] = (uint8_t)(0x20 | (24 + s));
+                ++n_inner;
+            } else {
+                if (c.count < 1 || c.count > 3) throw Error("bvh8: leaf size out of range");
+                const size_t off = tri_cursor - tri_base;
+                if (off + c.count > 24) throw Error("bvh8: more than 24 triangles under one node");
+                meta[s] = (uint8_t)((((1u << c.count) - 1u) << 5) | (uint32_t)off);
+                for (int k = 0; k < c.count; ++k, ++tri_cursor) {
+                    const WorldTri &t = tris[bvh.order[c.first + k]];
+                    float *o = &out.tris[12 * tri_cursor];
+                    o[0] = t.p0.x; o[1] = t.p0.y; o[2] = t.p0.z; o[3] = t.n.x;
+                    o[4] = t.e1.x; o[5] = t.e1.y; o[6] = t.e1.z; o[7] = t.n.y;
+                    o[8] = t.e2.x; o[9] = t.e2.y; o[10] = t.e2.z; o[11] = t.n.z;
+                    out.tri_ids[2 * tri_cursor] = t.inst;
+                    out.tri_ids[2 * tri_cursor + 1] = t.prim;
+                }
+            }
+        }
+        out.nodes.resize(out.nodes.size() + 20 * (size_t)n_inner, 0u);
+        int k = 0;
+        for (int s = 0; s < 8; ++s)
+            if (imask & (1u << s)) queue.push_back({slot_child[s], (int)child_base + k++, task.depth + 1});
+
+        uint32_t *w = &out.nodes[20 * (size_t)task.index];
+        std::memcpy(w, p, 12);
+        w[3] = (uint32_t)(e[0] + 127) | (uint32_t)(e[1] + 127) << 8 | (uint32_t)(e[2] + 127) << 16 | imask << 24;
+        w[4] = child_base;
+        w[5] = tri_base;
+        auto pack = [](const uint8_t *b) { return (uint32_t)b[0] | (uint32_t)b[1] << 8 | (uint32_t)b[2] << 16 | (uint32_t)b[3] << 24; };
+        w[6] = pack(meta); w[7] = pack(meta + 4);
+        w[8] = pack(qlo[0]); w[9] = pack(qlo[0] + 4); w[10] = pack(qlo[1]); w[11] = pack(qlo[1] + 4);
+        w[12] = pack(qlo[2]); w[13] = pack(qlo[2] + 4); w[14] = pack(qhi[0]); w[15] = pack(qhi[0] + 4);
+        w[16] = pack(qhi[1]); w[17] = pack(qhi[1] + 4); w[18] = pack(qhi[2]); w[19] = pack(qhi[2] + 4);
+    }
+    if (tri_cursor != n_tris) throw Error("bvh8: triangle count mismatch");
     return out;
 }
 

@@ -23,7 +23,8 @@ struct BinaryBvh {
 };
 
 // boxes/centers: one per primitive.  max_leaf: largest allowed leaf.
-BinaryBvh build_binary_bvh(const std::vector<AABB> &boxes, const std::vector<Vec3> &centers, int max_leaf);
+// force_leaf: every range of <= max_leaf primitives becomes a leaf without asking the SAH (wide layout).
+BinaryBvh build_binary_bvh(const std::vector<AABB> &boxes, const std::vector<Vec3> &centers, int max_leaf, bool force_leaf = false);
 
 // World-space triangle as the traversal kernels consume it (lib/bvh/include/bvh/triangle.hpp:27-34 convention:
 // e1 = p0 - p1, e2 = p2 - p0, n = cross(e1, e2)).
@@ -46,6 +47,30 @@ struct FlatBvh2 {
 };
 
 FlatBvh2 flatten_bvh2(const BinaryBvh &bvh, const std::vector<WorldTri> &tris);
+
+// ---- compressed 8-wide layout ("bvh_layout": "wide8") ---------------------------------------------------------------------
+// The "compact wide BVH" of BASELINE's north_star, after Ylitie, Karras, Laine 2017: the binary SAH tree above, collapsed into
+// 8-wide nodes by the SAH-optimal dynamic programme, child boxes quantised to 8 bits in a per-node frame.
+// 80-byte nodes = five 16-byte vectors
+//   v0 = (p.x, p.y, p.z, ex | ey << 8 | ez << 16 | imask << 24)    quantisation origin, per-axis scale exponents (biased),
+//                                                                     bit i of imask set <=> slot i holds an inner node
+//   v1 = (child_base, tri_base, meta[0..3], meta[4..7])             first inner child / first triangle slot of this node
+//   v2 = (qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7])        8-bit child boxes: plane = p + q * 2^(e - 127)
+//   v3 = (qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7])
+//   v4 = (qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7])
+// meta[i]: 0 = empty slot; inner child: 0b001'11000 | i; leaf: (unary triangle count 0b001/0b011/0b111) << 5 | offset of
+// its first triangle from tri_base (< 24).  Inner children are stored contiguously in slot order from child_base,
+// triangles of the leaf children contiguously from tri_base.  Children are assigned to slots by octant so that
+// (slot ^ ray octant) orders them front to back.  10 M triangles: 0.6 GB of binary nodes -> 0.11 GB.
+struct WideBvh8 {
+    std::vector<uint32_t> nodes;    // 20 words per node, node 0 = root
+    std::vector<float> tris;        // 12 floats per triangle slot
+    std::vector<uint32_t> tri_ids;  // 2 per triangle slot
+    int depth = 0;                  // levels of wide nodes
+};
+
+// `bvh` must have leaves of at most 3 primitives (build_binary_bvh(boxes, centers, 3, true)).
+WideBvh8 build_wide_bvh8(const BinaryBvh &bvh, const std::vector<WorldTri> &tris);
 
 // ---- two-level hierarchy for instanced scenes --------------------------------------------------------------------------------
 // The reference builds one GAS per mesh and an IAS over the instances (utils/optix/context.cpp:158-294, core/scene.cpp:196-209).

@@ -43,6 +43,7 @@ Renderer::Renderer(Scene &scene, int state_count_override) : scene_(scene) {
     cfg_.sm_count = prop.multiProcessorCount;
     {   // traversal loop form by BVH footprint against the L2 (kernels.h: LaunchCfg::traverse_ifif); BTRC_TRAVERSE=ww|ifif overrides
         const size_t bvh_bytes = scene.renderer.lbvh ? 64 * (size_t)scene.lbvh_nodes + 48 * scene.world_tris.size()
+                                 : scene.wide_bvh8 ? (scene.wide_bvh.nodes.size() + scene.wide_bvh.tris.size()) * sizeof(float)
                                                      : scene.flat_bvh.nodes.size() * sizeof(float) + scene.flat_bvh.tris.size() * sizeof(float);
         cfg_.traverse_ifif = bvh_bytes > (size_t)prop.l2CacheSize;
         if (const char *e = std::getenv("BTRC_TRAVERSE")) cfg_.traverse_ifif = std::string(e) == "ifif";

@@ -512,8 +512,8 @@ void Scene::create(const NodeP &root) {
         }
         if (auto ln = r->find("bvh_layout")) {
             const std::string lt = ln->as_string();
-            if (lt != "auto" && lt != "flat" && lt != "instanced") throw Error("unknown bvh layout: " + lt);
-            renderer.bvh_layout = lt == "flat" ? 1 : lt == "instanced" ? 2 : 0;
+            if (lt != "auto" && lt != "flat" && lt != "instanced" && lt != "wide8") throw Error("unknown bvh layout: " + lt);
+            renderer.bvh_layout = lt == "flat" ? 1 : lt == "instanced" ? 2 : lt == "wide8" ? 3 : 0;
         }
         if (auto sn = r->find("sampler")) {  // wavefront/common.h:36-37 chooses at compile time; here it is a renderer parameter
             const std::string st = sn->as_string();
@@ -688,9 +688,11 @@ void Scene::commit() {
     two_level = TwoLevelBvh();
     {
         int layout = renderer.bvh_layout;
-        if (const char *e = std::getenv("BTRC_BVH_LAYOUT")) layout = std::string(e) == "flat" ? 1 : std::string(e) == "instanced" ? 2 : 0;
+        if (const char *e = std::getenv("BTRC_BVH_LAYOUT")) layout = std::string(e) == "flat" ? 1 : std::string(e) == "instanced" ? 2 : std::string(e) == "wide8" ? 3 : 0;
         instanced_bvh = !renderer.lbvh && layout == 2;
+        wide_bvh8 = !renderer.lbvh && layout == 3;
     }
+    wide_bvh = WideBvh8();
     if (renderer.lbvh) {  // built on the device at upload (device/lbvh.cu): only the unsorted triangle arrays are prepared here
         flat_bvh = FlatBvh2();
         bvh_depth = 0;
@@ -726,10 +728,20 @@ void Scene::commit() {
         float coord_max = 0;
         for (int a = 0; a < 3; ++a) coord_max = std::max(coord_max, std::max(std::fabs(wb.lo[a]), std::fabs(wb.hi[a])));
         padded_triangle_boxes(world_tris, coord_max, boxes, centers);  // DESIGN.md, "conservative boxes"
-        BinaryBvh bb = build_binary_bvh(boxes, centers, 4);
-        bvh_depth = tree_depth(bb);
-        if (bvh_depth > 60) throw Error("bvh too deep for the traversal stack: " + std::to_string(bvh_depth));
-        flat_bvh = flatten_bvh2(bb, world_tris);
+        if (wide_bvh8) {  // "bvh_layout": "wide8" (bvh.h): leaves of at most 3 triangles, collapsed 8-wide, 8-bit child boxes.  Measured on B200
+            // (profiles/r2v_ab_wide_bvh8.md): a fifth of the node bytes, but a step costs ~5x the instructions of a binary step for ~0.6x
+            // the steps -- slower than the binary tree on every BASELINE scene, hence on request only.
+            flat_bvh = FlatBvh2();
+            const BinaryBvh bb = build_binary_bvh(boxes, centers, 3, true);
+            wide_bvh = build_wide_bvh8(bb, world_tris);
+            bvh_depth = wide_bvh.depth;
+            if (bvh_depth > 30) throw Error("wide bvh too deep for the traversal stack: " + std::to_string(bvh_depth));
+        } else {
+            BinaryBvh bb = build_binary_bvh(boxes, centers, 4);
+            bvh_depth = tree_depth(bb);
+            if (bvh_depth > 60) throw Error("bvh too deep for the traversal stack: " + std::to_string(bvh_depth));
+            flat_bvh = flatten_bvh2(bb, world_tris);
+        }
     }
     bvh_build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
@@ -901,6 +913,13 @@ void Scene::upload_device() {
         dev.bvh.tri_ids = reinterpret_cast<const uint2 *>(upload(two_level.tri_ids));
         dev.bvh.root_ref = two_level.tl_root_ref;
         dev.bvh.two_level = 1;
+        dev.bvh.n_tris = (int)world_tris.size();
+    } else if (wide_bvh8) {
+        dev.bvh.wide_nodes = reinterpret_cast<const uint4 *>(upload(wide_bvh.nodes));
+        dev.bvh.tris = reinterpret_cast<const float4 *>(upload(wide_bvh.tris));
+        dev.bvh.tri_ids = reinterpret_cast<const uint2 *>(upload(wide_bvh.tri_ids));
+        dev.bvh.root_ref = 0;
+        dev.bvh.wide = 1;
         dev.bvh.n_tris = (int)world_tris.size();
     } else {
         dev.bvh.nodes = reinterpret_cast<const float4 *>(upload(flat_bvh.nodes));

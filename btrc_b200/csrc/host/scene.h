@@ -105,8 +105,9 @@ struct RendererDesc {  // builtin/renderer/wavefront.cpp:375-398
     bool tile = false;
     bool lbvh = false;    // "bvh_builder": "sah" (host binned SAH, default) | "lbvh" (device-side Morton-code build at upload)
     // "bvh_layout": "flat" (instances flattened into one world-space tree) | "instanced" (one object-space tree per mesh under a tree
-    // over the instances: bvh.h; saves the per-instance copies of a mesh's nodes, measured slower to trace) | "auto" (default: flat)
-    int bvh_layout = 0;   // 0 auto, 1 flat, 2 instanced
+    // over the instances: bvh.h; saves the per-instance copies of a mesh's nodes, measured slower to trace) | "wide8" (the flat tree
+    // collapsed into compressed 8-wide nodes: bvh.h WideBvh8; a fifth of the node bytes, measured slower to trace) | "auto" (default: flat)
+    int bvh_layout = 0;   // 0 auto, 1 flat, 2 instanced, 3 wide8
     bool halton = false;  // "sampler": "independent" (default, what the reference's wavefront renderer is compiled with) | "halton"
     int spp = 128;
     int min_depth = 5, max_depth = 10;
@@ -148,6 +149,8 @@ public:
     FlatBvh2 flat_bvh;
     TwoLevelBvh two_level;       // used instead of flat_bvh when `instanced_bvh`
     bool instanced_bvh = false;
+    WideBvh8 wide_bvh;           // used instead of flat_bvh when `wide_bvh8`
+    bool wide_bvh8 = false;
     std::vector<AliasUnit> filter_alias;
     std::vector<float> ibl_tile_probs;      // EnvirLightSampler tile table (light/env_sampler.cpp:72-122)
     std::vector<AliasUnit> ibl_alias;

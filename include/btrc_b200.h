@@ -39,7 +39,7 @@ typedef struct btrc_scene_info {
     float bvh_build_seconds;
     uint64_t bvh_bytes;           /* nodes + triangles the traversal kernels walk (compare with the 126 MB L2)           */
     int32_t bvh_instanced;        /* 1: two-level layout (one object-space tree per mesh under a tree over the instances) */
-    int32_t reserved;
+    int32_t bvh_wide;             /* 1: compressed 8-wide layout ("bvh_layout": "wide8"; 80-byte nodes, 8-bit child boxes)   */
 } btrc_scene_info_t;
 
 typedef struct btrc_render_stats {

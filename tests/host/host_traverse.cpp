@@ -235,6 +235,71 @@ void ht2_any(void *hh, int n, const float *o_med, const float *d_t1, uint8_t *oc
                                                       d_t1[4 * i + 3]).slot >= 0;
 }
 
+// The compressed 8-wide layout ("bvh_layout": "wide8"): build_binary_bvh(.., 3, true) + build_wide_bvh8 as Scene::commit does,
+// walked by traverse_bvh8 (the product's device function compiled for the host).
+struct HostWide8 { WideBvh8 w; };
+
+void *ht8_build(int n, const float *verts, const uint32_t *ids) {
+    std::vector<WorldTri> tris(n);
+    AABB wb;
+    for (int i = 0; i < n; ++i) {
+        tris[i] = make_tri(verts + 9 * (size_t)i, ids[2 * i], ids[2 * i + 1]);
+        wb.extend(tris[i].p0); wb.extend(tris[i].p1); wb.extend(tris[i].p2);
+    }
+    float coord_max = 0;
+    for (int a = 0; a < 3; ++a) coord_max = std::max(coord_max, std::max(std::fabs(wb.lo[a]), std::fabs(wb.hi[a])));
+    std::vector<AABB> boxes;
+    std::vector<Vec3> centers;
+    padded_triangle_boxes(tris, coord_max, boxes, centers);
+    const BinaryBvh bb = build_binary_bvh(boxes, centers, 3, true);
+    auto *h = new HostWide8;
+    h->w = build_wide_bvh8(bb, tris);
+    return h;
+}
+void ht8_free(void *h) { delete static_cast<HostWide8 *>(h); }
+int ht8_info(void *hh, int which) {  // 0: wide nodes, 1: levels of wide nodes
+    const HostWide8 *h = static_cast<HostWide8 *>(hh);
+    return which == 0 ? (int)(h->w.nodes.size() / 20) : h->w.depth;
+}
+static BvhDevice view8(const HostWide8 *h) {
+    BvhDevice b{};
+    b.wide_nodes = reinterpret_cast<const uint4 *>(h->w.nodes.data());
+    b.tris = reinterpret_cast<const float4 *>(h->w.tris.data());
+    b.tri_ids = reinterpret_cast<const uint2 *>(h->w.tri_ids.data());
+    b.n_tris = (int)(h->w.tri_ids.size() / 2);
+    b.wide = 1;
+    return b;
+}
+void ht8_closest(void *hh, int n, const float *o_med, const float *d_t1, uint32_t *out_ids, float *out_tuv, uint64_t *steps) {
+    const HostWide8 *h = static_cast<HostWide8 *>(hh);
+    const BvhDevice b = view8(h);
+    uint64_t n_nodes = 0, n_tests = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : n_nodes, n_tests)
+    for (int i = 0; i < n; ++i) {
+        g_count[0] = g_count[1] = 0;
+        const HitRec r = traverse_bvh8<false, false>(b, o_med[4 * i], o_med[4 * i + 1], o_med[4 * i + 2], d_t1[4 * i], d_t1[4 * i + 1],
+                                                     d_t1[4 * i + 2], d_t1[4 * i + 3]);
+        if (r.slot < 0) {
+            out_ids[2 * i] = out_ids[2 * i + 1] = 0xffffffffu;
+            out_tuv[3 * i] = out_tuv[3 * i + 1] = out_tuv[3 * i + 2] = 0;
+        } else {
+            out_ids[2 * i] = h->w.tri_ids[2 * r.slot];
+            out_ids[2 * i + 1] = h->w.tri_ids[2 * r.slot + 1];
+            out_tuv[3 * i] = r.t; out_tuv[3 * i + 1] = r.u; out_tuv[3 * i + 2] = r.v;
+        }
+        n_nodes += g_count[0];
+        n_tests += g_count[1];
+    }
+    if (steps) { steps[0] = n_nodes; steps[1] = n_tests; }
+}
+void ht8_any(void *hh, int n, const float *o_med, const float *d_t1, uint8_t *occluded) {
+    const BvhDevice b = view8(static_cast<HostWide8 *>(hh));
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int i = 0; i < n; ++i)
+        occluded[i] = traverse_bvh8<true, false>(b, o_med[4 * i], o_med[4 * i + 1], o_med[4 * i + 2], d_t1[4 * i], d_t1[4 * i + 1], d_t1[4 * i + 2],
+                                                 d_t1[4 * i + 3]).slot >= 0;
+}
+
 void ht_free(void *h) { delete static_cast<HostBvh *>(h); }
 int ht_num_nodes(void *h) { return static_cast<HostBvh *>(h)->n_inner; }
 
