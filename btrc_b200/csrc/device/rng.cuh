@@ -49,12 +49,29 @@ struct Pcg {
         }
         state = acc_mult * state + acc_plus;
     }
-    // advance(blocks << 16): the first 16 rounds of the loop above see zero bits only and square the step map; they are folded
-    // into compile-time constants, the remaining rounds are the same arithmetic -- the resulting state is bit-identical
-    // (independent.cpp:11-15 advances by sample_index * 65536; a 256-spp render then loops 8 times instead of 24)
+    // advance(blocks << 16) (independent.cpp:11-15 advances by sample_index * 65536).  2^(16+j) steps of the generator are the map
+    // x -> M_j x + S_j inc with compile-time M_j, S_j; the maps of the set bits of `blocks` are applied one after the other (they
+    // commute: powers of one affine map) -- two 64-bit multiplies per SET bit instead of the loop above's two per bit for squaring the
+    // map plus three per set bit.  All arithmetic is exact mod 2^64, so the state is bit-identical to advance(blocks << 16).
+    template <int J>
+    __device__ __forceinline__ void skip_bit(uint64_t blocks) {
+        constexpr uint64_t m = pcg_mult_pow2(16 + J), s = pcg_plus_sum2(16 + J);
+        if ((blocks >> J) & 1) state = m * state + s * inc;
+    }
     __device__ __forceinline__ void advance_blocks_of_65536(uint64_t blocks) {
-        constexpr uint64_t kM16 = pcg_mult_pow2(16), kS16 = pcg_plus_sum2(16);
-        uint64_t cur_mult = kM16, cur_plus = kS16 * inc, acc_mult = 1, acc_plus = 0;
+        skip_bit<0>(blocks); skip_bit<1>(blocks); skip_bit<2>(blocks); skip_bit<3>(blocks); skip_bit<4>(blocks);
+        if (blocks >> 5) {
+            skip_bit<5>(blocks); skip_bit<6>(blocks); skip_bit<7>(blocks); skip_bit<8>(blocks); skip_bit<9>(blocks);
+            if (blocks >> 10) {
+                skip_bit<10>(blocks); skip_bit<11>(blocks); skip_bit<12>(blocks); skip_bit<13>(blocks); skip_bit<14>(blocks); skip_bit<15>(blocks);
+                constexpr uint64_t kM32 = pcg_mult_pow2(32), kS32 = pcg_plus_sum2(32);
+                if (blocks >> 16) advance_blocks_loop(blocks >> 16, kM32, kS32);
+            }
+        }
+    }
+    // the generic loop, starting from the map of 2^k steps (mult0 = M^(2^k), sum0 = S_k)
+    __device__ __noinline__ void advance_blocks_loop(uint64_t blocks, uint64_t mult0, uint64_t sum0) {
+        uint64_t cur_mult = mult0, cur_plus = sum0 * inc, acc_mult = 1, acc_plus = 0;
         while (blocks > 0) {
             if (blocks & 1) {
                 acc_mult *= cur_mult;

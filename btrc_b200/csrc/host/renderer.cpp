@@ -142,7 +142,7 @@ void Renderer::render_part(int parts, int part, int rows_per_strip) {
         if (const char *e = std::getenv("BTRC_TILE_W")) if (std::atoi(e) > 0) kTileW = std::atoi(e);
     }
     static const bool tiles_2d = !(std::getenv("BTRC_TILES_2D") && std::atoi(std::getenv("BTRC_TILES_2D")) == 0);
-    if (tiles_2d && W % kTileW == 0 && H % rows == 0) {
+    if (tiles_2d && W % kTileW == 0 && H % rows == 0 && kTileW * rows * spp < (1LL << 31)) {  // the kernel's in-tile arithmetic is 32-bit
         const long long block = kTileW * rows * spp, tiles = (W / kTileW) * (H / rows);
         const long long owned = part < tiles ? (tiles - 1 - part) / parts + 1 : 0;
         render_range(0, owned * block, block, parts, part, (int)kTileW, (int)rows);
@@ -159,7 +159,7 @@ void Renderer::render_part(int parts, int part, int rows_per_strip) {
 }
 
 void Renderer::render_range(long long begin, long long end, long long stride_block, int stride_parts, int stride_part, int stride_bw, int stride_rows) {
-    if (stride_bw > 0 && (stride_rows <= 0 || scene_.width % stride_bw || scene_.height % stride_rows ||
+    if (stride_bw > 0 && (stride_rows <= 0 || scene_.width % stride_bw || scene_.height % stride_rows || stride_block >= (1LL << 31) ||
                           stride_block != (long long)stride_bw * stride_rows * scene_.renderer.spp))
         throw Error("render_range: 2-D tiles must divide the image");
     if (stride_block < 0 || stride_parts < 1 || stride_part < 0 || stride_part >= stride_parts) throw Error("render_range: bad stride");
@@ -198,8 +198,9 @@ void Renderer::render_range(long long begin, long long end, long long stride_blo
                     init.order_sample_major = mode == 's' ? 1 : (mode == 'c' && init.order_ns % 32 == 0) ? 2 : 0;  // c: 32-sample chunks
                 }
             }
-            init.cursor = 0;
-            init.end = end - begin;
+            // the kernel divides inside a row of blocks in 32 bits; a row that large (16 K-wide image at 4096 spp) keeps index order
+            if ((long long)scene_.width * init.order_bh * init.order_ns >= (1LL << 31)) init.order_ns = 0;
+            else { init.cursor = 0; init.end = end - begin; }
         }
     }
     ctl_host_[8] = init;  // pinned staging slot: the upload is a true async copy on the renderer's stream
