@@ -10,6 +10,7 @@
 #include "dev_math.cuh"
 #include "rng.cuh"
 #include "shading.cuh"
+#include "path_index.cuh"
 #include "traverse.cuh"
 
 namespace btrc {
@@ -133,91 +134,17 @@ __device__ __forceinline__ GenOut<HALTON> generate_one(const SceneDevice &scene,
     return g;
 }
 
-// a / d and the remainder for a path index a: in 32-bit arithmetic when the whole index range of the render fits (`small`, uniform
-// over the grid), else one 64-bit division.  Quotient and remainder always fit 32 bits where this is used (the host checks, renderer.cpp).
-__device__ __forceinline__ uint32_t index_divmod(long long a, uint32_t d, bool small, uint32_t &rem) {
-    if (small) {
-        const uint32_t a32 = (uint32_t)a, q = a32 / d;
-        rem = a32 - q * d;
-        return q;
-    }
-    const long long q = a / (long long)d;
-    rem = (uint32_t)(a - q * (long long)d);
-    return (uint32_t)q;
-}
-
-// generate.cpp:39-86.  The kernel's own part is WHICH (pixel, sample) the i-th new path of the wave is: index order (uniform mode:
-// sample planes, generate.cpp:49-55; tile mode: pixel-major, :56-60), the strided / 2-D-tile partitions of a multi-GPU render and the
-// block-coherent order (types.h WaveCtl).  One division of the path index (64-bit only when the range needs it), the rest 32-bit.
+// generate.cpp:39-86.  The kernel's own part is WHICH (pixel, sample) the i-th new path of the wave is: path_index.cuh.
 template <bool HALTON>
 __global__ void __launch_bounds__(kBlock) generate_kernel(SceneDevice scene, RenderParams P, PathQueue q, FilmDevice film, const WaveCtl *ctl) {
     const int n_new = ctl->n_new;
     const int base_slot = ctl->n_survivors;
     const long long gen_base = ctl->gen_base;
-    const long long sblock = ctl->stride_block;
-    const uint32_t sparts = ctl->stride_parts, spart = ctl->stride_part, sbw = ctl->stride_bw, srows = ctl->stride_rows;
     const bool splat_weight = ctl->weight_prefilled == 0;
-    const uint32_t order_ns = ctl->order_ns, order_s0 = ctl->order_s0;
-    const int osm = ctl->order_sample_major;
-    const uint32_t obw = ctl->order_bw, obh = ctl->order_bh;
-    const uint32_t W = P.width, H = P.height, spp = P.spp;
-    const bool small = ctl->end <= 0xffffffffLL;                  // every index of this render fits 32 bits
-    const uint32_t tiles_x = sbw ? W / sbw : 1;
-    const uint32_t per_block_row = W * obh * order_ns;            // block-coherent order: paths of one row of blocks (< 2^31, renderer.cpp)
-    const uint32_t sblock32 = (uint32_t)sblock;                   // 2-D tiles: paths of a tile (< 2^31, renderer.cpp)
+    const PathIndexMap map = make_path_index_map(*ctl, P.width, P.height, P.spp, P.tile);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) {
-        long long accu = gen_base + i;
         uint32_t x, y, sample;
-        if (sblock > 0 && sbw > 0) {  // 2-D tiles of the tile-mode index space (types.h WaveCtl::stride_bw)
-            uint32_t within;
-            const uint32_t blk = index_divmod(accu, sblock32, small, within) * sparts + spart;
-            uint32_t pq;  // pixel ordinal inside the tile
-            if (spp % 32 == 0) {  // 32 samples of a pixel (one warp), then the next pixel of the tile, ... then the next 32 samples
-                const uint32_t per_chunk = sbw * srows * 32, chunk = within / per_chunk, rem = within - chunk * per_chunk;
-                pq = rem >> 5; sample = chunk * 32 + (rem & 31);
-            } else {
-                pq = within / spp; sample = within - pq * spp;
-            }
-            const uint32_t ty = blk / tiles_x, tx = blk - ty * tiles_x, qy = pq / sbw, qx = pq - qy * sbw;
-            x = tx * sbw + qx; y = ty * srows + qy;
-        } else if (order_ns > 0) {  // block-coherent order over whole sample planes (types.h WaveCtl::order_ns): virtual -> (pixel, sample)
-            uint32_t in_row;
-            const uint32_t br = index_divmod(accu, per_block_row, small, in_row);
-            const uint32_t hr = (br + 1) * obh <= H ? obh : H - br * obh;   // the last block row may be lower
-            uint32_t bc, within;  // block column, pixel ordinal inside the block (row-major)
-            if (!osm) {    // all samples of a pixel consecutively
-                const uint32_t pq = in_row / order_ns;
-                sample = order_s0 + (in_row - pq * order_ns);
-                bc = pq / (obw * hr);
-                within = pq - bc * obw * hr;
-            } else {
-                const uint32_t full = obw * hr * order_ns;                  // paths of a full-width block of this row
-                bc = in_row / full;
-                const uint32_t in_block = in_row - bc * full;
-                const uint32_t npb = ((bc + 1) * obw <= W ? obw : W - bc * obw) * hr;   // pixels of this block
-                if (osm == 2) {  // 32 samples of a pixel (one warp), then the next pixel, ... then the next 32 samples
-                    const uint32_t chunk = in_block / (npb * 32), rem = in_block - chunk * npb * 32;
-                    sample = order_s0 + chunk * 32 + (rem & 31);
-                    within = rem >> 5;
-                } else {         // sample plane by sample plane
-                    const uint32_t plane = in_block / npb;
-                    sample = order_s0 + plane;
-                    within = in_block - plane * npb;
-                }
-            }
-            const uint32_t wc = (bc + 1) * obw <= W ? obw : W - bc * obw;
-            const uint32_t qy = within / wc;
-            x = bc * obw + (within - qy * wc); y = br * obh + qy;
-        } else {
-            if (sblock > 0) accu = ((accu / sblock) * sparts + spart) * sblock + accu % sblock;  // strips of whole rows (WaveCtl::stride_block)
-            uint32_t pixel_index;
-            if (!P.tile) {   // generate.cpp:49-55
-                sample = index_divmod(accu, W * H, accu <= 0xffffffffLL, pixel_index);
-            } else {         // generate.cpp:56-60
-                pixel_index = index_divmod(accu, spp, accu <= 0xffffffffLL, sample);
-            }
-            y = pixel_index / W; x = pixel_index - y * W;
-        }
+        decode_path_index(map, gen_base + i, x, y, sample);
         GenOut<HALTON> g = generate_one<HALTON>(scene, P, (int)x, (int)y, (int)sample);
         const uint32_t pixel = g.py * (uint32_t)P.width + g.px;
         // generate.cpp:79: film.splat_atomic(pixel, weight, 1).  A render over a known index range fills the plane beforehand

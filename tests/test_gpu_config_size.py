@@ -316,3 +316,57 @@ def test_partitions_with_2d_tiles(tmp_path, built, spp):
             acc += rad; wacc += wgt
         assert np.array_equal(wacc, wfull) and np.abs(acc - full).max() <= tol
     s.close()
+
+
+def test_path_indices_beyond_32_bits(tmp_path, built):
+    """Renders with more than 2^32 camera paths (BASELINE config 5 on one GPU has 8.5e9): the generate kernel divides the path index
+    in 32 bits when the whole range fits and in 64 bits otherwise.  The film weights are closed-form (weight_fill_kernel), so the
+    witness of WHERE the kernel started its paths is the albedo plane: every camera path that hits adds its surface albedo to its
+    own pixel (shade.cpp:118-126), i.e. albedo sum / albedo of the pixel = number of paths generated there.
+    (a) index ranges that straddle 2^32 land in exactly the pixels the index space says (uniform: index = sample * W*H + pixel,
+    generate.cpp:49-55; tile: index = pixel * spp + sample, :56-60); (b) uniform mode: a whole render of 4.32e9 paths in the
+    block-coherent order generates every (pixel, sample) once."""
+    import torch
+
+    from btrc_b200 import api, scenes
+
+    W = H = 2048
+    spp = 1030
+    npix = W * H
+    assert npix * spp > 2 ** 32
+
+    def planes(s, begin, end):
+        s.film_clear()
+        st = s.render_range(begin, end)
+        rad = torch.zeros(H, W, 4, device="cuda"); wgt = torch.zeros(H, W, device="cuda"); alb = torch.zeros(H, W, 4, device="cuda")
+        s.film_export(rad, wgt, alb)
+        return wgt.cpu().numpy().reshape(-1), alb.cpu().numpy().reshape(-1, 4)[:, 0], st
+
+    scn = {}
+    for tile in (False, True):
+        path = scenes.make_cornell(str(tmp_path / ("t%d" % tile)), width=W, height=H, spp=spp, state_count=33554432, min_depth=1, max_depth=1, albedo=True, tile=tile)
+        scn[tile] = api.Scene(path)
+    _, alb0, _ = planes(scn[False], 0, npix)          # sample 0 of every pixel: the pixel's albedo (red channel)
+    flat = alb0 > 0.01                                # pixels that see a surface
+    assert flat.mean() > 0.9
+    begin, end = 2 ** 32 - 3 * npix - 70001, 2 ** 32 + 2 * npix + 50003
+    idx = np.arange(begin, end, dtype=np.int64)
+    for tile in (False, True):
+        pix = idx // spp if tile else idx % npix
+        expect = np.bincount(pix, minlength=npix).astype(np.float64)
+        wgt, alb, st = planes(scn[tile], begin, end)
+        assert st["n_gen"] == end - begin and np.array_equal(wgt, expect.astype(np.float32))
+        assert not alb[expect == 0].any()                                           # nothing started outside the range's pixels
+        on = flat & (expect > 0)
+        ratio = alb[on] / expect[on]
+        # a pixel's albedo is constant except across material edges (sub-pixel jitter): all but a few per cent agree to 1e-3
+        assert (np.abs(ratio - alb0[on]) <= 1e-3 * np.maximum(alb0[on], 0.05)).mean() > 0.97, tile
+        # and the total is the number of paths times the mean albedo: a path started in a wrong pixel of equal albedo would still show above
+        assert abs(alb[on].sum() / (expect[on] * alb0[on]).sum() - 1) < 2e-3
+    wgt, alb, st = planes(scn[False], 0, npix * spp)
+    assert st["n_gen"] == npix * spp and (wgt == spp).all()
+    ratio = alb[flat] / spp
+    assert (np.abs(ratio - alb0[flat]) <= 2e-3 * np.maximum(alb0[flat], 0.05)).mean() > 0.97
+    assert abs(alb[flat].sum() / (spp * alb0[flat].sum()) - 1) < 2e-3
+    for s in scn.values():
+        s.close()
