@@ -276,19 +276,30 @@ struct FilmDevice {
 };
 
 // Device-resident wave control block: lets the host enqueue whole iterations without reading anything back.
+// BTRC_CTL_LINE: the counters that every warp of a persistent kernel hits with an atomic per 32-entry batch (work cursors, output
+// counters, class counts) each start their own 128-byte line, so that the L2 serves them from different lines (and slices) instead
+// of queueing every atomic of a kernel -- and every warp's read of n_active -- on ONE line.
+#ifndef BTRC_CTL_PAD
+#define BTRC_CTL_PAD 0
+#endif
+#if BTRC_CTL_PAD
+#define BTRC_CTL_LINE alignas(128)
+#else
+#define BTRC_CTL_LINE
+#endif
 struct WaveCtl {
     int n_active;       // states processed by trace/shade this iteration
     int n_survivors;    // states carried over from the previous iteration (slots [0, n_survivors))
-    // the two output counters share one aligned 64-bit word: a warp reserves its slots in both queues with ONE atomic
-    int n_next;         // shade's output counter (reference: StateCounters::active_state_counter)         -- low half
-    int n_shadow;       // shade's shadow-ray counter (reference: StateCounters::shadow_ray_counter)       -- high half
     int n_new;          // camera paths generated this iteration (slots [n_survivors, n_active))
     int n_shadow_cur;   // shadow rays to trace this iteration
-    int trace_cursor;   // dynamic work cursors for the persistent traversal kernels
-    int shadow_cursor;
-    int class_count[8]; // entries of each shade class list this iteration (kNumShadeClasses <= 8)
-    int class_cursor[8]; // dynamic work cursors of the shade kernels (one 32-entry batch per grab)
-    long long gen_base;   // first camera-path index generated this iteration
+    // the two output counters share one aligned 64-bit word: a warp reserves its slots in both queues with ONE atomic
+    BTRC_CTL_LINE alignas(8) int n_next;  // shade's output counter (reference: StateCounters::active_state_counter)  -- low half
+    int n_shadow;       // shade's shadow-ray counter (reference: StateCounters::shadow_ray_counter)       -- high half
+    BTRC_CTL_LINE int trace_cursor;   // dynamic work cursors for the persistent traversal kernels
+    BTRC_CTL_LINE int shadow_cursor;
+    BTRC_CTL_LINE int class_count[8]; // entries of each shade class list this iteration (kNumShadeClasses <= 8)
+    BTRC_CTL_LINE int class_cursor[8]; // dynamic work cursors of the shade kernels (one 32-entry batch per grab)
+    BTRC_CTL_LINE long long gen_base;   // first camera-path index generated this iteration
     long long cursor;     // next camera-path index
     long long end;        // one past the last camera-path index of this render
     int pool;             // state_count

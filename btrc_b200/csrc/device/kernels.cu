@@ -36,6 +36,30 @@ __device__ __forceinline__ HitRec traverse_warp(const BvhDevice &bvh, float4 o4,
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// Hand-out of 32-entry batches to the warps of a persistent kernel.  BTRC_STATIC_SHARE (percent, default 0 = all dynamic): the first
+// share of the batches is dealt statically (warp w of T takes batches w, w + T, ...: no atomic, neighbouring batches still run on
+// neighbouring warps at the same time), the rest through the atomic cursor, which keeps the tail balanced.
+#ifndef BTRC_STATIC_SHARE
+#define BTRC_STATIC_SHARE 0
+#endif
+struct BatchCursor {
+    int round, static_rounds, total_warps, warp_gid;
+    __device__ __forceinline__ void init(int n) {
+        total_warps = gridDim.x * (blockDim.x >> 5);
+        warp_gid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const int n_batches = (n + 31) >> 5;
+        static_rounds = BTRC_STATIC_SHARE ? int((long long)n_batches * BTRC_STATIC_SHARE / 100 / total_warps) : 0;
+        round = 0;
+    }
+    // first entry of this warp's next batch, or a value >= n when the work is gone
+    __device__ __forceinline__ int next(int *cursor) {
+        if (BTRC_STATIC_SHARE && round < static_rounds) return (round++ * total_warps + warp_gid) * 32;
+        int base = 0;
+        if (lane_id() == 0) base = atomicAdd(cursor, 32);
+        return __shfl_sync(0xffffffffu, base, 0) + (BTRC_STATIC_SHARE ? static_rounds * total_warps * 32 : 0);
+    }
+};
+
 // Warp-aggregated slot allocation: returns this lane's slot (valid only where pred is true).
 __device__ __forceinline__ int warp_alloc(int *counter, bool pred) {
     const unsigned m = __ballot_sync(kFull, pred);
@@ -311,13 +335,11 @@ __global__ void __launch_bounds__(kBlock, trace_min_blocks<TRAV>()) trace_kernel
     const int n_sorted = SORTED ? ctl->n_sorted : 0;
     const bool append = !SORTED || ctl->sort_enabled != 2;
     unsigned long long hits = 0;
-    int next_base = 0;
-    if (BTRC_CURSOR_AHEAD && lane_id() == 0) next_base = atomicAdd(&ctl->trace_cursor, 32);
+    BatchCursor bc;
+    bc.init(n);
     for (;;) {
-        if (!BTRC_CURSOR_AHEAD && lane_id() == 0) next_base = atomicAdd(&ctl->trace_cursor, 32);
-        const int base = __shfl_sync(kFull, next_base, 0);
+        const int base = bc.next(&ctl->trace_cursor);
         if (base >= n) break;
-        if (BTRC_CURSOR_AHEAD && lane_id() == 0) next_base = atomicAdd(&ctl->trace_cursor, 32);
         const int j = base + lane_id();
         const bool valid = j < n;
         const int i = (SORTED && valid && j < n_sorted) ? (int)rs.order[j] : j;  // survivors bin by bin, new camera paths in pixel order
@@ -755,13 +777,11 @@ __global__ void __launch_bounds__(kBlock, trace_min_blocks<TRAV>()) shadow_kerne
     const int n = ctl->n_shadow;
     const int n_sorted = SORTED ? ctl->n_shadow_sorted : 0;
     unsigned long long misses = 0;
-    int next_base = 0;
-    if (BTRC_CURSOR_AHEAD && lane_id() == 0) next_base = atomicAdd(&ctl->shadow_cursor, 32);
+    BatchCursor bc;
+    bc.init(n);
     for (;;) {
-        if (!BTRC_CURSOR_AHEAD && lane_id() == 0) next_base = atomicAdd(&ctl->shadow_cursor, 32);
-        const int base = __shfl_sync(kFull, next_base, 0);
+        const int base = bc.next(&ctl->shadow_cursor);
         if (base >= n) break;
-        if (BTRC_CURSOR_AHEAD && lane_id() == 0) next_base = atomicAdd(&ctl->shadow_cursor, 32);
         const int j = base + lane_id();
         const bool valid = j < n;
         const int i = (SORTED && valid && j < n_sorted) ? (int)rs.order[j] : j;
