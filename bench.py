@@ -590,8 +590,9 @@ def measure(args, D, workload, steps, warmup, spp_override=0, e2e=True, cpu=True
         "cpu_baseline": cpu_line,
     }
     if e2e_s is not None:
-        line["e2e"] = {"value": n_gen / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 208,
-                       "d2h_bytes_per_step": int(npix * 16 + 208 * (n_iter / steps / world)),
+        ctl_bytes = api.wave_ctl_bytes()
+        line["e2e"] = {"value": n_gen / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": ctl_bytes,
+                       "d2h_bytes_per_step": int(npix * 16 + ctl_bytes * (n_iter / steps / world)),
                        "note": "api.Scene.render() into pinned host memory: film clear, waves, resolve, D2H of the W*H float4 image; the scene (BVH, tables) stays "
                                "resident like model weights; H2D per step is the wave control block"}
     if world > 1:

@@ -89,6 +89,7 @@ def lib():
         L.btrc_scene_file_parse.argtypes = [c_char_p, c_char_p, c_int32, c_void_p, POINTER(c_int32)]
         L.btrc_device_sm_count.restype = c_int
         L.btrc_device_count.restype = c_int
+        L.btrc_wave_ctl_bytes.restype = c_int
         L.btrc_set_device.argtypes = [c_int32]
         L.btrc_render_part.argtypes = [c_void_p, c_int32, c_int32, c_int32, POINTER(RenderStats)]
         L.btrc_nccl_unique_id.argtypes = [c_void_p]
@@ -382,6 +383,11 @@ class Comm:
         if self.h:
             lib().btrc_comm_destroy(self.h)
             self.h = c_void_p()
+
+
+def wave_ctl_bytes():
+    """Bytes of the device-resident wave control block (uploaded once per render, read back per progress snapshot)."""
+    return int(lib().btrc_wave_ctl_bytes())
 
 
 def set_device(index):

@@ -157,6 +157,8 @@ int btrc_device_sm_count(void) {
     return n;
 }
 
+int btrc_wave_ctl_bytes(void) { return (int)sizeof(btrc::WaveCtl); }
+
 int btrc_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -279,8 +279,9 @@ struct FilmDevice {
 // BTRC_CTL_LINE: the counters that every warp of a persistent kernel hits with an atomic per 32-entry batch (work cursors, output
 // counters, class counts) each start their own 128-byte line, so that the L2 serves them from different lines (and slices) instead
 // of queueing every atomic of a kernel -- and every warp's read of n_active -- on ONE line.
+// Measured (profiles/r2ab_ab_ctl_lines.md): C2 +1.3 %, C3 +1.5 %, C4 +-0; closest-hit kernel -3.4 % / -5 %.
 #ifndef BTRC_CTL_PAD
-#define BTRC_CTL_PAD 0
+#define BTRC_CTL_PAD 1
 #endif
 #if BTRC_CTL_PAD
 #define BTRC_CTL_LINE alignas(128)
@@ -297,7 +298,8 @@ struct WaveCtl {
     int n_shadow;       // shade's shadow-ray counter (reference: StateCounters::shadow_ray_counter)       -- high half
     BTRC_CTL_LINE int trace_cursor;   // dynamic work cursors for the persistent traversal kernels
     BTRC_CTL_LINE int shadow_cursor;
-    BTRC_CTL_LINE int class_count[8]; // entries of each shade class list this iteration (kNumShadeClasses <= 8)
+    BTRC_CTL_LINE int class_count[8]; // entries of each shade class list this iteration (kNumShadeClasses <= 8); one line per list measured no
+                                      // different from one line for all eight (profiles/r2ab_ab_ctl_lines.md)
     BTRC_CTL_LINE int class_cursor[8]; // dynamic work cursors of the shade kernels (one 32-entry batch per grab)
     BTRC_CTL_LINE long long gen_base;   // first camera-path index generated this iteration
     long long cursor;     // next camera-path index

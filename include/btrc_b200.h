@@ -193,6 +193,7 @@ void *btrc_stream(btrc_scene_t *scene);
  * before the scene is loaded). */
 int btrc_device_sm_count(void);
 int btrc_device_count(void);
+int btrc_wave_ctl_bytes(void);   /* size of the wave control block: the only per-render upload, and what comes back per progress snapshot */
 int btrc_set_device(int32_t device);
 const char *btrc_version(void);
 
