@@ -612,6 +612,9 @@ __global__ void __launch_bounds__(kBlock) shade_miss_kernel(SceneDevice scene, P
 #ifndef BTRC_SHADE_BLOCKS_HEAVY
 #define BTRC_SHADE_BLOCKS_HEAVY 2
 #endif
+#ifndef BTRC_SHADE_BLOCKS_LIGHT
+#define BTRC_SHADE_BLOCKS_LIGHT 3
+#endif
 #ifndef BTRC_SHADE_CTA_SYNC
 #define BTRC_SHADE_CTA_SYNC 0
 #endif
@@ -621,7 +624,7 @@ __global__ void __launch_bounds__(kBlock) shade_miss_kernel(SceneDevice scene, P
 template <int MAT> constexpr bool shade_is_heavy() { return MAT == MAT_DISNEY || MAT == MAT_METAL; }
 template <int MAT> constexpr int shade_block() { return shade_is_heavy<MAT>() ? BTRC_SHADE_BLOCK_HEAVY : kBlock; }
 template <int MAT, bool HALTON>
-__global__ void __launch_bounds__(shade_block<MAT>(), shade_is_heavy<MAT>() ? BTRC_SHADE_BLOCKS_HEAVY : 3)
+__global__ void __launch_bounds__(shade_block<MAT>(), shade_is_heavy<MAT>() ? BTRC_SHADE_BLOCKS_HEAVY : BTRC_SHADE_BLOCKS_LIGHT)
 shade_kernel(SceneDevice scene, RenderParams P, PathQueue q, HitQueue hq, PathQueue nq, ShadowQueue sq, FilmDevice film, WaveCtl *ctl) {
     const int n = ctl->class_count[1 + MAT];
     const uint32_t *list = hq.class_list + (size_t)(1 + MAT) * hq.class_stride;
