@@ -162,6 +162,8 @@ void Renderer::render_range(long long begin, long long end, long long stride_blo
     if (stride_bw > 0 && (stride_rows <= 0 || scene_.width % stride_bw || scene_.height % stride_rows || stride_block >= (1LL << 31) ||
                           stride_block != (long long)stride_bw * stride_rows * scene_.renderer.spp))
         throw Error("render_range: 2-D tiles must divide the image");
+    // inside a tile the paths are walked warp by warp (path_index.cuh), so only whole tiles have a closed-form weight per pixel
+    if (stride_bw > 0 && (begin % stride_block != 0 || end % stride_block != 0)) throw Error("render_range: a 2-D tile partition renders whole tiles");
     if (stride_block < 0 || stride_parts < 1 || stride_part < 0 || stride_part >= stride_parts) throw Error("render_range: bad stride");
     if (stride_block > 0 && (!scene_.renderer.tile || stride_block % scene_.renderer.spp != 0))
         throw Error("render_range: a strided partition needs tile-mode indexing and whole pixels per block");
