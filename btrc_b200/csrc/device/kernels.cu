@@ -60,22 +60,6 @@ struct BatchCursor {
     }
 };
 
-// Warp-aggregated slot allocation: returns this lane's slot (valid only where pred is true).
-__device__ __forceinline__ int warp_alloc(int *counter, bool pred) {
-    const unsigned m = __ballot_sync(kFull, pred);
-    if (m == 0) return -1;
-    int base = 0;
-    const int leader = __ffs(m) - 1;
-    if (lane_id() == leader) base = atomicAdd(counter, __popc(m));
-    base = __shfl_sync(kFull, base, leader);
-    return base + __popc(m & ((1u << lane_id()) - 1u));
-}
-
-__device__ __forceinline__ void warp_count(unsigned long long *counter, bool pred) {
-    const unsigned m = __ballot_sync(kFull, pred);
-    if (m && lane_id() == __ffs(m) - 1) atomicAdd(counter, (unsigned long long)__popc(m));
-}
-
 // core/film.cpp:131-165: bounds are guaranteed by construction, the isfinite test is kept
 __device__ __forceinline__ void film_splat3(float *buf, uint32_t pixel, f3 v) {
     if (isfinite3(v)) {
