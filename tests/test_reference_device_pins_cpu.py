@@ -185,17 +185,16 @@ def test_generate_matches_reference(pair):
         _assert_bits(so[k], sr[k], "%s generate.%s" % (kind, k))
 
 
-def test_stages_match_reference_bit_for_bit(pair):
-    """Closest hit, medium and shade over three bounces: oracle == reference's own device code, bit for bit."""
-    kind, O, R = pair
-    n = R.width * R.height * 2
-    st = O.generate(0, n)
-    seen = np.zeros(16, np.int64)
+def _stages_of_batch(kind, O, R, first, n, seen, label):
+    """generate [first, first + n) and follow it for three bounces of closest hit, [medium,] shade; returns the states compared."""
+    st = O.generate(first, n)
+    total = 0
     for bounce in range(3):
-        what = "%s bounce %d" % (kind, bounce)
+        what = "%s %s bounce %d" % (kind, label, bounce)
         fo, do = O.closest_hit(st["o_med"], st["d_t1"])
         fr, dr = R.closest_hit(st["o_med"], st["d_t1"])
         assert np.array_equal(fo, fr) and np.array_equal(do, dr), what + " closest hit"
+        total += st["o_med"].shape[0]
         mo = None
         if R.has_medium():
             so2, fo2, mo = O.medium(st, fo, do)
@@ -220,7 +219,25 @@ def test_stages_match_reference_bit_for_bit(pair):
             parts.append({k: v[km] for k, v in mo["next"].items()})
         st = {k: np.ascontiguousarray(np.concatenate([p[k] for p in parts])) for k in parts[0]}
         assert st["o_med"].shape[0] > (100 if bounce == 0 else 16), what + ": too few surviving paths to mean anything"
-    assert seen[1:].sum() > n, "stages exercised"
+    return total
+
+
+def test_stages_match_reference_bit_for_bit(pair):
+    """Closest hit, medium and shade over three bounces: oracle == reference's own device code, bit for bit -- on at least 250,000
+    states per scene type (batch after batch of camera paths, sample indices running past the scene's spp: the sampler does not care;
+    the tile-mode scene stops at its own spp)."""
+    kind, O, R = pair
+    batch = R.width * R.height * 2
+    seen = np.zeros(16, np.int64)
+    total, first, k = 0, 0, 0
+    # "extras" renders in tile mode (index = pixel * spp + sample): indices past W * H * spp name no pixel, so it stops at its 4 spp
+    limit = R.width * R.height * 4 if kind == "extras" else None
+    while total < 250000 and (limit is None or first + batch <= limit):
+        total += _stages_of_batch(kind, O, R, first, batch, seen, "batch %d" % k)
+        first += batch
+        k += 1
+    assert total >= (250000 if limit is None else 20000)
+    assert seen[1:].sum() > batch, "stages exercised"
 
 
 def test_shadow_stage_matches_reference(pair):
