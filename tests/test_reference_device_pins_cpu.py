@@ -55,6 +55,8 @@ def _make(kind, d):
         return scenes.make_ibl_scene(d, width=96, height=54, spp=4, rings=10, segments=14, env_res=(128, 64), lut=(32, 16), state_count=40000)
     if kind == "volumes":    # two overlapping volume primitives
         return scenes.make_volume_scene(d, width=64, height=48, spp=4, grid_res=16, state_count=40000)
+    if kind == "instanced":  # BASELINE config 4 in small: one mesh under 10 rigid transforms + scales, diffuse / metal, 6 quad lights, depth 16
+        return scenes.make_instanced_scene(d, width=96, height=54, spp=4, rings=13, segments=24, n_instances=10, n_lights=6, state_count=60000)
     if kind == "extras":
         return _make_extras(d)
     if kind == "medium_bytes":
@@ -129,7 +131,7 @@ def _make_extras(d):
     return path
 
 
-KINDS = ["cornell", "materials", "medium", "homogeneous", "ibl", "volumes", "extras", "medium_bytes"]
+KINDS = ["cornell", "materials", "medium", "homogeneous", "ibl", "volumes", "extras", "medium_bytes", "instanced"]
 
 
 @pytest.fixture(scope="module", params=KINDS)
