@@ -56,6 +56,9 @@ def lib():
         L.orc_add_material.argtypes = [c_void_p, c_int, POINTER(c_int32), c_int, c_int]
         L.orc_add_image.argtypes = [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_float), c_int, c_int, c_int, c_int, c_int, POINTER(c_float)]
         L.orc_add_texture_array.argtypes = [c_void_p, c_int]
+        L.orc_set_image_border_levels.argtypes = [c_void_p, c_int, c_int]
+        L.orc_set_image_minmax.argtypes = [c_void_p, c_int, POINTER(c_float), POINTER(c_float)]
+        L.orc_render_pixels.argtypes = [c_void_p, c_int, POINTER(c_uint32), c_int, c_int, POINTER(c_float), POINTER(c_uint64)]
         L.orc_add_texture_binary.argtypes = [c_void_p, c_int, c_int, c_int]
         L.orc_add_texture_transform.argtypes = [c_void_p, c_int, POINTER(c_float)]
         L.orc_eval_texture2d.argtypes = [c_void_p, c_int, c_int, POINTER(c_float), POINTER(c_float)]
